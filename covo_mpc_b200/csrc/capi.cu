@@ -1,0 +1,935 @@
+// C-ABI (include/covo_b200.h): handle, device workspace and the per-mode step schedules.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/covo_b200.h"
+#include "common.cuh"
+#include "hessian.cuh"
+#include "offline.cuh"
+#include "rng.cuh"
+#include "sigma.cuh"
+
+using namespace covo;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) return fail(COVO_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        n = count;
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T));
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+__global__ void shift_blocks_kernel(float* Lblk, float* cov, int H) {
+    // a_cov <- concat(a_cov[1:], a_cov[-1:])  (controllers/mppi.py:46-49), same for its factor
+    const int env = blockIdx.x;
+    float* L = Lblk + (long long)env * H * 16;
+    float* C = cov + (long long)env * H * 16;
+    extern __shared__ float sh[];
+    for (int i = threadIdx.x; i < H * 16; i += blockDim.x) {
+        sh[i] = L[i];
+        sh[H * 16 + i] = C[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H * 16; i += blockDim.x) {
+        int h = i >> 4, r = i & 15;
+        int hs = min(h + 1, H - 1);
+        L[i] = sh[hs * 16 + r];
+        C[i] = sh[H * 16 + hs * 16 + r];
+    }
+}
+
+__global__ void debug_eps_kernel(float* out, int n_local, int offset, int n, unsigned long long seed, unsigned int stream) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int blocks4 = n >> 2;
+    if (idx >= n_local * blocks4) return;
+    int s = idx / blocks4, b = idx % blocks4;
+    float z[4];
+    philox_normal4(seed, stream, (uint32_t)(offset + s), (uint32_t)b, z);
+    for (int j = 0; j < 4; ++j) out[(long long)s * n + 4 * b + j] = z[j];
+}
+
+}  // namespace
+
+struct covo_handle {
+    covo_config cfg;
+    EnvConsts env;
+    int H, n, n_pad, E, T;
+    int n_local, sample_offset, n_cta, rec;
+    size_t lt_floats;
+    cudaStream_t own_stream = nullptr;
+    unsigned int rng_stream = 0;
+    bool pos_stats_on = false;
+    bool profiling = false;
+    bool have_factor = false;
+    int t_sched = 0;
+    cudaEvent_t ev[8] = {};
+    float kernel_ms[6] = {0, 0, 0, 0, 0, 0};
+    // inputs
+    DevBuf<float> state24, pos_traj, vel_traj, acc_traj, a_mean, eps, fdist;
+    DevBuf<int> time;
+    // covariance pipeline
+    DevBuf<float> R, Vh, tau, F, Z, cov, Lfull, Lt, Lblk, hess_ws;
+    DevBuf<double> diag, zolo;
+    DevBuf<int> status;
+    // offline schedule (batched over schedule steps)
+    DevBuf<float> cov_table, Lt_table, sched_states, sched_anom, sched_R, sched_Vh, sched_tau, sched_F, sched_Z, sched_ws;
+    DevBuf<double> sched_diag;
+    DevBuf<int> sched_times, sched_status;
+    // rollout
+    DevBuf<float> partials, rank_partial, action, costs, samples, pos_stats, gathered_scratch;
+    DevBuf<unsigned int> counters;
+    // pinned staging
+    float* h_state = nullptr;
+    int* h_time = nullptr;
+    float* h_action = nullptr;
+};
+
+namespace {
+
+void release_all(covo_handle* h) {
+    h->state24.release(); h->pos_traj.release(); h->vel_traj.release(); h->acc_traj.release();
+    h->a_mean.release(); h->eps.release(); h->fdist.release(); h->time.release();
+    h->R.release(); h->Vh.release(); h->tau.release(); h->F.release(); h->Z.release(); h->cov.release();
+    h->Lfull.release(); h->Lt.release(); h->Lblk.release(); h->hess_ws.release(); h->diag.release();
+    h->zolo.release(); h->status.release();
+    h->cov_table.release(); h->Lt_table.release(); h->sched_states.release(); h->sched_anom.release();
+    h->sched_R.release(); h->sched_Vh.release(); h->sched_tau.release(); h->sched_F.release(); h->sched_Z.release();
+    h->sched_ws.release(); h->sched_diag.release(); h->sched_times.release(); h->sched_status.release();
+    h->partials.release(); h->rank_partial.release(); h->action.release(); h->costs.release();
+    h->samples.release(); h->pos_stats.release(); h->gathered_scratch.release(); h->counters.release();
+    if (h->h_state) cudaFreeHost(h->h_state);
+    if (h->h_time) cudaFreeHost(h->h_time);
+    if (h->h_action) cudaFreeHost(h->h_action);
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+}
+
+HessianArgs hess_args(covo_handle* h, const float* st, const int* tm, const float* a_mean, int shift, float* R, float* ws,
+                      long long traj_stride) {
+    HessianArgs a;
+    a.H = h->H;
+    a.traj_len = h->T;
+    a.shift = shift;
+    a.traj_stride = traj_stride;
+    a.env = h->env;
+    a.state24 = st;
+    a.time = tm;
+    a.pos_traj = h->pos_traj.p;
+    a.vel_traj = h->vel_traj.p;
+    a.a_mean = a_mean;
+    a.workspace = ws;
+    a.R = R;
+    return a;
+}
+
+SigmaArgs sigma_args(covo_handle* h) {
+    SigmaArgs a;
+    a.n = h->n;
+    a.n_pad = h->n_pad;
+    a.sample_sigma = h->cfg.sample_sigma;
+    a.R = h->R.p;
+    a.Vh = h->Vh.p;
+    a.tau = h->tau.p;
+    a.F = h->F.p;
+    a.Z = h->Z.p;
+    a.cov = h->cov.p;
+    a.L = h->Lfull.p;
+    a.Lt = h->Lt.p;
+    a.diag = h->diag.p;
+    a.zolo = h->zolo.p;
+    a.status = h->status.p;
+    a.lt_stride = (long long)h->lt_floats;
+    return a;
+}
+
+RolloutArgs rollout_args(covo_handle* h, const float* st, const int* tm, const float* a_in, int shift, const float* eps,
+                         const float* fdist, float* a_out, float* act, float* costs, float* samples, int finalize) {
+    RolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_samples = h->n_local;
+    a.sample_offset = h->sample_offset;
+    a.H = h->H;
+    a.n = h->n;
+    a.n_pad = h->n_pad;
+    a.mode = (h->cfg.mode == COVO_MODE_MPPI) ? 1 : 0;
+    a.shift = shift;
+    a.finalize = finalize;
+    a.traj_len = h->T;
+    a.traj_stride = (long long)h->T * 3;
+    a.lam = h->cfg.lam;
+    a.gamma_mean = h->cfg.gamma_mean;
+    a.discount = h->cfg.discount;
+    a.env = h->env;
+    a.seed = h->cfg.seed;
+    a.stream = h->rng_stream;
+    a.state24 = st;
+    a.time = tm;
+    a.pos_traj = h->pos_traj.p;
+    a.vel_traj = h->vel_traj.p;
+    a.a_mean_in = a_in;
+    a.eps = eps;
+    a.fdist_seq = fdist;
+    a.partials = h->partials.p;
+    a.counters = h->counters.p;
+    a.rank_partial = h->rank_partial.p;
+    a.a_mean_out = a_out;
+    a.action_out = act;
+    a.costs_out = costs;
+    a.samples_out = samples;
+    a.pos_stats = h->pos_stats_on ? h->pos_stats.p : nullptr;
+    if (a.mode == 1) {
+        a.Lfac = h->Lblk.p;
+        a.lfac_stride = (long long)h->H * 16;
+    } else if (h->cfg.mode == COVO_MODE_COVO_OFFLINE && h->t_sched > 0) {
+        a.Lfac = h->Lt_table.p;
+        a.lfac_stride = 0;
+        a.lfac_time_stride = (long long)h->lt_floats;
+        a.lfac_time_max = h->t_sched - 1;
+    } else {
+        a.Lfac = h->Lt.p;
+        a.lfac_stride = (long long)h->lt_floats;
+    }
+    return a;
+}
+
+struct Prof {
+    covo_handle* h;
+    cudaStream_t st;
+    int slot = 0;
+    Prof(covo_handle* h_, cudaStream_t s) : h(h_), st(s) {
+        if (h->profiling) cudaEventRecord(h->ev[0], st);
+    }
+    void mark(int idx) {  // idx-th boundary (1..7)
+        if (h->profiling) cudaEventRecord(h->ev[idx], st);
+    }
+};
+
+// covariance step for the online mode: R (already in h->R) -> cov -> factor
+int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf) {
+    SigmaArgs sa = sigma_args(h);
+    // sigma: tridiag+rational, then the two apply-Q passes; mark after the tridiag kernel is not possible
+    // without splitting launch_sigma, so the pipeline is timed as [tridiag][applyQ x2] via two events inside.
+    CK(launch_sigma(sa, h->E, st));
+    if (pf) pf->mark(4);
+    CK(launch_cholesky(sa, h->E, st));
+    if (pf) pf->mark(5);
+    h->have_factor = true;
+    return COVO_OK;
+}
+
+int step_common(covo_handle* h, const float* st_d, const int* tm_d, const float* eps_d, float* act_d, cudaStream_t st,
+                int finalize) {
+    Prof pf(h, st);
+    const int mode = h->cfg.mode;
+    if (h->pos_stats_on) CK(cudaMemsetAsync(h->pos_stats.p, 0, h->pos_stats.n * sizeof(float), st));
+    if (mode == COVO_MODE_MPPI) {
+        shift_blocks_kernel<<<h->E, 128, 2 * h->H * 16 * sizeof(float), st>>>(h->Lblk.p, h->cov.p, h->H);
+        CK(cudaGetLastError());
+        for (int i = 1; i <= 5; ++i) pf.mark(i);
+    } else if (mode == COVO_MODE_COVO_ONLINE) {
+        HessianArgs ha = hess_args(h, st_d, tm_d, h->a_mean.p, 1, h->R.p, h->hess_ws.p, (long long)h->T * 3);
+        CK(launch_hessian(ha, h->E, st));
+        pf.mark(1);
+        pf.mark(2);
+        pf.mark(3);
+        int rc = run_sigma_chol(h, st, &pf);
+        if (rc) return rc;
+    } else {
+        if (h->t_sched <= 0) return fail(COVO_ERR_INVALID, "covo-offline: no schedule; call covo_reset_offline or covo_set_cov_offline first");
+        for (int i = 1; i <= 5; ++i) pf.mark(i);
+    }
+    RolloutArgs ra = rollout_args(h, st_d, tm_d, h->a_mean.p, 1, eps_d, nullptr, h->a_mean.p, act_d, nullptr, nullptr, finalize);
+    CK(launch_rollout(ra, h->E, st));
+    pf.mark(6);
+    if (!eps_d) h->rng_stream += 1;
+    return COVO_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* covo_last_error(void) { return g_err.c_str(); }
+const char* covo_version(void) { return "covo_b200 0.1 (sm_100a)"; }
+
+int covo_default_config(covo_config* c) {
+    if (!c) return fail(COVO_ERR_INVALID, "null config");
+    memset(c, 0, sizeof(*c));
+    c->mode = COVO_MODE_COVO_ONLINE;
+    c->n_samples = 8192;  // envs/quadrotor.py:673-676
+    c->horizon = 32;
+    c->n_env = 1;
+    c->traj_len = 300;
+    c->device = 0;
+    c->rank = 0;
+    c->world = 1;
+    c->lam = 0.01f;
+    c->sample_sigma = 0.5f;
+    c->gamma_mean = 1.0f;
+    c->gamma_sigma = 0.0f;
+    c->discount = 1.0f;
+    c->m = 0.027f;  // dynamics/dataclass.py:43-49, 71, 76, 81
+    c->g = 9.81f;
+    c->max_thrust = 0.8f;
+    c->dt = 0.02f;
+    c->alpha_bodyrate = 0.5f;
+    c->action_scale = 1.0f;
+    c->pos_limit = 3.0f;
+    c->max_omega[0] = 10.f;
+    c->max_omega[1] = 10.f;
+    c->max_omega[2] = 3.f;
+    c->max_steps_in_episode = 300;
+    c->seed = 0;
+    return COVO_OK;
+}
+
+int covo_create(const covo_config* cfg, covo_handle** out) {
+    if (!cfg || !out) return fail(COVO_ERR_INVALID, "null argument");
+    if (cfg->mode < 0 || cfg->mode > 2) return fail(COVO_ERR_NOT_IMPLEMENTED, "unknown mode %d", cfg->mode);
+    if (cfg->horizon < 2 || cfg->horizon > kMaxH) return fail(COVO_ERR_INVALID, "horizon must be in [2, %d]", kMaxH);
+    if (cfg->mode != COVO_MODE_MPPI && 4 * cfg->horizon > kSigmaMaxN)
+        return fail(COVO_ERR_INVALID, "CoVO modes support 4*H <= %d (H <= %d)", kSigmaMaxN, kSigmaMaxN / 4);
+    if (cfg->n_samples < 1 || cfg->n_env < 1 || cfg->traj_len < 1) return fail(COVO_ERR_INVALID, "sizes must be positive");
+    if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(COVO_ERR_INVALID, "bad rank/world");
+    if (cfg->n_samples % cfg->world) return fail(COVO_ERR_INVALID, "n_samples must divide evenly across world");
+    if (cfg->gamma_sigma != 0.f) return fail(COVO_ERR_NOT_IMPLEMENTED, "gamma_sigma != 0 (MPPI covariance update) is not implemented");
+    if (cfg->mode == COVO_MODE_COVO_OFFLINE && cfg->n_env != 1)
+        return fail(COVO_ERR_NOT_IMPLEMENTED, "covo-offline supports n_env == 1");
+    if (!(cfg->lam > 0.f)) return fail(COVO_ERR_INVALID, "lam must be positive");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(COVO_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(ce));
+    CK(cudaSetDevice(cfg->device));
+    covo_handle* h = new covo_handle();
+    h->cfg = *cfg;
+    h->env.m = cfg->m;
+    h->env.g = cfg->g;
+    h->env.max_thrust = cfg->max_thrust;
+    h->env.dt = cfg->dt;
+    h->env.alpha_bodyrate = cfg->alpha_bodyrate;
+    h->env.action_scale = cfg->action_scale;
+    h->env.pos_limit = cfg->pos_limit;
+    for (int k = 0; k < 3; ++k) h->env.max_omega[k] = cfg->max_omega[k];
+    h->env.max_steps = cfg->max_steps_in_episode;
+    h->H = cfg->horizon;
+    h->n = 4 * h->H;
+    h->n_pad = round_up8(h->n);
+    h->E = cfg->n_env;
+    h->T = cfg->traj_len;
+    h->n_local = cfg->n_samples / cfg->world;
+    h->sample_offset = cfg->rank * h->n_local;
+    h->n_cta = (h->n_local + kTileSamples - 1) / kTileSamples;
+    h->rec = kPartialHdr + h->n_pad;
+    h->lt_floats = (size_t)lt_size(h->n, h->n_pad);
+    const size_t E = h->E, n = h->n, nn = n * n;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    A(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    for (auto& ev : h->ev) A(cudaEventCreate(&ev));
+    A(h->state24.alloc(E * kStateFloats));
+    A(h->time.alloc(E));
+    A(h->pos_traj.alloc(E * h->T * 3));
+    A(h->vel_traj.alloc(E * h->T * 3));
+    A(h->acc_traj.alloc(E * h->T * 3));
+    A(h->a_mean.alloc(E * n));
+    A(h->partials.alloc(E * h->n_cta * h->rec));
+    A(h->rank_partial.alloc(E * h->rec));
+    A(h->counters.alloc(E));
+    A(h->action.alloc(E * 4));
+    A(h->pos_stats.alloc(E * h->H * 6));
+    A(h->status.alloc(E));
+    if (cfg->mode == COVO_MODE_MPPI) {
+        A(h->Lblk.alloc(E * h->H * 16));
+        A(h->cov.alloc(E * h->H * 16));
+    } else {
+        A(h->R.alloc(E * nn));
+        A(h->Vh.alloc(E * nn));
+        A(h->tau.alloc(E * n));
+        A(h->F.alloc(E * nn));
+        A(h->Z.alloc(E * nn));
+        A(h->cov.alloc(E * nn));
+        A(h->Lfull.alloc(E * nn));
+        A(h->Lt.alloc(E * h->lt_floats));
+        A(h->diag.alloc(E * 4 * n));
+        A(h->hess_ws.alloc(E * hessian_workspace_floats(h->H)));
+        A(h->zolo.alloc((size_t)kZoloLadder * 2 * kZoloPoles));
+        if (e == cudaSuccess) {
+            std::vector<double> tab((size_t)kZoloLadder * 2 * kZoloPoles);
+            zolotarev_table(tab.data());
+            A(cudaMemcpy(h->zolo.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
+    A(cudaMallocHost(&h->h_state, E * kStateFloats * sizeof(float)));
+    A(cudaMallocHost(&h->h_time, E * sizeof(int)));
+    A(cudaMallocHost(&h->h_action, E * 4 * sizeof(float)));
+    if (e != cudaSuccess) {
+        release_all(h);
+        delete h;
+        return fail(COVO_ERR_CUDA, "workspace allocation failed: %s", cudaGetErrorString(e));
+    }
+    // defaults of get_controller (envs/quadrotor.py:685-690, 703-746)
+    {
+        std::vector<float> mean(E * n);
+        float th = (cfg->m * cfg->g / cfg->max_thrust) * 2.0f - 1.0f;
+        for (size_t i = 0; i < E * (size_t)h->H; ++i) {
+            mean[i * 4 + 0] = th;
+            mean[i * 4 + 1] = mean[i * 4 + 2] = mean[i * 4 + 3] = 0.f;
+        }
+        cudaMemcpy(h->a_mean.p, mean.data(), mean.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (cfg->mode == COVO_MODE_MPPI) {
+            std::vector<float> L(E * h->H * 16, 0.f), C(E * h->H * 16, 0.f);
+            for (size_t b = 0; b < E * (size_t)h->H; ++b)
+                for (int k = 0; k < 4; ++k) {
+                    L[b * 16 + k * 5] = cfg->sample_sigma;
+                    C[b * 16 + k * 5] = cfg->sample_sigma * cfg->sample_sigma;
+                }
+            cudaMemcpy(h->Lblk.p, L.data(), L.size() * sizeof(float), cudaMemcpyHostToDevice);
+            cudaMemcpy(h->cov.p, C.data(), C.size() * sizeof(float), cudaMemcpyHostToDevice);
+            h->have_factor = true;
+        }
+    }
+    *out = h;
+    return COVO_OK;
+}
+
+int covo_destroy(covo_handle* h) {
+    if (!h) return COVO_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    release_all(h);
+    delete h;
+    return COVO_OK;
+}
+
+int covo_set_reference(covo_handle* h, const float* pos, const float* vel, const float* acc) {
+    if (!h || !pos || !vel) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    size_t bytes = (size_t)h->E * h->T * 3 * sizeof(float);
+    CK(cudaMemcpy(h->pos_traj.p, pos, bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->vel_traj.p, vel, bytes, cudaMemcpyHostToDevice));
+    if (acc) CK(cudaMemcpy(h->acc_traj.p, acc, bytes, cudaMemcpyHostToDevice));
+    else CK(cudaMemset(h->acc_traj.p, 0, bytes));
+    return COVO_OK;
+}
+
+int covo_set_mean(covo_handle* h, const float* a_mean) {
+    if (!h || !a_mean) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->own_stream));
+    CK(cudaMemcpy(h->a_mean.p, a_mean, (size_t)h->E * h->n * sizeof(float), cudaMemcpyHostToDevice));
+    return COVO_OK;
+}
+int covo_get_mean(covo_handle* h, float* a_mean) {
+    if (!h || !a_mean) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->own_stream));
+    CK(cudaMemcpy(a_mean, h->a_mean.p, (size_t)h->E * h->n * sizeof(float), cudaMemcpyDeviceToHost));
+    return COVO_OK;
+}
+
+int covo_set_cov(covo_handle* h, const float* a_cov) {
+    if (!h || !a_cov) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->own_stream));
+    if (h->cfg.mode == COVO_MODE_MPPI) {
+        size_t cnt = (size_t)h->E * h->H * 16;
+        std::vector<float> L(cnt, 0.f);
+        for (size_t b = 0; b < (size_t)h->E * h->H; ++b) {  // 4x4 lower Cholesky on the host (setup path)
+            const float* C = a_cov + b * 16;
+            float* Lb = L.data() + b * 16;
+            for (int j = 0; j < 4; ++j) {
+                double s = C[j * 4 + j];
+                for (int k = 0; k < j; ++k) s -= (double)Lb[j * 4 + k] * Lb[j * 4 + k];
+                if (!(s > 0.0)) return fail(COVO_ERR_NUMERIC, "a_cov block %zu is not positive definite", b);
+                double d = sqrt(s);
+                Lb[j * 4 + j] = (float)d;
+                for (int i = j + 1; i < 4; ++i) {
+                    double t = C[i * 4 + j];
+                    for (int k = 0; k < j; ++k) t -= (double)Lb[i * 4 + k] * Lb[j * 4 + k];
+                    Lb[i * 4 + j] = (float)(t / d);
+                }
+            }
+        }
+        CK(cudaMemcpy(h->Lblk.p, L.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->cov.p, a_cov, cnt * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+        CK(cudaMemcpy(h->cov.p, a_cov, (size_t)h->E * h->n * h->n * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemset(h->status.p, 0, h->E * sizeof(int)));
+        SigmaArgs sa = sigma_args(h);
+        CK(launch_cholesky(sa, h->E, h->own_stream));
+        CK(cudaStreamSynchronize(h->own_stream));
+    }
+    h->have_factor = true;
+    return COVO_OK;
+}
+int covo_get_cov(covo_handle* h, float* a_cov) {
+    if (!h || !a_cov) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->own_stream));
+    size_t cnt = (h->cfg.mode == COVO_MODE_MPPI) ? (size_t)h->E * h->H * 16 : (size_t)h->E * h->n * h->n;
+    CK(cudaMemcpy(a_cov, h->cov.p, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+    return COVO_OK;
+}
+
+static int alloc_schedule(covo_handle* h, int t_sched, bool full) {
+    if (h->cfg.mode != COVO_MODE_COVO_OFFLINE) return fail(COVO_ERR_INVALID, "handle is not in covo-offline mode");
+    if (t_sched < 1) return fail(COVO_ERR_INVALID, "t_sched must be positive");
+    const size_t nn = (size_t)h->n * h->n, S = t_sched;
+    if ((int)(h->cov_table.n / nn) < t_sched) {
+        h->cov_table.release();
+        h->Lt_table.release();
+        h->sched_status.release();
+        CK(h->cov_table.alloc(S * nn));
+        CK(h->Lt_table.alloc(S * h->lt_floats));
+        CK(h->sched_status.alloc(S));
+    }
+    if (full && (int)(h->sched_R.n / nn) < t_sched) {
+        h->sched_states.release(); h->sched_times.release(); h->sched_anom.release(); h->sched_R.release();
+        h->sched_Vh.release(); h->sched_tau.release(); h->sched_F.release(); h->sched_Z.release();
+        h->sched_ws.release(); h->sched_diag.release();
+        CK(h->sched_states.alloc(S * kStateFloats));
+        CK(h->sched_times.alloc(S));
+        CK(h->sched_anom.alloc(S * h->n));
+        CK(h->sched_R.alloc(S * nn));
+        CK(h->sched_Vh.alloc(S * nn));
+        CK(h->sched_tau.alloc(S * h->n));
+        CK(h->sched_F.alloc(S * nn));
+        CK(h->sched_Z.alloc(S * nn));
+        CK(h->sched_ws.alloc(S * hessian_workspace_floats(h->H)));
+        CK(h->sched_diag.alloc(S * 4 * h->n));
+    }
+    return COVO_OK;
+}
+
+static SigmaArgs sched_sigma_args(covo_handle* h) {
+    SigmaArgs a = sigma_args(h);
+    a.R = h->sched_R.p;
+    a.Vh = h->sched_Vh.p;
+    a.tau = h->sched_tau.p;
+    a.F = h->sched_F.p;
+    a.Z = h->sched_Z.p;
+    a.cov = h->cov_table.p;
+    a.L = nullptr;
+    a.Lt = h->Lt_table.p;
+    a.diag = h->sched_diag.p;
+    a.status = h->sched_status.p;
+    return a;
+}
+
+int covo_set_cov_offline(covo_handle* h, const float* table, int t_sched) {
+    if (!h || !table) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = alloc_schedule(h, t_sched, false);
+    if (rc) return rc;
+    CK(cudaMemcpy(h->cov_table.p, table, (size_t)t_sched * h->n * h->n * sizeof(float), cudaMemcpyHostToDevice));
+    SigmaArgs sa = sigma_args(h);
+    sa.cov = h->cov_table.p;
+    sa.L = nullptr;
+    sa.Lt = h->Lt_table.p;
+    sa.status = h->sched_status.p;
+    CK(cudaMemset(h->sched_status.p, 0, t_sched * sizeof(int)));
+    CK(launch_cholesky(sa, t_sched, h->own_stream));
+    CK(cudaStreamSynchronize(h->own_stream));
+    h->t_sched = t_sched;
+    h->have_factor = true;
+    return COVO_OK;
+}
+
+int covo_get_cov_offline(covo_handle* h, float* table, int t_sched) {
+    if (!h || !table) return fail(COVO_ERR_INVALID, "null argument");
+    if (t_sched > h->t_sched) return fail(COVO_ERR_INVALID, "schedule has %d steps", h->t_sched);
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->own_stream));
+    CK(cudaMemcpy(table, h->cov_table.p, (size_t)t_sched * h->n * h->n * sizeof(float), cudaMemcpyDeviceToHost));
+    return COVO_OK;
+}
+
+int covo_reset_offline(covo_handle* h, const float* state24, const int* time, int t_sched) {
+    if (!h || !state24 || !time) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = alloc_schedule(h, t_sched, true);
+    if (rc) return rc;
+    cudaStream_t st = h->own_stream;
+    CK(cudaMemcpyAsync(h->state24.p, state24, kStateFloats * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->time.p, time, sizeof(int), cudaMemcpyHostToDevice, st));
+    OfflineArgs oa;
+    oa.H = h->H;
+    oa.traj_len = h->T;
+    oa.t_sched = t_sched;
+    oa.env = h->env;
+    oa.max_thrust = h->cfg.max_thrust;
+    oa.Kp = 10.f;  // controllers/covo.py:48-53
+    oa.Kd = 5.f;
+    oa.Kp_att = 10.f;
+    oa.state24 = h->state24.p;
+    oa.time = h->time.p;
+    oa.pos_traj = h->pos_traj.p;
+    oa.vel_traj = h->vel_traj.p;
+    oa.acc_traj = h->acc_traj.p;
+    oa.states24 = h->sched_states.p;
+    oa.times = h->sched_times.p;
+    oa.a_nom = h->sched_anom.p;
+    CK(launch_offline_paths(oa, st));
+    // all schedule steps as one batch: "environment" t = schedule step t, shared reference trajectory
+    HessianArgs ha = hess_args(h, h->sched_states.p, h->sched_times.p, h->sched_anom.p, 0, h->sched_R.p, h->sched_ws.p, 0);
+    CK(launch_hessian(ha, t_sched, st));
+    CK(cudaMemsetAsync(h->sched_status.p, 0, t_sched * sizeof(int), st));
+    SigmaArgs sa = sched_sigma_args(h);
+    CK(launch_sigma(sa, t_sched, st));
+    CK(launch_cholesky(sa, t_sched, st));
+    CK(cudaStreamSynchronize(st));
+    h->t_sched = t_sched;
+    h->have_factor = true;
+    return COVO_OK;
+}
+
+int covo_step_device(covo_handle* h, const float* st_d, const int* tm_d, const float* eps_d, float* act_d, void* stream) {
+    if (!h || !st_d || !tm_d || !act_d) return fail(COVO_ERR_INVALID, "null argument");
+    if (h->cfg.world != 1) return fail(COVO_ERR_INVALID, "world > 1: use covo_step_partial_device + covo_step_merge_device");
+    CK(cudaSetDevice(h->cfg.device));
+    return step_common(h, st_d, tm_d, eps_d, act_d, (cudaStream_t)stream, 1);
+}
+
+int covo_step(covo_handle* h, const float* state24, const int* time, const float* eps, float* action) {
+    if (!h || !state24 || !time || !action) return fail(COVO_ERR_INVALID, "null argument");
+    if (h->cfg.world != 1) return fail(COVO_ERR_INVALID, "world > 1: use the *_device partial/merge entry points");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->own_stream;
+    memcpy(h->h_state, state24, (size_t)h->E * kStateFloats * sizeof(float));
+    memcpy(h->h_time, time, (size_t)h->E * sizeof(int));
+    CK(cudaMemcpyAsync(h->state24.p, h->h_state, (size_t)h->E * kStateFloats * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->time.p, h->h_time, (size_t)h->E * sizeof(int), cudaMemcpyHostToDevice, st));
+    const float* eps_d = nullptr;
+    if (eps) {
+        size_t cnt = (size_t)h->E * h->n_local * h->n;
+        if (h->eps.n < cnt) {
+            h->eps.release();
+            CK(h->eps.alloc(cnt));
+        }
+        CK(cudaMemcpyAsync(h->eps.p, eps, cnt * sizeof(float), cudaMemcpyHostToDevice, st));
+        eps_d = h->eps.p;
+    }
+    int rc = step_common(h, h->state24.p, h->time.p, eps_d, h->action.p, st, 1);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->h_action, h->action.p, (size_t)h->E * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(action, h->h_action, (size_t)h->E * 4 * sizeof(float));
+    return COVO_OK;
+}
+
+int covo_step_partial_device(covo_handle* h, const float* st_d, const int* tm_d, const float* eps_d, void* stream) {
+    if (!h || !st_d || !tm_d) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    // a_mean is NOT updated here (finalize = 0): the merge kernel applies the shift + update
+    Prof pf(h, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mode = h->cfg.mode;
+    if (mode == COVO_MODE_MPPI) {
+        shift_blocks_kernel<<<h->E, 128, 2 * h->H * 16 * sizeof(float), st>>>(h->Lblk.p, h->cov.p, h->H);
+        CK(cudaGetLastError());
+    } else if (mode == COVO_MODE_COVO_ONLINE) {
+        HessianArgs ha = hess_args(h, st_d, tm_d, h->a_mean.p, 1, h->R.p, h->hess_ws.p, (long long)h->T * 3);
+        CK(launch_hessian(ha, h->E, st));
+        int rc = run_sigma_chol(h, st, nullptr);
+        if (rc) return rc;
+    } else if (h->t_sched <= 0) {
+        return fail(COVO_ERR_INVALID, "covo-offline: no schedule");
+    }
+    RolloutArgs ra = rollout_args(h, st_d, tm_d, h->a_mean.p, 1, eps_d, nullptr, h->a_mean.p, h->action.p, nullptr, nullptr, 0);
+    CK(launch_rollout(ra, h->E, st));
+    if (!eps_d) h->rng_stream += 1;
+    return COVO_OK;
+}
+
+int covo_partial_buffer(covo_handle* h, float** dev_ptr, int* n_floats) {
+    if (!h || !dev_ptr || !n_floats) return fail(COVO_ERR_INVALID, "null argument");
+    *dev_ptr = h->rank_partial.p;
+    *n_floats = h->E * h->rec;
+    return COVO_OK;
+}
+
+int covo_step_merge_device(covo_handle* h, const float* gathered_dev, float* action_dev, void* stream) {
+    if (!h || !gathered_dev || !action_dev) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    MergeArgs m;
+    m.world = h->cfg.world;
+    m.n = h->n;
+    m.n_pad = h->n_pad;
+    m.n_env = h->E;
+    m.lam = h->cfg.lam;
+    m.gamma_mean = h->cfg.gamma_mean;
+    m.shift = 1;
+    m.gathered = gathered_dev;
+    // the merge reads the un-shifted mean and writes the updated one; a scratch copy keeps it race-free
+    if (h->gathered_scratch.n < (size_t)h->E * h->n) {
+        h->gathered_scratch.release();
+        CK(h->gathered_scratch.alloc((size_t)h->E * h->n));
+    }
+    CK(cudaMemcpyAsync(h->gathered_scratch.p, h->a_mean.p, (size_t)h->E * h->n * sizeof(float), cudaMemcpyDeviceToDevice,
+                       (cudaStream_t)stream));
+    m.a_mean_in = h->gathered_scratch.p;
+    m.a_mean_out = h->a_mean.p;
+    m.action_out = action_dev;
+    CK(launch_merge(m, (cudaStream_t)stream));
+    return COVO_OK;
+}
+
+// ---- operators ------------------------------------------------------------------------------------
+static int upload_state(covo_handle* h, const float* state24, const int* time) {
+    CK(cudaMemcpy(h->state24.p, state24, (size_t)h->E * kStateFloats * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->time.p, time, (size_t)h->E * sizeof(int), cudaMemcpyHostToDevice));
+    return COVO_OK;
+}
+
+int covo_hessian(covo_handle* h, const float* state24, const int* time, const float* a_mean, int shift, float* R) {
+    if (!h || !state24 || !time || !a_mean || !R) return fail(COVO_ERR_INVALID, "null argument");
+    if (h->cfg.mode == COVO_MODE_MPPI) return fail(COVO_ERR_INVALID, "handle is in MPPI mode");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->own_stream));
+    int rc = upload_state(h, state24, time);
+    if (rc) return rc;
+    DevBuf<float> am;
+    CK(am.alloc((size_t)h->E * h->n));
+    CK(cudaMemcpy(am.p, a_mean, (size_t)h->E * h->n * sizeof(float), cudaMemcpyHostToDevice));
+    HessianArgs ha = hess_args(h, h->state24.p, h->time.p, am.p, shift, h->R.p, h->hess_ws.p, (long long)h->T * 3);
+    cudaError_t e = launch_hessian(ha, h->E, h->own_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->own_stream);
+    am.release();
+    if (e != cudaSuccess) return fail(COVO_ERR_CUDA, "hessian: %s", cudaGetErrorString(e));
+    CK(cudaMemcpy(R, h->R.p, (size_t)h->E * h->n * h->n * sizeof(float), cudaMemcpyDeviceToHost));
+    return COVO_OK;
+}
+
+static int check_status(covo_handle* h, const char* what) {
+    std::vector<int> s(h->E);
+    CK(cudaMemcpy(s.data(), h->status.p, h->E * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int e = 0; e < h->E; ++e)
+        if (s[e]) return fail(COVO_ERR_NUMERIC, "%s: numeric status %d in environment %d", what, s[e], e);
+    return COVO_OK;
+}
+
+int covo_optimize_sigma(covo_handle* h, const float* R, float* a_cov) {
+    if (!h || !R || !a_cov) return fail(COVO_ERR_INVALID, "null argument");
+    if (h->cfg.mode == COVO_MODE_MPPI) return fail(COVO_ERR_INVALID, "handle is in MPPI mode");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->own_stream));
+    size_t bytes = (size_t)h->E * h->n * h->n * sizeof(float);
+    CK(cudaMemcpy(h->R.p, R, bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemset(h->status.p, 0, h->E * sizeof(int)));
+    int rc = run_sigma_chol(h, h->own_stream, nullptr);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->own_stream));
+    CK(cudaMemcpy(a_cov, h->cov.p, bytes, cudaMemcpyDeviceToHost));
+    return check_status(h, "optimize_sigma");
+}
+
+int covo_cholesky(covo_handle* h, const float* a_cov, float* L) {
+    if (!h || !a_cov || !L) return fail(COVO_ERR_INVALID, "null argument");
+    if (h->cfg.mode == COVO_MODE_MPPI) return fail(COVO_ERR_INVALID, "handle is in MPPI mode");
+    int rc = covo_set_cov(h, a_cov);
+    if (rc) return rc;
+    CK(cudaMemcpy(L, h->Lfull.p, (size_t)h->E * h->n * h->n * sizeof(float), cudaMemcpyDeviceToHost));
+    return check_status(h, "cholesky");
+}
+
+int covo_rollout(covo_handle* h, const float* state24, const int* time, const float* a_mean, int shift, const float* eps,
+                 const float* fdist_seq, float* a_mean_out, float* action, float* costs, float* samples) {
+    if (!h || !state24 || !time || !a_mean) return fail(COVO_ERR_INVALID, "null argument");
+    if (!h->have_factor) return fail(COVO_ERR_INVALID, "no covariance factor: call covo_set_cov / covo_optimize_sigma first");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->own_stream));
+    int rc = upload_state(h, state24, time);
+    if (rc) return rc;
+    const size_t E = h->E, n = h->n, NL = h->n_local;
+    DevBuf<float> am, amo;
+    CK(am.alloc(E * n));
+    CK(amo.alloc(E * n));
+    CK(cudaMemcpy(am.p, a_mean, E * n * sizeof(float), cudaMemcpyHostToDevice));
+    const float* eps_d = nullptr;
+    if (eps) {
+        if (h->eps.n < E * NL * n) {
+            h->eps.release();
+            CK(h->eps.alloc(E * NL * n));
+        }
+        CK(cudaMemcpy(h->eps.p, eps, E * NL * n * sizeof(float), cudaMemcpyHostToDevice));
+        eps_d = h->eps.p;
+    }
+    const float* fd_d = nullptr;
+    if (fdist_seq) {
+        if (h->fdist.n < E * h->H * 3) {
+            h->fdist.release();
+            CK(h->fdist.alloc(E * h->H * 3));
+        }
+        CK(cudaMemcpy(h->fdist.p, fdist_seq, E * h->H * 3 * sizeof(float), cudaMemcpyHostToDevice));
+        fd_d = h->fdist.p;
+    }
+    if (costs && h->costs.n < E * NL) {
+        h->costs.release();
+        CK(h->costs.alloc(E * NL));
+    }
+    if (samples && h->samples.n < E * NL * n) {
+        h->samples.release();
+        CK(h->samples.alloc(E * NL * n));
+    }
+    if (h->pos_stats_on) CK(cudaMemset(h->pos_stats.p, 0, h->pos_stats.n * sizeof(float)));
+    const int finalize = (h->cfg.world == 1) ? 1 : 0;
+    RolloutArgs ra = rollout_args(h, h->state24.p, h->time.p, am.p, shift, eps_d, fd_d, amo.p, h->action.p,
+                                  costs ? h->costs.p : nullptr, samples ? h->samples.p : nullptr, finalize);
+    cudaError_t e = launch_rollout(ra, h->E, h->own_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->own_stream);
+    if (!eps_d) h->rng_stream += 1;
+    int ret = COVO_OK;
+    if (e != cudaSuccess) ret = fail(COVO_ERR_CUDA, "rollout: %s", cudaGetErrorString(e));
+    if (!ret && a_mean_out) cudaMemcpy(a_mean_out, amo.p, E * n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (!ret && action) cudaMemcpy(action, h->action.p, E * 4 * sizeof(float), cudaMemcpyDeviceToHost);
+    if (!ret && costs) cudaMemcpy(costs, h->costs.p, E * NL * sizeof(float), cudaMemcpyDeviceToHost);
+    if (!ret && samples) cudaMemcpy(samples, h->samples.p, E * NL * n * sizeof(float), cudaMemcpyDeviceToHost);
+    am.release();
+    amo.release();
+    return ret;
+}
+
+// ---- debug / introspection ------------------------------------------------------------------------
+int covo_enable_pos_stats(covo_handle* h, int on) {
+    if (!h) return fail(COVO_ERR_INVALID, "null argument");
+    h->pos_stats_on = on != 0;
+    return COVO_OK;
+}
+
+int covo_get_pos_stats(covo_handle* h, float* pos_mean, float* pos_std) {
+    if (!h || !pos_mean || !pos_std) return fail(COVO_ERR_INVALID, "null argument");
+    if (!h->pos_stats_on) return fail(COVO_ERR_INVALID, "position statistics are disabled (covo_enable_pos_stats)");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->own_stream));
+    std::vector<float> s(h->pos_stats.n);
+    CK(cudaMemcpy(s.data(), h->pos_stats.p, s.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    const double N = (double)h->n_local;
+    for (int i = 0; i < h->E * h->H; ++i)
+        for (int k = 0; k < 3; ++k) {
+            double mean = s[i * 6 + k] / N, sq = s[i * 6 + 3 + k] / N;
+            pos_mean[i * 3 + k] = (float)mean;
+            pos_std[i * 3 + k] = (float)sqrt(fmax(sq - mean * mean, 0.0));  // jnp.std, ddof = 0
+        }
+    return COVO_OK;
+}
+
+int covo_debug_eps(covo_handle* h, unsigned int stream_id, float* eps) {
+    if (!h || !eps) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    DevBuf<float> d;
+    size_t cnt = (size_t)h->n_local * h->n;
+    CK(d.alloc(cnt));
+    int total = h->n_local * (h->n >> 2);
+    debug_eps_kernel<<<(total + 255) / 256, 256, 0, h->own_stream>>>(d.p, h->n_local, h->sample_offset, h->n, h->cfg.seed, stream_id);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->own_stream);
+    if (e == cudaSuccess) e = cudaMemcpy(eps, d.p, cnt * sizeof(float), cudaMemcpyDeviceToHost);
+    d.release();
+    if (e != cudaSuccess) return fail(COVO_ERR_CUDA, "debug_eps: %s", cudaGetErrorString(e));
+    return COVO_OK;
+}
+
+int covo_debug_tridiag(covo_handle* h, double* d, double* e, double* scalars5) {
+    if (!h || !d || !e || !scalars5) return fail(COVO_ERR_INVALID, "null argument");
+    if (h->cfg.mode == COVO_MODE_MPPI) return fail(COVO_ERR_INVALID, "handle is in MPPI mode");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->own_stream));
+    CK(cudaMemcpy(d, h->diag.p, h->n * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(e, h->diag.p + h->n, h->n * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(scalars5, h->diag.p + 2 * h->n, 5 * sizeof(double), cudaMemcpyDeviceToHost));
+    return COVO_OK;
+}
+
+int covo_zolotarev_nodes(double m, double M, int n_poles, double* shifts, double* weights) {
+    if (!shifts || !weights || n_poles < 1 || !(m > 0.0) || !(M > m)) return fail(COVO_ERR_INVALID, "bad argument");
+    zolotarev_nodes(m, M, n_poles, shifts, weights);
+    return COVO_OK;
+}
+
+int covo_get_status(covo_handle* h, int* status) {
+    if (!h || !status) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->own_stream));
+    CK(cudaMemcpy(status, h->status.p, h->E * sizeof(int), cudaMemcpyDeviceToHost));
+    return COVO_OK;
+}
+
+int covo_set_profiling(covo_handle* h, int on) {
+    if (!h) return fail(COVO_ERR_INVALID, "null argument");
+    h->profiling = on != 0;
+    return COVO_OK;
+}
+
+int covo_get_kernel_ms(covo_handle* h, float* ms6) {
+    if (!h || !ms6) return fail(COVO_ERR_INVALID, "null argument");
+    if (!h->profiling) return fail(COVO_ERR_INVALID, "profiling is off");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaEventSynchronize(h->ev[6]));
+    // boundaries: 0 start | 1..3 hessian (local+assemble reported together in slot 0) | 4 sigma | 5 cholesky | 6 rollout
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, h->ev[0], h->ev[3]));
+    ms6[0] = t;
+    ms6[1] = 0.f;
+    CK(cudaEventElapsedTime(&t, h->ev[3], h->ev[4]));
+    ms6[2] = t;
+    ms6[3] = 0.f;
+    CK(cudaEventElapsedTime(&t, h->ev[4], h->ev[5]));
+    ms6[4] = t;
+    CK(cudaEventElapsedTime(&t, h->ev[5], h->ev[6]));
+    ms6[5] = t;
+    return COVO_OK;
+}
+
+int covo_rng_step(covo_handle* h, unsigned int* stream_id) {
+    if (!h || !stream_id) return fail(COVO_ERR_INVALID, "null argument");
+    *stream_id = h->rng_stream;
+    return COVO_OK;
+}
+
+int covo_local_samples(covo_handle* h, int* n_local, int* offset) {
+    if (!h || !n_local || !offset) return fail(COVO_ERR_INVALID, "null argument");
+    *n_local = h->n_local;
+    *offset = h->sample_offset;
+    return COVO_OK;
+}
+
+}  // extern "C"

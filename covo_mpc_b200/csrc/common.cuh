@@ -1,0 +1,77 @@
+// Shared declarations of the kernel family (internal; the public boundary is include/covo_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "quad_model.cuh"
+
+namespace covo {
+
+constexpr int kMaxH = 64;        // horizon limit: n = 4H <= 256 control dimensions
+constexpr int kStateFloats = 24;  // covo_state24
+constexpr int kTileSamples = 64;  // trajectories per CTA in the rollout kernel
+constexpr int kRolloutThreads = 256;
+constexpr int kPartialHdr = 4;  // (m, s, pad, pad) before v[n_pad] in a softmax partial record
+
+__host__ __device__ inline int round_up8(int x) { return (x + 7) & ~7; }
+
+// Packed, k-major ("transposed") storage of the lower Cholesky factor used by the sampler:
+// column k of L holds rows r >= (k & ~7) contiguously (rows (k&~7) .. k-1 are explicit zeros so that
+// every 8-row group is float4 aligned).  lt_col_offset(k) = sum_{j<k} (n_pad - (j & ~7)).
+__host__ __device__ inline int lt_col_offset(int k, int n_pad) {
+    int B = k >> 3, c = k & 7;
+    return k * n_pad - 32 * B * (B - 1) - 8 * c * B;
+}
+__host__ __device__ inline int lt_size(int n, int n_pad) { return lt_col_offset(n, n_pad); }
+
+struct RolloutArgs {
+    int n_samples;      // samples of THIS launch (this rank's shard)
+    int sample_offset;  // global index of the first one (N-sharding keeps the RNG field global)
+    int H, n, n_pad;
+    int mode;  // 0: dense packed Lt (CoVO), 1: block-diagonal per-step 4x4 (MPPI)
+    int shift;  // apply the shift operator to a_mean_in on load
+    int finalize;  // last CTA merges partials and writes a_mean_out / action_out (world == 1)
+    int traj_len;
+    long long traj_stride;  // floats between environments in pos_traj / vel_traj (0: shared)
+    float lam, gamma_mean, discount;
+    EnvConsts env;
+    unsigned long long seed;
+    unsigned int stream;
+    // inputs (per environment e = blockIdx.y, strides below)
+    const float* state24;    // [E][24]
+    const int* time;         // [E]
+    const float* pos_traj;   // [E][T][3]
+    const float* vel_traj;   // [E][T][3]
+    const float* a_mean_in;  // [E][n]
+    const float* Lfac;       // dense: [E][lt_size]; block-diag: [E][H][16] row-major lower
+    const float* eps;        // optional [E][n_samples][n]  (parity mode), else nullptr
+    const float* fdist_seq;  // optional [E][H][3]: force produced by step h (acts during step h+1)
+    // outputs
+    float* partials;         // [E][n_cta][kPartialHdr + n_pad]
+    unsigned int* counters;  // [E]
+    float* rank_partial;     // [E][kPartialHdr + n_pad]   (when !finalize)
+    float* a_mean_out;       // [E][n]
+    float* action_out;       // [E][4]
+    float* costs_out;        // optional [E][n_samples]
+    float* samples_out;      // optional [E][n_samples][n]  clipped samples
+    float* pos_stats;        // optional [E][H][6]  sum(pos), sum(pos^2) over the samples
+    long long lfac_stride;   // floats between environments in Lfac
+    long long lfac_time_stride;  // CoVO-offline: factor table indexed by min(time, lfac_time_max)
+    int lfac_time_max;
+};
+
+struct MergeArgs {
+    int world, n, n_pad, n_env;
+    float lam, gamma_mean;
+    int shift;
+    const float* gathered;   // [world][E][kPartialHdr + n_pad]
+    const float* a_mean_in;  // [E][n]
+    float* a_mean_out;       // [E][n]
+    float* action_out;       // [E][4]
+};
+
+cudaError_t launch_rollout(const RolloutArgs& a, int n_env, cudaStream_t st);
+cudaError_t launch_merge(const MergeArgs& a, cudaStream_t st);
+size_t rollout_smem_bytes(int n_pad, int mode, int H);
+
+}  // namespace covo

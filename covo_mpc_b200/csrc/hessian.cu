@@ -1,0 +1,232 @@
+// K3 + K4: exact control-space Hessian of the nominal-rollout cost.
+//
+// Replaces controllers/covo.py:134-185 (get_hessian = jacfwd(jacfwd(get_cumulated_cost)) over the
+// Python-unrolled H-step rollout with deterministic=True, no termination freeze, no discount).
+//
+// The reference pushes (4H)^2 second-order tangent lanes through all H steps.  Here the same exact
+// Hessian is assembled from per-transition derivatives (verified against the forward-over-forward
+// oracle to round-off, tests/test_hessian_gpu.py):
+//   z_t = (x_t, u_t),  x_{t+1} = F(z_t),  c_t(x_t) = -r(x_t),  A_t = dF/dx, B_t = dF/du
+//   adjoint      lam_H = 0,  lam_t = grad c_t + A_t^T lam_{t+1}
+//   Lagrangian   W_t = blkdiag(hess c_t, 0) + sum_k lam_{t+1,k} hess F_k(z_t)        (17 x 17)
+//   backward     P_H = 0,  X = P_{t+1} [A_t B_t],
+//                S_t = W_t^{xu} + A_t^T X_B,  D_t = W_t^{uu} + B_t^T X_B,  P_t = W_t^{xx} + A_t^T X_A
+//   forward      Phi = B_I;  for J > I:  R[I,J] = Phi^T S_J,  Phi <- A_J Phi;   R[I,I] = D_I
+// Kernel 1 (grid = H x envs): CTA t re-runs the nominal rollout to x_t, then 153 threads evaluate the
+//   transition and the cost once each in hyper-dual arithmetic (quad_model.cuh) -- one (a <= b) pair of
+//   the 17 local inputs per thread -- giving A_t, B_t, grad/hess c_t and all 13 hess F_k.
+// Kernel 2 (grid = envs): adjoint, contraction, the 13x13 backward recursion and the H forward chains.
+// Sub-gradient conventions (clip ties, |.|, sqrt at 0) are those of quad_model.cuh / the oracle.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "hessian.cuh"
+#include "hessian_local.cuh"
+
+namespace covo {
+
+size_t hessian_workspace_floats(int H) { return (size_t)H * (14 * NPAIR + 14 * NZ); }
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160) hess_local_kernel(const HessianArgs a) {
+    const int t = blockIdx.x, env = blockIdx.y, tid = threadIdx.x;
+    const int H = a.H;
+    __shared__ float sx[16], su[4], sfd[4], spt[4], svt[4];
+    if (tid == 0) {
+        const float* st_g = a.state24 + (long long)env * kStateFloats;
+        QState<float> s;
+        float fd[3], pt[3], vt[3];
+        load_state24(st_g, s, fd, pt, vt);
+        const int t0 = a.time[env];
+        const float* mu = a.a_mean + (long long)env * 4 * H;
+        for (int h = 0; h < t; ++h) {
+            int hs = a.shift ? min(h + 1, H - 1) : h;
+            float u[4] = {mu[hs * 4 + 0], mu[hs * 4 + 1], mu[hs * 4 + 2], mu[hs * 4 + 3]};
+            quad_step(s, u, fd, a.env);
+            // deterministic=True: the disturbance is zero after the first step (envs/quadrotor.py:234-235)
+            fd[0] = fd[1] = fd[2] = 0.f;
+        }
+        if (t > 0) {
+            int row = min(t0 + t, a.traj_len - 1);  // clamped gather, dynamics/free.py:153-155
+            for (int k = 0; k < 3; ++k) {
+                pt[k] = a.pos_traj[((long long)env * a.traj_stride + (long long)row * 3) + k];
+                vt[k] = a.vel_traj[((long long)env * a.traj_stride + (long long)row * 3) + k];
+            }
+        }
+        for (int k = 0; k < 3; ++k) sx[k] = s.p[k];
+        for (int k = 0; k < 4; ++k) sx[3 + k] = s.q[k];
+        for (int k = 0; k < 3; ++k) sx[7 + k] = s.v[k];
+        for (int k = 0; k < 3; ++k) sx[10 + k] = s.w[k];
+        int hs = a.shift ? min(t + 1, H - 1) : t;
+        for (int k = 0; k < 4; ++k) su[k] = mu[hs * 4 + k];
+        for (int k = 0; k < 3; ++k) { sfd[k] = fd[k]; spt[k] = pt[k]; svt[k] = vt[k]; }
+    }
+    __syncthreads();
+    if (tid >= NPAIR) return;
+    int pa, pb;
+    pair_from_index(tid, pa, pb);
+    float x[13], u[4], fd[3], pt[3], vt[3], Fab[14], Fa[14];
+    for (int k = 0; k < 13; ++k) x[k] = sx[k];
+    for (int k = 0; k < 4; ++k) u[k] = su[k];
+    for (int k = 0; k < 3; ++k) { fd[k] = sfd[k]; pt[k] = spt[k]; vt[k] = svt[k]; }
+    hess_local_task(x, u, fd, pt, vt, a.env, pa, pb, Fab, Fa);
+    float* ws = a.workspace + ((long long)env * H + t) * (14 * NPAIR + 14 * NZ);
+    for (int k = 0; k < 14; ++k) ws[k * NPAIR + tid] = Fab[k];
+    if (pa == pb) {
+        float* g = ws + 14 * NPAIR;
+        for (int k = 0; k < 14; ++k) g[k * NZ + pa] = Fa[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kAsmThreads = 320;
+
+__global__ void __launch_bounds__(kAsmThreads) hess_assemble_kernel(const HessianArgs a) {
+    extern __shared__ __align__(16) float smf[];
+    const int env = blockIdx.x, tid = threadIdx.x;
+    const int H = a.H, n = 4 * H;
+    // shared layout (S and D first: they are read as float4)
+    float* S = smf;                    // [H][13][4]
+    float* D = S + H * NX * 4;         // [H][4][4]
+    float* G = D + H * 16;             // [H][13][17]  (A_t | B_t)
+    float* cg = G + H * NX * NZ;       // [H][13]
+    float* lam = cg + H * NX;          // [H+1][13]
+    float* W = lam + (H + 1) * NX;     // [H][153]
+    float* P = W + H * NPAIR;          // [13][13]
+    float* X = P + NX * NX;            // [13][17]
+    const float* wsb = a.workspace + (long long)env * H * (14 * NPAIR + 14 * NZ);
+    const int rec = 14 * NPAIR + 14 * NZ;
+
+    for (int i = tid; i < H * NX * NZ; i += blockDim.x) {
+        int t = i / (NX * NZ), r = i % (NX * NZ);
+        G[i] = wsb[(long long)t * rec + 14 * NPAIR + r];
+    }
+    for (int i = tid; i < H * NX; i += blockDim.x) {
+        int t = i / NX, k = i % NX;
+        cg[i] = (t >= 1) ? wsb[(long long)t * rec + 14 * NPAIR + 13 * NZ + k] : 0.f;  // c_0 is constant in U
+    }
+    for (int i = tid; i < NX; i += blockDim.x) lam[H * NX + i] = 0.f;
+    __syncthreads();
+
+    // adjoint, serial in t, 13 lanes of warp 0
+    if (tid < 32) {
+        for (int t = H - 1; t >= 1; --t) {
+            if (tid < NX) {
+                float acc = cg[t * NX + tid];
+                const float* At = G + t * NX * NZ;
+                const float* ln = lam + (t + 1) * NX;
+#pragma unroll
+                for (int j = 0; j < NX; ++j) acc = fmaf(At[j * NZ + tid], ln[j], acc);
+                lam[t * NX + tid] = acc;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // Lagrangian Hessians W_t (packed upper, 153 entries)
+    for (int i = tid; i < H * NPAIR; i += blockDim.x) {
+        int t = i / NPAIR, pi = i % NPAIR;
+        const float* T = wsb + (long long)t * rec;
+        float acc = (t >= 1) ? T[13 * NPAIR + pi] : 0.f;
+        const float* ln = lam + (t + 1) * NX;
+#pragma unroll
+        for (int k = 0; k < NX; ++k) acc = fmaf(ln[k], T[k * NPAIR + pi], acc);
+        W[i] = acc;
+    }
+    for (int i = tid; i < NX * NX; i += blockDim.x) P[i] = 0.f;
+    __syncthreads();
+
+    // backward recursion for P (13x13), S_t (13x4), D_t (4x4)
+    for (int t = H - 1; t >= 0; --t) {
+        const float* Gt = G + t * NX * NZ;
+        for (int i = tid; i < NX * NZ; i += blockDim.x) {  // X = P [A B]
+            int r = i / NZ, c = i % NZ;
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < NX; ++k) acc = fmaf(P[r * NX + k], Gt[k * NZ + c], acc);
+            X[i] = acc;
+        }
+        __syncthreads();
+        for (int i = tid; i < NZ * NZ; i += blockDim.x) {  // W + [A B]^T X
+            int r = i / NZ, c = i % NZ;
+            if (r >= NX && c < NX) continue;  // lower-left block is the transpose of S, not needed
+            int lo = min(r, c), hi = max(r, c);
+            float acc = W[t * NPAIR + pair_index(lo, hi)];
+#pragma unroll
+            for (int k = 0; k < NX; ++k) acc = fmaf(Gt[k * NZ + r], X[k * NZ + c], acc);
+            if (r < NX && c < NX) P[r * NX + c] = acc;
+            else if (r < NX) S[(t * NX + r) * 4 + (c - NX)] = acc;
+            else D[t * 16 + (r - NX) * 4 + (c - NX)] = acc;
+        }
+        __syncthreads();
+    }
+
+    // forward chains: thread (I, c) carries Phi = d x_J / d u_{I,c}
+    float* Rg = a.R + (long long)env * n * n;
+    for (int id = tid; id < n; id += blockDim.x) {
+        const int I = id >> 2, c = id & 3;
+        float phi[NX];
+        const float* GI = G + I * NX * NZ;
+#pragma unroll
+        for (int k = 0; k < NX; ++k) phi[k] = GI[k * NZ + NX + c];
+        {
+            float4 d = *reinterpret_cast<const float4*>(D + I * 16 + c * 4);
+            // D is symmetric up to round-off; symmetrise so R is exactly symmetric
+            float dd[4] = {d.x, d.y, d.z, d.w};
+            for (int e = 0; e < 4; ++e) dd[e] = 0.5f * (dd[e] + D[I * 16 + e * 4 + c]);
+            *reinterpret_cast<float4*>(Rg + (long long)id * n + 4 * I) = make_float4(dd[0], dd[1], dd[2], dd[3]);
+        }
+        for (int J = I + 1; J < H; ++J) {
+            const float* SJ = S + J * NX * 4;
+            float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < NX; ++k) {
+                float4 sj = *reinterpret_cast<const float4*>(SJ + k * 4);
+                r0 = fmaf(phi[k], sj.x, r0);
+                r1 = fmaf(phi[k], sj.y, r1);
+                r2 = fmaf(phi[k], sj.z, r2);
+                r3 = fmaf(phi[k], sj.w, r3);
+            }
+            *reinterpret_cast<float4*>(Rg + (long long)id * n + 4 * J) = make_float4(r0, r1, r2, r3);
+            Rg[(long long)(4 * J + 0) * n + id] = r0;
+            Rg[(long long)(4 * J + 1) * n + id] = r1;
+            Rg[(long long)(4 * J + 2) * n + id] = r2;
+            Rg[(long long)(4 * J + 3) * n + id] = r3;
+            const float* GJ = G + J * NX * NZ;
+            float nphi[NX];
+#pragma unroll
+            for (int r = 0; r < NX; ++r) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < NX; ++k) acc = fmaf(GJ[r * NZ + k], phi[k], acc);
+                nphi[r] = acc;
+            }
+#pragma unroll
+            for (int k = 0; k < NX; ++k) phi[k] = nphi[k];
+        }
+    }
+}
+
+size_t hessian_assemble_smem(int H) {
+    size_t f = (size_t)H * NX * NZ + H * NX + (H + 1) * NX + (size_t)H * NPAIR + H * NX * 4 + H * 16 + NX * NX + NX * NZ;
+    return f * sizeof(float);
+}
+
+cudaError_t launch_hessian(const HessianArgs& a, int n_env, cudaStream_t st) {
+    dim3 g1(a.H, n_env);
+    hess_local_kernel<<<g1, 160, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    size_t smem = hessian_assemble_smem(a.H);
+    static size_t configured = 0;
+    if (smem > configured) {
+        e = cudaFuncSetAttribute(hess_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    hess_assemble_kernel<<<n_env, kAsmThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace covo

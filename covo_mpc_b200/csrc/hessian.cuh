@@ -1,0 +1,24 @@
+// Internal declarations for the Hessian kernels (hessian.cu).
+#pragma once
+#include "common.cuh"
+
+namespace covo {
+
+struct HessianArgs {
+    int H, traj_len, shift;
+    long long traj_stride;  // floats between environments in pos_traj / vel_traj (0: shared)
+    EnvConsts env;
+    const float* state24;   // [E][24]
+    const int* time;        // [E]
+    const float* pos_traj;  // [E][T][3]
+    const float* vel_traj;  // [E][T][3]
+    const float* a_mean;    // [E][H][4]   nominal controls (shift applied on load if `shift`)
+    float* workspace;       // [E][H][14*153 + 14*17]
+    float* R;               // [E][n][n]
+};
+
+size_t hessian_workspace_floats(int H);
+size_t hessian_assemble_smem(int H);
+cudaError_t launch_hessian(const HessianArgs& a, int n_env, cudaStream_t st);
+
+}  // namespace covo

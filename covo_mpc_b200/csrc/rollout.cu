@@ -1,0 +1,520 @@
+// K1 + K2: sample -> rollout -> softmax-reduce, one fused kernel.
+//
+// Replaces (reference file:line): controllers/covo.py:201-203, 212-278 and controllers/mppi.py:46-116
+// (shift, multivariate_normal draw as mean + chol(cov) eps, clip, N x H step_env rollout with reward
+// freeze on termination, discounted cost, softmax(-(cost - min)/lam) weighted mean), with
+// envs/quadrotor.py:215-263, dynamics/free.py:74-155 and dynamics/utils.py:266-294 inlined
+// (quad_model.cuh).
+//
+// One CTA owns a tile of TS = 64 trajectories of one environment:
+//   phase 0  TMA bulk copy of the packed Cholesky factor (k-major, ~83 KB at n = 200) into shared
+//            memory, overlapped with staging the mean, the reference-trajectory slice and the eps tile
+//            (drawn in-kernel from the counter RNG, or read from HBM in parity mode);
+//   phase 1  U = clip(mu + E L^T): a register-tiled fp32 triangular GEMM; every thread owns two
+//            4-sample x 8-row tiles (row groups g and G-1-g, so the triangular work is balanced);
+//   phase 2  64 threads roll one trajectory each through H steps, state in registers, controls read
+//            from the U tile (conflict-free), reference rows broadcast from shared memory;
+//   phase 3  tile-local (min, sum exp, sum exp * u) partial, then a single grid-wide merge by the last
+//            CTA to finish (overflow-safe: partials carry their own min).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace covo {
+
+namespace {
+
+constexpr int TS = kTileSamples;
+constexpr int TSP = TS + 4;  // padded sample stride of the E/U tile (float4 aligned, conflict-free)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct Smem {
+    float* lfac;   // packed Lt (dense) or Lblk [H][16]
+    float* tile;   // E then U: [n_pad][TSP]
+    float* mu;     // [n_pad]
+    float* ref;    // [H][8]: pos_tar(3), vel_tar(3), fdist(2 of 3 -> see fds)
+    float* fds;    // [H][4]: disturbance force acting during step h
+    float* cost;   // [TS]
+    float* wgt;    // [TS]
+    float* red;    // [32] scratch
+    uint64_t* bar;
+};
+
+__device__ __forceinline__ Smem carve(unsigned char* base, int n_pad, int H, int lfac_floats) {
+    Smem s;
+    float* f = reinterpret_cast<float*>(base);
+    s.lfac = f;
+    f += (lfac_floats + 3) & ~3;
+    s.tile = f;
+    f += n_pad * TSP;
+    s.mu = f;
+    f += n_pad;
+    s.ref = f;
+    f += H * 8;
+    s.fds = f;
+    f += H * 4;
+    s.cost = f;
+    f += TS;
+    s.wgt = f;
+    f += TS;
+    s.red = f;
+    f += 32;
+    s.bar = reinterpret_cast<uint64_t*>(f);
+    return s;
+}
+
+}  // namespace
+
+size_t rollout_smem_bytes(int n_pad, int mode, int H) {
+    int lf = (mode == 0) ? lt_size(4 * H, n_pad) : H * 16;
+    lf = (lf + 3) & ~3;
+    size_t floats = (size_t)lf + (size_t)n_pad * TSP + n_pad + H * 8 + H * 4 + TS + TS + 32;
+    return floats * sizeof(float) + 16;
+}
+
+__global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const RolloutArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int env = blockIdx.y;
+    const int n = a.n, n_pad = a.n_pad, H = a.H;
+    const int lfac_floats = (a.mode == 0) ? lt_size(n, n_pad) : H * 16;
+    Smem sm = carve(smem_raw, n_pad, H, lfac_floats);
+    const int tile0 = blockIdx.x * TS;                       // first local sample of this tile
+    const int n_valid = min(TS, a.n_samples - tile0);        // valid samples in this tile
+    const float* lfac_g = a.Lfac + (long long)env * a.lfac_stride;
+    if (a.lfac_time_stride) lfac_g += (long long)min(max(a.time[env], 0), a.lfac_time_max) * a.lfac_time_stride;
+
+    // ---------------- phase 0: staging -------------------------------------------------------
+    if (tid == 0) {
+        mbar_init(sm.bar, 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t total = (uint32_t)lfac_floats * 4u;
+        mbar_expect_tx(sm.bar, total);
+        uint32_t done = 0;
+        while (done < total) {  // TMA bulk copies, <= 32 KB each
+            uint32_t chunk = min(total - done, 32768u);
+            tma_load_1d(reinterpret_cast<unsigned char*>(sm.lfac) + done,
+                        reinterpret_cast<const unsigned char*>(lfac_g) + done, chunk, sm.bar);
+            done += chunk;
+        }
+    }
+    // mean with the shift operator (controllers/covo.py:201-203) fused into the load
+    const float* mu_g = a.a_mean_in + (long long)env * n;
+    for (int r = tid; r < n_pad; r += blockDim.x) {
+        float v = 0.f;
+        if (r < n) {
+            int h = r >> 2, c = r & 3;
+            int hs = a.shift ? min(h + 1, H - 1) : h;
+            v = mu_g[hs * 4 + c];
+        }
+        sm.mu[r] = v;
+    }
+    // reference slice: step h sees traj[min(t0 + h, T-1)] (clamped gather, dynamics/free.py:153-155);
+    // h = 0 uses the targets stored in the state itself.
+    const float* st_g = a.state24 + (long long)env * kStateFloats;
+    const int t0 = a.time[env];
+    for (int i = tid; i < H * 8; i += blockDim.x) {
+        int h = i >> 3, c = i & 7;
+        float v = 0.f;
+        if (c < 6) {
+            if (h == 0) {
+                v = st_g[16 + c];
+            } else {
+                int row = min(t0 + h, a.traj_len - 1);
+                const float* src = (c < 3 ? a.pos_traj : a.vel_traj) + ((long long)env * a.traj_stride + (long long)row * 3);
+                v = src[c < 3 ? c : c - 3];
+            }
+        }
+        sm.ref[i] = v;
+    }
+    for (int i = tid; i < H * 4; i += blockDim.x) {
+        int h = i >> 2, c = i & 3;
+        float v = 0.f;
+        if (c < 3) {
+            if (h == 0) v = st_g[13 + c];
+            else if (a.fdist_seq) v = a.fdist_seq[((long long)env * H + (h - 1)) * 3 + c];
+        }
+        sm.fds[i] = v;
+    }
+    // eps tile E[c][s]
+    if (a.eps) {
+        // parity mode: eps[env][i][c] from HBM; each thread moves 8 consecutive columns of one sample
+        const float* eg = a.eps + ((long long)env * a.n_samples + tile0) * n;
+        const int cblocks = n_pad >> 3;
+        for (int i = tid; i < TS * cblocks; i += blockDim.x) {
+            int s = i % TS, cb = i / TS;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+            if (s < n_valid) {
+                const float* src = eg + (long long)s * n + cb * 8;
+                if (cb * 8 + 8 <= n && ((((uintptr_t)src) & 15) == 0)) {
+                    float4 x0 = __ldg(reinterpret_cast<const float4*>(src));
+                    float4 x1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                    v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
+                    v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (cb * 8 + j < n) v[j] = __ldg(src + j);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sm.tile[(cb * 8 + j) * TSP + s] = v[j];
+        }
+    } else {
+        const int blocks4 = n_pad >> 2;
+        for (int i = tid; i < TS * blocks4; i += blockDim.x) {
+            int s = i % TS, b = i / TS;
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+            if (s < n_valid && b * 4 < n)
+                philox_normal4(a.seed, a.stream, (uint32_t)(a.sample_offset + tile0 + s), (uint32_t)b, z);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sm.tile[(b * 4 + j) * TSP + s] = z[j];
+        }
+    }
+    __syncthreads();
+    mbar_wait(sm.bar, 0);
+
+    // ---------------- phase 1: U = clip(mu + E L^T) ------------------------------------------
+    if (a.mode == 0) {
+        const int SG = TS / 4;
+        const int G = n_pad >> 3;
+        const int NP = (G + 1) >> 1;
+        float accA[4][8], accB[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) accA[i][j] = accB[i][j] = 0.f;
+        const bool active = tid < SG * NP;
+        const int sg = tid % SG, pr = tid / SG;
+        const int gA = pr, gB = G - 1 - pr;
+        const bool hasB = active && (gB != gA);
+        if (active) {
+            const int kendA = min(8 * gA + 8, n), kendB = hasB ? min(8 * gB + 8, n) : 0;
+            const float* Erow = sm.tile + 4 * sg;
+            int off = 0;  // lt_col_offset(k)
+            int k = 0;
+            for (; k < kendA; ++k) {
+                const float4 e = *reinterpret_cast<const float4*>(Erow + k * TSP);
+                const float* col = sm.lfac + off - (k & ~7);
+                const float4 la0 = *reinterpret_cast<const float4*>(col + 8 * gA);
+                const float4 la1 = *reinterpret_cast<const float4*>(col + 8 * gA + 4);
+                const float ev[4] = {e.x, e.y, e.z, e.w};
+                const float lav[8] = {la0.x, la0.y, la0.z, la0.w, la1.x, la1.y, la1.z, la1.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) accA[i][j] = fmaf(ev[i], lav[j], accA[i][j]);
+                if (hasB) {
+                    const float4 lb0 = *reinterpret_cast<const float4*>(col + 8 * gB);
+                    const float4 lb1 = *reinterpret_cast<const float4*>(col + 8 * gB + 4);
+                    const float lbv[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) accB[i][j] = fmaf(ev[i], lbv[j], accB[i][j]);
+                }
+                off += n_pad - (k & ~7);
+            }
+            for (; k < kendB; ++k) {
+                const float4 e = *reinterpret_cast<const float4*>(Erow + k * TSP);
+                const float* col = sm.lfac + off - (k & ~7);
+                const float4 lb0 = *reinterpret_cast<const float4*>(col + 8 * gB);
+                const float4 lb1 = *reinterpret_cast<const float4*>(col + 8 * gB + 4);
+                const float ev[4] = {e.x, e.y, e.z, e.w};
+                const float lbv[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) accB[i][j] = fmaf(ev[i], lbv[j], accB[i][j]);
+                off += n_pad - (k & ~7);
+            }
+        }
+        __syncthreads();  // everyone is done reading E; U may now overwrite it
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int rA = 8 * gA + j;
+                float4 o;
+                float m = sm.mu[rA];
+                o.x = clip_(m + accA[0][j], -1.f, 1.f);
+                o.y = clip_(m + accA[1][j], -1.f, 1.f);
+                o.z = clip_(m + accA[2][j], -1.f, 1.f);
+                o.w = clip_(m + accA[3][j], -1.f, 1.f);
+                *reinterpret_cast<float4*>(sm.tile + rA * TSP + 4 * sg) = o;
+                if (hasB) {
+                    int rB = 8 * gB + j;
+                    float mb = sm.mu[rB];
+                    o.x = clip_(mb + accB[0][j], -1.f, 1.f);
+                    o.y = clip_(mb + accB[1][j], -1.f, 1.f);
+                    o.z = clip_(mb + accB[2][j], -1.f, 1.f);
+                    o.w = clip_(mb + accB[3][j], -1.f, 1.f);
+                    *reinterpret_cast<float4*>(sm.tile + rB * TSP + 4 * sg) = o;
+                }
+            }
+        }
+    } else {
+        // MPPI: independent 4x4 Gaussians per horizon step (controllers/mppi.py:56-66), in place
+        for (int i = tid; i < TS * H; i += blockDim.x) {
+            int s = i % TS, h = i / TS;
+            const float* Lb = sm.lfac + h * 16;
+            float e[4], u[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) e[c] = sm.tile[(4 * h + c) * TSP + s];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float acc = sm.mu[4 * h + r];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c <= r) acc = fmaf(Lb[r * 4 + c], e[c], acc);
+                u[r] = clip_(acc, -1.f, 1.f);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) sm.tile[(4 * h + r) * TSP + s] = u[r];
+        }
+    }
+    __syncthreads();
+
+    if (a.samples_out) {
+        float* og = a.samples_out + ((long long)env * a.n_samples + tile0) * n;
+        for (int i = tid; i < TS * n; i += blockDim.x) {
+            int s = i / n, r = i % n;
+            if (s < n_valid) og[(long long)s * n + r] = sm.tile[r * TSP + s];
+        }
+    }
+
+    // ---------------- phase 2: rollouts --------------------------------------------------------
+    if (tid < TS) {
+        // lanes past the end of a ragged last tile run the same code on the same state (their U columns
+        // are clip(mu)) so the warp stays converged for the shuffles; they contribute nothing.
+        const bool valid = tid < n_valid;
+        QState<float> s;
+        float fd[3], p0[3], v0[3];
+        load_state24(st_g, s, fd, p0, v0);
+        float reward_before = 0.f, sum = 0.f, disc = 1.f;
+        bool done_before = false;
+        const EnvConsts env_c = a.env;
+        float* ps = a.pos_stats ? a.pos_stats + (long long)env * H * 6 : nullptr;
+        for (int h = 0; h < H; ++h) {
+            const float4 r0 = *reinterpret_cast<const float4*>(sm.ref + h * 8);
+            const float4 r1 = *reinterpret_cast<const float4*>(sm.ref + h * 8 + 4);
+            const float4 f4 = *reinterpret_cast<const float4*>(sm.fds + h * 4);
+            const float pt[3] = {r0.x, r0.y, r0.z};
+            const float vt[3] = {r0.w, r1.x, r1.y};
+            const float fdh[3] = {f4.x, f4.y, f4.z};
+            // reward / done of the PRE-step state (envs/quadrotor.py:243-244)
+            float r = quad_reward(s, pt, vt);
+            bool done = quad_terminal(s, t0 + h, env_c);
+            float u[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) u[c] = sm.tile[(4 * h + c) * TSP + tid];
+            quad_step(s, u, fdh, env_c);
+            r = done_before ? reward_before : r;  // controllers/covo.py:233
+            reward_before = r;
+            done_before = done_before || done;
+            sum = fmaf(r, disc, sum);
+            disc *= a.discount;
+            if (ps) {  // debug statistics of env_state.pos after the step (covo.py:236, :281)
+                float vals[6] = {s.p[0], s.p[1], s.p[2], s.p[0] * s.p[0], s.p[1] * s.p[1], s.p[2] * s.p[2]};
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    float t = warp_sum(valid ? vals[c] : 0.f);
+                    if ((tid & 31) == 0) atomicAdd(ps + h * 6 + c, t);
+                }
+            }
+        }
+        float cost = -sum;
+        if (!valid || !(fabsf(cost) <= 3.0e38f)) cost = CUDART_INF_F;  // EXTENSION: non-finite cost -> weight 0
+        if (valid && a.costs_out) a.costs_out[(long long)env * a.n_samples + tile0 + tid] = cost;
+        sm.cost[tid] = cost;
+        float m = warp_min(cost);
+        if ((tid & 31) == 0) sm.red[tid >> 5] = m;
+    }
+    __syncthreads();
+
+    // ---------------- phase 3: tile partial + grid-wide merge ---------------------------------
+    float m_b = sm.red[0];
+#pragma unroll
+    for (int w = 1; w < TS / 32; ++w) m_b = fminf(m_b, sm.red[w]);
+    const float inv_lam = 1.0f / a.lam;
+    if (tid < TS) {
+        float c = sm.cost[tid];
+        float w = (c < CUDART_INF_F) ? expf(-(c - m_b) * inv_lam) : 0.f;
+        sm.wgt[tid] = w;
+        float sw = warp_sum(w);
+        if ((tid & 31) == 0) sm.red[8 + (tid >> 5)] = sw;
+    }
+    __syncthreads();
+    float s_b = 0.f;
+#pragma unroll
+    for (int w = 0; w < TS / 32; ++w) s_b += sm.red[8 + w];
+    const int n_cta = gridDim.x;
+    const int rec = kPartialHdr + n_pad;
+    float* part = a.partials + ((long long)env * n_cta + blockIdx.x) * rec;
+    for (int r = tid; r < n_pad; r += blockDim.x) {
+        float acc = 0.f;
+        if (r < n) {
+            const float* row = sm.tile + r * TSP;
+#pragma unroll 4
+            for (int j = 0; j < TS; ++j) {
+                int i = (j + r) & (TS - 1);  // rotated start: conflict-free across consecutive r
+                acc = fmaf(sm.wgt[i], row[i], acc);
+            }
+        }
+        part[kPartialHdr + r] = acc;
+    }
+    if (tid == 0) {
+        part[0] = m_b;
+        part[1] = s_b;
+        part[2] = 0.f;
+        part[3] = 0.f;
+    }
+    __threadfence();
+    __syncthreads();
+    __shared__ unsigned int s_ticket;
+    if (tid == 0) s_ticket = atomicAdd(a.counters + env, 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(n_cta - 1)) return;
+
+    // last CTA of this environment: merge all tile partials in tile order (bit-reproducible)
+    __threadfence();
+    const float* base = a.partials + (long long)env * n_cta * rec;
+    float* scale = sm.tile;  // the U tile is dead now; reuse it as scratch [n_cta]
+    float lm = CUDART_INF_F;
+    for (int b = tid; b < n_cta; b += blockDim.x) lm = fminf(lm, __ldcg(base + (long long)b * rec));
+    lm = warp_min(lm);
+    if ((tid & 31) == 0) sm.red[16 + (tid >> 5)] = lm;
+    __syncthreads();
+    float M = CUDART_INF_F;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) M = fminf(M, sm.red[16 + w]);
+    for (int b = tid; b < n_cta; b += blockDim.x) {
+        float mb = __ldcg(base + (long long)b * rec);
+        scale[b] = (mb < CUDART_INF_F) ? expf(-(mb - M) * inv_lam) : 0.f;
+    }
+    __syncthreads();
+    // S in tile order by one thread per 32-tile chunk would need another reduction; n_cta is small, so
+    // every thread accumulates the same ordered sum (deterministic, identical on all threads).
+    float S = 0.f;
+    for (int b = 0; b < n_cta; ++b) S = fmaf(__ldcg(base + (long long)b * rec + 1), scale[b], S);
+    for (int r = tid; r < n_pad; r += blockDim.x) {
+        float V = 0.f;
+        for (int b = 0; b < n_cta; ++b) V = fmaf(__ldcg(base + (long long)b * rec + kPartialHdr + r), scale[b], V);
+        if (a.finalize) {
+            if (r < n) {
+                // controllers/covo.py:270-278
+                float mu = sm.mu[r];
+                float nm = (S > 0.f) ? (V / S) * a.gamma_mean + mu * (1.0f - a.gamma_mean) : mu;
+                a.a_mean_out[(long long)env * n + r] = nm;
+                if (r < 4) a.action_out[(long long)env * 4 + r] = nm;
+            }
+        } else {
+            a.rank_partial[(long long)env * rec + kPartialHdr + r] = V;
+        }
+    }
+    if (tid == 0) {
+        if (!a.finalize) {
+            float* rp = a.rank_partial + (long long)env * rec;
+            rp[0] = M;
+            rp[1] = S;
+            rp[2] = 0.f;
+            rp[3] = 0.f;
+        }
+        a.counters[env] = 0u;  // re-arm for the next launch
+    }
+}
+
+// C1 epilogue: merge the per-rank (m, s, v) records gathered over NCCL, in rank order.
+__global__ void merge_ranks_kernel(const MergeArgs a) {
+    const int env = blockIdx.x;
+    const int rec = kPartialHdr + a.n_pad;
+    const float inv_lam = 1.0f / a.lam;
+    float M = CUDART_INF_F;
+    for (int w = 0; w < a.world; ++w) M = fminf(M, a.gathered[((long long)w * a.n_env + env) * rec]);
+    float S = 0.f;
+    for (int w = 0; w < a.world; ++w) {
+        const float* g = a.gathered + ((long long)w * a.n_env + env) * rec;
+        float sc = (g[0] < CUDART_INF_F) ? expf(-(g[0] - M) * inv_lam) : 0.f;
+        S = fmaf(g[1], sc, S);
+    }
+    const int H = a.n >> 2;
+    for (int r = threadIdx.x; r < a.n; r += blockDim.x) {
+        float V = 0.f;
+        for (int w = 0; w < a.world; ++w) {
+            const float* g = a.gathered + ((long long)w * a.n_env + env) * rec;
+            float sc = (g[0] < CUDART_INF_F) ? expf(-(g[0] - M) * inv_lam) : 0.f;
+            V = fmaf(g[kPartialHdr + r], sc, V);
+        }
+        int h = r >> 2, c = r & 3;
+        int hs = a.shift ? min(h + 1, H - 1) : h;
+        float mu = a.a_mean_in[(long long)env * a.n + hs * 4 + c];
+        float nm = (S > 0.f) ? (V / S) * a.gamma_mean + mu * (1.0f - a.gamma_mean) : mu;
+        a.a_mean_out[(long long)env * a.n + r] = nm;
+        if (r < 4) a.action_out[(long long)env * 4 + r] = nm;
+    }
+}
+
+cudaError_t launch_rollout(const RolloutArgs& a, int n_env, cudaStream_t st) {
+    size_t smem = rollout_smem_bytes(a.n_pad, a.mode, a.H);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    int n_cta = (a.n_samples + TS - 1) / TS;
+    dim3 grid(n_cta, n_env);
+    rollout_kernel<<<grid, kRolloutThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge(const MergeArgs& a, cudaStream_t st) {
+    merge_ranks_kernel<<<a.n_env, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace covo

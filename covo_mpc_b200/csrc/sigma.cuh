@@ -1,0 +1,37 @@
+// Internal declarations for the CoVO covariance kernels (sigma.cu).
+#pragma once
+#include "common.cuh"
+
+namespace covo {
+
+constexpr int kZoloPoles = 16;    // poles of the rational approximation of x^(-1/2)
+constexpr int kZoloLadder = 10;   // spectral-ratio ladder: M/m = 4^(4+i), i = 0..9
+constexpr int kSigmaMaxN = 224;   // n = 4H limit of the shared-memory resident kernels (H <= 56)
+constexpr double kCovoOffset = 1e-2;  // "offset = -min_eign + 1e-2", controllers/covo.py:120-121
+
+struct SigmaArgs {
+    int n, n_pad;
+    float sample_sigma;
+    const float* R;      // [E][n][n]
+    float* Vh;           // [E][n][n]  row k = Householder vector v_k (zeros for index <= k, v[k+1] = 1)
+    float* tau;          // [E][n]
+    float* F;            // [E][n][n]  exp(log_const/2) * (T - lam_min + offset)^(-1/2)
+    float* Z;            // [E][n][n]  Q F
+    float* cov;          // [E][n][n]  Sigma = Q F Q^T (symmetrised)          -> a_cov
+    float* L;            // [E][n][n]  optional: lower Cholesky factor, row-major
+    float* Lt;           // [E][lt_size]  packed k-major factor for the sampler
+    double* diag;        // [E][4][n]: d, e, then (lam_min, gersh_lo, gersh_hi, logdet, ladder idx) for tests
+    const double* zolo;  // [kZoloLadder][2][kZoloPoles]  shifts t_j, weights w_j (host-computed)
+    int* status;         // [E]  0 ok, 1 spectral ratio beyond ladder, 2 Cholesky breakdown
+    long long lt_stride;
+};
+
+// host: Zolotarev/Hale-Higham-Trefethen nodes for x^(-1/2) on [m, M]
+void zolotarev_nodes(double m, double M, int N, double* t, double* w);
+void zolotarev_table(double* table /* [kZoloLadder][2][kZoloPoles] */);
+double zolotarev_ladder_M(int i);
+
+cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st);     // R -> cov
+cudaError_t launch_cholesky(const SigmaArgs& a, int n_env, cudaStream_t st);  // cov -> L, Lt (and symmetrise cov)
+
+}  // namespace covo

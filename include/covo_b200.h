@@ -1,0 +1,146 @@
+/* covo_b200.h -- C-ABI of the B200-native CoVO-MPC / MPPI inner loop.
+ *
+ * This is the drop-in boundary for the controller hot path of LeCAR-Lab/CoVO-MPC
+ * (reference paths are relative to the reference checkout):
+ *
+ *   covo_create / covo_destroy     <-> CoVOController.__init__ / MPPIController.__init__
+ *                                      quadjax/controllers/covo.py:26-114, mppi.py:22-26,
+ *                                      constants chosen by get_controller, envs/quadrotor.py:670-752
+ *   covo_step / covo_step_device   <-> CoVOController.__call__  controllers/covo.py:187-283
+ *                                      MPPIController.__call__  controllers/mppi.py:28-134
+ *   covo_reset_offline             <-> reset_a_cov_offline      controllers/covo.py:58-104
+ *   covo_hessian                   <-> CoVOController.get_hessian      controllers/covo.py:134-185
+ *   covo_optimize_sigma            <-> CoVOController.optimize_sigma   controllers/covo.py:116-132
+ *   covo_cholesky                  <-> the factorisation inside jax.random.multivariate_normal
+ *                                      (controllers/covo.py:216, mppi.py:59)
+ *   covo_rollout                   <-> sample + rollout + softmax update, controllers/covo.py:212-278
+ *
+ * Plain pointers and sizes only; no torch / CUDA types in the signatures (a stream is a void*).
+ * Every function returns 0 on success, non-zero on failure; covo_last_error() gives the reason.
+ * The reference raises NotImplementedError / AssertionError for bad arguments
+ * (envs/quadrotor.py:751, controllers/covo.py:45-47, :114); the Python host maps the codes below
+ * to the same exception types.
+ *
+ * Ownership: the handle owns its device workspace.  Buffers passed in are caller-owned and never
+ * freed or retained beyond the call (except by the *_device variants, which read them on the given
+ * stream).  One handle <-> one device <-> one stream at a time; calls on one handle are not
+ * thread-safe, distinct handles are independent.
+ *
+ * Layouts (all float32, C order):
+ *   state24   [E][24]: pos(3) quat xyzw(4) vel(3) omega(3) f_disturb(3) pos_tar(3) vel_tar(3) pad(2)
+ *             -- the "noisy_state" the reference controllers plan from (controllers/covo.py:198)
+ *   time      [E] int32: env_state.time
+ *   a_mean    [E][H][4]      a_cov (CoVO) [E][4H][4H]      a_cov (MPPI) [E][H][4][4]
+ *   eps       [E][N_local][4H]  standard normal draws ("parity mode": the caller supplies what
+ *             jax.random.normal would have drawn); NULL = in-kernel counter RNG ("production mode")
+ *   reference trajectory  pos/vel/acc [E][T][3]   (dynamics/utils.py:49-53, 87-130, 183-251)
+ */
+#ifndef COVO_B200_H
+#define COVO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COVO_OK 0
+#define COVO_ERR_INVALID 1        /* bad argument (reference: AssertionError / ValueError) */
+#define COVO_ERR_NOT_IMPLEMENTED 2 /* unsupported mode / option (reference: NotImplementedError) */
+#define COVO_ERR_CUDA 3           /* CUDA runtime failure; message carries cudaGetErrorString */
+#define COVO_ERR_NUMERIC 4        /* spectral range beyond the rational table, Cholesky breakdown */
+
+#define COVO_MODE_MPPI 0
+#define COVO_MODE_COVO_ONLINE 1
+#define COVO_MODE_COVO_OFFLINE 2
+
+typedef struct covo_handle covo_handle;
+
+typedef struct covo_config {
+    int mode;       /* COVO_MODE_* */
+    int n_samples;  /* N, global number of sampled control sequences (reference default 8192) */
+    int horizon;    /* H (reference default 32); u_dim is 4 */
+    int n_env;      /* environments batched behind this handle (reference: 1) */
+    int traj_len;   /* rows T of the reference trajectory (300 / 320 / 350) */
+    int device;     /* CUDA device ordinal */
+    int rank;       /* N-sharding: this handle rolls samples [rank*N/world, (rank+1)*N/world) */
+    int world;
+    float lam;           /* temperature (reference default 0.01) */
+    float sample_sigma;  /* sigma (0.5) */
+    float gamma_mean;    /* 1.0 */
+    float gamma_sigma;   /* 0.0 (MPPI covariance update; only 0 is implemented) */
+    float discount;      /* 1.0 */
+    /* EnvParams3D, quadjax/dynamics/dataclass.py:40-100 */
+    float m, g, max_thrust, dt, alpha_bodyrate, action_scale, pos_limit;
+    float max_omega[3];
+    int max_steps_in_episode;
+    unsigned long long seed; /* production-mode RNG key */
+} covo_config;
+
+/* Fill *cfg with the reference defaults (get_controller with controller_params == "",
+ * envs/quadrotor.py:671-683, and EnvParams3D defaults). */
+int covo_default_config(covo_config* cfg);
+
+int covo_create(const covo_config* cfg, covo_handle** out);
+int covo_destroy(covo_handle* h);
+const char* covo_last_error(void);
+const char* covo_version(void);
+
+/* Reference trajectory held in the env state (EnvState3D.pos_traj / vel_traj / acc_traj). Host
+ * pointers, [E][T][3]; acc may be NULL (zeros). */
+int covo_set_reference(covo_handle* h, const float* pos_traj, const float* vel_traj, const float* acc_traj);
+
+/* control_params.a_mean / a_cov accessors (host pointers). */
+int covo_set_mean(covo_handle* h, const float* a_mean);
+int covo_get_mean(covo_handle* h, float* a_mean);
+int covo_set_cov(covo_handle* h, const float* a_cov); /* MPPI: [E][H][4][4]; CoVO: [E][4H][4H] (factorised on device) */
+int covo_get_cov(covo_handle* h, float* a_cov);
+/* CoVO-offline table a_cov_offline [T_sched][4H][4H] (E == 1); factorised on device in one batch. */
+int covo_set_cov_offline(covo_handle* h, const float* table, int t_sched);
+int covo_get_cov_offline(covo_handle* h, float* table, int t_sched);
+/* Build the table on device: PID expansion policy closed loop + nominal rollouts + Hessian + sigma,
+ * as controllers/covo.py:58-104 with disturb_type == "none".  state24/time: the reset state. */
+int covo_reset_offline(covo_handle* h, const float* state24, const int* time, int t_sched);
+
+/* One MPC step for all E environments.  Host buffers; H2D of (state24, time[, eps]) and D2H of the
+ * action happen inside the call, which returns after the stream is idle.  eps may be NULL. */
+int covo_step(covo_handle* h, const float* state24, const int* time, const float* eps, float* action);
+/* Same, device pointers, asynchronous on `stream` (a cudaStream_t passed as void*). */
+int covo_step_device(covo_handle* h, const float* state24_dev, const int* time_dev, const float* eps_dev,
+                     float* action_dev, void* stream);
+
+/* N-sharded step (world > 1): phase A leaves this rank's (min cost, sum w, sum w*u) record, 4 + n_pad
+ * floats per environment, in the buffer returned by covo_partial_buffer(); the caller all-gathers the
+ * records of all ranks (NCCL, rank order) and calls phase B on every rank. */
+int covo_step_partial_device(covo_handle* h, const float* state24_dev, const int* time_dev, const float* eps_dev,
+                             void* stream);
+int covo_partial_buffer(covo_handle* h, float** dev_ptr, int* n_floats);
+int covo_step_merge_device(covo_handle* h, const float* gathered_dev, float* action_dev, void* stream);
+
+/* Operators, exposed on their own for parity tests (host pointers, synchronous). */
+int covo_hessian(covo_handle* h, const float* state24, const int* time, const float* a_mean, int shift, float* R);
+int covo_optimize_sigma(covo_handle* h, const float* R, float* a_cov);
+int covo_cholesky(covo_handle* h, const float* a_cov, float* L);
+/* sample + rollout + softmax update with an explicit covariance factor source:
+ *   uses the handle's current factor (set by covo_set_cov / covo_optimize_sigma+covo_cholesky).
+ * Optional outputs may be NULL: costs [E][N_local], samples [E][N_local][4H]. */
+int covo_rollout(covo_handle* h, const float* state24, const int* time, const float* a_mean, int shift,
+                 const float* eps, const float* fdist_seq, float* a_mean_out, float* action, float* costs,
+                 float* samples);
+
+/* Debug / introspection. */
+int covo_get_pos_stats(covo_handle* h, float* pos_mean, float* pos_std); /* info dict, controllers/covo.py:281; [E][H][3] each */
+int covo_enable_pos_stats(covo_handle* h, int on);
+int covo_debug_eps(covo_handle* h, unsigned int stream_id, float* eps);  /* the production-mode field, [N_local][4H] */
+int covo_debug_tridiag(covo_handle* h, double* d, double* e, double* scalars5); /* after covo_optimize_sigma, env 0 */
+int covo_zolotarev_nodes(double m, double M, int n_poles, double* shifts, double* weights); /* host only, no GPU */
+int covo_get_status(covo_handle* h, int* status); /* [E] numeric status of the last covariance step */
+/* Per-kernel device time of the last instrumented step, CUDA events on the launch stream.
+ * slots: 0 hessian-local, 1 hessian-assemble, 2 tridiag+rational, 3 apply-Q (both), 4 cholesky, 5 rollout */
+int covo_set_profiling(covo_handle* h, int on);
+int covo_get_kernel_ms(covo_handle* h, float* ms6);
+int covo_rng_step(covo_handle* h, unsigned int* stream_id); /* counter of production-mode draws so far */
+int covo_local_samples(covo_handle* h, int* n_local, int* offset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COVO_B200_H */
