@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- MPC control steps/sec of the CoVO-MPC hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+
+Workload (config.workload): CoVO-online, tracking_zigzag, N=8192 samples, H=50, u_dim=4 -- BASELINE.json's
+headline single-GPU configuration.  One "step" = one controller call (shift -> exact Hessian -> optimize_sigma
+-> Cholesky -> sample -> N x H rollout -> softmax update) for one environment, driven over the noisy states of
+a closed-loop episode recorded beforehand (synthetic zigzag reference trajectory, observation noise as in
+envs/quadrotor.py:323-351).
+
+  value  : states / times resident in HBM, covo_step_device on the launch stream, CUDA events per step,
+           L2 flushed (256 MiB memset) between steps and excluded from the timing.
+  e2e    : the same steps through the reference-facing plugin call controller(obs, state, params, rng,
+           control_params, info) with HOST numpy state: H2D (pinned) + kernels + D2H inside the timed region.
+  N > 1  : one process per GPU (torch.distributed / NCCL for barrier + max-over-ranks); default is one
+           independent environment per rank (no data-path collective, weak scaling).  --shard nsample splits
+           the N samples of ONE environment across ranks with one all-gather of 808 B per rank per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SAMPLES, HORIZON, LAM, TASK = 8192, 50, 0.01, "tracking_zigzag"
+METRIC, UNIT = "mpc_control_steps_per_sec", "steps/s"
+
+
+# ---------------------------------------------------------------------------------------------------
+def record_states(n_states: int, seed: int, controller_name="covo-online", N=1024):
+    """Closed-loop episode (untimed, smaller N) to obtain a realistic sequence of noisy states."""
+    import covo_mpc_b200 as cm
+
+    env = cm.Quad3D(TASK)
+    ctl, _ = cm.get_controller(env, controller_name, f"N{N}_H{HORIZON}_lam{LAM}", seed=seed)
+    rec = []
+    rng = np.random.default_rng(seed)
+    while len(rec) < n_states:
+        cm.run_episode(env, ctl, rng, n_steps=min(290, n_states - len(rec)), record=rec, reset_rng=np.random.default_rng(seed))
+    traj = ctl._ref_keepalive
+    ctl.close()
+    states = np.stack([r[0] for r in rec[:n_states]]).astype(np.float32)
+    times = np.array([r[1] for r in rec[:n_states]], dtype=np.int32)
+    return env, states, times, traj
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(n, H, N, parity=False):
+    """SURVEY 8(d) / DESIGN.md: mandatory HBM bytes per MPC step, per kernel."""
+    nn = 4 * n * n
+    rollout = nn // 2 + 4 * 4 * n + 4 * (H + 1) * 6 + 96 + 2 * 4 * n + (4 * N * n if parity else 0)
+    return {
+        "hessian": 96 + 4 * n + 4 * H * 6 + 2 * 4 * H * (14 * 153 + 14 * 17) + nn,  # state, mean, ref; workspace w+r; R
+        "sigma": nn + nn + 4 * n + nn + 2 * (2 * nn),  # R in; Vh, tau, F out; two apply-Q passes (read F/Z + Vh, write Z/cov)
+        "cholesky": nn + nn + nn + nn // 2,  # cov in, symmetrised cov out, L out, packed factor out
+        "rollout": rollout,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import covo_mpc_b200 as cm
+    from covo_mpc_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+    shard = args.shard if world > 1 else "env"
+    n_states = W + K
+    seed = 100 + (rank if shard == "env" else 0)
+    mode_name = "covo-offline" if shard == "nsample" else args.controller
+    env, states_h, times_h, traj = record_states(n_states, seed, "covo-online" if mode_name != "mppi" else "mppi")
+
+    cfg = _lib.default_config()
+    cfg.mode = {"covo-online": _lib.MODE_COVO_ONLINE, "covo-offline": _lib.MODE_COVO_OFFLINE, "mppi": _lib.MODE_MPPI}[mode_name]
+    cfg.n_samples, cfg.horizon, cfg.traj_len, cfg.device = N_SAMPLES, HORIZON, int(traj[0].shape[0]), local_rank
+    cfg.lam, cfg.seed = LAM, seed
+    if shard == "nsample":
+        cfg.rank, cfg.world = rank, world
+    h = _lib.Handle(cfg)
+    h.set_reference(traj[0][None], traj[1][None])
+    if cfg.mode == _lib.MODE_COVO_OFFLINE:
+        h.reset_offline(states_h[0], [0], 300)
+    states = torch.from_numpy(states_h).to(dev)
+    times = torch.from_numpy(times_h).to(dev)
+    actions = torch.zeros((n_states, 4), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+    gathered = None
+    if shard == "nsample":
+        pbuf, pn = h.partial_buffer()
+        gathered = torch.zeros((world, pn), dtype=torch.float32, device=dev)
+        part_view = None
+
+    def one_step(i):
+        sp, tp, ap = states.data_ptr() + 96 * i, times.data_ptr() + 4 * i, actions.data_ptr() + 16 * i
+        if shard == "nsample":
+            h.step_partial_device(sp, tp, 0, stream)
+            # 808 B per rank: all-gather of (min cost, sum w, sum w*u) records, then the merge kernel
+            src = _as_tensor(pbuf, pn, dev)
+            dist.all_gather_into_tensor(gathered.view(-1), src)
+            h.step_merge_device(gathered.data_ptr(), ap, stream)
+        else:
+            h.step_device(sp, tp, 0, ap, stream)
+
+    def _as_tensor(ptr, n, dev):
+        nonlocal part_view
+        if part_view is None:
+            class _W:  # __cuda_array_interface__ view of the library-owned partial buffer
+                __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+            part_view = torch.as_tensor(_W(), device=dev)
+        return part_view
+
+    for i in range(W):
+        one_step(i)
+    torch.cuda.synchronize()
+    # per-kernel device time (instrumented pass, not the timed one)
+    kernel_ms = None
+    if shard == "env" and cfg.mode != _lib.MODE_MPPI:
+        h.set_profiling(True)
+        acc = np.zeros(6)
+        reps = min(10, K)
+        for i in range(reps):
+            flush.zero_()
+            one_step(W + i)
+            acc += h.kernel_ms()
+        kernel_ms = acc / reps
+        h.set_profiling(False)
+        # restart the controller state so the timed pass sees the same sequence again
+        h.set_mean(np.tile(np.array([(0.027 * 9.81 / 0.8) * 2 - 1, 0, 0, 0], np.float32), (1, HORIZON, 1)))
+        for i in range(W):
+            one_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()  # L2 flush, outside the event pair
+        ev[i][0].record()
+        one_step(W + i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = float(step_ms.sum())
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    units = K * (world if shard == "env" else 1)
+    value = units / (total_ms_max / 1e3)
+    acts = actions[W:W + K].cpu().numpy()
+    assert np.isfinite(acts).all(), "non-finite actions"
+
+    # ---- e2e through the plugin surface with host buffers -------------------------------------------
+    e2e = None
+    if shard == "env":
+        ctl, cp = cm.get_controller(env, mode_name, f"N{N_SAMPLES}_H{HORIZON}_lam{LAM}", device=local_rank, seed=seed)
+        f32 = np.float32
+        st0 = cm.EnvState3D(pos=np.zeros(3, f32), vel=np.zeros(3, f32), quat=np.array([0, 0, 0, 1], f32), omega=np.zeros(3, f32),
+                            pos_traj=traj[0], vel_traj=traj[1], acc_traj=np.zeros_like(traj[0]), pos_tar=np.zeros(3, f32),
+                            vel_tar=np.zeros(3, f32), acc_tar=np.zeros(3, f32), time=0, f_disturb=np.zeros(3, f32))
+
+        def mk(i):
+            s = states_h[i]
+            return st0.replace(pos=s[0:3], quat=s[3:7], vel=s[7:10], omega=s[10:13], f_disturb=s[13:16], pos_tar=s[16:19],
+                               vel_tar=s[19:22], time=int(times_h[i]))
+
+        host_states = [mk(i) for i in range(n_states)]
+        if mode_name == "covo-offline":
+            cp = ctl.reset(host_states[0], env.default_params, cp, None)
+        for i in range(W):
+            _, cp, _ = ctl(None, host_states[i], env.default_params, None, cp, {"noisy_state": host_states[i]})
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            act, cp, _ = ctl(None, host_states[W + i], env.default_params, None, cp, {"noisy_state": host_states[W + i]})
+        torch.cuda.synchronize()
+        te = time.perf_counter() - t0
+        tt = torch.tensor([te], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": K * world / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": 24 * 4 + 4, "d2h_bytes_per_step": 16,
+               "ms_per_step": 1e3 * float(tt.item()) / K}
+        ctl.close()
+
+    launches_per_step = {"covo-online": 7, "covo-offline": 1, "mppi": 2}[mode_name] + (1 if shard == "nsample" else 0)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak" if shard == "env" else "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{mode_name} {TASK} N={N_SAMPLES} H={HORIZON} u_dim=4 lam={LAM} sigma=0.5, 1 env per GPU"
+                   if shard == "env" else f"covo-offline tracking_zigzag N={N_SAMPLES} H={HORIZON} N-sharded over {world} GPUs",
+                   "controller": mode_name, "n_samples": N_SAMPLES, "horizon": HORIZON, "envs_per_gpu": 1,
+                   "parallelism": ("env-replicas x%d (no collective)" % world) if shard == "env" else "nsample-shard x%d (allgather 808B/rank/step)" % world,
+                   "rng": "in-kernel Philox (production mode)", "l2": "256 MiB memset between steps, excluded from the event timing",
+                   "timing": "CUDA events per step on the launch stream, sum over K steps, max over ranks"},
+        "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
+        "step_ms_p50": float(np.median(step_ms)), "step_ms_p99": float(np.percentile(step_ms, 99)),
+        "gpu_launches": launches_per_step * K, "clocks": clocks,
+    }
+    if e2e:
+        out["e2e"] = e2e
+    # ---- roofline ---------------------------------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    n = 4 * HORIZON
+    ab = algorithmic_bytes(n, HORIZON, N_SAMPLES)
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+    if kernel_ms is not None:
+        per = {"hessian": kernel_ms[0], "sigma": kernel_ms[2], "cholesky": kernel_ms[4], "rollout": kernel_ms[5]}
+        dom = max(per, key=per.get)
+        rl = {}
+        for k, ms in per.items():
+            ach = ab[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            rl[k] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(k),
+                     "ms": float(ms), "algorithmic_bytes": ab[k], "share_of_step": float(ms / sum(per.values()))}
+        out["roofline"] = dict(rl[dom], kernel=dom, peak_source=peak_src,
+                               note="latency-bound serial factorisation by construction (SURVEY 8d): HBM traffic is ~0.5 MB per step")
+        out["roofline_kernels"] = rl
+        flops = N_SAMPLES * n * (n + 1) + N_SAMPLES * HORIZON * 200 + 2 * N_SAMPLES * n
+        out["rollout_fp32"] = {"algorithmic_gflop": flops / 1e9, "achieved_tflops": flops / (per["rollout"] * 1e-3) / 1e12,
+                               "nominal_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12}
+    elif cfg.mode != _lib.MODE_COVO_ONLINE or shard != "env":
+        ms = total_ms_max / K
+        ach = ab["rollout"] / (ms * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                           "traffic": traffic.get("rollout"), "kernel": "rollout", "peak_source": peak_src}
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(states_h, times_h, traj, budget_s=args.cpu_budget, mode_name=mode_name)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_baseline(states_h, times_h, traj, budget_s=20.0, mode_name="covo-online", max_steps=None, warmup=0):
+    """The reference algorithm (oracle/ port) on the host CPU: full MPC steps on the same recorded states."""
+    from oracle import oracle_np as o
+
+    try:
+        from oracle import oracle_c
+
+        fast = oracle_c.available()
+    except Exception:
+        fast = False
+    p = o.EnvParams()
+    a_mean = o.hover_mean(HORIZON, p)
+    rng = np.random.default_rng(0)
+    n = 4 * HORIZON
+    t_used, done = 0.0, 0
+    i = 0
+    cores = os.cpu_count() if fast else 1
+    a_cov = None
+    while True:
+        s = states_h[i % len(states_h)]
+        ns = o.make_state(s[0:3], s[3:7], s[7:10], s[10:13], s[13:16], int(times_h[i % len(times_h)]), traj[0], traj[1], s[16:19],
+                          s[19:22], dtype=np.float32)
+        eps = rng.standard_normal((N_SAMPLES, n)).astype(np.float32)
+        t0 = time.perf_counter()
+        if fast:
+            _, a_mean = oracle_c.covo_step(ns, a_mean, eps, p, LAM, online=(mode_name == "covo-online"), a_cov=a_cov)
+        else:
+            if mode_name == "covo-online" or a_cov is None:
+                _, a_mean, a_cov, _ = o.covo_call(ns, a_mean, eps, p, lam=LAM, hessian_dtype=np.float32)
+            else:
+                _, a_mean, a_cov, _ = o.covo_call(ns, a_mean, eps, p, lam=LAM, a_cov=a_cov)
+        dt = time.perf_counter() - t0
+        i += 1
+        if i <= warmup:
+            continue
+        t_used += dt
+        done += 1
+        if (max_steps is not None and done >= max_steps) or (max_steps is None and t_used >= budget_s) or t_used > 170.0:
+            break
+    return {"value": done / t_used, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{done} full MPC steps ({mode_name}, N={N_SAMPLES}, H={HORIZON}) of the oracle restatement "
+                      f"({'C/OpenMP + LAPACK' if fast else 'NumPy float32 + LAPACK eigh'}); JAX is not installable here",
+            "steps": done, "seconds": t_used}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    # states: a fixed synthetic sequence (no GPU needed): hover-ish noisy states along a zigzag reference
+    from oracle import oracle_np as o
+
+    p = o.EnvParams()
+    rng = np.random.default_rng(100)
+    s = o.reset_env(TASK, p, rng, dtype=np.float32, zero_disturb=True)
+    states, times = [], []
+    hover = o.hover_mean(1, p)[0]
+    for _ in range(32):
+        ns = o.noisy_state(s, p, rng)
+        states.append(o.state_to_vec24(ns))
+        times.append(ns.time)
+        s, _, _, _ = o.env_step(s, hover + rng.normal(0, 0.1, 4), p, rng, "none")
+    cb = cpu_baseline(np.stack(states), np.array(times), (s.pos_traj, s.vel_traj), mode_name=args.controller, max_steps=K, warmup=W)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": cb["steps"],
+           "warmup": W, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{args.controller} {TASK} N={N_SAMPLES} H={HORIZON} u_dim=4 lam={LAM} sigma=0.5, 1 env",
+                      "note": "CPU restatement of the reference algorithm (JAX cannot be installed offline); timed steps capped at ~170 s"},
+           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--controller", default="covo-online", choices=["covo-online", "covo-offline", "mppi"])
+    ap.add_argument("--shard", default="env", choices=["env", "nsample"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 60:
+            args.steps = 60  # bounded sample: each step is one full N=8192, H=50 MPC step on the CPU
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,322 @@
+"""ctypes binding of libcovo_b200.so (include/covo_b200.h).
+
+The library is the product; there is no CPU implementation behind it.  Loading fails loudly if the
+shared object is missing, and ``Handle`` creation fails loudly if no CUDA device is visible.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcovo_b200.so")
+
+MODE_MPPI, MODE_COVO_ONLINE, MODE_COVO_OFFLINE = 0, 1, 2
+ERR_INVALID, ERR_NOT_IMPLEMENTED, ERR_CUDA, ERR_NUMERIC = 1, 2, 3, 4
+
+
+class CovoConfig(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int), ("n_samples", C.c_int), ("horizon", C.c_int), ("n_env", C.c_int),
+        ("traj_len", C.c_int), ("device", C.c_int), ("rank", C.c_int), ("world", C.c_int),
+        ("lam", C.c_float), ("sample_sigma", C.c_float), ("gamma_mean", C.c_float),
+        ("gamma_sigma", C.c_float), ("discount", C.c_float),
+        ("m", C.c_float), ("g", C.c_float), ("max_thrust", C.c_float), ("dt", C.c_float),
+        ("alpha_bodyrate", C.c_float), ("action_scale", C.c_float), ("pos_limit", C.c_float),
+        ("max_omega", C.c_float * 3), ("max_steps_in_episode", C.c_int),
+        ("seed", C.c_ulonglong),
+    ]
+
+
+class CovoCudaError(RuntimeError):
+    pass
+
+
+class CovoNumericError(ArithmeticError):
+    pass
+
+
+_lib: Optional[C.CDLL] = None
+
+_F = C.POINTER(C.c_float)
+_I = C.POINTER(C.c_int)
+_D = C.POINTER(C.c_double)
+_H = C.c_void_p
+
+_SIGNATURES = {
+    "covo_default_config": [C.POINTER(CovoConfig)],
+    "covo_create": [C.POINTER(CovoConfig), C.POINTER(_H)],
+    "covo_destroy": [_H],
+    "covo_set_reference": [_H, _F, _F, _F],
+    "covo_set_mean": [_H, _F],
+    "covo_get_mean": [_H, _F],
+    "covo_set_cov": [_H, _F],
+    "covo_get_cov": [_H, _F],
+    "covo_set_cov_offline": [_H, _F, C.c_int],
+    "covo_get_cov_offline": [_H, _F, C.c_int],
+    "covo_reset_offline": [_H, _F, _I, C.c_int],
+    "covo_step": [_H, _F, _I, _F, _F],
+    "covo_step_device": [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    "covo_step_partial_device": [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    "covo_partial_buffer": [_H, C.POINTER(C.c_void_p), _I],
+    "covo_step_merge_device": [_H, C.c_void_p, C.c_void_p, C.c_void_p],
+    "covo_hessian": [_H, _F, _I, _F, C.c_int, _F],
+    "covo_optimize_sigma": [_H, _F, _F],
+    "covo_cholesky": [_H, _F, _F],
+    "covo_rollout": [_H, _F, _I, _F, C.c_int, _F, _F, _F, _F, _F, _F],
+    "covo_get_pos_stats": [_H, _F, _F],
+    "covo_enable_pos_stats": [_H, C.c_int],
+    "covo_debug_eps": [_H, C.c_uint, _F],
+    "covo_debug_tridiag": [_H, _D, _D, _D],
+    "covo_zolotarev_nodes": [C.c_double, C.c_double, C.c_int, _D, _D],
+    "covo_get_status": [_H, _I],
+    "covo_set_profiling": [_H, C.c_int],
+    "covo_get_kernel_ms": [_H, _F],
+    "covo_rng_step": [_H, C.POINTER(C.c_uint)],
+    "covo_local_samples": [_H, _I, _I],
+}
+EXPORTED = sorted(list(_SIGNATURES) + ["covo_last_error", "covo_version"])
+
+
+def load() -> C.CDLL:
+    """Load the shared library (built in-tree by covo_mpc_b200/build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m covo_mpc_b200.build` (nvcc, sm_100a). "
+            "covo_mpc_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.covo_last_error.restype = C.c_char_p
+    lib.covo_last_error.argtypes = []
+    lib.covo_version.restype = C.c_char_p
+    lib.covo_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    """Map C status codes to the exception types the reference raises for the same conditions."""
+    if rc == 0:
+        return
+    msg = load().covo_last_error().decode("utf-8", "replace")
+    if rc == ERR_INVALID:
+        raise ValueError(msg)
+    if rc == ERR_NOT_IMPLEMENTED:
+        raise NotImplementedError(msg)  # envs/quadrotor.py:751, controllers/covo.py:114
+    if rc == ERR_NUMERIC:
+        raise CovoNumericError(msg)
+    raise CovoCudaError(msg)
+
+
+def f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def fptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_F)
+
+
+def iptr(a: np.ndarray):
+    return a.ctypes.data_as(_I)
+
+
+def default_config() -> CovoConfig:
+    cfg = CovoConfig()
+    check(load().covo_default_config(C.byref(cfg)))
+    return cfg
+
+
+class Handle:
+    """Owner of one ``covo_handle`` (one device, one stream)."""
+
+    def __init__(self, cfg: CovoConfig):
+        self.lib = load()
+        self.cfg = cfg
+        self._h = _H()
+        check(self.lib.covo_create(C.byref(cfg), C.byref(self._h)))
+        self.H = cfg.horizon
+        self.n = 4 * cfg.horizon
+        self.E = cfg.n_env
+        nl, off = C.c_int(), C.c_int()
+        check(self.lib.covo_local_samples(self._h, C.byref(nl), C.byref(off)))
+        self.n_local, self.sample_offset = nl.value, off.value
+
+    def close(self):
+        if self._h:
+            self.lib.covo_destroy(self._h)
+            self._h = _H()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- control params -----------------------------------------------------------------------
+    def set_reference(self, pos, vel, acc=None):
+        pos, vel = f32(pos), f32(vel)
+        acc = None if acc is None else f32(acc)
+        exp = (self.E * self.cfg.traj_len * 3,)
+        if pos.size != exp[0] or vel.size != exp[0]:
+            raise ValueError(f"reference trajectory must have {self.E}x{self.cfg.traj_len}x3 entries")
+        check(self.lib.covo_set_reference(self._h, fptr(pos), fptr(vel), fptr(acc)))
+
+    def set_mean(self, a_mean):
+        a = f32(a_mean)
+        if a.size != self.E * self.n:
+            raise ValueError("a_mean has the wrong size")
+        check(self.lib.covo_set_mean(self._h, fptr(a)))
+
+    def get_mean(self) -> np.ndarray:
+        out = np.empty((self.E, self.H, 4), dtype=np.float32)
+        check(self.lib.covo_get_mean(self._h, fptr(out)))
+        return out
+
+    def cov_shape(self):
+        return (self.E, self.H, 4, 4) if self.cfg.mode == MODE_MPPI else (self.E, self.n, self.n)
+
+    def set_cov(self, a_cov):
+        a = f32(a_cov)
+        if a.size != int(np.prod(self.cov_shape())):
+            raise ValueError("a_cov has the wrong size")
+        check(self.lib.covo_set_cov(self._h, fptr(a)))
+
+    def get_cov(self) -> np.ndarray:
+        out = np.empty(self.cov_shape(), dtype=np.float32)
+        check(self.lib.covo_get_cov(self._h, fptr(out)))
+        return out
+
+    def set_cov_offline(self, table):
+        t = f32(table)
+        check(self.lib.covo_set_cov_offline(self._h, fptr(t), int(t.shape[0])))
+
+    def get_cov_offline(self, t_sched: int) -> np.ndarray:
+        out = np.empty((t_sched, self.n, self.n), dtype=np.float32)
+        check(self.lib.covo_get_cov_offline(self._h, fptr(out), t_sched))
+        return out
+
+    def reset_offline(self, state24, time, t_sched: int):
+        s, t = f32(state24), i32(time)
+        check(self.lib.covo_reset_offline(self._h, fptr(s), iptr(t), t_sched))
+
+    # -- the MPC step -----------------------------------------------------------------------------
+    def step(self, state24, time, eps=None) -> np.ndarray:
+        s, t = f32(state24), i32(time)
+        if s.size != self.E * 24 or t.size != self.E:
+            raise ValueError("state24 / time have the wrong size")
+        e = None
+        if eps is not None:
+            e = f32(eps)
+            if e.size != self.E * self.n_local * self.n:
+                raise ValueError("eps must be [E][N_local][4H]")
+        out = np.empty((self.E, 4), dtype=np.float32)
+        check(self.lib.covo_step(self._h, fptr(s), iptr(t), fptr(e), fptr(out)))
+        return out
+
+    def step_device(self, state24_ptr: int, time_ptr: int, eps_ptr: int, action_ptr: int, stream: int = 0):
+        check(self.lib.covo_step_device(self._h, state24_ptr, time_ptr, eps_ptr or None, action_ptr, stream or None))
+
+    def step_partial_device(self, state24_ptr: int, time_ptr: int, eps_ptr: int, stream: int = 0):
+        check(self.lib.covo_step_partial_device(self._h, state24_ptr, time_ptr, eps_ptr or None, stream or None))
+
+    def partial_buffer(self):
+        p, n = C.c_void_p(), C.c_int()
+        check(self.lib.covo_partial_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def step_merge_device(self, gathered_ptr: int, action_ptr: int, stream: int = 0):
+        check(self.lib.covo_step_merge_device(self._h, gathered_ptr, action_ptr, stream or None))
+
+    # -- operators -------------------------------------------------------------------------------
+    def hessian(self, state24, time, a_mean, shift: bool = False) -> np.ndarray:
+        s, t, a = f32(state24), i32(time), f32(a_mean)
+        out = np.empty((self.E, self.n, self.n), dtype=np.float32)
+        check(self.lib.covo_hessian(self._h, fptr(s), iptr(t), fptr(a), int(shift), fptr(out)))
+        return out
+
+    def optimize_sigma(self, R) -> np.ndarray:
+        r = f32(R)
+        if r.size != self.E * self.n * self.n:
+            raise ValueError("R has the wrong size")
+        out = np.empty((self.E, self.n, self.n), dtype=np.float32)
+        check(self.lib.covo_optimize_sigma(self._h, fptr(r), fptr(out)))
+        return out
+
+    def cholesky(self, a_cov) -> np.ndarray:
+        c = f32(a_cov)
+        out = np.empty((self.E, self.n, self.n), dtype=np.float32)
+        check(self.lib.covo_cholesky(self._h, fptr(c), fptr(out)))
+        return out
+
+    def rollout(self, state24, time, a_mean, shift=False, eps=None, fdist_seq=None, want_costs=False, want_samples=False):
+        s, t, a = f32(state24), i32(time), f32(a_mean)
+        e = None if eps is None else f32(eps)
+        fd = None if fdist_seq is None else f32(fdist_seq)
+        a_out = np.empty((self.E, self.H, 4), dtype=np.float32)
+        act = np.empty((self.E, 4), dtype=np.float32)
+        costs = np.empty((self.E, self.n_local), dtype=np.float32) if want_costs else None
+        samples = np.empty((self.E, self.n_local, self.H, 4), dtype=np.float32) if want_samples else None
+        check(self.lib.covo_rollout(self._h, fptr(s), iptr(t), fptr(a), int(shift), fptr(e), fptr(fd), fptr(a_out),
+                                    fptr(act), fptr(costs), fptr(samples)))
+        return a_out, act, costs, samples
+
+    # -- introspection ------------------------------------------------------------------------------
+    def enable_pos_stats(self, on=True):
+        check(self.lib.covo_enable_pos_stats(self._h, int(on)))
+
+    def pos_stats(self):
+        m = np.empty((self.E, self.H, 3), dtype=np.float32)
+        s = np.empty((self.E, self.H, 3), dtype=np.float32)
+        check(self.lib.covo_get_pos_stats(self._h, fptr(m), fptr(s)))
+        return m, s
+
+    def debug_eps(self, stream_id: int) -> np.ndarray:
+        out = np.empty((self.n_local, self.n), dtype=np.float32)
+        check(self.lib.covo_debug_eps(self._h, stream_id, fptr(out)))
+        return out
+
+    def debug_tridiag(self):
+        d = np.empty(self.n, dtype=np.float64)
+        e = np.empty(self.n, dtype=np.float64)
+        sc = np.empty(5, dtype=np.float64)
+        check(self.lib.covo_debug_tridiag(self._h, d.ctypes.data_as(_D), e.ctypes.data_as(_D), sc.ctypes.data_as(_D)))
+        return d, e, sc
+
+    def status(self) -> np.ndarray:
+        out = np.empty(self.E, dtype=np.int32)
+        check(self.lib.covo_get_status(self._h, iptr(out)))
+        return out
+
+    def set_profiling(self, on=True):
+        check(self.lib.covo_set_profiling(self._h, int(on)))
+
+    def kernel_ms(self) -> np.ndarray:
+        out = np.empty(6, dtype=np.float32)
+        check(self.lib.covo_get_kernel_ms(self._h, fptr(out)))
+        return out
+
+    def rng_step(self) -> int:
+        v = C.c_uint()
+        check(self.lib.covo_rng_step(self._h, C.byref(v)))
+        return v.value
+
+
+def zolotarev_nodes(m: float, M: float, n_poles: int):
+    t = np.empty(n_poles, dtype=np.float64)
+    w = np.empty(n_poles, dtype=np.float64)
+    check(load().covo_zolotarev_nodes(m, M, n_poles, t.ctypes.data_as(_D), w.ctypes.data_as(_D)))
+    return t, w

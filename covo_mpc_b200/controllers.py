@@ -1,0 +1,339 @@
+"""Host-side mirror of the reference's controller plugin surface.
+
+    controller, control_params = get_controller(env, "covo-online", "N8192_H50_lam0.01")
+    control_params = controller.reset(env_state, env_params, controller.init_control_params, key)
+    action, control_params, info = controller(obs, env_state, env_params, rng_act, control_params, env_info)
+
+is the reference's contract (quadjax/controllers/base.py:5-19; dispatch quadjax/envs/quadrotor.py:670-752;
+call sites :523-525, :548-550, :609-611, :618-620) and works unchanged here for the names
+"mppi", "covo-online" / "covo_online", "covo-offline" / "covo_offline".  Everything numeric happens in
+libcovo_b200.so (hand-written sm_100a CUDA); this module only moves a 24-float state record in and a
+4-float action out per step.  There is no CPU fallback.
+
+``rng_act`` (a JAX PRNG key in the reference):
+  * ``None`` or a 2-word uint32 key  -> production mode, Gaussian draws from the in-kernel counter RNG;
+  * a float array of standard normals, shape (N, 4H) (CoVO) or (N, H, 4) (MPPI) -> "parity mode": the
+    caller supplies exactly what ``jax.random.normal`` would have drawn (the JAX Threefry stream itself is
+    un-pinned third-party arithmetic);
+  * a ``numpy.random.Generator`` -> the draws are taken from it on the host.
+
+``control_params`` keeps the reference's functional style: the call returns a new params object.  The
+mean / covariance stay resident in HBM; the returned object materialises them lazily on attribute access.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Optional
+
+import numpy as np
+
+from . import _lib
+from .env import EnvParams3D, EnvState3D, Quad3D
+
+
+class _DeviceArray:
+    """Lazy host view of a controller-resident array, valid for one controller generation."""
+
+    def __init__(self, owner: "_SamplingController", generation: int, what: str):
+        self._owner, self._gen, self._what, self._cache = owner, generation, what, None
+
+    def _get(self) -> np.ndarray:
+        if self._cache is None:
+            if self._owner._generation != self._gen:
+                raise RuntimeError("stale control_params: the controller state has advanced past this object")
+            self._cache = self._owner._download(self._what)
+        return self._cache
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._get()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    @property
+    def shape(self):
+        return self._get().shape
+
+
+@dataclass
+class MPPIParams:
+    """quadjax/controllers/mppi.py:11-19"""
+
+    gamma_mean: float
+    gamma_sigma: float
+    discount: float
+    sample_sigma: float
+    a_mean: Any
+    a_cov: Any
+    _gen: int = field(default=-1, repr=False)
+
+    def replace(self, **kw):
+        d = dict(gamma_mean=self.gamma_mean, gamma_sigma=self.gamma_sigma, discount=self.discount,
+                 sample_sigma=self.sample_sigma, a_mean=self.a_mean, a_cov=self.a_cov)
+        d.update(kw)
+        return MPPIParams(**d)
+
+
+@dataclass
+class CoVOParams:
+    """quadjax/controllers/covo.py:13-22"""
+
+    gamma_mean: float
+    gamma_sigma: float
+    discount: float
+    sample_sigma: float
+    a_mean: Any
+    a_cov: Any
+    a_cov_offline: Any
+    _gen: int = field(default=-1, repr=False)
+
+    def replace(self, **kw):
+        d = dict(gamma_mean=self.gamma_mean, gamma_sigma=self.gamma_sigma, discount=self.discount,
+                 sample_sigma=self.sample_sigma, a_mean=self.a_mean, a_cov=self.a_cov, a_cov_offline=self.a_cov_offline)
+        d.update(kw)
+        return CoVOParams(**d)
+
+
+class BaseController:
+    """quadjax/controllers/base.py:5-19"""
+
+    def __init__(self, env, control_params) -> None:
+        self.env = env
+        self.init_control_params = control_params
+
+    def update_params(self, env_params, control_params):
+        return control_params
+
+    def reset(self, env_state=None, env_params=None, control_params=None, key=None):
+        return self.init_control_params
+
+    def __call__(self, obs, state, env_params, rng_act, control_params, env_info=None):
+        raise NotImplementedError
+
+
+class _SamplingController(BaseController):
+    _mode = -1
+
+    def __init__(self, env, control_params, N: int, H: int, lam: float, *, device: int = 0, seed: int = 0,
+                 rank: int = 0, world: int = 1) -> None:
+        super().__init__(env, control_params)
+        self.N, self.H, self.lam = int(N), int(H), float(lam)
+        self.action_dim = getattr(env, "action_dim", 4)
+        assert self.action_dim == 4, "only support 4D action space Quadrotor environment for now"  # covo.py:45-47
+        p: EnvParams3D = env.default_params
+        cfg = _lib.default_config()
+        cfg.mode = self._mode
+        cfg.n_samples, cfg.horizon, cfg.n_env = self.N, self.H, 1
+        cfg.device, cfg.rank, cfg.world = device, rank, world
+        cfg.lam = self.lam
+        cfg.sample_sigma = float(control_params.sample_sigma)
+        cfg.gamma_mean = float(control_params.gamma_mean)
+        cfg.gamma_sigma = float(control_params.gamma_sigma)
+        cfg.discount = float(control_params.discount)
+        cfg.m, cfg.g, cfg.max_thrust, cfg.dt = p.m, p.g, p.max_thrust, p.dt
+        cfg.alpha_bodyrate, cfg.action_scale, cfg.pos_limit = p.alpha_bodyrate, p.action_scale, 3.0
+        for k in range(3):
+            cfg.max_omega[k] = p.max_omega[k]
+        cfg.max_steps_in_episode = p.max_steps_in_episode
+        cfg.seed = seed
+        self._cfg = cfg
+        self._handle: Optional[_lib.Handle] = None
+        self._traj_id = None
+        self._generation = 0
+        self.want_info = False  # pos_mean / pos_std (covo.py:281) are computed only on request
+
+    # -- plumbing ---------------------------------------------------------------------------------------
+    def _ensure_handle(self, traj_len: int) -> _lib.Handle:
+        if self._handle is None or self._cfg.traj_len != traj_len:
+            if self._handle is not None:
+                self._handle.close()
+            self._cfg.traj_len = traj_len
+            self._handle = _lib.Handle(self._cfg)
+            self._traj_id = None
+            self._on_new_handle()
+        return self._handle
+
+    def _on_new_handle(self):
+        pass
+
+    def _sync_reference(self, state: EnvState3D):
+        h = self._ensure_handle(int(state.pos_traj.shape[0]))
+        tid = (id(state.pos_traj), id(state.vel_traj))
+        if tid != self._traj_id:  # trajectories change only at reset
+            h.set_reference(state.pos_traj, state.vel_traj, state.acc_traj)
+            self._traj_id = tid
+            self._ref_keepalive = (state.pos_traj, state.vel_traj)
+        return h
+
+    def _download(self, what: str) -> np.ndarray:
+        h = self._handle
+        if what == "a_mean":
+            return h.get_mean()[0]
+        if what == "a_cov":
+            return h.get_cov()[0]
+        raise KeyError(what)
+
+    def _upload_params(self, control_params):
+        if getattr(control_params, "_gen", -1) == self._generation:
+            return  # the object we returned last time: the state is already resident
+        self._handle.set_mean(np.asarray(control_params.a_mean, dtype=np.float32).reshape(1, self.H, 4))
+        self._upload_cov(control_params)
+
+    def _upload_cov(self, control_params):
+        pass
+
+    def _eps(self, rng_act, shape):
+        if rng_act is None:
+            return None
+        if isinstance(rng_act, np.random.Generator):
+            return rng_act.standard_normal(shape).astype(np.float32)
+        a = np.asarray(rng_act)
+        if a.dtype.kind == "u" and a.size == 2:
+            return None  # a JAX-style key: production RNG
+        if a.size != int(np.prod(shape)):
+            raise ValueError(f"explicit normal draws must have shape {shape}")
+        return a.astype(np.float32).reshape(shape)
+
+    def _finish(self, control_params, action):
+        self._generation += 1
+        gen = self._generation
+        new = control_params.replace(a_mean=_DeviceArray(self, gen, "a_mean"), a_cov=_DeviceArray(self, gen, "a_cov"))
+        new._gen = gen
+        info = None
+        if self.want_info:
+            m, s = self._handle.pos_stats()
+            info = {"pos_mean": m[0], "pos_std": s[0]}
+        return action, new, info
+
+    def close(self):
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
+
+
+class MPPIController(_SamplingController):
+    """quadjax/controllers/mppi.py:21-134"""
+
+    _mode = _lib.MODE_MPPI
+
+    def _upload_cov(self, control_params):
+        self._handle.set_cov(np.asarray(control_params.a_cov, dtype=np.float32).reshape(1, self.H, 4, 4))
+
+    def __call__(self, obs, env_state, env_params, rng_act, control_params, info=None):
+        state: EnvState3D = info["noisy_state"]  # mppi.py:40
+        h = self._sync_reference(state)
+        self._upload_params(control_params)
+        if self.want_info:
+            h.enable_pos_stats(True)
+        eps = self._eps(rng_act, (1, h.n_local, self.H * 4))
+        action = h.step(state.to_state24(), [state.time], eps)[0]
+        return self._finish(control_params, action)
+
+
+class CoVOController(_SamplingController):
+    """quadjax/controllers/covo.py:25-283"""
+
+    def __init__(self, env, control_params, N: int, H: int, lam: float, mode: str = "online", **kw) -> None:
+        if mode == "online":
+            self._mode = _lib.MODE_COVO_ONLINE
+        elif mode == "offline":
+            self._mode = _lib.MODE_COVO_OFFLINE
+        else:
+            raise NotImplementedError(mode)  # covo.py:113-114
+        self.mode = mode
+        super().__init__(env, control_params, N, H, lam, **kw)
+        self._table = None
+
+    def _on_new_handle(self):
+        if self._mode == _lib.MODE_COVO_OFFLINE and self._table is not None:
+            self._handle.set_cov_offline(self._table)
+
+    def reset(self, env_state=None, env_params=None, control_params=None, key=None):
+        if self._mode != _lib.MODE_COVO_OFFLINE:
+            return self.init_control_params
+        # reset_a_cov_offline, covo.py:101-104: rebuild the covariance schedule from this state (on device)
+        if getattr(self.env, "disturb_type", "none") != "none":
+            raise NotImplementedError("covo-offline schedule: only disturb_type='none' is implemented")
+        h = self._sync_reference(env_state)
+        T = int(self.env.default_params.max_steps_in_episode)
+        h.reset_offline(env_state.to_state24(), [env_state.time], T)
+        self._table = None
+        self._generation += 1
+        cp = control_params if control_params is not None else self.init_control_params
+        new = cp.replace(a_cov_offline=_OfflineTable(self, T))
+        return new
+
+    def _upload_cov(self, control_params):
+        if self._mode == _lib.MODE_COVO_OFFLINE:
+            tab = control_params.a_cov_offline
+            if isinstance(tab, _OfflineTable) and tab.owner is self:
+                return
+            tab = np.asarray(tab, dtype=np.float32)
+            if tab.ndim != 3 or tab.shape[1] != 4 * self.H:
+                raise ValueError("a_cov_offline must be (T, 4H, 4H); call controller.reset first")
+            self._table = tab
+            self._handle.set_cov_offline(tab)
+
+    def __call__(self, obs, env_state, env_params, rng_act, control_params, info=None):
+        state: EnvState3D = info["noisy_state"]  # covo.py:198
+        h = self._sync_reference(state)
+        self._upload_params(control_params)
+        if self.want_info:
+            h.enable_pos_stats(True)
+        eps = self._eps(rng_act, (1, h.n_local, self.H * 4))
+        action = h.step(state.to_state24(), [state.time], eps)[0]
+        return self._finish(control_params, action)
+
+
+class _OfflineTable:
+    """Handle to the device-resident a_cov_offline schedule (materialised on np.asarray)."""
+
+    def __init__(self, owner: CoVOController, T: int):
+        self.owner, self.T = owner, T
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.owner._handle.get_cov_offline(self.T)
+        return a if dtype is None else a.astype(dtype)
+
+    @property
+    def shape(self):
+        return (self.T, 4 * self.owner.H, 4 * self.owner.H)
+
+
+def get_controller(env, controller_name: str, controller_params: Optional[str] = None, debug: bool = False, **kw):
+    """quadjax/envs/quadrotor.py:670-752 -- same names, same parameter string, same defaults."""
+
+    def parse_sample_params(param_text):
+        if not param_text:
+            return 8192, 32, 0.01, 0.5
+        parts = param_text.split("_")
+        return int(parts[0][1:]), int(parts[1][1:]), float(parts[2][3:]), 0.5
+
+    p = env.default_params
+
+    def get_sample_mean(H):
+        th = (p.m * p.g / p.max_thrust) * 2.0 - 1.0
+        return np.tile(np.array([th, 0.0, 0.0, 0.0], np.float32), (H, 1))
+
+    if controller_name == "mppi":
+        N, H, lam, sigma = parse_sample_params(controller_params)
+        if debug:
+            N, H = 4, 2
+        a_cov = np.tile(np.diag(np.full(4, sigma ** 2, np.float32)), (H, 1, 1))
+        control_params = MPPIParams(gamma_mean=1.0, gamma_sigma=0.0, discount=1.0, sample_sigma=sigma,
+                                    a_mean=get_sample_mean(H), a_cov=a_cov)
+        controller = MPPIController(env=env, control_params=control_params, N=N, H=H, lam=lam, **kw)
+    elif "covo" in controller_name:
+        N, H, lam, sigma = parse_sample_params(controller_params)
+        if debug:
+            N, H = 4, 2
+        mode = "offline" if "offline" in controller_name else "online"
+        control_params = CoVOParams(gamma_mean=1.0, gamma_sigma=0.0, discount=1.0, sample_sigma=sigma,
+                                    a_mean=get_sample_mean(H), a_cov=np.diag(np.full(H * 4, sigma ** 2, np.float32)),
+                                    a_cov_offline=np.zeros((H, 4, 4), np.float32))
+        controller = CoVOController(env=env, control_params=control_params, N=N, H=H, lam=lam, mode=mode, **kw)
+    else:
+        # "pid" / "random" are out of scope of this hot path
+        raise NotImplementedError(controller_name)
+    return controller, control_params

@@ -1,0 +1,49 @@
+"""Episode loops around the controllers: the eager ``render_env`` loop (quadjax/envs/quadrotor.py:594-667)
+and the ``eval_env`` protocol (:506-591: 4 reference trajectories x episodes, metric = mean/std over episodes
+of the per-episode mean ``err_pos``).  The reference's jitted ``lax.scan`` variant of eval_env cannot host a
+non-JAX plugin; this is the same protocol driven eagerly."""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+
+
+def run_episode(env, controller, rng: np.random.Generator, n_steps: Optional[int] = None, rng_act_fn: Optional[Callable] = None,
+                record: Optional[list] = None, reset_rng: Optional[np.random.Generator] = None):
+    """One episode: reset -> controller.reset -> n_steps x (controller call, env.step).
+
+    rng_act_fn(step) -> the ``rng_act`` argument of each controller call (None = production RNG).
+    Returns (err_pos[n_steps], rewards[n_steps])."""
+    params = env.default_params
+    n_steps = n_steps or params.max_steps_in_episode
+    obs, info, state = env.reset(reset_rng if reset_rng is not None else rng, params)
+    control_params = controller.reset(state, params, controller.init_control_params, None)
+    errs, rews = [], []
+    for i in range(n_steps):
+        if record is not None:
+            record.append((info["noisy_state"].to_state24(), int(info["noisy_state"].time)))
+        rng_act = rng_act_fn(i) if rng_act_fn else None
+        action, control_params, _ = controller(obs, state, params, rng_act, control_params, info)
+        obs, state, reward, done, info = env.step(rng, state, action, params)
+        errs.append(info["err_pos"])
+        rews.append(reward)
+        if done:
+            break
+    return np.asarray(errs), np.asarray(rews)
+
+
+def eval_env(env, controller, total_steps: int = 300 * 4 * 10, num_trajs: int = 4, seed: int = 1):
+    """quadjax/envs/quadrotor.py:506-591 (PRNGKey(1); num_trajs reference trajectories, each re-used for
+    num_eps // num_trajs episodes).  Returns (mean, std, per-episode array)."""
+    T = env.default_params.max_steps_in_episode
+    num_eps = int(total_steps // T)
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(num_trajs):
+        traj_seed = int(rng.integers(0, 2 ** 31))
+        for _ in range(num_eps // num_trajs):
+            errs, _ = run_episode(env, controller, rng, T, reset_rng=np.random.default_rng(traj_seed))
+            out.append(errs.mean())
+    out = np.asarray(out)
+    return float(out.mean()), float(out.std()), out

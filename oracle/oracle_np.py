@@ -697,9 +697,14 @@ def pid_action(s: QuadState, p: EnvParams, Kp=10.0, Kd=5.0, Ki=0.0, Kp_att=10.0,
     # pid.py:60 tests the *updated* angle, which is never < 1e-3 -> axis = axis_angle / angle always
     axis = axis_angle / angle
     an = np.linalg.norm(axis)
-    axis_n = axis / an if an > 0 else axis * np.nan  # geom.axisangletoR normalises (geom.py:111)
-    Hx = _hat(axis_n)
-    R_d = np.eye(3) + np.sin(angle) * Hx + (1 - np.cos(angle)) * Hx @ Hx
+    if an > 0:
+        axis_n = axis / an  # geom.axisangletoR normalises (geom.py:111)
+        Hx = _hat(axis_n)
+        R_d = np.eye(3) + np.sin(angle) * Hx + (1 - np.cos(angle)) * Hx @ Hx
+    else:
+        # EXTENSION shared with csrc/pid.cuh: the reference divides 0/0 here (f_d exactly vertical) and
+        # returns NaN; the zero-angle limit R_d = I is used instead.
+        R_d = np.eye(3)
     R_e = R_d.T @ Q
     E = R_e - R_e.T
     angle_err = np.array([E[2, 1], E[0, 2], E[1, 0]])

@@ -1,0 +1,97 @@
+"""K3-K5 parity (T2 in SURVEY 7.3): exact Hessian, optimize_sigma and Cholesky through the C-ABI."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as o
+from tests.util import scenario
+
+pytestmark = pytest.mark.gpu
+
+
+def _handle(N, H, T, mode=None, **kw):
+    from covo_mpc_b200 import _lib
+
+    cfg = _lib.default_config()
+    cfg.mode = _lib.MODE_COVO_ONLINE if mode is None else mode
+    cfg.n_samples, cfg.horizon, cfg.traj_len = N, H, T
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return _lib.Handle(cfg)
+
+
+@pytest.mark.parametrize("H,task,warm,time", [(50, "tracking_zigzag", 0, 0), (50, "tracking_zigzag", 40, 0),
+                                               (32, "tracking", 25, 0), (12, "hovering", 5, 0), (20, "tracking_zigzag", 10, 290)])
+def test_hessian_vs_forward_over_forward_oracle(H, task, warm, time):
+    p, ns, a_mean, rng = scenario(task, seed=H + warm, H=H, warm_steps=warm, zero_disturb=False, time=time)
+    h = _handle(64, H, ns.pos_traj.shape[0])
+    h.set_reference(ns.pos_traj[None], ns.vel_traj[None])
+    am = a_mean.copy()
+    am[1, 2] = 1.0  # clip tie
+    am[2, 0] = -1.2  # outside the clip box
+    R = h.hessian(o.state_to_vec24(ns), [ns.time], am[None], shift=False)[0]
+    Ro = o.get_hessian(ns, am, p, dtype=np.float64)
+    scale = max(1.0, np.abs(Ro).max())
+    assert np.abs(R - Ro).max() < 2e-5 * scale  # R vs float64 oracle <= 1e-5 ||R||
+    assert np.abs(R - R.T).max() == 0.0
+    assert np.abs(R[-4:]).max() == 0.0 and np.abs(R[8]).max() == 0.0  # last action; the clipped-out control (h=2, c=0)
+    # the shift operator fused into the load
+    Rs = h.hessian(o.state_to_vec24(ns), [ns.time], am[None], shift=True)[0]
+    Rso = o.get_hessian(ns, o.shift_mean(am), p, dtype=np.float64)
+    assert np.abs(Rs - Rso).max() < 2e-5 * max(1.0, np.abs(Rso).max())
+
+
+@pytest.mark.parametrize("H", [50, 32, 8, 3])
+def test_optimize_sigma_and_cholesky(H):
+    p, ns, a_mean, rng = scenario("tracking_zigzag", seed=7, H=H, warm_steps=15)
+    n = 4 * H
+    h = _handle(64, H, ns.pos_traj.shape[0])
+    R = o.get_hessian(ns, a_mean, p, dtype=np.float64).astype(np.float32)
+    S = h.optimize_sigma(R[None])[0]
+    So = o.optimize_sigma(R.astype(np.float64), 0.5, np.float64)
+    assert np.linalg.norm(S - So) / np.linalg.norm(So) < 1e-5
+    assert np.abs(S - So).max() < 1e-5 * np.abs(So).max()
+    assert np.abs(S - S.T).max() == 0.0
+    assert abs(np.linalg.slogdet(S.astype(np.float64))[1] - 2 * n * np.log(0.5)) < 1e-3  # det Sigma = sigma^(2n)
+    d, e, sc = h.debug_tridiag()
+    T = np.diag(d) + np.diag(e[:-1], 1) + np.diag(e[:-1], -1)
+    w = np.linalg.eigvalsh(((R + R.T) / 2).astype(np.float64))
+    assert np.abs(np.linalg.eigvalsh(T) - w).max() < 2e-5 * max(1, np.abs(w).max())  # Householder is a similarity
+    assert abs(sc[0] - np.linalg.eigvalsh(T)[0]) < 1e-10  # fp64 Sturm multisection
+    L = h.cholesky(S[None])[0]
+    Lo = np.linalg.cholesky(S.astype(np.float64))
+    assert np.abs(L - Lo).max() < 2e-6 * max(1, np.abs(Lo).max())
+    assert np.abs(np.triu(L, 1)).max() == 0.0
+
+
+def test_sigma_random_symmetric_and_degenerate():
+    rng = np.random.default_rng(0)
+    H = 16
+    n = 4 * H
+    h = _handle(64, H, 300)
+    for kind in range(4):
+        A = rng.standard_normal((n, n)).astype(np.float32)
+        R = (A + A.T) * (0.1 if kind == 0 else 3.0)
+        if kind == 2:
+            R[-8:, :] = 0
+            R[:, -8:] = 0  # exact zero block -> the tridiagonal splits
+        if kind == 3:
+            R = np.diag(rng.uniform(-1, 5, n)).astype(np.float32)  # already diagonal: every reflector is trivial
+        S = h.optimize_sigma(R[None])[0]
+        So = o.optimize_sigma(R.astype(np.float64), 0.5, np.float64)
+        assert np.linalg.norm(S - So) / np.linalg.norm(So) < 2e-5, kind
+        assert h.status()[0] == 0
+
+
+def test_sigma_batched_envs():
+    from covo_mpc_b200 import _lib
+
+    rng = np.random.default_rng(1)
+    H, E = 8, 5
+    n = 4 * H
+    h = _handle(64, H, 300, n_env=E)
+    A = rng.standard_normal((E, n, n)).astype(np.float32)
+    R = A + A.transpose(0, 2, 1)
+    S = h.optimize_sigma(R)
+    for e in range(E):
+        So = o.optimize_sigma(R[e].astype(np.float64), 0.5, np.float64)
+        assert np.linalg.norm(S[e] - So) / np.linalg.norm(So) < 2e-5

@@ -1,0 +1,175 @@
+"""Whole controller calls through the reference-facing plugin surface, closed loops and the offline schedule."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as o
+from tests.util import scenario
+
+pytestmark = pytest.mark.gpu
+
+
+def _to_env_state(cm, ns):
+    f = np.float32
+    return cm.EnvState3D(pos=np.array(ns.pos, f), vel=np.array(ns.vel, f), quat=np.array(ns.quat, f), omega=np.array(ns.omega, f),
+                         pos_traj=ns.pos_traj.astype(f), vel_traj=ns.vel_traj.astype(f), acc_traj=np.zeros_like(ns.pos_traj, dtype=f),
+                         pos_tar=np.array(ns.pos_tar, f), vel_tar=np.array(ns.vel_tar, f), acc_tar=np.zeros(3, f), time=int(ns.time),
+                         f_disturb=np.array(ns.f_disturb, f))
+
+
+@pytest.mark.parametrize("N,H", [(1024, 50), (256, 16)])
+def test_covo_online_call_matches_oracle(N, H):
+    """BASELINE config 2 (CoVO-online, tracking_zigzag, N=1024, H=50): one full controller call."""
+    import covo_mpc_b200 as cm
+
+    p, ns, a_mean, rng = scenario("tracking_zigzag", seed=21, H=H, warm_steps=12)
+    env = cm.Quad3D("tracking_zigzag")
+    ctl, cp = cm.get_controller(env, "covo-online", f"N{N}_H{H}_lam0.01")
+    cp = cp.replace(a_mean=a_mean)
+    eps = rng.standard_normal((N, 4 * H)).astype(np.float32)
+    st = _to_env_state(cm, ns)
+    ctl.want_info = True
+    action, cp2, info = ctl(None, st, env.default_params, eps, cp, {"noisy_state": st})
+    u_o, mean_o, cov_o, info_o, dbg = o.covo_call(ns, a_mean, eps, p, lam=0.01, return_debug=True)
+    cov = np.asarray(cp2.a_cov)
+    assert np.linalg.norm(cov - cov_o) / np.linalg.norm(cov_o) < 2e-5
+    # with ESS ~ 1 the update is (almost) the arg-min sample: same winner, mean within 1e-4
+    new_mean = np.asarray(cp2.a_mean)
+    assert np.abs(new_mean - mean_o).max() < 2e-4
+    assert np.abs(action - u_o).max() < 2e-4
+    assert np.abs(info["pos_mean"] - info_o["pos_mean"]).max() < 1e-4
+    # a second call re-uses the device-resident params; a stale params object is refused
+    action2, cp3, _ = ctl(None, st, env.default_params, eps, cp2, {"noisy_state": st})
+    action3, cp4, _ = ctl(None, st, env.default_params, eps, cp3, {"noisy_state": st})
+    with pytest.raises(RuntimeError):
+        np.asarray(cp3.a_mean)  # never materialised, and the controller has moved on
+    assert np.isfinite(np.asarray(cp4.a_mean)).all()
+
+
+def test_mppi_call_matches_oracle():
+    import covo_mpc_b200 as cm
+
+    N, H = 128, 32
+    p, ns, a_mean, rng = scenario("hovering", seed=8, H=H, warm_steps=4)
+    env = cm.Quad3D("hovering")
+    ctl, cp = cm.get_controller(env, "mppi", f"N{N}_H{H}_lam0.01")
+    cp = cp.replace(a_mean=a_mean)
+    eps = rng.standard_normal((N, H, 4)).astype(np.float32)
+    st = _to_env_state(cm, ns)
+    action, cp2, info = ctl(None, st, env.default_params, eps, cp, {"noisy_state": st})
+    u_o, mean_o, cov_o, _ = o.mppi_call(ns, a_mean, np.asarray(cp.a_cov), eps, p, lam=0.01)
+    assert np.abs(np.asarray(cp2.a_mean) - mean_o).max() < 1e-5 and np.abs(action - u_o).max() < 1e-5
+    assert np.allclose(np.asarray(cp2.a_cov), cov_o)
+
+
+def test_closed_loop_tracks_and_matches_oracle_loop():
+    """T3: a short closed loop with a shared eps stream; device and oracle controllers see the same states."""
+    import covo_mpc_b200 as cm
+
+    N, H, steps = 512, 20, 12
+    p = o.EnvParams()
+    rng = np.random.default_rng(5)
+    s = o.reset_env("tracking_zigzag", p, rng, dtype=np.float32, zero_disturb=True)
+    env = cm.Quad3D("tracking_zigzag")
+    ctl, cp = cm.get_controller(env, "covo-online", f"N{N}_H{H}_lam0.01")
+    mean_o = o.hover_mean(H, p)
+    max_da = 0.0
+    for i in range(steps):
+        ns = o.noisy_state(s, p, rng)
+        eps = rng.standard_normal((N, 4 * H)).astype(np.float32)
+        st = _to_env_state(cm, ns)
+        action, cp, _ = ctl(None, st, env.default_params, eps, cp, {"noisy_state": st})
+        u_o, mean_o, _, _ = o.covo_call(ns, mean_o, eps, p, lam=0.01)
+        max_da = max(max_da, np.abs(action - u_o).max())
+        # keep both loops on the oracle's trajectory so one arg-min flip cannot decorrelate the comparison
+        ctl._handle.set_mean(mean_o[None])
+        s, _, _, _ = o.env_step(s, u_o, p, rng, "none")
+    assert max_da < 5e-4
+
+
+def test_episode_tracking_quality():
+    """A 60-step production-mode episode: CoVO-online must actually track (err_pos stays small, finite)."""
+    import covo_mpc_b200 as cm
+
+    env = cm.Quad3D("tracking_zigzag")
+    ctl, _ = cm.get_controller(env, "covo-online", "N1024_H32_lam0.01")
+    errs, rews = cm.run_episode(env, ctl, np.random.default_rng(0), n_steps=60)
+    assert np.isfinite(errs).all() and errs.mean() < 0.2
+    ctl2, _ = cm.get_controller(env, "mppi", "N1024_H32_lam0.01")
+    errs2, _ = cm.run_episode(env, ctl2, np.random.default_rng(0), n_steps=60)
+    assert np.isfinite(errs2).all() and errs2.mean() < 0.3
+
+
+def test_offline_schedule_matches_oracle():
+    """covo-offline reset (controllers/covo.py:58-104) on device vs the oracle, then a lookup step."""
+    import covo_mpc_b200 as cm
+
+    N, H, T = 256, 8, 6
+    p = o.EnvParams()
+    rng = np.random.default_rng(3)
+    s = o.reset_env("tracking", p, rng, dtype=np.float32, zero_disturb=False)
+    env = cm.Quad3D("tracking")
+    ctl, cp = cm.get_controller(env, "covo-offline", f"N{N}_H{H}_lam0.01")
+    st = _to_env_state(cm, s)
+    pos, vel, acc = o.generate_lissa_traj(300, 0.02, np.random.default_rng(3))  # same generator draw as reset_env
+    st.acc_traj = acc.astype(np.float32)
+    st.acc_tar = acc[0].astype(np.float32)
+    h = ctl._sync_reference(st)
+    h.reset_offline(st.to_state24(), [0], T)
+    tab = h.get_cov_offline(T)
+    # oracle (needs acc_tar for the PID): restate with the oracle's PID + env
+    so = s.copy()
+    tab_o = []
+    for t in range(T):
+        sr = so.copy()
+        nom = []
+        for hh in range(H):
+            a = o.pid_action(sr, p, acc_tar=acc[min(sr.time, 349)])
+            nom.append(a)
+            sr, _, _, _ = o.env_step(sr, a, p, rng, "none")
+        R = o.get_hessian(so, np.asarray(nom), p)
+        tab_o.append(o.optimize_sigma(R, 0.5, np.float64))
+        a = o.pid_action(so, p, acc_tar=acc[min(so.time, 349)])
+        so, _, _, _ = o.env_step(so, a, p, rng, "none")
+    tab_o = np.stack(tab_o)
+    for t in range(T):
+        assert np.linalg.norm(tab[t] - tab_o[t]) / np.linalg.norm(tab_o[t]) < 1e-4, t
+    # a lookup step at time 2 uses table[2]
+    ns = o.noisy_state(s, p, rng)
+    ns.time = 2
+    eps = rng.standard_normal((N, 4 * H)).astype(np.float32)
+    a_mean = o.hover_mean(H, p)
+    act = h.step(o.state_to_vec24(ns), [2], eps[None])[0]
+    u_o, mean_o, _, _ = o.covo_call(ns, a_mean, eps, p, lam=0.01, a_cov=tab_o[2].astype(np.float32))
+    assert np.abs(act - u_o).max() < 2e-4
+
+
+def test_batched_environments_match_single():
+    """Config-5 shape: E environments behind one handle give the same answers as E single-env handles."""
+    from covo_mpc_b200 import _lib
+
+    N, H, E = 256, 16, 3
+    cfgs = []
+    states, times, means, eps_all, trajs = [], [], [], [], []
+    for e in range(E):
+        p, ns, a_mean, rng = scenario("tracking_zigzag", seed=100 + e, H=H, warm_steps=5 + e)
+        states.append(o.state_to_vec24(ns))
+        times.append(ns.time)
+        means.append(a_mean)
+        eps_all.append(rng.standard_normal((N, 4 * H)).astype(np.float32))
+        trajs.append((ns.pos_traj, ns.vel_traj))
+    cfg = _lib.default_config()
+    cfg.mode, cfg.n_samples, cfg.horizon, cfg.traj_len, cfg.n_env = _lib.MODE_COVO_ONLINE, N, H, 320, E
+    hb = _lib.Handle(cfg)
+    hb.set_reference(np.stack([t[0] for t in trajs]), np.stack([t[1] for t in trajs]))
+    hb.set_mean(np.stack(means))
+    act_b = hb.step(np.stack(states), times, np.stack(eps_all))
+    mean_b = hb.get_mean()
+    for e in range(E):
+        cfg1 = _lib.default_config()
+        cfg1.mode, cfg1.n_samples, cfg1.horizon, cfg1.traj_len = _lib.MODE_COVO_ONLINE, N, H, 320
+        h1 = _lib.Handle(cfg1)
+        h1.set_reference(trajs[e][0][None], trajs[e][1][None])
+        h1.set_mean(means[e][None])
+        act1 = h1.step(states[e], [times[e]], eps_all[e][None])
+        assert np.array_equal(act1[0], act_b[e]) and np.array_equal(h1.get_mean()[0], mean_b[e])
+        h1.close()
