@@ -75,6 +75,7 @@ _SIGNATURES = {
     "covo_get_status": [_H, _I],
     "covo_set_profiling": [_H, C.c_int],
     "covo_get_kernel_ms": [_H, _F],
+    "covo_debug_phase_clocks": [_H, C.c_int, C.POINTER(C.c_longlong)],
     "covo_rng_step": [_H, C.POINTER(C.c_uint)],
     "covo_local_samples": [_H, _I, _I],
 }
@@ -307,6 +308,11 @@ class Handle:
     def kernel_ms(self) -> np.ndarray:
         out = np.empty(6, dtype=np.float32)
         check(self.lib.covo_get_kernel_ms(self._h, fptr(out)))
+        return out
+
+    def phase_clocks(self, on=True, read=False):
+        out = np.zeros(64, dtype=np.int64) if read else None
+        check(self.lib.covo_debug_phase_clocks(self._h, int(on), None if out is None else out.ctypes.data_as(C.POINTER(C.c_longlong))))
         return out
 
     def rng_step(self) -> int:

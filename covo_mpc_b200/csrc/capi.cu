@@ -46,6 +46,7 @@ struct DevBuf {
         if (count == 0) return cudaSuccess;
         cudaError_t e = cudaMalloc(&p, count * sizeof(T));
         if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T));
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();  // the handle's stream is non-blocking
         return e;
     }
     void release() {
@@ -114,11 +115,20 @@ struct covo_handle {
     // rollout
     DevBuf<float> partials, rank_partial, action, costs, samples, pos_stats, gathered_scratch;
     DevBuf<unsigned int> counters;
+    DevBuf<long long> prof;
+    bool phase_clocks = false;
     // pinned staging
     float* h_state = nullptr;
     int* h_time = nullptr;
     float* h_action = nullptr;
 };
+
+
+// All host<->device traffic goes through the handle's own (non-blocking) stream: a plain cudaMemcpy on the
+// legacy default stream is NOT ordered against it (a staged pageable H2D copy may still be in flight).
+static cudaError_t h2d(covo_handle* h, void* dst, const void* src, size_t bytes);
+static cudaError_t d2h(covo_handle* h, void* dst, const void* src, size_t bytes);
+static cudaError_t dzero(covo_handle* h, void* dst, size_t bytes);
 
 namespace {
 
@@ -132,7 +142,7 @@ void release_all(covo_handle* h) {
     h->sched_R.release(); h->sched_Vh.release(); h->sched_tau.release(); h->sched_F.release(); h->sched_Z.release();
     h->sched_ws.release(); h->sched_diag.release(); h->sched_times.release(); h->sched_status.release();
     h->partials.release(); h->rank_partial.release(); h->action.release(); h->costs.release();
-    h->samples.release(); h->pos_stats.release(); h->gathered_scratch.release(); h->counters.release();
+    h->prof.release(); h->samples.release(); h->pos_stats.release(); h->gathered_scratch.release(); h->counters.release();
     if (h->h_state) cudaFreeHost(h->h_state);
     if (h->h_time) cudaFreeHost(h->h_time);
     if (h->h_action) cudaFreeHost(h->h_action);
@@ -156,6 +166,7 @@ HessianArgs hess_args(covo_handle* h, const float* st, const int* tm, const floa
     a.a_mean = a_mean;
     a.workspace = ws;
     a.R = R;
+    a.prof = h->phase_clocks ? h->prof.p : nullptr;
     return a;
 }
 
@@ -176,6 +187,7 @@ SigmaArgs sigma_args(covo_handle* h) {
     a.zolo = h->zolo.p;
     a.status = h->status.p;
     a.lt_stride = (long long)h->lt_floats;
+    a.prof = h->phase_clocks ? h->prof.p : nullptr;
     return a;
 }
 
@@ -214,6 +226,7 @@ RolloutArgs rollout_args(covo_handle* h, const float* st, const int* tm, const f
     a.costs_out = costs;
     a.samples_out = samples;
     a.pos_stats = h->pos_stats_on ? h->pos_stats.p : nullptr;
+    a.prof = h->phase_clocks ? h->prof.p : nullptr;
     if (a.mode == 1) {
         a.Lfac = h->Lblk.p;
         a.lfac_stride = (long long)h->H * 16;
@@ -242,8 +255,9 @@ struct Prof {
 };
 
 // covariance step for the online mode: R (already in h->R) -> cov -> factor
-int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf) {
+int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = false) {
     SigmaArgs sa = sigma_args(h);
+    if (!want_L) sa.L = nullptr;  // the sampler only needs the packed factor
     // sigma: tridiag+rational, then the two apply-Q passes; mark after the tridiag kernel is not possible
     // without splitting launch_sigma, so the pipeline is timed as [tridiag][applyQ x2] via two events inside.
     CK(launch_sigma(sa, h->E, st));
@@ -283,6 +297,17 @@ int step_common(covo_handle* h, const float* st_d, const int* tm_d, const float*
 }
 
 }  // namespace
+
+
+static cudaError_t h2d(covo_handle* h, void* dst, const void* src, size_t bytes) {
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->own_stream);
+}
+static cudaError_t d2h(covo_handle* h, void* dst, const void* src, size_t bytes) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->own_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->own_stream);
+    return e;
+}
+static cudaError_t dzero(covo_handle* h, void* dst, size_t bytes) { return cudaMemsetAsync(dst, 0, bytes, h->own_stream); }
 
 // =================================================================================================
 extern "C" {
@@ -377,6 +402,7 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
     A(h->action.alloc(E * 4));
     A(h->pos_stats.alloc(E * h->H * 6));
     A(h->status.alloc(E));
+    A(h->prof.alloc(64));
     if (cfg->mode == COVO_MODE_MPPI) {
         A(h->Lblk.alloc(E * h->H * 16));
         A(h->cov.alloc(E * h->H * 16));
@@ -395,7 +421,7 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
         if (e == cudaSuccess) {
             std::vector<double> tab((size_t)kZoloLadder * 2 * kZoloPoles);
             zolotarev_table(tab.data());
-            A(cudaMemcpy(h->zolo.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+            A(h2d(h, h->zolo.p, tab.data(), tab.size() * sizeof(double)));
         }
     }
     A(cudaMallocHost(&h->h_state, E * kStateFloats * sizeof(float)));
@@ -414,7 +440,7 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
             mean[i * 4 + 0] = th;
             mean[i * 4 + 1] = mean[i * 4 + 2] = mean[i * 4 + 3] = 0.f;
         }
-        cudaMemcpy(h->a_mean.p, mean.data(), mean.size() * sizeof(float), cudaMemcpyHostToDevice);
+        h2d(h, h->a_mean.p, mean.data(), mean.size() * sizeof(float));
         if (cfg->mode == COVO_MODE_MPPI) {
             std::vector<float> L(E * h->H * 16, 0.f), C(E * h->H * 16, 0.f);
             for (size_t b = 0; b < E * (size_t)h->H; ++b)
@@ -422,8 +448,8 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
                     L[b * 16 + k * 5] = cfg->sample_sigma;
                     C[b * 16 + k * 5] = cfg->sample_sigma * cfg->sample_sigma;
                 }
-            cudaMemcpy(h->Lblk.p, L.data(), L.size() * sizeof(float), cudaMemcpyHostToDevice);
-            cudaMemcpy(h->cov.p, C.data(), C.size() * sizeof(float), cudaMemcpyHostToDevice);
+            h2d(h, h->Lblk.p, L.data(), L.size() * sizeof(float));
+            h2d(h, h->cov.p, C.data(), C.size() * sizeof(float));
             h->have_factor = true;
         }
     }
@@ -444,10 +470,10 @@ int covo_set_reference(covo_handle* h, const float* pos, const float* vel, const
     if (!h || !pos || !vel) return fail(COVO_ERR_INVALID, "null argument");
     CK(cudaSetDevice(h->cfg.device));
     size_t bytes = (size_t)h->E * h->T * 3 * sizeof(float);
-    CK(cudaMemcpy(h->pos_traj.p, pos, bytes, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->vel_traj.p, vel, bytes, cudaMemcpyHostToDevice));
-    if (acc) CK(cudaMemcpy(h->acc_traj.p, acc, bytes, cudaMemcpyHostToDevice));
-    else CK(cudaMemset(h->acc_traj.p, 0, bytes));
+    CK(h2d(h, h->pos_traj.p, pos, bytes));
+    CK(h2d(h, h->vel_traj.p, vel, bytes));
+    if (acc) CK(h2d(h, h->acc_traj.p, acc, bytes));
+    else CK(dzero(h, h->acc_traj.p, bytes));
     return COVO_OK;
 }
 
@@ -455,14 +481,14 @@ int covo_set_mean(covo_handle* h, const float* a_mean) {
     if (!h || !a_mean) return fail(COVO_ERR_INVALID, "null argument");
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->own_stream));
-    CK(cudaMemcpy(h->a_mean.p, a_mean, (size_t)h->E * h->n * sizeof(float), cudaMemcpyHostToDevice));
+    CK(h2d(h, h->a_mean.p, a_mean, (size_t)h->E * h->n * sizeof(float)));
     return COVO_OK;
 }
 int covo_get_mean(covo_handle* h, float* a_mean) {
     if (!h || !a_mean) return fail(COVO_ERR_INVALID, "null argument");
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->own_stream));
-    CK(cudaMemcpy(a_mean, h->a_mean.p, (size_t)h->E * h->n * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(d2h(h, a_mean, h->a_mean.p, (size_t)h->E * h->n * sizeof(float)));
     return COVO_OK;
 }
 
@@ -489,11 +515,11 @@ int covo_set_cov(covo_handle* h, const float* a_cov) {
                 }
             }
         }
-        CK(cudaMemcpy(h->Lblk.p, L.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->cov.p, a_cov, cnt * sizeof(float), cudaMemcpyHostToDevice));
+        CK(h2d(h, h->Lblk.p, L.data(), cnt * sizeof(float)));
+        CK(h2d(h, h->cov.p, a_cov, cnt * sizeof(float)));
     } else {
-        CK(cudaMemcpy(h->cov.p, a_cov, (size_t)h->E * h->n * h->n * sizeof(float), cudaMemcpyHostToDevice));
-        CK(cudaMemset(h->status.p, 0, h->E * sizeof(int)));
+        CK(h2d(h, h->cov.p, a_cov, (size_t)h->E * h->n * h->n * sizeof(float)));
+        CK(dzero(h, h->status.p, h->E * sizeof(int)));
         SigmaArgs sa = sigma_args(h);
         CK(launch_cholesky(sa, h->E, h->own_stream));
         CK(cudaStreamSynchronize(h->own_stream));
@@ -506,7 +532,7 @@ int covo_get_cov(covo_handle* h, float* a_cov) {
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->own_stream));
     size_t cnt = (h->cfg.mode == COVO_MODE_MPPI) ? (size_t)h->E * h->H * 16 : (size_t)h->E * h->n * h->n;
-    CK(cudaMemcpy(a_cov, h->cov.p, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(d2h(h, a_cov, h->cov.p, cnt * sizeof(float)));
     return COVO_OK;
 }
 
@@ -560,13 +586,13 @@ int covo_set_cov_offline(covo_handle* h, const float* table, int t_sched) {
     CK(cudaSetDevice(h->cfg.device));
     int rc = alloc_schedule(h, t_sched, false);
     if (rc) return rc;
-    CK(cudaMemcpy(h->cov_table.p, table, (size_t)t_sched * h->n * h->n * sizeof(float), cudaMemcpyHostToDevice));
+    CK(h2d(h, h->cov_table.p, table, (size_t)t_sched * h->n * h->n * sizeof(float)));
     SigmaArgs sa = sigma_args(h);
     sa.cov = h->cov_table.p;
     sa.L = nullptr;
     sa.Lt = h->Lt_table.p;
     sa.status = h->sched_status.p;
-    CK(cudaMemset(h->sched_status.p, 0, t_sched * sizeof(int)));
+    CK(dzero(h, h->sched_status.p, t_sched * sizeof(int)));
     CK(launch_cholesky(sa, t_sched, h->own_stream));
     CK(cudaStreamSynchronize(h->own_stream));
     h->t_sched = t_sched;
@@ -579,7 +605,7 @@ int covo_get_cov_offline(covo_handle* h, float* table, int t_sched) {
     if (t_sched > h->t_sched) return fail(COVO_ERR_INVALID, "schedule has %d steps", h->t_sched);
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->own_stream));
-    CK(cudaMemcpy(table, h->cov_table.p, (size_t)t_sched * h->n * h->n * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(d2h(h, table, h->cov_table.p, (size_t)t_sched * h->n * h->n * sizeof(float)));
     return COVO_OK;
 }
 
@@ -715,8 +741,8 @@ int covo_step_merge_device(covo_handle* h, const float* gathered_dev, float* act
 
 // ---- operators ------------------------------------------------------------------------------------
 static int upload_state(covo_handle* h, const float* state24, const int* time) {
-    CK(cudaMemcpy(h->state24.p, state24, (size_t)h->E * kStateFloats * sizeof(float), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->time.p, time, (size_t)h->E * sizeof(int), cudaMemcpyHostToDevice));
+    CK(h2d(h, h->state24.p, state24, (size_t)h->E * kStateFloats * sizeof(float)));
+    CK(h2d(h, h->time.p, time, (size_t)h->E * sizeof(int)));
     return COVO_OK;
 }
 
@@ -729,19 +755,19 @@ int covo_hessian(covo_handle* h, const float* state24, const int* time, const fl
     if (rc) return rc;
     DevBuf<float> am;
     CK(am.alloc((size_t)h->E * h->n));
-    CK(cudaMemcpy(am.p, a_mean, (size_t)h->E * h->n * sizeof(float), cudaMemcpyHostToDevice));
+    CK(h2d(h, am.p, a_mean, (size_t)h->E * h->n * sizeof(float)));
     HessianArgs ha = hess_args(h, h->state24.p, h->time.p, am.p, shift, h->R.p, h->hess_ws.p, (long long)h->T * 3);
     cudaError_t e = launch_hessian(ha, h->E, h->own_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->own_stream);
     am.release();
     if (e != cudaSuccess) return fail(COVO_ERR_CUDA, "hessian: %s", cudaGetErrorString(e));
-    CK(cudaMemcpy(R, h->R.p, (size_t)h->E * h->n * h->n * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(d2h(h, R, h->R.p, (size_t)h->E * h->n * h->n * sizeof(float)));
     return COVO_OK;
 }
 
 static int check_status(covo_handle* h, const char* what) {
     std::vector<int> s(h->E);
-    CK(cudaMemcpy(s.data(), h->status.p, h->E * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(d2h(h, s.data(), h->status.p, h->E * sizeof(int)));
     for (int e = 0; e < h->E; ++e)
         if (s[e]) return fail(COVO_ERR_NUMERIC, "%s: numeric status %d in environment %d", what, s[e], e);
     return COVO_OK;
@@ -753,12 +779,12 @@ int covo_optimize_sigma(covo_handle* h, const float* R, float* a_cov) {
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->own_stream));
     size_t bytes = (size_t)h->E * h->n * h->n * sizeof(float);
-    CK(cudaMemcpy(h->R.p, R, bytes, cudaMemcpyHostToDevice));
-    CK(cudaMemset(h->status.p, 0, h->E * sizeof(int)));
+    CK(h2d(h, h->R.p, R, bytes));
+    CK(dzero(h, h->status.p, h->E * sizeof(int)));
     int rc = run_sigma_chol(h, h->own_stream, nullptr);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->own_stream));
-    CK(cudaMemcpy(a_cov, h->cov.p, bytes, cudaMemcpyDeviceToHost));
+    CK(d2h(h, a_cov, h->cov.p, bytes));
     return check_status(h, "optimize_sigma");
 }
 
@@ -767,7 +793,7 @@ int covo_cholesky(covo_handle* h, const float* a_cov, float* L) {
     if (h->cfg.mode == COVO_MODE_MPPI) return fail(COVO_ERR_INVALID, "handle is in MPPI mode");
     int rc = covo_set_cov(h, a_cov);
     if (rc) return rc;
-    CK(cudaMemcpy(L, h->Lfull.p, (size_t)h->E * h->n * h->n * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(d2h(h, L, h->Lfull.p, (size_t)h->E * h->n * h->n * sizeof(float)));
     return check_status(h, "cholesky");
 }
 
@@ -783,14 +809,14 @@ int covo_rollout(covo_handle* h, const float* state24, const int* time, const fl
     DevBuf<float> am, amo;
     CK(am.alloc(E * n));
     CK(amo.alloc(E * n));
-    CK(cudaMemcpy(am.p, a_mean, E * n * sizeof(float), cudaMemcpyHostToDevice));
+    CK(h2d(h, am.p, a_mean, E * n * sizeof(float)));
     const float* eps_d = nullptr;
     if (eps) {
         if (h->eps.n < E * NL * n) {
             h->eps.release();
             CK(h->eps.alloc(E * NL * n));
         }
-        CK(cudaMemcpy(h->eps.p, eps, E * NL * n * sizeof(float), cudaMemcpyHostToDevice));
+        CK(h2d(h, h->eps.p, eps, E * NL * n * sizeof(float)));
         eps_d = h->eps.p;
     }
     const float* fd_d = nullptr;
@@ -799,7 +825,7 @@ int covo_rollout(covo_handle* h, const float* state24, const int* time, const fl
             h->fdist.release();
             CK(h->fdist.alloc(E * h->H * 3));
         }
-        CK(cudaMemcpy(h->fdist.p, fdist_seq, E * h->H * 3 * sizeof(float), cudaMemcpyHostToDevice));
+        CK(h2d(h, h->fdist.p, fdist_seq, E * h->H * 3 * sizeof(float)));
         fd_d = h->fdist.p;
     }
     if (costs && h->costs.n < E * NL) {
@@ -810,7 +836,7 @@ int covo_rollout(covo_handle* h, const float* state24, const int* time, const fl
         h->samples.release();
         CK(h->samples.alloc(E * NL * n));
     }
-    if (h->pos_stats_on) CK(cudaMemset(h->pos_stats.p, 0, h->pos_stats.n * sizeof(float)));
+    if (h->pos_stats_on) CK(dzero(h, h->pos_stats.p, h->pos_stats.n * sizeof(float)));
     const int finalize = (h->cfg.world == 1) ? 1 : 0;
     RolloutArgs ra = rollout_args(h, h->state24.p, h->time.p, am.p, shift, eps_d, fd_d, amo.p, h->action.p,
                                   costs ? h->costs.p : nullptr, samples ? h->samples.p : nullptr, finalize);
@@ -819,10 +845,10 @@ int covo_rollout(covo_handle* h, const float* state24, const int* time, const fl
     if (!eps_d) h->rng_stream += 1;
     int ret = COVO_OK;
     if (e != cudaSuccess) ret = fail(COVO_ERR_CUDA, "rollout: %s", cudaGetErrorString(e));
-    if (!ret && a_mean_out) cudaMemcpy(a_mean_out, amo.p, E * n * sizeof(float), cudaMemcpyDeviceToHost);
-    if (!ret && action) cudaMemcpy(action, h->action.p, E * 4 * sizeof(float), cudaMemcpyDeviceToHost);
-    if (!ret && costs) cudaMemcpy(costs, h->costs.p, E * NL * sizeof(float), cudaMemcpyDeviceToHost);
-    if (!ret && samples) cudaMemcpy(samples, h->samples.p, E * NL * n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (!ret && a_mean_out) d2h(h, a_mean_out, amo.p, E * n * sizeof(float));
+    if (!ret && action) d2h(h, action, h->action.p, E * 4 * sizeof(float));
+    if (!ret && costs) d2h(h, costs, h->costs.p, E * NL * sizeof(float));
+    if (!ret && samples) d2h(h, samples, h->samples.p, E * NL * n * sizeof(float));
     am.release();
     amo.release();
     return ret;
@@ -841,7 +867,7 @@ int covo_get_pos_stats(covo_handle* h, float* pos_mean, float* pos_std) {
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->own_stream));
     std::vector<float> s(h->pos_stats.n);
-    CK(cudaMemcpy(s.data(), h->pos_stats.p, s.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(d2h(h, s.data(), h->pos_stats.p, s.size() * sizeof(float)));
     const double N = (double)h->n_local;
     for (int i = 0; i < h->E * h->H; ++i)
         for (int k = 0; k < 3; ++k) {
@@ -862,7 +888,7 @@ int covo_debug_eps(covo_handle* h, unsigned int stream_id, float* eps) {
     debug_eps_kernel<<<(total + 255) / 256, 256, 0, h->own_stream>>>(d.p, h->n_local, h->sample_offset, h->n, h->cfg.seed, stream_id);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->own_stream);
-    if (e == cudaSuccess) e = cudaMemcpy(eps, d.p, cnt * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = d2h(h, eps, d.p, cnt * sizeof(float));
     d.release();
     if (e != cudaSuccess) return fail(COVO_ERR_CUDA, "debug_eps: %s", cudaGetErrorString(e));
     return COVO_OK;
@@ -873,9 +899,9 @@ int covo_debug_tridiag(covo_handle* h, double* d, double* e, double* scalars5) {
     if (h->cfg.mode == COVO_MODE_MPPI) return fail(COVO_ERR_INVALID, "handle is in MPPI mode");
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->own_stream));
-    CK(cudaMemcpy(d, h->diag.p, h->n * sizeof(double), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(e, h->diag.p + h->n, h->n * sizeof(double), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(scalars5, h->diag.p + 2 * h->n, 5 * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(d2h(h, d, h->diag.p, h->n * sizeof(double)));
+    CK(d2h(h, e, h->diag.p + h->n, h->n * sizeof(double)));
+    CK(d2h(h, scalars5, h->diag.p + 2 * h->n, 5 * sizeof(double)));
     return COVO_OK;
 }
 
@@ -889,7 +915,7 @@ int covo_get_status(covo_handle* h, int* status) {
     if (!h || !status) return fail(COVO_ERR_INVALID, "null argument");
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->own_stream));
-    CK(cudaMemcpy(status, h->status.p, h->E * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(d2h(h, status, h->status.p, h->E * sizeof(int)));
     return COVO_OK;
 }
 
@@ -916,6 +942,14 @@ int covo_get_kernel_ms(covo_handle* h, float* ms6) {
     ms6[4] = t;
     CK(cudaEventElapsedTime(&t, h->ev[5], h->ev[6]));
     ms6[5] = t;
+    return COVO_OK;
+}
+
+int covo_debug_phase_clocks(covo_handle* h, int on, long long* out64) {
+    if (!h) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    h->phase_clocks = on != 0;
+    if (out64) CK(d2h(h, out64, h->prof.p, 64 * sizeof(long long)));
     return COVO_OK;
 }
 

@@ -24,7 +24,13 @@ __host__ __device__ inline int lt_col_offset(int k, int n_pad) {
 }
 __host__ __device__ inline int lt_size(int n, int n_pad) { return lt_col_offset(n, n_pad); }
 
+#define COVO_STAMP(args, slot)                                              \
+    do {                                                                     \
+        if ((args).prof && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) (args).prof[slot] = clock64(); \
+    } while (0)
+
 struct RolloutArgs {
+    long long* prof = nullptr;  // optional: clock64() stamps at phase boundaries (debug)
     int n_samples;      // samples of THIS launch (this rank's shard)
     int sample_offset;  // global index of the first one (N-sharding keeps the RNG field global)
     int H, n, n_pad;

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(160) hess_local_kernel(const HessianArgs a) {
         for (int k = 0; k < 3; ++k) { sfd[k] = fd[k]; spt[k] = pt[k]; svt[k] = vt[k]; }
     }
     __syncthreads();
+    if (a.prof && tid == 0 && t == H - 1 && env == 0) a.prof[6] = clock64();
     if (tid >= NPAIR) return;
     int pa, pb;
     pair_from_index(tid, pa, pb);
@@ -80,136 +81,165 @@ __global__ void __launch_bounds__(160) hess_local_kernel(const HessianArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 constexpr int kAsmThreads = 320;
+constexpr int NZP = 20;  // row pitch of [A_t | B_t] in shared memory: 13 + 4 entries padded to 5 float4
 
 __global__ void __launch_bounds__(kAsmThreads) hess_assemble_kernel(const HessianArgs a) {
     extern __shared__ __align__(16) float smf[];
     const int env = blockIdx.x, tid = threadIdx.x;
     const int H = a.H, n = 4 * H;
-    // shared layout (S and D first: they are read as float4)
+    // shared layout (everything read as float4 first)
     float* S = smf;                    // [H][13][4]
     float* D = S + H * NX * 4;         // [H][4][4]
-    float* G = D + H * 16;             // [H][13][17]  (A_t | B_t)
-    float* cg = G + H * NX * NZ;       // [H][13]
+    float* G = D + H * 16;             // [H][13][NZP]  (A_t | B_t | pad)
+    float* cg = G + H * NX * NZP;      // [H][13]
     float* lam = cg + H * NX;          // [H+1][13]
     float* W = lam + (H + 1) * NX;     // [H][153]
     float* P = W + H * NPAIR;          // [13][13]
-    float* X = P + NX * NX;            // [13][17]
+    float* X = P + NX * NX;            // [13][NZP]
     const float* wsb = a.workspace + (long long)env * H * (14 * NPAIR + 14 * NZ);
     const int rec = 14 * NPAIR + 14 * NZ;
+    COVO_STAMP(a, 0);
 
-    for (int i = tid; i < H * NX * NZ; i += blockDim.x) {
-        int t = i / (NX * NZ), r = i % (NX * NZ);
-        G[i] = wsb[(long long)t * rec + 14 * NPAIR + r];
+    for (int i = tid; i < H * NX * NZP; i += blockDim.x) {
+        int t = i / (NX * NZP), rr = i - t * (NX * NZP);
+        int r = rr / NZP, c = rr - r * NZP;
+        G[i] = (c < NZ) ? wsb[(long long)t * rec + 14 * NPAIR + r * NZ + c] : 0.f;
     }
     for (int i = tid; i < H * NX; i += blockDim.x) {
-        int t = i / NX, k = i % NX;
+        int t = i / NX, k = i - t * NX;
         cg[i] = (t >= 1) ? wsb[(long long)t * rec + 14 * NPAIR + 13 * NZ + k] : 0.f;  // c_0 is constant in U
     }
     for (int i = tid; i < NX; i += blockDim.x) lam[H * NX + i] = 0.f;
     __syncthreads();
+    COVO_STAMP(a, 1);
 
     // adjoint, serial in t, 13 lanes of warp 0
     if (tid < 32) {
         for (int t = H - 1; t >= 1; --t) {
             if (tid < NX) {
                 float acc = cg[t * NX + tid];
-                const float* At = G + t * NX * NZ;
+                const float* At = G + t * NX * NZP;
                 const float* ln = lam + (t + 1) * NX;
 #pragma unroll
-                for (int j = 0; j < NX; ++j) acc = fmaf(At[j * NZ + tid], ln[j], acc);
+                for (int j = 0; j < NX; ++j) acc = fmaf(At[j * NZP + tid], ln[j], acc);
                 lam[t * NX + tid] = acc;
             }
             __syncwarp();
         }
     }
     __syncthreads();
+    COVO_STAMP(a, 2);
 
-    // Lagrangian Hessians W_t (packed upper, 153 entries)
+    // Lagrangian Hessians W_t (packed upper, 153 entries); the 14 loads of one output are in flight together
     for (int i = tid; i < H * NPAIR; i += blockDim.x) {
-        int t = i / NPAIR, pi = i % NPAIR;
+        int t = i / NPAIR, pi = i - t * NPAIR;
         const float* T = wsb + (long long)t * rec;
-        float acc = (t >= 1) ? T[13 * NPAIR + pi] : 0.f;
+        float tv[14];
+#pragma unroll
+        for (int k = 0; k < 14; ++k) tv[k] = __ldg(T + k * NPAIR + pi);
+        float acc = (t >= 1) ? tv[13] : 0.f;
         const float* ln = lam + (t + 1) * NX;
 #pragma unroll
-        for (int k = 0; k < NX; ++k) acc = fmaf(ln[k], T[k * NPAIR + pi], acc);
+        for (int k = 0; k < NX; ++k) acc = fmaf(ln[k], tv[k], acc);
         W[i] = acc;
     }
     for (int i = tid; i < NX * NX; i += blockDim.x) P[i] = 0.f;
     __syncthreads();
+    COVO_STAMP(a, 3);
 
     // backward recursion for P (13x13), S_t (13x4), D_t (4x4)
     for (int t = H - 1; t >= 0; --t) {
-        const float* Gt = G + t * NX * NZ;
-        for (int i = tid; i < NX * NZ; i += blockDim.x) {  // X = P [A B]
-            int r = i / NZ, c = i % NZ;
+        const float* Gt = G + t * NX * NZP;
+        if (tid < NX * NZ) {  // X = P [A B]
+            int r = tid / NZ, c = tid - r * NZ;
             float acc = 0.f;
 #pragma unroll
-            for (int k = 0; k < NX; ++k) acc = fmaf(P[r * NX + k], Gt[k * NZ + c], acc);
-            X[i] = acc;
+            for (int k = 0; k < NX; ++k) acc = fmaf(P[r * NX + k], Gt[k * NZP + c], acc);
+            X[r * NZP + c] = acc;
         }
         __syncthreads();
-        for (int i = tid; i < NZ * NZ; i += blockDim.x) {  // W + [A B]^T X
-            int r = i / NZ, c = i % NZ;
-            if (r >= NX && c < NX) continue;  // lower-left block is the transpose of S, not needed
-            int lo = min(r, c), hi = max(r, c);
-            float acc = W[t * NPAIR + pair_index(lo, hi)];
+        if (tid < NZ * NZ) {  // W + [A B]^T X
+            int r = tid / NZ, c = tid - r * NZ;
+            if (!(r >= NX && c < NX)) {  // lower-left block is the transpose of S, not needed
+                int lo = min(r, c), hi = max(r, c);
+                float acc = W[t * NPAIR + pair_index(lo, hi)];
 #pragma unroll
-            for (int k = 0; k < NX; ++k) acc = fmaf(Gt[k * NZ + r], X[k * NZ + c], acc);
-            if (r < NX && c < NX) P[r * NX + c] = acc;
-            else if (r < NX) S[(t * NX + r) * 4 + (c - NX)] = acc;
-            else D[t * 16 + (r - NX) * 4 + (c - NX)] = acc;
+                for (int k = 0; k < NX; ++k) acc = fmaf(Gt[k * NZP + r], X[k * NZP + c], acc);
+                if (r < NX && c < NX) P[r * NX + c] = acc;
+                else if (r < NX) S[(t * NX + r) * 4 + (c - NX)] = acc;
+                else D[t * 16 + (r - NX) * 4 + (c - NX)] = acc;
+            }
         }
         __syncthreads();
     }
+    COVO_STAMP(a, 4);
 
-    // forward chains: thread (I, c) carries Phi = d x_J / d u_{I,c}
+    // forward chains: thread (I, c) carries Phi = d x_J / d u_{I,c}.  The J loop is uniform across the block,
+    // so every A_J / S_J read is a shared-memory broadcast.
     float* Rg = a.R + (long long)env * n * n;
-    for (int id = tid; id < n; id += blockDim.x) {
-        const int I = id >> 2, c = id & 3;
-        float phi[NX];
-        const float* GI = G + I * NX * NZ;
+    const int id = tid;
+    const bool active = id < n;
+    const int I = id >> 2, c = id & 3;
+    float phi[NX];
+    if (active) {
+        const float* GI = G + I * NX * NZP;
 #pragma unroll
-        for (int k = 0; k < NX; ++k) phi[k] = GI[k * NZ + NX + c];
-        {
-            float4 d = *reinterpret_cast<const float4*>(D + I * 16 + c * 4);
-            // D is symmetric up to round-off; symmetrise so R is exactly symmetric
-            float dd[4] = {d.x, d.y, d.z, d.w};
-            for (int e = 0; e < 4; ++e) dd[e] = 0.5f * (dd[e] + D[I * 16 + e * 4 + c]);
-            *reinterpret_cast<float4*>(Rg + (long long)id * n + 4 * I) = make_float4(dd[0], dd[1], dd[2], dd[3]);
-        }
-        for (int J = I + 1; J < H; ++J) {
-            const float* SJ = S + J * NX * 4;
-            float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
-#pragma unroll
-            for (int k = 0; k < NX; ++k) {
-                float4 sj = *reinterpret_cast<const float4*>(SJ + k * 4);
-                r0 = fmaf(phi[k], sj.x, r0);
-                r1 = fmaf(phi[k], sj.y, r1);
-                r2 = fmaf(phi[k], sj.z, r2);
-                r3 = fmaf(phi[k], sj.w, r3);
-            }
-            *reinterpret_cast<float4*>(Rg + (long long)id * n + 4 * J) = make_float4(r0, r1, r2, r3);
-            Rg[(long long)(4 * J + 0) * n + id] = r0;
-            Rg[(long long)(4 * J + 1) * n + id] = r1;
-            Rg[(long long)(4 * J + 2) * n + id] = r2;
-            Rg[(long long)(4 * J + 3) * n + id] = r3;
-            const float* GJ = G + J * NX * NZ;
-            float nphi[NX];
-#pragma unroll
-            for (int r = 0; r < NX; ++r) {
-                float acc = 0.f;
-#pragma unroll
-                for (int k = 0; k < NX; ++k) acc = fmaf(GJ[r * NZ + k], phi[k], acc);
-                nphi[r] = acc;
-            }
-#pragma unroll
-            for (int k = 0; k < NX; ++k) phi[k] = nphi[k];
-        }
+        for (int k = 0; k < NX; ++k) phi[k] = GI[k * NZP + NX + c];
+        float4 d = *reinterpret_cast<const float4*>(D + I * 16 + c * 4);
+        // D is symmetric up to round-off; symmetrise so R is exactly symmetric
+        float dd[4] = {d.x, d.y, d.z, d.w};
+        for (int e = 0; e < 4; ++e) dd[e] = 0.5f * (dd[e] + D[I * 16 + e * 4 + c]);
+        *reinterpret_cast<float4*>(Rg + (long long)id * n + 4 * I) = make_float4(dd[0], dd[1], dd[2], dd[3]);
     }
+    for (int J = 1; J < H; ++J) {
+        if (!active || J <= I) continue;
+        const float* SJ = S + J * NX * 4;
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NX; ++k) {
+            float4 sj = *reinterpret_cast<const float4*>(SJ + k * 4);
+            r0 = fmaf(phi[k], sj.x, r0);
+            r1 = fmaf(phi[k], sj.y, r1);
+            r2 = fmaf(phi[k], sj.z, r2);
+            r3 = fmaf(phi[k], sj.w, r3);
+        }
+        *reinterpret_cast<float4*>(Rg + (long long)id * n + 4 * J) = make_float4(r0, r1, r2, r3);
+        Rg[(long long)(4 * J + 0) * n + id] = r0;
+        Rg[(long long)(4 * J + 1) * n + id] = r1;
+        Rg[(long long)(4 * J + 2) * n + id] = r2;
+        Rg[(long long)(4 * J + 3) * n + id] = r3;
+        if (J == H - 1) break;
+        const float* GJ = G + J * NX * NZP;
+        float nphi[NX];
+#pragma unroll
+        for (int r = 0; r < NX; ++r) {
+            const float4 a0 = *reinterpret_cast<const float4*>(GJ + r * NZP);
+            const float4 a1 = *reinterpret_cast<const float4*>(GJ + r * NZP + 4);
+            const float4 a2 = *reinterpret_cast<const float4*>(GJ + r * NZP + 8);
+            const float a12 = GJ[r * NZP + 12];
+            float acc = a0.x * phi[0];
+            acc = fmaf(a0.y, phi[1], acc);
+            acc = fmaf(a0.z, phi[2], acc);
+            acc = fmaf(a0.w, phi[3], acc);
+            acc = fmaf(a1.x, phi[4], acc);
+            acc = fmaf(a1.y, phi[5], acc);
+            acc = fmaf(a1.z, phi[6], acc);
+            acc = fmaf(a1.w, phi[7], acc);
+            acc = fmaf(a2.x, phi[8], acc);
+            acc = fmaf(a2.y, phi[9], acc);
+            acc = fmaf(a2.z, phi[10], acc);
+            acc = fmaf(a2.w, phi[11], acc);
+            acc = fmaf(a12, phi[12], acc);
+            nphi[r] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < NX; ++k) phi[k] = nphi[k];
+    }
+    COVO_STAMP(a, 5);
 }
 
 size_t hessian_assemble_smem(int H) {
-    size_t f = (size_t)H * NX * NZ + H * NX + (H + 1) * NX + (size_t)H * NPAIR + H * NX * 4 + H * 16 + NX * NX + NX * NZ;
+    size_t f = (size_t)H * NX * NZP + H * NX + (H + 1) * NX + (size_t)H * NPAIR + H * NX * 4 + H * 16 + NX * NX + NX * NZP;
     return f * sizeof(float);
 }
 

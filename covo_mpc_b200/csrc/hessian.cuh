@@ -5,6 +5,7 @@
 namespace covo {
 
 struct HessianArgs {
+    long long* prof = nullptr;  // optional: clock64() stamps at phase boundaries (debug)
     int H, traj_len, shift;
     long long traj_stride;  // floats between environments in pos_traj / vel_traj (0: shared)
     EnvConsts env;

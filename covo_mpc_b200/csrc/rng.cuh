@@ -43,10 +43,13 @@ __device__ __forceinline__ void philox_normal4(unsigned long long seed, uint32_t
     const float s = 2.3283064365386963e-10f;  // 2^-32
     float u0 = (__uint2float_rn(c[0]) + 0.5f) * s, u1 = (__uint2float_rn(c[1]) + 0.5f) * s;
     float u2 = (__uint2float_rn(c[2]) + 0.5f) * s, u3 = (__uint2float_rn(c[3]) + 0.5f) * s;
-    float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+    // fast intrinsics: MUFU lg2 / rsq / sin / cos; the field only has to be Gaussian, and the oracle is fed the
+    // device's own draws when bit-for-bit agreement matters (covo_debug_eps)
+    const float l0 = -2.0f * __logf(u0), l1 = -2.0f * __logf(u2);
+    const float r0 = l0 * rsqrtf(fmaxf(l0, 1e-30f)), r1 = l1 * rsqrtf(fmaxf(l1, 1e-30f));
     float s0, c0, s1, c1;
-    sincospif(2.0f * u1, &s0, &c0);
-    sincospif(2.0f * u3, &s1, &c1);
+    __sincosf(6.283185307179586f * u1 - 3.141592653589793f, &s0, &c0);
+    __sincosf(6.283185307179586f * u3 - 3.141592653589793f, &s1, &c1);
     z[0] = r0 * c0;
     z[1] = r0 * s0;
     z[2] = r1 * c1;

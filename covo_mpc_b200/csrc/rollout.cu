@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
     const float* lfac_g = a.Lfac + (long long)env * a.lfac_stride;
     if (a.lfac_time_stride) lfac_g += (long long)min(max(a.time[env], 0), a.lfac_time_max) * a.lfac_time_stride;
 
+    COVO_STAMP(a, 32);
     // ---------------- phase 0: staging -------------------------------------------------------
     if (tid == 0) {
         mbar_init(sm.bar, 1);
@@ -218,7 +219,9 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
         }
     }
     __syncthreads();
+    COVO_STAMP(a, 33);
     mbar_wait(sm.bar, 0);
+    COVO_STAMP(a, 34);
 
     // ---------------- phase 1: U = clip(mu + E L^T) ------------------------------------------
     if (a.mode == 0) {
@@ -239,6 +242,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
             const float* Erow = sm.tile + 4 * sg;
             int off = 0;  // lt_col_offset(k)
             int k = 0;
+#pragma unroll 2
             for (; k < kendA; ++k) {
                 const float4 e = *reinterpret_cast<const float4*>(Erow + k * TSP);
                 const float* col = sm.lfac + off - (k & ~7);
@@ -261,6 +265,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
                 }
                 off += n_pad - (k & ~7);
             }
+#pragma unroll 4
             for (; k < kendB; ++k) {
                 const float4 e = *reinterpret_cast<const float4*>(Erow + k * TSP);
                 const float* col = sm.lfac + off - (k & ~7);
@@ -328,6 +333,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
         }
     }
 
+    COVO_STAMP(a, 35);
     // ---------------- phase 2: rollouts --------------------------------------------------------
     if (tid < TS) {
         // lanes past the end of a ragged last tile run the same code on the same state (their U columns
@@ -377,6 +383,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
     }
     __syncthreads();
 
+    COVO_STAMP(a, 36);
     // ---------------- phase 3: tile partial + grid-wide merge ---------------------------------
     float m_b = sm.red[0];
 #pragma unroll
@@ -419,7 +426,9 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
     __shared__ unsigned int s_ticket;
     if (tid == 0) s_ticket = atomicAdd(a.counters + env, 1u);
     __syncthreads();
+    COVO_STAMP(a, 37);
     if (s_ticket != (unsigned)(n_cta - 1)) return;
+    if (a.prof && tid == 0) a.prof[38] = clock64();
 
     // last CTA of this environment: merge all tile partials in tile order (bit-reproducible)
     __threadfence();
@@ -437,13 +446,28 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
         scale[b] = (mb < CUDART_INF_F) ? expf(-(mb - M) * inv_lam) : 0.f;
     }
     __syncthreads();
-    // S in tile order by one thread per 32-tile chunk would need another reduction; n_cta is small, so
-    // every thread accumulates the same ordered sum (deterministic, identical on all threads).
+    // Ordered (bit-reproducible) sums over the tile partials.  Loads are issued eight at a time so the L2
+    // latency of the records overlaps instead of serialising (the partials were written by other SMs).
     float S = 0.f;
-    for (int b = 0; b < n_cta; ++b) S = fmaf(__ldcg(base + (long long)b * rec + 1), scale[b], S);
+    for (int b0 = 0; b0 < n_cta; b0 += 16) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (b0 + j < n_cta) ? __ldcg(base + (long long)(b0 + j) * rec + 1) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (b0 + j < n_cta) S = fmaf(v[j], scale[b0 + j], S);
+    }
     for (int r = tid; r < n_pad; r += blockDim.x) {
         float V = 0.f;
-        for (int b = 0; b < n_cta; ++b) V = fmaf(__ldcg(base + (long long)b * rec + kPartialHdr + r), scale[b], V);
+        for (int b0 = 0; b0 < n_cta; b0 += 16) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                v[j] = (b0 + j < n_cta) ? __ldcg(base + (long long)(b0 + j) * rec + kPartialHdr + r) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (b0 + j < n_cta) V = fmaf(v[j], scale[b0 + j], V);
+        }
         if (a.finalize) {
             if (r < n) {
                 // controllers/covo.py:270-278
@@ -465,6 +489,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
             rp[3] = 0.f;
         }
         a.counters[env] = 0u;  // re-arm for the next launch
+        if (a.prof) a.prof[39] = clock64();
     }
 }
 

@@ -92,11 +92,6 @@ void zolotarev_table(double* table) {
 namespace {
 
 constexpr int TT = 1024;
-// shared region holding the matrix during E1 and the fp64 pivot scratch + (gd, cu) during E2
-__host__ __device__ inline int tridiag_region_floats(int n) {
-    int a = n * n, b = (2 * 2 * (kZoloPoles + 1) * n) * 2 + 2 * kZoloPoles * n;
-    return ((a > b ? a : b) + 3) & ~3;
-}
 constexpr int NPOLE = kZoloPoles;
 
 __device__ __forceinline__ float wsum(float v) {
@@ -122,25 +117,41 @@ __device__ __forceinline__ double wmaxd(double v) {
 
 // number of eigenvalues of tridiag(d, e) strictly below x: sign changes of the Sturm sequence,
 // evaluated division-free with rescaling (a zero term takes the sign opposite to its predecessor).
-__device__ int sturm_count(const double* d, const double* e, int n, double x) {
+__device__ int sturm_count(const double* d, const double* e2, int n, double x) {
+    // e2[i] = e[i]^2 (coupling between i and i+1).  The loads run one iteration ahead of the fp64 chain.
     double pm = 1.0, p = d[0] - x;
     if (p == 0.0) p = -1e-300;
-    int cnt = p < 0.0;
-    for (int i = 1; i < n; ++i) {
-        double e2 = e[i - 1] * e[i - 1];
-        double pn = (d[i] - x) * p - e2 * pm;
-        if (pn == 0.0) pn = (p > 0.0) ? -1e-300 : 1e-300;
-        cnt += ((pn < 0.0) != (p < 0.0));
-        double ap = fabs(pn);
-        if (ap > 1e200) {
-            pn *= 1e-200;
-            p *= 1e-200;
-        } else if (ap < 1e-200) {
-            pn *= 1e200;
-            p *= 1e200;
+    int cnt = (__double2hiint(p) >> 31) & 1;
+    double dn = d[1], en = e2[0];
+    for (int i0 = 1; i0 < n; i0 += 8) {
+        const int i1 = min(i0 + 8, n);
+        for (int i = i0; i < i1; ++i) {
+            const double di = dn, ei = en;
+            if (i + 1 < n) {
+                dn = d[i + 1];
+                en = e2[i];
+            }
+            double pn = fma(di - x, p, -(ei * pm));
+            // sign tests on the high word (integer pipe): only the recurrence itself runs on the fp64 pipe
+            int hn = __double2hiint(pn);
+            const int hp = __double2hiint(p);
+            if (((hn & 0x7fffffff) | __double2loint(pn)) == 0) {
+                pn = (hp < 0) ? 1e-300 : -1e-300;
+                hn = __double2hiint(pn);
+            }
+            cnt += ((hn ^ hp) >> 31) & 1;
+            pm = p;
+            p = pn;
         }
-        pm = p;
-        p = pn;
+        // the terms grow by at most ~(|d - x| + |e|) per step, so a range check every 8 steps is enough
+        const int ex = (__double2hiint(p) >> 20) & 0x7ff;
+        if (ex > 1023 + 400) {
+            p *= 1e-120;
+            pm *= 1e-120;
+        } else if (ex < 1023 - 400) {
+            p *= 1e120;
+            pm *= 1e120;
+        }
     }
     return cnt;
 }
@@ -150,131 +161,240 @@ __device__ int sturm_count(const double* d, const double* e, int n, double x) {
 // ---------------------------------------------------------------------------------------------
 // E1 + E2
 // ---------------------------------------------------------------------------------------------
+// Row pitch of the shared-memory matrix: n + 4 or n + 8 so that pitch == 4 (mod 8): eight consecutive rows
+// of one float4 column group then fall into eight different bank quadruples (conflict-free LDS.128).
+__host__ __device__ inline int tridiag_pitch(int n) { return (n & 7) ? n + 8 : n + 4; }
+__host__ __device__ inline int tridiag_region_floats(int n) {
+    int a = n * tridiag_pitch(n);
+    // E2 scratch: fp64 pivot numerators/denominators [2][2][17][n], then float gd[16][n], and the
+    // (hi, lo, sign/zero) prefix arrays of the semiseparable generators [16][n+1] x 3
+    int b = (2 * 2 * (kZoloPoles + 1) * n) * 2 + kZoloPoles * n + 3 * kZoloPoles * (n + 1);
+    return ((a > b ? a : b) + 3) & ~3;
+}
+
 __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int n = a.n, tid = threadIdx.x, env = blockIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* As = reinterpret_cast<float*>(smraw);  // [n][n]
-    float* part = As + tridiag_region_floats(n);  // [4096]
-    float* vs = part + 4096;                      // [256] zero-extended Householder vector
-    float* ws = vs + 256;                         // [256]
-    double* dd = reinterpret_cast<double*>(ws + 256);  // [256]
-    double* ee = dd + 256;                             // [256]
-    double* sc = ee + 256;                             // [16] scalars
-    float* red = reinterpret_cast<float*>(sc + 16);    // [64]
-    int* ired = reinterpret_cast<int*>(red + 64);      // [4]
+    const int LD = tridiag_pitch(n);
+    float* As = reinterpret_cast<float*>(smraw);          // [n][LD]
+    float* vs = As + tridiag_region_floats(n);            // [2048] v/q double buffers + w (see E1)
+    float* ws = vs + 256;
+    double* dd = reinterpret_cast<double*>(vs + 2048);    // [256]
+    double* ee = dd + 256;                                // [256]
+    double* e2s = ee + 256;                               // [256] e^2
+    double* sc = e2s + 256;                               // [16] scalars
+    double* rdbuf = sc + 16;                              // [64]
+    float* red = reinterpret_cast<float*>(rdbuf + 64);    // [64]
+    int* ired = reinterpret_cast<int*>(red + 64);         // [4]
 
     const float* Rg = a.R + (long long)env * n * n;
     float* Vg = a.Vh + (long long)env * n * n;
     float* taug = a.tau + (long long)env * n;
 
-    for (int idx = tid; idx < n * n; idx += TT) {
-        int i = idx / n, j = idx - i * n;
-        As[idx] = 0.5f * (Rg[idx] + Rg[j * n + i]);  // R <- (R + R^T)/2, controllers/covo.py:117
-    }
-    if (tid < 256) {
-        vs[tid] = 0.f;
-        ws[tid] = 0.f;
+    // R <- (R + R^T)/2 (controllers/covo.py:117): coalesced load, then symmetrise in shared memory
+    for (int i = warp; i < n; i += TT / 32)
+        for (int j = lane; j < n; j += 32) As[i * LD + j] = Rg[i * n + j];
+    for (int i = tid; i < 2048; i += TT) vs[i] = 0.f;
+    __syncthreads();
+    for (int i = warp; i < n; i += TT / 32)
+        for (int j = lane; j < i; j += 32) {
+            const float s2 = 0.5f * (As[i * LD + j] + As[j * LD + i]);
+            As[i * LD + j] = s2;
+            As[j * LD + i] = s2;
+        }
+    __syncthreads();
+    COVO_STAMP(a, 8);
+
+    // ---- E1: Householder tridiagonalisation (LAPACK ssytd2 recurrences), one pass over A per step -----
+    // thread = (column group cgi of 4 columns, row class ch of 16): rows k+1+ch, k+1+ch+16, ...
+    // State entering step k: A updated through step k-1; v_k (vs[cur], zero-extended, v[k+1] = 1), tau_k and
+    // the raw matvec q_k = A v_k (qs[cur]).  Step k:
+    //   A) s = q.v (block reduction)                      -> w = tau q - (tau^2 s / 2) v
+    //   B) warp 0 forms the UPDATED row k+1 from (A, v, w), i.e. the next Householder vector v_{k+1}
+    //      (look-ahead) while the other threads publish w;
+    //   C) one pass: A <- A - v w^T - w v^T fused with q_{k+1} = A_new v_{k+1}.
+    const int cgi = tid >> 4, ch = tid & 15;
+    float* vbuf[2] = {vs, vs + 512};  // vs, ws are reused as [cur/next] v and q buffers (4 x 256 floats total)
+    float* qbuf[2] = {ws, ws + 512};
+    // layout: vs[0..255] v0 | ws[0..255] q0 | vs+512 v1 | ws+512 q1   (allocated below: 1024 floats)
+    int cur = 0;
+    // prologue: v_0, tau_0 from row 0; q_0 = A v_0
+    if (warp == 0) {
+        const float* x = As;
+        float sig = 0.f;
+        for (int j = 2 + lane; j < n; j += 32) sig = fmaf(x[j], x[j], sig);
+        sig = wsum(sig);
+        const float x0 = x[1];
+        float beta, tau, scale;
+        if (sig == 0.f) {
+            beta = x0; tau = 0.f; scale = 0.f;
+        } else {
+            beta = -copysignf(sqrtf(fmaf(x0, x0, sig)), x0);
+            tau = (beta - x0) / beta;
+            scale = 1.0f / (x0 - beta);
+        }
+        for (int j = lane; j < 256; j += 32) {
+            float v = 0.f;
+            if (j == 1) v = 1.f;
+            else if (j >= 2 && j < n && tau != 0.f) v = x[j] * scale;
+            vbuf[0][j] = v;
+        }
+        if (lane == 0) {
+            red[0] = beta;
+            red[1] = tau;
+        }
     }
     __syncthreads();
-
-    // ---- E1: Householder tridiagonalisation (LAPACK ssytd2 recurrences) -----------------------
+    {
+        const int c0 = 0, col = c0 + 4 * cgi;
+        const bool active = cgi < (n >> 2);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) {
+            for (int i = 1 + ch; i < n; i += 16) {
+                const float4 av = *reinterpret_cast<const float4*>(As + i * LD + col);
+                const float vi = vbuf[0][i];
+                acc.x = fmaf(av.x, vi, acc.x);
+                acc.y = fmaf(av.y, vi, acc.y);
+                acc.z = fmaf(av.z, vi, acc.z);
+                acc.w = fmaf(av.w, vi, acc.w);
+            }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+        }
+        if (active && ch == 0) *reinterpret_cast<float4*>(qbuf[0] + col) = acc;
+    }
+    __syncthreads();
+    long long pa[6] = {0, 0, 0, 0, 0, 0}, pt0 = 0;
+#define PH(i) do { if (a.prof && tid == 0) { long long t_ = clock64(); pa[i] += t_ - pt0; pt0 = t_; } } while (0)
+    if (a.prof && tid == 0) pt0 = clock64();
     for (int k = 0; k < n - 2; ++k) {
-        if (warp == 0) {
-            const float* x = As + k * n;
-            float s = 0.f;
-            for (int j = k + 2 + lane; j < n; j += 32) s = fmaf(x[j], x[j], s);
-            s = wsum(s);
-            float x0 = x[k + 1];
-            float beta, tau, scale;
-            if (s == 0.f) {
-                beta = x0;
-                tau = 0.f;
-                scale = 0.f;
-            } else {
-                beta = -copysignf(sqrtf(fmaf(x0, x0, s)), x0);
-                tau = (beta - x0) / beta;
-                scale = 1.0f / (x0 - beta);
-            }
-            if (lane == 0) {
-                red[0] = beta;
-                red[1] = tau;
-                red[2] = scale;
-            }
-        }
-        __syncthreads();
-        const float beta = red[0], tau = red[1], scale = red[2];
-        if (tid < n) {
-            float v = (tid <= k) ? 0.f : ((tid == k + 1) ? 1.f : As[k * n + tid] * scale);
-            if (tau == 0.f && tid > k + 1) v = 0.f;
-            vs[tid] = v;
-            Vg[k * n + tid] = v;
-        }
+        const float* v = vbuf[cur];
+        const float* q = qbuf[cur];
+        float* vn = vbuf[cur ^ 1];
+        float* qn = qbuf[cur ^ 1];
+        const float beta = red[0], tau = red[1];
+        // A) s = q.v over j > k
+        float part = (tid < n && tid > k) ? q[tid] * v[tid] : 0.f;
+        part = wsum(part);
+        if (lane == 0) red[8 + warp] = part;
+        if (tid < n) Vg[k * n + tid] = v[tid];
         if (tid == 0) {
-            dd[k] = (double)As[k * n + k];
+            dd[k] = (double)As[k * LD + k];
             ee[k] = (double)beta;
             taug[k] = tau;
         }
         __syncthreads();
-        if (tau != 0.f) {  // block-uniform
+        PH(0);
+        float sdot = 0.f;
+#pragma unroll
+        for (int w = 0; w < TT / 32; ++w) sdot += red[8 + w];
+        const float c2 = 0.5f * tau * tau * sdot;
+        // B) publish w (any thread), look-ahead Householder for step k+1 (warp 0)
+        if (tid < 256) ws[1024 + tid] = (tid < n && tid > k) ? fmaf(tau, q[tid], -c2 * v[tid]) : 0.f;
+        if (warp == 0) {
+            const int r1 = k + 1;                               // row being finalised
+            const float wr1 = fmaf(tau, q[r1], -c2 * v[r1]);    // w_{k+1}  (v_{k+1} = 1)
+            const float* arow = As + r1 * LD;
+            float rj[8];
+            float sig = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int j = lane + 32 * t;
+                float r = 0.f;
+                if (j >= k + 2 && j < n) {
+                    const float wj = fmaf(tau, q[j], -c2 * v[j]);
+                    r = arow[j] - wj - wr1 * v[j];               // updated A[k+1][j]
+                }
+                rj[t] = r;
+                if (j >= k + 3) sig = fmaf(r, r, sig);
+            }
+            sig = wsum(sig);
+            // x0 = updated A[k+1][k+2], held by lane (k+2) & 31, slot (k+2) >> 5
+            float x0 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float cand = __shfl_sync(0xffffffffu, rj[t], (k + 2) & 31);
+                if (t == ((k + 2) >> 5)) x0 = cand;
+            }
+            float nbeta, ntau, nscale;
+            if (k + 2 >= n) {
+                nbeta = 0.f; ntau = 0.f; nscale = 0.f;
+            } else if (sig == 0.f) {
+                nbeta = x0; ntau = 0.f; nscale = 0.f;
+            } else {
+                nbeta = -copysignf(sqrtf(fmaf(x0, x0, sig)), x0);
+                ntau = (nbeta - x0) / nbeta;
+                nscale = 1.0f / (x0 - nbeta);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int j = lane + 32 * t;
+                float vv = 0.f;
+                if (j == k + 2 && j < n) vv = 1.f;
+                else if (j >= k + 3 && j < n && ntau != 0.f) vv = rj[t] * nscale;
+                vn[j] = vv;
+            }
+            if (lane == 0) {
+                red[2] = nbeta;
+                red[3] = ntau;
+            }
+        }
+        __syncthreads();
+        PH(1);
+        // C) fused pass
+        {
+            const float* wv = ws + 1024;
             const int c0 = (k + 1) & ~3;
             const int ncg = (n - c0) >> 2;
-            const int m = n - (k + 1);
-            const int chunks = min(TT / ncg, m);
-            const int rows_per = (m + chunks - 1) / chunks;
-            const int cg = tid % ncg, ch = tid / ncg;
-            const int i0 = k + 1 + ch * rows_per, i1 = min(i0 + rows_per, n);
-            // p = tau * A v   (column partials over row chunks; A symmetric)
-            if (ch < chunks) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int i = i0; i < i1; ++i) {
-                    const float4 av = *reinterpret_cast<const float4*>(As + i * n + c0 + 4 * cg);
-                    const float vi = vs[i];
-                    acc.x = fmaf(av.x, vi, acc.x);
-                    acc.y = fmaf(av.y, vi, acc.y);
-                    acc.z = fmaf(av.z, vi, acc.z);
-                    acc.w = fmaf(av.w, vi, acc.w);
-                }
-                *reinterpret_cast<float4*>(part + (ch * ncg + cg) * 4) = acc;
-            }
-            __syncthreads();
-            float pj = 0.f, contrib = 0.f;
-            if (tid < n && tid > k) {
-                const int g = (tid - c0) >> 2, comp = (tid - c0) & 3;
-                float s = 0.f;
-                for (int c = 0; c < chunks; ++c) s += part[(c * ncg + g) * 4 + comp];
-                pj = tau * s;
-                contrib = pj * vs[tid];
-            }
-            contrib = wsum(contrib);
-            if (lane == 0) red[8 + warp] = contrib;
-            __syncthreads();
-            float alpha = 0.f;
-#pragma unroll
-            for (int w = 0; w < TT / 32; ++w) alpha += red[8 + w];
-            if (tid < n) ws[tid] = (tid > k) ? pj - 0.5f * tau * alpha * vs[tid] : 0.f;
-            __syncthreads();
-            // A <- A - v w^T - w v^T
-            if (ch < chunks) {
-                const float4 wj = *reinterpret_cast<const float4*>(ws + c0 + 4 * cg);
-                const float4 vj = *reinterpret_cast<const float4*>(vs + c0 + 4 * cg);
-                for (int i = i0; i < i1; ++i) {
-                    const float vi = vs[i], wi = ws[i];
-                    float4* p = reinterpret_cast<float4*>(As + i * n + c0 + 4 * cg);
+            const bool active = cgi < ncg;
+            const int col = c0 + 4 * cgi;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active) {
+                const float4 wj = *reinterpret_cast<const float4*>(wv + col);
+                const float4 vj = *reinterpret_cast<const float4*>(v + col);
+#pragma unroll 2
+                for (int i = k + 1 + ch; i < n; i += 16) {
+                    const float vi = v[i], wi = wv[i], vni = vn[i];
+                    float4* p = reinterpret_cast<float4*>(As + i * LD + col);
                     float4 av = *p;
                     av.x -= fmaf(vi, wj.x, wi * vj.x);
                     av.y -= fmaf(vi, wj.y, wi * vj.y);
                     av.z -= fmaf(vi, wj.z, wi * vj.z);
                     av.w -= fmaf(vi, wj.w, wi * vj.w);
                     *p = av;
+                    acc.x = fmaf(av.x, vni, acc.x);
+                    acc.y = fmaf(av.y, vni, acc.y);
+                    acc.z = fmaf(av.z, vni, acc.z);
+                    acc.w = fmaf(av.w, vni, acc.w);
                 }
             }
-            __syncthreads();
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+            }
+            if (active && ch == 0) *reinterpret_cast<float4*>(qn + col) = acc;
+            if (tid == 0) {
+                red[0] = red[2];
+                red[1] = red[3];
+            }
         }
+        __syncthreads();
+        PH(2);
+        cur ^= 1;
     }
+    if (a.prof && tid == 0) for (int i = 0; i < 5; ++i) a.prof[40 + i] = pa[i];
     if (tid == 0) {
-        dd[n - 2] = (double)As[(n - 2) * n + (n - 2)];
-        dd[n - 1] = (double)As[(n - 1) * n + (n - 1)];
-        ee[n - 2] = (double)As[(n - 1) * n + (n - 2)];
+        dd[n - 2] = (double)As[(n - 2) * LD + (n - 2)];
+        dd[n - 1] = (double)As[(n - 1) * LD + (n - 1)];
+        ee[n - 2] = (double)As[(n - 1) * LD + (n - 2)];
         ee[n - 1] = 0.0;
         taug[n - 2] = 0.f;
         taug[n - 1] = 0.f;
@@ -284,6 +404,7 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
         Vg[(n - 1) * n + tid] = 0.f;
     }
     __syncthreads();
+    COVO_STAMP(a, 9);
 
     // ---- E2: everything on the tridiagonal, fp64 ---------------------------------------------
     // Gershgorin interval
@@ -294,19 +415,19 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
             lo = dd[tid] - r;
             hi = dd[tid] + r;
         }
+        if (tid < n) e2s[tid] = ee[tid] * ee[tid];
         lo = wmind(lo);
         hi = wmaxd(hi);
-        double* rd = reinterpret_cast<double*>(part);
         if (lane == 0) {
-            rd[warp] = lo;
-            rd[32 + warp] = hi;
+            rdbuf[warp] = lo;
+            rdbuf[32 + warp] = hi;
         }
         __syncthreads();
         if (tid == 0) {
-            double l = rd[0], h = rd[32];
+            double l = rdbuf[0], h = rdbuf[32];
             for (int w = 1; w < TT / 32; ++w) {
-                l = fmin(l, rd[w]);
-                h = fmax(h, rd[32 + w]);
+                l = fmin(l, rdbuf[w]);
+                h = fmax(h, rdbuf[32 + w]);
             }
             double pad = 1e-9 * fmax(1.0, fmax(fabs(l), fabs(h)));
             sc[0] = l - pad;
@@ -316,22 +437,30 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
         }
         __syncthreads();
     }
-    // lam_min by multisection: 5 rounds x 1025-fold shrink
-    for (int round = 0; round < 5; ++round) {
+    COVO_STAMP(a, 10);
+    // lam_min by multisection.  fp64 issues at ~1/9 of the fp32 rate on this part and the Sturm recurrence is
+    // a serial chain, so the cost is (evaluation points) x (rounds): 128 points (one warp per scheduler) x 6
+    // rounds shrink the Gershgorin bracket by 129^6 ~ 4.6e12, i.e. to ~1e-11 absolute.
+    constexpr int MS = 128;
+    for (int round = 0; round < 6; ++round) {
         const double lo = sc[0], hi = sc[1];
-        if (tid == 0) ired[0] = TT;
+        if (tid == 0) ired[0] = MS;
         __syncthreads();
-        const double x = lo + (hi - lo) * ((double)(tid + 1) / (double)(TT + 1));
-        if (sturm_count(dd, ee, n, x) >= 1) atomicMin(ired, tid);
+        // spread the four evaluation warps over the four schedulers: warps 0..3
+        if (tid < MS) {
+            const double x = lo + (hi - lo) * ((double)(tid + 1) / (double)(MS + 1));
+            if (sturm_count(dd, e2s, n, x) >= 1) atomicMin(ired, tid);
+        }
         __syncthreads();
         if (tid == 0) {
             const int ts = ired[0];
-            const double step = (hi - lo) / (double)(TT + 1);
+            const double step = (hi - lo) / (double)(MS + 1);
             sc[0] = (ts == 0) ? lo : lo + step * ts;
-            sc[1] = (ts == TT) ? hi : lo + step * (ts + 1);
+            sc[1] = (ts == MS) ? hi : lo + step * (ts + 1);
         }
         __syncthreads();
     }
+    COVO_STAMP(a, 11);
     const double lam_min = 0.5 * (sc[0] + sc[1]);
     const double shift0 = kCovoOffset - lam_min;  // T_s = T + shift0 I
     // ladder index from the Gershgorin upper bound of T_s
@@ -350,10 +479,10 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
     const double* zw = zt + NPOLE;                        // w_j
 
     // pivots of T_s + t_q, q = 0..15 (q = 16: unshifted, for log det): product recurrences, rescaled
-    double* num = reinterpret_cast<double*>(As);        // [2][17][n]
-    double* den = num + 2 * (NPOLE + 1) * n;            // [2][17][n]
-    float* gd = reinterpret_cast<float*>(den + 2 * (NPOLE + 1) * n);  // [16][n]  diag of (T_s+t_q)^-1
-    float* cu = gd + NPOLE * n;                                        // [16][n]  -b_l / dm_{l+1}
+    double* num = reinterpret_cast<double*>(As);                      // [2][17][n]
+    double* den = num + 2 * (NPOLE + 1) * n;                          // [2][17][n]
+    float* gd = reinterpret_cast<float*>(den + 2 * (NPOLE + 1) * n);  // [16][n]    diag of (T_s+t_q)^-1
+    float* lcl = gd + NPOLE * n;                                      // [16][n+1]  c_q[l]
     if (tid < NPOLE + 1 || (tid >= 32 && tid < 32 + NPOLE + 1)) {
         const bool fwd = tid < 32;
         const int q = fwd ? tid : tid - 32;
@@ -361,44 +490,50 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
         double* nm = num + ((fwd ? 0 : 1) * (NPOLE + 1) + q) * n;
         double* dn = den + ((fwd ? 0 : 1) * (NPOLE + 1) + q) * n;
         double pm = 0.0, p = 1.0;
+        const double sh = shift0 + tq;
+        double an = dd[fwd ? 0 : n - 1] + sh, bn = 0.0;
         for (int s = 0; s < n; ++s) {
             const int i = fwd ? s : n - 1 - s;
-            const double ai = dd[i] + shift0 + tq;
-            double b2 = 0.0;
-            if (s > 0) {
-                const double b = fwd ? ee[i - 1] : ee[i];
-                b2 = b * b;
+            const double ai = an, b2 = bn;
+            if (s + 1 < n) {  // operands of the next step, off the dependent chain
+                const int i2 = fwd ? s + 1 : n - 2 - s;
+                an = dd[i2] + sh;
+                bn = e2s[fwd ? i2 - 1 : i2];
             }
-            double pn = ai * p - b2 * pm;
+            double pn = fma(ai, p, -(b2 * pm));
             nm[i] = pn;
             dn[i] = p;
-            const double ap = fabs(pn);
-            if (ap > 1e200) {
-                pn *= 1e-200;
-                p *= 1e-200;
-            } else if (ap < 1e-200) {
-                pn *= 1e200;
-                p *= 1e200;
+            // range control on the exponent field (integer test, keeps the fp64 pipe for the recurrence)
+            const int ex = (__double2hiint(pn) >> 20) & 0x7ff;
+            if (ex > 1023 + 400) {
+                pn *= 1e-120;
+                p *= 1e-120;
+            } else if (ex < 1023 - 400) {
+                pn *= 1e120;
+                p *= 1e120;
             }
             pm = p;
             p = pn;
         }
     }
     __syncthreads();
+    COVO_STAMP(a, 12);
     // log det T_s = sum log dp_i (unshifted forward pivots)
     {
         double l = 0.0;
         if (tid < n) l = log(num[(0 * (NPOLE + 1) + NPOLE) * n + tid] / den[(0 * (NPOLE + 1) + NPOLE) * n + tid]);
         l = wsumd(l);
-        double* rd = reinterpret_cast<double*>(part);
-        if (lane == 0) rd[warp] = l;
+        if (lane == 0) rdbuf[warp] = l;
         __syncthreads();
         if (tid == 0) {
             double s = 0.0;
-            for (int w = 0; w < TT / 32; ++w) s += rd[w];
+            for (int w = 0; w < TT / 32; ++w) s += rdbuf[w];
             sc[4] = s;
         }
     }
+    // generators of the semiseparable inverses: (T_s+t_q)^-1[i][l] = g_q[i] * prod_{s=i}^{l-1} c_q[s], l >= i,
+    //   g_q[i] = 1 / (dp_i + dm_i - a_i),   c_q[s] = -b_s / dm_{s+1}   (c = 0 where the tridiagonal splits).
+    float* cq = lcl;  // [16][n+1]: c_q[l] as float (re-uses the slot of the lo log-prefix, which is not needed)
     for (int idx = tid; idx < NPOLE * n; idx += TT) {
         const int q = idx / n, i = idx - q * n;
         const double tq = zt[q];
@@ -411,33 +546,58 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
             const double dm1 = num[(1 * (NPOLE + 1) + q) * n + i + 1] / den[(1 * (NPOLE + 1) + q) * n + i + 1];
             c = (float)(-ee[i] / dm1);
         }
-        cu[idx] = c;
+        cq[q * (n + 1) + i] = c;
     }
     __syncthreads();
-    // F = exp(log_const / 2) * sum_q w_q (T_s + t_q)^-1, written straight to HBM (rows i and n-1-i per thread)
+    // P32_q[l] = prod_{s=l}^{l+31} c_q[s]: the factor that advances an entry 32 columns along a row.
+    // It overwrites the (now dead) pivot scratch at the start of the region.
+    float* p32 = reinterpret_cast<float*>(num);  // [16][n]
+    for (int idx = tid; idx < NPOLE * n; idx += TT) {
+        const int q = idx / n, l = idx - q * n;
+        float pr = 0.f;
+        if (l + 32 <= n - 1) {
+            pr = 1.f;
+#pragma unroll 8
+            for (int s2 = 0; s2 < 32; ++s2) pr *= cq[q * (n + 1) + l + s2];
+        }
+        p32[idx] = pr;
+    }
+    __syncthreads();
+    COVO_STAMP(a, 13);
+    // F = exp(log_const / 2) * sum_q w_q (T_s + t_q)^-1, upper triangle only (row i, columns l >= i): one warp
+    // per row, lanes over the columns (coalesced stores).  Lane j starts at column i + j with the product of
+    // its first j factors (a 5-step warp scan per pole), then hops 32 columns at a time with P32.
     {
         const double logdet = sc[4];
         // controllers/covo.py:124-128: log_const = (n * 2 log(sigma) * 2 + sum log o) / n
         const double log_const = (4.0 * n * log((double)a.sample_sigma) + logdet) / (double)n;
         const float cscale = (float)exp(0.5 * log_const);
         float* Fg = a.F + (long long)env * n * n;
-        float wq[NPOLE];
+        for (int i = warp; i < n; i += TT / 32) {
+            float val[NPOLE];
 #pragma unroll
-        for (int q = 0; q < NPOLE; ++q) wq[q] = (float)zw[q] * cscale;
-        if (tid < n) {
-            // thread t < n/2 takes row t, thread t >= n/2 takes row n-1-(t-n/2): balances the chain lengths per warp
-            const int i = (tid < n / 2) ? tid : (n - 1 - (tid - n / 2));
-            float prod[NPOLE];
+            for (int q = 0; q < NPOLE; ++q) {
+                // exclusive prefix product of c_q[i .. i+31] across the lanes
+                float c = (i + lane < n) ? cq[q * (n + 1) + i + lane] : 0.f;
+                float pr = c;
 #pragma unroll
-            for (int q = 0; q < NPOLE; ++q) prod[q] = gd[q * n + i];
-            for (int l = i; l < n; ++l) {
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float up = __shfl_up_sync(0xffffffffu, pr, o);
+                    if (lane >= o) pr *= up;
+                }
+                float ex = __shfl_up_sync(0xffffffffu, pr, 1);
+                if (lane == 0) ex = 1.f;
+                val[q] = gd[q * n + i] * ex * ((float)zw[q] * cscale);
+            }
+            for (int l = i + lane; l < n; l += 32) {
                 float f = 0.f;
 #pragma unroll
-                for (int q = 0; q < NPOLE; ++q) f = fmaf(wq[q], prod[q], f);
+                for (int q = 0; q < NPOLE; ++q) f += val[q];
                 Fg[(long long)i * n + l] = f;
-                Fg[(long long)l * n + i] = f;
+                if (l + 32 < n) {
 #pragma unroll
-                for (int q = 0; q < NPOLE; ++q) prod[q] *= cu[q * n + l];
+                    for (int q = 0; q < NPOLE; ++q) val[q] *= p32[q * n + l];
+                }
             }
         }
         if (tid == 0) {
@@ -454,87 +614,161 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
             dg[n + tid] = ee[tid];
         }
     }
+    __syncthreads();
+    COVO_STAMP(a, 14);
 }
 
 // ---------------------------------------------------------------------------------------------
-// E3: out(:, c) = Q in(c, :)^T, one warp per vector; Q = H_0 H_1 ... H_{n-3}
+// E3: out(:, c) = Q in(c, :)^T;  Q = H_0 H_1 ... H_{n-3}.  One warp owns two vectors (their elements spread
+// over the lanes, 7 registers each); the reflectors stream through shared memory in chunks of 32 rows with a
+// two-stage cp.async pipeline, so the serial chain per reflector is dot -> 5 shuffles -> axpy and nothing waits
+// on global memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int kApplyWarps = 8;
-constexpr int kMaxLi = kSigmaMaxN / 32;  // 7
+constexpr int kApplyCols = 2;                 // vectors per warp
+constexpr int kApplyChunk = 32;               // reflectors per pipeline stage
+constexpr int kMaxLi = kSigmaMaxN / 32;       // 7
 
-template <bool STORE_STRIDED>
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <bool STORE_STRIDED, bool UPPER_ONLY>
 __global__ void __launch_bounds__(kApplyWarps * 32) applyq_kernel(const float* __restrict__ Vh,
                                                                  const float* __restrict__ tau,
                                                                  const float* __restrict__ in, float* __restrict__ out,
                                                                  int n) {
+    extern __shared__ __align__(16) float sv[];  // [2][kApplyChunk][n] reflectors, then [2][kApplyChunk] tau
     const int env = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * kApplyWarps + warp;
-    if (c >= n) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = (blockIdx.x * kApplyWarps + warp) * kApplyCols;
     Vh += (long long)env * n * n;
     tau += (long long)env * n;
     in += (long long)env * n * n;
     out += (long long)env * n * n;
-    float x[kMaxLi], v[kMaxLi], vn[kMaxLi];
+    float* stau = sv + 2 * kApplyChunk * n;
+    float x[kApplyCols][kMaxLi];
 #pragma unroll
-    for (int li = 0; li < kMaxLi; ++li) {
-        int i = lane + 32 * li;
-        x[li] = (i < n) ? in[(long long)c * n + i] : 0.f;
-    }
-    int k = n - 3;
+    for (int j = 0; j < kApplyCols; ++j)
 #pragma unroll
-    for (int li = 0; li < kMaxLi; ++li) {
-        int i = lane + 32 * li;
-        v[li] = (i < n && k >= 0) ? __ldg(Vh + (long long)k * n + i) : 0.f;
-    }
-    for (; k >= 0; --k) {
-        const float tk = __ldg(tau + k);
-        if (k > 0) {
+        for (int li = 0; li < kMaxLi; ++li) {
+            int i = lane + 32 * li;
+            float xv = 0.f;
+            if (i < n && c0 + j < n) {
+                const int cc = c0 + j;
+                // `in` is symmetric; when only its upper triangle is stored (F), read (min, max)
+                xv = UPPER_ONLY ? in[(long long)min(cc, i) * n + max(cc, i)] : in[(long long)cc * n + i];
+            }
+            x[j][li] = xv;
+        }
+    const int nref = n - 2;                                   // reflectors k = 0 .. n-3, applied in descending k
+    const int nchunks = (nref + kApplyChunk - 1) / kApplyChunk;
+    const int vec_per_row = n >> 2;
+    auto prefetch = [&](int j) {
+        // chunk j holds k = kh, kh-1, ..., kl  (kh = n-3 - j*chunk); stored so that slot s <-> k = kh - s
+        const int kh = n - 3 - j * kApplyChunk;
+        const int cnt = min(kApplyChunk, kh + 1);
+        float* dst = sv + (j & 1) * kApplyChunk * n;
+        for (int idx = tid; idx < cnt * vec_per_row; idx += kApplyWarps * 32) {
+            int s = idx / vec_per_row, v4 = idx - s * vec_per_row;
+            cp_async16(dst + s * n + 4 * v4, Vh + (long long)(kh - s) * n + 4 * v4);
+        }
+        if (tid < cnt) stau[(j & 1) * kApplyChunk + tid] = __ldg(tau + kh - tid);
+        cp_async_commit();
+    };
+    prefetch(0);
+    for (int j = 0; j < nchunks; ++j) {
+        if (j + 1 < nchunks) {
+            prefetch(j + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int kh = n - 3 - j * kApplyChunk;
+        const int cnt = min(kApplyChunk, kh + 1);
+        const float* buf = sv + (j & 1) * kApplyChunk * n;
+        const float* tb = stau + (j & 1) * kApplyChunk;
+        for (int s = 0; s < cnt; ++s) {
+            const float tk = tb[s];
+            if (tk == 0.f) continue;  // warp-uniform
+            float v[kMaxLi];
 #pragma unroll
             for (int li = 0; li < kMaxLi; ++li) {
                 int i = lane + 32 * li;
-                vn[li] = (i < n) ? __ldg(Vh + (long long)(k - 1) * n + i) : 0.f;
+                v[li] = (i < n) ? buf[s * n + i] : 0.f;
+            }
+            float dot[kApplyCols];
+#pragma unroll
+            for (int jj = 0; jj < kApplyCols; ++jj) {
+                float d = 0.f;
+#pragma unroll
+                for (int li = 0; li < kMaxLi; ++li) d = fmaf(v[li], x[jj][li], d);
+                dot[jj] = d;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int jj = 0; jj < kApplyCols; ++jj) dot[jj] += __shfl_xor_sync(0xffffffffu, dot[jj], o);
+#pragma unroll
+            for (int jj = 0; jj < kApplyCols; ++jj) {
+                const float f = -dot[jj] * tk;
+#pragma unroll
+                for (int li = 0; li < kMaxLi; ++li) x[jj][li] = fmaf(f, v[li], x[jj][li]);
             }
         }
-        float dot = 0.f;
-#pragma unroll
-        for (int li = 0; li < kMaxLi; ++li) dot = fmaf(v[li], x[li], dot);
-        dot = wsum(dot) * tk;
-#pragma unroll
-        for (int li = 0; li < kMaxLi; ++li) x[li] = fmaf(-dot, v[li], x[li]);
-#pragma unroll
-        for (int li = 0; li < kMaxLi; ++li) v[li] = vn[li];
+        __syncthreads();  // the buffer is recycled two chunks later
     }
 #pragma unroll
-    for (int li = 0; li < kMaxLi; ++li) {
-        int i = lane + 32 * li;
-        if (i < n) {
-            if (STORE_STRIDED) out[(long long)i * n + c] = x[li];
-            else out[(long long)c * n + i] = x[li];
+    for (int jj = 0; jj < kApplyCols; ++jj)
+#pragma unroll
+        for (int li = 0; li < kMaxLi; ++li) {
+            int i = lane + 32 * li;
+            if (i < n && c0 + jj < n) {
+                if (STORE_STRIDED) out[(long long)i * n + (c0 + jj)] = x[jj][li];
+                else out[(long long)(c0 + jj) * n + i] = x[jj][li];
+            }
         }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// E4: Cholesky (blocked right-looking, NB = 8), one CTA per matrix
+// E4: Cholesky (blocked right-looking, NB = 8), one CTA per matrix.
+//   per panel: (a) one warp factors the 8x8 diagonal block in registers (shuffles), (b) one thread per row
+//   solves its 8 panel entries and also stores them transposed (Lp[c][row]) so that (c) the rank-8 trailing
+//   update reads both operands as conflict-free float4 and runs on all lower-triangle 4x4 tiles at once.
 // ---------------------------------------------------------------------------------------------
-constexpr int TC = 512;
+constexpr int TC = 1024;
 __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int n = a.n, n_pad = a.n_pad, tid = threadIdx.x, env = blockIdx.x, lane = tid & 31, warp = tid >> 5;
     float* As = reinterpret_cast<float*>(smraw);  // [n][n]
-    float* L11 = As + n * n;                      // [8][8]
+    float* Lp = As + n * n;                       // [8][n_pad]  panel, transposed
+    float* L11 = Lp + 8 * n_pad;                  // [8][8]
     float* covg = a.cov + (long long)env * n * n;
-    for (int idx = tid; idx < n * n; idx += TC) {
-        int i = idx / n, j = idx - i * n;
-        As[idx] = 0.5f * (covg[idx] + covg[j * n + i]);  // (a_cov + a_cov.T)/2, controllers/covo.py:132
-    }
+    COVO_STAMP(a, 23);
+    // (a_cov + a_cov.T)/2, controllers/covo.py:132: coalesced load, symmetrise in shared memory, write back
+    for (int i = warp; i < n; i += TC / 32)
+        for (int j = lane; j < n; j += 32) As[i * n + j] = covg[i * n + j];
     __syncthreads();
-    for (int idx = tid; idx < n * n; idx += TC) covg[idx] = As[idx];
-
+    for (int i = warp; i < n; i += TC / 32)
+        for (int j = lane; j < i; j += 32) {
+            const float s2 = 0.5f * (As[i * n + j] + As[j * n + i]);
+            As[i * n + j] = s2;
+            As[j * n + i] = s2;
+        }
+    __syncthreads();
+    for (int i = warp; i < n; i += TC / 32)
+        for (int j = lane; j < n; j += 32) covg[i * n + j] = As[i * n + j];
+    COVO_STAMP(a, 24);
     for (int jb = 0; jb < n; jb += 8) {
         const int nb = min(8, n - jb);
-        // (a) factor the nb x nb diagonal block with one warp; lane r holds row r
+        if (jb == 8) COVO_STAMP(a, 26);
         if (warp == 0) {
             float r8[8];
 #pragma unroll
@@ -547,9 +781,10 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
                         if (lane == 0) a.status[env] = 2;
                         dcc = 1e-30f;
                     }
-                    float d = sqrtf(dcc);
-                    if (lane == c) r8[c] = d;
-                    else if (lane > c) r8[c] = r8[c] / d;
+                    float rinv = rsqrtf(dcc);
+                    rinv = rinv * (1.5f - 0.5f * dcc * rinv * rinv);
+                    if (lane == c) r8[c] = dcc * rinv;  // sqrt
+                    else if (lane > c) r8[c] = r8[c] * rinv;
                 }
 #pragma unroll
                 for (int c2 = c + 1; c2 < 8; ++c2) {
@@ -557,82 +792,80 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
                     if (c2 < nb && lane >= c2) r8[c2] = fmaf(-r8[c], l2, r8[c2]);
                 }
             }
-            if (lane < nb) {
+            if (lane < 8) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    if (c < nb) {
-                        float v = (c <= lane) ? r8[c] : 0.f;
-                        As[(jb + lane) * n + jb + c] = v;
-                        L11[lane * 8 + c] = v;
-                    }
+                    float v = (lane < nb && c < nb && c <= lane) ? r8[c] : 0.f;
+                    if (lane < nb && c < nb) As[(jb + lane) * n + jb + c] = v;
+                    // L11 holds the factor with the RECIPROCAL diagonal (the panel solve multiplies)
+                    L11[lane * 8 + c] = (c == lane) ? ((lane < nb) ? 1.0f / r8[c] : 1.0f) : v;
                 }
             }
         }
         __syncthreads();
-        // (b) panel: L21 = A21 L11^-T, one thread per row
+        // (b) panel: L21 = A21 L11^-T
         for (int i = jb + nb + tid; i < n; i += TC) {
             float x[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) x[c] = (c < nb) ? As[i * n + jb + c] : 0.f;
+            const float4 p0 = *reinterpret_cast<const float4*>(As + i * n + jb);
+            x[0] = p0.x; x[1] = p0.y; x[2] = p0.z; x[3] = p0.w;
+            if (nb == 8) {
+                const float4 p1 = *reinterpret_cast<const float4*>(As + i * n + jb + 4);
+                x[4] = p1.x; x[5] = p1.y; x[6] = p1.z; x[7] = p1.w;
+            } else {
+                x[4] = x[5] = x[6] = x[7] = 0.f;
+            }
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                if (c < nb) {
-                    float s = x[c];
+                float s = x[c];
 #pragma unroll
-                    for (int c2 = 0; c2 < c; ++c2) s = fmaf(-x[c2], L11[c * 8 + c2], s);
-                    x[c] = s / L11[c * 8 + c];
-                }
+                for (int c2 = 0; c2 < c; ++c2) s = fmaf(-x[c2], L11[c * 8 + c2], s);
+                x[c] = s * L11[c * 8 + c];
             }
+            *reinterpret_cast<float4*>(As + i * n + jb) = make_float4(x[0], x[1], x[2], x[3]);
+            if (nb == 8) *reinterpret_cast<float4*>(As + i * n + jb + 4) = make_float4(x[4], x[5], x[6], x[7]);
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (c < nb) As[i * n + jb + c] = x[c];
+            for (int c = 0; c < 8; ++c) Lp[c * n_pad + i] = x[c];
         }
         __syncthreads();
-        // (c) trailing update of the lower triangle in 4x4 tiles
+        // (c) trailing update on the lower-triangle 4x4 tiles
         const int r0 = jb + nb;
         const int T = (n - r0) >> 2;
-        for (int ti = warp; ti < T; ti += TC / 32) {
-            for (int tk = lane; tk <= ti; tk += 32) {
-                const int i = r0 + 4 * ti, kk = r0 + 4 * tk;
-                float li[4][8], lk[4][8];
+        const int ntiles = T * (T + 1) / 2;
+        for (int q = tid; q < ntiles; q += TC) {
+            int ti = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+            while (ti * (ti + 1) / 2 > q) --ti;
+            while ((ti + 1) * (ti + 2) / 2 <= q) ++ti;
+            const int tk = q - ti * (ti + 1) / 2;
+            const int i = r0 + 4 * ti, kk = r0 + 4 * tk;
+            float o[4][4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float4 p0 = *reinterpret_cast<const float4*>(As + (i + r) * n + jb);
-                    const float4 q0 = *reinterpret_cast<const float4*>(As + (kk + r) * n + jb);
-                    li[r][0] = p0.x; li[r][1] = p0.y; li[r][2] = p0.z; li[r][3] = p0.w;
-                    lk[r][0] = q0.x; lk[r][1] = q0.y; lk[r][2] = q0.z; lk[r][3] = q0.w;
-                    if (nb == 8) {
-                        const float4 p1 = *reinterpret_cast<const float4*>(As + (i + r) * n + jb + 4);
-                        const float4 q1 = *reinterpret_cast<const float4*>(As + (kk + r) * n + jb + 4);
-                        li[r][4] = p1.x; li[r][5] = p1.y; li[r][6] = p1.z; li[r][7] = p1.w;
-                        lk[r][4] = q1.x; lk[r][5] = q1.y; lk[r][6] = q1.z; lk[r][7] = q1.w;
-                    } else {
-#pragma unroll
-                        for (int c = 4; c < 8; ++c) li[r][c] = lk[r][c] = 0.f;
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    float4* pa = reinterpret_cast<float4*>(As + (i + r) * n + kk);
-                    float4 av = *pa;
-                    float o[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) o[cc] = fmaf(-li[r][c], lk[cc][c], o[cc]);
-                    *pa = make_float4(o[0], o[1], o[2], o[3]);
-                }
+            for (int r = 0; r < 4; ++r) {
+                const float4 av = *reinterpret_cast<const float4*>(As + (i + r) * n + kk);
+                o[r][0] = av.x; o[r][1] = av.y; o[r][2] = av.z; o[r][3] = av.w;
             }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 li = *reinterpret_cast<const float4*>(Lp + c * n_pad + i);
+                const float4 lk = *reinterpret_cast<const float4*>(Lp + c * n_pad + kk);
+                const float lir[4] = {li.x, li.y, li.z, li.w};
+                const float lkr[4] = {lk.x, lk.y, lk.z, lk.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) o[r][cc] = fmaf(-lir[r], lkr[cc], o[r][cc]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                *reinterpret_cast<float4*>(As + (i + r) * n + kk) = make_float4(o[r][0], o[r][1], o[r][2], o[r][3]);
         }
         __syncthreads();
     }
+    COVO_STAMP(a, 25);
     // outputs: row-major L (upper part zeroed) and the packed k-major factor
     if (a.L) {
         float* Lg = a.L + (long long)env * n * n;
-        for (int idx = tid; idx < n * n; idx += TC) {
-            int i = idx / n, j = idx - i * n;
-            Lg[idx] = (j <= i) ? As[idx] : 0.f;
-        }
+        for (int i = warp; i < n; i += TC / 32)
+            for (int j = lane; j < n; j += 32) Lg[i * n + j] = (j <= i) ? As[i * n + j] : 0.f;
     }
     if (a.Lt) {
         float* Ltg = a.Lt + (long long)env * a.lt_stride;
@@ -642,13 +875,15 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
             for (int r = rs + lane; r < n_pad; r += 32) Ltg[off + (r - rs)] = (r >= k && r < n) ? As[r * n + k] : 0.f;
         }
     }
+    __syncthreads();
+    COVO_STAMP(a, 27);
 }
 
 // ---------------------------------------------------------------------------------------------
 static size_t tridiag_smem(int n) {
-    return (size_t)tridiag_region_floats(n) * 4 + 4096 * 4 + 256 * 4 * 2 + 256 * 8 * 2 + 16 * 8 + 64 * 4 + 16;
+    return (size_t)tridiag_region_floats(n) * 4 + 2048 * 4 + 256 * 8 * 3 + 16 * 8 + 64 * 8 + 64 * 4 + 16;
 }
-static size_t chol_smem(int n) { return (size_t)n * n * 4 + 64 * 4; }
+static size_t chol_smem(int n) { return (size_t)n * n * 4 + (size_t)8 * round_up8(n) * 4 + 64 * 4; }
 
 cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
     if (a.n > kSigmaMaxN || (a.n & 3)) return cudaErrorInvalidValue;
@@ -662,9 +897,18 @@ cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
     sigma_tridiag_kernel<<<n_env, TT, smem, st>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    dim3 g((a.n + kApplyWarps - 1) / kApplyWarps, n_env);
-    applyq_kernel<true><<<g, kApplyWarps * 32, 0, st>>>(a.Vh, a.tau, a.F, a.Z, a.n);
-    applyq_kernel<false><<<g, kApplyWarps * 32, 0, st>>>(a.Vh, a.tau, a.Z, a.cov, a.n);
+    const int cols_per_cta = kApplyWarps * kApplyCols;
+    dim3 g((a.n + cols_per_cta - 1) / cols_per_cta, n_env);
+    const size_t asm_bytes = (size_t)(2 * kApplyChunk * a.n + 2 * kApplyChunk) * sizeof(float);
+    static size_t conf_q = 0;
+    if (asm_bytes > conf_q) {
+        e = cudaFuncSetAttribute(applyq_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(applyq_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_bytes);
+        if (e != cudaSuccess) return e;
+        conf_q = asm_bytes;
+    }
+    applyq_kernel<true, true><<<g, kApplyWarps * 32, asm_bytes, st>>>(a.Vh, a.tau, a.F, a.Z, a.n);
+    applyq_kernel<false, false><<<g, kApplyWarps * 32, asm_bytes, st>>>(a.Vh, a.tau, a.Z, a.cov, a.n);
     return cudaGetLastError();
 }
 

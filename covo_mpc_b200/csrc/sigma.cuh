@@ -10,6 +10,7 @@ constexpr int kSigmaMaxN = 224;   // n = 4H limit of the shared-memory resident 
 constexpr double kCovoOffset = 1e-2;  // "offset = -min_eign + 1e-2", controllers/covo.py:120-121
 
 struct SigmaArgs {
+    long long* prof = nullptr;  // optional: clock64() stamps at phase boundaries (debug)
     int n, n_pad;
     float sample_sigma;
     const float* R;      // [E][n][n]

@@ -137,6 +137,8 @@ int covo_get_status(covo_handle* h, int* status); /* [E] numeric status of the l
  * slots: 0 hessian-local, 1 hessian-assemble, 2 tridiag+rational, 3 apply-Q (both), 4 cholesky, 5 rollout */
 int covo_set_profiling(covo_handle* h, int on);
 int covo_get_kernel_ms(covo_handle* h, float* ms6);
+/* Debug: switch in-kernel clock64() phase stamps on/off and read the 64 slots of the last step (may be NULL). */
+int covo_debug_phase_clocks(covo_handle* h, int on, long long* out64);
 int covo_rng_step(covo_handle* h, unsigned int* stream_id); /* counter of production-mode draws so far */
 int covo_local_samples(covo_handle* h, int* n_local, int* offset);
 

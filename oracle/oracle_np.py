@@ -885,5 +885,6 @@ def philox_normals(seed: int, stream: int, n_samples: int, n_cols: int, sample_o
     r1 = np.sqrt(-2.0 * np.log(u[..., 2]))
     t0 = 2.0 * np.pi * u[..., 1]
     t1 = 2.0 * np.pi * u[..., 3]
-    z = np.stack([r0 * np.cos(t0), r0 * np.sin(t0), r1 * np.cos(t1), r1 * np.sin(t1)], axis=-1)
+    # the kernel evaluates cos/sin at theta - pi (argument range of the fast intrinsics): a sign flip
+    z = -np.stack([r0 * np.cos(t0), r0 * np.sin(t0), r1 * np.cos(t1), r1 * np.sin(t1)], axis=-1)
     return z.reshape(n_samples, n_cols).astype(np.float32)
