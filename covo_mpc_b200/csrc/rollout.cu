@@ -59,6 +59,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+__device__ __forceinline__ int warp_id_of(int tid) { return tid >> 5; }
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -446,38 +447,50 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
         scale[b] = (mb < CUDART_INF_F) ? expf(-(mb - M) * inv_lam) : 0.f;
     }
     __syncthreads();
-    // Ordered (bit-reproducible) sums over the tile partials.  Loads are issued eight at a time so the L2
-    // latency of the records overlaps instead of serialising (the partials were written by other SMs).
-    float S = 0.f;
-    for (int b0 = 0; b0 < n_cta; b0 += 16) {
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (b0 + j < n_cta) ? __ldcg(base + (long long)(b0 + j) * rec + 1) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (b0 + j < n_cta) S = fmaf(v[j], scale[b0 + j], S);
+    // Deterministic sums over the tile partials.  Loads are issued 16 at a time so the L2 latency of the records
+    // overlaps (the partials were written by other SMs).  V[r]: thread r, tiles in order.  S: the last warp,
+    // lane l takes tiles l, l+32, ... in order, then a fixed butterfly.
+    __shared__ float s_S;
+    if (warp_id_of(tid) == (int)(blockDim.x >> 5) - 1) {
+        float sp = 0.f;
+        for (int b = tid & 31; b < n_cta; b += 32) sp = fmaf(__ldcg(base + (long long)b * rec + 1), scale[b], sp);
+        sp = warp_sum(sp);
+        if ((tid & 31) == 0) s_S = sp;
     }
-    for (int r = tid; r < n_pad; r += blockDim.x) {
-        float V = 0.f;
-        for (int b0 = 0; b0 < n_cta; b0 += 16) {
-            float v[16];
+    float Vr[2] = {0.f, 0.f};
+    {
+        int slot = 0;
+        for (int r = tid; r < n_pad; r += blockDim.x, ++slot) {
+            float V = 0.f;
+            for (int b0 = 0; b0 < n_cta; b0 += 16) {
+                float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                v[j] = (b0 + j < n_cta) ? __ldcg(base + (long long)(b0 + j) * rec + kPartialHdr + r) : 0.f;
+                for (int j = 0; j < 16; ++j)
+                    v[j] = (b0 + j < n_cta) ? __ldcg(base + (long long)(b0 + j) * rec + kPartialHdr + r) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (b0 + j < n_cta) V = fmaf(v[j], scale[b0 + j], V);
-        }
-        if (a.finalize) {
-            if (r < n) {
-                // controllers/covo.py:270-278
-                float mu = sm.mu[r];
-                float nm = (S > 0.f) ? (V / S) * a.gamma_mean + mu * (1.0f - a.gamma_mean) : mu;
-                a.a_mean_out[(long long)env * n + r] = nm;
-                if (r < 4) a.action_out[(long long)env * 4 + r] = nm;
+                for (int j = 0; j < 16; ++j)
+                    if (b0 + j < n_cta) V = fmaf(v[j], scale[b0 + j], V);
             }
-        } else {
-            a.rank_partial[(long long)env * rec + kPartialHdr + r] = V;
+            if (slot < 2) Vr[slot] = V;
+        }
+    }
+    __syncthreads();
+    const float S = s_S;
+    {
+        int slot = 0;
+        for (int r = tid; r < n_pad; r += blockDim.x, ++slot) {
+            const float V = Vr[slot < 2 ? slot : 1];
+            if (a.finalize) {
+                if (r < n) {
+                    // controllers/covo.py:270-278
+                    float mu = sm.mu[r];
+                    float nm = (S > 0.f) ? (V / S) * a.gamma_mean + mu * (1.0f - a.gamma_mean) : mu;
+                    a.a_mean_out[(long long)env * n + r] = nm;
+                    if (r < 4) a.action_out[(long long)env * 4 + r] = nm;
+                }
+            } else {
+                a.rank_partial[(long long)env * rec + kPartialHdr + r] = V;
+            }
         }
     }
     if (tid == 0) {

@@ -266,7 +266,14 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
             acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
             acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
         }
-        if (active && ch == 0) *reinterpret_cast<float4*>(qbuf[0] + col) = acc;
+        float part0 = 0.f;
+        if (active && ch == 0) {
+            *reinterpret_cast<float4*>(qbuf[0] + col) = acc;
+            const float4 vv = *reinterpret_cast<const float4*>(vbuf[0] + col);
+            part0 = acc.x * vv.x + acc.y * vv.y + acc.z * vv.z + acc.w * vv.w;  // v is zero for j <= 0
+        }
+        part0 += __shfl_xor_sync(0xffffffffu, part0, 16);
+        if (lane == 0) red[8 + warp] = part0;
     }
     __syncthreads();
     long long pa[6] = {0, 0, 0, 0, 0, 0}, pt0 = 0;
@@ -278,25 +285,23 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
         float* vn = vbuf[cur ^ 1];
         float* qn = qbuf[cur ^ 1];
         const float beta = red[0], tau = red[1];
-        // A) s = q.v over j > k
-        float part = (tid < n && tid > k) ? q[tid] * v[tid] : 0.f;
-        part = wsum(part);
-        if (lane == 0) red[8 + warp] = part;
-        if (tid < n) Vg[k * n + tid] = v[tid];
-        if (tid == 0) {
+        // A) bookkeeping of step k (off the critical path)
+        if (tid >= 32 && tid < 32 + 256) {
+            const int j = tid - 32;
+            if (j < n) Vg[k * n + j] = v[j];
+        }
+        if (tid == 320) {
             dd[k] = (double)As[k * LD + k];
             ee[k] = (double)beta;
             taug[k] = tau;
         }
-        __syncthreads();
-        PH(0);
-        float sdot = 0.f;
-#pragma unroll
-        for (int w = 0; w < TT / 32; ++w) sdot += red[8 + w];
-        const float c2 = 0.5f * tau * tau * sdot;
-        // B) publish w (any thread), look-ahead Householder for step k+1 (warp 0)
-        if (tid < 256) ws[1024 + tid] = (tid < n && tid > k) ? fmaf(tau, q[tid], -c2 * v[tid]) : 0.f;
+        // B) warp 0 alone: s = q.v from the per-warp partials the previous pass left in red[8..39], then
+        //    w = tau q - (tau^2 s / 2) v (published for the pass) and the look-ahead Householder vector of
+        //    step k+1 from the UPDATED row k+1.  Everybody else waits at the barrier (an all-thread sum of
+        //    the 32 partials costs ~1k LSU cycles per step).
         if (warp == 0) {
+            const float sdot = wsum(red[8 + lane]);
+            const float c2 = 0.5f * tau * tau * sdot;
             const int r1 = k + 1;                               // row being finalised
             const float wr1 = fmaf(tau, q[r1], -c2 * v[r1]);    // w_{k+1}  (v_{k+1} = 1)
             const float* arow = As + r1 * LD;
@@ -305,11 +310,10 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 const int j = lane + 32 * t;
-                float r = 0.f;
-                if (j >= k + 2 && j < n) {
-                    const float wj = fmaf(tau, q[j], -c2 * v[j]);
-                    r = arow[j] - wj - wr1 * v[j];               // updated A[k+1][j]
-                }
+                float r = 0.f, wj = 0.f;
+                if (j > k && j < n) wj = fmaf(tau, q[j], -c2 * v[j]);
+                ws[1024 + j] = wj;
+                if (j >= k + 2 && j < n) r = arow[j] - wj - wr1 * v[j];  // updated A[k+1][j]
                 rj[t] = r;
                 if (j >= k + 3) sig = fmaf(r, r, sig);
             }
@@ -380,7 +384,16 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
                 acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
                 acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
             }
-            if (active && ch == 0) *reinterpret_cast<float4*>(qn + col) = acc;
+            // leaders publish q_{k+1} and their share of s_{k+1} = q_{k+1} . v_{k+1}
+            float partn = 0.f;
+            if (active && ch == 0) {
+                *reinterpret_cast<float4*>(qn + col) = acc;
+                const float4 vv = *reinterpret_cast<const float4*>(vn + col);  // zero for j <= k+1
+                partn = acc.x * vv.x + acc.y * vv.y + acc.z * vv.z + acc.w * vv.w;
+            }
+            partn += __shfl_xor_sync(0xffffffffu, partn, 16);
+            // red[8..39] of this step were consumed before sync B, so they can be overwritten here
+            if (lane == 0) red[8 + warp] = partn;
             if (tid == 0) {
                 red[0] = red[2];
                 red[1] = red[3];

@@ -1,0 +1,62 @@
+"""Committed fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the float64-Hessian oracle).
+CPU: the oracle still reproduces them.  GPU: the CUDA path reproduces them through the C-ABI."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as o
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+
+
+def _state(g):
+    s = g["state24"]
+    return o.make_state(s[0:3], s[3:7], s[7:10], s[10:13], s[13:16], int(g["time"]), g["pos_traj"], g["vel_traj"], s[16:19],
+                        s[19:22], dtype=np.float32)
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
+def test_oracle_reproduces_golden(path):
+    g = np.load(path)
+    p = o.EnvParams()
+    ns = _state(g)
+    H = g["a_mean"].shape[0]
+    if "mppi" in os.path.basename(path):
+        u, new_mean, _, _, dbg = o.mppi_call(ns, g["a_mean"], g["a_cov"], g["eps"].reshape(-1, H, 4), p, lam=0.01, return_debug=True)
+    else:
+        u, new_mean, a_cov, _, dbg = o.covo_call(ns, g["a_mean"], g["eps"], p, lam=0.01, return_debug=True)
+        assert np.abs(dbg["R"] - g["R"]).max() <= 1e-9 * max(1, np.abs(g["R"]).max())
+        assert np.abs(a_cov - g["a_cov"]).max() < 1e-6
+    assert np.abs(dbg["cost"] - g["cost"]).max() < 1e-5
+    assert np.abs(new_mean - g["a_mean_new"]).max() < 1e-6 and np.abs(u - g["action"]).max() < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
+def test_cuda_path_reproduces_golden(path):
+    from covo_mpc_b200 import _lib
+
+    g = np.load(path)
+    H = g["a_mean"].shape[0]
+    N = g["eps"].shape[0]
+    mppi = "mppi" in os.path.basename(path)
+    cfg = _lib.default_config()
+    cfg.mode = _lib.MODE_MPPI if mppi else _lib.MODE_COVO_ONLINE
+    cfg.n_samples, cfg.horizon, cfg.traj_len = N, H, g["pos_traj"].shape[0]
+    h = _lib.Handle(cfg)
+    h.set_reference(g["pos_traj"][None], g["vel_traj"][None])
+    h.set_mean(g["a_mean"][None])
+    if mppi:
+        h.set_cov(g["a_cov"][None])
+    else:
+        R = h.hessian(g["state24"], [int(g["time"])], g["a_mean"][None], shift=True)[0]
+        assert np.abs(R - g["R"]).max() < 2e-5 * max(1, np.abs(g["R"]).max())
+    act = h.step(g["state24"], [int(g["time"])], g["eps"][None])[0]
+    assert np.abs(act - g["action"]).max() < 2e-4
+    assert np.abs(h.get_mean()[0] - g["a_mean_new"]).max() < 2e-4
+    if not mppi:
+        cov = h.get_cov()[0]
+        assert np.linalg.norm(cov - g["a_cov"]) / np.linalg.norm(g["a_cov"]) < 2e-5
