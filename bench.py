@@ -38,12 +38,12 @@ METRIC, UNIT = "mpc_control_steps_per_sec", "steps/s"
 
 
 # ---------------------------------------------------------------------------------------------------
-def record_states(n_states: int, seed: int, controller_name="covo-online", N=1024):
+def record_states(n_states: int, seed: int, controller_name="covo-online", N=1024, device=0):
     """Closed-loop episode (untimed, smaller N) to obtain a realistic sequence of noisy states."""
     import covo_mpc_b200 as cm
 
     env = cm.Quad3D(TASK)
-    ctl, _ = cm.get_controller(env, controller_name, f"N{N}_H{HORIZON}_lam{LAM}", seed=seed)
+    ctl, _ = cm.get_controller(env, controller_name, f"N{N}_H{HORIZON}_lam{LAM}", seed=seed, device=device)
     rec = []
     rng = np.random.default_rng(seed)
     while len(rec) < n_states:
@@ -141,7 +141,7 @@ def run_gpu(args):
     n_states = W + K
     seed = 100 + (rank if shard == "env" else 0)
     mode_name = "covo-offline" if shard == "nsample" else args.controller
-    env, states_h, times_h, traj = record_states(n_states, seed, "covo-online" if mode_name != "mppi" else "mppi")
+    env, states_h, times_h, traj = record_states(n_states, seed, "covo-online" if mode_name != "mppi" else "mppi", device=local_rank)
 
     cfg = _lib.default_config()
     cfg.mode = {"covo-online": _lib.MODE_COVO_ONLINE, "covo-offline": _lib.MODE_COVO_OFFLINE, "mppi": _lib.MODE_MPPI}[mode_name]
@@ -386,7 +386,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": cb["steps"],
            "warmup": W, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{args.controller} {TASK} N={N_SAMPLES} H={HORIZON} u_dim=4 lam={LAM} sigma=0.5, 1 env",
+           "config": {"workload": f"{args.controller} {TASK} N={N_SAMPLES} H={HORIZON} u_dim=4 lam={LAM} sigma=0.5, 1 env per GPU",
                       "note": "CPU restatement of the reference algorithm (JAX cannot be installed offline); timed steps capped at ~170 s"},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))

@@ -76,6 +76,21 @@ struct MergeArgs {
     float* action_out;       // [E][4]
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remember what was configured on each one.
+template <class K>
+inline cudaError_t ensure_smem_attr(K kernel, size_t bytes, size_t (&configured)[32]) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    dev &= 31;
+    if (bytes > configured[dev]) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        configured[dev] = bytes;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_rollout(const RolloutArgs& a, int n_env, cudaStream_t st);
 cudaError_t launch_merge(const MergeArgs& a, cudaStream_t st);
 size_t rollout_smem_bytes(int n_pad, int mode, int H);

@@ -249,12 +249,9 @@ cudaError_t launch_hessian(const HessianArgs& a, int n_env, cudaStream_t st) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     size_t smem = hessian_assemble_smem(a.H);
-    static size_t configured = 0;
-    if (smem > configured) {
-        e = cudaFuncSetAttribute(hess_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static size_t configured[32] = {};
+    e = ensure_smem_attr(hess_assemble_kernel, smem, configured);
+    if (e != cudaSuccess) return e;
     hess_assemble_kernel<<<n_env, kAsmThreads, smem, st>>>(a);
     return cudaGetLastError();
 }

@@ -538,12 +538,9 @@ __global__ void merge_ranks_kernel(const MergeArgs a) {
 
 cudaError_t launch_rollout(const RolloutArgs& a, int n_env, cudaStream_t st) {
     size_t smem = rollout_smem_bytes(a.n_pad, a.mode, a.H);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static size_t configured[32] = {};
+    cudaError_t e = ensure_smem_attr(rollout_kernel, smem, configured);
+    if (e != cudaSuccess) return e;
     int n_cta = (a.n_samples + TS - 1) / TS;
     dim3 grid(n_cta, n_env);
     rollout_kernel<<<grid, kRolloutThreads, smem, st>>>(a);

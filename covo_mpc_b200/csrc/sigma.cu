@@ -900,26 +900,20 @@ static size_t chol_smem(int n) { return (size_t)n * n * 4 + (size_t)8 * round_up
 
 cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
     if (a.n > kSigmaMaxN || (a.n & 3)) return cudaErrorInvalidValue;
-    static size_t conf = 0;
+    static size_t conf[32] = {};
     size_t smem = tridiag_smem(a.n);
-    if (smem > conf) {
-        cudaError_t e = cudaFuncSetAttribute(sigma_tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        conf = smem;
-    }
+    cudaError_t e0 = ensure_smem_attr(sigma_tridiag_kernel, smem, conf);
+    if (e0 != cudaSuccess) return e0;
     sigma_tridiag_kernel<<<n_env, TT, smem, st>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int cols_per_cta = kApplyWarps * kApplyCols;
     dim3 g((a.n + cols_per_cta - 1) / cols_per_cta, n_env);
     const size_t asm_bytes = (size_t)(2 * kApplyChunk * a.n + 2 * kApplyChunk) * sizeof(float);
-    static size_t conf_q = 0;
-    if (asm_bytes > conf_q) {
-        e = cudaFuncSetAttribute(applyq_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_bytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(applyq_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_bytes);
-        if (e != cudaSuccess) return e;
-        conf_q = asm_bytes;
-    }
+    static size_t conf_q1[32] = {}, conf_q2[32] = {};
+    e = ensure_smem_attr(applyq_kernel<true, true>, asm_bytes, conf_q1);
+    if (e == cudaSuccess) e = ensure_smem_attr(applyq_kernel<false, false>, asm_bytes, conf_q2);
+    if (e != cudaSuccess) return e;
     applyq_kernel<true, true><<<g, kApplyWarps * 32, asm_bytes, st>>>(a.Vh, a.tau, a.F, a.Z, a.n);
     applyq_kernel<false, false><<<g, kApplyWarps * 32, asm_bytes, st>>>(a.Vh, a.tau, a.Z, a.cov, a.n);
     return cudaGetLastError();
@@ -927,13 +921,10 @@ cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
 
 cudaError_t launch_cholesky(const SigmaArgs& a, int n_env, cudaStream_t st) {
     if (a.n > kSigmaMaxN || (a.n & 3)) return cudaErrorInvalidValue;
-    static size_t conf = 0;
+    static size_t conf[32] = {};
     size_t smem = chol_smem(a.n);
-    if (smem > conf) {
-        cudaError_t e = cudaFuncSetAttribute(cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        conf = smem;
-    }
+    cudaError_t e = ensure_smem_attr(cholesky_kernel, smem, conf);
+    if (e != cudaSuccess) return e;
     cholesky_kernel<<<n_env, TC, smem, st>>>(a);
     return cudaGetLastError();
 }
