@@ -105,7 +105,7 @@ struct covo_handle {
     DevBuf<float> state24, pos_traj, vel_traj, acc_traj, a_mean, eps, fdist;
     DevBuf<int> time;
     // covariance pipeline
-    DevBuf<float> R, Vh, tau, F, Z, cov, Lfull, Lt, Lblk, hess_ws;
+    DevBuf<float> R, Vh, tau, Tw, sched_Tw, F, Z, cov, Lfull, Lt, Lblk, hess_ws;
     DevBuf<double> diag, zolo;
     DevBuf<int> status;
     // offline schedule (batched over schedule steps)
@@ -135,7 +135,7 @@ namespace {
 void release_all(covo_handle* h) {
     h->state24.release(); h->pos_traj.release(); h->vel_traj.release(); h->acc_traj.release();
     h->a_mean.release(); h->eps.release(); h->fdist.release(); h->time.release();
-    h->R.release(); h->Vh.release(); h->tau.release(); h->F.release(); h->Z.release(); h->cov.release();
+    h->R.release(); h->Vh.release(); h->tau.release(); h->Tw.release(); h->sched_Tw.release(); h->F.release(); h->Z.release(); h->cov.release();
     h->Lfull.release(); h->Lt.release(); h->Lblk.release(); h->hess_ws.release(); h->diag.release();
     h->zolo.release(); h->status.release();
     h->cov_table.release(); h->Lt_table.release(); h->sched_states.release(); h->sched_anom.release();
@@ -178,6 +178,7 @@ SigmaArgs sigma_args(covo_handle* h) {
     a.R = h->R.p;
     a.Vh = h->Vh.p;
     a.tau = h->tau.p;
+    a.Tw = h->Tw.p;
     a.F = h->F.p;
     a.Z = h->Z.p;
     a.cov = h->cov.p;
@@ -410,6 +411,7 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
         A(h->R.alloc(E * nn));
         A(h->Vh.alloc(E * nn));
         A(h->tau.alloc(E * n));
+        A(h->Tw.alloc(E * (n / kWyBlock + 1) * 64));
         A(h->F.alloc(E * nn));
         A(h->Z.alloc(E * nn));
         A(h->cov.alloc(E * nn));
@@ -558,6 +560,8 @@ static int alloc_schedule(covo_handle* h, int t_sched, bool full) {
         CK(h->sched_R.alloc(S * nn));
         CK(h->sched_Vh.alloc(S * nn));
         CK(h->sched_tau.alloc(S * h->n));
+        h->sched_Tw.release();
+        CK(h->sched_Tw.alloc(S * (h->n / kWyBlock + 1) * 64));
         CK(h->sched_F.alloc(S * nn));
         CK(h->sched_Z.alloc(S * nn));
         CK(h->sched_ws.alloc(S * hessian_workspace_floats(h->H)));
@@ -571,6 +575,7 @@ static SigmaArgs sched_sigma_args(covo_handle* h) {
     a.R = h->sched_R.p;
     a.Vh = h->sched_Vh.p;
     a.tau = h->sched_tau.p;
+    a.Tw = h->sched_Tw.p;
     a.F = h->sched_F.p;
     a.Z = h->sched_Z.p;
     a.cov = h->cov_table.p;

@@ -179,7 +179,9 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
     float* As = reinterpret_cast<float*>(smraw);          // [n][LD]
     float* vs = As + tridiag_region_floats(n);            // [2048] v/q double buffers + w (see E1)
     float* ws = vs + 256;
-    double* dd = reinterpret_cast<double*>(vs + 2048);    // [256]
+    float* rw4 = vs + 2048;                               // [256] float4: per-row (-v, -w, vnext, 0) of the pass
+    float* taus = vs + 3072;                              // [256] tau_k
+    double* dd = reinterpret_cast<double*>(vs + 3328);    // [256]
     double* ee = dd + 256;                                // [256]
     double* e2s = ee + 256;                               // [256] e^2
     double* sc = e2s + 256;                               // [16] scalars
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
     // R <- (R + R^T)/2 (controllers/covo.py:117): coalesced load, then symmetrise in shared memory
     for (int i = warp; i < n; i += TT / 32)
         for (int j = lane; j < n; j += 32) As[i * LD + j] = Rg[i * n + j];
-    for (int i = tid; i < 2048; i += TT) vs[i] = 0.f;
+    for (int i = tid; i < 3328; i += TT) vs[i] = 0.f;
     __syncthreads();
     for (int i = warp; i < n; i += TT / 32)
         for (int j = lane; j < i; j += 32) {
@@ -285,65 +287,68 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
         float* vn = vbuf[cur ^ 1];
         float* qn = qbuf[cur ^ 1];
         const float beta = red[0], tau = red[1];
-        // A) bookkeeping of step k (off the critical path)
-        if (tid >= 32 && tid < 32 + 256) {
-            const int j = tid - 32;
-            if (j < n) Vg[k * n + j] = v[j];
+        // A) bookkeeping of step k.  No global stores inside the loop: a barrier after a global store waits for the
+        //    L2 round trip.  v_k is parked LAPACK-style in the dead part of row k of A (entries j >= k+2; v[k+1] = 1
+        //    is implicit) and everything is written to HBM once after the loop.
+        if (tid >= 512 && tid < 512 + 256) {
+            const int j = tid - 512;
+            if (j >= k + 2 && j < n) As[k * LD + j] = v[j];
         }
-        if (tid == 320) {
+        if (tid == 800) {
             dd[k] = (double)As[k * LD + k];
             ee[k] = (double)beta;
-            taug[k] = tau;
+            taus[k] = tau;
         }
-        // B) warp 0 alone: s = q.v from the per-warp partials the previous pass left in red[8..39], then
-        //    w = tau q - (tau^2 s / 2) v (published for the pass) and the look-ahead Householder vector of
-        //    step k+1 from the UPDATED row k+1.  Everybody else waits at the barrier (an all-thread sum of
-        //    the 32 partials costs ~1k LSU cycles per step).
-        if (warp == 0) {
+        // B) look-ahead Householder vector of step k+1 from the UPDATED row k+1, all threads:
+        //      s = q.v (partials left in red[8..39] by the previous pass), c2 = tau^2 s / 2,
+        //      w_j = tau q_j - c2 v_j,   updated row  r_j = A[k+1][j] - w_j - w_{k+1} v_j   (v_{k+1} = 1)
+        //    B1: thread j forms w_j, r_j and its share of sigma = sum_{j >= k+3} r_j^2  -> barrier
+        //    B2: every warp finishes sigma, the scalar chain (beta', tau', scale'), thread j publishes v'_j
+        // Only warps 0..7 (one thread per entry of the row) run B; the other 24 warps go straight to the barriers,
+        // so the eight working warps see near single-warp latencies on their shuffle / MUFU chains.
+        float wj = 0.f, rj = 0.f;
+        const int j = tid;
+        if (warp < 8) {
             const float sdot = wsum(red[8 + lane]);
             const float c2 = 0.5f * tau * tau * sdot;
-            const int r1 = k + 1;                               // row being finalised
-            const float wr1 = fmaf(tau, q[r1], -c2 * v[r1]);    // w_{k+1}  (v_{k+1} = 1)
-            const float* arow = As + r1 * LD;
-            float rj[8];
-            float sig = 0.f;
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const int j = lane + 32 * t;
-                float r = 0.f, wj = 0.f;
-                if (j > k && j < n) wj = fmaf(tau, q[j], -c2 * v[j]);
-                ws[1024 + j] = wj;
-                if (j >= k + 2 && j < n) r = arow[j] - wj - wr1 * v[j];  // updated A[k+1][j]
-                rj[t] = r;
-                if (j >= k + 3) sig = fmaf(r, r, sig);
-            }
-            sig = wsum(sig);
-            // x0 = updated A[k+1][k+2], held by lane (k+2) & 31, slot (k+2) >> 5
-            float x0 = 0.f;
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const float cand = __shfl_sync(0xffffffffu, rj[t], (k + 2) & 31);
-                if (t == ((k + 2) >> 5)) x0 = cand;
-            }
+            const int r1 = k + 1;
+            const float wr1 = fmaf(tau, q[r1], -c2 * v[r1]);
+            const float vj = v[j];
+            float sq = 0.f;
+            if (j > k && j < n) wj = fmaf(tau, q[j], -c2 * vj);
+            if (j >= k + 2 && j < n) rj = As[r1 * LD + j] - wj - wr1 * vj;
+            if (j >= k + 3) sq = rj * rj;
+            ws[1024 + j] = wj;
+            if (j == k + 2) red[4] = rj;  // x0
+            sq = wsum(sq);
+            if (lane == 0) red[40 + warp] = sq;
+        }
+        __syncthreads();
+        if (warp < 8) {
+            float sig = red[40 + (lane & 7)];
+            sig += __shfl_xor_sync(0xffffffffu, sig, 4);
+            sig += __shfl_xor_sync(0xffffffffu, sig, 2);
+            sig += __shfl_xor_sync(0xffffffffu, sig, 1);
+            const float x0 = red[4];
             float nbeta, ntau, nscale;
-            if (k + 2 >= n) {
-                nbeta = 0.f; ntau = 0.f; nscale = 0.f;
-            } else if (sig == 0.f) {
+            if (sig == 0.f) {
                 nbeta = x0; ntau = 0.f; nscale = 0.f;
             } else {
-                nbeta = -copysignf(sqrtf(fmaf(x0, x0, sig)), x0);
-                ntau = (nbeta - x0) / nbeta;
-                nscale = 1.0f / (x0 - nbeta);
+                // MUFU rsq / rcp + one Newton step (~1 ulp), instead of the IEEE sqrt / div sequences
+                const float nn2 = fmaf(x0, x0, sig);
+                float rs = rsqrtf(nn2);
+                rs = rs * (1.5f - 0.5f * nn2 * rs * rs);
+                nbeta = -copysignf(nn2 * rs, x0);
+                float rb = __frcp_rn(nbeta);
+                ntau = (nbeta - x0) * rb;
+                nscale = __frcp_rn(x0 - nbeta);
             }
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const int j = lane + 32 * t;
-                float vv = 0.f;
-                if (j == k + 2 && j < n) vv = 1.f;
-                else if (j >= k + 3 && j < n && ntau != 0.f) vv = rj[t] * nscale;
-                vn[j] = vv;
-            }
-            if (lane == 0) {
+            float vv = 0.f;
+            if (j == k + 2 && j < n) vv = 1.f;
+            else if (j >= k + 3 && j < n && ntau != 0.f) vv = rj * nscale;
+            vn[j] = vv;
+            reinterpret_cast<float4*>(rw4)[j] = make_float4(-v[j], -wj, vv, 0.f);
+            if (tid == 0) {
                 red[2] = nbeta;
                 red[3] = ntau;
             }
@@ -355,27 +360,40 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
             const float* wv = ws + 1024;
             const int c0 = (k + 1) & ~3;
             const int ncg = (n - c0) >> 2;
-            const bool active = cgi < ncg;
-            const int col = c0 + 4 * cgi;
+            // thread map: 64 column groups x 16 row classes while more than 32 column groups are alive, then
+            // 32 x 32 (halves the rows per thread once half of the column-group slots would idle)
+            const bool wide = false;  // measured: the 32 x 32 map is slower (fixed per-step costs dominate the tail)
+            const int cg2 = wide ? (tid >> 5) : cgi;
+            const int ch2 = wide ? lane : ch;
+            const int rstep = wide ? 32 : 16;
+            const bool active = cg2 < ncg;
+            const int col = c0 + 4 * cg2;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             if (active) {
-                const float4 wj = *reinterpret_cast<const float4*>(wv + col);
-                const float4 vj = *reinterpret_cast<const float4*>(v + col);
-#pragma unroll 2
-                for (int i = k + 1 + ch; i < n; i += 16) {
-                    const float vi = v[i], wi = wv[i], vni = vn[i];
+                const float4 wj4 = *reinterpret_cast<const float4*>(wv + col);
+                const float4 vj4 = *reinterpret_cast<const float4*>(v + col);
+                const float4* rowp = reinterpret_cast<const float4*>(rw4);
+#pragma unroll 4
+                for (int i = k + 1 + ch2; i < n; i += rstep) {
+                    const float4 r4 = rowp[i];  // (-v_i, -w_i, vnext_i, 0): one LDS.128 per row
                     float4* p = reinterpret_cast<float4*>(As + i * LD + col);
                     float4 av = *p;
-                    av.x -= fmaf(vi, wj.x, wi * vj.x);
-                    av.y -= fmaf(vi, wj.y, wi * vj.y);
-                    av.z -= fmaf(vi, wj.z, wi * vj.z);
-                    av.w -= fmaf(vi, wj.w, wi * vj.w);
+                    av.x = fmaf(r4.x, wj4.x, fmaf(r4.y, vj4.x, av.x));
+                    av.y = fmaf(r4.x, wj4.y, fmaf(r4.y, vj4.y, av.y));
+                    av.z = fmaf(r4.x, wj4.z, fmaf(r4.y, vj4.z, av.z));
+                    av.w = fmaf(r4.x, wj4.w, fmaf(r4.y, vj4.w, av.w));
                     *p = av;
-                    acc.x = fmaf(av.x, vni, acc.x);
-                    acc.y = fmaf(av.y, vni, acc.y);
-                    acc.z = fmaf(av.z, vni, acc.z);
-                    acc.w = fmaf(av.w, vni, acc.w);
+                    acc.x = fmaf(av.x, r4.z, acc.x);
+                    acc.y = fmaf(av.y, r4.z, acc.y);
+                    acc.z = fmaf(av.z, r4.z, acc.z);
+                    acc.w = fmaf(av.w, r4.z, acc.w);
                 }
+            }
+            if (wide) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
+                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
             }
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) {
@@ -386,12 +404,13 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
             }
             // leaders publish q_{k+1} and their share of s_{k+1} = q_{k+1} . v_{k+1}
             float partn = 0.f;
-            if (active && ch == 0) {
+            if (active && ch2 == 0) {
                 *reinterpret_cast<float4*>(qn + col) = acc;
                 const float4 vv = *reinterpret_cast<const float4*>(vn + col);  // zero for j <= k+1
                 partn = acc.x * vv.x + acc.y * vv.y + acc.z * vv.z + acc.w * vv.w;
             }
-            partn += __shfl_xor_sync(0xffffffffu, partn, 16);
+            if (!wide) partn += __shfl_xor_sync(0xffffffffu, partn, 16);
+            else partn = __shfl_sync(0xffffffffu, partn, 0);
             // red[8..39] of this step were consumed before sync B, so they can be overwritten here
             if (lane == 0) red[8 + warp] = partn;
             if (tid == 0) {
@@ -409,12 +428,96 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
         dd[n - 1] = (double)As[(n - 1) * LD + (n - 1)];
         ee[n - 2] = (double)As[(n - 1) * LD + (n - 2)];
         ee[n - 1] = 0.0;
-        taug[n - 2] = 0.f;
-        taug[n - 1] = 0.f;
+        taus[n - 2] = 0.f;
+        taus[n - 1] = 0.f;
     }
-    if (tid < n) {
-        Vg[(n - 2) * n + tid] = 0.f;
-        Vg[(n - 1) * n + tid] = 0.f;
+    __syncthreads();
+    // reflectors -> HBM, row k = v_k zero-extended (coalesced), and tau
+    for (int k2 = warp; k2 < n; k2 += TT / 32) {
+        const bool live = (k2 < n - 2) && (taus[k2] != 0.f);
+        for (int j = lane; j < n; j += 32) {
+            float vv = 0.f;
+            if (k2 < n - 2) {
+                if (j == k2 + 1) vv = 1.f;
+                else if (j >= k2 + 2 && live) vv = As[k2 * LD + j];
+            }
+            Vg[(long long)k2 * n + j] = vv;
+        }
+    }
+    if (tid < n) taug[tid] = taus[tid];
+    __syncthreads();
+    // Compact-WY factors for apply-Q: block m holds reflectors k = k_hi-7 .. k_hi, k_hi = n-3-8m (ascending local
+    // index r <-> k = k_hi-7+r; missing ones have tau = 0).  H_{k_lo} ... H_{k_hi} = I - V T V^T, T upper triangular
+    // (LAPACK slarft, forward / columnwise): T[i][i] = tau_i, T[0:i, i] = -tau_i T[0:i,0:i] (V[:,0:i]^T v_i).
+    {
+        const int nblk = (n - 2 + kWyBlock - 1) / kWyBlock;
+        float* Twg = a.Tw + (long long)env * (n / kWyBlock + 1) * 64;
+        float* gsm = reinterpret_cast<float*>(rdbuf);  // per-warp scratch is not needed: one warp per block, Gram in regs
+        (void)gsm;
+        for (int m = warp; m < nblk; m += TT / 32) {
+            const int khi = n - 3 - kWyBlock * m;
+            // Gram entries g[r][c] = v_r . v_c for r < c, all lanes end with the sums
+            float g[8][8];
+            float vr[8][7];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int k = khi - 7 + r;
+#pragma unroll
+                for (int li = 0; li < 7; ++li) {
+                    const int i = lane + 32 * li;
+                    float vv = 0.f;
+                    if (k >= 0 && i < n) {
+                        if (i == k + 1) vv = 1.f;
+                        else if (i >= k + 2 && taus[k] != 0.f) vv = As[k * LD + i];
+                    }
+                    vr[r][li] = vv;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = r + 1; c < 8; ++c) {
+                    float d = 0.f;
+#pragma unroll
+                    for (int li = 0; li < 7; ++li) d = fmaf(vr[r][li], vr[c][li], d);
+                    g[r][c] = d;
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = r + 1; c < 8; ++c) g[r][c] += __shfl_xor_sync(0xffffffffu, g[r][c], o);
+            float tauk[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int k = khi - 7 + r;
+                tauk[r] = (k >= 0) ? taus[k] : 0.f;
+            }
+            float T[8][8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) T[r][c] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                T[i][i] = tauk[i];
+#pragma unroll
+                for (int r = 0; r < i; ++r) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int c = r; c < i; ++c) acc = fmaf(T[r][c], g[c][i], acc);
+                    T[r][i] = -tauk[i] * acc;
+                }
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (lane == r) Twg[m * 64 + r * 8 + c] = T[r][c];
+            }
+        }
     }
     __syncthreads();
     COVO_STAMP(a, 9);
@@ -637,8 +740,8 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
 // two-stage cp.async pipeline, so the serial chain per reflector is dot -> 5 shuffles -> axpy and nothing waits
 // on global memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int kApplyWarps = 8;
-constexpr int kApplyCols = 2;                 // vectors per warp
+constexpr int kApplyWarps = 4;
+constexpr int kApplyCols = 1;                 // vectors per warp (the instruction stream per warp is the critical path)
 constexpr int kApplyChunk = 32;               // reflectors per pipeline stage
 constexpr int kMaxLi = kSigmaMaxN / 32;       // 7
 
@@ -654,18 +757,18 @@ __device__ __forceinline__ void cp_async_wait() {
 
 template <bool STORE_STRIDED, bool UPPER_ONLY>
 __global__ void __launch_bounds__(kApplyWarps * 32) applyq_kernel(const float* __restrict__ Vh,
-                                                                 const float* __restrict__ tau,
+                                                                 const float* __restrict__ Tw,
                                                                  const float* __restrict__ in, float* __restrict__ out,
                                                                  int n) {
-    extern __shared__ __align__(16) float sv[];  // [2][kApplyChunk][n] reflectors, then [2][kApplyChunk] tau
+    extern __shared__ __align__(16) float sv[];  // [2][kApplyChunk][n] reflectors, then [2][4][64] T factors
     const int env = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c0 = (blockIdx.x * kApplyWarps + warp) * kApplyCols;
     Vh += (long long)env * n * n;
-    tau += (long long)env * n;
+    Tw += (long long)env * (n / kWyBlock + 1) * 64;
     in += (long long)env * n * n;
     out += (long long)env * n * n;
-    float* stau = sv + 2 * kApplyChunk * n;
+    float* sT = sv + 2 * kApplyChunk * n;
     float x[kApplyCols][kMaxLi];
 #pragma unroll
     for (int j = 0; j < kApplyCols; ++j)
@@ -684,7 +787,8 @@ __global__ void __launch_bounds__(kApplyWarps * 32) applyq_kernel(const float* _
     const int nchunks = (nref + kApplyChunk - 1) / kApplyChunk;
     const int vec_per_row = n >> 2;
     auto prefetch = [&](int j) {
-        // chunk j holds k = kh, kh-1, ..., kl  (kh = n-3 - j*chunk); stored so that slot s <-> k = kh - s
+        // chunk j holds k = kh, kh-1, ..., kl  (kh = n-3 - j*chunk); slot s <-> k = kh - s.  Its 4 WY blocks are
+        // the blocks m = 4j .. 4j+3 of the T table.
         const int kh = n - 3 - j * kApplyChunk;
         const int cnt = min(kApplyChunk, kh + 1);
         float* dst = sv + (j & 1) * kApplyChunk * n;
@@ -692,7 +796,9 @@ __global__ void __launch_bounds__(kApplyWarps * 32) applyq_kernel(const float* _
             int s = idx / vec_per_row, v4 = idx - s * vec_per_row;
             cp_async16(dst + s * n + 4 * v4, Vh + (long long)(kh - s) * n + 4 * v4);
         }
-        if (tid < cnt) stau[(j & 1) * kApplyChunk + tid] = __ldg(tau + kh - tid);
+        const int nblk = (cnt + kWyBlock - 1) / kWyBlock;
+        for (int idx = tid; idx < nblk * 16; idx += kApplyWarps * 32)
+            cp_async16(sT + (j & 1) * 256 + idx * 4, Tw + (long long)(4 * j) * 64 + idx * 4);
         cp_async_commit();
     };
     prefetch(0);
@@ -707,33 +813,58 @@ __global__ void __launch_bounds__(kApplyWarps * 32) applyq_kernel(const float* _
         const int kh = n - 3 - j * kApplyChunk;
         const int cnt = min(kApplyChunk, kh + 1);
         const float* buf = sv + (j & 1) * kApplyChunk * n;
-        const float* tb = stau + (j & 1) * kApplyChunk;
-        for (int s = 0; s < cnt; ++s) {
-            const float tk = tb[s];
-            if (tk == 0.f) continue;  // warp-uniform
-            float v[kMaxLi];
+        const int nblk = (cnt + kWyBlock - 1) / kWyBlock;
+        for (int q = 0; q < nblk; ++q) {
+            // block q: slots 8q .. 8q+7 (descending k); ascending local index r <-> slot 8q + 7 - r
+            const float* Tb = sT + (j & 1) * 256 + q * 64;
+            // y = V^T x  (slots past the end of the chunk hold stale data but their T rows/cols are zero: tau = 0)
+            float y[kApplyCols][8];
 #pragma unroll
-            for (int li = 0; li < kMaxLi; ++li) {
-                int i = lane + 32 * li;
-                v[li] = (i < n) ? buf[s * n + i] : 0.f;
-            }
-            float dot[kApplyCols];
+            for (int r = 0; r < 8; ++r) {
+                const int s = 8 * q + 7 - r;
+                float v[kMaxLi];
 #pragma unroll
-            for (int jj = 0; jj < kApplyCols; ++jj) {
-                float d = 0.f;
+                for (int li = 0; li < kMaxLi; ++li) {
+                    int i = lane + 32 * li;
+                    v[li] = (i < n && s < cnt) ? buf[s * n + i] : 0.f;
+                }
 #pragma unroll
-                for (int li = 0; li < kMaxLi; ++li) d = fmaf(v[li], x[jj][li], d);
-                dot[jj] = d;
+                for (int jj = 0; jj < kApplyCols; ++jj) {
+                    float d = 0.f;
+#pragma unroll
+                    for (int li = 0; li < kMaxLi; ++li) d = fmaf(v[li], x[jj][li], d);
+                    y[jj][r] = d;
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                for (int jj = 0; jj < kApplyCols; ++jj) dot[jj] += __shfl_xor_sync(0xffffffffu, dot[jj], o);
+                for (int jj = 0; jj < kApplyCols; ++jj)
 #pragma unroll
-            for (int jj = 0; jj < kApplyCols; ++jj) {
-                const float f = -dot[jj] * tk;
+                    for (int r = 0; r < 8; ++r) y[jj][r] += __shfl_xor_sync(0xffffffffu, y[jj][r], o);
+            // z = T y (upper triangular), then x -= V z
+            float z[kApplyCols][8];
 #pragma unroll
-                for (int li = 0; li < kMaxLi; ++li) x[jj][li] = fmaf(f, v[li], x[jj][li]);
+            for (int r = 0; r < 8; ++r) {
+#pragma unroll
+                for (int jj = 0; jj < kApplyCols; ++jj) z[jj][r] = 0.f;
+#pragma unroll
+                for (int c = r; c < 8; ++c) {
+                    const float t = Tb[r * 8 + c];
+#pragma unroll
+                    for (int jj = 0; jj < kApplyCols; ++jj) z[jj][r] = fmaf(t, y[jj][c], z[jj][r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int s = 8 * q + 7 - r;
+#pragma unroll
+                for (int li = 0; li < kMaxLi; ++li) {
+                    int i = lane + 32 * li;
+                    const float v = (i < n && s < cnt) ? buf[s * n + i] : 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < kApplyCols; ++jj) x[jj][li] = fmaf(-z[jj][r], v, x[jj][li]);
+                }
             }
         }
         __syncthreads();  // the buffer is recycled two chunks later
@@ -894,7 +1025,7 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 static size_t tridiag_smem(int n) {
-    return (size_t)tridiag_region_floats(n) * 4 + 2048 * 4 + 256 * 8 * 3 + 16 * 8 + 64 * 8 + 64 * 4 + 16;
+    return (size_t)tridiag_region_floats(n) * 4 + 3328 * 4 + 256 * 8 * 3 + 16 * 8 + 64 * 8 + 64 * 4 + 16;
 }
 static size_t chol_smem(int n) { return (size_t)n * n * 4 + (size_t)8 * round_up8(n) * 4 + 64 * 4; }
 
@@ -909,13 +1040,13 @@ cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     const int cols_per_cta = kApplyWarps * kApplyCols;
     dim3 g((a.n + cols_per_cta - 1) / cols_per_cta, n_env);
-    const size_t asm_bytes = (size_t)(2 * kApplyChunk * a.n + 2 * kApplyChunk) * sizeof(float);
+    const size_t asm_bytes = (size_t)(2 * kApplyChunk * a.n + 2 * 256) * sizeof(float);
     static size_t conf_q1[32] = {}, conf_q2[32] = {};
     e = ensure_smem_attr(applyq_kernel<true, true>, asm_bytes, conf_q1);
     if (e == cudaSuccess) e = ensure_smem_attr(applyq_kernel<false, false>, asm_bytes, conf_q2);
     if (e != cudaSuccess) return e;
-    applyq_kernel<true, true><<<g, kApplyWarps * 32, asm_bytes, st>>>(a.Vh, a.tau, a.F, a.Z, a.n);
-    applyq_kernel<false, false><<<g, kApplyWarps * 32, asm_bytes, st>>>(a.Vh, a.tau, a.Z, a.cov, a.n);
+    applyq_kernel<true, true><<<g, kApplyWarps * 32, asm_bytes, st>>>(a.Vh, a.Tw, a.F, a.Z, a.n);
+    applyq_kernel<false, false><<<g, kApplyWarps * 32, asm_bytes, st>>>(a.Vh, a.Tw, a.Z, a.cov, a.n);
     return cudaGetLastError();
 }
 

@@ -6,6 +6,7 @@ namespace covo {
 
 constexpr int kZoloPoles = 16;    // poles of the rational approximation of x^(-1/2)
 constexpr int kZoloLadder = 10;   // spectral-ratio ladder: M/m = 4^(4+i), i = 0..9
+constexpr int kWyBlock = 8;       // reflectors per compact-WY block in apply-Q
 constexpr int kSigmaMaxN = 224;   // n = 4H limit of the shared-memory resident kernels (H <= 56)
 constexpr double kCovoOffset = 1e-2;  // "offset = -min_eign + 1e-2", controllers/covo.py:120-121
 
@@ -16,6 +17,7 @@ struct SigmaArgs {
     const float* R;      // [E][n][n]
     float* Vh;           // [E][n][n]  row k = Householder vector v_k (zeros for index <= k, v[k+1] = 1)
     float* tau;          // [E][n]
+    float* Tw;           // [E][n/8 + 1][64]  compact-WY T factors of the reflector blocks (8 per block)
     float* F;            // [E][n][n]  exp(log_const/2) * (T - lam_min + offset)^(-1/2)
     float* Z;            // [E][n][n]  Q F
     float* cov;          // [E][n][n]  Sigma = Q F Q^T (symmetrised)          -> a_cov
