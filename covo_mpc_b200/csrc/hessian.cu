@@ -100,14 +100,23 @@ __global__ void __launch_bounds__(kAsmThreads) hess_assemble_kernel(const Hessia
     const int rec = 14 * NPAIR + 14 * NZ;
     COVO_STAMP(a, 0);
 
-    for (int i = tid; i < H * NX * NZP; i += blockDim.x) {
-        int t = i / (NX * NZP), rr = i - t * (NX * NZP);
-        int r = rr / NZP, c = rr - r * NZP;
-        G[i] = (c < NZ) ? wsb[(long long)t * rec + 14 * NPAIR + r * NZ + c] : 0.f;
-    }
-    for (int i = tid; i < H * NX; i += blockDim.x) {
-        int t = i / NX, k = i - t * NX;
-        cg[i] = (t >= 1) ? wsb[(long long)t * rec + 14 * NPAIR + 13 * NZ + k] : 0.f;  // c_0 is constant in U
+    // [A_t | B_t | grad c_t] rows of the workspace: 14 x 17 contiguous floats per t, several loads in flight
+    {
+        const int per_t = 14 * NZ;  // 238
+        const int total = H * per_t;
+#pragma unroll 4
+        for (int i = tid; i < total; i += kAsmThreads) {
+            const int t = i / per_t, rr = i - t * per_t;
+            const int r = rr / NZ, c = rr - r * NZ;
+            const float val = __ldg(wsb + (long long)t * rec + 14 * NPAIR + rr);
+            if (r < NX) G[(t * NX + r) * NZP + c] = val;
+            else if (c < NX) cg[t * NX + c] = (t >= 1) ? val : 0.f;  // c_0 is constant in U
+        }
+        for (int i = tid; i < H * NX; i += kAsmThreads) {  // zero the three pad columns
+            G[i * NZP + 17] = 0.f;
+            G[i * NZP + 18] = 0.f;
+            G[i * NZP + 19] = 0.f;
+        }
     }
     for (int i = tid; i < NX; i += blockDim.x) lam[H * NX + i] = 0.f;
     __syncthreads();
