@@ -25,6 +25,7 @@
 #include <math.h>
 #include <math_constants.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "sigma.cuh"
 
@@ -159,292 +160,351 @@ __device__ int sturm_count(const double* d, const double* e2, int n, double x) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-// E1 + E2
+// E1: Householder tridiagonalisation with the matrix resident in REGISTERS of a thread-block CLUSTER
 // ---------------------------------------------------------------------------------------------
-// Row pitch of the shared-memory matrix: n + 4 or n + 8 so that pitch == 4 (mod 8): eight consecutive rows
-// of one float4 column group then fall into eight different bank quadruples (conflict-free LDS.128).
-__host__ __device__ inline int tridiag_pitch(int n) { return (n & 7) ? n + 8 : n + 4; }
-__host__ __device__ inline int tridiag_region_floats(int n) {
-    int a = n * tridiag_pitch(n);
-    // E2 scratch: fp64 pivot numerators/denominators [2][2][17][n], then float gd[16][n], and the
-    // (hi, lo, sign/zero) prefix arrays of the semiseparable generators [16][n+1] x 3
-    int b = (2 * 2 * (kZoloPoles + 1) * n) * 2 + kZoloPoles * n + 3 * kZoloPoles * (n + 1);
-    return ((a > b ? a : b) + 3) & ~3;
+// NC CTAs x 8 warps.  Element (i, j) of A lives in lane (i mod 32), row slot i / 32 of the warp that owns column
+// j; global warp g = 8 rank + warp owns the column PAIRS (2 g + 16 NC c, +1), c = 0..C2-1, each pair held as one
+// float2 so that the rank-2 update and the matvec run on the packed FFMA2 pipe of sm_100.  Every warp holds
+// complete columns (rows over the lanes):
+//   * the matvec q = A v' is 7 FFMA2 per column pair followed by ONE transposition through a private
+//     shared-memory tile -- no shared-memory traffic for A itself, ever;
+//   * the scalar work of a step -- s = q.v, w = tau q - (tau^2 s / 2) v, the UPDATED row m
+//         r_i = A[m][i] - v_i w_m - w_i      (look-ahead: the next Householder vector is made of it),
+//     its norm, (beta, tau') and v' -- is done REDUNDANTLY by every warp of every CTA on 7 values per lane: no
+//     block-wide reduction, no special warp, ONE (cluster) barrier per step;
+//   * what a step exchanges is tiny: every warp writes its entries of q and of row m+1 into the shared memory
+//     of ALL CTAs of the cluster (distributed shared memory), 2 x n floats per step in total.
+// Iteration m (0 <= m < n), LAPACK ssytd2 recurrences; state: A carries reflectors 0..m-2; (v, tau, q = A v)
+// belong to reflector m-1:
+//   1. s, w;  r = updated row m -> d_m = r_m, Householder of r[m+1:] -> e_m = beta, tau_m, v_m
+//   2. A <- A - v w^T - w v^T     (finished columns have v_j = w_j = 0: no masking, no branches)
+//   3. publish row m+1;  q = A v_m  (entries j <= m are stored as zero, which makes w_j = 0 there)  -> barrier
+// Why a cluster: one SM is issue-/latency-bound on this loop (two single-CTA versions, 16 warps x 128 registers
+// and 8 warps x 255 registers, ran at 0.25 IPC per warp: the register file is full of A, so nothing can be
+// software-pipelined).  Spreading the columns over NC SMs leaves ~60 registers of A per thread, straight-line
+// code, and the per-step cost becomes the redundant scalar chain plus one cluster barrier.
+constexpr int EW = 8;         // warps per CTA
+constexpr int ET = EW * 32;   // threads per CTA
+constexpr int RS = kSigmaMaxN / 32;  // row slots per lane (7)
+constexpr int kTilePitch = 36;       // floats; rows of the transposition tile are float4-aligned and conflict-free
+
+__host__ __device__ inline size_t e1_smem_bytes(int n, int c2) {
+    // reflector store Vs [n][n]; q[2][256], v[2][256], row[2][256], tau[256], d[256], e[256]; transposition tiles
+    return ((size_t)n * n + 256 * 9 + EW * 2 * c2 * kTilePitch + 4 + EW * 64) * sizeof(float);  // + mbarrier pair, scratch
 }
 
-__global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    const int n = a.n, tid = threadIdx.x, env = blockIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int LD = tridiag_pitch(n);
-    float* As = reinterpret_cast<float*>(smraw);          // [n][LD]
-    float* vs = As + tridiag_region_floats(n);            // [2048] v/q double buffers + w (see E1)
-    float* ws = vs + 256;
-    float* rw4 = vs + 2048;                               // [256] float4: per-row (-v, -w, vnext, 0) of the pass
-    float* taus = vs + 3072;                              // [256] tau_k
-    double* dd = reinterpret_cast<double*>(vs + 3328);    // [256]
-    double* ee = dd + 256;                                // [256]
-    double* e2s = ee + 256;                               // [256] e^2
-    double* sc = e2s + 256;                               // [16] scalars
-    double* rdbuf = sc + 16;                              // [64]
-    float* red = reinterpret_cast<float*>(rdbuf + 64);    // [64]
-    int* ired = reinterpret_cast<int*>(red + 64);         // [4]
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `saddr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ unsigned dsmem_addr(unsigned saddr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void dsmem_st2(unsigned addr, float2 v) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+// Store that carries its own completion signal: the destination CTA's mbarrier receives 4 bytes of
+// transaction count when the value has landed -- no fence, no separate arrive.
+__device__ __forceinline__ void dsmem_st_signal(unsigned addr, float v, unsigned mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(addr), "f"(v),
+                 "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+    }
+}
+// MUFU approximations + one Newton step (~1 ulp), without the IEEE slow paths of sqrtf / division
+__device__ __forceinline__ float rcp_newton(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * fmaf(-x, r, 2.f);
+}
+__device__ __forceinline__ float rsqrt_newton(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * fmaf(-0.5f * x * r, r, 1.5f);
+}
+
+// Warp all-reduce through shared memory: one STS, eight broadcast LDS.128 and an add tree -- about half the
+// latency of the five dependent SHFL + FADD levels of a butterfly.  Every lane adds in the same order, so all
+// lanes (and all warps given the same inputs) obtain bit-identical sums.
+__device__ __forceinline__ float wsum_smem(float x, float* scratch /* [32], warp-private, 16-byte aligned */) {
+    scratch[threadIdx.x & 31] = x;
+    __syncwarp();
+    const float4* p4 = reinterpret_cast<const float4*>(scratch);
+    const float4 a0 = p4[0], a1 = p4[1], a2 = p4[2], a3 = p4[3], a4 = p4[4], a5 = p4[5], a6 = p4[6], a7 = p4[7];
+    const float b0 = (a0.x + a0.y) + (a0.z + a0.w), b1 = (a1.x + a1.y) + (a1.z + a1.w);
+    const float b2 = (a2.x + a2.y) + (a2.z + a2.w), b3 = (a3.x + a3.y) + (a3.z + a3.w);
+    const float b4 = (a4.x + a4.y) + (a4.z + a4.w), b5 = (a5.x + a5.y) + (a5.z + a5.w);
+    const float b6 = (a6.x + a6.y) + (a6.z + a6.w), b7 = (a7.x + a7.y) + (a7.z + a7.w);
+    return ((b0 + b1) + (b2 + b3)) + ((b4 + b5) + (b6 + b7));
+}
+
+template <int C2, int NC>
+__global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
+    extern __shared__ __align__(16) float esm[];
+    const int n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (NC > 1) ? (int)cluster_rank() : 0;
+    const int env = blockIdx.x / NC;
+    const int gw = rank * EW + warp;        // global warp: owns columns 2 gw + CS c, 2 gw + CS c + 1
+    constexpr int GW = EW * NC;             // warps of the cluster
+    constexpr int CS = 2 * GW;              // column stride between pair slots
+    float* Vs = esm;                    // [n][n] reflectors (row k = v_k)
+    float* qsm0 = esm + n * n;          // [2][256]
+    float* vsm0 = qsm0 + 512;           // [2][256]
+    float* row0 = vsm0 + 512;           // [2][256]
+    float* taus = row0 + 512;           // [256]
+    float* dsm = taus + 256;            // [256]
+    float* esm_e = dsm + 256;           // [256]
+    float* tile = esm_e + 256 + warp * 2 * C2 * kTilePitch;  // [2 C2][36] private transposition tile
+    unsigned long long* mbars = reinterpret_cast<unsigned long long*>(esm_e + 256 + EW * 2 * C2 * kTilePitch);  // [2]
+    float* red = esm_e + 256 + EW * 2 * C2 * kTilePitch + 4 + warp * 64;  // [2][32] private reduction scratch
 
     const float* Rg = a.R + (long long)env * n * n;
     float* Vg = a.Vh + (long long)env * n * n;
     float* taug = a.tau + (long long)env * n;
-
-    // R <- (R + R^T)/2 (controllers/covo.py:117): coalesced load, then symmetrise in shared memory
-    for (int i = warp; i < n; i += TT / 32)
-        for (int j = lane; j < n; j += 32) As[i * LD + j] = Rg[i * n + j];
-    for (int i = tid; i < 3328; i += TT) vs[i] = 0.f;
-    __syncthreads();
-    for (int i = warp; i < n; i += TT / 32)
-        for (int j = lane; j < i; j += 32) {
-            const float s2 = 0.5f * (As[i * LD + j] + As[j * LD + i]);
-            As[i * LD + j] = s2;
-            As[j * LD + i] = s2;
-        }
-    __syncthreads();
     COVO_STAMP(a, 8);
-
-    // ---- E1: Householder tridiagonalisation (LAPACK ssytd2 recurrences), one pass over A per step -----
-    // thread = (column group cgi of 4 columns, row class ch of 16): rows k+1+ch, k+1+ch+16, ...
-    // State entering step k: A updated through step k-1; v_k (vs[cur], zero-extended, v[k+1] = 1), tau_k and
-    // the raw matvec q_k = A v_k (qs[cur]).  Step k:
-    //   A) s = q.v (block reduction)                      -> w = tau q - (tau^2 s / 2) v
-    //   B) warp 0 forms the UPDATED row k+1 from (A, v, w), i.e. the next Householder vector v_{k+1}
-    //      (look-ahead) while the other threads publish w;
-    //   C) one pass: A <- A - v w^T - w v^T fused with q_{k+1} = A_new v_{k+1}.
-    const int cgi = tid >> 4, ch = tid & 15;
-    float* vbuf[2] = {vs, vs + 512};  // vs, ws are reused as [cur/next] v and q buffers (4 x 256 floats total)
-    float* qbuf[2] = {ws, ws + 512};
-    // layout: vs[0..255] v0 | ws[0..255] q0 | vs+512 v1 | ws+512 q1   (allocated below: 1024 floats)
-    int cur = 0;
-    // prologue: v_0, tau_0 from row 0; q_0 = A v_0
-    if (warp == 0) {
-        const float* x = As;
-        float sig = 0.f;
-        for (int j = 2 + lane; j < n; j += 32) sig = fmaf(x[j], x[j], sig);
-        sig = wsum(sig);
-        const float x0 = x[1];
-        float beta, tau, scale;
-        if (sig == 0.f) {
-            beta = x0; tau = 0.f; scale = 0.f;
-        } else {
-            beta = -copysignf(sqrtf(fmaf(x0, x0, sig)), x0);
-            tau = (beta - x0) / beta;
-            scale = 1.0f / (x0 - beta);
-        }
-        for (int j = lane; j < 256; j += 32) {
-            float v = 0.f;
-            if (j == 1) v = 1.f;
-            else if (j >= 2 && j < n && tau != 0.f) v = x[j] * scale;
-            vbuf[0][j] = v;
-        }
-        if (lane == 0) {
-            red[0] = beta;
-            red[1] = tau;
-        }
+    for (int i = tid; i < 256 * 9; i += ET) qsm0[i] = 0.f;
+    const unsigned mbar_local = (unsigned)__cvta_generic_to_shared(mbars);
+    if (tid == 0) {
+        mbar_init(mbar_local, 1);
+        mbar_init(mbar_local + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    {
-        const int c0 = 0, col = c0 + 4 * cgi;
-        const bool active = cgi < (n >> 2);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) {
-            for (int i = 1 + ch; i < n; i += 16) {
-                const float4 av = *reinterpret_cast<const float4*>(As + i * LD + col);
-                const float vi = vbuf[0][i];
-                acc.x = fmaf(av.x, vi, acc.x);
-                acc.y = fmaf(av.y, vi, acc.y);
-                acc.z = fmaf(av.z, vi, acc.z);
-                acc.w = fmaf(av.w, vi, acc.w);
-            }
-        }
+    // (R + R^T)/2 (controllers/covo.py:117) straight from HBM / L2 into registers
+    float2 A2[RS][C2];
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    for (int c = 0; c < C2; ++c) {
+        const int j0 = 2 * gw + CS * c;
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            const int i = lane + 32 * r;
+            float2 x = make_float2(0.f, 0.f);
+            if (i < n && j0 < n) {  // n is a multiple of 4 and j0 is even: j0 + 1 < n as well
+                const float2 rowv = *reinterpret_cast<const float2*>(Rg + (long long)i * n + j0);
+                x.x = 0.5f * (rowv.x + Rg[(long long)j0 * n + i]);
+                x.y = 0.5f * (rowv.y + Rg[(long long)(j0 + 1) * n + i]);
+            }
+            A2[r][c] = x;
         }
-        float part0 = 0.f;
-        if (active && ch == 0) {
-            *reinterpret_cast<float4*>(qbuf[0] + col) = acc;
-            const float4 vv = *reinterpret_cast<const float4*>(vbuf[0] + col);
-            part0 = acc.x * vv.x + acc.y * vv.y + acc.z * vv.z + acc.w * vv.w;  // v is zero for j <= 0
-        }
-        part0 += __shfl_xor_sync(0xffffffffu, part0, 16);
-        if (lane == 0) red[8 + warp] = part0;
     }
-    __syncthreads();
-    long long pa[6] = {0, 0, 0, 0, 0, 0}, pt0 = 0;
-#define PH(i) do { if (a.prof && tid == 0) { long long t_ = clock64(); pa[i] += t_ - pt0; pt0 = t_; } } while (0)
+    // shared::cluster addresses of the exchange buffers and of the mbarrier pair in every CTA of the cluster
+    unsigned q_remote[NC], row_remote[NC], bar_remote[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        q_remote[k] = dsmem_addr((unsigned)__cvta_generic_to_shared(qsm0), k);
+        row_remote[k] = dsmem_addr((unsigned)__cvta_generic_to_shared(row0), k);
+        bar_remote[k] = dsmem_addr(mbar_local, k);
+    }
+    cluster_barrier();  // zero-fill and mbarrier init done everywhere before anybody publishes
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < C2; ++c) {
+            const int j0 = 2 * gw + CS * c;
+            if (j0 < n) {
+#pragma unroll
+                for (int k = 0; k < NC; ++k) dsmem_st2(row_remote[k] + 4 * j0, A2[0][c]);  // row 0
+            }
+        }
+    }
+    cluster_barrier();
+    COVO_STAMP(a, 15);
+
+    float vi[RS];
+#pragma unroll
+    for (int r = 0; r < RS; ++r) vi[r] = 0.f;
+    float tau = 0.f;
+    long long pa[4] = {0, 0, 0, 0}, pt0 = 0;
+#define PH(i) do { if (a.prof && tid == 0 && blockIdx.x == 0) { long long t_ = clock64(); pa[i] += t_ - pt0; pt0 = t_; } } while (0)
     if (a.prof && tid == 0) pt0 = clock64();
-    for (int k = 0; k < n - 2; ++k) {
-        const float* v = vbuf[cur];
-        const float* q = qbuf[cur];
-        float* vn = vbuf[cur ^ 1];
-        float* qn = qbuf[cur ^ 1];
-        const float beta = red[0], tau = red[1];
-        // A) bookkeeping of step k.  No global stores inside the loop: a barrier after a global store waits for the
-        //    L2 round trip.  v_k is parked LAPACK-style in the dead part of row k of A (entries j >= k+2; v[k+1] = 1
-        //    is implicit) and everything is written to HBM once after the loop.
-        if (tid >= 512 && tid < 512 + 256) {
-            const int j = tid - 512;
-            if (j >= k + 2 && j < n) As[k * LD + j] = v[j];
+    for (int m = 0; m < n; ++m) {
+        const int p = (m & 1) << 8, pn = p ^ 256;
+        const float* qsm = qsm0 + p;    // q = A v of reflector m-1 (zero for indices < m)
+        const float* vsm = vsm0 + p;    // v of reflector m-1 (zeros for m = 0)
+        const float* rowm = row0 + p;   // row m of A (reflectors <= m-2 applied)
+        // ---- 1. scalar work, redundantly in every warp ------------------------------------------------
+        float wi[RS], ri[RS];
+        float pe = 0.f, po = 0.f;
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            wi[r] = qsm[lane + 32 * r];  // q_i for now
+            ri[r] = rowm[lane + 32 * r];
+            if (r & 1) po = fmaf(wi[r], vi[r], po); else pe = fmaf(wi[r], vi[r], pe);
         }
-        if (tid == 800) {
-            dd[k] = (double)As[k * LD + k];
-            ee[k] = (double)beta;
-            taus[k] = tau;
+        const int m1 = min(m + 1, n - 1);
+        const float q_m = qsm[m], q_m1 = qsm[m1], row_m = rowm[m], row_m1 = rowm[m1], v_m1 = vsm[m1];
+        // column values of the rank-2 update, loaded ahead of the reduction
+        float2 vc[C2], qc[C2];
+#pragma unroll
+        for (int c = 0; c < C2; ++c) {
+            vc[c] = *reinterpret_cast<const float2*>(vsm + 2 * gw + CS * c);
+            qc[c] = *reinterpret_cast<const float2*>(qsm + 2 * gw + CS * c);
         }
-        // B) look-ahead Householder vector of step k+1 from the UPDATED row k+1, all threads:
-        //      s = q.v (partials left in red[8..39] by the previous pass), c2 = tau^2 s / 2,
-        //      w_j = tau q_j - c2 v_j,   updated row  r_j = A[k+1][j] - w_j - w_{k+1} v_j   (v_{k+1} = 1)
-        //    B1: thread j forms w_j, r_j and its share of sigma = sum_{j >= k+3} r_j^2  -> barrier
-        //    B2: every warp finishes sigma, the scalar chain (beta', tau', scale'), thread j publishes v'_j
-        // Only warps 0..7 (one thread per entry of the row) run B; the other 24 warps go straight to the barriers,
-        // so the eight working warps see near single-warp latencies on their shuffle / MUFU chains.
-        float wj = 0.f, rj = 0.f;
-        const int j = tid;
-        if (warp < 8) {
-            const float sdot = wsum(red[8 + lane]);
-            const float c2 = 0.5f * tau * tau * sdot;
-            const int r1 = k + 1;
-            const float wr1 = fmaf(tau, q[r1], -c2 * v[r1]);
-            const float vj = v[j];
-            float sq = 0.f;
-            if (j > k && j < n) wj = fmaf(tau, q[j], -c2 * vj);
-            if (j >= k + 2 && j < n) rj = As[r1 * LD + j] - wj - wr1 * vj;
-            if (j >= k + 3) sq = rj * rj;
-            ws[1024 + j] = wj;
-            if (j == k + 2) red[4] = rj;  // x0
-            sq = wsum(sq);
-            if (lane == 0) red[40 + warp] = sq;
+        const float s = wsum_smem(pe + po, red);
+        const float c2 = 0.5f * tau * tau * s;  // tau = 0 when there is no previous reflector: w = 0
+        const float w_m = fmaf(tau, q_m, -c2);  // v_{m-1}[m] = 1
+        const float w_m1 = fmaf(tau, q_m1, -c2 * v_m1);
+        float sge = 0.f, sgo = 0.f;
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            const int i = lane + 32 * r;
+            const float w = fmaf(tau, wi[r], -c2 * vi[r]);  // zero for i < m (q and v are)
+            wi[r] = w;
+            const float x = (i >= m + 2 && i < n) ? ri[r] - vi[r] * w_m - w : 0.f;
+            ri[r] = x;
+            if (r & 1) sgo = fmaf(x, x, sgo); else sge = fmaf(x, x, sge);
         }
-        __syncthreads();
-        if (warp < 8) {
-            float sig = red[40 + (lane & 7)];
-            sig += __shfl_xor_sync(0xffffffffu, sig, 4);
-            sig += __shfl_xor_sync(0xffffffffu, sig, 2);
-            sig += __shfl_xor_sync(0xffffffffu, sig, 1);
-            const float x0 = red[4];
-            float nbeta, ntau, nscale;
-            if (sig == 0.f) {
-                nbeta = x0; ntau = 0.f; nscale = 0.f;
-            } else {
-                // MUFU rsq / rcp + one Newton step (~1 ulp), instead of the IEEE sqrt / div sequences
-                const float nn2 = fmaf(x0, x0, sig);
-                float rs = rsqrtf(nn2);
-                rs = rs * (1.5f - 0.5f * nn2 * rs * rs);
-                nbeta = -copysignf(nn2 * rs, x0);
-                float rb = __frcp_rn(nbeta);
-                ntau = (nbeta - x0) * rb;
-                nscale = __frcp_rn(x0 - nbeta);
-            }
-            float vv = 0.f;
-            if (j == k + 2 && j < n) vv = 1.f;
-            else if (j >= k + 3 && j < n && ntau != 0.f) vv = rj * nscale;
-            vn[j] = vv;
-            reinterpret_cast<float4*>(rw4)[j] = make_float4(-v[j], -wj, vv, 0.f);
-            if (tid == 0) {
-                red[2] = nbeta;
-                red[3] = ntau;
-            }
-        }
-        __syncthreads();
-        PH(1);
-        // C) fused pass
+        // ---- 2. rank-2 update with reflector m-1, in the shadow of the second reduction ------------------
+        // (unconditional: tau = 0 gives w = 0 and a zero update; finished columns have v_j = w_j = 0)
         {
-            const float* wv = ws + 1024;
-            const int c0 = (k + 1) & ~3;
-            const int ncg = (n - c0) >> 2;
-            // thread map: 64 column groups x 16 row classes while more than 32 column groups are alive, then
-            // 32 x 32 (halves the rows per thread once half of the column-group slots would idle)
-            const bool wide = false;  // measured: the 32 x 32 map is slower (fixed per-step costs dominate the tail)
-            const int cg2 = wide ? (tid >> 5) : cgi;
-            const int ch2 = wide ? lane : ch;
-            const int rstep = wide ? 32 : 16;
-            const bool active = cg2 < ncg;
-            const int col = c0 + 4 * cg2;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active) {
-                const float4 wj4 = *reinterpret_cast<const float4*>(wv + col);
-                const float4 vj4 = *reinterpret_cast<const float4*>(v + col);
-                const float4* rowp = reinterpret_cast<const float4*>(rw4);
-#pragma unroll 4
-                for (int i = k + 1 + ch2; i < n; i += rstep) {
-                    const float4 r4 = rowp[i];  // (-v_i, -w_i, vnext_i, 0): one LDS.128 per row
-                    float4* p = reinterpret_cast<float4*>(As + i * LD + col);
-                    float4 av = *p;
-                    av.x = fmaf(r4.x, wj4.x, fmaf(r4.y, vj4.x, av.x));
-                    av.y = fmaf(r4.x, wj4.y, fmaf(r4.y, vj4.y, av.y));
-                    av.z = fmaf(r4.x, wj4.z, fmaf(r4.y, vj4.z, av.z));
-                    av.w = fmaf(r4.x, wj4.w, fmaf(r4.y, vj4.w, av.w));
-                    *p = av;
-                    acc.x = fmaf(av.x, r4.z, acc.x);
-                    acc.y = fmaf(av.y, r4.z, acc.y);
-                    acc.z = fmaf(av.z, r4.z, acc.z);
-                    acc.w = fmaf(av.w, r4.z, acc.w);
+            const float2 tau2 = make_float2(tau, tau), nc2 = make_float2(-c2, -c2);
+#pragma unroll
+            for (int c = 0; c < C2; ++c) {
+                const float2 wc = __ffma2_rn(tau2, qc[c], __fmul2_rn(nc2, vc[c]));
+#pragma unroll
+                for (int r = 0; r < RS; ++r)
+                    A2[r][c] = __ffma2_rn(make_float2(-vi[r], -vi[r]), wc,
+                                          __ffma2_rn(make_float2(-wi[r], -wi[r]), vc[c], A2[r][c]));
+            }
+        }
+        const unsigned bar_off = (m & 1) << 3;
+        // publish column m+1 (= row m+1): it sits in ONE warp, already in the (lane + 32 r) layout of the vectors
+        if (m + 1 < n && (((m + 1) >> 1) & (GW - 1)) == gw) {
+            const int cstar = (m + 1) / CS;
+            const bool hi = (m + 1) & 1;
+#pragma unroll
+            for (int c = 0; c < C2; ++c)
+                if (c == cstar) {
+#pragma unroll
+                    for (int r = 0; r < RS; ++r) {
+                        const float val = hi ? A2[r][c].y : A2[r][c].x;
+#pragma unroll
+                        for (int k = 0; k < NC; ++k)
+                            dsmem_st_signal(row_remote[k] + 4 * (pn + lane + 32 * r), val, bar_remote[k] + bar_off);
+                    }
+                }
+        }
+        const float sg = wsum_smem(sge + sgo, red + 32);
+        const float dm = row_m - 2.f * w_m;
+        const float x0 = (m + 1 < n) ? row_m1 - v_m1 * w_m - w_m1 : 0.f;
+        // Householder scalars, branch-free: norm = ||(x0, r)||, beta = -sign(x0) norm, t = x0 - beta,
+        // tau = t / (sign(x0) norm) = |t| / norm, scale = 1 / t   (sigma = 0: tau = scale = 0, beta = x0)
+        const bool live = sg > 1e-30f;
+        const float nn2 = fmaf(x0, x0, live ? sg : 1.f);
+        const float rs = rsqrt_newton(nn2);
+        const float nrm = copysignf(nn2 * rs, x0);
+        const float t = x0 + nrm;
+        const float nbeta = live ? -nrm : x0;
+        const float ntau = live ? fabsf(t) * rs : 0.f;
+        const float nscale = live ? rcp_newton(t) : 0.f;
+        float vn[RS];
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            const int i = lane + 32 * r;
+            vn[r] = (i == m + 1 && i < n) ? 1.f : ri[r] * nscale;  // v_m (ri is zero outside m+2 <= i < n)
+        }
+        const bool do_matvec = (m <= n - 3) && (ntau != 0.f);
+        PH(0);
+        // ---- 3. q = A v_m ---------------------------------------------------------------------------------
+#pragma unroll
+        for (int r = 0; r < RS; ++r) vi[r] = vn[r];
+        tau = ntau;
+        if (do_matvec) {
+#pragma unroll
+            for (int c = 0; c < C2; ++c) {
+                float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int r = 0; r < RS; r += 2) sa = __ffma2_rn(A2[r][c], make_float2(vi[r], vi[r]), sa);
+#pragma unroll
+                for (int r = 1; r < RS; r += 2) sb = __ffma2_rn(A2[r][c], make_float2(vi[r], vi[r]), sb);
+                const float2 t = __fadd2_rn(sa, sb);
+                // transposition through the warp's tile: partial sums of column k at tile[k][lane]
+                tile[(2 * c) * kTilePitch + lane] = t.x;
+                tile[(2 * c + 1) * kTilePitch + lane] = t.y;
+            }
+            __syncwarp();
+            if (lane < 2 * C2) {  // lane L adds up row L = the 32 partials of its column k = L
+                const float4* rowp = reinterpret_cast<const float4*>(tile + lane * kTilePitch);
+                float4 t4 = rowp[0];
+#pragma unroll
+                for (int t = 1; t < 8; ++t) {
+                    const float4 x = rowp[t];
+                    t4.x += x.x; t4.y += x.y; t4.z += x.z; t4.w += x.w;
+                }
+                const float t1 = (t4.x + t4.y) + (t4.z + t4.w);
+                const int j = 2 * gw + CS * (lane >> 1) + (lane & 1);
+                if (j < n) {
+                    const float qv = (j >= m + 1) ? t1 : 0.f;
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) dsmem_st_signal(q_remote[k] + 4 * (pn + j), qv, bar_remote[k] + bar_off);
                 }
             }
-            if (wide) {
-                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
-                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
-                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
-            }
+            __syncwarp();  // the tile is rewritten in the next step
+        }
+        if (warp == (m & (EW - 1))) {  // bookkeeping by a rotating warp (every CTA keeps its own copy)
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+            for (int r = 0; r < RS; ++r) {
+                const int i = lane + 32 * r;
+                if (i < n) {
+                    vsm0[pn + i] = vi[r];
+                    Vs[m * n + i] = vi[r];
+                }
             }
-            // leaders publish q_{k+1} and their share of s_{k+1} = q_{k+1} . v_{k+1}
-            float partn = 0.f;
-            if (active && ch2 == 0) {
-                *reinterpret_cast<float4*>(qn + col) = acc;
-                const float4 vv = *reinterpret_cast<const float4*>(vn + col);  // zero for j <= k+1
-                partn = acc.x * vv.x + acc.y * vv.y + acc.z * vv.z + acc.w * vv.w;
+            if (lane == 0) {
+                dsm[m] = dm;
+                esm_e[m] = nbeta;
+                taus[m] = ntau;
             }
-            if (!wide) partn += __shfl_xor_sync(0xffffffffu, partn, 16);
-            else partn = __shfl_sync(0xffffffffu, partn, 0);
-            // red[8..39] of this step were consumed before sync B, so they can be overwritten here
-            if (lane == 0) red[8 + warp] = partn;
-            if (tid == 0) {
-                red[0] = red[2];
-                red[1] = red[3];
-            }
+            __syncwarp();
+            // this step's incoming traffic: column m+1 (7 x 32 floats) and, if the matvec runs, the n entries of q
+            if (lane == 0) mbar_expect_tx(mbar_local + bar_off, ((m + 1 < n) ? 4u * 32u * RS : 0u) + (do_matvec ? 4u * n : 0u));
         }
-        __syncthreads();
         PH(2);
-        cur ^= 1;
+        // everything this CTA reads in step m+1 has landed when its mbarrier phase completes
+        mbar_wait(mbar_local + bar_off, (m >> 1) & 1);
+        PH(3);
     }
-    if (a.prof && tid == 0) for (int i = 0; i < 5; ++i) a.prof[40 + i] = pa[i];
-    if (tid == 0) {
-        dd[n - 2] = (double)As[(n - 2) * LD + (n - 2)];
-        dd[n - 1] = (double)As[(n - 1) * LD + (n - 1)];
-        ee[n - 2] = (double)As[(n - 1) * LD + (n - 2)];
-        ee[n - 1] = 0.0;
-        taus[n - 2] = 0.f;
-        taus[n - 1] = 0.f;
-    }
+#undef PH
+    if (a.prof && tid == 0 && blockIdx.x == 0)
+        for (int i = 0; i < 4; ++i) a.prof[40 + i] = pa[i];
     __syncthreads();
-    // reflectors -> HBM, row k = v_k zero-extended (coalesced), and tau
-    for (int k2 = warp; k2 < n; k2 += TT / 32) {
-        const bool live = (k2 < n - 2) && (taus[k2] != 0.f);
-        for (int j = lane; j < n; j += 32) {
-            float vv = 0.f;
-            if (k2 < n - 2) {
-                if (j == k2 + 1) vv = 1.f;
-                else if (j >= k2 + 2 && live) vv = As[k2 * LD + j];
-            }
-            Vg[(long long)k2 * n + j] = vv;
+    if (NC > 1) cluster_barrier();  // nobody leaves while a peer could still be sending to it
+    COVO_STAMP(a, 9);
+    // every CTA holds the complete result (d, e, tau, reflectors): the write-out is split over the ranks.
+    // d, e -> HBM for the E2 kernel; reflectors (row k = v_k, zero-extended) and tau for apply-Q
+    if (rank == 0) {
+        double* dg = a.diag + (long long)env * 4 * n;
+        if (tid < n) {
+            dg[tid] = (double)dsm[tid];
+            dg[n + tid] = (tid < n - 1) ? (double)esm_e[tid] : 0.0;
+            taug[tid] = (tid < n - 2) ? taus[tid] : 0.f;
         }
     }
-    if (tid < n) taug[tid] = taus[tid];
+    if (tid >= n - 2 && tid < n) taus[tid] = 0.f;
+    for (int idx = rank * ET + tid; idx < n * n; idx += ET * NC) {
+        const int k2 = idx / n;
+        Vg[idx] = (k2 < n - 2) ? Vs[idx] : 0.f;
+    }
     __syncthreads();
     // Compact-WY factors for apply-Q: block m holds reflectors k = k_hi-7 .. k_hi, k_hi = n-3-8m (ascending local
     // index r <-> k = k_hi-7+r; missing ones have tau = 0).  H_{k_lo} ... H_{k_hi} = I - V T V^T, T upper triangular
@@ -452,36 +512,28 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
     {
         const int nblk = (n - 2 + kWyBlock - 1) / kWyBlock;
         float* Twg = a.Tw + (long long)env * (n / kWyBlock + 1) * 64;
-        float* gsm = reinterpret_cast<float*>(rdbuf);  // per-warp scratch is not needed: one warp per block, Gram in regs
-        (void)gsm;
-        for (int m = warp; m < nblk; m += TT / 32) {
-            const int khi = n - 3 - kWyBlock * m;
-            // Gram entries g[r][c] = v_r . v_c for r < c, all lanes end with the sums
+        for (int mb = gw; mb < nblk; mb += EW * NC) {
+            const int khi = n - 3 - kWyBlock * mb;
             float g[8][8];
-            float vr[8][7];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int k = khi - 7 + r;
-#pragma unroll
-                for (int li = 0; li < 7; ++li) {
-                    const int i = lane + 32 * li;
-                    float vv = 0.f;
-                    if (k >= 0 && i < n) {
-                        if (i == k + 1) vv = 1.f;
-                        else if (i >= k + 2 && taus[k] != 0.f) vv = As[k * LD + i];
-                    }
-                    vr[r][li] = vv;
-                }
-            }
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
-                for (int c = r + 1; c < 8; ++c) {
-                    float d = 0.f;
+                for (int c = r + 1; c < 8; ++c) g[r][c] = 0.f;
+            // Gram entries g[r][c] = v_r . v_c for r < c, accumulated slot by slot (keeps the register count low)
 #pragma unroll
-                    for (int li = 0; li < 7; ++li) d = fmaf(vr[r][li], vr[c][li], d);
-                    g[r][c] = d;
+            for (int li = 0; li < RS; ++li) {
+                const int i = lane + 32 * li;
+                float vr[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int k = khi - 7 + r;
+                    vr[r] = (k >= 0 && i < n) ? Vs[k * n + i] : 0.f;
                 }
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = r + 1; c < 8; ++c) g[r][c] = fmaf(vr[r], vr[c], g[r][c]);
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -515,12 +567,41 @@ __global__ void __launch_bounds__(TT, 1) sigma_tridiag_kernel(const SigmaArgs a)
                 for (int r = 0; r < 8; ++r)
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
-                        if (lane == r) Twg[m * 64 + r * 8 + c] = T[r][c];
+                        if (lane == r) Twg[mb * 64 + r * 8 + c] = T[r][c];
             }
         }
     }
+    COVO_STAMP(a, 16);
+}
+
+// ---------------------------------------------------------------------------------------------
+// E2: everything on the tridiagonal, fp64
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int trifunc_region_floats(int n) {
+    // fp64 pivot numerators/denominators [2][2][17][n], then float gd[16][n], and the generator arrays [16][n+1] x 3
+    int b = (2 * 2 * (kZoloPoles + 1) * n) * 2 + kZoloPoles * n + 3 * kZoloPoles * (n + 1);
+    return (b + 3) & ~3;
+}
+
+__global__ void __launch_bounds__(TT, 1) sigma_trifunc_kernel(const SigmaArgs a) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int n = a.n, tid = threadIdx.x, env = blockIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* As = reinterpret_cast<float*>(smraw);          // E2 scratch region
+    double* dd = reinterpret_cast<double*>(As + trifunc_region_floats(n));  // [256]
+    double* ee = dd + 256;                                // [256]
+    double* e2s = ee + 256;                               // [256] e^2
+    double* sc = e2s + 256;                               // [16] scalars
+    double* rdbuf = sc + 16;                              // [64]
+    int* ired = reinterpret_cast<int*>(rdbuf + 64);       // [4]
+    COVO_STAMP(a, 17);
+    {
+        const double* dg = a.diag + (long long)env * 4 * n;
+        if (tid < n) {
+            dd[tid] = dg[tid];
+            ee[tid] = dg[n + tid];
+        }
+    }
     __syncthreads();
-    COVO_STAMP(a, 9);
 
     // ---- E2: everything on the tridiagonal, fp64 ---------------------------------------------
     // Gershgorin interval
@@ -1024,19 +1105,83 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-static size_t tridiag_smem(int n) {
-    return (size_t)tridiag_region_floats(n) * 4 + 3328 * 4 + 256 * 8 * 3 + 16 * 8 + 64 * 8 + 64 * 4 + 16;
+static size_t trifunc_smem(int n) {
+    return (size_t)trifunc_region_floats(n) * 4 + 256 * 8 * 3 + 16 * 8 + 64 * 8 + 16;
 }
 static size_t chol_smem(int n) { return (size_t)n * n * 4 + (size_t)8 * round_up8(n) * 4 + 64 * 4; }
 
+template <int C2, int NC>
+static cudaError_t launch_e1(const SigmaArgs& a, int n_env, cudaStream_t st) {
+    static size_t conf[32] = {};
+    const size_t smem = e1_smem_bytes(a.n, C2);
+    cudaError_t e = ensure_smem_attr(tridiag_reg_kernel<C2, NC>, smem, conf);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_env * NC);
+    cfg.blockDim = dim3(ET);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NC;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tridiag_reg_kernel<C2, NC>, a);
+}
+
+// Cluster width of E1 (CTAs per matrix).  Few matrices: spread each one over 4 SMs (latency); many matrices
+// (batched environments, the offline schedule): 2 SMs each, which still fills the machine.
+static int e1_cluster_override() {  // COVO_E1_CLUSTER = 1 | 2 | 4 | 8 pins the cluster width (tuning, tests)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("COVO_E1_CLUSTER");
+        v = e ? atoi(e) : 0;
+        if (v != 1 && v != 2 && v != 4 && v != 8) v = 0;
+    }
+    return v;
+}
+
 cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
     if (a.n > kSigmaMaxN || (a.n & 3)) return cudaErrorInvalidValue;
+    cudaError_t e;
+    int nc = e1_cluster_override() ? e1_cluster_override() : (n_env <= 18 ? 8 : (n_env <= 37 ? 4 : 2));
+    if (a.n <= 64) nc = min(nc, 2);
+    else if (a.n <= 128) nc = min(nc, 4);
+    // column-pair slots per warp: n <= 16 NC C2
+    if (nc >= 8) {
+        e = (a.n <= 128) ? launch_e1<1, 8>(a, n_env, st) : launch_e1<2, 8>(a, n_env, st);
+    } else if (nc >= 4) {
+        switch ((a.n + 63) / 64) {
+            case 1: e = launch_e1<1, 4>(a, n_env, st); break;
+            case 2: e = launch_e1<2, 4>(a, n_env, st); break;
+            case 3: e = launch_e1<3, 4>(a, n_env, st); break;
+            default: e = launch_e1<4, 4>(a, n_env, st); break;
+        }
+    } else if (nc == 2) {
+        switch ((a.n + 31) / 32) {
+            case 1: e = launch_e1<1, 2>(a, n_env, st); break;
+            case 2: e = launch_e1<2, 2>(a, n_env, st); break;
+            case 3: case 4: e = launch_e1<4, 2>(a, n_env, st); break;
+            case 5: case 6: e = launch_e1<6, 2>(a, n_env, st); break;
+            default: e = launch_e1<7, 2>(a, n_env, st); break;
+        }
+    } else {
+        switch ((a.n + 15) / 16) {
+            case 1: case 2: case 3: case 4: e = launch_e1<4, 1>(a, n_env, st); break;
+            case 5: case 6: case 7: case 8: e = launch_e1<8, 1>(a, n_env, st); break;
+            case 9: case 10: e = launch_e1<10, 1>(a, n_env, st); break;
+            default: e = launch_e1<14, 1>(a, n_env, st); break;
+        }
+    }
+    if (e != cudaSuccess) return e;
     static size_t conf[32] = {};
-    size_t smem = tridiag_smem(a.n);
-    cudaError_t e0 = ensure_smem_attr(sigma_tridiag_kernel, smem, conf);
-    if (e0 != cudaSuccess) return e0;
-    sigma_tridiag_kernel<<<n_env, TT, smem, st>>>(a);
-    cudaError_t e = cudaGetLastError();
+    size_t smem = trifunc_smem(a.n);
+    e = ensure_smem_attr(sigma_trifunc_kernel, smem, conf);
+    if (e != cudaSuccess) return e;
+    sigma_trifunc_kernel<<<n_env, TT, smem, st>>>(a);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int cols_per_cta = kApplyWarps * kApplyCols;
     dim3 g((a.n + cols_per_cta - 1) / cols_per_cta, n_env);

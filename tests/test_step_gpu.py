@@ -176,12 +176,17 @@ def test_batched_environments_match_single():
 
 
 def test_headline_config_closed_loop_cost():
-    """BASELINE config 3 (CoVO-online, tracking_zigzag, N=8192, H=50): closed loops of the device controller and of
-    the oracle on identical eps.  While both pick the same arg-min sample (ESS ~ 1) the accumulated
-    tracking cost must agree within 1e-4 relative (north star) and every action within 5e-4.  If the actions ever
-    differ, the oracle's own two best samples must be within a few lambda of each other (the softmax
-    with lambda = 0.01 amplifies 1e-4-level cost differences there); the comparison stops at that step because two
-    float32 closed loops legitimately decorrelate after it."""
+    """BASELINE config 3 (CoVO-online, tracking_zigzag, N=8192, H=50), closed loop on identical eps.
+
+    The loop is chaotic in float32: Sigma = (R - lam_min + 1e-2)^(-1/2) has condition ~1e5 (||R|| ~ 2e3 after the
+    first steps), so a 1e-6 difference in the carried mean grows ~10x per MPC step through the Hessian (measured:
+    covariance distance 1.5e-6 -> 2.9e-5 -> 4.7e-4 -> 4.8e-3 between two float32 implementations, LAPACK's ssytrd
+    included).  The parity statement is therefore split the way SURVEY 7.3 (T1/T3) prescribes:
+      (a) PER STEP, teacher-forced: the oracle is evaluated on the device loop's own inputs (same noisy state, same
+          carried mean, same eps); the device action must agree within 5e-4 and the updated mean within 2e-3, unless
+          the oracle's two best samples are within 3 lambda of each other (the softmax is an arg-min, SURVEY fact 4);
+      (b) FREE-RUNNING: the oracle's own closed loop; while its actions stay within 5e-4 of the device's, the
+          accumulated tracking cost must agree within 1e-4 relative (north star) -- at least 3 steps."""
     import covo_mpc_b200 as cm
 
     N, H, steps = 8192, 50, 6
@@ -191,28 +196,36 @@ def test_headline_config_closed_loop_cost():
     s_ora = s_dev.copy()
     env = cm.Quad3D("tracking_zigzag")
     ctl, cp = cm.get_controller(env, "covo-online", f"N{N}_H{H}_lam0.01")
-    mean_o = o.hover_mean(H, p)
+    mean_dev = o.hover_mean(H, p)  # the mean carried by the device loop (host copy)
+    mean_o = o.hover_mean(H, p)    # the mean carried by the free-running oracle loop
     cost_dev = cost_ora = 0.0
-    agreed = 0
+    agreed, free_running = 0, True
     for i in range(steps):
         ns_dev = o.noisy_state(s_dev, p, np.random.default_rng(1000 + i))
-        ns_ora = o.noisy_state(s_ora, p, np.random.default_rng(1000 + i))
         eps = np.random.default_rng(2000 + i).standard_normal((N, 4 * H)).astype(np.float32)
         st = _to_env_state(cm, ns_dev)
         a_dev, cp, _ = ctl(None, st, env.default_params, eps, cp, {"noisy_state": st})
-        a_ora, mean_o, _, _, dbg = o.covo_call(ns_ora, mean_o, eps, p, lam=0.01, return_debug=True)
-        if np.abs(a_dev - a_ora).max() >= 5e-4:
-            c = np.sort(dbg["cost"].astype(np.float64))
-            gap = (c[1] - c[0]) / 0.01  # in units of lambda: the runner-up's log-weight deficit
-            # with lambda = 0.01 a cost perturbation of 1e-4 relative (~2e-3 absolute = 0.2 lambda, the size two
-            # float32 closed loops accumulate) re-weights any runner-up that sits within a few lambda of the winner
-            assert gap < 3.0, f"step {i}: actions differ but the oracle's top-2 gap is {gap:.3f} lambda"
-            break
-        agreed += 1
+        # (a) teacher-forced oracle on the device loop's inputs
+        a_tf, mean_tf, _, _, dbg = o.covo_call(ns_dev, mean_dev, eps, p, lam=0.01, return_debug=True)
+        c = np.sort(dbg["cost"].astype(np.float64))
+        gap = (c[1] - c[0]) / 0.01  # in units of lambda: the runner-up's log-weight deficit
+        mean_dev = np.asarray(cp.a_mean).reshape(H, 4).copy()
+        if gap >= 3.0:
+            assert np.abs(a_dev - a_tf).max() < 5e-4, f"step {i}: action differs from the teacher-forced oracle (gap {gap:.1f} lambda)"
+            assert np.abs(mean_dev - mean_tf).max() < 2e-3, f"step {i}: mean differs from the teacher-forced oracle"
+        # (b) free-running oracle loop
+        if free_running:
+            ns_ora = o.noisy_state(s_ora, p, np.random.default_rng(1000 + i))
+            a_ora, mean_o, _, _ = o.covo_call(ns_ora, mean_o, eps, p, lam=0.01)
+            if np.abs(a_dev - a_ora).max() >= 5e-4:
+                free_running = False  # the two float32 closed loops have decorrelated: stop accumulating
+            else:
+                agreed += 1
+                s_ora, r_ora, _, _ = o.env_step(s_ora, a_ora, p, rng, "none")
+                cost_ora -= r_ora
         s_dev, r_dev, _, _ = o.env_step(s_dev, a_dev, p, rng, "none")
-        s_ora, r_ora, _, _ = o.env_step(s_ora, a_ora, p, rng, "none")
-        cost_dev -= r_dev
-        cost_ora -= r_ora
+        if free_running:
+            cost_dev -= r_dev
     assert agreed >= 3
     assert abs(cost_dev - cost_ora) <= 1e-4 * abs(cost_ora)
 
