@@ -105,11 +105,11 @@ struct covo_handle {
     DevBuf<float> state24, pos_traj, vel_traj, acc_traj, a_mean, eps, fdist;
     DevBuf<int> time;
     // covariance pipeline
-    DevBuf<float> R, Vh, tau, Tw, sched_Tw, F, Z, cov, Lfull, Lt, Lblk, hess_ws;
+    DevBuf<float> R, Qt, F, cov, Lfull, Lt, Lblk, hess_ws;
     DevBuf<double> diag, zolo;
     DevBuf<int> status;
     // offline schedule (batched over schedule steps)
-    DevBuf<float> cov_table, Lt_table, sched_states, sched_anom, sched_R, sched_Vh, sched_tau, sched_F, sched_Z, sched_ws;
+    DevBuf<float> cov_table, Lt_table, sched_states, sched_anom, sched_R, sched_Qt, sched_F, sched_ws;
     DevBuf<double> sched_diag;
     DevBuf<int> sched_times, sched_status;
     // rollout
@@ -135,11 +135,11 @@ namespace {
 void release_all(covo_handle* h) {
     h->state24.release(); h->pos_traj.release(); h->vel_traj.release(); h->acc_traj.release();
     h->a_mean.release(); h->eps.release(); h->fdist.release(); h->time.release();
-    h->R.release(); h->Vh.release(); h->tau.release(); h->Tw.release(); h->sched_Tw.release(); h->F.release(); h->Z.release(); h->cov.release();
+    h->R.release(); h->Qt.release(); h->F.release(); h->cov.release();
     h->Lfull.release(); h->Lt.release(); h->Lblk.release(); h->hess_ws.release(); h->diag.release();
     h->zolo.release(); h->status.release();
     h->cov_table.release(); h->Lt_table.release(); h->sched_states.release(); h->sched_anom.release();
-    h->sched_R.release(); h->sched_Vh.release(); h->sched_tau.release(); h->sched_F.release(); h->sched_Z.release();
+    h->sched_R.release(); h->sched_Qt.release(); h->sched_F.release();
     h->sched_ws.release(); h->sched_diag.release(); h->sched_times.release(); h->sched_status.release();
     h->partials.release(); h->rank_partial.release(); h->action.release(); h->costs.release();
     h->prof.release(); h->samples.release(); h->pos_stats.release(); h->gathered_scratch.release(); h->counters.release();
@@ -176,11 +176,8 @@ SigmaArgs sigma_args(covo_handle* h) {
     a.n_pad = h->n_pad;
     a.sample_sigma = h->cfg.sample_sigma;
     a.R = h->R.p;
-    a.Vh = h->Vh.p;
-    a.tau = h->tau.p;
-    a.Tw = h->Tw.p;
+    a.Qt = h->Qt.p;
     a.F = h->F.p;
-    a.Z = h->Z.p;
     a.cov = h->cov.p;
     a.L = h->Lfull.p;
     a.Lt = h->Lt.p;
@@ -409,11 +406,8 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
         A(h->cov.alloc(E * h->H * 16));
     } else {
         A(h->R.alloc(E * nn));
-        A(h->Vh.alloc(E * nn));
-        A(h->tau.alloc(E * n));
-        A(h->Tw.alloc(E * (n / kWyBlock + 1) * 64));
+        A(h->Qt.alloc(E * nn));
         A(h->F.alloc(E * nn));
-        A(h->Z.alloc(E * nn));
         A(h->cov.alloc(E * nn));
         A(h->Lfull.alloc(E * nn));
         A(h->Lt.alloc(E * h->lt_floats));
@@ -552,18 +546,14 @@ static int alloc_schedule(covo_handle* h, int t_sched, bool full) {
     }
     if (full && (int)(h->sched_R.n / nn) < t_sched) {
         h->sched_states.release(); h->sched_times.release(); h->sched_anom.release(); h->sched_R.release();
-        h->sched_Vh.release(); h->sched_tau.release(); h->sched_F.release(); h->sched_Z.release();
+        h->sched_Qt.release(); h->sched_F.release();
         h->sched_ws.release(); h->sched_diag.release();
         CK(h->sched_states.alloc(S * kStateFloats));
         CK(h->sched_times.alloc(S));
         CK(h->sched_anom.alloc(S * h->n));
         CK(h->sched_R.alloc(S * nn));
-        CK(h->sched_Vh.alloc(S * nn));
-        CK(h->sched_tau.alloc(S * h->n));
-        h->sched_Tw.release();
-        CK(h->sched_Tw.alloc(S * (h->n / kWyBlock + 1) * 64));
+        CK(h->sched_Qt.alloc(S * nn));
         CK(h->sched_F.alloc(S * nn));
-        CK(h->sched_Z.alloc(S * nn));
         CK(h->sched_ws.alloc(S * hessian_workspace_floats(h->H)));
         CK(h->sched_diag.alloc(S * 4 * h->n));
     }
@@ -573,11 +563,8 @@ static int alloc_schedule(covo_handle* h, int t_sched, bool full) {
 static SigmaArgs sched_sigma_args(covo_handle* h) {
     SigmaArgs a = sigma_args(h);
     a.R = h->sched_R.p;
-    a.Vh = h->sched_Vh.p;
-    a.tau = h->sched_tau.p;
-    a.Tw = h->sched_Tw.p;
+    a.Qt = h->sched_Qt.p;
     a.F = h->sched_F.p;
-    a.Z = h->sched_Z.p;
     a.cov = h->cov_table.p;
     a.L = nullptr;
     a.Lt = h->Lt_table.p;

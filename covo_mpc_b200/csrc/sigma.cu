@@ -188,9 +188,9 @@ constexpr int ET = EW * 32;   // threads per CTA
 constexpr int RS = kSigmaMaxN / 32;  // row slots per lane (7)
 constexpr int kTilePitch = 36;       // floats; rows of the transposition tile are float4-aligned and conflict-free
 
-__host__ __device__ inline size_t e1_smem_bytes(int n, int c2) {
-    // reflector store Vs [n][n]; q[2][256], v[2][256], row[2][256], tau[256], d[256], e[256]; transposition tiles
-    return ((size_t)n * n + 256 * 9 + EW * 2 * c2 * kTilePitch + 4 + EW * 64) * sizeof(float);  // + mbarrier pair, scratch
+__host__ __device__ inline size_t e1_smem_bytes(int c2) {
+    // q[2][256], v[2][256], row[2][256], d[256], e[256]; transposition tiles; mbarrier pair; reduction scratch
+    return ((size_t)256 * 8 + EW * 2 * c2 * kTilePitch + 4 + EW * 64) * sizeof(float);
 }
 
 __device__ __forceinline__ void cluster_barrier() {
@@ -269,22 +269,19 @@ __global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
     const int gw = rank * EW + warp;        // global warp: owns columns 2 gw + CS c, 2 gw + CS c + 1
     constexpr int GW = EW * NC;             // warps of the cluster
     constexpr int CS = 2 * GW;              // column stride between pair slots
-    float* Vs = esm;                    // [n][n] reflectors (row k = v_k)
-    float* qsm0 = esm + n * n;          // [2][256]
+    float* qsm0 = esm;                  // [2][256]
     float* vsm0 = qsm0 + 512;           // [2][256]
     float* row0 = vsm0 + 512;           // [2][256]
-    float* taus = row0 + 512;           // [256]
-    float* dsm = taus + 256;            // [256]
+    float* dsm = row0 + 512;            // [256]
     float* esm_e = dsm + 256;           // [256]
     float* tile = esm_e + 256 + warp * 2 * C2 * kTilePitch;  // [2 C2][36] private transposition tile
     unsigned long long* mbars = reinterpret_cast<unsigned long long*>(esm_e + 256 + EW * 2 * C2 * kTilePitch);  // [2]
     float* red = esm_e + 256 + EW * 2 * C2 * kTilePitch + 4 + warp * 64;  // [2][32] private reduction scratch
 
     const float* Rg = a.R + (long long)env * n * n;
-    float* Vg = a.Vh + (long long)env * n * n;
-    float* taug = a.tau + (long long)env * n;
+    float* Qg = a.Qt + (long long)env * n * n;
     COVO_STAMP(a, 8);
-    for (int i = tid; i < 256 * 9; i += ET) qsm0[i] = 0.f;
+    for (int i = tid; i < 256 * 8; i += ET) qsm0[i] = 0.f;
     const unsigned mbar_local = (unsigned)__cvta_generic_to_shared(mbars);
     if (tid == 0) {
         mbar_init(mbar_local, 1);
@@ -306,6 +303,18 @@ __global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
                 x.y = 0.5f * (rowv.y + Rg[(long long)(j0 + 1) * n + i]);
             }
             A2[r][c] = x;
+        }
+    }
+    // P = Q^T = H_{m} ... H_0, accumulated next to A in the same layout (rows over the lanes, own column pairs):
+    // P <- H_m P = P - tau v (v^T P) needs, per column, a dot product over the rows, i.e. inside ONE warp.
+    float2 P2[RS][C2];
+#pragma unroll
+    for (int c = 0; c < C2; ++c) {
+        const int j0 = 2 * gw + CS * c;
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            const int i = lane + 32 * r;
+            P2[r][c] = make_float2(i == j0 ? 1.f : 0.f, i == j0 + 1 ? 1.f : 0.f);
         }
     }
     // shared::cluster addresses of the exchange buffers and of the mbarrier pair in every CTA of the cluster
@@ -465,21 +474,44 @@ __global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
 #pragma unroll
             for (int r = 0; r < RS; ++r) {
                 const int i = lane + 32 * r;
-                if (i < n) {
-                    vsm0[pn + i] = vi[r];
-                    Vs[m * n + i] = vi[r];
-                }
+                if (i < n) vsm0[pn + i] = vi[r];
             }
             if (lane == 0) {
                 dsm[m] = dm;
                 esm_e[m] = nbeta;
-                taus[m] = ntau;
             }
             __syncwarp();
             // this step's incoming traffic: column m+1 (7 x 32 floats) and, if the matvec runs, the n entries of q
             if (lane == 0) mbar_expect_tx(mbar_local + bar_off, ((m + 1 < n) ? 4u * 32u * RS : 0u) + (do_matvec ? 4u * n : 0u));
         }
         PH(2);
+        // ---- 4. P <- H_m P, in the shadow of the exchange latency -----------------------------------------
+        if (tau != 0.f) {
+            float2 z[C2];
+#pragma unroll
+            for (int c = 0; c < C2; ++c) {
+                float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int r = 0; r < RS; r += 2) sa = __ffma2_rn(P2[r][c], make_float2(vi[r], vi[r]), sa);
+#pragma unroll
+                for (int r = 1; r < RS; r += 2) sb = __ffma2_rn(P2[r][c], make_float2(vi[r], vi[r]), sb);
+                z[c] = __fadd2_rn(sa, sb);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int c = 0; c < C2; ++c) {
+                    z[c].x += __shfl_xor_sync(0xffffffffu, z[c].x, o);
+                    z[c].y += __shfl_xor_sync(0xffffffffu, z[c].y, o);
+                }
+#pragma unroll
+            for (int c = 0; c < C2; ++c)
+#pragma unroll
+                for (int r = 0; r < RS; ++r) {
+                    const float tv = -tau * vi[r];
+                    P2[r][c] = __ffma2_rn(make_float2(tv, tv), z[c], P2[r][c]);
+                }
+        }
         // everything this CTA reads in step m+1 has landed when its mbarrier phase completes
         mbar_wait(mbar_local + bar_off, (m >> 1) & 1);
         PH(3);
@@ -490,85 +522,19 @@ __global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
     __syncthreads();
     if (NC > 1) cluster_barrier();  // nobody leaves while a peer could still be sending to it
     COVO_STAMP(a, 9);
-    // every CTA holds the complete result (d, e, tau, reflectors): the write-out is split over the ranks.
-    // d, e -> HBM for the E2 kernel; reflectors (row k = v_k, zero-extended) and tau for apply-Q
-    if (rank == 0) {
+    // d, e -> HBM for the E2 kernel (every CTA holds them; rank 0 writes); Q^T from the registers of all warps
+    if (rank == 0 && tid < n) {
         double* dg = a.diag + (long long)env * 4 * n;
-        if (tid < n) {
-            dg[tid] = (double)dsm[tid];
-            dg[n + tid] = (tid < n - 1) ? (double)esm_e[tid] : 0.0;
-            taug[tid] = (tid < n - 2) ? taus[tid] : 0.f;
-        }
+        dg[tid] = (double)dsm[tid];
+        dg[n + tid] = (tid < n - 1) ? (double)esm_e[tid] : 0.0;
     }
-    if (tid >= n - 2 && tid < n) taus[tid] = 0.f;
-    for (int idx = rank * ET + tid; idx < n * n; idx += ET * NC) {
-        const int k2 = idx / n;
-        Vg[idx] = (k2 < n - 2) ? Vs[idx] : 0.f;
-    }
-    __syncthreads();
-    // Compact-WY factors for apply-Q: block m holds reflectors k = k_hi-7 .. k_hi, k_hi = n-3-8m (ascending local
-    // index r <-> k = k_hi-7+r; missing ones have tau = 0).  H_{k_lo} ... H_{k_hi} = I - V T V^T, T upper triangular
-    // (LAPACK slarft, forward / columnwise): T[i][i] = tau_i, T[0:i, i] = -tau_i T[0:i,0:i] (V[:,0:i]^T v_i).
-    {
-        const int nblk = (n - 2 + kWyBlock - 1) / kWyBlock;
-        float* Twg = a.Tw + (long long)env * (n / kWyBlock + 1) * 64;
-        for (int mb = gw; mb < nblk; mb += EW * NC) {
-            const int khi = n - 3 - kWyBlock * mb;
-            float g[8][8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+    for (int c = 0; c < C2; ++c) {
+        const int j0 = 2 * gw + CS * c;
 #pragma unroll
-                for (int c = r + 1; c < 8; ++c) g[r][c] = 0.f;
-            // Gram entries g[r][c] = v_r . v_c for r < c, accumulated slot by slot (keeps the register count low)
-#pragma unroll
-            for (int li = 0; li < RS; ++li) {
-                const int i = lane + 32 * li;
-                float vr[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int k = khi - 7 + r;
-                    vr[r] = (k >= 0 && i < n) ? Vs[k * n + i] : 0.f;
-                }
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-#pragma unroll
-                    for (int c = r + 1; c < 8; ++c) g[r][c] = fmaf(vr[r], vr[c], g[r][c]);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-#pragma unroll
-                    for (int c = r + 1; c < 8; ++c) g[r][c] += __shfl_xor_sync(0xffffffffu, g[r][c], o);
-            float tauk[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int k = khi - 7 + r;
-                tauk[r] = (k >= 0) ? taus[k] : 0.f;
-            }
-            float T[8][8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int c = 0; c < 8; ++c) T[r][c] = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                T[i][i] = tauk[i];
-#pragma unroll
-                for (int r = 0; r < i; ++r) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int c = r; c < i; ++c) acc = fmaf(T[r][c], g[c][i], acc);
-                    T[r][i] = -tauk[i] * acc;
-                }
-            }
-            if (lane < 8) {
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (lane == r) Twg[mb * 64 + r * 8 + c] = T[r][c];
-            }
+        for (int r = 0; r < RS; ++r) {
+            const int i = lane + 32 * r;
+            if (i < n && j0 < n) *reinterpret_cast<float2*>(Qg + (long long)i * n + j0) = P2[r][c];
         }
     }
     COVO_STAMP(a, 16);
@@ -791,6 +757,7 @@ __global__ void __launch_bounds__(TT, 1) sigma_trifunc_kernel(const SigmaArgs a)
 #pragma unroll
                 for (int q = 0; q < NPOLE; ++q) f += val[q];
                 Fg[(long long)i * n + l] = f;
+                Fg[(long long)l * n + i] = f;  // full symmetric storage (the sandwich kernel reads F by columns)
                 if (l + 32 < n) {
 #pragma unroll
                     for (int q = 0; q < NPOLE; ++q) val[q] *= p32[q * n + l];
@@ -816,15 +783,11 @@ __global__ void __launch_bounds__(TT, 1) sigma_trifunc_kernel(const SigmaArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-// E3: out(:, c) = Q in(c, :)^T;  Q = H_0 H_1 ... H_{n-3}.  One warp owns two vectors (their elements spread
-// over the lanes, 7 registers each); the reflectors stream through shared memory in chunks of 32 rows with a
-// two-stage cp.async pipeline, so the serial chain per reflector is dot -> 5 shuffles -> axpy and nothing waits
-// on global memory.
+// E3: Sigma = Q F Q^T = P^T F P with P = Q^T from E1 and the symmetric F from E2: one launch, grid of 32 x 16
+// output tiles.  Each CTA first forms Z = F P[:, J] (n x 16, kept in shared memory; recomputed by the CTAs
+// that share J -- 0.6 MFLOP, cheaper than a second launch), then Sigma[I, J] = P[:, I]^T Z.
 // ---------------------------------------------------------------------------------------------
-constexpr int kApplyWarps = 4;
-constexpr int kApplyCols = 1;                 // vectors per warp (the instruction stream per warp is the critical path)
-constexpr int kApplyChunk = 32;               // reflectors per pipeline stage
-constexpr int kMaxLi = kSigmaMaxN / 32;       // 7
+constexpr int kSwI = 32, kSwJ = 16, kSwThreads = 256, kSwChunk = 32;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -836,130 +799,104 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <bool STORE_STRIDED, bool UPPER_ONLY>
-__global__ void __launch_bounds__(kApplyWarps * 32) applyq_kernel(const float* __restrict__ Vh,
-                                                                 const float* __restrict__ Tw,
-                                                                 const float* __restrict__ in, float* __restrict__ out,
-                                                                 int n) {
-    extern __shared__ __align__(16) float sv[];  // [2][kApplyChunk][n] reflectors, then [2][4][64] T factors
-    const int env = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c0 = (blockIdx.x * kApplyWarps + warp) * kApplyCols;
-    Vh += (long long)env * n * n;
-    Tw += (long long)env * (n / kWyBlock + 1) * 64;
-    in += (long long)env * n * n;
-    out += (long long)env * n * n;
-    float* sT = sv + 2 * kApplyChunk * n;
-    float x[kApplyCols][kMaxLi];
-#pragma unroll
-    for (int j = 0; j < kApplyCols; ++j)
-#pragma unroll
-        for (int li = 0; li < kMaxLi; ++li) {
-            int i = lane + 32 * li;
-            float xv = 0.f;
-            if (i < n && c0 + j < n) {
-                const int cc = c0 + j;
-                // `in` is symmetric; when only its upper triangle is stored (F), read (min, max)
-                xv = UPPER_ONLY ? in[(long long)min(cc, i) * n + max(cc, i)] : in[(long long)cc * n + i];
-            }
-            x[j][li] = xv;
-        }
-    const int nref = n - 2;                                   // reflectors k = 0 .. n-3, applied in descending k
-    const int nchunks = (nref + kApplyChunk - 1) / kApplyChunk;
-    const int vec_per_row = n >> 2;
-    auto prefetch = [&](int j) {
-        // chunk j holds k = kh, kh-1, ..., kl  (kh = n-3 - j*chunk); slot s <-> k = kh - s.  Its 4 WY blocks are
-        // the blocks m = 4j .. 4j+3 of the T table.
-        const int kh = n - 3 - j * kApplyChunk;
-        const int cnt = min(kApplyChunk, kh + 1);
-        float* dst = sv + (j & 1) * kApplyChunk * n;
-        for (int idx = tid; idx < cnt * vec_per_row; idx += kApplyWarps * 32) {
-            int s = idx / vec_per_row, v4 = idx - s * vec_per_row;
-            cp_async16(dst + s * n + 4 * v4, Vh + (long long)(kh - s) * n + 4 * v4);
-        }
-        const int nblk = (cnt + kWyBlock - 1) / kWyBlock;
-        for (int idx = tid; idx < nblk * 16; idx += kApplyWarps * 32)
-            cp_async16(sT + (j & 1) * 256 + idx * 4, Tw + (long long)(4 * j) * 64 + idx * 4);
+__host__ __device__ inline size_t sandwich_smem_bytes(int n) {
+    return (size_t)n * (2 * kSwJ + kSwI + 2 * kSwChunk) * sizeof(float);
+}
+
+__global__ void __launch_bounds__(kSwThreads) sandwich_kernel(const float* __restrict__ Qt, const float* __restrict__ F,
+                                                             float* __restrict__ cov, int n) {
+    extern __shared__ __align__(16) float ssm[];
+    float* Pj = ssm;                 // [n][16]  P[:, J]
+    float* Zs = Pj + n * kSwJ;       // [n][16]  Z = F P[:, J]
+    float* Pi = Zs + n * kSwJ;       // [n][32]  P[:, I]
+    float* Fs = Pi + n * kSwI;       // [2][32][n]  row chunks of F, double-buffered (cp.async)
+    const int env = blockIdx.z, tid = threadIdx.x;
+    const int I0 = blockIdx.x * kSwI, J0 = blockIdx.y * kSwJ;
+    Qt += (long long)env * n * n;
+    F += (long long)env * n * n;
+    cov += (long long)env * n * n;
+    const int nv4 = n >> 2;
+    auto prefetch_F = [&](int c) {
+        const int l0 = c * kSwChunk, rows = min(kSwChunk, n - l0);
+        float* dst = Fs + (c & 1) * kSwChunk * n;
+        for (int idx = tid; idx < rows * nv4; idx += kSwThreads) cp_async16(dst + 4 * idx, F + (long long)l0 * n + 4 * idx);
         cp_async_commit();
     };
-    prefetch(0);
-    for (int j = 0; j < nchunks; ++j) {
-        if (j + 1 < nchunks) {
-            prefetch(j + 1);
+    // P[:, J] and P[:, I] (16-byte pieces; pieces beyond column n are zero-filled)
+    for (int idx = tid; idx < n * (kSwJ / 4); idx += kSwThreads) {
+        const int l = idx >> 2, q4 = idx & 3;
+        if (J0 + 4 * q4 < n) cp_async16(Pj + l * kSwJ + 4 * q4, Qt + (long long)l * n + J0 + 4 * q4);
+        else *reinterpret_cast<float4*>(Pj + l * kSwJ + 4 * q4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int idx = tid; idx < n * (kSwI / 4); idx += kSwThreads) {
+        const int l = idx >> 3, q4 = idx & 7;
+        if (I0 + 4 * q4 < n) cp_async16(Pi + l * kSwI + 4 * q4, Qt + (long long)l * n + I0 + 4 * q4);
+        else *reinterpret_cast<float4*>(Pi + l * kSwI + 4 * q4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    prefetch_F(0);
+    // Z[k][:] for k = tid: F is symmetric, so column k is read as F[l][k] -- consecutive k, conflict-free
+    float acc[kSwJ];
+#pragma unroll
+    for (int jj = 0; jj < kSwJ; ++jj) acc[jj] = 0.f;
+    const int nch = (n + kSwChunk - 1) / kSwChunk;
+    for (int c = 0; c < nch; ++c) {
+        if (c + 1 < nch) {
+            prefetch_F(c + 1);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncthreads();
-        const int kh = n - 3 - j * kApplyChunk;
-        const int cnt = min(kApplyChunk, kh + 1);
-        const float* buf = sv + (j & 1) * kApplyChunk * n;
-        const int nblk = (cnt + kWyBlock - 1) / kWyBlock;
-        for (int q = 0; q < nblk; ++q) {
-            // block q: slots 8q .. 8q+7 (descending k); ascending local index r <-> slot 8q + 7 - r
-            const float* Tb = sT + (j & 1) * 256 + q * 64;
-            // y = V^T x  (slots past the end of the chunk hold stale data but their T rows/cols are zero: tau = 0)
-            float y[kApplyCols][8];
+        if (tid < n) {
+            const int l0 = c * kSwChunk, rows = min(kSwChunk, n - l0);
+            const float* fb = Fs + (c & 1) * kSwChunk * n + tid;
+#pragma unroll 4
+            for (int l = 0; l < rows; ++l) {
+                const float f = fb[l * n];
+                const float4* pr = reinterpret_cast<const float4*>(Pj + (l0 + l) * kSwJ);
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int s = 8 * q + 7 - r;
-                float v[kMaxLi];
-#pragma unroll
-                for (int li = 0; li < kMaxLi; ++li) {
-                    int i = lane + 32 * li;
-                    v[li] = (i < n && s < cnt) ? buf[s * n + i] : 0.f;
-                }
-#pragma unroll
-                for (int jj = 0; jj < kApplyCols; ++jj) {
-                    float d = 0.f;
-#pragma unroll
-                    for (int li = 0; li < kMaxLi; ++li) d = fmaf(v[li], x[jj][li], d);
-                    y[jj][r] = d;
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int jj = 0; jj < kApplyCols; ++jj)
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) y[jj][r] += __shfl_xor_sync(0xffffffffu, y[jj][r], o);
-            // z = T y (upper triangular), then x -= V z
-            float z[kApplyCols][8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-#pragma unroll
-                for (int jj = 0; jj < kApplyCols; ++jj) z[jj][r] = 0.f;
-#pragma unroll
-                for (int c = r; c < 8; ++c) {
-                    const float t = Tb[r * 8 + c];
-#pragma unroll
-                    for (int jj = 0; jj < kApplyCols; ++jj) z[jj][r] = fmaf(t, y[jj][c], z[jj][r]);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int s = 8 * q + 7 - r;
-#pragma unroll
-                for (int li = 0; li < kMaxLi; ++li) {
-                    int i = lane + 32 * li;
-                    const float v = (i < n && s < cnt) ? buf[s * n + i] : 0.f;
-#pragma unroll
-                    for (int jj = 0; jj < kApplyCols; ++jj) x[jj][li] = fmaf(-z[jj][r], v, x[jj][li]);
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 pv = pr[q4];
+                    acc[4 * q4 + 0] = fmaf(f, pv.x, acc[4 * q4 + 0]);
+                    acc[4 * q4 + 1] = fmaf(f, pv.y, acc[4 * q4 + 1]);
+                    acc[4 * q4 + 2] = fmaf(f, pv.z, acc[4 * q4 + 2]);
+                    acc[4 * q4 + 3] = fmaf(f, pv.w, acc[4 * q4 + 3]);
                 }
             }
         }
-        __syncthreads();  // the buffer is recycled two chunks later
+        __syncthreads();  // the buffer is refilled two chunks later
     }
+    if (tid < n) {
 #pragma unroll
-    for (int jj = 0; jj < kApplyCols; ++jj)
-#pragma unroll
-        for (int li = 0; li < kMaxLi; ++li) {
-            int i = lane + 32 * li;
-            if (i < n && c0 + jj < n) {
-                if (STORE_STRIDED) out[(long long)i * n + (c0 + jj)] = x[jj][li];
-                else out[(long long)(c0 + jj) * n + i] = x[jj][li];
-            }
+        for (int q4 = 0; q4 < 4; ++q4)
+            reinterpret_cast<float4*>(Zs + tid * kSwJ)[q4] = make_float4(acc[4 * q4], acc[4 * q4 + 1], acc[4 * q4 + 2], acc[4 * q4 + 3]);
+    }
+    __syncthreads();
+    // Sigma[I0 + ii][J0 + jj .. +1] = sum_k P[k][I0 + ii] Z[k][jj]: thread = (ii, pair of jj)
+    {
+        const int ii = tid & 31, jp = tid >> 5;  // jp = 0..7 -> columns 2 jp, 2 jp + 1
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+        int k = 0;
+        for (; k + 1 < n; k += 2) {
+            const float p0 = Pi[k * kSwI + ii], p1 = Pi[(k + 1) * kSwI + ii];
+            const float2 z0 = *reinterpret_cast<const float2*>(Zs + k * kSwJ + 2 * jp);
+            const float2 z1 = *reinterpret_cast<const float2*>(Zs + (k + 1) * kSwJ + 2 * jp);
+            a0 = fmaf(p0, z0.x, a0);
+            a1 = fmaf(p0, z0.y, a1);
+            b0 = fmaf(p1, z1.x, b0);
+            b1 = fmaf(p1, z1.y, b1);
         }
+        for (; k < n; ++k) {
+            const float p0 = Pi[k * kSwI + ii];
+            a0 = fmaf(p0, Zs[k * kSwJ + 2 * jp], a0);
+            a1 = fmaf(p0, Zs[k * kSwJ + 2 * jp + 1], a1);
+        }
+        const int i = I0 + ii, j = J0 + 2 * jp;
+        if (i < n && j < n) {
+            cov[(long long)i * n + j] = a0 + b0;
+            if (j + 1 < n) cov[(long long)i * n + j + 1] = a1 + b1;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1113,7 +1050,7 @@ static size_t chol_smem(int n) { return (size_t)n * n * 4 + (size_t)8 * round_up
 template <int C2, int NC>
 static cudaError_t launch_e1(const SigmaArgs& a, int n_env, cudaStream_t st) {
     static size_t conf[32] = {};
-    const size_t smem = e1_smem_bytes(a.n, C2);
+    const size_t smem = e1_smem_bytes(C2);
     cudaError_t e = ensure_smem_attr(tridiag_reg_kernel<C2, NC>, smem, conf);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -1133,12 +1070,12 @@ static cudaError_t launch_e1(const SigmaArgs& a, int n_env, cudaStream_t st) {
 
 // Cluster width of E1 (CTAs per matrix).  Few matrices: spread each one over 4 SMs (latency); many matrices
 // (batched environments, the offline schedule): 2 SMs each, which still fills the machine.
-static int e1_cluster_override() {  // COVO_E1_CLUSTER = 1 | 2 | 4 | 8 pins the cluster width (tuning, tests)
+static int e1_cluster_override() {  // COVO_E1_CLUSTER = 2 | 4 | 8 pins the cluster width (tuning, tests)
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("COVO_E1_CLUSTER");
         v = e ? atoi(e) : 0;
-        if (v != 1 && v != 2 && v != 4 && v != 8) v = 0;
+        if (v != 2 && v != 4 && v != 8) v = 0;
     }
     return v;
 }
@@ -1159,20 +1096,13 @@ cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
             case 3: e = launch_e1<3, 4>(a, n_env, st); break;
             default: e = launch_e1<4, 4>(a, n_env, st); break;
         }
-    } else if (nc == 2) {
+    } else {  // 2 CTAs per matrix (the accumulated Q^T needs the register space of at least two SMs at n > 112)
         switch ((a.n + 31) / 32) {
             case 1: e = launch_e1<1, 2>(a, n_env, st); break;
             case 2: e = launch_e1<2, 2>(a, n_env, st); break;
             case 3: case 4: e = launch_e1<4, 2>(a, n_env, st); break;
             case 5: case 6: e = launch_e1<6, 2>(a, n_env, st); break;
             default: e = launch_e1<7, 2>(a, n_env, st); break;
-        }
-    } else {
-        switch ((a.n + 15) / 16) {
-            case 1: case 2: case 3: case 4: e = launch_e1<4, 1>(a, n_env, st); break;
-            case 5: case 6: case 7: case 8: e = launch_e1<8, 1>(a, n_env, st); break;
-            case 9: case 10: e = launch_e1<10, 1>(a, n_env, st); break;
-            default: e = launch_e1<14, 1>(a, n_env, st); break;
         }
     }
     if (e != cudaSuccess) return e;
@@ -1183,15 +1113,12 @@ cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
     sigma_trifunc_kernel<<<n_env, TT, smem, st>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const int cols_per_cta = kApplyWarps * kApplyCols;
-    dim3 g((a.n + cols_per_cta - 1) / cols_per_cta, n_env);
-    const size_t asm_bytes = (size_t)(2 * kApplyChunk * a.n + 2 * 256) * sizeof(float);
-    static size_t conf_q1[32] = {}, conf_q2[32] = {};
-    e = ensure_smem_attr(applyq_kernel<true, true>, asm_bytes, conf_q1);
-    if (e == cudaSuccess) e = ensure_smem_attr(applyq_kernel<false, false>, asm_bytes, conf_q2);
+    dim3 g((a.n + kSwI - 1) / kSwI, (a.n + kSwJ - 1) / kSwJ, n_env);
+    const size_t sw_bytes = sandwich_smem_bytes(a.n);
+    static size_t conf_sw[32] = {};
+    e = ensure_smem_attr(sandwich_kernel, sw_bytes, conf_sw);
     if (e != cudaSuccess) return e;
-    applyq_kernel<true, true><<<g, kApplyWarps * 32, asm_bytes, st>>>(a.Vh, a.Tw, a.F, a.Z, a.n);
-    applyq_kernel<false, false><<<g, kApplyWarps * 32, asm_bytes, st>>>(a.Vh, a.Tw, a.Z, a.cov, a.n);
+    sandwich_kernel<<<g, kSwThreads, sw_bytes, st>>>(a.Qt, a.F, a.cov, a.n);
     return cudaGetLastError();
 }
 

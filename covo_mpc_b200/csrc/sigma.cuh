@@ -6,7 +6,6 @@ namespace covo {
 
 constexpr int kZoloPoles = 16;    // poles of the rational approximation of x^(-1/2)
 constexpr int kZoloLadder = 10;   // spectral-ratio ladder: M/m = 4^(4+i), i = 0..9
-constexpr int kWyBlock = 8;       // reflectors per compact-WY block in apply-Q
 constexpr int kSigmaMaxN = 224;   // n = 4H limit of the shared-memory resident kernels (H <= 56)
 constexpr double kCovoOffset = 1e-2;  // "offset = -min_eign + 1e-2", controllers/covo.py:120-121
 
@@ -15,11 +14,8 @@ struct SigmaArgs {
     int n, n_pad;
     float sample_sigma;
     const float* R;      // [E][n][n]
-    float* Vh;           // [E][n][n]  row k = Householder vector v_k (zeros for index <= k, v[k+1] = 1)
-    float* tau;          // [E][n]
-    float* Tw;           // [E][n/8 + 1][64]  compact-WY T factors of the reflector blocks (8 per block)
-    float* F;            // [E][n][n]  exp(log_const/2) * (T - lam_min + offset)^(-1/2)
-    float* Z;            // [E][n][n]  Q F
+    float* Qt;           // [E][n][n]  Q^T = H_{n-3} ... H_1 H_0 (accumulated inside the tridiagonalisation)
+    float* F;            // [E][n][n]  exp(log_const/2) * (T - lam_min + offset)^(-1/2), full symmetric
     float* cov;          // [E][n][n]  Sigma = Q F Q^T (symmetrised)          -> a_cov
     float* L;            // [E][n][n]  optional: lower Cholesky factor, row-major
     float* Lt;           // [E][lt_size]  packed k-major factor for the sampler
