@@ -260,6 +260,7 @@ int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = fals
     // without splitting launch_sigma, so the pipeline is timed as [tridiag][applyQ x2] via two events inside.
     CK(launch_sigma(sa, h->E, st));
     if (pf) pf->mark(4);
+    sa.cov_symmetric = 1;
     CK(launch_cholesky(sa, h->E, st));
     if (pf) pf->mark(5);
     h->have_factor = true;
@@ -633,6 +634,7 @@ int covo_reset_offline(covo_handle* h, const float* state24, const int* time, in
     CK(cudaMemsetAsync(h->sched_status.p, 0, t_sched * sizeof(int), st));
     SigmaArgs sa = sched_sigma_args(h);
     CK(launch_sigma(sa, t_sched, st));
+    sa.cov_symmetric = 1;
     CK(launch_cholesky(sa, t_sched, st));
     CK(cudaStreamSynchronize(st));
     h->t_sched = t_sched;

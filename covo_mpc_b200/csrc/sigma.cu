@@ -784,7 +784,7 @@ __global__ void __launch_bounds__(TT, 1) sigma_trifunc_kernel(const SigmaArgs a)
 
 // ---------------------------------------------------------------------------------------------
 // E3: Sigma = Q F Q^T = P^T F P with P = Q^T from E1 and the symmetric F from E2: one launch, grid of 32 x 16
-// output tiles.  Each CTA first forms Z = F P[:, J] (n x 16, kept in shared memory; recomputed by the CTAs
+// output tiles of the lower triangle (mirrored on store).  Each CTA first forms Z = F P[:, J] (n x 16, kept in shared memory; recomputed by the CTAs
 // that share J -- 0.6 MFLOP, cheaper than a second launch), then Sigma[I, J] = P[:, I]^T Z.
 // ---------------------------------------------------------------------------------------------
 constexpr int kSwI = 32, kSwJ = 16, kSwThreads = 256, kSwChunk = 32;
@@ -812,6 +812,7 @@ __global__ void __launch_bounds__(kSwThreads) sandwich_kernel(const float* __res
     float* Fs = Pi + n * kSwI;       // [2][32][n]  row chunks of F, double-buffered (cp.async)
     const int env = blockIdx.z, tid = threadIdx.x;
     const int I0 = blockIdx.x * kSwI, J0 = blockIdx.y * kSwJ;
+    if (I0 + kSwI - 1 < J0) return;  // only tiles that touch the lower triangle: the result is mirrored
     Qt += (long long)env * n * n;
     F += (long long)env * n * n;
     cov += (long long)env * n * n;
@@ -891,10 +892,19 @@ __global__ void __launch_bounds__(kSwThreads) sandwich_kernel(const float* __res
             a0 = fmaf(p0, Zs[k * kSwJ + 2 * jp], a0);
             a1 = fmaf(p0, Zs[k * kSwJ + 2 * jp + 1], a1);
         }
+        // lower triangle + mirror image: Sigma is exactly symmetric by construction (controllers/covo.py:132
+        // symmetrises its product the same way up to rounding)
         const int i = I0 + ii, j = J0 + 2 * jp;
-        if (i < n && j < n) {
-            cov[(long long)i * n + j] = a0 + b0;
-            if (j + 1 < n) cov[(long long)i * n + j + 1] = a1 + b1;
+        if (i < n) {
+            const float s0 = a0 + b0, s1 = a1 + b1;
+            if (j <= i) {
+                cov[(long long)i * n + j] = s0;
+                if (j < i) cov[(long long)j * n + i] = s0;
+            }
+            if (j + 1 <= i) {
+                cov[(long long)i * n + j + 1] = s1;
+                if (j + 1 < i) cov[(long long)(j + 1) * n + i] = s1;
+            }
         }
     }
 }
@@ -911,82 +921,130 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
     const int n = a.n, n_pad = a.n_pad, tid = threadIdx.x, env = blockIdx.x, lane = tid & 31, warp = tid >> 5;
     float* As = reinterpret_cast<float*>(smraw);  // [n][n]
     float* Lp = As + n * n;                       // [8][n_pad]  panel, transposed
-    float* L11 = Lp + 8 * n_pad;                  // [8][8]
     float* covg = a.cov + (long long)env * n * n;
     COVO_STAMP(a, 23);
-    // (a_cov + a_cov.T)/2, controllers/covo.py:132: coalesced load, symmetrise in shared memory, write back
-    for (int i = warp; i < n; i += TC / 32)
-        for (int j = lane; j < n; j += 32) As[i * n + j] = covg[i * n + j];
-    __syncthreads();
-    for (int i = warp; i < n; i += TC / 32)
-        for (int j = lane; j < i; j += 32) {
-            const float s2 = 0.5f * (As[i * n + j] + As[j * n + i]);
-            As[i * n + j] = s2;
-            As[j * n + i] = s2;
+    // (a_cov + a_cov.T)/2, controllers/covo.py:132, in ONE pass: the row part of a float4 is read coalesced, its
+    // four transposed partners straight from L2; all loads of a batch are in flight together.
+    if (a.cov_symmetric) {
+        // written by the sandwich kernel: exactly symmetric by construction -> plain coalesced load
+        const int nv4 = (n * n) >> 2;
+        const float4* g4 = reinterpret_cast<const float4*>(covg);
+        constexpr int kB = 10;
+        for (int base = 0; base < nv4; base += kB * TC) {
+            float4 rv[kB];
+#pragma unroll
+            for (int k = 0; k < kB; ++k) {
+                const int idx = base + k * TC + tid;
+                if (idx < nv4) rv[k] = g4[idx];
+            }
+#pragma unroll
+            for (int k = 0; k < kB; ++k) {
+                const int idx = base + k * TC + tid;
+                if (idx < nv4) reinterpret_cast<float4*>(As)[idx] = rv[k];
+            }
         }
+    } else {
+        const int nv4 = (n * n) >> 2, nq = n >> 2;
+        const float4* g4 = reinterpret_cast<const float4*>(covg);
+        constexpr int kBatch = 5;
+        for (int base = 0; base < nv4; base += kBatch * TC) {
+            float4 rv[kBatch], cv[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const int idx = base + k * TC + tid;
+                if (idx < nv4) {
+                    const int i = idx / nq, j = 4 * (idx - i * nq);
+                    rv[k] = g4[idx];
+                    cv[k].x = covg[(long long)j * n + i];
+                    cv[k].y = covg[(long long)(j + 1) * n + i];
+                    cv[k].z = covg[(long long)(j + 2) * n + i];
+                    cv[k].w = covg[(long long)(j + 3) * n + i];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const int idx = base + k * TC + tid;
+                if (idx < nv4) {
+                    const float4 sv = make_float4(0.5f * (rv[k].x + cv[k].x), 0.5f * (rv[k].y + cv[k].y),
+                                                  0.5f * (rv[k].z + cv[k].z), 0.5f * (rv[k].w + cv[k].w));
+                    reinterpret_cast<float4*>(As)[idx] = sv;
+                }
+            }
+        }
+        __syncthreads();  // every transposed partner has been read from HBM / L2 before anything is overwritten
+        for (int idx = tid; idx < nv4; idx += TC) reinterpret_cast<float4*>(covg)[idx] = reinterpret_cast<const float4*>(As)[idx];
+    }
     __syncthreads();
-    for (int i = warp; i < n; i += TC / 32)
-        for (int j = lane; j < n; j += 32) covg[i * n + j] = As[i * n + j];
     COVO_STAMP(a, 24);
     for (int jb = 0; jb < n; jb += 8) {
         const int nb = min(8, n - jb);
         if (jb == 8) COVO_STAMP(a, 26);
-        if (warp == 0) {
-            float r8[8];
+        // (a) + (b): every row thread of the panel factors the 8x8 diagonal block PRIVATELY in registers (170
+        // dependent-ish FMAs, no shuffles, no broadcast, no barrier) and goes straight on to its row of
+        // L21 = A21 L11^-T.  Thread 0 also writes the factored block back.
+        const int nrows = n - jb - nb;
+        if (tid < max(nrows, 1)) {
+            float d[8][8], linv[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) r8[c] = (lane < nb && c < nb) ? As[(jb + lane) * n + jb + c] : 0.f;
+            for (int r = 0; r < 8; ++r) {
+                const float4 p0 = (r < nb) ? *reinterpret_cast<const float4*>(As + (jb + r) * n + jb) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 p1 = (r < nb && nb == 8) ? *reinterpret_cast<const float4*>(As + (jb + r) * n + jb + 4)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                d[r][0] = p0.x; d[r][1] = p0.y; d[r][2] = p0.z; d[r][3] = p0.w;
+                d[r][4] = p1.x; d[r][5] = p1.y; d[r][6] = p1.z; d[r][7] = p1.w;
+                if (r >= nb) d[r][r] = 1.f;
+            }
+            bool bad = false;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                float dcc = __shfl_sync(0xffffffffu, r8[c], c);
-                if (c < nb) {
-                    if (!(dcc > 0.f)) {
-                        if (lane == 0) a.status[env] = 2;
-                        dcc = 1e-30f;
-                    }
-                    float rinv = rsqrtf(dcc);
-                    rinv = rinv * (1.5f - 0.5f * dcc * rinv * rinv);
-                    if (lane == c) r8[c] = dcc * rinv;  // sqrt
-                    else if (lane > c) r8[c] = r8[c] * rinv;
+                float dcc = d[c][c];
+                if (!(dcc > 0.f)) {
+                    bad = true;
+                    dcc = 1e-30f;
                 }
+                const float rinv = rsqrt_newton(dcc);
+                linv[c] = rinv;
+                d[c][c] = dcc * rinv;
 #pragma unroll
-                for (int c2 = c + 1; c2 < 8; ++c2) {
-                    float l2 = __shfl_sync(0xffffffffu, r8[c], c2);
-                    if (c2 < nb && lane >= c2) r8[c2] = fmaf(-r8[c], l2, r8[c2]);
-                }
+                for (int r = c + 1; r < 8; ++r) d[r][c] *= rinv;
+#pragma unroll
+                for (int c2 = c + 1; c2 < 8; ++c2)
+#pragma unroll
+                    for (int r = c2; r < 8; ++r) d[r][c2] = fmaf(-d[r][c], d[c2][c], d[r][c2]);
             }
-            if (lane < 8) {
+            if (tid == 0) {
+                if (bad) a.status[env] = 2;
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (r < nb) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (c < nb) As[(jb + r) * n + jb + c] = (c <= r) ? d[r][c] : 0.f;
+                    }
+            }
+            if (tid < nrows) {
+                const int i = jb + nb + tid;
+                float x[8];
+                const float4 p0 = *reinterpret_cast<const float4*>(As + i * n + jb);
+                x[0] = p0.x; x[1] = p0.y; x[2] = p0.z; x[3] = p0.w;
+                if (nb == 8) {
+                    const float4 p1 = *reinterpret_cast<const float4*>(As + i * n + jb + 4);
+                    x[4] = p1.x; x[5] = p1.y; x[6] = p1.z; x[7] = p1.w;
+                } else {
+                    x[4] = x[5] = x[6] = x[7] = 0.f;
+                }
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    float v = (lane < nb && c < nb && c <= lane) ? r8[c] : 0.f;
-                    if (lane < nb && c < nb) As[(jb + lane) * n + jb + c] = v;
-                    // L11 holds the factor with the RECIPROCAL diagonal (the panel solve multiplies)
-                    L11[lane * 8 + c] = (c == lane) ? ((lane < nb) ? 1.0f / r8[c] : 1.0f) : v;
+                    float sx = x[c];
+#pragma unroll
+                    for (int c2 = 0; c2 < c; ++c2) sx = fmaf(-x[c2], d[c][c2], sx);
+                    x[c] = sx * linv[c];
                 }
-            }
-        }
-        __syncthreads();
-        // (b) panel: L21 = A21 L11^-T
-        for (int i = jb + nb + tid; i < n; i += TC) {
-            float x[8];
-            const float4 p0 = *reinterpret_cast<const float4*>(As + i * n + jb);
-            x[0] = p0.x; x[1] = p0.y; x[2] = p0.z; x[3] = p0.w;
-            if (nb == 8) {
-                const float4 p1 = *reinterpret_cast<const float4*>(As + i * n + jb + 4);
-                x[4] = p1.x; x[5] = p1.y; x[6] = p1.z; x[7] = p1.w;
-            } else {
-                x[4] = x[5] = x[6] = x[7] = 0.f;
-            }
+                *reinterpret_cast<float4*>(As + i * n + jb) = make_float4(x[0], x[1], x[2], x[3]);
+                if (nb == 8) *reinterpret_cast<float4*>(As + i * n + jb + 4) = make_float4(x[4], x[5], x[6], x[7]);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float s = x[c];
-#pragma unroll
-                for (int c2 = 0; c2 < c; ++c2) s = fmaf(-x[c2], L11[c * 8 + c2], s);
-                x[c] = s * L11[c * 8 + c];
+                for (int c = 0; c < 8; ++c) Lp[c * n_pad + i] = x[c];
             }
-            *reinterpret_cast<float4*>(As + i * n + jb) = make_float4(x[0], x[1], x[2], x[3]);
-            if (nb == 8) *reinterpret_cast<float4*>(As + i * n + jb + 4) = make_float4(x[4], x[5], x[6], x[7]);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) Lp[c * n_pad + i] = x[c];
         }
         __syncthreads();
         // (c) trailing update on the lower-triangle 4x4 tiles
@@ -1045,7 +1103,7 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
 static size_t trifunc_smem(int n) {
     return (size_t)trifunc_region_floats(n) * 4 + 256 * 8 * 3 + 16 * 8 + 64 * 8 + 16;
 }
-static size_t chol_smem(int n) { return (size_t)n * n * 4 + (size_t)8 * round_up8(n) * 4 + 64 * 4; }
+static size_t chol_smem(int n) { return (size_t)n * n * 4 + (size_t)8 * round_up8(n) * 4; }
 
 template <int C2, int NC>
 static cudaError_t launch_e1(const SigmaArgs& a, int n_env, cudaStream_t st) {

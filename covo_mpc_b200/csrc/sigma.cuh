@@ -16,13 +16,14 @@ struct SigmaArgs {
     const float* R;      // [E][n][n]
     float* Qt;           // [E][n][n]  Q^T = H_{n-3} ... H_1 H_0 (accumulated inside the tridiagonalisation)
     float* F;            // [E][n][n]  exp(log_const/2) * (T - lam_min + offset)^(-1/2), full symmetric
-    float* cov;          // [E][n][n]  Sigma = Q F Q^T (symmetrised)          -> a_cov
+    float* cov;          // [E][n][n]  Sigma = Q F Q^T, exactly symmetric          -> a_cov
     float* L;            // [E][n][n]  optional: lower Cholesky factor, row-major
     float* Lt;           // [E][lt_size]  packed k-major factor for the sampler
     double* diag;        // [E][4][n]: d, e, then (lam_min, gersh_lo, gersh_hi, logdet, ladder idx) for tests
     const double* zolo;  // [kZoloLadder][2][kZoloPoles]  shifts t_j, weights w_j (host-computed)
     int* status;         // [E]  0 ok, 1 spectral ratio beyond ladder, 2 Cholesky breakdown
     long long lt_stride;
+    int cov_symmetric = 0;  // cov is exactly symmetric already (written by the sandwich kernel): Cholesky skips (C + C^T)/2
 };
 
 // host: Zolotarev/Hale-Higham-Trefethen nodes for x^(-1/2) on [m, M]
