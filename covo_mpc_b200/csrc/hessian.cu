@@ -15,7 +15,8 @@
 // Kernel 1 (grid = H x envs): CTA t re-runs the nominal rollout to x_t, then 153 threads evaluate the
 //   transition and the cost once each in hyper-dual arithmetic (quad_model.cuh) -- one (a <= b) pair of
 //   the 17 local inputs per thread -- giving A_t, B_t, grad/hess c_t and all 13 hess F_k.
-// Kernel 2 (grid = envs): adjoint, contraction, the 13x13 backward recursion and the H forward chains.
+// Kernel 2 (grid = envs): adjoint, contraction and the 13x13 backward recursion.
+// Kernel 3 (grid = 4H/8 x envs): the 4H forward chains, one quad of lanes each, spread over the SMs.
 // Sub-gradient conventions (clip ties, |.|, sqrt at 0) are those of quad_model.cuh / the oracle.
 #include <cuda_runtime.h>
 
@@ -80,8 +81,9 @@ __global__ void __launch_bounds__(160) hess_local_kernel(const HessianArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int kAsmThreads = 320;
+constexpr int kAsmThreads = 1024;
 constexpr int NZP = 20;  // row pitch of [A_t | B_t] in shared memory: 13 + 4 entries padded to 5 float4
+constexpr int kFwRec = NX * NZP + NX * 4 + 16;  // 328 floats per step handed to the forward-chain kernel (float4 multiple)
 
 __global__ void __launch_bounds__(kAsmThreads) hess_assemble_kernel(const HessianArgs a) {
     extern __shared__ __align__(16) float smf[];
@@ -183,68 +185,108 @@ __global__ void __launch_bounds__(kAsmThreads) hess_assemble_kernel(const Hessia
     }
     COVO_STAMP(a, 4);
 
-    // forward chains: thread (I, c) carries Phi = d x_J / d u_{I,c}.  The J loop is uniform across the block,
-    // so every A_J / S_J read is a shared-memory broadcast.
-    float* Rg = a.R + (long long)env * n * n;
-    const int id = tid;
-    const bool active = id < n;
-    const int I = id >> 2, c = id & 3;
-    float phi[NX];
-    if (active) {
-        const float* GI = G + I * NX * NZP;
-#pragma unroll
-        for (int k = 0; k < NX; ++k) phi[k] = GI[k * NZP + NX + c];
-        float4 d = *reinterpret_cast<const float4*>(D + I * 16 + c * 4);
-        // D is symmetric up to round-off; symmetrise so R is exactly symmetric
-        float dd[4] = {d.x, d.y, d.z, d.w};
-        for (int e = 0; e < 4; ++e) dd[e] = 0.5f * (dd[e] + D[I * 16 + e * 4 + c]);
-        *reinterpret_cast<float4*>(Rg + (long long)id * n + 4 * I) = make_float4(dd[0], dd[1], dd[2], dd[3]);
-    }
-    for (int J = 1; J < H; ++J) {
-        if (!active || J <= I) continue;
-        const float* SJ = S + J * NX * 4;
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
-#pragma unroll
-        for (int k = 0; k < NX; ++k) {
-            float4 sj = *reinterpret_cast<const float4*>(SJ + k * 4);
-            r0 = fmaf(phi[k], sj.x, r0);
-            r1 = fmaf(phi[k], sj.y, r1);
-            r2 = fmaf(phi[k], sj.z, r2);
-            r3 = fmaf(phi[k], sj.w, r3);
+    // export [A_t | B_t] (13 x 20), S_t (13 x 4) and D_t (4 x 4) for the forward-chain kernel: they overwrite the
+    // head of each per-step record of the workspace, which this CTA has fully consumed above
+    {
+        float* wso = a.workspace + (long long)env * H * rec;
+        for (int i = tid; i < H * kFwRec; i += kAsmThreads) {
+            const int t = i / kFwRec, rr = i - t * kFwRec;
+            float v;
+            if (rr < NX * NZP) v = G[t * NX * NZP + rr];
+            else if (rr < NX * NZP + NX * 4) v = S[t * NX * 4 + (rr - NX * NZP)];
+            else v = D[t * 16 + (rr - NX * NZP - NX * 4)];
+            wso[(long long)t * rec + rr] = v;
         }
-        *reinterpret_cast<float4*>(Rg + (long long)id * n + 4 * J) = make_float4(r0, r1, r2, r3);
-        Rg[(long long)(4 * J + 0) * n + id] = r0;
-        Rg[(long long)(4 * J + 1) * n + id] = r1;
-        Rg[(long long)(4 * J + 2) * n + id] = r2;
-        Rg[(long long)(4 * J + 3) * n + id] = r3;
-        if (J == H - 1) break;
-        const float* GJ = G + J * NX * NZP;
-        float nphi[NX];
-#pragma unroll
-        for (int r = 0; r < NX; ++r) {
-            const float4 a0 = *reinterpret_cast<const float4*>(GJ + r * NZP);
-            const float4 a1 = *reinterpret_cast<const float4*>(GJ + r * NZP + 4);
-            const float4 a2 = *reinterpret_cast<const float4*>(GJ + r * NZP + 8);
-            const float a12 = GJ[r * NZP + 12];
-            float acc = a0.x * phi[0];
-            acc = fmaf(a0.y, phi[1], acc);
-            acc = fmaf(a0.z, phi[2], acc);
-            acc = fmaf(a0.w, phi[3], acc);
-            acc = fmaf(a1.x, phi[4], acc);
-            acc = fmaf(a1.y, phi[5], acc);
-            acc = fmaf(a1.z, phi[6], acc);
-            acc = fmaf(a1.w, phi[7], acc);
-            acc = fmaf(a2.x, phi[8], acc);
-            acc = fmaf(a2.y, phi[9], acc);
-            acc = fmaf(a2.z, phi[10], acc);
-            acc = fmaf(a2.w, phi[11], acc);
-            acc = fmaf(a12, phi[12], acc);
-            nphi[r] = acc;
-        }
-#pragma unroll
-        for (int k = 0; k < NX; ++k) phi[k] = nphi[k];
     }
     COVO_STAMP(a, 5);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward chains R[I, J] = Phi^T S_J, Phi <- A_J Phi (Phi = d x_J / d u_{I,c}, starts as column c of B_I), J > I, and
+// the diagonal blocks R[I, I] = D_I.  One QUAD of lanes per chain (I, c): lane q forms rows q, q+4, q+8 (, 12) of
+// A_J Phi and the output column q; the quad re-assembles Phi with 13 shuffles.  One warp (8 chains) per CTA, the
+// CTAs spread over the SMs: the 49-step dependent chain runs at single-warp latency instead of sharing one SM
+// with 200 other chains.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFwThreads = 128;
+
+__global__ void __launch_bounds__(kFwThreads) hess_forward_kernel(const HessianArgs a) {
+    extern __shared__ __align__(16) float fsm[];  // [H][kFwRec]
+    const int env = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int H = a.H, n = 4 * H;
+    const int rec = 14 * NPAIR + 14 * NZ;
+    const float* wsb = a.workspace + (long long)env * H * rec;
+    const int id0 = blockIdx.x * 8;          // first chain of this CTA
+    const int Imin = id0 >> 2;
+    // stage the records J >= Imin (16-byte pieces, all threads)
+    {
+        const int v4 = kFwRec / 4;
+        for (int i = tid; i < (H - Imin) * v4; i += kFwThreads) {
+            const int t = Imin + i / v4, q4 = i - (t - Imin) * v4;
+            unsigned d = (unsigned)__cvta_generic_to_shared(fsm + t * kFwRec + 4 * q4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(wsb + (long long)t * rec + 4 * q4) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid >= 32) return;
+    const int id = id0 + (lane >> 2), q = lane & 3;
+    if (id >= n) return;  // n is a multiple of 8 only when H is even; whole quads drop out together
+    const int I = id >> 2, c = id & 3;
+    const unsigned qmask = 0xFu << (lane & ~3);
+    float* Rg = a.R + (long long)env * n * n;
+    float phi[NX];
+    {
+        const float* GI = fsm + I * kFwRec;
+#pragma unroll
+        for (int k = 0; k < NX; ++k) phi[k] = GI[k * NZP + NX + c];
+        // D is symmetric up to round-off; symmetrise so R is exactly symmetric
+        const float* DI = fsm + I * kFwRec + NX * NZP + NX * 4;
+        Rg[(long long)id * n + 4 * I + q] = 0.5f * (DI[c * 4 + q] + DI[q * 4 + c]);
+    }
+    for (int J = I + 1; J < H; ++J) {
+        const float* GJ = fsm + J * kFwRec;
+        const float* SJ = GJ + NX * NZP;
+        float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NX; k += 2) {
+            r0 = fmaf(phi[k], SJ[k * 4 + q], r0);
+            if (k + 1 < NX) r1 = fmaf(phi[k + 1], SJ[(k + 1) * 4 + q], r1);
+        }
+        const float rq = r0 + r1;
+        Rg[(long long)id * n + 4 * J + q] = rq;
+        Rg[(long long)(4 * J + q) * n + id] = rq;
+        if (J == H - 1) break;
+        // rows q, q+4, q+8 (and 12 for q = 0) of A_J Phi
+        float np[4];
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+            const int r = q + 4 * sl;
+            float acc = 0.f;
+            if (r < NX) {
+                const float4 a0 = *reinterpret_cast<const float4*>(GJ + r * NZP);
+                const float4 a1 = *reinterpret_cast<const float4*>(GJ + r * NZP + 4);
+                const float4 a2 = *reinterpret_cast<const float4*>(GJ + r * NZP + 8);
+                const float a12 = GJ[r * NZP + 12];
+                float e0 = a0.x * phi[0], e1 = a0.y * phi[1];
+                e0 = fmaf(a0.z, phi[2], e0);
+                e1 = fmaf(a0.w, phi[3], e1);
+                e0 = fmaf(a1.x, phi[4], e0);
+                e1 = fmaf(a1.y, phi[5], e1);
+                e0 = fmaf(a1.z, phi[6], e0);
+                e1 = fmaf(a1.w, phi[7], e1);
+                e0 = fmaf(a2.x, phi[8], e0);
+                e1 = fmaf(a2.y, phi[9], e1);
+                e0 = fmaf(a2.z, phi[10], e0);
+                e1 = fmaf(a2.w, phi[11], e1);
+                e0 = fmaf(a12, phi[12], e0);
+                acc = e0 + e1;
+            }
+            np[sl] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < NX; ++k) phi[k] = __shfl_sync(qmask, np[k >> 2], (lane & ~3) + (k & 3));
+    }
 }
 
 size_t hessian_assemble_smem(int H) {
@@ -262,6 +304,13 @@ cudaError_t launch_hessian(const HessianArgs& a, int n_env, cudaStream_t st) {
     e = ensure_smem_attr(hess_assemble_kernel, smem, configured);
     if (e != cudaSuccess) return e;
     hess_assemble_kernel<<<n_env, kAsmThreads, smem, st>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const size_t fsmem = (size_t)a.H * kFwRec * sizeof(float);
+    static size_t configured_fw[32] = {};
+    e = ensure_smem_attr(hess_forward_kernel, fsmem, configured_fw);
+    if (e != cudaSuccess) return e;
+    hess_forward_kernel<<<dim3((4 * a.H + 7) / 8, n_env), kFwThreads, fsmem, st>>>(a);
     return cudaGetLastError();
 }
 

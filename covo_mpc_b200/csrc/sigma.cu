@@ -116,45 +116,89 @@ __device__ __forceinline__ double wmaxd(double v) {
     return v;
 }
 
-// number of eigenvalues of tridiag(d, e) strictly below x: sign changes of the Sturm sequence,
-// evaluated division-free with rescaling (a zero term takes the sign opposite to its predecessor).
-__device__ int sturm_count(const double* d, const double* e2, int n, double x) {
-    // e2[i] = e[i]^2 (coupling between i and i+1).  The loads run one iteration ahead of the fp64 chain.
-    double pm = 1.0, p = d[0] - x;
-    if (p == 0.0) p = -1e-300;
-    int cnt = (__double2hiint(p) >> 31) & 1;
-    double dn = d[1], en = e2[0];
-    for (int i0 = 1; i0 < n; i0 += 8) {
-        const int i1 = min(i0 + 8, n);
-        for (int i = i0; i < i1; ++i) {
-            const double di = dn, ei = en;
-            if (i + 1 < n) {
-                dn = d[i + 1];
-                en = e2[i];
-            }
-            double pn = fma(di - x, p, -(ei * pm));
-            // sign tests on the high word (integer pipe): only the recurrence itself runs on the fp64 pipe
-            int hn = __double2hiint(pn);
-            const int hp = __double2hiint(p);
-            if (((hn & 0x7fffffff) | __double2loint(pn)) == 0) {
-                pn = (hp < 0) ? 1e-300 : -1e-300;
-                hn = __double2hiint(pn);
-            }
-            cnt += ((hn ^ hp) >> 31) & 1;
-            pm = p;
-            p = pn;
-        }
-        // the terms grow by at most ~(|d - x| + |e|) per step, so a range check every 8 steps is enough
-        const int ex = (__double2hiint(p) >> 20) & 0x7ff;
-        if (ex > 1023 + 400) {
-            p *= 1e-120;
-            pm *= 1e-120;
-        } else if (ex < 1023 - 400) {
-            p *= 1e120;
-            pm *= 1e120;
-        }
+// ---------------------------------------------------------------------------------------------
+// Three-term recurrences on the tridiagonal, evaluated by ONE WARP as a prefix product of 2x2 matrices:
+//   p_i = alpha_i p_{i-1} - beta_i p_{i-2},  p_{-1} = 1, p_{-2} = 0      (Sturm sequence / pivot numerators)
+//   (p_i, p_{i-1})^T = M_i ... M_0 (1, 0)^T,  M_i = [[alpha_i, -beta_i], [1, 0]].
+// Lane L multiplies the matrices of its segment of ceil(n/32) indices, a Kogge-Stone scan combines the segments
+// (5 levels), and the lane walks its segment again from the prefix state.  The dependent chain is ~2 x 7 + 5
+// matrix products instead of n = 200 steps.  Only sign patterns and the ratios p_i / p_{i-1} are used, so every
+// partial product is rescaled by a power of two (no overflow, exact).
+// ---------------------------------------------------------------------------------------------
+struct M2 {
+    double a, b, c, d;  // [[a, b], [c, d]]
+};
+__device__ __forceinline__ M2 m2_mul(const M2& x, const M2& y) {  // x * y
+    M2 r;
+    r.a = fma(x.a, y.a, x.b * y.c);
+    r.b = fma(x.a, y.b, x.b * y.d);
+    r.c = fma(x.c, y.a, x.d * y.c);
+    r.d = fma(x.c, y.b, x.d * y.d);
+    return r;
+}
+__device__ __forceinline__ M2 m2_normalise(const M2& x) {
+    const int e = max(max(__double2hiint(x.a) & 0x7ff00000, __double2hiint(x.b) & 0x7ff00000),
+                      max(__double2hiint(x.c) & 0x7ff00000, __double2hiint(x.d) & 0x7ff00000));
+    const double sc = __hiloint2double(0x7fe00000 - e, 0);  // 2^(1023 - biased exponent of the largest entry)
+    M2 r;
+    r.a = x.a * sc; r.b = x.b * sc; r.c = x.c * sc; r.d = x.d * sc;
+    return r;
+}
+__device__ __forceinline__ M2 m2_shfl_up(const M2& x, int off) {
+    M2 r;
+    r.a = __shfl_up_sync(0xffffffffu, x.a, off);
+    r.b = __shfl_up_sync(0xffffffffu, x.b, off);
+    r.c = __shfl_up_sync(0xffffffffu, x.c, off);
+    r.d = __shfl_up_sync(0xffffffffu, x.d, off);
+    return r;
+}
+// AB(s, alpha, beta) supplies the coefficients of step s (beta of step 0 is ignored); EMIT(s, p_s, p_{s-1}) consumes
+// the sequence (both values carry the same positive scale factor).  All 32 lanes of the warp must call.
+template <class AB, class EMIT>
+__device__ __forceinline__ void warp_recurrence(int n, AB ab, EMIT emit) {
+    const int lane = threadIdx.x & 31;
+    const int seg = (n + 31) >> 5, s0 = lane * seg, s1 = min(s0 + seg, n);
+    M2 P = {1.0, 0.0, 0.0, 1.0};
+    for (int s = s0; s < s1; ++s) {
+        double al, be;
+        ab(s, al, be);
+        if (s == 0) be = 0.0;
+        const M2 t = P;
+        P.a = fma(al, t.a, -be * t.c);
+        P.b = fma(al, t.b, -be * t.d);
+        P.c = t.a;
+        P.d = t.b;
     }
-    return cnt;
+    P = m2_normalise(P);
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const M2 Q = m2_shfl_up(P, off);
+        if (lane >= off) P = m2_normalise(m2_mul(P, Q));
+    }
+    const M2 Q = m2_shfl_up(P, 1);
+    double p = (lane == 0) ? 1.0 : Q.a, pm = (lane == 0) ? 0.0 : Q.c;
+    for (int s = s0; s < s1; ++s) {
+        double al, be;
+        ab(s, al, be);
+        if (s == 0) be = 0.0;
+        const double pn = fma(al, p, -be * pm);
+        emit(s, pn, p);
+        pm = p;
+        p = pn;
+    }
+}
+// does tridiag(d, e) have an eigenvalue below x?  (sign change in the Sturm sequence; a zero term counts as a
+// change, which is the conservative answer for the bracket)
+__device__ __forceinline__ bool warp_has_eig_below(const double* d, const double* e2, int n, double x) {
+    bool neg = false;
+    warp_recurrence(
+        n, [&](int s, double& al, double& be) { al = d[s] - x; be = (s > 0) ? e2[s - 1] : 0.0; },
+        [&](int, double pn, double p) {
+            // signs on the high words; +-0 of either term is treated as a change
+            const int hn = __double2hiint(pn), hp = __double2hiint(p);
+            neg |= ((hn ^ hp) < 0) || (pn == 0.0) || (p == 0.0);
+        });
+    return __any_sync(0xffffffffu, neg);
 }
 
 }  // namespace
@@ -551,7 +595,8 @@ __host__ __device__ inline int trifunc_region_floats(int n) {
 
 __global__ void __launch_bounds__(TT, 1) sigma_trifunc_kernel(const SigmaArgs a) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    const int n = a.n, tid = threadIdx.x, env = blockIdx.x, lane = tid & 31, warp = tid >> 5;
+    // grid (NB, E): the NB CTAs of one matrix repeat the (cheap, deterministic) scalar stages and share out the rows of F
+    const int n = a.n, tid = threadIdx.x, env = blockIdx.y, part = blockIdx.x, nparts = gridDim.x, lane = tid & 31, warp = tid >> 5;
     float* As = reinterpret_cast<float*>(smraw);          // E2 scratch region
     double* dd = reinterpret_cast<double*>(As + trifunc_region_floats(n));  // [256]
     double* ee = dd + 256;                                // [256]
@@ -601,18 +646,16 @@ __global__ void __launch_bounds__(TT, 1) sigma_trifunc_kernel(const SigmaArgs a)
         __syncthreads();
     }
     COVO_STAMP(a, 10);
-    // lam_min by multisection.  fp64 issues at ~1/9 of the fp32 rate on this part and the Sturm recurrence is
-    // a serial chain, so the cost is (evaluation points) x (rounds): 128 points (one warp per scheduler) x 6
-    // rounds shrink the Gershgorin bracket by 129^6 ~ 4.6e12, i.e. to ~1e-11 absolute.
-    constexpr int MS = 128;
-    for (int round = 0; round < 6; ++round) {
+    // lam_min by multisection: every warp evaluates one trial shift per round with the warp-scan Sturm test
+    // (~0.5 us), 9 rounds shrink the Gershgorin bracket by 33^9 ~ 4.6e13, i.e. to ~1e-10 absolute.
+    constexpr int MS = TT / 32;
+    for (int round = 0; round < 9; ++round) {
         const double lo = sc[0], hi = sc[1];
         if (tid == 0) ired[0] = MS;
         __syncthreads();
-        // spread the four evaluation warps over the four schedulers: warps 0..3
-        if (tid < MS) {
-            const double x = lo + (hi - lo) * ((double)(tid + 1) / (double)(MS + 1));
-            if (sturm_count(dd, e2s, n, x) >= 1) atomicMin(ired, tid);
+        {
+            const double x = lo + (hi - lo) * ((double)(warp + 1) / (double)(MS + 1));
+            if (warp_has_eig_below(dd, e2s, n, x) && lane == 0) atomicMin(ired, warp);
         }
         __syncthreads();
         if (tid == 0) {
@@ -646,38 +689,26 @@ __global__ void __launch_bounds__(TT, 1) sigma_trifunc_kernel(const SigmaArgs a)
     double* den = num + 2 * (NPOLE + 1) * n;                          // [2][17][n]
     float* gd = reinterpret_cast<float*>(den + 2 * (NPOLE + 1) * n);  // [16][n]    diag of (T_s+t_q)^-1
     float* lcl = gd + NPOLE * n;                                      // [16][n+1]  c_q[l]
-    if (tid < NPOLE + 1 || (tid >= 32 && tid < 32 + NPOLE + 1)) {
-        const bool fwd = tid < 32;
-        const int q = fwd ? tid : tid - 32;
+    // one warp-scan per (direction, pole): 34 recurrences over the 32 warps
+    for (int task = warp; task < 2 * (NPOLE + 1); task += TT / 32) {
+        const bool fwd = task < NPOLE + 1;
+        const int q = fwd ? task : task - (NPOLE + 1);
         const double tq = (q < NPOLE) ? zt[q] : 0.0;
         double* nm = num + ((fwd ? 0 : 1) * (NPOLE + 1) + q) * n;
         double* dn = den + ((fwd ? 0 : 1) * (NPOLE + 1) + q) * n;
-        double pm = 0.0, p = 1.0;
         const double sh = shift0 + tq;
-        double an = dd[fwd ? 0 : n - 1] + sh, bn = 0.0;
-        for (int s = 0; s < n; ++s) {
-            const int i = fwd ? s : n - 1 - s;
-            const double ai = an, b2 = bn;
-            if (s + 1 < n) {  // operands of the next step, off the dependent chain
-                const int i2 = fwd ? s + 1 : n - 2 - s;
-                an = dd[i2] + sh;
-                bn = e2s[fwd ? i2 - 1 : i2];
-            }
-            double pn = fma(ai, p, -(b2 * pm));
-            nm[i] = pn;
-            dn[i] = p;
-            // range control on the exponent field (integer test, keeps the fp64 pipe for the recurrence)
-            const int ex = (__double2hiint(pn) >> 20) & 0x7ff;
-            if (ex > 1023 + 400) {
-                pn *= 1e-120;
-                p *= 1e-120;
-            } else if (ex < 1023 - 400) {
-                pn *= 1e120;
-                p *= 1e120;
-            }
-            pm = p;
-            p = pn;
-        }
+        warp_recurrence(
+            n,
+            [&](int s2, double& al, double& be) {
+                const int i = fwd ? s2 : n - 1 - s2;
+                al = dd[i] + sh;
+                be = (s2 > 0) ? e2s[fwd ? i - 1 : i] : 0.0;
+            },
+            [&](int s2, double pn, double pp) {
+                const int i = fwd ? s2 : n - 1 - s2;
+                nm[i] = pn;
+                dn[i] = pp;
+            });
     }
     __syncthreads();
     COVO_STAMP(a, 12);
@@ -736,7 +767,7 @@ __global__ void __launch_bounds__(TT, 1) sigma_trifunc_kernel(const SigmaArgs a)
         const double log_const = (4.0 * n * log((double)a.sample_sigma) + logdet) / (double)n;
         const float cscale = (float)exp(0.5 * log_const);
         float* Fg = a.F + (long long)env * n * n;
-        for (int i = warp; i < n; i += TT / 32) {
+        for (int i = part + nparts * warp; i < n; i += nparts * (TT / 32)) {  // rows interleaved over the CTAs
             float val[NPOLE];
 #pragma unroll
             for (int q = 0; q < NPOLE; ++q) {
@@ -764,18 +795,13 @@ __global__ void __launch_bounds__(TT, 1) sigma_trifunc_kernel(const SigmaArgs a)
                 }
             }
         }
-        if (tid == 0) {
+        if (tid == 0 && part == 0) {
             double* dg = a.diag + (long long)env * 4 * n;
             dg[2 * n + 0] = lam_min;
             dg[2 * n + 1] = sc[2];
             dg[2 * n + 2] = sc[3];
             dg[2 * n + 3] = logdet;
             dg[2 * n + 4] = (double)lad;
-        }
-        if (tid < n) {
-            double* dg = a.diag + (long long)env * 4 * n;
-            dg[tid] = dd[tid];
-            dg[n + tid] = ee[tid];
         }
     }
     __syncthreads();
@@ -1129,13 +1155,9 @@ static cudaError_t launch_e1(const SigmaArgs& a, int n_env, cudaStream_t st) {
 // Cluster width of E1 (CTAs per matrix).  Few matrices: spread each one over 4 SMs (latency); many matrices
 // (batched environments, the offline schedule): 2 SMs each, which still fills the machine.
 static int e1_cluster_override() {  // COVO_E1_CLUSTER = 2 | 4 | 8 pins the cluster width (tuning, tests)
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("COVO_E1_CLUSTER");
-        v = e ? atoi(e) : 0;
-        if (v != 2 && v != 4 && v != 8) v = 0;
-    }
-    return v;
+    const char* e = getenv("COVO_E1_CLUSTER");
+    const int v = e ? atoi(e) : 0;
+    return (v == 2 || v == 4 || v == 8) ? v : 0;
 }
 
 cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
@@ -1168,7 +1190,9 @@ cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
     size_t smem = trifunc_smem(a.n);
     e = ensure_smem_attr(sigma_trifunc_kernel, smem, conf);
     if (e != cudaSuccess) return e;
-    sigma_trifunc_kernel<<<n_env, TT, smem, st>>>(a);
+    // CTAs per matrix: the scalar stages are repeated by each of them, the rows of F are shared out
+    const int nb = (n_env <= 18) ? 8 : (n_env <= 74 ? 2 : 1);
+    sigma_trifunc_kernel<<<dim3(nb, n_env), TT, smem, st>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dim3 g((a.n + kSwI - 1) / kSwI, (a.n + kSwJ - 1) / kSwJ, n_env);

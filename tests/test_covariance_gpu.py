@@ -95,3 +95,42 @@ def test_sigma_batched_envs():
     for e in range(E):
         So = o.optimize_sigma(R[e].astype(np.float64), 0.5, np.float64)
         assert np.linalg.norm(S[e] - So) / np.linalg.norm(So) < 2e-5
+
+
+@pytest.mark.parametrize("nc", [2, 4, 8])
+def test_sigma_cluster_widths_agree(nc, monkeypatch):
+    """The tridiagonalisation spreads one matrix over 2, 4 or 8 CTAs of a cluster (batched environments use the
+    narrow ones): every width must deliver the same covariance at the headline size n = 200."""
+    p, ns, a_mean, rng = scenario("tracking_zigzag", seed=3, H=50, warm_steps=20)
+    R = o.get_hessian(ns, a_mean, p, dtype=np.float64).astype(np.float32)
+    So = o.optimize_sigma(R.astype(np.float64), 0.5, np.float64)
+    monkeypatch.setenv("COVO_E1_CLUSTER", str(nc))
+    h = _handle(64, 50, ns.pos_traj.shape[0])
+    S = h.optimize_sigma(R[None])[0]
+    assert np.linalg.norm(S - So) / np.linalg.norm(So) < 1e-5
+    assert np.abs(S - S.T).max() == 0.0
+    d, e, sc = h.debug_tridiag()
+    T = np.diag(d) + np.diag(e[:-1], 1) + np.diag(e[:-1], -1)
+    w = np.linalg.eigvalsh(((R + R.T) / 2).astype(np.float64))
+    assert np.abs(np.linalg.eigvalsh(T) - w).max() < 2e-5 * max(1, np.abs(w).max())
+    assert abs(sc[0] - np.linalg.eigvalsh(T)[0]) < 1e-9
+
+
+def test_sigma_many_matrices_batched():
+    """40 matrices at once (environment batch / offline schedule): the 2-CTA path of E1 and the 2-CTA path of E2."""
+    from covo_mpc_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    H, E = 20, 40
+    n = 4 * H
+    h = _handle(64, H, 300, n_env=E)
+    A = rng.standard_normal((E, n, n)).astype(np.float32)
+    R = A + A.transpose(0, 2, 1)
+    S = h.optimize_sigma(R)
+    L = h.cholesky(S)
+    for e in (0, 7, 39):
+        So = o.optimize_sigma(R[e].astype(np.float64), 0.5, np.float64)
+        assert np.linalg.norm(S[e] - So) / np.linalg.norm(So) < 2e-5
+        Lo = np.linalg.cholesky(S[e].astype(np.float64))
+        assert np.abs(L[e] - Lo).max() < 2e-6 * max(1, np.abs(Lo).max())
+    assert (h.status() == 0).all()
