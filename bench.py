@@ -111,9 +111,12 @@ def algorithmic_bytes(n, H, N, parity=False):
     nn = 4 * n * n
     rollout = nn // 2 + 4 * 4 * n + 4 * (H + 1) * 6 + 96 + 2 * 4 * n + (4 * N * n if parity else 0)
     return {
-        "hessian": 96 + 4 * n + 4 * H * 6 + 2 * 4 * H * (14 * 153 + 14 * 17) + nn,  # state, mean, ref; workspace w+r; R
-        "sigma": nn + nn + 4 * n + nn + 2 * (2 * nn),  # R in; Vh, tau, F out; two apply-Q passes (read F/Z + Vh, write Z/cov)
-        "cholesky": nn + nn + nn + nn // 2,  # cov in, symmetrised cov out, L out, packed factor out
+        # state, mean, ref; per-step derivative records written + read; [A|B], S, D hand-over written + read; R
+        "hessian": 96 + 4 * n + 4 * H * 6 + 2 * 4 * H * (14 * 153 + 14 * 17) + 2 * 4 * H * 328 + nn,
+        "tridiag": nn + nn + 2 * 8 * n,  # R in; Q^T out; (d, e) fp64 out
+        "trifunc": 2 * 8 * n + nn,       # (d, e) in; F out (full symmetric)
+        "sandwich": nn + nn + nn,        # Q^T, F in; Sigma out
+        "cholesky": nn + nn // 2,        # Sigma in; packed factor out
         "rollout": rollout,
     }
 
@@ -265,7 +268,7 @@ def run_gpu(args):
                "ms_per_step": 1e3 * float(tt.item()) / K}
         ctl.close()
 
-    launches_per_step = {"covo-online": 7, "covo-offline": 1, "mppi": 2}[mode_name] + (1 if shard == "nsample" else 0)
+    launches_per_step = {"covo-online": 8, "covo-offline": 1, "mppi": 2}[mode_name] + (1 if shard == "nsample" else 0)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak" if shard == "env" else "strong",
@@ -291,7 +294,8 @@ def run_gpu(args):
     if os.path.exists(tp):
         traffic = json.load(open(tp))
     if kernel_ms is not None:
-        per = {"hessian": kernel_ms[0], "sigma": kernel_ms[2], "cholesky": kernel_ms[4], "rollout": kernel_ms[5]}
+        per = {"hessian": kernel_ms[0], "tridiag": kernel_ms[1], "trifunc": kernel_ms[2], "sandwich": kernel_ms[3],
+               "cholesky": kernel_ms[4], "rollout": kernel_ms[5]}
         dom = max(per, key=per.get)
         rl = {}
         for k, ms in per.items():
@@ -299,7 +303,8 @@ def run_gpu(args):
             rl[k] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(k),
                      "ms": float(ms), "algorithmic_bytes": ab[k], "share_of_step": float(ms / sum(per.values()))}
         out["roofline"] = dict(rl[dom], kernel=dom, peak_source=peak_src,
-                               note="latency-bound serial factorisation by construction (SURVEY 8d): HBM traffic is ~0.5 MB per step")
+                               note="latency-bound serial factorisation by construction (SURVEY 8d): 198 dependent Householder steps, "
+                                    "one DSMEM exchange each; HBM traffic is ~0.3 MB per launch")
         out["roofline_kernels"] = rl
         flops = N_SAMPLES * n * (n + 1) + N_SAMPLES * HORIZON * 200 + 2 * N_SAMPLES * n
         out["rollout_fp32"] = {"algorithmic_gflop": flops / 1e9, "achieved_tflops": flops / (per["rollout"] * 1e-3) / 1e12,

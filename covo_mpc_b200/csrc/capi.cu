@@ -256,9 +256,11 @@ struct Prof {
 int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = false) {
     SigmaArgs sa = sigma_args(h);
     if (!want_L) sa.L = nullptr;  // the sampler only needs the packed factor
-    // sigma: tridiag+rational, then the two apply-Q passes; mark after the tridiag kernel is not possible
-    // without splitting launch_sigma, so the pipeline is timed as [tridiag][applyQ x2] via two events inside.
-    CK(launch_sigma(sa, h->E, st));
+    CK(launch_tridiag(sa, h->E, st));
+    if (pf) pf->mark(2);
+    CK(launch_trifunc(sa, h->E, st));
+    if (pf) pf->mark(3);
+    CK(launch_sandwich(sa, h->E, st));
     if (pf) pf->mark(4);
     sa.cov_symmetric = 1;
     CK(launch_cholesky(sa, h->E, st));
@@ -280,8 +282,6 @@ int step_common(covo_handle* h, const float* st_d, const int* tm_d, const float*
         HessianArgs ha = hess_args(h, st_d, tm_d, h->a_mean.p, 1, h->R.p, h->hess_ws.p, (long long)h->T * 3);
         CK(launch_hessian(ha, h->E, st));
         pf.mark(1);
-        pf.mark(2);
-        pf.mark(3);
         int rc = run_sigma_chol(h, st, &pf);
         if (rc) return rc;
     } else {
@@ -924,18 +924,13 @@ int covo_get_kernel_ms(covo_handle* h, float* ms6) {
     if (!h->profiling) return fail(COVO_ERR_INVALID, "profiling is off");
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaEventSynchronize(h->ev[6]));
-    // boundaries: 0 start | 1..3 hessian (local+assemble reported together in slot 0) | 4 sigma | 5 cholesky | 6 rollout
-    float t = 0.f;
-    CK(cudaEventElapsedTime(&t, h->ev[0], h->ev[3]));
-    ms6[0] = t;
-    ms6[1] = 0.f;
-    CK(cudaEventElapsedTime(&t, h->ev[3], h->ev[4]));
-    ms6[2] = t;
-    ms6[3] = 0.f;
-    CK(cudaEventElapsedTime(&t, h->ev[4], h->ev[5]));
-    ms6[4] = t;
-    CK(cudaEventElapsedTime(&t, h->ev[5], h->ev[6]));
-    ms6[5] = t;
+    // boundaries: 0 start | 1 hessian (3 kernels) | 2 tridiagonalisation | 3 tridiagonal function | 4 sandwich |
+    // 5 cholesky | 6 rollout
+    for (int i = 0; i < 6; ++i) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]));
+        ms6[i] = t;
+    }
     return COVO_OK;
 }
 

@@ -457,20 +457,42 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
         sp = warp_sum(sp);
         if ((tid & 31) == 0) s_S = sp;
     }
+    // V[r] = sum_b scale[b] part[b][r]: thread = (float4 column group, tile group); the tile groups run their
+    // tiles in order with up to 32 float4 loads in flight (the records sit in L2, written by other SMs), then the
+    // groups are added in order -- a fixed summation tree, bit-reproducible.
     float Vr[2] = {0.f, 0.f};
     {
+        const int ncol4 = n_pad >> 2;                       // <= 64
+        const int ngrp = max(1, (int)blockDim.x / ncol4);   // tile groups (4 at n_pad = 208)
+        const int per = (n_cta + ngrp - 1) / ngrp;
+        float* vpart = sm.tile + ((n_cta + 3) & ~3);        // [ngrp][n_pad] behind the scale table
+        const int cg = tid % ncol4, tg = tid / ncol4;
+        if (tg < ngrp) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int b_lo = tg * per, b_hi = min(b_lo + per, n_cta);
+            for (int b0 = b_lo; b0 < b_hi; b0 += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    v[j] = (b0 + j < b_hi) ? __ldcg(reinterpret_cast<const float4*>(base + (long long)(b0 + j) * rec + kPartialHdr) + cg)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (b0 + j < b_hi) {
+                        const float sc = scale[b0 + j];
+                        acc.x = fmaf(v[j].x, sc, acc.x);
+                        acc.y = fmaf(v[j].y, sc, acc.y);
+                        acc.z = fmaf(v[j].z, sc, acc.z);
+                        acc.w = fmaf(v[j].w, sc, acc.w);
+                    }
+            }
+            *reinterpret_cast<float4*>(vpart + tg * n_pad + 4 * cg) = acc;
+        }
+        __syncthreads();
         int slot = 0;
         for (int r = tid; r < n_pad; r += blockDim.x, ++slot) {
             float V = 0.f;
-            for (int b0 = 0; b0 < n_cta; b0 += 16) {
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    v[j] = (b0 + j < n_cta) ? __ldcg(base + (long long)(b0 + j) * rec + kPartialHdr + r) : 0.f;
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (b0 + j < n_cta) V = fmaf(v[j], scale[b0 + j], V);
-            }
+            for (int g = 0; g < ngrp; ++g) V += vpart[g * n_pad + r];
             if (slot < 2) Vr[slot] = V;
         }
     }

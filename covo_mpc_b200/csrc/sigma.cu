@@ -1160,7 +1160,7 @@ static int e1_cluster_override() {  // COVO_E1_CLUSTER = 2 | 4 | 8 pins the clus
     return (v == 2 || v == 4 || v == 8) ? v : 0;
 }
 
-cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
+cudaError_t launch_tridiag(const SigmaArgs& a, int n_env, cudaStream_t st) {
     if (a.n > kSigmaMaxN || (a.n & 3)) return cudaErrorInvalidValue;
     cudaError_t e;
     int nc = e1_cluster_override() ? e1_cluster_override() : (n_env <= 18 ? 8 : (n_env <= 37 ? 4 : 2));
@@ -1185,7 +1185,12 @@ cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
             default: e = launch_e1<7, 2>(a, n_env, st); break;
         }
     }
-    if (e != cudaSuccess) return e;
+    return e;
+}
+
+cudaError_t launch_trifunc(const SigmaArgs& a, int n_env, cudaStream_t st) {
+    if (a.n > kSigmaMaxN || (a.n & 3)) return cudaErrorInvalidValue;
+    cudaError_t e;
     static size_t conf[32] = {};
     size_t smem = trifunc_smem(a.n);
     e = ensure_smem_attr(sigma_trifunc_kernel, smem, conf);
@@ -1193,8 +1198,12 @@ cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
     // CTAs per matrix: the scalar stages are repeated by each of them, the rows of F are shared out
     const int nb = (n_env <= 18) ? 8 : (n_env <= 74 ? 2 : 1);
     sigma_trifunc_kernel<<<dim3(nb, n_env), TT, smem, st>>>(a);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sandwich(const SigmaArgs& a, int n_env, cudaStream_t st) {
+    if (a.n > kSigmaMaxN || (a.n & 3)) return cudaErrorInvalidValue;
+    cudaError_t e;
     dim3 g((a.n + kSwI - 1) / kSwI, (a.n + kSwJ - 1) / kSwJ, n_env);
     const size_t sw_bytes = sandwich_smem_bytes(a.n);
     static size_t conf_sw[32] = {};
@@ -1202,6 +1211,13 @@ cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     sandwich_kernel<<<g, kSwThreads, sw_bytes, st>>>(a.Qt, a.F, a.cov, a.n);
     return cudaGetLastError();
+}
+
+cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
+    cudaError_t e = launch_tridiag(a, n_env, st);
+    if (e == cudaSuccess) e = launch_trifunc(a, n_env, st);
+    if (e == cudaSuccess) e = launch_sandwich(a, n_env, st);
+    return e;
 }
 
 cudaError_t launch_cholesky(const SigmaArgs& a, int n_env, cudaStream_t st) {

@@ -31,7 +31,10 @@ void zolotarev_nodes(double m, double M, int N, double* t, double* w);
 void zolotarev_table(double* table /* [kZoloLadder][2][kZoloPoles] */);
 double zolotarev_ladder_M(int i);
 
-cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st);     // R -> cov
+cudaError_t launch_tridiag(const SigmaArgs& a, int n_env, cudaStream_t st);   // E1: R -> (d, e), Q^T
+cudaError_t launch_trifunc(const SigmaArgs& a, int n_env, cudaStream_t st);   // E2: (d, e) -> F
+cudaError_t launch_sandwich(const SigmaArgs& a, int n_env, cudaStream_t st);  // E3: Q F Q^T -> cov
+cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st);     // E1 + E2 + E3: R -> cov
 cudaError_t launch_cholesky(const SigmaArgs& a, int n_env, cudaStream_t st);  // cov -> L, Lt (and symmetrise cov)
 
 }  // namespace covo

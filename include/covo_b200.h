@@ -134,7 +134,8 @@ int covo_debug_tridiag(covo_handle* h, double* d, double* e, double* scalars5); 
 int covo_zolotarev_nodes(double m, double M, int n_poles, double* shifts, double* weights); /* host only, no GPU */
 int covo_get_status(covo_handle* h, int* status); /* [E] numeric status of the last covariance step */
 /* Per-kernel device time of the last instrumented step, CUDA events on the launch stream.
- * slots: 0 hessian-local, 1 hessian-assemble, 2 tridiag+rational, 3 apply-Q (both), 4 cholesky, 5 rollout */
+ * slots: 0 hessian (local + assemble + forward chains), 1 tridiagonalisation (cluster), 2 tridiagonal matrix function,
+ *        3 Sigma = Q F Q^T, 4 cholesky, 5 rollout */
 int covo_set_profiling(covo_handle* h, int on);
 int covo_get_kernel_ms(covo_handle* h, float* ms6);
 /* Debug: switch in-kernel clock64() phase stamps on/off and read the 64 slots of the last step (may be NULL). */

@@ -31,7 +31,7 @@ def main():
         h.step(states[i], times[i:i + 1])
         acc += h.kernel_ms()
     h.set_profiling(False)
-    names = ["hess_local+assemble", "(1)", "sigma (tridiag+applyq x2)", "(3)", "cholesky", "rollout"]
+    names = ["hessian (3 kernels)", "E1 tridiag (cluster)", "E2 trifunc", "E3 sandwich", "cholesky", "rollout"]
     print("kernel ms (CUDA events, mean of 6):", {k: round(float(v) / 6, 4) for k, v in zip(names, acc)})
     h.phase_clocks(True)
     h.step(states[10], times[10:11])
