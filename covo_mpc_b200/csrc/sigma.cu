@@ -946,7 +946,7 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int n = a.n, n_pad = a.n_pad, tid = threadIdx.x, env = blockIdx.x, lane = tid & 31, warp = tid >> 5;
     float* As = reinterpret_cast<float*>(smraw);  // [n][n]
-    float* Lp = As + n * n;                       // [8][n_pad]  panel, transposed
+    float* Lp = As + n * n;                       // panel buffers, see below
     float* covg = a.cov + (long long)env * n * n;
     COVO_STAMP(a, 23);
     // (a_cov + a_cov.T)/2, controllers/covo.py:132, in ONE pass: the row part of a float4 is read coalesced, its
@@ -1002,14 +1002,20 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
     }
     __syncthreads();
     COVO_STAMP(a, 24);
-    for (int jb = 0; jb < n; jb += 8) {
-        const int nb = min(8, n - jb);
-        if (jb == 8) COVO_STAMP(a, 26);
-        // (a) + (b): every row thread of the panel factors the 8x8 diagonal block PRIVATELY in registers (170
-        // dependent-ish FMAs, no shuffles, no broadcast, no barrier) and goes straight on to its row of
-        // L21 = A21 L11^-T.  Thread 0 also writes the factored block back.
+    // Right-looking blocked factorisation (NB = 8) with LOOK-AHEAD: while the other warps apply panel p to the
+    // trailing matrix, the eight "panel warps" first update the 8 columns of panel p+1, then factor its diagonal
+    // block (privately, in registers: no shuffles, no broadcast) and solve its rows, so the serial part of a step
+    // hides behind the rank-8 update.  The panel chain is bound by its instruction count and by the shared-memory
+    // hand-overs between its stages (NB = 4 was measured slower: twice the hand-overs); it owns the highest warp
+    // ids because the warp scheduler favours them.
+    constexpr int kPanelThreads = 256;
+    float* LpA = Lp;                 // [8][n_pad] panel, transposed (double-buffered)
+    float* LpB = Lp + 8 * n_pad;
+    float* Lp8 = LpB + 8 * n_pad;    // [8][8] factored diagonal block, parked until its rows are no longer being read
+    const int pt = tid - (TC - kPanelThreads);
+    auto factor_panel = [&](int jb, int nb, float* LpOut) {
         const int nrows = n - jb - nb;
-        if (tid < max(nrows, 1)) {
+        if (pt < max(nrows, 1)) {
             float d[8][8], linv[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
@@ -1038,18 +1044,8 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
 #pragma unroll
                     for (int r = c2; r < 8; ++r) d[r][c2] = fmaf(-d[r][c], d[c2][c], d[r][c2]);
             }
-            if (tid == 0) {
-                if (bad) a.status[env] = 2;
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if (r < nb) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            if (c < nb) As[(jb + r) * n + jb + c] = (c <= r) ? d[r][c] : 0.f;
-                    }
-            }
-            if (tid < nrows) {
-                const int i = jb + nb + tid;
+            if (pt < nrows) {
+                const int i = jb + nb + pt;
                 float x[8];
                 const float4 p0 = *reinterpret_cast<const float4*>(As + i * n + jb);
                 x[0] = p0.x; x[1] = p0.y; x[2] = p0.z; x[3] = p0.w;
@@ -1069,43 +1065,104 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
                 *reinterpret_cast<float4*>(As + i * n + jb) = make_float4(x[0], x[1], x[2], x[3]);
                 if (nb == 8) *reinterpret_cast<float4*>(As + i * n + jb + 4) = make_float4(x[4], x[5], x[6], x[7]);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) Lp[c * n_pad + i] = x[c];
+                for (int c = 0; c < 8; ++c) LpOut[c * n_pad + i] = x[c];
+            }
+            if (pt == 0) {
+                if (bad) a.status[env] = 2;
+                // the block rows are still being read by the other row threads: park the factor, write back later
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) Lp8[r * 8 + c] = (c <= r) ? d[r][c] : 0.f;
             }
         }
-        __syncthreads();
-        // (c) trailing update on the lower-triangle 4x4 tiles
-        const int r0 = jb + nb;
-        const int T = (n - r0) >> 2;
-        const int ntiles = T * (T + 1) / 2;
-        for (int q = tid; q < ntiles; q += TC) {
-            int ti = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
-            while (ti * (ti + 1) / 2 > q) --ti;
-            while ((ti + 1) * (ti + 2) / 2 <= q) ++ti;
-            const int tk = q - ti * (ti + 1) / 2;
-            const int i = r0 + 4 * ti, kk = r0 + 4 * tk;
-            float o[4][4];
+    };
+    // prologue: panel 0
+    if (pt >= 0) factor_panel(0, min(8, n), LpA);
+    __syncthreads();
+    for (int jb = 0, it = 0; jb < n; jb += 8, ++it) {
+        const int nb = min(8, n - jb);
+        float* LpCur = (it & 1) ? LpB : LpA;
+        float* LpNext = (it & 1) ? LpA : LpB;
+        if (jb == 8) COVO_STAMP(a, 26);
+        // the factored diagonal block of panel jb (parked by panel thread 0) goes back into As
+        if (pt >= 0 && pt < 64) {
+            const int r = pt >> 3, c = pt & 7;
+            if (r < nb && c < nb) As[(jb + r) * n + jb + c] = Lp8[pt];
+        }
+        const int r0 = jb + nb;           // first row / column of the trailing matrix
+        if (r0 >= n) break;
+        const int nbn = min(8, n - r0);   // width of the next panel
+        if (pt >= 0) {
+            // (1) rank-8 update of the strip: rows i >= r0, columns r0 .. r0 + nbn - 1
+            const int i = r0 + pt;
+            if (i < n) {
+                float x[8];
+                const float4 p0 = *reinterpret_cast<const float4*>(As + i * n + r0);
+                x[0] = p0.x; x[1] = p0.y; x[2] = p0.z; x[3] = p0.w;
+                if (nbn == 8) {
+                    const float4 p1 = *reinterpret_cast<const float4*>(As + i * n + r0 + 4);
+                    x[4] = p1.x; x[5] = p1.y; x[6] = p1.z; x[7] = p1.w;
+                } else {
+                    x[4] = x[5] = x[6] = x[7] = 0.f;
+                }
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const float4 av = *reinterpret_cast<const float4*>(As + (i + r) * n + kk);
-                o[r][0] = av.x; o[r][1] = av.y; o[r][2] = av.z; o[r][3] = av.w;
+                for (int k = 0; k < 8; ++k) {
+                    const float li = LpCur[k * n_pad + i];
+                    const float4 l0 = *reinterpret_cast<const float4*>(LpCur + k * n_pad + r0);
+                    x[0] = fmaf(-li, l0.x, x[0]); x[1] = fmaf(-li, l0.y, x[1]);
+                    x[2] = fmaf(-li, l0.z, x[2]); x[3] = fmaf(-li, l0.w, x[3]);
+                    if (nbn == 8) {
+                        const float4 l1 = *reinterpret_cast<const float4*>(LpCur + k * n_pad + r0 + 4);
+                        x[4] = fmaf(-li, l1.x, x[4]); x[5] = fmaf(-li, l1.y, x[5]);
+                        x[6] = fmaf(-li, l1.z, x[6]); x[7] = fmaf(-li, l1.w, x[7]);
+                    }
+                }
+                *reinterpret_cast<float4*>(As + i * n + r0) = make_float4(x[0], x[1], x[2], x[3]);
+                if (nbn == 8) *reinterpret_cast<float4*>(As + i * n + r0 + 4) = make_float4(x[4], x[5], x[6], x[7]);
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // panel warps only
+            // (2) factor panel p+1 while the other warps are busy with the trailing update
+            factor_panel(r0, nbn, LpNext);
+        } else {
+            // (c) trailing update on the lower-triangle 4x4 tiles right of the strip: 64 packed FFMA2 per tile
+            const int c0 = r0 + nbn;
+            const int T = (n - c0) >> 2;  // n, r0, nbn are multiples of 4
+            const int ntiles = T * (T + 1) / 2;
+            for (int q = tid; q < ntiles; q += TC - kPanelThreads) {
+                int ti = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+                while (ti * (ti + 1) / 2 > q) --ti;
+                while ((ti + 1) * (ti + 2) / 2 <= q) ++ti;
+                const int tk = q - ti * (ti + 1) / 2;
+                const int i = c0 + 4 * ti, kk = c0 + 4 * tk;
+                float2 o[4][2];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 li = *reinterpret_cast<const float4*>(Lp + c * n_pad + i);
-                const float4 lk = *reinterpret_cast<const float4*>(Lp + c * n_pad + kk);
-                const float lir[4] = {li.x, li.y, li.z, li.w};
-                const float lkr[4] = {lk.x, lk.y, lk.z, lk.w};
+                for (int r = 0; r < 4; ++r) {
+                    const float4 av = *reinterpret_cast<const float4*>(As + (i + r) * n + kk);
+                    o[r][0] = make_float2(av.x, av.y);
+                    o[r][1] = make_float2(av.z, av.w);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 li = *reinterpret_cast<const float4*>(LpCur + c * n_pad + i);
+                    const float4 lk = *reinterpret_cast<const float4*>(LpCur + c * n_pad + kk);
+                    const float lir[4] = {-li.x, -li.y, -li.z, -li.w};
+                    const float2 lk0 = make_float2(lk.x, lk.y), lk1 = make_float2(lk.z, lk.w);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float2 l2 = make_float2(lir[r], lir[r]);
+                        o[r][0] = __ffma2_rn(l2, lk0, o[r][0]);
+                        o[r][1] = __ffma2_rn(l2, lk1, o[r][1]);
+                    }
+                }
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) o[r][cc] = fmaf(-lir[r], lkr[cc], o[r][cc]);
+                    *reinterpret_cast<float4*>(As + (i + r) * n + kk) = make_float4(o[r][0].x, o[r][0].y, o[r][1].x, o[r][1].y);
             }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                *reinterpret_cast<float4*>(As + (i + r) * n + kk) = make_float4(o[r][0], o[r][1], o[r][2], o[r][3]);
         }
         __syncthreads();
     }
+    __syncthreads();
     COVO_STAMP(a, 25);
     // outputs: row-major L (upper part zeroed) and the packed k-major factor
     if (a.L) {
@@ -1129,7 +1186,7 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
 static size_t trifunc_smem(int n) {
     return (size_t)trifunc_region_floats(n) * 4 + 256 * 8 * 3 + 16 * 8 + 64 * 8 + 16;
 }
-static size_t chol_smem(int n) { return (size_t)n * n * 4 + (size_t)8 * round_up8(n) * 4; }
+static size_t chol_smem(int n) { return (size_t)n * n * 4 + (size_t)(2 * 8 * round_up8(n) + 64) * 4; }
 
 template <int C2, int NC>
 static cudaError_t launch_e1(const SigmaArgs& a, int n_env, cudaStream_t st) {
