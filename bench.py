@@ -340,7 +340,7 @@ def cpu_baseline(states_h, times_h, traj, budget_s=20.0, mode_name="covo-online"
     n = 4 * HORIZON
     t_used, done = 0.0, 0
     i = 0
-    cores = os.cpu_count() if fast else 1
+    cores = oracle_c.num_threads() if fast else 1  # OpenMP threads the port actually runs on
     a_cov = None
     while True:
         s = states_h[i % len(states_h)]
@@ -374,6 +374,16 @@ def run_reference(args):
     if rank != 0:
         return
     K, W = args.steps, args.warmup
+    # all host threads this process may use: torchrun exports OMP_NUM_THREADS=1, which would silently serialise the
+    # OpenMP loops of the port (libgomp reads it when the library is first loaded, i.e. below) and LAPACK/BLAS
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(ncores)
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=ncores)
+    except Exception:
+        pass
     # states: a fixed synthetic sequence (no GPU needed): hover-ish noisy states along a zigzag reference
     from oracle import oracle_np as o
 
