@@ -268,6 +268,18 @@ def run_gpu(args):
                "ms_per_step": 1e3 * float(tt.item()) / K}
         ctl.close()
 
+    # ---- device-resident closed loop: controller + environment step, no host round trip -----
+    closed = None
+    if shard == "env":
+        h.set_mean(np.tile(np.array([(0.027 * 9.81 / 0.8) * 2 - 1, 0, 0, 0], np.float32), (1, HORIZON, 1)))
+        h.env_reset(states_h[0][None], times_h[:1])
+        h.closed_loop(W, noise_seed=seed)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, _, err_cl = h.closed_loop(K, noise_seed=seed + 1)
+        tc = time.perf_counter() - t0
+        closed = {"value": K * world / tc, "unit": UNIT, "ms_per_step": 1e3 * tc / K, "mean_err_pos": float(err_cl.mean()),
+                  "note": "covo_closed_loop: K x [noisy state -> controller -> Quad3D.step_env] on the device, one D2H of the logs at the end (wall clock)"}
     launches_per_step = {"covo-online": 8, "covo-offline": 1, "mppi": 2}[mode_name] + (1 if shard == "nsample" else 0)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -285,6 +297,8 @@ def run_gpu(args):
     }
     if e2e:
         out["e2e"] = e2e
+    if closed:
+        out["closed_loop"] = closed
     # ---- roofline ---------------------------------------------------------------------------------------
     peak, peak_src = measured_peaks()
     n = 4 * HORIZON

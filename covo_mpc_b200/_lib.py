@@ -77,6 +77,10 @@ _SIGNATURES = {
     "covo_get_kernel_ms": [_H, _F],
     "covo_debug_phase_clocks": [_H, C.c_int, C.POINTER(C.c_longlong)],
     "covo_rng_step": [_H, C.POINTER(C.c_uint)],
+    "covo_env_reset": [_H, _F, _I],
+    "covo_env_get_state": [_H, _F, _I],
+    "covo_env_step": [_H, _F, _F, C.c_ulonglong, C.c_uint, C.c_int, C.c_float, C.c_float, _F, _F, _F, _I],
+    "covo_closed_loop": [_H, C.c_int, C.c_ulonglong, C.c_int, C.c_float, C.c_float, _F, _F, _F, _F],
     "covo_local_samples": [_H, _I, _I],
 }
 EXPORTED = sorted(list(_SIGNATURES) + ["covo_last_error", "covo_version"])
@@ -274,6 +278,49 @@ class Handle:
         check(self.lib.covo_rollout(self._h, fptr(s), iptr(t), fptr(a), int(shift), fptr(e), fptr(fd), fptr(a_out),
                                     fptr(act), fptr(costs), fptr(samples)))
         return a_out, act, costs, samples
+
+    # -- device-resident environment / closed loop ----------------------------------
+    def env_reset(self, state24, time):
+        s, t = f32(state24), i32(time)
+        if s.size != self.E * 24 or t.size != self.E:
+            raise ValueError("state24 / time have the wrong size")
+        check(self.lib.covo_env_reset(self._h, fptr(s), iptr(t)))
+
+    def env_state(self):
+        s = np.empty((self.E, 24), dtype=np.float32)
+        t = np.empty(self.E, dtype=np.int32)
+        check(self.lib.covo_env_get_state(self._h, fptr(s), iptr(t)))
+        return s, t
+
+    def env_step(self, action, noise=None, noise_seed=0, noise_step=0, gaussian=False, obs_noise_scale=0.05, dyn_noise_scale=0.05):
+        """One Quad3D.step_env + get_info transition on the device (action None: only the noisy copy of the state).
+        Returns (noisy24 [E][24], reward [E], err_pos [E], done [E]); the last three describe the PRE-step state."""
+        a = None if action is None else f32(action)
+        if a is not None and a.size != self.E * 4:
+            raise ValueError("action must be [E][4]")
+        z = None if noise is None else f32(noise)
+        if z is not None and z.size != self.E * 16:
+            raise ValueError("noise must be [E][16]")
+        noisy = np.empty((self.E, 24), dtype=np.float32)
+        rew = np.zeros(self.E, dtype=np.float32)
+        err = np.zeros(self.E, dtype=np.float32)
+        done = np.zeros(self.E, dtype=np.int32)
+        check(self.lib.covo_env_step(self._h, fptr(a), fptr(z), int(noise_seed), int(noise_step), int(gaussian), float(obs_noise_scale),
+                                     float(dyn_noise_scale), fptr(noisy), fptr(rew), fptr(err), iptr(done)))
+        return noisy, rew, err, done
+
+    def closed_loop(self, n_steps, noise=None, noise_seed=0, gaussian=False, obs_noise_scale=0.05, dyn_noise_scale=0.05):
+        """n_steps x [controller (production RNG) -> env step] without a host round trip.
+        Returns (actions [n][E][4], rewards [n][E], err_pos [n][E])."""
+        z = None if noise is None else f32(noise)
+        if z is not None and z.size != (n_steps + 1) * self.E * 16:
+            raise ValueError("noise must be [n_steps+1][E][16]")
+        act = np.empty((n_steps, self.E, 4), dtype=np.float32)
+        rew = np.empty((n_steps, self.E), dtype=np.float32)
+        err = np.empty((n_steps, self.E), dtype=np.float32)
+        check(self.lib.covo_closed_loop(self._h, int(n_steps), int(noise_seed), int(gaussian), float(obs_noise_scale), float(dyn_noise_scale),
+                                        fptr(z), fptr(act), fptr(rew), fptr(err)))
+        return act, rew, err
 
     # -- introspection ------------------------------------------------------------------------------
     def enable_pos_stats(self, on=True):

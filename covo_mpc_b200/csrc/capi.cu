@@ -14,6 +14,7 @@
 #include "offline.cuh"
 #include "rng.cuh"
 #include "sigma.cuh"
+#include "envstep.cuh"
 
 using namespace covo;
 
@@ -117,6 +118,10 @@ struct covo_handle {
     DevBuf<unsigned int> counters;
     DevBuf<long long> prof;
     bool phase_clocks = false;
+    // device-resident environment (caller side of the hot path)
+    DevBuf<float> env_state24, env_noisy24, env_noise, env_log_f, env_action;
+    DevBuf<int> env_time, env_noisy_time, env_done;
+    bool env_ready = false;
     // pinned staging
     float* h_state = nullptr;
     int* h_time = nullptr;
@@ -142,6 +147,8 @@ void release_all(covo_handle* h) {
     h->sched_R.release(); h->sched_Qt.release(); h->sched_F.release();
     h->sched_ws.release(); h->sched_diag.release(); h->sched_times.release(); h->sched_status.release();
     h->partials.release(); h->rank_partial.release(); h->action.release(); h->costs.release();
+    h->env_state24.release(); h->env_noisy24.release(); h->env_noise.release(); h->env_log_f.release(); h->env_action.release();
+    h->env_time.release(); h->env_noisy_time.release(); h->env_done.release();
     h->prof.release(); h->samples.release(); h->pos_stats.release(); h->gathered_scratch.release(); h->counters.release();
     if (h->h_state) cudaFreeHost(h->h_state);
     if (h->h_time) cudaFreeHost(h->h_time);
@@ -647,6 +654,157 @@ int covo_step_device(covo_handle* h, const float* st_d, const int* tm_d, const f
     if (h->cfg.world != 1) return fail(COVO_ERR_INVALID, "world > 1: use covo_step_partial_device + covo_step_merge_device");
     CK(cudaSetDevice(h->cfg.device));
     return step_common(h, st_d, tm_d, eps_d, act_d, (cudaStream_t)stream, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-resident environment and closed loop
+// ---------------------------------------------------------------------------------------------------------
+static int env_alloc(covo_handle* h) {
+    const size_t E = (size_t)h->E;
+    if (h->env_state24.n < E * kStateFloats) {
+        CK(h->env_state24.alloc(E * kStateFloats));
+        CK(h->env_noisy24.alloc(E * kStateFloats));
+        CK(h->env_time.alloc(E));
+        CK(h->env_noisy_time.alloc(E));
+        CK(h->env_done.alloc(E));
+        CK(h->env_action.alloc(E * 4));
+    }
+    return COVO_OK;
+}
+
+static EnvStepArgs env_args(covo_handle* h, int gaussian, float obs_scale, float dyn_scale, unsigned long long seed) {
+    EnvStepArgs a;
+    a.env = h->env;
+    a.n_env = h->E;
+    a.traj_len = h->T;
+    a.traj_stride = (long long)h->T * 3;
+    a.obs_noise_scale = obs_scale;
+    a.dyn_noise_scale = dyn_scale;
+    a.gaussian = gaussian;
+    a.do_step = 1;
+    a.seed = seed;
+    a.stream = 0;
+    a.state24 = h->env_state24.p;
+    a.time = h->env_time.p;
+    a.pos_traj = h->pos_traj.p;
+    a.vel_traj = h->vel_traj.p;
+    a.action = nullptr;
+    a.noise_in = nullptr;
+    a.noisy24 = h->env_noisy24.p;
+    a.noisy_time = h->env_noisy_time.p;
+    a.reward = nullptr;
+    a.err_pos = nullptr;
+    a.done = nullptr;
+    return a;
+}
+
+int covo_env_reset(covo_handle* h, const float* state24, const int* time) {
+    if (!h || !state24 || !time) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    if (int rc = env_alloc(h)) return rc;
+    CK(h2d(h, h->env_state24.p, state24, (size_t)h->E * kStateFloats * sizeof(float)));
+    CK(h2d(h, h->env_time.p, time, (size_t)h->E * sizeof(int)));
+    h->env_ready = true;
+    return COVO_OK;
+}
+
+int covo_env_get_state(covo_handle* h, float* state24, int* time) {
+    if (!h || !state24 || !time) return fail(COVO_ERR_INVALID, "null argument");
+    if (!h->env_ready) return fail(COVO_ERR_INVALID, "covo_env_reset has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(d2h(h, state24, h->env_state24.p, (size_t)h->E * kStateFloats * sizeof(float)));
+    CK(d2h(h, time, h->env_time.p, (size_t)h->E * sizeof(int)));
+    return COVO_OK;
+}
+
+int covo_env_step(covo_handle* h, const float* action, const float* noise, unsigned long long noise_seed, unsigned int noise_step,
+                  int gaussian, float obs_noise_scale, float dyn_noise_scale, float* noisy24, float* reward, float* err_pos,
+                  int* done) {
+    if (!h) return fail(COVO_ERR_INVALID, "null argument");
+    if (!h->env_ready) return fail(COVO_ERR_INVALID, "covo_env_reset has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t E = (size_t)h->E;
+    if (h->env_log_f.n < 2 * E) {
+        h->env_log_f.release();
+        CK(h->env_log_f.alloc(2 * E));
+    }
+    EnvStepArgs a = env_args(h, gaussian, obs_noise_scale, dyn_noise_scale, noise_seed);
+    a.stream = noise_step;
+    a.do_step = action ? 1 : 0;  // NULL action: only the noisy copy of the current state (after a reset)
+    if (action) {
+        CK(h2d(h, h->env_action.p, action, E * 4 * sizeof(float)));
+        a.action = h->env_action.p;
+    }
+    if (noise) {
+        if (h->env_noise.n < E * kEnvNoiseFloats) {
+            h->env_noise.release();
+            CK(h->env_noise.alloc(E * kEnvNoiseFloats));
+        }
+        CK(h2d(h, h->env_noise.p, noise, E * kEnvNoiseFloats * sizeof(float)));
+        a.noise_in = h->env_noise.p;
+    }
+    a.reward = h->env_log_f.p;
+    a.err_pos = h->env_log_f.p + E;
+    a.done = h->env_done.p;
+    CK(launch_env_step(a, h->own_stream));
+    if (noisy24) CK(d2h(h, noisy24, h->env_noisy24.p, E * kStateFloats * sizeof(float)));
+    if (action) {
+        if (reward) CK(d2h(h, reward, h->env_log_f.p, E * sizeof(float)));
+        if (err_pos) CK(d2h(h, err_pos, h->env_log_f.p + E, E * sizeof(float)));
+        if (done) CK(d2h(h, done, h->env_done.p, E * sizeof(int)));
+    }
+    CK(cudaStreamSynchronize(h->own_stream));
+    return COVO_OK;
+}
+
+int covo_closed_loop(covo_handle* h, int n_steps, unsigned long long noise_seed, int gaussian, float obs_noise_scale,
+                     float dyn_noise_scale, const float* noise, float* actions, float* rewards, float* err_pos) {
+    if (!h || n_steps <= 0) return fail(COVO_ERR_INVALID, "bad argument");
+    if (!h->env_ready) return fail(COVO_ERR_INVALID, "covo_env_reset has not been called");
+    if (h->cfg.world != 1) return fail(COVO_ERR_INVALID, "closed loop: world must be 1 (shard environments, not samples)");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->own_stream;
+    const size_t E = (size_t)h->E, S = (size_t)n_steps;
+    // logs: actions [S][E][4] | rewards [S][E] | err_pos [S][E]
+    if (h->env_log_f.n < S * E * 6) {
+        h->env_log_f.release();
+        CK(h->env_log_f.alloc(S * E * 6));
+    }
+    float* act_d = h->env_log_f.p;
+    float* rew_d = act_d + S * E * 4;
+    float* err_d = rew_d + S * E;
+    if (noise) {
+        const size_t cnt = (S + 1) * E * kEnvNoiseFloats;
+        if (h->env_noise.n < cnt) {
+            h->env_noise.release();
+            CK(h->env_noise.alloc(cnt));
+        }
+        CK(h2d(h, h->env_noise.p, noise, cnt * sizeof(float)));
+    }
+    EnvStepArgs a = env_args(h, gaussian, obs_noise_scale, dyn_noise_scale, noise_seed);
+    // the noisy copy of the initial state (quadrotor.py:366-370: reset_env ends with get_info)
+    a.do_step = 0;
+    a.stream = 0;
+    a.noise_in = noise ? h->env_noise.p : nullptr;
+    CK(launch_env_step(a, st));
+    for (int i = 0; i < n_steps; ++i) {
+        float* ai = act_d + (size_t)i * E * 4;
+        int rc = step_common(h, h->env_noisy24.p, h->env_noisy_time.p, nullptr, ai, st, 1);
+        if (rc) return rc;
+        a.do_step = 1;
+        a.stream = (unsigned)(i + 1);
+        a.action = ai;
+        a.noise_in = noise ? h->env_noise.p + (size_t)(i + 1) * E * kEnvNoiseFloats : nullptr;
+        a.reward = rew_d + (size_t)i * E;
+        a.err_pos = err_d + (size_t)i * E;
+        a.done = h->env_done.p;
+        CK(launch_env_step(a, st));
+    }
+    if (actions) CK(d2h(h, actions, act_d, S * E * 4 * sizeof(float)));
+    if (rewards) CK(d2h(h, rewards, rew_d, S * E * sizeof(float)));
+    if (err_pos) CK(d2h(h, err_pos, err_d, S * E * sizeof(float)));
+    CK(cudaStreamSynchronize(st));
+    return COVO_OK;
 }
 
 int covo_step(covo_handle* h, const float* state24, const int* time, const float* eps, float* action) {

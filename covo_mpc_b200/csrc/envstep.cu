@@ -1,0 +1,83 @@
+// Device-resident environment step: the caller side of the hot path, so that a whole closed loop
+// (noisy state -> controller -> env step) runs without a host round trip.
+//
+// Replaces, per environment,
+//   Quad3D.step_env            envs/quadrotor.py:215-248   reward and done of the PRE-step state, then the transition
+//   free_dynamics_3d_bodyrate  dynamics/free.py:114-202    (the same templated quad_step the rollout kernel runs)
+//   disturbances               dynamics/free.py:58-72      "none" -> 0, "gaussian" -> dyn_noise_scale * N(0, I)
+//   Quad3D.get_info            envs/quadrotor.py:314-361   noisy_state = next_state + N(0, (obs_noise_scale * k)^2),
+//                                                          k = 0.25 / 0.5 / 0.02 / 0.5 for pos / vel / quat / omega
+// Not replicated: the auto-reset of BaseEnvironment.step (envs/base.py:27-38); episodes are bounded by the caller
+// (the MPC harness runs exactly max_steps_in_episode steps per episode).
+// Noise: Philox field keyed by (seed, step, environment), or normals supplied by the caller (parity tests).
+#include <cuda_runtime.h>
+
+#include "envstep.cuh"
+#include "rng.cuh"
+
+namespace covo {
+
+__global__ void __launch_bounds__(128) env_step_kernel(const EnvStepArgs a) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n_env) return;
+    float* sg = a.state24 + (long long)e * kStateFloats;
+    QState<float> s;
+    float fd[3], pt[3], vt[3];
+    load_state24(sg, s, fd, pt, vt);
+    int t = a.time[e];
+    float z[kEnvNoiseFloats];
+    if (a.noise_in) {
+#pragma unroll
+        for (int k = 0; k < kEnvNoiseFloats; ++k) z[k] = a.noise_in[(long long)e * kEnvNoiseFloats + k];
+    } else {
+#pragma unroll
+        for (int b = 0; b < kEnvNoiseFloats / 4; ++b) philox_normal4(a.seed, a.stream, (uint32_t)e, (uint32_t)b, z + 4 * b);
+    }
+    if (a.do_step) {
+        // reward / done / err_pos of the PRE-step state (envs/quadrotor.py:243-244)
+        const float ex = pt[0] - s.p[0], ey = pt[1] - s.p[1], ez = pt[2] - s.p[2];
+        if (a.err_pos) a.err_pos[e] = sqrtf(ex * ex + ey * ey + ez * ez);
+        if (a.reward) a.reward[e] = quad_reward(s, pt, vt);
+        if (a.done) a.done[e] = quad_terminal(s, t, a.env) ? 1 : 0;
+        const float* ag = a.action + (long long)e * 4;
+        const float u[4] = {ag[0], ag[1], ag[2], ag[3]};
+        quad_step(s, u, fd, a.env);
+        // f_disturb <- disturb_func (dynamics/free.py:144-147)
+        for (int k = 0; k < 3; ++k) fd[k] = a.gaussian ? a.dyn_noise_scale * z[13 + k] : 0.f;
+        t += 1;
+        const int row = min(t, a.traj_len - 1);  // clamped gather, dynamics/free.py:153-155
+        const float* pr = a.pos_traj + (long long)e * a.traj_stride + (long long)row * 3;
+        const float* vr = a.vel_traj + (long long)e * a.traj_stride + (long long)row * 3;
+        for (int k = 0; k < 3; ++k) {
+            pt[k] = pr[k];
+            vt[k] = vr[k];
+        }
+        for (int k = 0; k < 3; ++k) sg[k] = s.p[k];
+        for (int k = 0; k < 4; ++k) sg[3 + k] = s.q[k];
+        for (int k = 0; k < 3; ++k) sg[7 + k] = s.v[k];
+        for (int k = 0; k < 3; ++k) sg[10 + k] = s.w[k];
+        for (int k = 0; k < 3; ++k) sg[13 + k] = fd[k];
+        for (int k = 0; k < 3; ++k) sg[16 + k] = pt[k];
+        for (int k = 0; k < 3; ++k) sg[19 + k] = vt[k];
+        a.time[e] = t;
+    }
+    // info["noisy_state"] (envs/quadrotor.py:323-351)
+    float* ng = a.noisy24 + (long long)e * kStateFloats;
+    const float sc = a.obs_noise_scale;
+    for (int k = 0; k < 3; ++k) ng[k] = s.p[k] + z[k] * (sc * 0.25f);
+    for (int k = 0; k < 3; ++k) ng[7 + k] = s.v[k] + z[3 + k] * (sc * 0.5f);
+    for (int k = 0; k < 4; ++k) ng[3 + k] = s.q[k] + z[6 + k] * (sc * 0.02f);
+    for (int k = 0; k < 3; ++k) ng[10 + k] = s.w[k] + z[10 + k] * (sc * 0.5f);
+    for (int k = 0; k < 3; ++k) ng[13 + k] = fd[k];
+    for (int k = 0; k < 3; ++k) ng[16 + k] = pt[k];
+    for (int k = 0; k < 3; ++k) ng[19 + k] = vt[k];
+    ng[22] = ng[23] = 0.f;
+    a.noisy_time[e] = t;
+}
+
+cudaError_t launch_env_step(const EnvStepArgs& a, cudaStream_t st) {
+    env_step_kernel<<<(a.n_env + 127) / 128, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace covo

@@ -1,0 +1,34 @@
+// Device-resident environment step (the caller side of the hot path): internal declarations.
+#pragma once
+#include "common.cuh"
+
+namespace covo {
+
+constexpr int kEnvNoiseFloats = 16;  // per environment and step: 13 observation-noise normals + 3 disturbance normals
+
+struct EnvStepArgs {
+    EnvConsts env;
+    int n_env, traj_len;
+    long long traj_stride;   // floats between environments in pos_traj / vel_traj (0: shared)
+    float obs_noise_scale;   // EnvParams3D.obs_noise_scale (0.05)
+    float dyn_noise_scale;   // EnvParams3D.dyn_noise_scale (0.05), used when gaussian != 0
+    int gaussian;            // disturb_type == "gaussian"
+    int do_step;             // 0: only draw the noisy copy of the current state (after a reset)
+    unsigned long long seed;
+    unsigned int stream;     // step counter of the noise field
+    float* state24;          // [E][24] TRUE state, in/out
+    int* time;               // [E] in/out
+    const float* pos_traj;   // [E][T][3]
+    const float* vel_traj;   // [E][T][3]
+    const float* action;     // [E][4]
+    const float* noise_in;   // optional [E][16] normals supplied by the caller (parity mode), else Philox
+    float* noisy24;          // [E][24] out: info["noisy_state"] for the next controller call
+    int* noisy_time;         // [E] out
+    float* reward;           // [E] out, of the PRE-step state
+    float* err_pos;          // [E] out, of the PRE-step state
+    int* done;               // [E] out, of the PRE-step state
+};
+
+cudaError_t launch_env_step(const EnvStepArgs& a, cudaStream_t st);
+
+}  // namespace covo

@@ -33,6 +33,27 @@ def run_episode(env, controller, rng: np.random.Generator, n_steps: Optional[int
     return np.asarray(errs), np.asarray(rews)
 
 
+def run_episode_device(env, controller, rng: np.random.Generator, n_steps: Optional[int] = None,
+                       reset_rng: Optional[np.random.Generator] = None, noise_seed: Optional[int] = None):
+    """The same episode with the environment ON THE DEVICE: reset on the host (trajectory generation), then
+    ``n_steps`` x [noisy state -> controller -> Quad3D.step_env] in one call without a host round trip
+    (``covo_closed_loop``; production RNG for the samples, Philox field for observation noise / disturbances).
+    Returns (err_pos[n_steps], rewards[n_steps]) like run_episode."""
+    params = env.default_params
+    n_steps = n_steps or params.max_steps_in_episode
+    obs, info, state = env.reset(reset_rng if reset_rng is not None else rng, params)
+    control_params = controller.reset(state, params, controller.init_control_params, None)
+    h = controller._sync_reference(state)
+    controller._upload_params(control_params)
+    h.env_reset(state.to_state24()[None], [int(state.time)])
+    seed = int(rng.integers(0, 2 ** 62)) if noise_seed is None else int(noise_seed)
+    _, rew, err = h.closed_loop(n_steps, noise_seed=seed, gaussian=(env.disturb_type == "gaussian"),
+                                obs_noise_scale=params.obs_noise_scale if env.generate_noisy_state else 0.0,
+                                dyn_noise_scale=params.dyn_noise_scale)
+    controller._generation += 1  # the device-resident mean has moved on: stale params objects are refused
+    return err[:, 0], rew[:, 0]
+
+
 def eval_env(env, controller, total_steps: int = 300 * 4 * 10, num_trajs: int = 4, seed: int = 1):
     """quadjax/envs/quadrotor.py:506-591 (PRNGKey(1); num_trajs reference trajectories, each re-used for
     num_eps // num_trajs episodes).  Returns (mean, std, per-episode array)."""

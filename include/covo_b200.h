@@ -133,6 +133,24 @@ int covo_debug_eps(covo_handle* h, unsigned int stream_id, float* eps);  /* the 
 int covo_debug_tridiag(covo_handle* h, double* d, double* e, double* scalars5); /* after covo_optimize_sigma, env 0 */
 int covo_zolotarev_nodes(double m, double M, int n_poles, double* shifts, double* weights); /* host only, no GPU */
 int covo_get_status(covo_handle* h, int* status); /* [E] numeric status of the last covariance step */
+/* ---- device-resident environment and closed loop -------------------------------------------
+ * The caller side of the hot path on the device, so that noisy state -> controller -> env step runs without a
+ * host round trip.  Replaces Quad3D.step_env (envs/quadrotor.py:215-248: reward/done of the PRE-step state, then
+ * free_dynamics_3d_bodyrate, dynamics/free.py:114-202) and Quad3D.get_info (envs/quadrotor.py:314-361: the noisy
+ * state the next controller call plans from).  No auto-reset (envs/base.py:27-38): episodes are bounded by the caller.
+ * `noise`: 16 standard normals per environment and step (13 observation noise: pos3 vel3 quat4 omega3; 3 disturbance
+ * force) supplied by the caller, or NULL -> Philox field keyed by (noise_seed, step, environment). */
+int covo_env_reset(covo_handle* h, const float* state24, const int* time);   /* [E][24], [E]: the TRUE state */
+int covo_env_get_state(covo_handle* h, float* state24, int* time);
+/* one transition; action == NULL only draws the noisy copy of the current state (what reset_env's get_info does) */
+int covo_env_step(covo_handle* h, const float* action, const float* noise, unsigned long long noise_seed,
+                  unsigned int noise_step, int gaussian_disturbance, float obs_noise_scale, float dyn_noise_scale,
+                  float* noisy24, float* reward, float* err_pos, int* done);
+/* n_steps x [controller call (production RNG) -> env step], all on the device; noise: [n_steps+1][E][16] or NULL.
+ * Outputs (host, optional): actions [n_steps][E][4], rewards / err_pos [n_steps][E] (of the pre-step states). */
+int covo_closed_loop(covo_handle* h, int n_steps, unsigned long long noise_seed, int gaussian_disturbance,
+                     float obs_noise_scale, float dyn_noise_scale, const float* noise, float* actions, float* rewards,
+                     float* err_pos);
 /* Per-kernel device time of the last instrumented step, CUDA events on the launch stream.
  * slots: 0 hessian (local + assemble + forward chains), 1 tridiagonalisation (cluster), 2 tridiagonal matrix function,
  *        3 Sigma = Q F Q^T, 4 cholesky, 5 rollout */

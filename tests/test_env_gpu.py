@@ -1,0 +1,108 @@
+"""Device-resident environment step and closed loop against the oracle's env_step / noisy_state
+(envs/quadrotor.py:215-248, 314-361) and against the host-driven loop."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as o
+from tests.util import scenario
+
+pytestmark = pytest.mark.gpu
+
+
+class SeqRng:
+    """Hands out pre-drawn standard normals in the order the oracle asks for them."""
+
+    def __init__(self, values):
+        self.v = list(values)
+
+    def standard_normal(self):
+        return self.v.pop(0)
+
+
+def _handle(mode, N, H, T, E=1, seed=0):
+    from covo_mpc_b200 import _lib
+
+    cfg = _lib.default_config()
+    cfg.mode, cfg.n_samples, cfg.horizon, cfg.traj_len, cfg.n_env, cfg.seed = mode, N, H, T, E, seed
+    return _lib.Handle(cfg)
+
+
+@pytest.mark.parametrize("disturb", ["none", "gaussian"])
+def test_env_step_matches_oracle(disturb):
+    from covo_mpc_b200 import _lib
+
+    E = 3
+    scen = [scenario("tracking_zigzag", seed=40 + e, H=8, warm_steps=3 + 4 * e, zero_disturb=(e == 0)) for e in range(E)]
+    p = scen[0][0]
+    T = scen[0][1].pos_traj.shape[0]
+    h = _handle(_lib.MODE_MPPI, 64, 8, T, E=E)
+    h.set_reference(np.stack([s[1].pos_traj for s in scen]), np.stack([s[1].vel_traj for s in scen]))
+    states = [s[1] for s in scen]
+    states[2].time = 318  # next targets come from the clamped last row of the trajectory
+    h.env_reset(np.stack([o.state_to_vec24(s) for s in states]), [s.time for s in states])
+    rng = np.random.default_rng(3)
+    for step in range(3):
+        act = rng.uniform(-1.3, 1.3, size=(E, 4)).astype(np.float32)  # some components outside the clip box
+        z = rng.standard_normal((E, 16)).astype(np.float32)
+        noisy, rew, err, done = h.env_step(act, noise=z, gaussian=(disturb == "gaussian"))
+        s24, tm = h.env_state()
+        for e in range(E):
+            seq = ([float(x) for x in z[e, 13:16]] if disturb == "gaussian" else []) + [float(x) for x in z[e, :13]]
+            srng = SeqRng(seq)
+            nxt, r_o, d_o, e_o = o.env_step(states[e], act[e], p, srng, disturb)
+            ns_o = o.noisy_state(nxt, p, srng)
+            assert abs(rew[e] - r_o) < 2e-6 * max(1.0, abs(r_o)) and abs(err[e] - e_o) < 2e-6 and bool(done[e]) == d_o
+            assert np.abs(s24[e] - o.state_to_vec24(nxt)).max() < 3e-6
+            assert tm[e] == nxt.time
+            assert np.abs(noisy[e] - o.state_to_vec24(ns_o)).max() < 3e-6
+            states[e] = nxt
+
+
+@pytest.mark.parametrize("mode_name", ["mppi", "covo-online"])
+def test_closed_loop_on_device_equals_step_by_step(mode_name):
+    """covo_closed_loop (no host round trip) == the same handle type driven one call at a time through
+    covo_env_step + covo_step with the same seeds: identical kernels, so the actions agree bit for bit."""
+    from covo_mpc_b200 import _lib
+
+    mode = _lib.MODE_MPPI if mode_name == "mppi" else _lib.MODE_COVO_ONLINE
+    N, H, steps = 256, 10, 6
+    p, ns, a_mean, rng = scenario("tracking_zigzag", seed=9, H=H, warm_steps=4)
+    T = ns.pos_traj.shape[0]
+    noise = rng.standard_normal((steps + 1, 1, 16)).astype(np.float32)
+
+    def mk():
+        h = _handle(mode, N, H, T, seed=21)
+        h.set_reference(ns.pos_traj[None], ns.vel_traj[None])
+        h.set_mean(a_mean[None])
+        h.env_reset(o.state_to_vec24(ns)[None], [ns.time])
+        return h
+
+    ha = mk()
+    act_a, rew_a, err_a = ha.closed_loop(steps, noise=noise)
+    hb = mk()
+    noisy, _, _, _ = hb.env_step(None, noise=noise[0])
+    _, tm = hb.env_state()
+    for i in range(steps):
+        a = hb.step(noisy, tm)
+        assert np.array_equal(a, act_a[i])
+        noisy, rew, err, _ = hb.env_step(a, noise=noise[i + 1])
+        _, tm = hb.env_state()
+        assert rew[0] == rew_a[i, 0] and err[0] == err_a[i, 0]
+    sa, ta = ha.env_state()
+    sb, tb = hb.env_state()
+    assert np.array_equal(sa, sb) and np.array_equal(ta, tb)
+    assert np.isfinite(act_a).all() and np.abs(act_a).max() <= 1.0 + 1e-6
+
+
+def test_run_episode_device_tracks_like_the_host_loop():
+    """A short episode through the harness with the environment on the device: the tracking error stays in the
+    range the host-driven episode reaches (different noise streams, same protocol)."""
+    import covo_mpc_b200 as cm
+
+    env = cm.Quad3D("tracking_zigzag")
+    ctl, _ = cm.get_controller(env, "covo-offline", "N512_H16_lam0.01", seed=5)
+    err_h, _ = cm.run_episode(env, ctl, np.random.default_rng(1), n_steps=40, reset_rng=np.random.default_rng(2))
+    err_d, rew_d = cm.run_episode_device(env, ctl, np.random.default_rng(1), n_steps=40, reset_rng=np.random.default_rng(2))
+    assert err_d.shape == (40,) and np.isfinite(err_d).all() and np.isfinite(rew_d).all()
+    assert err_d.mean() < 3.0 * err_h.mean() + 0.05
+    ctl.close()
