@@ -95,6 +95,8 @@ struct covo_handle {
     int n_local, sample_offset, n_cta, rec;
     size_t lt_floats;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;  // side stream of the covariance step (Q accumulation next to E2)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned int rng_stream = 0;
     bool pos_stats_on = false;
     bool profiling = false;
@@ -106,11 +108,11 @@ struct covo_handle {
     DevBuf<float> state24, pos_traj, vel_traj, acc_traj, a_mean, eps, fdist;
     DevBuf<int> time;
     // covariance pipeline
-    DevBuf<float> R, Qt, F, cov, Lfull, Lt, Lblk, hess_ws;
+    DevBuf<float> R, Vh, tau, Qt, F, cov, Lfull, Lt, Lblk, hess_ws;
     DevBuf<double> diag, zolo;
     DevBuf<int> status;
     // offline schedule (batched over schedule steps)
-    DevBuf<float> cov_table, Lt_table, sched_states, sched_anom, sched_R, sched_Qt, sched_F, sched_ws;
+    DevBuf<float> cov_table, Lt_table, sched_states, sched_anom, sched_R, sched_Vh, sched_tau, sched_Qt, sched_F, sched_ws;
     DevBuf<double> sched_diag;
     DevBuf<int> sched_times, sched_status;
     // rollout
@@ -140,11 +142,11 @@ namespace {
 void release_all(covo_handle* h) {
     h->state24.release(); h->pos_traj.release(); h->vel_traj.release(); h->acc_traj.release();
     h->a_mean.release(); h->eps.release(); h->fdist.release(); h->time.release();
-    h->R.release(); h->Qt.release(); h->F.release(); h->cov.release();
+    h->R.release(); h->Vh.release(); h->tau.release(); h->Qt.release(); h->F.release(); h->cov.release();
     h->Lfull.release(); h->Lt.release(); h->Lblk.release(); h->hess_ws.release(); h->diag.release();
     h->zolo.release(); h->status.release();
     h->cov_table.release(); h->Lt_table.release(); h->sched_states.release(); h->sched_anom.release();
-    h->sched_R.release(); h->sched_Qt.release(); h->sched_F.release();
+    h->sched_R.release(); h->sched_Vh.release(); h->sched_tau.release(); h->sched_Qt.release(); h->sched_F.release();
     h->sched_ws.release(); h->sched_diag.release(); h->sched_times.release(); h->sched_status.release();
     h->partials.release(); h->rank_partial.release(); h->action.release(); h->costs.release();
     h->env_state24.release(); h->env_noisy24.release(); h->env_noise.release(); h->env_log_f.release(); h->env_action.release();
@@ -156,6 +158,9 @@ void release_all(covo_handle* h) {
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
 }
 
 HessianArgs hess_args(covo_handle* h, const float* st, const int* tm, const float* a_mean, int shift, float* R, float* ws,
@@ -183,6 +188,8 @@ SigmaArgs sigma_args(covo_handle* h) {
     a.n_pad = h->n_pad;
     a.sample_sigma = h->cfg.sample_sigma;
     a.R = h->R.p;
+    a.Vh = h->Vh.p;
+    a.tau = h->tau.p;
     a.Qt = h->Qt.p;
     a.F = h->F.p;
     a.cov = h->cov.p;
@@ -265,8 +272,15 @@ int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = fals
     if (!want_L) sa.L = nullptr;  // the sampler only needs the packed factor
     CK(launch_tridiag(sa, h->E, st));
     if (pf) pf->mark(2);
+    // Q^T from the reflectors does not depend on the tridiagonal matrix function: it runs on a side stream, in
+    // the shadow of E2, and joins before the sandwich kernel
+    CK(cudaEventRecord(h->ev_fork, st));
+    CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+    CK(launch_qacc(sa, h->E, h->aux_stream));
+    CK(cudaEventRecord(h->ev_join, h->aux_stream));
     CK(launch_trifunc(sa, h->E, st));
     if (pf) pf->mark(3);
+    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
     CK(launch_sandwich(sa, h->E, st));
     if (pf) pf->mark(4);
     sa.cov_symmetric = 1;
@@ -395,6 +409,9 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     A(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    A(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    A(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     for (auto& ev : h->ev) A(cudaEventCreate(&ev));
     A(h->state24.alloc(E * kStateFloats));
     A(h->time.alloc(E));
@@ -414,6 +431,8 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
         A(h->cov.alloc(E * h->H * 16));
     } else {
         A(h->R.alloc(E * nn));
+        A(h->Vh.alloc(E * nn));
+        A(h->tau.alloc(E * n));
         A(h->Qt.alloc(E * nn));
         A(h->F.alloc(E * nn));
         A(h->cov.alloc(E * nn));
@@ -554,12 +573,14 @@ static int alloc_schedule(covo_handle* h, int t_sched, bool full) {
     }
     if (full && (int)(h->sched_R.n / nn) < t_sched) {
         h->sched_states.release(); h->sched_times.release(); h->sched_anom.release(); h->sched_R.release();
-        h->sched_Qt.release(); h->sched_F.release();
+        h->sched_Vh.release(); h->sched_tau.release(); h->sched_Qt.release(); h->sched_F.release();
         h->sched_ws.release(); h->sched_diag.release();
         CK(h->sched_states.alloc(S * kStateFloats));
         CK(h->sched_times.alloc(S));
         CK(h->sched_anom.alloc(S * h->n));
         CK(h->sched_R.alloc(S * nn));
+        CK(h->sched_Vh.alloc(S * nn));
+        CK(h->sched_tau.alloc(S * h->n));
         CK(h->sched_Qt.alloc(S * nn));
         CK(h->sched_F.alloc(S * nn));
         CK(h->sched_ws.alloc(S * hessian_workspace_floats(h->H)));
@@ -571,6 +592,8 @@ static int alloc_schedule(covo_handle* h, int t_sched, bool full) {
 static SigmaArgs sched_sigma_args(covo_handle* h) {
     SigmaArgs a = sigma_args(h);
     a.R = h->sched_R.p;
+    a.Vh = h->sched_Vh.p;
+    a.tau = h->sched_tau.p;
     a.Qt = h->sched_Qt.p;
     a.F = h->sched_F.p;
     a.cov = h->cov_table.p;

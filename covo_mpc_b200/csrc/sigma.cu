@@ -232,9 +232,10 @@ constexpr int ET = EW * 32;   // threads per CTA
 constexpr int RS = kSigmaMaxN / 32;  // row slots per lane (7)
 constexpr int kTilePitch = 36;       // floats; rows of the transposition tile are float4-aligned and conflict-free
 
-__host__ __device__ inline size_t e1_smem_bytes(int c2) {
-    // q[2][256], v[2][256], row[2][256], d[256], e[256]; transposition tiles; mbarrier pair; reduction scratch
-    return ((size_t)256 * 8 + EW * 2 * c2 * kTilePitch + 4 + EW * 64) * sizeof(float);
+__host__ __device__ inline size_t e1_smem_bytes(int n, int c2) {
+    // reflector store Vs [n][n]; q[2][256], v[2][256], row[2][256], tau[256], d[256], e[256]; transposition tiles;
+    // mbarrier pair; reduction scratch
+    return ((size_t)n * n + 256 * 9 + EW * 2 * c2 * kTilePitch + 4 + EW * 64) * sizeof(float);
 }
 
 __device__ __forceinline__ void cluster_barrier() {
@@ -313,19 +314,22 @@ __global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
     const int gw = rank * EW + warp;        // global warp: owns columns 2 gw + CS c, 2 gw + CS c + 1
     constexpr int GW = EW * NC;             // warps of the cluster
     constexpr int CS = 2 * GW;              // column stride between pair slots
-    float* qsm0 = esm;                  // [2][256]
+    float* Vs = esm;                    // [n][n] reflectors (row k = v_k), every CTA keeps a copy
+    float* qsm0 = esm + n * n;          // [2][256]
     float* vsm0 = qsm0 + 512;           // [2][256]
     float* row0 = vsm0 + 512;           // [2][256]
-    float* dsm = row0 + 512;            // [256]
+    float* taus = row0 + 512;           // [256]
+    float* dsm = taus + 256;            // [256]
     float* esm_e = dsm + 256;           // [256]
     float* tile = esm_e + 256 + warp * 2 * C2 * kTilePitch;  // [2 C2][36] private transposition tile
     unsigned long long* mbars = reinterpret_cast<unsigned long long*>(esm_e + 256 + EW * 2 * C2 * kTilePitch);  // [2]
     float* red = esm_e + 256 + EW * 2 * C2 * kTilePitch + 4 + warp * 64;  // [2][32] private reduction scratch
 
     const float* Rg = a.R + (long long)env * n * n;
-    float* Qg = a.Qt + (long long)env * n * n;
+    float* Vg = a.Vh + (long long)env * n * n;
+    float* taug = a.tau + (long long)env * n;
     COVO_STAMP(a, 8);
-    for (int i = tid; i < 256 * 8; i += ET) qsm0[i] = 0.f;
+    for (int i = tid; i < 256 * 9; i += ET) qsm0[i] = 0.f;
     const unsigned mbar_local = (unsigned)__cvta_generic_to_shared(mbars);
     if (tid == 0) {
         mbar_init(mbar_local, 1);
@@ -347,18 +351,6 @@ __global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
                 x.y = 0.5f * (rowv.y + Rg[(long long)(j0 + 1) * n + i]);
             }
             A2[r][c] = x;
-        }
-    }
-    // P = Q^T = H_{m} ... H_0, accumulated next to A in the same layout (rows over the lanes, own column pairs):
-    // P <- H_m P = P - tau v (v^T P) needs, per column, a dot product over the rows, i.e. inside ONE warp.
-    float2 P2[RS][C2];
-#pragma unroll
-    for (int c = 0; c < C2; ++c) {
-        const int j0 = 2 * gw + CS * c;
-#pragma unroll
-        for (int r = 0; r < RS; ++r) {
-            const int i = lane + 32 * r;
-            P2[r][c] = make_float2(i == j0 ? 1.f : 0.f, i == j0 + 1 ? 1.f : 0.f);
         }
     }
     // shared::cluster addresses of the exchange buffers and of the mbarrier pair in every CTA of the cluster
@@ -518,44 +510,21 @@ __global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
 #pragma unroll
             for (int r = 0; r < RS; ++r) {
                 const int i = lane + 32 * r;
-                if (i < n) vsm0[pn + i] = vi[r];
+                if (i < n) {
+                    vsm0[pn + i] = vi[r];
+                    Vs[m * n + i] = vi[r];
+                }
             }
             if (lane == 0) {
                 dsm[m] = dm;
                 esm_e[m] = nbeta;
+                taus[m] = ntau;
             }
             __syncwarp();
             // this step's incoming traffic: column m+1 (7 x 32 floats) and, if the matvec runs, the n entries of q
             if (lane == 0) mbar_expect_tx(mbar_local + bar_off, ((m + 1 < n) ? 4u * 32u * RS : 0u) + (do_matvec ? 4u * n : 0u));
         }
         PH(2);
-        // ---- 4. P <- H_m P, in the shadow of the exchange latency -----------------------------------------
-        if (tau != 0.f) {
-            float2 z[C2];
-#pragma unroll
-            for (int c = 0; c < C2; ++c) {
-                float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int r = 0; r < RS; r += 2) sa = __ffma2_rn(P2[r][c], make_float2(vi[r], vi[r]), sa);
-#pragma unroll
-                for (int r = 1; r < RS; r += 2) sb = __ffma2_rn(P2[r][c], make_float2(vi[r], vi[r]), sb);
-                z[c] = __fadd2_rn(sa, sb);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int c = 0; c < C2; ++c) {
-                    z[c].x += __shfl_xor_sync(0xffffffffu, z[c].x, o);
-                    z[c].y += __shfl_xor_sync(0xffffffffu, z[c].y, o);
-                }
-#pragma unroll
-            for (int c = 0; c < C2; ++c)
-#pragma unroll
-                for (int r = 0; r < RS; ++r) {
-                    const float tv = -tau * vi[r];
-                    P2[r][c] = __ffma2_rn(make_float2(tv, tv), z[c], P2[r][c]);
-                }
-        }
         // everything this CTA reads in step m+1 has landed when its mbarrier phase completes
         mbar_wait(mbar_local + bar_off, (m >> 1) & 1);
         PH(3);
@@ -566,19 +535,18 @@ __global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
     __syncthreads();
     if (NC > 1) cluster_barrier();  // nobody leaves while a peer could still be sending to it
     COVO_STAMP(a, 9);
-    // d, e -> HBM for the E2 kernel (every CTA holds them; rank 0 writes); Q^T from the registers of all warps
+    // every CTA holds the complete result: d, e (fp64, for E2) and tau by rank 0, the reflector rows shared out
     if (rank == 0 && tid < n) {
         double* dg = a.diag + (long long)env * 4 * n;
         dg[tid] = (double)dsm[tid];
         dg[n + tid] = (tid < n - 1) ? (double)esm_e[tid] : 0.0;
+        taug[tid] = (tid < n - 2) ? taus[tid] : 0.f;
     }
-#pragma unroll
-    for (int c = 0; c < C2; ++c) {
-        const int j0 = 2 * gw + CS * c;
-#pragma unroll
-        for (int r = 0; r < RS; ++r) {
-            const int i = lane + 32 * r;
-            if (i < n && j0 < n) *reinterpret_cast<float2*>(Qg + (long long)i * n + j0) = P2[r][c];
+    {
+        const int nv4 = (n * n) >> 2;
+        for (int idx = rank * ET + tid; idx < nv4; idx += ET * NC) {
+            const int k2 = (4 * idx) / n;
+            reinterpret_cast<float4*>(Vg)[idx] = (k2 < n - 2) ? reinterpret_cast<const float4*>(Vs)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     COVO_STAMP(a, 16);
@@ -806,6 +774,85 @@ __global__ void __launch_bounds__(TT, 1) sigma_trifunc_kernel(const SigmaArgs a)
     }
     __syncthreads();
     COVO_STAMP(a, 14);
+}
+
+// ---------------------------------------------------------------------------------------------
+// E1b: Q^T = H_{n-3} ... H_1 H_0 from the stored reflectors.  P <- H_m P = P - tau_m v_m (v_m^T P) acts on every
+// COLUMN of P independently: one warp per column pair (rows over the lanes, float2 = two columns, as in E1), no
+// communication between warps at all.  The kernel depends only on E1, so the host runs it on a side stream next
+// to E2 and joins before the sandwich kernel: an explicit Q for free.
+// ---------------------------------------------------------------------------------------------
+constexpr int kQaccWarps = 4, kQaccChunk = 32;
+
+__global__ void __launch_bounds__(kQaccWarps * 32) qacc_kernel(const SigmaArgs a) {
+    extern __shared__ __align__(16) float qsmf[];  // [2][kQaccChunk][n] reflector chunks (cp.async), then tau[256]
+    const int n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, env = blockIdx.y;
+    const float* Vg = a.Vh + (long long)env * n * n;
+    const float* taug = a.tau + (long long)env * n;
+    float* Qg = a.Qt + (long long)env * n * n;
+    float* taus = qsmf + 2 * kQaccChunk * n;
+    const int j0 = 2 * (blockIdx.x * kQaccWarps + warp);  // this warp's column pair
+    const int nref = n - 2, nch = (nref + kQaccChunk - 1) / kQaccChunk, nv4 = n >> 2;
+    auto prefetch = [&](int c) {
+        const int m0 = c * kQaccChunk, rows = min(kQaccChunk, nref - m0);
+        float* dst = qsmf + (c & 1) * kQaccChunk * n;
+        for (int idx = tid; idx < rows * nv4; idx += kQaccWarps * 32) {
+            unsigned d = (unsigned)__cvta_generic_to_shared(dst + 4 * idx);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(Vg + (long long)m0 * n + 4 * idx) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(0);
+    for (int i = tid; i < n; i += kQaccWarps * 32) taus[i] = taug[i];
+    float2 P2[RS];
+#pragma unroll
+    for (int r = 0; r < RS; ++r) {
+        const int i = lane + 32 * r;
+        P2[r] = make_float2(i == j0 ? 1.f : 0.f, i == j0 + 1 ? 1.f : 0.f);
+    }
+    for (int c = 0; c < nch; ++c) {
+        if (c + 1 < nch) {
+            prefetch(c + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int m0 = c * kQaccChunk, rows = min(kQaccChunk, nref - m0);
+        const float* buf = qsmf + (c & 1) * kQaccChunk * n;
+        if (j0 < n) {
+            for (int mm = 0; mm < rows; ++mm) {
+                const float tau = taus[m0 + mm];
+                float v[RS];
+#pragma unroll
+                for (int r = 0; r < RS; ++r) v[r] = (lane + 32 * r < n) ? buf[mm * n + lane + 32 * r] : 0.f;
+                float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int r = 0; r < RS; r += 2) sa = __ffma2_rn(P2[r], make_float2(v[r], v[r]), sa);
+#pragma unroll
+                for (int r = 1; r < RS; r += 2) sb = __ffma2_rn(P2[r], make_float2(v[r], v[r]), sb);
+                float2 z = __fadd2_rn(sa, sb);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    z.x += __shfl_xor_sync(0xffffffffu, z.x, o);
+                    z.y += __shfl_xor_sync(0xffffffffu, z.y, o);
+                }
+#pragma unroll
+                for (int r = 0; r < RS; ++r) {
+                    const float tv = -tau * v[r];
+                    P2[r] = __ffma2_rn(make_float2(tv, tv), z, P2[r]);
+                }
+            }
+        }
+        __syncthreads();  // the buffer is refilled two chunks later
+    }
+    if (j0 < n) {
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            const int i = lane + 32 * r;
+            if (i < n) *reinterpret_cast<float2*>(Qg + (long long)i * n + j0) = P2[r];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1191,7 +1238,7 @@ static size_t chol_smem(int n) { return (size_t)n * n * 4 + (size_t)(2 * 8 * rou
 template <int C2, int NC>
 static cudaError_t launch_e1(const SigmaArgs& a, int n_env, cudaStream_t st) {
     static size_t conf[32] = {};
-    const size_t smem = e1_smem_bytes(C2);
+    const size_t smem = e1_smem_bytes(a.n, C2);
     cudaError_t e = ensure_smem_attr(tridiag_reg_kernel<C2, NC>, smem, conf);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -1245,6 +1292,16 @@ cudaError_t launch_tridiag(const SigmaArgs& a, int n_env, cudaStream_t st) {
     return e;
 }
 
+cudaError_t launch_qacc(const SigmaArgs& a, int n_env, cudaStream_t st) {
+    if (a.n > kSigmaMaxN || (a.n & 3)) return cudaErrorInvalidValue;
+    const size_t smem = ((size_t)2 * kQaccChunk * a.n + 256) * sizeof(float);
+    static size_t conf[32] = {};
+    cudaError_t e = ensure_smem_attr(qacc_kernel, smem, conf);
+    if (e != cudaSuccess) return e;
+    qacc_kernel<<<dim3((a.n / 2 + kQaccWarps - 1) / kQaccWarps, n_env), kQaccWarps * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_trifunc(const SigmaArgs& a, int n_env, cudaStream_t st) {
     if (a.n > kSigmaMaxN || (a.n & 3)) return cudaErrorInvalidValue;
     cudaError_t e;
@@ -1272,6 +1329,7 @@ cudaError_t launch_sandwich(const SigmaArgs& a, int n_env, cudaStream_t st) {
 
 cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st) {
     cudaError_t e = launch_tridiag(a, n_env, st);
+    if (e == cudaSuccess) e = launch_qacc(a, n_env, st);
     if (e == cudaSuccess) e = launch_trifunc(a, n_env, st);
     if (e == cudaSuccess) e = launch_sandwich(a, n_env, st);
     return e;

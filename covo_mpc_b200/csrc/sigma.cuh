@@ -14,7 +14,9 @@ struct SigmaArgs {
     int n, n_pad;
     float sample_sigma;
     const float* R;      // [E][n][n]
-    float* Qt;           // [E][n][n]  Q^T = H_{n-3} ... H_1 H_0 (accumulated inside the tridiagonalisation)
+    float* Vh;           // [E][n][n]  row k = Householder vector v_k (zeros for index <= k, v[k+1] = 1)
+    float* tau;          // [E][n]
+    float* Qt;           // [E][n][n]  Q^T = H_{n-3} ... H_1 H_0 (accumulated from the reflectors by qacc_kernel)
     float* F;            // [E][n][n]  exp(log_const/2) * (T - lam_min + offset)^(-1/2), full symmetric
     float* cov;          // [E][n][n]  Sigma = Q F Q^T, exactly symmetric          -> a_cov
     float* L;            // [E][n][n]  optional: lower Cholesky factor, row-major
@@ -31,7 +33,8 @@ void zolotarev_nodes(double m, double M, int N, double* t, double* w);
 void zolotarev_table(double* table /* [kZoloLadder][2][kZoloPoles] */);
 double zolotarev_ladder_M(int i);
 
-cudaError_t launch_tridiag(const SigmaArgs& a, int n_env, cudaStream_t st);   // E1: R -> (d, e), Q^T
+cudaError_t launch_tridiag(const SigmaArgs& a, int n_env, cudaStream_t st);   // E1: R -> (d, e), reflectors
+cudaError_t launch_qacc(const SigmaArgs& a, int n_env, cudaStream_t st);      // E1b: reflectors -> Q^T (independent of E2)
 cudaError_t launch_trifunc(const SigmaArgs& a, int n_env, cudaStream_t st);   // E2: (d, e) -> F
 cudaError_t launch_sandwich(const SigmaArgs& a, int n_env, cudaStream_t st);  // E3: Q F Q^T -> cov
 cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st);     // E1 + E2 + E3: R -> cov
