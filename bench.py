@@ -113,7 +113,7 @@ def algorithmic_bytes(n, H, N, parity=False):
     return {
         # state, mean, ref; per-step derivative records written + read; [A|B], S, D hand-over written + read; R
         "hessian": 96 + 4 * n + 4 * H * 6 + 2 * 4 * H * (14 * 153 + 14 * 17) + 2 * 4 * H * 328 + nn,
-        "tridiag": nn + nn + 2 * 8 * n,  # R in; Q^T out; (d, e) fp64 out
+        "tridiag": nn + nn + 2 * 8 * n,  # R in; reflectors out; (d, e) fp64 out (Q^T: qacc kernel, side stream, +2 nn)
         "trifunc": 2 * 8 * n + nn,       # (d, e) in; F out (full symmetric)
         "sandwich": nn + nn + nn,        # Q^T, F in; Sigma out
         "cholesky": nn + nn // 2,        # Sigma in; packed factor out
@@ -280,7 +280,7 @@ def run_gpu(args):
         tc = time.perf_counter() - t0
         closed = {"value": K * world / tc, "unit": UNIT, "ms_per_step": 1e3 * tc / K, "mean_err_pos": float(err_cl.mean()),
                   "note": "covo_closed_loop: K x [noisy state -> controller -> Quad3D.step_env] on the device, one D2H of the logs at the end (wall clock)"}
-    launches_per_step = {"covo-online": 8, "covo-offline": 1, "mppi": 2}[mode_name] + (1 if shard == "nsample" else 0)
+    launches_per_step = {"covo-online": 9, "covo-offline": 1, "mppi": 2}[mode_name] + (1 if shard == "nsample" else 0)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak" if shard == "env" else "strong",

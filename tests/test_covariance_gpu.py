@@ -134,3 +134,23 @@ def test_sigma_many_matrices_batched():
         Lo = np.linalg.cholesky(S[e].astype(np.float64))
         assert np.abs(L[e] - Lo).max() < 2e-6 * max(1, np.abs(Lo).max())
     assert (h.status() == 0).all()
+
+
+def test_maximum_horizon_full_step():
+    """H = 56 (n = 224, the shared-memory / register limit of the covariance kernels): one full CoVO-online call."""
+    import covo_mpc_b200 as cm
+    from tests.test_step_gpu import _to_env_state
+
+    N, H = 256, 56
+    p, ns, a_mean, rng = scenario("tracking_zigzag", seed=77, H=H, warm_steps=10)
+    env = cm.Quad3D("tracking_zigzag")
+    ctl, cp = cm.get_controller(env, "covo-online", f"N{N}_H{H}_lam0.01")
+    cp = cp.replace(a_mean=a_mean)
+    eps = rng.standard_normal((N, 4 * H)).astype(np.float32)
+    st = _to_env_state(cm, ns)
+    action, cp2, _ = ctl(None, st, env.default_params, eps, cp, {"noisy_state": st})
+    u_o, mean_o, cov_o, _ = o.covo_call(ns, a_mean, eps, p, lam=0.01)
+    cov = np.asarray(cp2.a_cov)
+    assert np.linalg.norm(cov - cov_o) / np.linalg.norm(cov_o) < 3e-5
+    assert np.abs(action - u_o).max() < 5e-4
+    ctl.close()
