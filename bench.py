@@ -331,6 +331,8 @@ def run_gpu(args):
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(states_h, times_h, traj, budget_s=args.cpu_budget, mode_name=mode_name)
+        if mode_name == "covo-online":
+            out["tracking_cost"] = tracking_cost(h, traj, seed, n_steps=min(100, max(K, 20)))
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -381,6 +383,55 @@ def cpu_baseline(states_h, times_h, traj, budget_s=20.0, mode_name="covo-online"
             "sample": f"{done} full MPC steps ({mode_name}, N={N_SAMPLES}, H={HORIZON}) of the oracle restatement "
                       f"({'C/OpenMP + LAPACK' if fast else 'NumPy float32 + LAPACK eigh'}); JAX is not installable here",
             "steps": done, "seconds": t_used}
+
+
+def tracking_cost(h, traj, seed, n_steps=100):
+    """BASELINE metric, second half ("tracking cost delta vs ref"): the same closed-loop protocol -- zigzag reference,
+    zero initial state, observation noise, disturb_type none -- through the device loop (covo_closed_loop) and through
+    the oracle port on the host.  Sample and noise streams are independent (the reference's Threefry streams are not
+    reproducible here), so this is a statistical comparison of mean ||pos_tar - pos|| over the episode."""
+    from oracle import oracle_np as o
+
+    try:
+        from oracle import oracle_c
+
+        step = lambda ns, mean, eps, p: oracle_c.covo_step(ns, mean, eps, p, LAM)
+    except Exception:
+        def step(ns, mean, eps, p):
+            u, m, _, _ = o.covo_call(ns, mean, eps, p, lam=LAM, hessian_dtype=np.float32)
+            return u, m
+    p = o.EnvParams()
+    s0 = o.make_state(np.zeros(3), np.array([0, 0, 0, 1.0]), np.zeros(3), np.zeros(3), np.zeros(3), 0, traj[0], traj[1], traj[0][0], traj[1][0],
+                      dtype=np.float32)
+    hover = o.hover_mean(HORIZON, p)
+    # device: 8 episodes (independent noise streams; the sample stream advances from episode to episode)
+    dev = []
+    for k in range(8):
+        h.set_mean(hover[None])
+        h.env_reset(o.state_to_vec24(s0)[None], [0])
+        _, _, err_d = h.closed_loop(n_steps, noise_seed=seed + 11 + k)
+        dev.append(float(err_d[:, 0].mean()))
+    # oracle port on the host: as many episodes as fit into ~40 s, at most 3
+    ora, t0 = [], time.perf_counter()
+    for k in range(3):
+        rng = np.random.default_rng(seed + 7 + k)
+        s, mean, errs = s0.copy(), hover, []
+        for i in range(n_steps):
+            ns = o.noisy_state(s, p, rng)
+            eps = rng.standard_normal((N_SAMPLES, 4 * HORIZON)).astype(np.float32)
+            u, mean = step(ns, mean, eps, p)
+            s, _, _, e = o.env_step(s, u, p, rng, "none")
+            errs.append(e)
+        ora.append(float(np.mean(errs)))
+        if time.perf_counter() - t0 > 25.0:
+            break
+    dm, om = float(np.mean(dev)), float(np.mean(ora))
+    return {"metric": "mean ||pos_tar - pos|| over the first %d closed-loop steps (m), mean over episodes" % n_steps,
+            "device": dm, "device_std": float(np.std(dev)), "device_episodes": len(dev),
+            "oracle_port": om, "oracle_std": float(np.std(ora)), "oracle_episodes": len(ora),
+            "rel_delta": (dm - om) / om if om > 0 else None,
+            "note": "same protocol and reference trajectory, independent sample/noise streams: statistical agreement only "
+                    "(episode-to-episode std ~12%); seed-identical parity is tests/test_step_gpu.py"}
 
 
 def run_reference(args):
