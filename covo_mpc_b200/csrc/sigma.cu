@@ -170,10 +170,13 @@ __device__ __forceinline__ void warp_recurrence(int n, AB ab, EMIT emit) {
         P.d = t.b;
     }
     P = m2_normalise(P);
+    // entries are <= 2 after the rescale; a product at most squares-and-doubles the bound (8, 128, 3e4, ...), so
+    // one more rescale in the middle of the five levels is plenty
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const M2 Q = m2_shfl_up(P, off);
-        if (lane >= off) P = m2_normalise(m2_mul(P, Q));
+        if (lane >= off) P = m2_mul(P, Q);
+        if (off == 4) P = m2_normalise(P);
     }
     const M2 Q = m2_shfl_up(P, 1);
     double p = (lane == 0) ? 1.0 : Q.a, pm = (lane == 0) ? 0.0 : Q.c;
@@ -571,7 +574,7 @@ __global__ void __launch_bounds__(TT, 1) sigma_trifunc_kernel(const SigmaArgs a)
     double* e2s = ee + 256;                               // [256] e^2
     double* sc = e2s + 256;                               // [16] scalars
     double* rdbuf = sc + 16;                              // [64]
-    int* ired = reinterpret_cast<int*>(rdbuf + 64);       // [4]
+    int* ired = reinterpret_cast<int*>(rdbuf + 64);       // [64]
     COVO_STAMP(a, 17);
     {
         const double* dg = a.diag + (long long)env * 4 * n;
@@ -614,23 +617,33 @@ __global__ void __launch_bounds__(TT, 1) sigma_trifunc_kernel(const SigmaArgs a)
         __syncthreads();
     }
     COVO_STAMP(a, 10);
-    // lam_min by multisection: every warp evaluates one trial shift per round with the warp-scan Sturm test
-    // (~0.5 us), 9 rounds shrink the Gershgorin bracket by 33^9 ~ 4.6e13, i.e. to ~1e-10 absolute.
-    constexpr int MS = TT / 32;
-    for (int round = 0; round < 9; ++round) {
-        const double lo = sc[0], hi = sc[1];
-        if (tid == 0) ired[0] = MS;
-        __syncthreads();
-        {
-            const double x = lo + (hi - lo) * ((double)(warp + 1) / (double)(MS + 1));
-            if (warp_has_eig_below(dd, e2s, n, x) && lane == 0) atomicMin(ired, warp);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const int ts = ired[0];
+    // lam_min by multisection: MS warps evaluate one trial shift each per round with the warp-scan Sturm test; the
+    // rounds shrink the Gershgorin bracket by (MS+1)^rounds >= 4e13, i.e. to ~1e-10 absolute.  One barrier per
+    // round: the warps post their verdicts, every thread derives the new bracket from them in registers.
+    {
+        const int MS = a.e2_points;  // 8, 16 or 32
+        const int rounds = (MS >= 32) ? 9 : (MS >= 16 ? 12 : 15);
+        int* flags = ired;  // [2][32]
+        double lo = sc[0], hi = sc[1];
+        for (int round = 0; round < rounds; ++round) {
+            int* fl = flags + (round & 1) * 32;
+            if (warp < MS) {
+                const double x = lo + (hi - lo) * ((double)(warp + 1) / (double)(MS + 1));
+                const bool below = warp_has_eig_below(dd, e2s, n, x);
+                if (lane == 0) fl[warp] = below ? 1 : 0;
+            }
+            __syncthreads();
+            const unsigned m = __ballot_sync(0xffffffffu, lane < MS && fl[lane] != 0);
+            const int ts = m ? (__ffs(m) - 1) : MS;  // first trial shift with an eigenvalue below it
             const double step = (hi - lo) / (double)(MS + 1);
-            sc[0] = (ts == 0) ? lo : lo + step * ts;
-            sc[1] = (ts == MS) ? hi : lo + step * (ts + 1);
+            const double nlo = (ts == 0) ? lo : lo + step * ts;
+            const double nhi = (ts == MS) ? hi : lo + step * (ts + 1);
+            lo = nlo;
+            hi = nhi;
+        }
+        if (tid == 0) {
+            sc[0] = lo;
+            sc[1] = hi;
         }
         __syncthreads();
     }
@@ -1231,7 +1244,7 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 static size_t trifunc_smem(int n) {
-    return (size_t)trifunc_region_floats(n) * 4 + 256 * 8 * 3 + 16 * 8 + 64 * 8 + 16;
+    return (size_t)trifunc_region_floats(n) * 4 + 256 * 8 * 3 + 16 * 8 + 64 * 8 + 64 * 4;
 }
 static size_t chol_smem(int n) { return (size_t)n * n * 4 + (size_t)(2 * 8 * round_up8(n) + 64) * 4; }
 
@@ -1311,7 +1324,13 @@ cudaError_t launch_trifunc(const SigmaArgs& a, int n_env, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     // CTAs per matrix: the scalar stages are repeated by each of them, the rows of F are shared out
     const int nb = (n_env <= 18) ? 8 : (n_env <= 74 ? 2 : 1);
-    sigma_trifunc_kernel<<<dim3(nb, n_env), TT, smem, st>>>(a);
+    SigmaArgs a2 = a;
+    {
+        const char* ev = getenv("COVO_E2_POINTS");  // tuning: trial shifts per multisection round
+        const int v = ev ? atoi(ev) : 0;
+        a2.e2_points = (v == 8 || v == 16 || v == 32) ? v : 16;
+    }
+    sigma_trifunc_kernel<<<dim3(nb, n_env), TT, smem, st>>>(a2);
     return cudaGetLastError();
 }
 

@@ -25,6 +25,7 @@ struct SigmaArgs {
     const double* zolo;  // [kZoloLadder][2][kZoloPoles]  shifts t_j, weights w_j (host-computed)
     int* status;         // [E]  0 ok, 1 spectral ratio beyond ladder, 2 Cholesky breakdown
     long long lt_stride;
+    int e2_points = 16;     // trial shifts (= warps) per multisection round in E2 (measured: 16 beats 32 and 8)
     int cov_symmetric = 0;  // cov is exactly symmetric already (written by the sandwich kernel): Cholesky skips (C + C^T)/2
 };
 
