@@ -16,7 +16,7 @@
 //   transition and the cost once each in hyper-dual arithmetic (quad_model.cuh) -- one (a <= b) pair of
 //   the 17 local inputs per thread -- giving A_t, B_t, grad/hess c_t and all 13 hess F_k.
 // Kernel 2 (grid = envs): adjoint, contraction and the 13x13 backward recursion.
-// Kernel 3 (grid = 4H/8 x envs): the 4H forward chains, one quad of lanes each, spread over the SMs.
+// Kernel 3 (grid = 4H/2 x envs): the 4H forward chains, one half-warp each, spread over the SMs.
 // Sub-gradient conventions (clip ties, |.|, sqrt at 0) are those of quad_model.cuh / the oracle.
 #include <cuda_runtime.h>
 
@@ -158,31 +158,35 @@ __global__ void __launch_bounds__(kAsmThreads) hess_assemble_kernel(const Hessia
     __syncthreads();
     COVO_STAMP(a, 3);
 
-    // backward recursion for P (13x13), S_t (13x4), D_t (4x4)
-    for (int t = H - 1; t >= 0; --t) {
-        const float* Gt = G + t * NX * NZP;
-        if (tid < NX * NZ) {  // X = P [A B]
-            int r = tid / NZ, c = tid - r * NZ;
-            float acc = 0.f;
+    // backward recursion for P (13x13), S_t (13x4), D_t (4x4): only the first ten warps take part (289 threads
+    // of work), on their own named barrier -- two 10-warp barriers per step instead of two 32-warp ones
+    if (tid < 320) {
+        for (int t = H - 1; t >= 0; --t) {
+            const float* Gt = G + t * NX * NZP;
+            if (tid < NX * NZ) {  // X = P [A B]
+                int r = tid / NZ, c = tid - r * NZ;
+                float acc = 0.f;
 #pragma unroll
-            for (int k = 0; k < NX; ++k) acc = fmaf(P[r * NX + k], Gt[k * NZP + c], acc);
-            X[r * NZP + c] = acc;
-        }
-        __syncthreads();
-        if (tid < NZ * NZ) {  // W + [A B]^T X
-            int r = tid / NZ, c = tid - r * NZ;
-            if (!(r >= NX && c < NX)) {  // lower-left block is the transpose of S, not needed
-                int lo = min(r, c), hi = max(r, c);
-                float acc = W[t * NPAIR + pair_index(lo, hi)];
-#pragma unroll
-                for (int k = 0; k < NX; ++k) acc = fmaf(Gt[k * NZP + r], X[k * NZP + c], acc);
-                if (r < NX && c < NX) P[r * NX + c] = acc;
-                else if (r < NX) S[(t * NX + r) * 4 + (c - NX)] = acc;
-                else D[t * 16 + (r - NX) * 4 + (c - NX)] = acc;
+                for (int k = 0; k < NX; ++k) acc = fmaf(P[r * NX + k], Gt[k * NZP + c], acc);
+                X[r * NZP + c] = acc;
             }
+            asm volatile("bar.sync 1, 320;" ::: "memory");
+            if (tid < NZ * NZ) {  // W + [A B]^T X
+                int r = tid / NZ, c = tid - r * NZ;
+                if (!(r >= NX && c < NX)) {  // lower-left block is the transpose of S, not needed
+                    int lo = min(r, c), hi = max(r, c);
+                    float acc = W[t * NPAIR + pair_index(lo, hi)];
+#pragma unroll
+                    for (int k = 0; k < NX; ++k) acc = fmaf(Gt[k * NZP + r], X[k * NZP + c], acc);
+                    if (r < NX && c < NX) P[r * NX + c] = acc;
+                    else if (r < NX) S[(t * NX + r) * 4 + (c - NX)] = acc;
+                    else D[t * 16 + (r - NX) * 4 + (c - NX)] = acc;
+                }
+            }
+            asm volatile("bar.sync 1, 320;" ::: "memory");
         }
-        __syncthreads();
     }
+    __syncthreads();
     COVO_STAMP(a, 4);
 
     // export [A_t | B_t] (13 x 20), S_t (13 x 4) and D_t (4 x 4) for the forward-chain kernel: they overwrite the
@@ -203,12 +207,14 @@ __global__ void __launch_bounds__(kAsmThreads) hess_assemble_kernel(const Hessia
 
 // ---------------------------------------------------------------------------------------------
 // Forward chains R[I, J] = Phi^T S_J, Phi <- A_J Phi (Phi = d x_J / d u_{I,c}, starts as column c of B_I), J > I, and
-// the diagonal blocks R[I, I] = D_I.  One QUAD of lanes per chain (I, c): lane q forms rows q, q+4, q+8 (, 12) of
-// A_J Phi and the output column q; the quad re-assembles Phi with 13 shuffles.  One warp (8 chains) per CTA, the
-// CTAs spread over the SMs: the 49-step dependent chain runs at single-warp latency instead of sharing one SM
-// with 200 other chains.
+// the diagonal blocks R[I, I] = D_I.  One HALF-WARP per chain (I, c): lane r < 13 forms row r of A_J Phi, lanes 0..3
+// also the output column q; the half-warp re-assembles Phi with 13 shuffles.  A lone warp issues roughly one
+// dependent instruction every four cycles, so the step time is its instruction count: ~60 here (a quad-per-chain
+// version needed ~120, a thread-per-chain version 250).  Two chains per warp, one warp per CTA, CTAs spread
+// over the SMs.
 // ---------------------------------------------------------------------------------------------
 constexpr int kFwThreads = 128;
+constexpr int kFwChains = 2;  // per CTA
 
 __global__ void __launch_bounds__(kFwThreads) hess_forward_kernel(const HessianArgs a) {
     extern __shared__ __align__(16) float fsm[];  // [H][kFwRec]
@@ -216,7 +222,7 @@ __global__ void __launch_bounds__(kFwThreads) hess_forward_kernel(const HessianA
     const int H = a.H, n = 4 * H;
     const int rec = 14 * NPAIR + 14 * NZ;
     const float* wsb = a.workspace + (long long)env * H * rec;
-    const int id0 = blockIdx.x * 8;          // first chain of this CTA
+    const int id0 = blockIdx.x * kFwChains;  // first chain of this CTA
     const int Imin = id0 >> 2;
     // stage the records J >= Imin (16-byte pieces, all threads)
     {
@@ -230,11 +236,13 @@ __global__ void __launch_bounds__(kFwThreads) hess_forward_kernel(const HessianA
     }
     __syncthreads();
     if (tid >= 32) return;
-    const int id = id0 + (lane >> 2), q = lane & 3;
-    if (id >= n) return;  // n is a multiple of 8 only when H is even; whole quads drop out together
+    const int id = id0 + (lane >> 4), r = lane & 15;  // chain, row of Phi owned by this lane (13..15: idle rows)
+    if (id >= n) return;  // whole half-warps drop out together (n is even)
     const int I = id >> 2, c = id & 3;
-    const unsigned qmask = 0xFu << (lane & ~3);
+    const unsigned hmask = 0xFFFFu << (lane & 16);
+    const int base = lane & 16;
     float* Rg = a.R + (long long)env * n * n;
+    const int rr = min(r, NX - 1), q = r & 3;
     float phi[NX];
     {
         const float* GI = fsm + I * kFwRec;
@@ -242,11 +250,12 @@ __global__ void __launch_bounds__(kFwThreads) hess_forward_kernel(const HessianA
         for (int k = 0; k < NX; ++k) phi[k] = GI[k * NZP + NX + c];
         // D is symmetric up to round-off; symmetrise so R is exactly symmetric
         const float* DI = fsm + I * kFwRec + NX * NZP + NX * 4;
-        Rg[(long long)id * n + 4 * I + q] = 0.5f * (DI[c * 4 + q] + DI[q * 4 + c]);
+        if (r < 4) Rg[(long long)id * n + 4 * I + q] = 0.5f * (DI[c * 4 + q] + DI[q * 4 + c]);
     }
     for (int J = I + 1; J < H; ++J) {
         const float* GJ = fsm + J * kFwRec;
         const float* SJ = GJ + NX * NZP;
+        // output column q (lanes 0..3 store it)
         float r0 = 0.f, r1 = 0.f;
 #pragma unroll
         for (int k = 0; k < NX; k += 2) {
@@ -254,38 +263,31 @@ __global__ void __launch_bounds__(kFwThreads) hess_forward_kernel(const HessianA
             if (k + 1 < NX) r1 = fmaf(phi[k + 1], SJ[(k + 1) * 4 + q], r1);
         }
         const float rq = r0 + r1;
-        Rg[(long long)id * n + 4 * J + q] = rq;
-        Rg[(long long)(4 * J + q) * n + id] = rq;
-        if (J == H - 1) break;
-        // rows q, q+4, q+8 (and 12 for q = 0) of A_J Phi
-        float np[4];
-#pragma unroll
-        for (int sl = 0; sl < 4; ++sl) {
-            const int r = q + 4 * sl;
-            float acc = 0.f;
-            if (r < NX) {
-                const float4 a0 = *reinterpret_cast<const float4*>(GJ + r * NZP);
-                const float4 a1 = *reinterpret_cast<const float4*>(GJ + r * NZP + 4);
-                const float4 a2 = *reinterpret_cast<const float4*>(GJ + r * NZP + 8);
-                const float a12 = GJ[r * NZP + 12];
-                float e0 = a0.x * phi[0], e1 = a0.y * phi[1];
-                e0 = fmaf(a0.z, phi[2], e0);
-                e1 = fmaf(a0.w, phi[3], e1);
-                e0 = fmaf(a1.x, phi[4], e0);
-                e1 = fmaf(a1.y, phi[5], e1);
-                e0 = fmaf(a1.z, phi[6], e0);
-                e1 = fmaf(a1.w, phi[7], e1);
-                e0 = fmaf(a2.x, phi[8], e0);
-                e1 = fmaf(a2.y, phi[9], e1);
-                e0 = fmaf(a2.z, phi[10], e0);
-                e1 = fmaf(a2.w, phi[11], e1);
-                e0 = fmaf(a12, phi[12], e0);
-                acc = e0 + e1;
-            }
-            np[sl] = acc;
+        if (r < 4) {
+            Rg[(long long)id * n + 4 * J + q] = rq;
+            Rg[(long long)(4 * J + q) * n + id] = rq;
         }
+        if (J == H - 1) break;
+        // row rr of A_J Phi
+        const float4 a0 = *reinterpret_cast<const float4*>(GJ + rr * NZP);
+        const float4 a1 = *reinterpret_cast<const float4*>(GJ + rr * NZP + 4);
+        const float4 a2 = *reinterpret_cast<const float4*>(GJ + rr * NZP + 8);
+        const float a12 = GJ[rr * NZP + 12];
+        float e0 = a0.x * phi[0], e1 = a0.y * phi[1];
+        e0 = fmaf(a0.z, phi[2], e0);
+        e1 = fmaf(a0.w, phi[3], e1);
+        e0 = fmaf(a1.x, phi[4], e0);
+        e1 = fmaf(a1.y, phi[5], e1);
+        e0 = fmaf(a1.z, phi[6], e0);
+        e1 = fmaf(a1.w, phi[7], e1);
+        e0 = fmaf(a2.x, phi[8], e0);
+        e1 = fmaf(a2.y, phi[9], e1);
+        e0 = fmaf(a2.z, phi[10], e0);
+        e1 = fmaf(a2.w, phi[11], e1);
+        e0 = fmaf(a12, phi[12], e0);
+        const float np = e0 + e1;
 #pragma unroll
-        for (int k = 0; k < NX; ++k) phi[k] = __shfl_sync(qmask, np[k >> 2], (lane & ~3) + (k & 3));
+        for (int k = 0; k < NX; ++k) phi[k] = __shfl_sync(hmask, np, base + k);
     }
 }
 
@@ -310,7 +312,7 @@ cudaError_t launch_hessian(const HessianArgs& a, int n_env, cudaStream_t st) {
     static size_t configured_fw[32] = {};
     e = ensure_smem_attr(hess_forward_kernel, fsmem, configured_fw);
     if (e != cudaSuccess) return e;
-    hess_forward_kernel<<<dim3((4 * a.H + 7) / 8, n_env), kFwThreads, fsmem, st>>>(a);
+    hess_forward_kernel<<<dim3((4 * a.H + kFwChains - 1) / kFwChains, n_env), kFwThreads, fsmem, st>>>(a);
     return cudaGetLastError();
 }
 
