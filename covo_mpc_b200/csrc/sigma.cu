@@ -869,11 +869,15 @@ __global__ void __launch_bounds__(kQaccWarps * 32) qacc_kernel(const SigmaArgs a
 }
 
 // ---------------------------------------------------------------------------------------------
-// E3: Sigma = Q F Q^T = P^T F P with P = Q^T from E1 and the symmetric F from E2: one launch, grid of 32 x 16
-// output tiles of the lower triangle (mirrored on store).  Each CTA first forms Z = F P[:, J] (n x 16, kept in shared memory; recomputed by the CTAs
-// that share J -- 0.6 MFLOP, cheaper than a second launch), then Sigma[I, J] = P[:, I]^T Z.
+// E3: Sigma = Q F Q^T = P^T F P with P = Q^T from E1b and the symmetric F from E2, one launch.  CTA J owns JW
+// columns of the result: Z = F P[:, J] (thread k = row k of Z, F streamed through shared memory row by row --
+// F is symmetric, so "row l, element k" is read with consecutive k), then Sigma[i, J] = sum_k P[k][i] Z[k][:]
+// (thread i, P streamed the same way), for the rows i on or below the diagonal; the tile is stored together with
+// its mirror image, so Sigma is exactly symmetric by construction (controllers/covo.py:132 symmetrises its product
+// the same way up to rounding) and the Cholesky kernel can skip its symmetrisation pass.
+// JW = 8 (25 CTAs per matrix) for latency, 16 for batches (half the L2 -> SM streaming per matrix).
 // ---------------------------------------------------------------------------------------------
-constexpr int kSwI = 32, kSwJ = 16, kSwThreads = 256, kSwChunk = 32;
+constexpr int kSwThreads = 256, kSwChunk = 32;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -885,111 +889,95 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-__host__ __device__ inline size_t sandwich_smem_bytes(int n) {
-    return (size_t)n * (2 * kSwJ + kSwI + 2 * kSwChunk) * sizeof(float);
+__host__ __device__ inline size_t sandwich_smem_bytes(int n, int jw) {
+    return (size_t)n * (2 * jw + 2 * kSwChunk) * sizeof(float);
 }
 
+template <int JW>
 __global__ void __launch_bounds__(kSwThreads) sandwich_kernel(const float* __restrict__ Qt, const float* __restrict__ F,
                                                              float* __restrict__ cov, int n) {
     extern __shared__ __align__(16) float ssm[];
-    float* Pj = ssm;                 // [n][16]  P[:, J]
-    float* Zs = Pj + n * kSwJ;       // [n][16]  Z = F P[:, J]
-    float* Pi = Zs + n * kSwJ;       // [n][32]  P[:, I]
-    float* Fs = Pi + n * kSwI;       // [2][32][n]  row chunks of F, double-buffered (cp.async)
-    const int env = blockIdx.z, tid = threadIdx.x;
-    const int I0 = blockIdx.x * kSwI, J0 = blockIdx.y * kSwJ;
-    if (I0 + kSwI - 1 < J0) return;  // only tiles that touch the lower triangle: the result is mirrored
+    float* Pj = ssm;                 // [n][JW]  P[:, J]
+    float* Zs = Pj + n * JW;         // [n][JW]  Z = F P[:, J]
+    float* Rs = Zs + n * JW;         // [2][32][n]  row chunks of F, then of P, double-buffered (cp.async)
+    const int env = blockIdx.y, tid = threadIdx.x;
+    const int J0 = blockIdx.x * JW;
     Qt += (long long)env * n * n;
     F += (long long)env * n * n;
     cov += (long long)env * n * n;
     const int nv4 = n >> 2;
-    auto prefetch_F = [&](int c) {
+    const int nch = (n + kSwChunk - 1) / kSwChunk;
+    auto prefetch = [&](const float* M, int c, int slot) {
         const int l0 = c * kSwChunk, rows = min(kSwChunk, n - l0);
-        float* dst = Fs + (c & 1) * kSwChunk * n;
-        for (int idx = tid; idx < rows * nv4; idx += kSwThreads) cp_async16(dst + 4 * idx, F + (long long)l0 * n + 4 * idx);
+        float* dst = Rs + slot * kSwChunk * n;
+        for (int idx = tid; idx < rows * nv4; idx += kSwThreads) cp_async16(dst + 4 * idx, M + (long long)l0 * n + 4 * idx);
         cp_async_commit();
     };
-    // P[:, J] and P[:, I] (16-byte pieces; pieces beyond column n are zero-filled)
-    for (int idx = tid; idx < n * (kSwJ / 4); idx += kSwThreads) {
-        const int l = idx >> 2, q4 = idx & 3;
-        if (J0 + 4 * q4 < n) cp_async16(Pj + l * kSwJ + 4 * q4, Qt + (long long)l * n + J0 + 4 * q4);
-        else *reinterpret_cast<float4*>(Pj + l * kSwJ + 4 * q4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    // P[:, J] (16-byte pieces; pieces beyond column n are zero-filled)
+    for (int idx = tid; idx < n * (JW / 4); idx += kSwThreads) {
+        const int l = idx / (JW / 4), q4 = idx - l * (JW / 4);
+        if (J0 + 4 * q4 < n) cp_async16(Pj + l * JW + 4 * q4, Qt + (long long)l * n + J0 + 4 * q4);
+        else *reinterpret_cast<float4*>(Pj + l * JW + 4 * q4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int idx = tid; idx < n * (kSwI / 4); idx += kSwThreads) {
-        const int l = idx >> 3, q4 = idx & 7;
-        if (I0 + 4 * q4 < n) cp_async16(Pi + l * kSwI + 4 * q4, Qt + (long long)l * n + I0 + 4 * q4);
-        else *reinterpret_cast<float4*>(Pi + l * kSwI + 4 * q4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    prefetch_F(0);
-    // Z[k][:] for k = tid: F is symmetric, so column k is read as F[l][k] -- consecutive k, conflict-free
-    float acc[kSwJ];
+    prefetch(F, 0, 0);
+    float acc[JW];
+    // ---- pass 1: Z[k][:] = sum_l F[l][k] P[l][J], thread k; pass 2: Sigma[i][J] = sum_k P[k][i] Z[k][:], thread i
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const float* M = pass ? Qt : F;
+        const float* B = pass ? Zs : Pj;
 #pragma unroll
-    for (int jj = 0; jj < kSwJ; ++jj) acc[jj] = 0.f;
-    const int nch = (n + kSwChunk - 1) / kSwChunk;
-    for (int c = 0; c < nch; ++c) {
-        if (c + 1 < nch) {
-            prefetch_F(c + 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        if (tid < n) {
-            const int l0 = c * kSwChunk, rows = min(kSwChunk, n - l0);
-            const float* fb = Fs + (c & 1) * kSwChunk * n + tid;
+        for (int jj = 0; jj < JW; ++jj) acc[jj] = 0.f;
+        for (int c = 0; c < nch; ++c) {
+            // chunk c sits in slot (pass * nch + c) & 1; the next chunk (of this pass or the first of the next) is prefetched
+            const int g = pass * nch + c;
+            if (c + 1 < nch) {
+                prefetch(M, c + 1, (g + 1) & 1);
+                cp_async_wait<1>();
+            } else if (pass == 0) {
+                prefetch(Qt, 0, (g + 1) & 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+            if (tid < n) {
+                const int l0 = c * kSwChunk, rows = min(kSwChunk, n - l0);
+                const float* fb = Rs + (g & 1) * kSwChunk * n + tid;
 #pragma unroll 4
-            for (int l = 0; l < rows; ++l) {
-                const float f = fb[l * n];
-                const float4* pr = reinterpret_cast<const float4*>(Pj + (l0 + l) * kSwJ);
+                for (int l = 0; l < rows; ++l) {
+                    const float f = fb[l * n];
+                    const float4* pr = reinterpret_cast<const float4*>(B + (l0 + l) * JW);
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const float4 pv = pr[q4];
-                    acc[4 * q4 + 0] = fmaf(f, pv.x, acc[4 * q4 + 0]);
-                    acc[4 * q4 + 1] = fmaf(f, pv.y, acc[4 * q4 + 1]);
-                    acc[4 * q4 + 2] = fmaf(f, pv.z, acc[4 * q4 + 2]);
-                    acc[4 * q4 + 3] = fmaf(f, pv.w, acc[4 * q4 + 3]);
+                    for (int q4 = 0; q4 < JW / 4; ++q4) {
+                        const float4 pv = pr[q4];
+                        acc[4 * q4 + 0] = fmaf(f, pv.x, acc[4 * q4 + 0]);
+                        acc[4 * q4 + 1] = fmaf(f, pv.y, acc[4 * q4 + 1]);
+                        acc[4 * q4 + 2] = fmaf(f, pv.z, acc[4 * q4 + 2]);
+                        acc[4 * q4 + 3] = fmaf(f, pv.w, acc[4 * q4 + 3]);
+                    }
                 }
             }
+            __syncthreads();  // the slot is refilled two chunks later
         }
-        __syncthreads();  // the buffer is refilled two chunks later
-    }
-    if (tid < n) {
+        if (pass == 0) {
+            if (tid < n) {
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-            reinterpret_cast<float4*>(Zs + tid * kSwJ)[q4] = make_float4(acc[4 * q4], acc[4 * q4 + 1], acc[4 * q4 + 2], acc[4 * q4 + 3]);
-    }
-    __syncthreads();
-    // Sigma[I0 + ii][J0 + jj .. +1] = sum_k P[k][I0 + ii] Z[k][jj]: thread = (ii, pair of jj)
-    {
-        const int ii = tid & 31, jp = tid >> 5;  // jp = 0..7 -> columns 2 jp, 2 jp + 1
-        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-        int k = 0;
-        for (; k + 1 < n; k += 2) {
-            const float p0 = Pi[k * kSwI + ii], p1 = Pi[(k + 1) * kSwI + ii];
-            const float2 z0 = *reinterpret_cast<const float2*>(Zs + k * kSwJ + 2 * jp);
-            const float2 z1 = *reinterpret_cast<const float2*>(Zs + (k + 1) * kSwJ + 2 * jp);
-            a0 = fmaf(p0, z0.x, a0);
-            a1 = fmaf(p0, z0.y, a1);
-            b0 = fmaf(p1, z1.x, b0);
-            b1 = fmaf(p1, z1.y, b1);
-        }
-        for (; k < n; ++k) {
-            const float p0 = Pi[k * kSwI + ii];
-            a0 = fmaf(p0, Zs[k * kSwJ + 2 * jp], a0);
-            a1 = fmaf(p0, Zs[k * kSwJ + 2 * jp + 1], a1);
-        }
-        // lower triangle + mirror image: Sigma is exactly symmetric by construction (controllers/covo.py:132
-        // symmetrises its product the same way up to rounding)
-        const int i = I0 + ii, j = J0 + 2 * jp;
-        if (i < n) {
-            const float s0 = a0 + b0, s1 = a1 + b1;
-            if (j <= i) {
-                cov[(long long)i * n + j] = s0;
-                if (j < i) cov[(long long)j * n + i] = s0;
+                for (int q4 = 0; q4 < JW / 4; ++q4)
+                    reinterpret_cast<float4*>(Zs + tid * JW)[q4] = make_float4(acc[4 * q4], acc[4 * q4 + 1], acc[4 * q4 + 2], acc[4 * q4 + 3]);
             }
-            if (j + 1 <= i) {
-                cov[(long long)i * n + j + 1] = s1;
-                if (j + 1 < i) cov[(long long)(j + 1) * n + i] = s1;
+            __syncthreads();
+        }
+    }
+    // lower triangle + mirror image
+    if (tid < n) {
+        const int i = tid;
+#pragma unroll
+        for (int jj = 0; jj < JW; ++jj) {
+            const int j = J0 + jj;
+            if (j <= i && j < n) {
+                cov[(long long)i * n + j] = acc[jj];
+                if (j < i) cov[(long long)j * n + i] = acc[jj];
             }
         }
     }
@@ -1337,12 +1325,18 @@ cudaError_t launch_trifunc(const SigmaArgs& a, int n_env, cudaStream_t st) {
 cudaError_t launch_sandwich(const SigmaArgs& a, int n_env, cudaStream_t st) {
     if (a.n > kSigmaMaxN || (a.n & 3)) return cudaErrorInvalidValue;
     cudaError_t e;
-    dim3 g((a.n + kSwI - 1) / kSwI, (a.n + kSwJ - 1) / kSwJ, n_env);
-    const size_t sw_bytes = sandwich_smem_bytes(a.n);
-    static size_t conf_sw[32] = {};
-    e = ensure_smem_attr(sandwich_kernel, sw_bytes, conf_sw);
-    if (e != cudaSuccess) return e;
-    sandwich_kernel<<<g, kSwThreads, sw_bytes, st>>>(a.Qt, a.F, a.cov, a.n);
+    static size_t conf8[32] = {}, conf16[32] = {};
+    if (n_env <= 18) {
+        const size_t bytes = sandwich_smem_bytes(a.n, 8);
+        e = ensure_smem_attr(sandwich_kernel<8>, bytes, conf8);
+        if (e != cudaSuccess) return e;
+        sandwich_kernel<8><<<dim3((a.n + 7) / 8, n_env), kSwThreads, bytes, st>>>(a.Qt, a.F, a.cov, a.n);
+    } else {
+        const size_t bytes = sandwich_smem_bytes(a.n, 16);
+        e = ensure_smem_attr(sandwich_kernel<16>, bytes, conf16);
+        if (e != cudaSuccess) return e;
+        sandwich_kernel<16><<<dim3((a.n + 15) / 16, n_env), kSwThreads, bytes, st>>>(a.Qt, a.F, a.cov, a.n);
+    }
     return cudaGetLastError();
 }
 
