@@ -237,8 +237,8 @@ constexpr int kTilePitch = 36;       // floats; rows of the transposition tile a
 
 __host__ __device__ inline size_t e1_smem_bytes(int n, int c2) {
     // reflector store Vs [n][n]; q[2][256], v[2][256], row[2][256], tau[256], d[256], e[256]; transposition tiles;
-    // mbarrier pair; reduction scratch
-    return ((size_t)n * n + 256 * 9 + EW * 2 * c2 * kTilePitch + 4 + EW * 64) * sizeof(float);
+    // mbarrier pair; reduction scratch; landing pad of the per-warp progress signals
+    return ((size_t)n * n + 256 * 9 + EW * 2 * c2 * kTilePitch + 4 + EW * 64 + 64) * sizeof(float);
 }
 
 __device__ __forceinline__ void cluster_barrier() {
@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
     const int gw = rank * EW + warp;        // global warp: owns columns 2 gw + CS c, 2 gw + CS c + 1
     constexpr int GW = EW * NC;             // warps of the cluster
     constexpr int CS = 2 * GW;              // column stride between pair slots
+    const int n_idle = GW - min(GW, n >> 1);  // warps that own no column at all (n < 2 GW)
     float* Vs = esm;                    // [n][n] reflectors (row k = v_k), every CTA keeps a copy
     float* qsm0 = esm + n * n;          // [2][256]
     float* vsm0 = qsm0 + 512;           // [2][256]
@@ -327,6 +328,7 @@ __global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
     float* tile = esm_e + 256 + warp * 2 * C2 * kTilePitch;  // [2 C2][36] private transposition tile
     unsigned long long* mbars = reinterpret_cast<unsigned long long*>(esm_e + 256 + EW * 2 * C2 * kTilePitch);  // [2]
     float* red = esm_e + 256 + EW * 2 * C2 * kTilePitch + 4 + warp * 64;  // [2][32] private reduction scratch
+    float* pad = esm_e + 256 + EW * 2 * C2 * kTilePitch + 4 + EW * 64;     // [64] landing pad of the progress signals
 
     const float* Rg = a.R + (long long)env * n * n;
     float* Vg = a.Vh + (long long)env * n * n;
@@ -357,9 +359,10 @@ __global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
         }
     }
     // shared::cluster addresses of the exchange buffers and of the mbarrier pair in every CTA of the cluster
-    unsigned q_remote[NC], row_remote[NC], bar_remote[NC];
+    unsigned q_remote[NC], row_remote[NC], bar_remote[NC], pad_remote[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
+        pad_remote[k] = dsmem_addr((unsigned)__cvta_generic_to_shared(pad), k);
         q_remote[k] = dsmem_addr((unsigned)__cvta_generic_to_shared(qsm0), k);
         row_remote[k] = dsmem_addr((unsigned)__cvta_generic_to_shared(row0), k);
         bar_remote[k] = dsmem_addr(mbar_local, k);
@@ -509,6 +512,17 @@ __global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
             }
             __syncwarp();  // the tile is rewritten in the next step
         }
+        // Progress signal.  A phase must complete only when EVERY warp of the cluster is done reading the step's
+        // buffers (they are overwritten in the next step).  Normally the q entries a warp sends after its reads say
+        // so; when no q is exchanged (tau = 0, the last two steps) or the warp owns no column (tiny n), it sends
+        // 4 bytes to every CTA instead.
+        if (!do_matvec || 2 * gw >= n) {  // warp-uniform
+            __syncwarp();                 // every lane is past its reads
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < NC; ++k) dsmem_st_signal(pad_remote[k] + 4 * gw, 0.f, bar_remote[k] + bar_off);
+            }
+        }
         if (warp == (m & (EW - 1))) {  // bookkeeping by a rotating warp (every CTA keeps its own copy)
 #pragma unroll
             for (int r = 0; r < RS; ++r) {
@@ -524,8 +538,10 @@ __global__ void __launch_bounds__(ET, 1) tridiag_reg_kernel(const SigmaArgs a) {
                 taus[m] = ntau;
             }
             __syncwarp();
-            // this step's incoming traffic: column m+1 (7 x 32 floats) and, if the matvec runs, the n entries of q
-            if (lane == 0) mbar_expect_tx(mbar_local + bar_off, ((m + 1 < n) ? 4u * 32u * RS : 0u) + (do_matvec ? 4u * n : 0u));
+            // this step's incoming traffic: column m+1 (7 x 32 floats), the n entries of q if the matvec runs, and one
+            // progress signal from every warp of the cluster
+            if (lane == 0)
+                mbar_expect_tx(mbar_local + bar_off, ((m + 1 < n) ? 4u * 32u * RS : 0u) + (do_matvec ? 4u * (n + n_idle) : 4u * GW));
         }
         PH(2);
         // everything this CTA reads in step m+1 has landed when its mbarrier phase completes

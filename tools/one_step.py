@@ -12,7 +12,8 @@ from covo_mpc_b200 import _lib  # noqa: E402
 
 
 def main():
-    N, H = 8192, 50
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+    H = int(sys.argv[2]) if len(sys.argv) > 2 else 50
     p = o.EnvParams()
     rng = np.random.default_rng(100)
     s = o.reset_env("tracking_zigzag", p, rng, dtype=np.float32, zero_disturb=True)
