@@ -1275,10 +1275,10 @@ static cudaError_t launch_e1(const SigmaArgs& a, int n_env, cudaStream_t st) {
 
 // Cluster width of E1 (CTAs per matrix).  Few matrices: spread each one over 4 SMs (latency); many matrices
 // (batched environments, the offline schedule): 2 SMs each, which still fills the machine.
-static int e1_cluster_override() {  // COVO_E1_CLUSTER = 2 | 4 | 8 pins the cluster width (tuning, tests)
+static int e1_cluster_override() {  // COVO_E1_CLUSTER = 1 | 2 | 4 | 8 pins the cluster width (tuning, tests)
     const char* e = getenv("COVO_E1_CLUSTER");
     const int v = e ? atoi(e) : 0;
-    return (v == 2 || v == 4 || v == 8) ? v : 0;
+    return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 0;
 }
 
 cudaError_t launch_tridiag(const SigmaArgs& a, int n_env, cudaStream_t st) {
@@ -1288,7 +1288,15 @@ cudaError_t launch_tridiag(const SigmaArgs& a, int n_env, cudaStream_t st) {
     if (a.n <= 64) nc = min(nc, 2);
     else if (a.n <= 128) nc = min(nc, 4);
     // column-pair slots per warp: n <= 16 NC C2
-    if (nc >= 8) {
+    if (nc == 1) {  // one SM per matrix (only through COVO_E1_CLUSTER=1: register spills make it slower than 2 CTAs)
+        switch ((a.n + 15) / 16) {
+            case 1: case 2: case 3: case 4: e = launch_e1<4, 1>(a, n_env, st); break;
+            case 5: case 6: case 7: case 8: e = launch_e1<8, 1>(a, n_env, st); break;
+            case 9: case 10: e = launch_e1<10, 1>(a, n_env, st); break;
+            case 11: case 12: case 13: e = launch_e1<13, 1>(a, n_env, st); break;
+            default: e = launch_e1<14, 1>(a, n_env, st); break;
+        }
+    } else if (nc >= 8) {
         e = (a.n <= 128) ? launch_e1<1, 8>(a, n_env, st) : launch_e1<2, 8>(a, n_env, st);
     } else if (nc >= 4) {
         switch ((a.n + 63) / 64) {
@@ -1297,7 +1305,7 @@ cudaError_t launch_tridiag(const SigmaArgs& a, int n_env, cudaStream_t st) {
             case 3: e = launch_e1<3, 4>(a, n_env, st); break;
             default: e = launch_e1<4, 4>(a, n_env, st); break;
         }
-    } else {  // 2 CTAs per matrix (the accumulated Q^T needs the register space of at least two SMs at n > 112)
+    } else {  // 2 CTAs per matrix
         switch ((a.n + 31) / 32) {
             case 1: e = launch_e1<1, 2>(a, n_env, st); break;
             case 2: e = launch_e1<2, 2>(a, n_env, st); break;

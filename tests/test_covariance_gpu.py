@@ -97,9 +97,9 @@ def test_sigma_batched_envs():
         assert np.linalg.norm(S[e] - So) / np.linalg.norm(So) < 2e-5
 
 
-@pytest.mark.parametrize("nc", [2, 4, 8])
+@pytest.mark.parametrize("nc", [1, 2, 4, 8])
 def test_sigma_cluster_widths_agree(nc, monkeypatch):
-    """The tridiagonalisation spreads one matrix over 2, 4 or 8 CTAs of a cluster (batched environments use the
+    """The tridiagonalisation spreads one matrix over 1, 2, 4 or 8 CTAs of a cluster (batched environments use the
     narrow ones): every width must deliver the same covariance at the headline size n = 200."""
     p, ns, a_mean, rng = scenario("tracking_zigzag", seed=3, H=50, warm_steps=20)
     R = o.get_hessian(ns, a_mean, p, dtype=np.float64).astype(np.float32)
