@@ -1,5 +1,5 @@
 """Four CoVO-online MPC steps at the headline size (N=8192, H=50) and nothing else: the target of the ncu captures
-(`-s 24 -c 8` = the 8 kernels of the fourth step).  GPU box only."""
+(`-s 27 -c 9` = the 9 kernels of the fourth step).  GPU box only."""
 import os
 import sys
 

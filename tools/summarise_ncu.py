@@ -15,7 +15,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
-GROUP = {"hess_local": "hessian", "hess_assemble": "hessian", "hess_forward": "hessian", "tridiag_reg": "tridiag", "sigma_trifunc": "trifunc",
+GROUP = {"hess_local": "hessian", "hess_assemble": "hessian", "hess_forward": "hessian", "tridiag_reg": "tridiag", "qacc": "qacc", "sigma_trifunc": "trifunc",
          "sandwich": "sandwich", "cholesky": "cholesky", "rollout": "rollout"}
 
 
