@@ -250,19 +250,30 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
                 const float4 la0 = *reinterpret_cast<const float4*>(col + 8 * gA);
                 const float4 la1 = *reinterpret_cast<const float4*>(col + 8 * gA + 4);
                 const float ev[4] = {e.x, e.y, e.z, e.w};
-                const float lav[8] = {la0.x, la0.y, la0.z, la0.w, la1.x, la1.y, la1.z, la1.w};
+                // packed FFMA2: one instruction per (sample, pair of rows)
+                const float2 la2[4] = {make_float2(la0.x, la0.y), make_float2(la0.z, la0.w), make_float2(la1.x, la1.y),
+                                       make_float2(la1.z, la1.w)};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) accA[i][j] = fmaf(ev[i], lav[j], accA[i][j]);
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 r = __ffma2_rn(make_float2(ev[i], ev[i]), la2[j], make_float2(accA[i][2 * j], accA[i][2 * j + 1]));
+                        accA[i][2 * j] = r.x;
+                        accA[i][2 * j + 1] = r.y;
+                    }
                 if (hasB) {
                     const float4 lb0 = *reinterpret_cast<const float4*>(col + 8 * gB);
                     const float4 lb1 = *reinterpret_cast<const float4*>(col + 8 * gB + 4);
-                    const float lbv[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
+                    const float2 lb2[4] = {make_float2(lb0.x, lb0.y), make_float2(lb0.z, lb0.w), make_float2(lb1.x, lb1.y),
+                                           make_float2(lb1.z, lb1.w)};
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) accB[i][j] = fmaf(ev[i], lbv[j], accB[i][j]);
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 r = __ffma2_rn(make_float2(ev[i], ev[i]), lb2[j], make_float2(accB[i][2 * j], accB[i][2 * j + 1]));
+                            accB[i][2 * j] = r.x;
+                            accB[i][2 * j + 1] = r.y;
+                        }
                 }
                 off += n_pad - (k & ~7);
             }
@@ -273,11 +284,16 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
                 const float4 lb0 = *reinterpret_cast<const float4*>(col + 8 * gB);
                 const float4 lb1 = *reinterpret_cast<const float4*>(col + 8 * gB + 4);
                 const float ev[4] = {e.x, e.y, e.z, e.w};
-                const float lbv[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
+                const float2 lb2[4] = {make_float2(lb0.x, lb0.y), make_float2(lb0.z, lb0.w), make_float2(lb1.x, lb1.y),
+                                       make_float2(lb1.z, lb1.w)};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) accB[i][j] = fmaf(ev[i], lbv[j], accB[i][j]);
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 r = __ffma2_rn(make_float2(ev[i], ev[i]), lb2[j], make_float2(accB[i][2 * j], accB[i][2 * j + 1]));
+                        accB[i][2 * j] = r.x;
+                        accB[i][2 * j + 1] = r.y;
+                    }
                 off += n_pad - (k & ~7);
             }
         }
