@@ -64,6 +64,7 @@ struct RolloutArgs {
     long long lfac_stride;   // floats between environments in Lfac
     long long lfac_time_stride;  // CoVO-offline: factor table indexed by min(time, lfac_time_max)
     int lfac_time_max;
+    int overlap = 0;  // set by launch_rollout: sampling GEMM and rollouts run concurrently (separate U tile fits in smem)
 };
 
 struct MergeArgs {

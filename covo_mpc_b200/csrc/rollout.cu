@@ -73,7 +73,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 struct Smem {
     float* lfac;   // packed Lt (dense) or Lblk [H][16]
-    float* tile;   // E then U: [n_pad][TSP]
+    float* tile;   // E (then U when the phases are not overlapped): [n_pad][TSP]
+    float* utile;  // U: [n_pad][TSP]; a separate region when GEMM and rollouts overlap, else == tile
+    int* prog;     // [8] progress of the GEMM warps (overlap mode)
     float* mu;     // [n_pad]
     float* ref;    // [H][8]: pos_tar(3), vel_tar(3), fdist(2 of 3 -> see fds)
     float* fds;    // [H][4]: disturbance force acting during step h
@@ -83,13 +85,20 @@ struct Smem {
     uint64_t* bar;
 };
 
-__device__ __forceinline__ Smem carve(unsigned char* base, int n_pad, int H, int lfac_floats) {
+__device__ __forceinline__ Smem carve(unsigned char* base, int n_pad, int H, int lfac_floats, int overlap) {
     Smem s;
     float* f = reinterpret_cast<float*>(base);
     s.lfac = f;
     f += (lfac_floats + 3) & ~3;
     s.tile = f;
     f += n_pad * TSP;
+    s.utile = s.tile;
+    if (overlap) {
+        s.utile = f;
+        f += n_pad * TSP;
+    }
+    s.prog = reinterpret_cast<int*>(f);
+    f += 8;
     s.mu = f;
     f += n_pad;
     s.ref = f;
@@ -108,12 +117,17 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int n_pad, int H, int
 
 }  // namespace
 
-size_t rollout_smem_bytes(int n_pad, int mode, int H) {
+static size_t rollout_smem_bytes2(int n_pad, int mode, int H, int overlap) {
     int lf = (mode == 0) ? lt_size(4 * H, n_pad) : H * 16;
     lf = (lf + 3) & ~3;
-    size_t floats = (size_t)lf + (size_t)n_pad * TSP + n_pad + H * 8 + H * 4 + TS + TS + 32;
+    size_t floats = (size_t)lf + (size_t)n_pad * TSP * (overlap ? 2 : 1) + 8 + n_pad + H * 8 + H * 4 + TS + TS + 32;
     return floats * sizeof(float) + 16;
 }
+// GEMM / rollout overlap needs a second [n_pad][TSP] tile: possible while everything fits into 227 KB (n <= 208)
+static int rollout_overlap(int n_pad, int mode, int H) {
+    return mode == 0 && rollout_smem_bytes2(n_pad, mode, H, 1) <= (size_t)227 * 1024;
+}
+size_t rollout_smem_bytes(int n_pad, int mode, int H) { return rollout_smem_bytes2(n_pad, mode, H, rollout_overlap(n_pad, mode, H)); }
 
 __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const RolloutArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -121,7 +135,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
     const int env = blockIdx.y;
     const int n = a.n, n_pad = a.n_pad, H = a.H;
     const int lfac_floats = (a.mode == 0) ? lt_size(n, n_pad) : H * 16;
-    Smem sm = carve(smem_raw, n_pad, H, lfac_floats);
+    Smem sm = carve(smem_raw, n_pad, H, lfac_floats, a.overlap);
     const int tile0 = blockIdx.x * TS;                       // first local sample of this tile
     const int n_valid = min(TS, a.n_samples - tile0);        // valid samples in this tile
     const float* lfac_g = a.Lfac + (long long)env * a.lfac_stride;
@@ -132,6 +146,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
     if (tid == 0) {
         mbar_init(sm.bar, 1);
     }
+    if (tid < 8) sm.prog[tid] = -1;
     __syncthreads();
     if (tid == 0) {
         const uint32_t total = (uint32_t)lfac_floats * 4u;
@@ -224,8 +239,60 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
     mbar_wait(sm.bar, 0);
     COVO_STAMP(a, 34);
 
+    // ---------------- phases 1 + 2 overlapped ------------------------------------------------------
+    // Four GEMM warps produce U = clip(mu + E L^T) row group by row group (8 rows = two horizon steps; warp j takes the
+    // groups j, j+4, ...; a lane owns 4 samples x 4 rows, 8 packed FFMA2 per k) into a SEPARATE tile, while the two
+    // rollout warps consume it step by step -- the triangular GEMM (14 us) hides behind the 50 serial rollout steps
+    // (18 us) instead of preceding them.  The GEMM warps are 2, 3, 6, 7, i.e. schedulers 2 and 3: the rollout
+    // warps (0, 1) keep schedulers 0 and 1 and their FMA pipes to themselves (with GEMM warps next to them the
+    // latency-bound rollout chain ran 50 % slower); warps 4 and 5 sit this phase out.
+    const bool overlapped = (a.mode == 0) && a.overlap;
+    constexpr int kGemmSlots = 4;
+    if (overlapped && tid >= TS && ((tid >> 5) & 2)) {
+        const int lane = tid & 31, w = tid >> 5, slot = (w & 1) + ((w >> 2) << 1);  // 2,3,6,7 -> 0,1,2,3
+        const int sg = lane & 15, rq = lane >> 4;
+        const int G = n_pad >> 3;
+        volatile int* prog = sm.prog;
+        for (int g = slot; g < G; g += kGemmSlots) {
+            const int K = min(8 * g + 8, n);
+            const float* Erow = sm.tile + 4 * sg;
+            float2 acc[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+            int off = 0;  // lt_col_offset(k)
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+                const float4 e = *reinterpret_cast<const float4*>(Erow + k * TSP);
+                const float4 l = *reinterpret_cast<const float4*>(sm.lfac + off - (k & ~7) + 8 * g + 4 * rq);
+                const float2 l01 = make_float2(l.x, l.y), l23 = make_float2(l.z, l.w);
+                const float ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][0] = __ffma2_rn(make_float2(ev[i], ev[i]), l01, acc[i][0]);
+                    acc[i][1] = __ffma2_rn(make_float2(ev[i], ev[i]), l23, acc[i][1]);
+                }
+                off += n_pad - (k & ~7);
+            }
+            const int r0 = 8 * g + 4 * rq;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float m = sm.mu[r0 + j];
+                float4 o;
+                o.x = clip_(m + ((j & 1) ? acc[0][j >> 1].y : acc[0][j >> 1].x), -1.f, 1.f);
+                o.y = clip_(m + ((j & 1) ? acc[1][j >> 1].y : acc[1][j >> 1].x), -1.f, 1.f);
+                o.z = clip_(m + ((j & 1) ? acc[2][j >> 1].y : acc[2][j >> 1].x), -1.f, 1.f);
+                o.w = clip_(m + ((j & 1) ? acc[3][j >> 1].y : acc[3][j >> 1].x), -1.f, 1.f);
+                *reinterpret_cast<float4*>(sm.utile + (r0 + j) * TSP + 4 * sg) = o;
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) prog[slot] = g;
+        }
+    }
     // ---------------- phase 1: U = clip(mu + E L^T) ------------------------------------------
-    if (a.mode == 0) {
+    if (overlapped) {
+        // done by the GEMM warps above, concurrently with phase 2
+    } else if (a.mode == 0) {
         const int SG = TS / 4;
         const int G = n_pad >> 3;
         const int NP = (G + 1) >> 1;
@@ -340,15 +407,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
             for (int r = 0; r < 4; ++r) sm.tile[(4 * h + r) * TSP + s] = u[r];
         }
     }
-    __syncthreads();
-
-    if (a.samples_out) {
-        float* og = a.samples_out + ((long long)env * a.n_samples + tile0) * n;
-        for (int i = tid; i < TS * n; i += blockDim.x) {
-            int s = i / n, r = i % n;
-            if (s < n_valid) og[(long long)s * n + r] = sm.tile[r * TSP + s];
-        }
-    }
+    if (!overlapped) __syncthreads();
 
     COVO_STAMP(a, 35);
     // ---------------- phase 2: rollouts --------------------------------------------------------
@@ -373,9 +432,18 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
             // reward / done of the PRE-step state (envs/quadrotor.py:243-244)
             float r = quad_reward(s, pt, vt);
             bool done = quad_terminal(s, t0 + h, env_c);
+            if (overlapped && !(h & 1)) {  // rows 4h .. 4h+7 belong to row group h/2: wait for its GEMM warp
+                const int g = h >> 1;
+                volatile int* prog = sm.prog;
+                if ((tid & 31) == 0)
+                    while (prog[g % 4] < g) {
+                    }
+                __syncwarp();
+                __threadfence_block();
+            }
             float u[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) u[c] = sm.tile[(4 * h + c) * TSP + tid];
+            for (int c = 0; c < 4; ++c) u[c] = sm.utile[(4 * h + c) * TSP + tid];
             quad_step(s, u, fdh, env_c);
             r = done_before ? reward_before : r;  // controllers/covo.py:233
             reward_before = r;
@@ -399,6 +467,13 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
         if ((tid & 31) == 0) sm.red[tid >> 5] = m;
     }
     __syncthreads();
+    if (a.samples_out) {
+        float* og = a.samples_out + ((long long)env * a.n_samples + tile0) * n;
+        for (int i = tid; i < TS * n; i += blockDim.x) {
+            int s = i / n, r = i % n;
+            if (s < n_valid) og[(long long)s * n + r] = sm.utile[r * TSP + s];
+        }
+    }
 
     COVO_STAMP(a, 36);
     // ---------------- phase 3: tile partial + grid-wide merge ---------------------------------
@@ -423,7 +498,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
     for (int r = tid; r < n_pad; r += blockDim.x) {
         float acc = 0.f;
         if (r < n) {
-            const float* row = sm.tile + r * TSP;
+            const float* row = sm.utile + r * TSP;
 #pragma unroll 4
             for (int j = 0; j < TS; ++j) {
                 int i = (j + r) & (TS - 1);  // rotated start: conflict-free across consecutive r
@@ -574,7 +649,9 @@ __global__ void merge_ranks_kernel(const MergeArgs a) {
     }
 }
 
-cudaError_t launch_rollout(const RolloutArgs& a, int n_env, cudaStream_t st) {
+cudaError_t launch_rollout(const RolloutArgs& a_in, int n_env, cudaStream_t st) {
+    RolloutArgs a = a_in;
+    a.overlap = rollout_overlap(a.n_pad, a.mode, a.H);
     size_t smem = rollout_smem_bytes(a.n_pad, a.mode, a.H);
     static size_t configured[32] = {};
     cudaError_t e = ensure_smem_attr(rollout_kernel, smem, configured);
