@@ -88,7 +88,7 @@ constexpr int kFwRec = NX * NZP + NX * 4 + 16;  // 328 floats per step handed to
 __global__ void __launch_bounds__(kAsmThreads) hess_assemble_kernel(const HessianArgs a) {
     extern __shared__ __align__(16) float smf[];
     const int env = blockIdx.x, tid = threadIdx.x;
-    const int H = a.H, n = 4 * H;
+    const int H = a.H;
     // shared layout (everything read as float4 first)
     float* S = smf;                    // [H][13][4]
     float* D = S + H * NX * 4;         // [H][4][4]
