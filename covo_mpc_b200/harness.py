@@ -4,16 +4,21 @@ of the per-episode mean ``err_pos``).  The reference's jitted ``lax.scan`` varia
 non-JAX plugin; this is the same protocol driven eagerly."""
 from __future__ import annotations
 
+import os
+import pickle
 from typing import Callable, Optional
 
 import numpy as np
 
 
 def run_episode(env, controller, rng: np.random.Generator, n_steps: Optional[int] = None, rng_act_fn: Optional[Callable] = None,
-                record: Optional[list] = None, reset_rng: Optional[np.random.Generator] = None):
+                record: Optional[list] = None, reset_rng: Optional[np.random.Generator] = None, state_seq: Optional[list] = None):
     """One episode: reset -> controller.reset -> n_steps x (controller call, env.step).
 
     rng_act_fn(step) -> the ``rng_act`` argument of each controller call (None = production RNG).
+    state_seq: if a list, one dict per step is appended in the layout ``render_env`` pickles
+    (``state.__dict__``, envs/quadrotor.py:655-666) -- the keys scripts/vis.py reads (pos, quat, pos_tar,
+    f_disturb, pos_traj) among them.
     Returns (err_pos[n_steps], rewards[n_steps])."""
     params = env.default_params
     n_steps = n_steps or params.max_steps_in_episode
@@ -24,6 +29,8 @@ def run_episode(env, controller, rng: np.random.Generator, n_steps: Optional[int
         if record is not None:
             record.append((info["noisy_state"].to_state24(), int(info["noisy_state"].time)))
         rng_act = rng_act_fn(i) if rng_act_fn else None
+        if state_seq is not None:
+            state_seq.append(dict(state.__dict__))
         action, control_params, _ = controller(obs, state, params, rng_act, control_params, info)
         obs, state, reward, done, info = env.step(rng, state, action, params)
         errs.append(info["err_pos"])
@@ -68,3 +75,23 @@ def eval_env(env, controller, total_steps: int = 300 * 4 * 10, num_trajs: int = 
             out.append(errs.mean())
     out = np.asarray(out)
     return float(out.mean()), float(out.std()), out
+
+
+def save_eval_results(err_pos_ep: np.ndarray, filename: str, results_dir: str = "results") -> str:
+    """``results/eval_err_pos_{filename}.pkl`` exactly as eval_env writes it (envs/quadrotor.py:581-591): one pickled
+    NumPy array of per-episode mean err_pos."""
+    os.makedirs(results_dir, exist_ok=True)
+    path = os.path.join(results_dir, f"eval_err_pos_{filename}.pkl")
+    with open(path, "wb") as f:
+        pickle.dump(np.asarray(err_pos_ep), f)
+    return path
+
+
+def save_state_seq(state_seq: list, filename: str, results_dir: str = "results") -> str:
+    """``results/state_seq_{filename}.pkl`` as render_env writes it (envs/quadrotor.py:655-666): a pickled list of
+    per-step state dicts, the input of scripts/vis.py:70-95."""
+    os.makedirs(results_dir, exist_ok=True)
+    path = os.path.join(results_dir, f"state_seq_{filename}.pkl")
+    with open(path, "wb") as f:
+        pickle.dump(list(state_seq), f)
+    return path

@@ -86,3 +86,22 @@ def test_termination_flags(host_check_lib):
         x[1] = pos1
         lib.hc_step(P(envp), P(x), P(u), P(z3), P(z3), P(z3), time, P(xn), ctypes.byref(r), ctypes.byref(d))
         assert d.value == exp
+
+
+def test_result_artefacts_match_the_reference_formats(tmp_path):
+    """eval_err_pos_{name}.pkl and state_seq_{name}.pkl (envs/quadrotor.py:581-591, 655-666): host-side only."""
+    import importlib.util
+    import os
+    import pickle
+
+    spec = importlib.util.spec_from_file_location("_harness", os.path.join(os.path.dirname(__file__), "..", "covo_mpc_b200", "harness.py"))
+    hz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(hz)
+    p1 = hz.save_eval_results(np.array([0.05, 0.06]), "covo_online", str(tmp_path))
+    assert os.path.basename(p1) == "eval_err_pos_covo_online.pkl"
+    assert np.allclose(pickle.load(open(p1, "rb")), [0.05, 0.06])
+    seq = [{"pos": np.zeros(3), "quat": np.array([0, 0, 0, 1.0]), "pos_tar": np.zeros(3), "f_disturb": np.zeros(3), "pos_traj": np.zeros((320, 3))}]
+    p2 = hz.save_state_seq(seq, "", str(tmp_path))
+    assert os.path.basename(p2) == "state_seq_.pkl"  # scripts/vis.py:71 loads exactly this name by default
+    back = pickle.load(open(p2, "rb"))
+    assert isinstance(back, list) and set(["pos", "quat", "pos_tar", "f_disturb", "pos_traj"]) <= set(back[0])
