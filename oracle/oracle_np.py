@@ -5,14 +5,17 @@ may import this module; only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` do, and only as
 the checker / the thing timed as the CPU baseline.
 
-PARITY UNPINNED.  The reference is pure JAX and cannot be imported in this
-container (jax, jaxlib, flax, chex, gymnax are all absent, no network) and it
-ships no tests, golden vectors or fixtures.  The arithmetic that lives in the
-un-vendored, un-pinned ``jax``/``jaxlib`` dependency (Threefry PRNG streams,
-LAPACK ``ssyevd`` / ``spotrf`` rounding, XLA's libm) is therefore restated from
-its published algorithms, not checked against reference output.  What IS pinned
-(see ``tests/test_oracle.py``): the analytic invariants the reference's maths
-guarantees, finite-difference agreement of the exact Hessian in float64, and
+PARITY: pinned by the reference's own source executed in this container under a
+NumPy stand-in for jax.numpy (tests/golden/make_reference_golden.py writes
+tests/golden/reference_*.npz; tests/test_reference_golden.py holds this module
+to them: step_env chains, geometry, reward, optimize_sigma, PID, get_controller
+defaults, whole CoVO-online / MPPI controller calls including the Hessian of the
+reference's own cost function, and the head of the covo-offline schedule).
+UNPINNED: the arithmetic that lives in the un-vendored, un-pinned ``jax`` /
+``jaxlib`` dependency -- Threefry PRNG bit-streams, XLA's float32 rounding and
+JAX's forward-mode AD itself (jax is not installable here: no wheel, no
+network).  Also checked (``tests/test_oracle.py``): analytic invariants of the
+reference's maths, finite-difference agreement of the exact Hessian in float64,
 Random123 known-answer vectors for the counter RNG.
 
 Every function cites the reference file:line (relative to /root/reference)

@@ -2,7 +2,7 @@
 
 The reference cannot be imported in this container (no jax / flax / gymnax, no network) and ships no golden
 vectors of its own, so these fixtures are ORACLE-generated: they pin the oracle against accidental change and
-give the CUDA path fixed, versioned inputs/outputs.  They are not reference output (parity stays "unpinned").
+give the CUDA path fixed, versioned inputs/outputs.  They are not reference output; the vectors produced by executing the reference itself are reference_*.npz (make_reference_golden.py).
     python tests/golden/make_golden.py
 """
 import os

@@ -106,3 +106,70 @@ def test_run_episode_device_tracks_like_the_host_loop():
     assert err_d.shape == (40,) and np.isfinite(err_d).all() and np.isfinite(rew_d).all()
     assert err_d.mean() < 3.0 * err_h.mean() + 0.05
     ctl.close()
+
+
+# ---- golden vectors produced by the reference's own source (tests/golden/make_reference_golden.py) ---------------------------
+def _golden(name):
+    import os
+
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+
+
+def test_env_step_kernel_matches_the_reference_source():
+    """Quad3D.step_env + get_info executed from /root/reference (NumPy standing in for jax.numpy) vs env_step_kernel:
+    4 chained episodes x 8 steps, crossing the |pos| > 3 box (episode 2) and time >= max_steps (episode 3)."""
+    from covo_mpc_b200 import _lib
+
+    g = _golden("reference_step_env.npz")
+    for ep in range(4):
+        h = _handle(_lib.MODE_MPPI, 64, 8, 320)
+        h.set_reference(g["pos_traj"][ep][None], g["vel_traj"][ep][None])
+        i0 = 8 * ep
+        h.env_reset(g["state24"][i0][None], [int(g["time"][i0])])
+        for i in range(i0, i0 + 8):
+            z = np.zeros((1, 16), np.float32)
+            z[0, :13] = g["noise13"][i]
+            noisy, rew, err, done = h.env_step(g["action"][i][None], noise=z)
+            s24, tm = h.env_state()
+            assert abs(rew[0] - g["reward"][i]) < 3e-6 * max(1.0, abs(g["reward"][i])), i
+            assert abs(err[0] - g["err_pos"][i]) < 3e-6 and bool(done[0]) == bool(g["done"][i]), i
+            assert int(tm[0]) == int(g["next_time"][i])
+            assert np.abs(s24[0] - g["next24"][i]).max() < 3e-6, i
+            assert np.abs(noisy[0] - g["noisy24"][i]).max() < 3e-6, i
+
+
+def test_rollout_kernel_cost_matches_the_reference_source_chain():
+    """A rollout of the recorded action sequence (zero perturbation) must cost what the reference's step_env chain paid:
+    -sum_h reward_h, the reward freezing after the first terminal pre-step state (controllers/covo.py:233)."""
+    from covo_mpc_b200 import _lib
+
+    g = _golden("reference_step_env.npz")
+    for ep in range(4):
+        h = _handle(_lib.MODE_MPPI, 64, 8, 320)
+        h.set_reference(g["pos_traj"][ep][None], g["vel_traj"][ep][None])
+        sl = slice(8 * ep, 8 * ep + 8)
+        a = np.clip(g["action"][sl], -1.0, 1.0)
+        _, _, costs, _ = h.rollout(g["state24"][8 * ep][None], [int(g["time"][8 * ep])], a[None],
+                                   eps=np.zeros((1, 64, 32), np.float32), want_costs=True)
+        r, d = g["reward"][sl].astype(np.float64), g["done"][sl]
+        total, frozen, r_before = 0.0, False, 0.0
+        for k in range(8):
+            rk = r_before if frozen else r[k]
+            total, r_before, frozen = total + rk, rk, frozen or bool(d[k])
+        assert np.abs(costs[0] + total).max() < 2e-5 * max(1.0, abs(total)), (ep, costs[0][:2], -total)
+
+
+def test_optimize_sigma_kernels_match_the_reference_source():
+    """optimize_sigma as executed from the reference (float32 LAPACK eigh) vs E1-E3."""
+    from covo_mpc_b200 import _lib
+
+    g = _golden("reference_optimize_sigma.npz")
+    off = 0
+    for H in g["H"]:
+        n = 4 * int(H)
+        R = g["R"][off:off + n * n].reshape(n, n)
+        S_ref = g["Sigma"][off:off + n * n].reshape(n, n)
+        off += n * n
+        h = _handle(_lib.MODE_COVO_ONLINE, 64, int(H), 320)
+        S = h.optimize_sigma(R[None])[0]
+        assert np.linalg.norm(S - S_ref) / np.linalg.norm(S_ref) < 5e-5, H

@@ -9,7 +9,8 @@ import pytest
 from oracle import oracle_np as o
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+# reference_*.npz are the vectors produced by the reference's own source; tests/test_reference_golden.py reads those
+FILES = sorted(f for f in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(f).startswith("reference_"))
 
 
 def _state(g):
@@ -60,3 +61,52 @@ def test_cuda_path_reproduces_golden(path):
     if not mppi:
         cov = h.get_cov()[0]
         assert np.linalg.norm(cov - g["a_cov"]) / np.linalg.norm(g["a_cov"]) < 2e-5
+
+
+# ---- vectors produced by executing the reference's own source (tests/golden/make_reference_golden.py, sections 6-8) -------
+REF_CALLS = ["reference_call_covo_online_lam0.01", "reference_call_covo_online_lam1.0", "reference_call_mppi"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", REF_CALLS)
+def test_cuda_path_reproduces_reference_call(name):
+    """One whole controller call through the C-ABI vs the same call executed from /root/reference (NumPy shim, logged draws)."""
+    from covo_mpc_b200 import _lib
+
+    g = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    mppi = "mppi" in name
+    N, H = int(g["N"]), int(g["H"])
+    cfg = _lib.default_config()
+    cfg.mode = _lib.MODE_MPPI if mppi else _lib.MODE_COVO_ONLINE
+    cfg.n_samples, cfg.horizon, cfg.traj_len, cfg.lam = N, H, g["pos_traj"].shape[0], float(g["lam"])
+    h = _lib.Handle(cfg)
+    h.set_reference(g["pos_traj"][None], g["vel_traj"][None])
+    h.set_mean(g["a_mean"][None])
+    if mppi:
+        h.set_cov(g["a_cov"][None])
+    else:
+        R = h.hessian(g["state24"], [int(g["time"])], g["a_mean"][None], shift=True)[0]
+        assert np.abs(R - g["R"]).max() < 2e-5 * np.abs(g["R"]).max()
+    act = h.step(g["state24"], [int(g["time"])], g["eps"].reshape(1, N, 4 * H))[0]
+    tol = 2e-4 if float(g["lam"]) < 0.1 else 5e-5
+    assert np.abs(act - g["action"]).max() < tol
+    assert np.abs(h.get_mean()[0] - g["a_mean_new"]).max() < tol
+    if not mppi:
+        cov = h.get_cov()[0]
+        assert np.linalg.norm(cov - g["a_cov"]) / np.linalg.norm(g["a_cov"]) < 5e-5
+
+
+@pytest.mark.gpu
+def test_cuda_offline_schedule_reproduces_reference():
+    """covo_reset_offline vs reset_a_cov_offline executed from /root/reference (first 3 table entries)."""
+    from covo_mpc_b200 import _lib
+
+    g = np.load(os.path.join(HERE, "golden", "reference_covo_offline_schedule.npz"))
+    cfg = _lib.default_config()
+    cfg.mode, cfg.n_samples, cfg.horizon, cfg.traj_len = _lib.MODE_COVO_OFFLINE, 64, int(g["H"]), g["pos_traj"].shape[0]
+    h = _lib.Handle(cfg)
+    h.set_reference(g["pos_traj"][None], g["vel_traj"][None])
+    h.reset_offline(g["state24"], [int(g["time"])], 3)
+    tab = h.get_cov_offline(3)
+    for k in range(3):
+        assert np.linalg.norm(tab[k] - g["a_cov_offline"][k]) / np.linalg.norm(g["a_cov_offline"][k]) < 1e-4, k
