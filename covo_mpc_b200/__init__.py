@@ -7,10 +7,11 @@ from . import _lib
 from ._lib import Handle, CovoConfig, default_config, MODE_MPPI, MODE_COVO_ONLINE, MODE_COVO_OFFLINE
 from .env import Quad3D, EnvParams3D, EnvState3D
 from .controllers import (BaseController, MPPIController, CoVOController, MPPIParams, CoVOParams, get_controller)
-from .harness import run_episode, run_episode_device, eval_env, save_eval_results, save_state_seq
+from . import jaxrng
+from .harness import run_episode, run_episode_device, run_episode_keyed, eval_env, save_eval_results, save_state_seq
 
 _lib.load()
 
 __all__ = ["Handle", "CovoConfig", "default_config", "MODE_MPPI", "MODE_COVO_ONLINE", "MODE_COVO_OFFLINE",
            "Quad3D", "EnvParams3D", "EnvState3D", "BaseController", "MPPIController", "CoVOController",
-           "MPPIParams", "CoVOParams", "get_controller", "run_episode", "run_episode_device", "eval_env", "save_eval_results", "save_state_seq"]
+           "MPPIParams", "CoVOParams", "get_controller", "jaxrng", "run_episode", "run_episode_device", "run_episode_keyed", "eval_env", "save_eval_results", "save_state_seq"]

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "covo_get_pos_stats": [_H, _F, _F],
     "covo_enable_pos_stats": [_H, C.c_int],
     "covo_debug_eps": [_H, C.c_uint, _F],
+    "covo_set_jax_key": [_H, C.POINTER(C.c_uint)],
     "covo_debug_tridiag": [_H, _D, _D, _D],
     "covo_zolotarev_nodes": [C.c_double, C.c_double, C.c_int, _D, _D],
     "covo_get_status": [_H, _I],
@@ -219,6 +220,13 @@ class Handle:
         check(self.lib.covo_reset_offline(self._h, fptr(s), iptr(t), t_sched))
 
     # -- the MPC step -----------------------------------------------------------------------------
+    def set_jax_key(self, act_key):
+        """The next sampling call draws what the reference would draw from ``act_key`` (covo_set_jax_key)."""
+        k = np.ascontiguousarray(act_key, dtype=np.uint32).ravel()
+        if k.size != 2:
+            raise ValueError("a JAX key is two uint32 words")
+        check(self.lib.covo_set_jax_key(self._h, k.ctypes.data_as(C.POINTER(C.c_uint))))
+
     def step(self, state24, time, eps=None) -> np.ndarray:
         s, t = f32(state24), i32(time)
         if s.size != self.E * 24 or t.size != self.E:

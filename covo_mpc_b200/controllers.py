@@ -11,7 +11,9 @@ libcovo_b200.so (hand-written sm_100a CUDA); this module only moves a 24-float s
 4-float action out per step.  There is no CPU fallback.
 
 ``rng_act`` (a JAX PRNG key in the reference):
-  * ``None`` or a 2-word uint32 key  -> production mode, Gaussian draws from the in-kernel counter RNG;
+  * ``None`` -> production mode, Gaussian draws from the in-kernel Philox counter RNG;
+  * a 2-word uint32 key (``jaxrng.PRNGKey`` / ``jaxrng.split``) -> the kernel draws what ``jax.random`` would draw from
+    that key (Threefry-2x32-20, legacy layout, SURVEY App. B): same split / normal sequence as the reference;
   * a float array of standard normals, shape (N, 4H) (CoVO) or (N, H, 4) (MPPI) -> "parity mode": the
     caller supplies exactly what ``jax.random.normal`` would have drawn (the JAX Threefry stream itself is
     un-pinned third-party arithmetic, SURVEY 8c);
@@ -27,7 +29,7 @@ from typing import Any, Optional
 
 import numpy as np
 
-from . import _lib
+from . import _lib, jaxrng
 from .env import EnvParams3D, EnvState3D, Quad3D
 
 
@@ -190,7 +192,10 @@ class _SamplingController(BaseController):
             return rng_act.standard_normal(shape).astype(np.float32)
         a = np.asarray(rng_act)
         if a.dtype.kind == "u" and a.size == 2:
-            return None  # a JAX-style key: production RNG
+            # a JAX PRNGKey: draw what the reference draws from it -- rng_act, act_key = split(rng_act); act_keys =
+            # split(act_key, N); normal(act_keys[i], ...) (controllers/covo.py:212-217, mppi.py:53-60) -- in the kernel
+            self._handle.set_jax_key(jaxrng.split(a.astype(np.uint32).reshape(2))[1])
+            return None
         if a.size != int(np.prod(shape)):
             raise ValueError(f"explicit normal draws must have shape {shape}")
         return a.astype(np.float32).reshape(shape)

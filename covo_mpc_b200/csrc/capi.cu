@@ -98,6 +98,8 @@ struct covo_handle {
     cudaStream_t aux_stream = nullptr;  // side stream of the covariance step (Q accumulation next to E2)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned int rng_stream = 0;
+    bool jax_key_pending = false;  // covo_set_jax_key: the next sampling launch uses the JAX-compatible stream
+    unsigned int jax_key[2] = {0, 0};
     bool pos_stats_on = false;
     bool profiling = false;
     bool have_factor = false;
@@ -223,6 +225,12 @@ RolloutArgs rollout_args(covo_handle* h, const float* st, const int* tm, const f
     a.env = h->env;
     a.seed = h->cfg.seed;
     a.stream = h->rng_stream;
+    if (h->jax_key_pending && !eps) {  // one-shot: consumed by this launch
+        a.rng_kind = 1;
+        a.seed = (unsigned long long)h->jax_key[0] | ((unsigned long long)h->jax_key[1] << 32);
+        a.n_total = h->cfg.n_samples;
+    }
+    h->jax_key_pending = false;
     a.state24 = st;
     a.time = tm;
     a.pos_traj = h->pos_traj.p;
@@ -1050,6 +1058,14 @@ int covo_get_pos_stats(covo_handle* h, float* pos_mean, float* pos_std) {
             pos_mean[i * 3 + k] = (float)mean;
             pos_std[i * 3 + k] = (float)sqrt(fmax(sq - mean * mean, 0.0));  // jnp.std, ddof = 0
         }
+    return COVO_OK;
+}
+
+int covo_set_jax_key(covo_handle* h, const unsigned int* act_key) {
+    if (!h || !act_key) return fail(COVO_ERR_INVALID, "null argument");
+    h->jax_key[0] = act_key[0];
+    h->jax_key[1] = act_key[1];
+    h->jax_key_pending = true;
     return COVO_OK;
 }
 

@@ -43,6 +43,8 @@ struct RolloutArgs {
     EnvConsts env;
     unsigned long long seed;
     unsigned int stream;
+    int rng_kind = 0;  // 0: Philox field (seed, stream); 1: JAX-compatible Threefry stream, seed = act_key words (lo = key[0], hi = key[1])
+    int n_total = 0;   // rng_kind 1: global sample count N (jax.random.split(act_key, N))
     // inputs (per environment e = blockIdx.y, strides below)
     const float* state24;    // [E][24]
     const int* time;         // [E]

@@ -223,6 +223,16 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
 #pragma unroll
             for (int j = 0; j < 8; ++j) sm.tile[(cb * 8 + j) * TSP + s] = v[j];
         }
+    } else if (a.rng_kind == 1) {
+        // the reference's own stream: jax.random.split / normal restated (rng.cuh); thread -> (sample tid % TS, part tid / TS)
+        const int s = tid % TS, parts = blockDim.x / TS, part = tid / TS;
+        for (int c = n + part; c < n_pad; c += parts) sm.tile[c * TSP + s] = 0.f;
+        if (s < n_valid) {
+            jax_sample_normals((uint32_t)a.seed, (uint32_t)(a.seed >> 32), (uint32_t)(a.sample_offset + tile0 + s), (uint32_t)a.n_total,
+                               n, H, a.mode == 1, part, parts, [&](int c, float z) { sm.tile[c * TSP + s] = z; });
+        } else {
+            for (int c = part; c < n; c += parts) sm.tile[c * TSP + s] = 0.f;
+        }
     } else {
         const int blocks4 = n_pad >> 2;
         for (int i = tid; i < TS * blocks4; i += blockDim.x) {

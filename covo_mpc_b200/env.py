@@ -5,8 +5,12 @@ Mirrors the surface the reference's harness uses around the controllers --
 ``default_params``, ``reset``, ``step`` and ``info["noisy_state"]``
 (quadjax/envs/quadrotor.py:23-370, quadjax/envs/base.py:15-50) -- in float32 NumPy for ONE
 environment.  It is not on the hot path (SURVEY 8f ranks the device-resident version "next"); it exists
-so that episodes can be driven through the drop-in controllers end to end.  Random draws use a NumPy
-generator: the reference's JAX Threefry streams are un-pinned third-party arithmetic.
+so that episodes can be driven through the drop-in controllers end to end.
+
+Every ``rng`` argument accepts either a ``numpy.random.Generator`` or a JAX PRNGKey (two uint32 words, see
+``jaxrng``).  With a key the function consumes it exactly as the reference does -- the same ``split`` tree, the same
+``uniform`` / ``normal`` calls in the same order -- so trajectories, initial disturbances and
+observation noise are those the reference generates from that key (up to float32 rounding of libm).
 """
 from __future__ import annotations
 
@@ -14,6 +18,8 @@ from dataclasses import dataclass, field, replace
 from typing import Optional, Tuple
 
 import numpy as np
+
+from . import jaxrng as jr
 
 F = np.float32
 
@@ -86,9 +92,14 @@ def generate_fixed_traj(max_steps: int, dt: float, rng=None):
     return z, z.copy(), z.copy()
 
 
-def generate_lissa_traj(max_steps: int, dt: float, rng: np.random.Generator):
-    amp = rng.uniform(-1.0, 1.0, size=(3, 2))
-    ph = rng.uniform(-np.pi, np.pi, size=(3, 2))
+def generate_lissa_traj(max_steps: int, dt: float, rng):
+    if jr.is_key(rng):  # dynamics/utils.py:89-94
+        key_amp, key_phase = jr.split(rng, 2)
+        amp = jr.uniform(key_amp, (3, 2), -1.0, 1.0).astype(np.float64)
+        ph = jr.uniform(key_phase, (3, 2), -np.pi, np.pi).astype(np.float64)
+    else:
+        amp = rng.uniform(-1.0, 1.0, size=(3, 2))
+        ph = rng.uniform(-np.pi, np.pi, size=(3, 2))
     ts = np.arange(0, max_steps + 50) * dt
     w1, w2 = 2 * np.pi * 0.2, 2 * np.pi * 0.4
     pos = np.stack([amp[i, 0] * np.sin(w1 * ts + ph[i, 0]) + amp[i, 1] * np.sin(w2 * ts + ph[i, 1]) for i in range(3)], 1)
@@ -98,7 +109,38 @@ def generate_lissa_traj(max_steps: int, dt: float, rng: np.random.Generator):
     return pos.astype(F), vel.astype(F), acc.astype(F)
 
 
-def generate_zigzag_traj(max_steps: int, dt: float, rng: np.random.Generator):
+def _zigzag_from_key(max_steps: int, dt: float, key):
+    """dynamics/utils.py:183-251 with the reference's key plumbing, float32 throughout: ``key_keypoints`` and ``key_angles``
+    are the same split of the same key (:187-188); the scan carry starts at keys[1] and is refreshed with keys[i + 1]
+    (clamped at the end), so segments 0 and 1 share a key (:238, :241)."""
+    point_per_seg = 40
+    num_seg = max_steps // point_per_seg + 1
+    keys = jr.split(key, num_seg)
+    prev = jr.uniform(keys[0], (3,), -1.0, 1.0)
+    prev = (prev / _norm(prev) * F(0.1)).astype(F)
+    carry = keys[1]
+    third = F(np.pi / 3)
+    ps, vs = [], []
+    for i in range(num_seg):
+        to_c = (-prev / _norm(prev)).astype(F)
+        dth, dph = jr.uniform(carry, (2,), -third, third)
+        theta = np.arccos(to_c[2]) + dth
+        phi = np.arctan2(to_c[1], to_c[0]) + dph
+        d = np.array([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)], F)
+        dist = jr.uniform(carry, (), 1.0, 1.5)
+        nxt = (prev + dist * d).astype(F)
+        ps.append(np.stack([np.linspace(prev[k], nxt[k], point_per_seg, endpoint=False) for k in range(3)], -1).astype(F))
+        vs.append(((nxt - prev) / F(point_per_seg + 1) * np.ones((point_per_seg, 3), F) / F(dt)).astype(F))
+        carry = keys[min(i + 1, num_seg - 1)]
+        prev = nxt
+    pos = np.concatenate(ps, 0)
+    pos = (pos - pos[0]).astype(F)
+    return pos, np.concatenate(vs, 0), np.zeros_like(pos)
+
+
+def generate_zigzag_traj(max_steps: int, dt: float, rng):
+    if jr.is_key(rng):
+        return _zigzag_from_key(max_steps, dt, rng)
     point_per_seg = 40
     num_seg = max_steps // point_per_seg + 1
     prev = rng.uniform(-1.0, 1.0, size=3)
@@ -176,20 +218,38 @@ class Quad3D:
         return done
 
     # -- reset / step ----------------------------------------------------------------------------------
-    def reset(self, rng: np.random.Generator, params: Optional[EnvParams3D] = None):
+    def reset(self, rng, params: Optional[EnvParams3D] = None):
         p = params or self.default_params
-        pos_traj, vel_traj, acc_traj = self.generate_traj(p.max_steps_in_episode, p.dt, rng)
+        info_rng = rng
+        if jr.is_key(rng):
+            # get_zero_state: traj_key, disturb_key, key = split(key, 3) (quadrotor.py:267); reset_env then splits the
+            # ORIGINAL key once more for get_info (:368)
+            traj_key, disturb_key, _ = jr.split(rng, 3)
+            pos_traj, vel_traj, acc_traj = self.generate_traj(p.max_steps_in_episode, p.dt, traj_key)
+            fd = jr.uniform(disturb_key, (3,), -p.disturb_scale, p.disturb_scale)
+            info_rng = jr.split(rng)[0]
+        else:
+            pos_traj, vel_traj, acc_traj = self.generate_traj(p.max_steps_in_episode, p.dt, rng)
+            fd = rng.uniform(-p.disturb_scale, p.disturb_scale, size=3).astype(F)  # quadrotor.py:300-305
         z = np.zeros(3, F)
-        fd = rng.uniform(-p.disturb_scale, p.disturb_scale, size=3).astype(F)  # quadrotor.py:300-305
         state = EnvState3D(pos=z.copy(), vel=z.copy(), quat=np.array([0, 0, 0, 1], F), omega=z.copy(),
                            pos_traj=pos_traj, vel_traj=vel_traj, acc_traj=acc_traj, pos_tar=pos_traj[0].copy(),
                            vel_tar=vel_traj[0].copy(), acc_tar=acc_traj[0].copy(), time=0, f_disturb=fd)
-        info = self.get_info(rng, state, state, p)
+        info = self.get_info(info_rng, state, state, p)
         return None, info, state  # obs is unused by the MPC controllers (controllers/covo.py:198)
 
     def get_info(self, rng, state: EnvState3D, next_state: EnvState3D, p: EnvParams3D) -> dict:
         noisy = None
-        if self.generate_noisy_state:  # quadrotor.py:323-351
+        if self.generate_noisy_state and jr.is_key(rng):  # quadrotor.py:323-351
+            k_pos, k_vel, k_quat, k_omega, _ = jr.split(rng, 5)
+            sc = F(p.obs_noise_scale)
+            noisy = next_state.replace(
+                pos=(next_state.pos + jr.normal(k_pos, (3,)) * sc * F(0.25)).astype(F),
+                vel=(next_state.vel + jr.normal(k_vel, (3,)) * sc * F(0.5)).astype(F),
+                quat=(next_state.quat + jr.normal(k_quat, (4,)) * sc * F(0.02)).astype(F),
+                omega=(next_state.omega + jr.normal(k_omega, (3,)) * sc * F(0.5)).astype(F),
+            )
+        elif self.generate_noisy_state:
             sc = p.obs_noise_scale
             noisy = next_state.replace(
                 pos=(next_state.pos + rng.standard_normal(3) * sc * 0.25).astype(F),
@@ -217,8 +277,15 @@ class Quad3D:
         qn = qn / _norm(qn)
         vel = state.vel + vdot * dt
         omega = F(p.alpha_bodyrate) * om + F(1 - p.alpha_bodyrate) * omega_tar
+        info_rng = rng
+        if jr.is_key(rng):
+            # raw_step: key, step_key = split(key) (quadrotor.py:262); step_fn: key, key_dyn = split(step_key);
+            # disturb_key, key = split(key) (dynamics/free.py:136,144); step_env: info_key, key = split(key) (:245)
+            disturb_key = jr.split(jr.split(jr.split(rng)[1])[0])[0]
+            info_rng = jr.split(rng)[0]
         if self.disturb_type == "gaussian" and not deterministic:
-            fd = (p.dyn_noise_scale * rng.standard_normal(3)).astype(F)
+            z3 = jr.normal(disturb_key, (3,)) if jr.is_key(rng) else rng.standard_normal(3)
+            fd = (F(p.dyn_noise_scale) * z3).astype(F)
         else:
             fd = np.zeros(3, F)
         time = state.time + 1
@@ -228,13 +295,16 @@ class Quad3D:
                             acc_tar=state.acc_traj[ti].copy(), last_thrust=float(thrust))
         reward = self.reward_fn(state)  # PRE-step state, quadrotor.py:243
         done = self.is_terminal(state, p)
-        info = self.get_info(rng, state, nxt, p)
+        info = self.get_info(info_rng, state, nxt, p)
         return None, nxt, reward, done, info
 
     def step(self, rng, state: EnvState3D, action, params: Optional[EnvParams3D] = None):
         """BaseEnvironment.step (envs/base.py:15-40) including the auto-reset on ``done``."""
         p = params or self.default_params
+        key_reset = rng
+        if jr.is_key(rng):
+            rng, key_reset = jr.split(rng)  # base.py:27
         obs, nxt, reward, done, info = self.step_env(rng, state, action, p)
         if done:
-            obs, info, nxt = self.reset(rng, p)
+            obs, info, nxt = self.reset(key_reset, p)
         return obs, nxt, reward, done, info

@@ -10,6 +10,8 @@ from typing import Callable, Optional
 
 import numpy as np
 
+from . import jaxrng as jr
+
 
 def run_episode(env, controller, rng: np.random.Generator, n_steps: Optional[int] = None, rng_act_fn: Optional[Callable] = None,
                 record: Optional[list] = None, reset_rng: Optional[np.random.Generator] = None, state_seq: Optional[list] = None):
@@ -61,11 +63,46 @@ def run_episode_device(env, controller, rng: np.random.Generator, n_steps: Optio
     return err[:, 0], rew[:, 0]
 
 
-def eval_env(env, controller, total_steps: int = 300 * 4 * 10, num_trajs: int = 4, seed: int = 1):
+def run_episode_keyed(env, controller, rng_reset, rng, n_steps: Optional[int] = None):
+    """``run_one_ep`` of eval_env (quadjax/envs/quadrotor.py:542-563) with the reference's key schedule: reset from
+    ``rng_reset``; ``rng_control, rng = split(rng)``; per step ``rng, rng_act, rng_step, rng_control = split(rng, 4)``, the
+    controller call with ``rng_act``, ``env.step(rng_step, ...)`` (auto-reset on done, the scan never stops early), then
+    ``rng, rng_control = split(rng)``.  Returns (rng, err_pos[n_steps], rewards[n_steps])."""
+    params = env.default_params
+    n_steps = n_steps or params.max_steps_in_episode
+    obs, info, state = env.reset(rng_reset, params)
+    rng_control, rng = jr.split(rng)
+    control_params = controller.reset(state, params, controller.init_control_params, rng_control)
+    errs, rews = [], []
+    for _ in range(n_steps):
+        rng, rng_act, rng_step, rng_control = jr.split(rng, 4)
+        action, control_params, _ = controller(obs, state, params, rng_act, control_params, info)
+        obs, state, reward, done, info = env.step(rng_step, state, action, params)
+        rng, rng_control = jr.split(rng)
+        errs.append(info["err_pos"])
+        rews.append(reward)
+    return rng, np.asarray(errs), np.asarray(rews)
+
+
+def eval_env(env, controller, total_steps: int = 300 * 4 * 10, num_trajs: int = 4, seed: int = 1, keyed: bool = False):
     """quadjax/envs/quadrotor.py:506-591 (PRNGKey(1); num_trajs reference trajectories, each re-used for
-    num_eps // num_trajs episodes).  Returns (mean, std, per-episode array)."""
+    num_eps // num_trajs episodes).  Returns (mean, std, per-episode array).
+
+    keyed=True threads JAX PRNG keys exactly as the reference does (``rng, rng_reset_meta = split(PRNGKey(seed))``,
+    ``split(rng_reset_meta, num_trajs)``, then run_episode_keyed): the four reference trajectories, initial disturbances,
+    observation noise and the controllers' sample streams are then the ones the reference's eval_env generates."""
     T = env.default_params.max_steps_in_episode
     num_eps = int(total_steps // T)
+    if keyed:
+        rng = jr.PRNGKey(seed)
+        rng, rng_reset_meta = jr.split(rng)
+        out = []
+        for rng_reset in jr.split(rng_reset_meta, num_trajs):
+            for _ in range(num_eps // num_trajs):
+                rng, errs, _ = run_episode_keyed(env, controller, rng_reset, rng, T)
+                out.append(errs.mean())
+        out = np.asarray(out)
+        return float(out.mean()), float(out.std()), out
     rng = np.random.default_rng(seed)
     out = []
     for i in range(num_trajs):

@@ -126,6 +126,15 @@ int covo_rollout(covo_handle* h, const float* state24, const int* time, const fl
                  const float* eps, const float* fdist_seq, float* a_mean_out, float* action, float* costs,
                  float* samples);
 
+/* JAX-compatible sampling stream.  Replaces, for ONE following sampling call (covo_step,
+ * covo_step_device, covo_step_partial_device or covo_rollout without explicit eps), the Philox field by the draws the
+ * reference itself would make from `act_key`:  act_keys = jax.random.split(act_key, N);  sample i draws
+ * jax.random.normal(act_keys[i], (4H,))  (controllers/covo.py:212-221)  or, in MPPI mode, normal(split(act_keys[i], H)[h], (4,))
+ * (controllers/mppi.py:53-61) -- Threefry-2x32-20, legacy counter layout, erfinv-based normal.  `act_key` = two uint32 words
+ * on the host.  The caller derives act_key from its rng_act exactly as the reference does (rng_act, act_key = split(rng_act));
+ * covo_mpc_b200/jaxrng.py is the host twin.  N-sharded handles index the stream by GLOBAL sample number. */
+int covo_set_jax_key(covo_handle* h, const unsigned int* act_key);
+
 /* Debug / introspection. */
 int covo_get_pos_stats(covo_handle* h, float* pos_mean, float* pos_std); /* info dict, controllers/covo.py:281; [E][H][3] each */
 int covo_enable_pos_stats(covo_handle* h, int on);

@@ -83,6 +83,18 @@ def vmap(f, in_axes=0, out_axes=0):
     return g
 
 
+class ClampArr(np.ndarray):
+    """JAX clamps out-of-range integer indices (dynamics/utils.py:238 relies on it); NumPy raises."""
+
+    def __getitem__(self, idx):
+        if isinstance(idx, (int, np.integer)):
+            idx = min(max(int(idx), -self.shape[0]), self.shape[0] - 1)
+        return np.asarray(np.ndarray.__getitem__(self, idx))
+
+    def __iter__(self):
+        return iter(np.asarray(self))
+
+
 class _Jac:
     def __init__(self, f):
         self.f = f
@@ -462,6 +474,43 @@ def main():
     assert table.shape == (3, 24, 24), table.shape
     np.savez_compressed(os.path.join(out_dir, "reference_covo_offline_schedule.npz"), state24=vec24(st), time=int(st.time),
                         pos_traj=np.asarray(st.pos_traj, F), vel_traj=np.asarray(st.vel_traj, F), a_cov_offline=table, H=ctl.H)
+
+    # ---- 9. key plumbing: the reference's reset / step / trajectory generators driven by REAL jax.random semantics --------------
+    # jax.random is now backed by covo_mpc_b200/jaxrng.py (Threefry-2x32-20, legacy layout; pinned by Random123 and
+    # JAX-documentation known answers in tests/test_jaxrng.py).  What this section pins is the reference's USE of its keys:
+    # which key is split how often and which draw feeds what (utils.py:87-130, 183-251; quadrotor.py:265-312, 314-370;
+    # free.py:136-146; base.py:27-40) -- the product's host environment must consume a key the same way.
+    from covo_mpc_b200 import jaxrng as jr
+
+    rnd = sys.modules["jax.random"]
+    rnd.PRNGKey = jr.PRNGKey
+    rnd.split = lambda key, num=2: jr.split(np.asarray(key, np.uint32), num).view(ClampArr)
+    rnd.uniform = lambda key, shape=(), dtype=F, minval=0.0, maxval=1.0: jr.uniform(np.asarray(key, np.uint32), shape, minval, maxval).view(JArr)
+    rnd.normal = lambda key, shape=(), dtype=F: jr.normal(np.asarray(key, np.uint32), shape)
+    keyed = {}
+    for task in ("tracking", "tracking_zigzag", "hovering"):
+        for disturb in ("none", "gaussian"):
+            e = Quad3D(task=task, obs_type="quad", lower_controller="base", enable_randomizer=False, disturb_type=disturb,
+                       disable_rollover_terminate=True, generate_noisy_state=True)
+            e.get_obs = lambda *a, **k: None
+            key = jr.PRNGKey(100 + len(keyed))
+            _, info, st = e.reset_env(key, params)
+            tag = f"{task}__{disturb}"
+            keyed[tag + "__key"] = key
+            keyed[tag + "__pos_traj"], keyed[tag + "__vel_traj"], keyed[tag + "__acc_traj"] = (np.asarray(x, F) for x in (st.pos_traj, st.vel_traj, st.acc_traj))
+            keyed[tag + "__reset24"] = vec24(st)
+            keyed[tag + "__reset_noisy24"] = vec24(info["noisy_state"])
+            cur, k = st, jr.PRNGKey(7)
+            steps_next, steps_noisy, steps_key = [], [], []
+            for j in range(3):
+                k, k_step = jr.split(k)
+                act = np.array([0.2 * j - 0.3, 0.1, -0.05 * j, 0.02], F)
+                # BaseEnvironment.step (base.py:15-40): key, key_reset = split(key); step_env(key, ...); auto-reset unused here
+                k_env, _ = jr.split(k_step)
+                _, cur, reward, done, info = e.step_env(k_env, cur, act, params)
+                steps_key.append(k_step); steps_next.append(vec24(cur)); steps_noisy.append(vec24(info["noisy_state"]))
+            keyed[tag + "__step_keys"], keyed[tag + "__step_next24"], keyed[tag + "__step_noisy24"] = np.array(steps_key), np.array(steps_next), np.array(steps_noisy)
+    np.savez_compressed(os.path.join(out_dir, "reference_keyed_env.npz"), **keyed)
     print("reference goldens written to", out_dir)
 
 

@@ -90,13 +90,11 @@ def test_termination_flags(host_check_lib):
 
 def test_result_artefacts_match_the_reference_formats(tmp_path):
     """eval_err_pos_{name}.pkl and state_seq_{name}.pkl (envs/quadrotor.py:581-591, 655-666): host-side only."""
-    import importlib.util
     import os
     import pickle
 
-    spec = importlib.util.spec_from_file_location("_harness", os.path.join(os.path.dirname(__file__), "..", "covo_mpc_b200", "harness.py"))
-    hz = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(hz)
+    from covo_mpc_b200 import harness as hz  # loads libcovo_b200.so (no GPU needed until a handle is created)
+
     p1 = hz.save_eval_results(np.array([0.05, 0.06]), "covo_online", str(tmp_path))
     assert os.path.basename(p1) == "eval_err_pos_covo_online.pkl"
     assert np.allclose(pickle.load(open(p1, "rb")), [0.05, 0.06])

@@ -1,0 +1,57 @@
+"""Host environment driven by JAX PRNG keys vs the reference's own reset / step / trajectory generators executed with the
+same keys (tests/golden/make_reference_golden.py section 9; jax.random backed by covo_mpc_b200/jaxrng.py, which is pinned
+separately in tests/test_jaxrng.py).  Pins the key plumbing: split tree, draw order, which draw feeds what."""
+import os
+
+import numpy as np
+import pytest
+
+import covo_mpc_b200 as cm
+from covo_mpc_b200 import jaxrng as jr
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_keyed_env.npz"))
+
+
+def _vec24(st):
+    return st.to_state24()
+
+
+@pytest.mark.parametrize("task", ["tracking", "tracking_zigzag", "hovering"])
+@pytest.mark.parametrize("disturb", ["none", "gaussian"])
+def test_reset_and_step_consume_keys_like_the_reference(task, disturb):
+    tag = f"{task}__{disturb}"
+    env = cm.Quad3D(task, disturb_type=disturb)
+    key = G[tag + "__key"]
+    assert jr.is_key(key)
+    _, info, st = env.reset(key)
+    # trajectories: float32 here vs the shim's mixed float32/float64 evaluation of the same expressions
+    assert st.pos_traj.shape == G[tag + "__pos_traj"].shape
+    assert np.abs(st.pos_traj - G[tag + "__pos_traj"]).max() < 2e-5
+    assert np.abs(st.vel_traj - G[tag + "__vel_traj"]).max() < 2e-5
+    assert np.abs(st.acc_traj - G[tag + "__acc_traj"]).max() < 1e-4
+    assert np.abs(_vec24(st) - G[tag + "__reset24"]).max() < 2e-5
+    assert np.array_equal(st.f_disturb, G[tag + "__reset24"][13:16])  # uniform(disturb_key): bit-identical
+    assert np.abs(_vec24(info["noisy_state"]) - G[tag + "__reset_noisy24"]).max() < 2e-5
+    noise = _vec24(info["noisy_state"])[:13] - _vec24(st)[:13]
+    assert np.abs(noise - (G[tag + "__reset_noisy24"][:13] - G[tag + "__reset24"][:13])).max() < 1e-7  # the same draws
+    cur = st
+    for j in range(3):
+        act = np.array([0.2 * j - 0.3, 0.1, -0.05 * j, 0.02], np.float32)
+        _, cur, reward, done, info = env.step(G[tag + "__step_keys"][j], cur, act)
+        assert not done
+        assert np.abs(_vec24(cur) - G[tag + "__step_next24"][j]).max() < 2e-5, j
+        assert np.abs(_vec24(info["noisy_state"]) - G[tag + "__step_noisy24"][j]).max() < 2e-5, j
+        if disturb == "gaussian":
+            assert np.abs(cur.f_disturb).max() > 0 and np.abs(cur.f_disturb - G[tag + "__step_next24"][j][13:16]).max() < 1e-7
+        else:
+            assert np.abs(cur.f_disturb).max() == 0
+
+
+def test_zigzag_key_quirks():
+    """Segments 0 and 1 are drawn from the same key (dynamics/utils.py:238, 241): same turn angles relative to the centre
+    direction and the same length."""
+    pos, vel, acc = cm.env.generate_zigzag_traj(300, 0.02, jr.PRNGKey(5))
+    assert pos.shape == (320, 3) and np.all(pos[0] == 0) and np.all(acc == 0)
+    seg = [np.linalg.norm(vel[40 * i]) * 41 * 0.02 for i in range(8)]  # |next - prev| per segment
+    assert abs(seg[0] - seg[1]) < 1e-5 and 1.0 <= min(seg) and max(seg) <= 1.5
+    assert len({round(float(x), 5) for x in seg[1:]}) == 7

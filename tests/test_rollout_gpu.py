@@ -213,3 +213,44 @@ def test_full_size_properties():
     a0, _, _, _ = h.rollout(st, [ns.time], a_mean[None], eps=eps[None])
     assert np.abs(a0[0] - np.clip(a_mean, -1, 1)).max() < 1e-5
     assert a_out.min() >= -1 and a_out.max() <= 1
+
+
+@pytest.mark.parametrize("mode_name", ["covo", "mppi"])
+def test_jax_compatible_stream_in_kernel(mode_name):
+    """covo_set_jax_key: the kernel's Threefry draws == the host twin of jax.random (covo_mpc_b200/jaxrng.py, pinned by the
+    Random123 / JAX-documentation known answers in tests/test_jaxrng.py), for both samplers, with a ragged last tile, and
+    independent of N-sharding."""
+    from covo_mpc_b200 import _lib, jaxrng
+
+    N, H = 160, 10  # 2.5 tiles of 64
+    p, ns, a_mean, rng = scenario("tracking_zigzag", seed=4, H=H, warm_steps=3)
+    mode = _lib.MODE_MPPI if mode_name == "mppi" else _lib.MODE_COVO_OFFLINE
+    act_key = jaxrng.split(jaxrng.PRNGKey(2024))[1]
+    eps = (jaxrng.mppi_normals(act_key, N, H).reshape(N, 4 * H) if mode_name == "mppi" else jaxrng.covo_normals(act_key, N, 4 * H))
+    st = o.state_to_vec24(ns)
+
+    def mk(**kw):
+        h = _handle(mode, N, H, ns.pos_traj.shape[0], **kw)
+        h.set_reference(ns.pos_traj[None], ns.vel_traj[None])
+        if mode_name == "covo":
+            A = rng_cov.standard_normal((4 * H, 4 * H)) * 0.1
+            h.set_cov_offline((A @ A.T + 0.2 * np.eye(4 * H)).astype(np.float32)[None])
+        return h
+
+    rng_cov = np.random.default_rng(0)
+    h = mk()
+    h.set_jax_key(act_key)
+    a1, act1, c1, s1 = h.rollout(st, [ns.time], a_mean[None], want_costs=True, want_samples=True)
+    a2, act2, c2, s2 = h.rollout(st, [ns.time], a_mean[None], eps=eps[None], want_costs=True, want_samples=True)
+    assert np.abs(s1 - s2).max() < 5e-6  # logf / sqrtf vs NumPy: last-ulp differences only
+    assert np.abs(c1 - c2).max() < 1e-4 and np.abs(a1 - a2).max() < 1e-4
+    # the key is one-shot: the next call is back on the Philox field
+    a3, _, c3, _ = h.rollout(st, [ns.time], a_mean[None], want_costs=True)
+    assert np.abs(c3 - c1).max() > 1e-3
+    # N-sharding: rank r draws rows [r N/2, (r+1) N/2) of the same stream
+    for r in range(2):
+        rng_cov = np.random.default_rng(0)
+        hr = mk(rank=r, world=2)
+        hr.set_jax_key(act_key)
+        _, _, cr, sr = hr.rollout(st, [ns.time], a_mean[None], want_costs=True, want_samples=True)
+        assert np.array_equal(sr[0], s1[0][r * N // 2:(r + 1) * N // 2])

@@ -282,3 +282,31 @@ def test_sample_sharded_step_equals_single_device():
     # same samples (global RNG index), same arg-min; the merge order differs from the single-device tile order
     assert np.abs(outs[0][1] - mean1).max() < 2e-6
     assert np.abs(outs[0][0] - act1.cpu().numpy()).max() < 2e-6
+
+
+def test_keyed_episode_follows_the_reference_key_schedule():
+    """run_episode_keyed: reset / noise / sampling all driven by JAX PRNG keys split as eval_env splits them
+    (envs/quadrotor.py:520-563).  Deterministic; and the controller's in-kernel Threefry draws equal the host twin's."""
+    import covo_mpc_b200 as cm
+    from covo_mpc_b200 import jaxrng as jr
+
+    env = cm.Quad3D("tracking_zigzag")
+    N, H = 192, 8
+    ctl, cp = cm.get_controller(env, "covo-online", f"N{N}_H{H}_lam0.01")
+    rng_reset, rng0 = jr.PRNGKey(11), jr.PRNGKey(12)
+    rng1, e1, r1 = cm.run_episode_keyed(env, ctl, rng_reset, rng0, 6)
+    rng2, e2, r2 = cm.run_episode_keyed(env, ctl, rng_reset, rng0, 6)
+    assert np.array_equal(e1, e2) and np.array_equal(r1, r2) and np.array_equal(rng1, rng2) and np.isfinite(e1).all()
+    # first controller call by hand: the same keys, explicit normals from the host twin of jax.random
+    params = env.default_params
+    _, info, state = env.reset(rng_reset, params)
+    _, rng = jr.split(rng0)
+    rng, rng_act, rng_step, _ = jr.split(rng, 4)
+    cpa = ctl.reset(state, params, ctl.init_control_params, None)
+    a_key, _, _ = ctl(None, state, params, rng_act, cpa, info)
+    eps = jr.covo_normals(jr.split(rng_act)[1], N, 4 * H)
+    cpb = ctl.reset(state, params, ctl.init_control_params, None)
+    a_eps, _, _ = ctl(None, state, params, eps, cpb, info)
+    assert np.abs(np.asarray(a_key) - np.asarray(a_eps)).max() < 1e-4
+    _, st1, _, _, info1 = env.step(rng_step, state, a_key, params)
+    assert abs(info1["err_pos"] - e1[0]) < 1e-6
