@@ -6,7 +6,8 @@ this package loads it and fails loudly if it has not been built.  There is no CP
 from . import _lib
 from ._lib import Handle, CovoConfig, default_config, MODE_MPPI, MODE_COVO_ONLINE, MODE_COVO_OFFLINE
 from .env import Quad3D, EnvParams3D, EnvState3D
-from .controllers import (BaseController, MPPIController, CoVOController, MPPIParams, CoVOParams, get_controller)
+from .controllers import (BaseController, MPPIController, CoVOController, PIDController, RandomController, MPPIParams, CoVOParams,
+                          PIDParams, get_controller)
 from . import jaxrng
 from .harness import run_episode, run_episode_device, run_episode_keyed, eval_env, save_eval_results, save_state_seq
 
@@ -14,4 +15,4 @@ _lib.load()
 
 __all__ = ["Handle", "CovoConfig", "default_config", "MODE_MPPI", "MODE_COVO_ONLINE", "MODE_COVO_OFFLINE",
            "Quad3D", "EnvParams3D", "EnvState3D", "BaseController", "MPPIController", "CoVOController",
-           "MPPIParams", "CoVOParams", "get_controller", "jaxrng", "run_episode", "run_episode_device", "run_episode_keyed", "eval_env", "save_eval_results", "save_state_seq"]
+           "PIDController", "RandomController", "MPPIParams", "CoVOParams", "PIDParams", "get_controller", "jaxrng", "run_episode", "run_episode_device", "run_episode_keyed", "eval_env", "save_eval_results", "save_state_seq"]

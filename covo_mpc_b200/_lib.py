@@ -71,6 +71,7 @@ _SIGNATURES = {
     "covo_enable_pos_stats": [_H, C.c_int],
     "covo_debug_eps": [_H, C.c_uint, _F],
     "covo_set_jax_key": [_H, C.POINTER(C.c_uint)],
+    "covo_pid_action": [_H, _F, _I, C.c_float, C.c_float, C.c_float, C.c_float, _F, _F],
     "covo_debug_tridiag": [_H, _D, _D, _D],
     "covo_zolotarev_nodes": [C.c_double, C.c_double, C.c_int, _D, _D],
     "covo_get_status": [_H, _I],
@@ -213,6 +214,18 @@ class Handle:
     def get_cov_offline(self, t_sched: int) -> np.ndarray:
         out = np.empty((t_sched, self.n, self.n), dtype=np.float32)
         check(self.lib.covo_get_cov_offline(self._h, fptr(out), t_sched))
+        return out
+
+    def pid_action(self, state24, time, Kp=10.0, Kd=5.0, Ki=0.0, Kp_att=10.0, integral=None) -> np.ndarray:
+        """PIDController.__call__ on the device for the handle's environments (covo_pid_action)."""
+        s, t = f32(state24), i32(time)
+        if s.size != self.E * 24 or t.size != self.E:
+            raise ValueError("state24 / time have the wrong size")
+        g = None if integral is None else f32(integral)
+        if g is not None and g.size != self.E * 3:
+            raise ValueError("integral must be [E][3]")
+        out = np.empty((self.E, 4), dtype=np.float32)
+        check(self.lib.covo_pid_action(self._h, fptr(s), iptr(t), Kp, Kd, Ki, Kp_att, fptr(g), fptr(out)))
         return out
 
     def reset_offline(self, state24, time, t_sched: int):

@@ -306,6 +306,83 @@ class _OfflineTable:
         return (self.T, 4 * self.owner.H, 4 * self.owner.H)
 
 
+
+@dataclass
+class PIDParams:
+    """quadjax/controllers/pid.py:11-22 (same names, same defaults)."""
+
+    Kp: float = 4.0
+    Kd: float = 4.0
+    Ki: float = 1.0
+    Kp_att: float = 4.0
+    Ki_att: float = 1.0
+    integral: Any = field(default_factory=lambda: np.zeros(3, np.float32))
+    quat_desired: Any = field(default_factory=lambda: np.array([0.0, 0.0, 0.0, 1.0], np.float32))
+    att_integral: Any = field(default_factory=lambda: np.zeros(3, np.float32))
+
+    def replace(self, **kw):
+        import dataclasses
+
+        return dataclasses.replace(self, **kw)
+
+
+class PIDController(BaseController):
+    """quadjax/controllers/pid.py:24-83 -- ``--controller pid`` and the expansion policy of CoVO-offline.  The action is
+    computed by the device PID kernel (the same ``pid_action`` the offline schedule uses); the integral bookkeeping
+    (:77-81) stays on the host.  ``quat_desired`` is not on any caller's path and is left unchanged."""
+
+    def __init__(self, env, control_params, *, device: int = 0) -> None:
+        super().__init__(env, control_params)
+        self.param = env.default_params
+        self._device = device
+        self._handle: Optional[_lib.Handle] = None
+        self._traj_id = None
+
+    def _sync(self, state: EnvState3D) -> _lib.Handle:
+        T = int(state.pos_traj.shape[0])
+        if self._handle is None or self._handle.cfg.traj_len != T:
+            if self._handle is not None:
+                self._handle.close()
+            p = self.param
+            cfg = _lib.default_config()
+            cfg.mode, cfg.n_samples, cfg.horizon, cfg.n_env, cfg.traj_len, cfg.device = _lib.MODE_MPPI, 64, 2, 1, T, self._device
+            cfg.m, cfg.g, cfg.max_thrust, cfg.dt = p.m, p.g, p.max_thrust, p.dt
+            for k in range(3):
+                cfg.max_omega[k] = p.max_omega[k]
+            self._handle = _lib.Handle(cfg)
+            self._traj_id = None
+        tid = (id(state.pos_traj), id(state.acc_traj))
+        if tid != self._traj_id:
+            self._handle.set_reference(state.pos_traj, state.vel_traj, state.acc_traj)
+            self._traj_id, self._keep = tid, (state.pos_traj, state.acc_traj)
+        return self._handle
+
+    def __call__(self, obs, state, env_param, rng_act, control_params, info=None):
+        h = self._sync(state)
+        integral = np.asarray(control_params.integral, np.float32)
+        action = h.pid_action(state.to_state24(), [state.time], control_params.Kp, control_params.Kd, control_params.Ki,
+                              control_params.Kp_att, integral)[0]
+        dt = np.float32(getattr(env_param, "dt", self.param.dt))
+        new = control_params.replace(integral=(integral + (np.asarray(state.pos, np.float32) - np.asarray(state.pos_tar, np.float32)) * dt))
+        return action, new, None
+
+    def close(self):
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
+
+
+class RandomController(BaseController):
+    """quadjax/controllers/random.py:8-16: 0.3 * normal(rng_act, (4,)); rng_act a JAX key or a NumPy generator."""
+
+    def __call__(self, obs, state, env_params, rng_act, control_params, env_info=None):
+        if jaxrng.is_key(rng_act):
+            z = jaxrng.normal(rng_act, (4,))
+        else:
+            z = (rng_act if rng_act is not None else np.random.default_rng()).standard_normal(4).astype(np.float32)
+        return z * np.float32(0.3), control_params, None
+
+
 def get_controller(env, controller_name: str, controller_params: Optional[str] = None, debug: bool = False, **kw):
     """quadjax/envs/quadrotor.py:670-752 -- same names, same parameter string, same defaults."""
 
@@ -338,7 +415,12 @@ def get_controller(env, controller_name: str, controller_params: Optional[str] =
                                     a_mean=get_sample_mean(H), a_cov=np.diag(np.full(H * 4, sigma ** 2, np.float32)),
                                     a_cov_offline=np.zeros((H, 4, 4), np.float32))
         controller = CoVOController(env=env, control_params=control_params, N=N, H=H, lam=lam, mode=mode, **kw)
+    elif controller_name == "pid":  # quadrotor.py:692-699
+        control_params = PIDParams(Kp=10.0, Kd=5.0, Ki=0.0, Kp_att=10.0)
+        controller = PIDController(env, control_params=control_params, **kw)
+    elif controller_name == "random":  # quadrotor.py:700-702
+        control_params = None
+        controller = RandomController(env, control_params)
     else:
-        # "pid" / "random" are out of scope of this hot path
-        raise NotImplementedError(controller_name)
+        raise NotImplementedError(controller_name)  # quadrotor.py:750-751
     return controller, control_params

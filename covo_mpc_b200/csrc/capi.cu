@@ -640,6 +640,40 @@ int covo_get_cov_offline(covo_handle* h, float* table, int t_sched) {
     return COVO_OK;
 }
 
+int covo_pid_action(covo_handle* h, const float* state24, const int* time, float Kp, float Kd, float Ki, float Kp_att,
+                    const float* integral, float* action) {
+    if (!h || !state24 || !time || !action) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->own_stream;
+    CK(cudaMemcpyAsync(h->state24.p, state24, (size_t)h->E * kStateFloats * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->time.p, time, (size_t)h->E * sizeof(int), cudaMemcpyHostToDevice, st));
+    DevBuf<float> integ;
+    if (integral) {
+        CK(integ.alloc((size_t)h->E * 3));
+        CK(cudaMemcpyAsync(integ.p, integral, (size_t)h->E * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    PidArgs pa;
+    pa.n_env = h->E;
+    pa.traj_len = h->T;
+    pa.env = h->env;
+    pa.max_thrust = h->cfg.max_thrust;
+    pa.Kp = Kp;
+    pa.Kd = Kd;
+    pa.Ki = Ki;
+    pa.Kp_att = Kp_att;
+    pa.state24 = h->state24.p;
+    pa.time = h->time.p;
+    pa.acc_traj = h->acc_traj.p;
+    pa.integral = integral ? integ.p : nullptr;
+    pa.action = h->action.p;
+    cudaError_t e = launch_pid(pa, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(action, h->action.p, (size_t)h->E * 4 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    integ.release();
+    if (e != cudaSuccess) return fail(COVO_ERR_CUDA, "pid_action: %s", cudaGetErrorString(e));
+    return COVO_OK;
+}
+
 int covo_reset_offline(covo_handle* h, const float* state24, const int* time, int t_sched) {
     if (!h || !state24 || !time) return fail(COVO_ERR_INVALID, "null argument");
     CK(cudaSetDevice(h->cfg.device));

@@ -77,6 +77,23 @@ __global__ void pid_nominal_kernel(const OfflineArgs a) {
     }
 }
 
+__global__ void pid_policy_kernel(const PidArgs a) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n_env) return;
+    QState<float> s;
+    float fd[3], pt[3], vt[3], at[3] = {0.f, 0.f, 0.f};
+    load_state24(a.state24 + (long long)e * kStateFloats, s, fd, pt, vt);
+    if (a.acc_traj) gather3(a.acc_traj + (long long)e * a.traj_len * 3, min(max(a.time[e], 0), a.traj_len - 1), at);
+    float act[4];
+    pid_action(s, pt, vt, at, a.env, a.max_thrust, a.Kp, a.Kd, a.Kp_att, act, a.Ki, a.integral ? a.integral + 3 * e : nullptr);
+    for (int k = 0; k < 4; ++k) a.action[4 * e + k] = act[k];
+}
+
+cudaError_t launch_pid(const PidArgs& a, cudaStream_t st) {
+    pid_policy_kernel<<<(a.n_env + 63) / 64, 64, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_offline_paths(const OfflineArgs& a, cudaStream_t st) {
     pid_path_kernel<<<1, 32, 0, st>>>(a);
     cudaError_t e = cudaGetLastError();

@@ -20,4 +20,17 @@ struct OfflineArgs {
 
 cudaError_t launch_offline_paths(const OfflineArgs& a, cudaStream_t st);
 
+// standalone PID policy (get_controller("pid"), controllers/pid.py:38-83): one action per environment
+struct PidArgs {
+    int n_env, traj_len;
+    EnvConsts env;
+    float max_thrust, Kp, Kd, Ki, Kp_att;
+    const float* state24;   // [E][24]
+    const int* time;        // [E]
+    const float* acc_traj;  // [E][T][3] or nullptr (acc_tar = 0)
+    const float* integral;  // [E][3] or nullptr
+    float* action;          // [E][4]
+};
+cudaError_t launch_pid(const PidArgs& a, cudaStream_t st);
+
 }  // namespace covo

@@ -12,15 +12,15 @@ COVO_HD void qtoQ(const float q[4], float Q[3][3]) {
     Q[2][0] = 2.f * (x * z - w * y); Q[2][1] = 2.f * (y * z + w * x); Q[2][2] = w * w - x * x - y * y + z * z;
 }
 
-// controllers/pid.py:38-83 with Ki = 0
+// controllers/pid.py:38-83 (Ki * integral term optional: the CoVO-offline expansion policy and get_controller("pid") use Ki = 0)
 COVO_HD void pid_action(const QState<float>& s, const float ptar[3], const float vtar[3],
                                     const float atar[3], const EnvConsts& c, float max_thrust, float Kp, float Kd,
-                                    float Kp_att, float act[4]) {
+                                    float Kp_att, float act[4], float Ki = 0.f, const float* integ = nullptr) {
     float Q[3][3];
     qtoQ(s.q, Q);
     float fd[3];
     for (int k = 0; k < 3; ++k)
-        fd[k] = c.m * (((k == 2) ? c.g : 0.f) - Kp * (s.p[k] - ptar[k]) - Kd * (s.v[k] - vtar[k]) + atar[k]);
+        fd[k] = c.m * (((k == 2) ? c.g : 0.f) - Kp * (s.p[k] - ptar[k]) - Kd * (s.v[k] - vtar[k]) - (integ ? Ki * integ[k] : 0.f) + atar[k]);
     float thrust = Q[0][2] * fd[0] + Q[1][2] * fd[1] + Q[2][2] * fd[2];
     thrust = fminf(fmaxf(thrust, 0.f), max_thrust);
     float nrm = sqrtf(fd[0] * fd[0] + fd[1] * fd[1] + fd[2] * fd[2]);

@@ -88,6 +88,13 @@ const char* covo_version(void);
  * pointers, [E][T][3]; acc may be NULL (zeros). */
 int covo_set_reference(covo_handle* h, const float* pos_traj, const float* vel_traj, const float* acc_traj);
 
+/* get_controller(env, "pid") -- PIDController.__call__ (controllers/pid.py:38-83; gains of envs/quadrotor.py:692-699) for the
+ * handle's n_env environments: position PD(+I) -> desired thrust vector -> attitude error -> (thrust, body rates) in the
+ * normalised action box.  state24/time as in covo_step; acc_tar is looked up in the reference's acceleration table
+ * (covo_set_reference) at `time`; integral: [n_env][3] or NULL (Ki term skipped).  All pointers are HOST pointers. */
+int covo_pid_action(covo_handle* h, const float* state24, const int* time, float Kp, float Kd, float Ki, float Kp_att,
+                    const float* integral, float* action);
+
 /* control_params.a_mean / a_cov accessors (host pointers). */
 int covo_set_mean(covo_handle* h, const float* a_mean);
 int covo_get_mean(covo_handle* h, float* a_mean);

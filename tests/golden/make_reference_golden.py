@@ -511,6 +511,23 @@ def main():
                 steps_key.append(k_step); steps_next.append(vec24(cur)); steps_noisy.append(vec24(info["noisy_state"]))
             keyed[tag + "__step_keys"], keyed[tag + "__step_next24"], keyed[tag + "__step_noisy24"] = np.array(steps_key), np.array(steps_next), np.array(steps_noisy)
     np.savez_compressed(os.path.join(out_dir, "reference_keyed_env.npz"), **keyed)
+
+    # ---- 10. whole controller calls driven by a PRNGKey (jax.random = the Threefry twin of section 9) -----------------------
+    # Same key in -> same action out is the drop-in claim: the product, handed this rng_act, must draw in its kernel what the
+    # reference drew here (rng_act, act_key = split(rng_act); split(act_key, N); normal(...)) and end at the same action.
+    rnd.multivariate_normal = lambda key, mean, cov: (np.asarray(mean, F) + np.linalg.cholesky(np.asarray(cov, F))
+                                                      @ jr.normal(np.asarray(key, np.uint32), (np.asarray(mean).shape[-1],))).astype(F)
+    for name, text, seed in (("covo-online", "N128_H8_lam0.01", 21), ("mppi", "N128_H8_lam0.01", 22)):
+        ctl, cp = get_controller(env, name, text)
+        pp, ns_, a_prev, _ = scenario("tracking_zigzag", seed=seed, H=ctl.H, warm_steps=5)
+        a_prev = np.clip(np.asarray(a_prev, F), -0.9, 0.9)
+        st = to_ref_state(ns_)
+        key = jr.PRNGKey(1000 + seed)
+        u, cp2, info = ctl(None, st, params, key, cp.replace(a_mean=a_prev), {"noisy_state": st})
+        np.savez_compressed(os.path.join(out_dir, f"reference_call_{name.replace('-', '_')}_keyed.npz"), state24=vec24(st), time=int(st.time),
+                            pos_traj=np.asarray(st.pos_traj, F), vel_traj=np.asarray(st.vel_traj, F), a_mean=a_prev, rng_act=key,
+                            a_cov_in=np.asarray(cp.a_cov, F), a_cov=np.asarray(cp2.a_cov, F), a_mean_new=np.asarray(cp2.a_mean, F),
+                            action=np.asarray(u, F), lam=ctl.lam, N=ctl.N, H=ctl.H)
     print("reference goldens written to", out_dir)
 
 

@@ -173,3 +173,38 @@ def test_optimize_sigma_kernels_match_the_reference_source():
         h = _handle(_lib.MODE_COVO_ONLINE, 64, int(H), 320)
         S = h.optimize_sigma(R[None])[0]
         assert np.linalg.norm(S - S_ref) / np.linalg.norm(S_ref) < 5e-5, H
+
+
+def test_pid_controller_matches_the_reference_source():
+    """get_controller(env, "pid"): the device PID policy vs PIDController.__call__ executed from /root/reference
+    (tests/golden/reference_pid.npz), through the controller object; integral bookkeeping as pid.py:77-81."""
+    import covo_mpc_b200 as cm
+
+    g = _golden("reference_pid.npz")
+    env = cm.Quad3D("tracking_zigzag")
+    ctl, cp = cm.get_controller(env, "pid")
+    assert (cp.Kp, cp.Kd, cp.Ki, cp.Kp_att) == (10.0, 5.0, 0.0, 10.0)
+    z = np.zeros((320, 3), np.float32)
+    for s, act in zip(g["state24"], g["action"]):
+        st = cm.EnvState3D(pos=s[0:3], quat=s[3:7], vel=s[7:10], omega=s[10:13], f_disturb=s[13:16], pos_tar=s[16:19], vel_tar=s[19:22],
+                           acc_tar=z[0], pos_traj=z, vel_traj=z, acc_traj=z, time=0)
+        a, cp2, info = ctl(None, st, env.default_params, None, cp, None)
+        assert info is None and np.abs(a - act).max() < 2e-5
+        assert np.allclose(cp2.integral, (s[0:3] - s[16:19]) * np.float32(0.02), atol=1e-7)
+    # Ki * integral term (pid.py:48) against the oracle's restatement
+    integ = np.array([0.05, -0.1, -0.2], np.float32)
+    cpi = cm.PIDParams(Kp=10.0, Kd=5.0, Ki=2.0, Kp_att=10.0, integral=integ)
+    for s in g["state24"][:6]:
+        st = cm.EnvState3D(pos=s[0:3], quat=s[3:7], vel=s[7:10], omega=s[10:13], f_disturb=s[13:16], pos_tar=s[16:19], vel_tar=s[19:22],
+                           acc_tar=z[0], pos_traj=z, vel_traj=z, acc_traj=z, time=0)
+        a_i, _, _ = ctl(None, st, env.default_params, None, cpi, None)
+        so = o.make_state(s[0:3], s[3:7], s[7:10], s[10:13], s[13:16], 0, z, z, s[16:19], s[19:22], dtype=np.float32)
+        a_o = o.pid_action(so, o.EnvParams(), Kp=10.0, Kd=5.0, Ki=2.0, Kp_att=10.0, integral=integ)
+        a_o = a_o[0] if isinstance(a_o, tuple) else a_o
+        assert np.abs(a_i - np.asarray(a_o, np.float32)).max() < 2e-5
+    # a PID episode flies the reference trajectory
+    errs, _ = cm.run_episode(env, ctl, np.random.default_rng(0), n_steps=80)
+    assert np.isfinite(errs).all() and errs.mean() < 0.5
+    ctl_r, cp_r = cm.get_controller(env, "random")
+    a_r, _, _ = ctl_r(None, st, env.default_params, cm.jaxrng.PRNGKey(0), cp_r, None)
+    assert a_r.shape == (4,) and np.allclose(a_r, 0.3 * cm.jaxrng.normal(cm.jaxrng.PRNGKey(0), (4,)))

@@ -110,3 +110,25 @@ def test_cuda_offline_schedule_reproduces_reference():
     tab = h.get_cov_offline(3)
     for k in range(3):
         assert np.linalg.norm(tab[k] - g["a_cov_offline"][k]) / np.linalg.norm(g["a_cov_offline"][k]) < 1e-4, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["covo-online", "mppi"])
+def test_same_key_in_same_action_out(name):
+    """The drop-in claim end to end: the reference's controller call, executed from its own source with rng_act = a PRNGKey,
+    vs the product's controller object handed the SAME key -- sampling happens in the kernel (Threefry twin of jax.random)."""
+    import covo_mpc_b200 as cm
+
+    g = np.load(os.path.join(HERE, "golden", f"reference_call_{name.replace('-', '_')}_keyed.npz"))
+    N, H = int(g["N"]), int(g["H"])
+    env = cm.Quad3D("tracking_zigzag")
+    ctl, cp = cm.get_controller(env, name, f"N{N}_H{H}_lam{float(g['lam'])}")
+    s = g["state24"]
+    z3 = np.zeros(3, np.float32)
+    st = cm.EnvState3D(pos=s[0:3], quat=s[3:7], vel=s[7:10], omega=s[10:13], f_disturb=s[13:16], pos_tar=s[16:19], vel_tar=s[19:22],
+                       acc_tar=z3, pos_traj=g["pos_traj"], vel_traj=g["vel_traj"], acc_traj=np.zeros_like(g["pos_traj"]), time=int(g["time"]))
+    action, cp2, _ = ctl(None, st, env.default_params, g["rng_act"], cp.replace(a_mean=g["a_mean"]), {"noisy_state": st})
+    assert np.abs(np.asarray(action) - g["action"]).max() < 2e-4
+    assert np.abs(np.asarray(cp2.a_mean) - g["a_mean_new"]).max() < 2e-4
+    if name != "mppi":
+        assert np.linalg.norm(np.asarray(cp2.a_cov) - g["a_cov"]) / np.linalg.norm(g["a_cov"]) < 5e-5

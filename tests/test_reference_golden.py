@@ -125,3 +125,21 @@ def test_covo_offline_schedule_matches_the_reference_source():
     tab = o.covo_offline_schedule(_call_state(g), o.EnvParams(), int(g["H"]), 0.5, np.random.default_rng(0), n_steps=3)
     for k in range(3):
         assert np.linalg.norm(tab[k] - g["a_cov_offline"][k]) / np.linalg.norm(g["a_cov_offline"][k]) < 2e-5, k
+
+
+@pytest.mark.parametrize("name", ["covo_online", "mppi"])
+def test_keyed_call_matches_the_reference_source(name):
+    """The reference's __call__ handed a PRNGKey (jax.random = the Threefry twin, generator section 10): the oracle fed the
+    normals that key produces lands on the same update."""
+    from covo_mpc_b200 import jaxrng as jr
+
+    g = np.load(os.path.join(G, f"reference_call_{name}_keyed.npz"))
+    N, H = int(g["N"]), int(g["H"])
+    act_key = jr.split(g["rng_act"])[1]  # rng_act, act_key = split(rng_act)   (covo.py:212, mppi.py:53)
+    if name == "mppi":
+        u, new_mean, _, _ = o.mppi_call(_call_state(g), g["a_mean"], g["a_cov_in"], jr.mppi_normals(act_key, N, H), o.EnvParams(),
+                                        lam=float(g["lam"]))
+    else:
+        u, new_mean, a_cov, _ = o.covo_call(_call_state(g), g["a_mean"], jr.covo_normals(act_key, N, 4 * H), o.EnvParams(), lam=float(g["lam"]))
+        assert np.linalg.norm(a_cov - g["a_cov"]) / np.linalg.norm(g["a_cov"]) < 2e-5
+    assert np.abs(new_mean - g["a_mean_new"]).max() < 2e-5 and np.abs(u - g["action"]).max() < 2e-5
