@@ -290,7 +290,10 @@ def run_gpu(args):
                    "controller": mode_name, "n_samples": N_SAMPLES, "horizon": HORIZON, "envs_per_gpu": 1,
                    "parallelism": ("env-replicas x%d (no collective)" % world) if shard == "env" else "nsample-shard x%d (allgather 808B/rank/step)" % world,
                    "rng": "in-kernel Philox (production mode)", "l2": "256 MiB memset between steps, excluded from the event timing",
-                   "timing": "CUDA events per step on the launch stream, sum over K steps, max over ranks"},
+                   "timing": "CUDA events per step on the launch stream, sum over K steps, max over ranks",
+                   "pipeline": ("cholesky -> rollout as a programmatic dependent launch: the rollout kernel runs next to the factorisation "
+                                "and consumes the factor 8 columns at a time; roofline_kernels are per-kernel times with the pipeline "
+                                "switched off (profiling mode), so their sum exceeds ms_per_step") if mode_name == "covo-online" else "n/a"},
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
         "step_ms_p50": float(np.median(step_ms)), "step_ms_p99": float(np.percentile(step_ms, 99)),
         "gpu_launches": launches_per_step * K, "clocks": clocks,

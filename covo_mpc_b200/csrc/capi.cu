@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -97,6 +98,13 @@ struct covo_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t aux_stream = nullptr;  // side stream of the covariance step (Q accumulation next to E2)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // Cholesky -> rollout pipeline: the rollout kernel runs next to the factorisation and consumes the factor column block
+    // by column block (RolloutArgs::lfac_progress)
+    DevBuf<int> chol_progress;  // [E] monotone counter: epoch + finished column blocks
+    int chol_epoch = 64;
+    int num_sms = 0;
+    bool pipeline_enabled = true;
+    bool pipeline_forced = false;  // COVO_PIPELINE=2 (development): keep the pipeline on while per-kernel timings are taken
     unsigned int rng_stream = 0;
     bool jax_key_pending = false;  // covo_set_jax_key: the next sampling launch uses the JAX-compatible stream
     unsigned int jax_key[2] = {0, 0};
@@ -163,6 +171,7 @@ void release_all(covo_handle* h) {
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    h->chol_progress.release();
 }
 
 HessianArgs hess_args(covo_handle* h, const float* st, const int* tm, const float* a_mean, int shift, float* R, float* ws,
@@ -275,7 +284,15 @@ struct Prof {
 };
 
 // covariance step for the online mode: R (already in h->R) -> cov -> factor
-int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = false) {
+// The rollout kernel may run NEXT TO the Cholesky kernel (programmatic dependent launch: it starts once every Cholesky CTA is
+// resident and has released it) when both grids fit on the device together with room to spare -- every CTA of either kernel on
+// an SM of its own in the worst case -- and nothing asks for per-kernel timings.
+bool pipeline_ok(covo_handle* h) {
+    return h->pipeline_enabled && ((!h->profiling && !h->phase_clocks) || h->pipeline_forced) && h->cfg.world == 1 &&
+           rollout_is_overlapped(h->n_pad, 0, h->H) && (long long)(h->n_cta + 1) * h->E <= h->num_sms;
+}
+
+int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = false, bool pipelined = false) {
     SigmaArgs sa = sigma_args(h);
     if (!want_L) sa.L = nullptr;  // the sampler only needs the packed factor
     CK(launch_tridiag(sa, h->E, st));
@@ -292,6 +309,10 @@ int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = fals
     CK(launch_sandwich(sa, h->E, st));
     if (pf) pf->mark(4);
     sa.cov_symmetric = 1;
+    if (pipelined) {  // the rollout kernel follows in the same stream as a programmatic dependent launch (step_common)
+        sa.progress = h->chol_progress.p;
+        sa.epoch = h->chol_epoch;
+    }
     CK(launch_cholesky(sa, h->E, st));
     if (pf) pf->mark(5);
     h->have_factor = true;
@@ -302,6 +323,7 @@ int step_common(covo_handle* h, const float* st_d, const int* tm_d, const float*
                 int finalize) {
     Prof pf(h, st);
     const int mode = h->cfg.mode;
+    bool pipelined = false;
     if (h->pos_stats_on) CK(cudaMemsetAsync(h->pos_stats.p, 0, h->pos_stats.n * sizeof(float), st));
     if (mode == COVO_MODE_MPPI) {
         shift_blocks_kernel<<<h->E, 128, 2 * h->H * 16 * sizeof(float), st>>>(h->Lblk.p, h->cov.p, h->H);
@@ -311,13 +333,19 @@ int step_common(covo_handle* h, const float* st_d, const int* tm_d, const float*
         HessianArgs ha = hess_args(h, st_d, tm_d, h->a_mean.p, 1, h->R.p, h->hess_ws.p, (long long)h->T * 3);
         CK(launch_hessian(ha, h->E, st));
         pf.mark(1);
-        int rc = run_sigma_chol(h, st, &pf);
+        pipelined = pipeline_ok(h);
+        int rc = run_sigma_chol(h, st, &pf, false, pipelined);
         if (rc) return rc;
     } else {
         if (h->t_sched <= 0) return fail(COVO_ERR_INVALID, "covo-offline: no schedule; call covo_reset_offline or covo_set_cov_offline first");
         for (int i = 1; i <= 5; ++i) pf.mark(i);
     }
     RolloutArgs ra = rollout_args(h, st_d, tm_d, h->a_mean.p, 1, eps_d, nullptr, h->a_mean.p, act_d, nullptr, nullptr, finalize);
+    if (pipelined) {
+        ra.lfac_progress = h->chol_progress.p;
+        ra.lfac_epoch = h->chol_epoch;
+        h->chol_epoch += 64;
+    }
     CK(launch_rollout(ra, h->E, st));
     pf.mark(6);
     if (!eps_d) h->rng_stream += 1;
@@ -420,6 +448,14 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
     A(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
     A(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     A(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    {
+        A(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+        A(h->chol_progress.alloc(E));
+        if (e == cudaSuccess) A(cudaMemset(h->chol_progress.p, 0, E * sizeof(int)));
+        const char* pe = getenv("COVO_PIPELINE");
+        h->pipeline_enabled = !(pe && pe[0] == '0');
+        h->pipeline_forced = pe && pe[0] == '2';
+    }
     for (auto& ev : h->ev) A(cudaEventCreate(&ev));
     A(h->state24.alloc(E * kStateFloats));
     A(h->time.alloc(E));

@@ -66,6 +66,10 @@ struct RolloutArgs {
     long long lfac_stride;   // floats between environments in Lfac
     long long lfac_time_stride;  // CoVO-offline: factor table indexed by min(time, lfac_time_max)
     int lfac_time_max;
+    // Cholesky -> rollout pipeline (dense mode, overlap layout only): the factor arrives column block by column block while
+    // cholesky_kernel is still running; lfac_progress[env] >= lfac_epoch + j + 1 means column block j (8 columns) is in HBM
+    const int* lfac_progress = nullptr;
+    int lfac_epoch = 0;
     int overlap = 0;  // set by launch_rollout: sampling GEMM and rollouts run concurrently (separate U tile fits in smem)
 };
 
@@ -97,5 +101,6 @@ inline cudaError_t ensure_smem_attr(K kernel, size_t bytes, size_t (&configured)
 cudaError_t launch_rollout(const RolloutArgs& a, int n_env, cudaStream_t st);
 cudaError_t launch_merge(const MergeArgs& a, cudaStream_t st);
 size_t rollout_smem_bytes(int n_pad, int mode, int H);
+int rollout_is_overlapped(int n_pad, int mode, int H);  // GEMM / rollout overlap layout in use (needed by the Cholesky pipeline)
 
 }  // namespace covo

@@ -16,6 +16,7 @@
 //            from the U tile (conflict-free), reference rows broadcast from shared memory;
 //   phase 3  tile-local (min, sum exp, sum exp * u) partial, then a single grid-wide merge by the last
 //            CTA to finish (overflow-safe: partials carry their own min).
+#include <cstdio>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -59,6 +60,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ int warp_id_of(int tid) { return tid >> 5; }
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
@@ -82,7 +89,8 @@ struct Smem {
     float* cost;   // [TS]
     float* wgt;    // [TS]
     float* red;    // [32] scratch
-    uint64_t* bar;
+    uint64_t* bar;   // whole-factor staging barrier
+    uint64_t* cbar;  // [32] one barrier per 8-column block of the factor (Cholesky -> rollout pipeline)
 };
 
 __device__ __forceinline__ Smem carve(unsigned char* base, int n_pad, int H, int lfac_floats, int overlap) {
@@ -112,6 +120,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int n_pad, int H, int
     s.red = f;
     f += 32;
     s.bar = reinterpret_cast<uint64_t*>(f);
+    s.cbar = s.bar + 1;
     return s;
 }
 
@@ -121,12 +130,13 @@ static size_t rollout_smem_bytes2(int n_pad, int mode, int H, int overlap) {
     int lf = (mode == 0) ? lt_size(4 * H, n_pad) : H * 16;
     lf = (lf + 3) & ~3;
     size_t floats = (size_t)lf + (size_t)n_pad * TSP * (overlap ? 2 : 1) + 8 + n_pad + H * 8 + H * 4 + TS + TS + 32;
-    return floats * sizeof(float) + 16;
+    return floats * sizeof(float) + 8 * 34;
 }
 // GEMM / rollout overlap needs a second [n_pad][TSP] tile: possible while everything fits into 227 KB (n <= 208)
 static int rollout_overlap(int n_pad, int mode, int H) {
     return mode == 0 && rollout_smem_bytes2(n_pad, mode, H, 1) <= (size_t)227 * 1024;
 }
+int rollout_is_overlapped(int n_pad, int mode, int H) { return rollout_overlap(n_pad, mode, H); }
 size_t rollout_smem_bytes(int n_pad, int mode, int H) { return rollout_smem_bytes2(n_pad, mode, H, rollout_overlap(n_pad, mode, H)); }
 
 __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const RolloutArgs a) {
@@ -143,12 +153,16 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
 
     COVO_STAMP(a, 32);
     // ---------------- phase 0: staging -------------------------------------------------------
+    // the factor streams in behind the running Cholesky kernel (see phase 1) instead of being staged here
+    const bool pipelined = a.lfac_progress != nullptr && a.mode == 0 && a.overlap;
     if (tid == 0) {
         mbar_init(sm.bar, 1);
+        if (pipelined)
+            for (int g = 0; g < (n_pad >> 3); ++g) mbar_init(sm.cbar + g, 1);
     }
     if (tid < 8) sm.prog[tid] = -1;
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && !pipelined) {
         const uint32_t total = (uint32_t)lfac_floats * 4u;
         mbar_expect_tx(sm.bar, total);
         uint32_t done = 0;
@@ -246,7 +260,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
     }
     __syncthreads();
     COVO_STAMP(a, 33);
-    mbar_wait(sm.bar, 0);
+    if (!pipelined) mbar_wait(sm.bar, 0);
     COVO_STAMP(a, 34);
 
     // ---------------- phases 1 + 2 overlapped ------------------------------------------------------
@@ -263,8 +277,11 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
         const int sg = lane & 15, rq = lane >> 4;
         const int G = n_pad >> 3;
         volatile int* prog = sm.prog;
+        int blocks_seen = 0;  // column blocks of the factor this warp has already waited for
         for (int g = slot; g < G; g += kGemmSlots) {
             const int K = min(8 * g + 8, n);
+            if (pipelined)  // row group g reads column blocks 0 .. g
+                for (; blocks_seen <= g; ++blocks_seen) mbar_wait(sm.cbar + blocks_seen, 0);
             const float* Erow = sm.tile + 4 * sg;
             float2 acc[4][2];
 #pragma unroll
@@ -297,6 +314,36 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
             __threadfence_block();
             __syncwarp();
             if (lane == 0) prog[slot] = g;
+        }
+    } else if (pipelined && tid == 4 * 32) {
+        // warp 4 is idle in this phase: its first lane follows the Cholesky kernel's progress counter and pulls every
+        // finished 8-column block of the packed factor (one contiguous piece) into shared memory with one bulk copy
+        const int G = n_pad >> 3;
+        const int* flag = a.lfac_progress + env;
+        unsigned long long t_start;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+        for (int g = 0; g < G; ++g) {
+            bool lost = false;
+            while (ld_acquire_gpu(flag) - (a.lfac_epoch + g + 1) < 0) {
+                __nanosleep(64);
+                unsigned long long t_now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+                if (t_now - t_start > 4000000000ull) {  // 4 s: the producer kernel is not running (cannot happen under
+                    lost = true;                         // pipeline_ok()); release the consumers instead of hanging the device
+                    break;
+                }
+            }
+            if (lost) {
+                if (blockIdx.x == 0) printf("covo rollout: Cholesky pipeline stalled at block %d (env %d)\n", g, env);
+                for (int gg = g; gg < G; ++gg)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sm.cbar + gg)) : "memory");
+                break;
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");  // the block was written by generic-proxy stores of another SM
+            const int off = lt_col_offset(8 * g, n_pad);
+            const uint32_t bytes = (uint32_t)(lt_col_offset(min(8 * g + 8, n), n_pad) - off) * 4u;
+            mbar_expect_tx(sm.cbar + g, bytes);
+            tma_load_1d(sm.lfac + off, lfac_g + off, bytes, sm.cbar + g);
         }
     }
     // ---------------- phase 1: U = clip(mu + E L^T) ------------------------------------------
@@ -668,6 +715,23 @@ cudaError_t launch_rollout(const RolloutArgs& a_in, int n_env, cudaStream_t st) 
     if (e != cudaSuccess) return e;
     int n_cta = (a.n_samples + TS - 1) / TS;
     dim3 grid(n_cta, n_env);
+    if (a.lfac_progress) {
+        // programmatic dependent launch: this grid may start as soon as every CTA of the preceding kernel in the stream
+        // (cholesky_kernel) has executed griddepcontrol.launch_dependents -- i.e. while the factorisation is running and
+        // already resident, which is what makes spinning on its progress counter safe.  The kernel never calls
+        // griddepcontrol.wait: the counter is its only dependency on the primary.
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kRolloutThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, rollout_kernel, a);
+    }
     rollout_kernel<<<grid, kRolloutThreads, smem, st>>>(a);
     return cudaGetLastError();
 }

@@ -1007,6 +1007,9 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
     float* As = reinterpret_cast<float*>(smraw);  // [n][n]
     float* Lp = As + n * n;                       // panel buffers, see below
     float* covg = a.cov + (long long)env * n * n;
+    // pipeline mode: let the dependent grid (the rollout kernel, launched with programmatic stream serialisation) start now;
+    // it synchronises with this kernel through a.progress only
+    if (a.progress) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     COVO_STAMP(a, 23);
     // (a_cov + a_cov.T)/2, controllers/covo.py:132, in ONE pass: the row part of a float4 is read coalesced, its
     // four transposed partners straight from L2; all loads of a batch are in flight together.
@@ -1148,7 +1151,19 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
         if (pt >= 0 && pt < 64) {
             const int r = pt >> 3, c = pt & 7;
             if (r < nb && c < nb) As[(jb + r) * n + jb + c] = Lp8[pt];
+            if (a.progress && c < nb) {  // rows jb .. jb+7 of the packed columns jb + c (zeros above the diagonal)
+                a.Lt[(long long)env * a.lt_stride + lt_col_offset(jb + c, n_pad) + r] = (r < nb) ? Lp8[pt] : 0.f;
+            }
         }
+        if (a.progress && pt < 0) {
+            // columns jb .. jb+nb-1 are final: rows below the block come from the transposed panel, rows >= n are padding
+            float* Ltg = a.Lt + (long long)env * a.lt_stride;
+            const int len = n_pad - jb - 8;
+            for (int q = tid; q < nb * len; q += TC - kPanelThreads) {
+                const int c = q / len, i = jb + 8 + (q - c * len);
+                Ltg[lt_col_offset(jb + c, n_pad) + (i - jb)] = (i < n) ? LpCur[c * n_pad + i] : 0.f;
+            }
+        }  // (published after the barrier at the end of the iteration)
         const int r0 = jb + nb;           // first row / column of the trailing matrix
         if (r0 >= n) break;
         const int nbn = min(8, n - r0);   // width of the next panel
@@ -1220,8 +1235,14 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
             }
         }
         __syncthreads();
+        // one release by one thread publishes the block: the CTA barrier orders every thread's stores before it and a
+        // release is cumulative (PTX memory model).  The publisher is the last trailing-update thread, idle in late panels.
+        if (a.progress && tid == TC - kPanelThreads - 32)
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.progress + env), "r"(a.epoch + it + 1) : "memory");
     }
     __syncthreads();
+    if (a.progress && tid == 0)  // the last block (its iteration left the loop before the barrier)
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.progress + env), "r"(a.epoch + ((n + 7) >> 3)) : "memory");
     COVO_STAMP(a, 25);
     // outputs: row-major L (upper part zeroed) and the packed k-major factor
     if (a.L) {
@@ -1229,7 +1250,7 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
         for (int i = warp; i < n; i += TC / 32)
             for (int j = lane; j < n; j += 32) Lg[i * n + j] = (j <= i) ? As[i * n + j] : 0.f;
     }
-    if (a.Lt) {
+    if (a.Lt && !a.progress) {
         float* Ltg = a.Lt + (long long)env * a.lt_stride;
         for (int k = warp; k < n; k += TC / 32) {
             const int rs = k & ~7;

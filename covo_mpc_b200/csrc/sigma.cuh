@@ -27,6 +27,10 @@ struct SigmaArgs {
     long long lt_stride;
     int e2_points = 16;     // trial shifts (= warps) per multisection round in E2 (measured: 16 beats 32 and 8)
     int cov_symmetric = 0;  // cov is exactly symmetric already (written by the sandwich kernel): Cholesky skips (C + C^T)/2
+    // Cholesky -> rollout pipeline: when set, every finished 8-column block of the packed factor is written to Lt at once and
+    // progress[env] is released to epoch + (blocks done), so that a concurrently running rollout kernel can start sampling
+    int* progress = nullptr;
+    int epoch = 0;
 };
 
 // host: Zolotarev/Hale-Higham-Trefethen nodes for x^(-1/2) on [m, M]

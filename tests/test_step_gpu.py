@@ -310,3 +310,31 @@ def test_keyed_episode_follows_the_reference_key_schedule():
     assert np.abs(np.asarray(a_key) - np.asarray(a_eps)).max() < 1e-4
     _, st1, _, _, info1 = env.step(rng_step, state, a_key, params)
     assert abs(info1["err_pos"] - e1[0]) < 1e-6
+
+
+@pytest.mark.parametrize("E,N,H", [(1, 8192, 50), (3, 1024, 20), (1, 256, 9)])
+def test_cholesky_rollout_pipeline_is_bit_identical(monkeypatch, E, N, H):
+    """The rollout kernel started next to the Cholesky kernel (programmatic dependent launch, factor consumed block by
+    block) must produce exactly what the serial schedule produces: same arithmetic, different timing only.  Covers the
+    headline size, a small batch of environments (one progress counter each) and n = 36 (last column block 4 wide)."""
+    from covo_mpc_b200 import _lib
+
+    scen = [scenario("tracking_zigzag", seed=60 + e, H=H, warm_steps=2 + e) for e in range(E)]
+    T = scen[0][1].pos_traj.shape[0]
+    st = np.stack([o.state_to_vec24(s[1]) for s in scen])
+    tm = [s[1].time for s in scen]
+
+    def run(flag):
+        monkeypatch.setenv("COVO_PIPELINE", flag)
+        cfg = _lib.default_config()
+        cfg.mode, cfg.n_samples, cfg.horizon, cfg.traj_len, cfg.n_env, cfg.seed = _lib.MODE_COVO_ONLINE, N, H, T, E, 5
+        h = _lib.Handle(cfg)
+        h.set_reference(np.stack([s[1].pos_traj for s in scen]), np.stack([s[1].vel_traj for s in scen]))
+        h.set_mean(np.stack([s[2] for s in scen]))
+        acts = [h.step(st, tm).copy() for _ in range(4)]  # the mean moves on: four different factors
+        return np.stack(acts), h.get_mean(), h.get_cov()
+
+    a1, m1, c1 = run("1")
+    a0, m0, c0 = run("0")
+    assert np.isfinite(a1).all()
+    assert np.array_equal(a1, a0) and np.array_equal(m1, m0) and np.array_equal(c1, c0)
