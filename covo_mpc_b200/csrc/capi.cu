@@ -101,7 +101,7 @@ struct covo_handle {
     // Cholesky -> rollout pipeline: the rollout kernel runs next to the factorisation and consumes the factor column block
     // by column block (RolloutArgs::lfac_progress)
     DevBuf<int> chol_progress;  // [E] monotone counter: epoch + finished column blocks
-    int chol_epoch = 64;
+    unsigned int chol_epoch = 64;  // wraps; compared as a signed difference on the device
     int num_sms = 0;
     bool pipeline_enabled = true;
     bool pipeline_forced = false;  // COVO_PIPELINE=2 (development): keep the pipeline on while per-kernel timings are taken
@@ -311,7 +311,7 @@ int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = fals
     sa.cov_symmetric = 1;
     if (pipelined) {  // the rollout kernel follows in the same stream as a programmatic dependent launch (step_common)
         sa.progress = h->chol_progress.p;
-        sa.epoch = h->chol_epoch;
+        sa.epoch = (int)h->chol_epoch;
     }
     CK(launch_cholesky(sa, h->E, st));
     if (pf) pf->mark(5);
@@ -343,7 +343,7 @@ int step_common(covo_handle* h, const float* st_d, const int* tm_d, const float*
     RolloutArgs ra = rollout_args(h, st_d, tm_d, h->a_mean.p, 1, eps_d, nullptr, h->a_mean.p, act_d, nullptr, nullptr, finalize);
     if (pipelined) {
         ra.lfac_progress = h->chol_progress.p;
-        ra.lfac_epoch = h->chol_epoch;
+        ra.lfac_epoch = (int)h->chol_epoch;
         h->chol_epoch += 64;
     }
     CK(launch_rollout(ra, h->E, st));

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
         for (int g = 0; g < G; ++g) {
             bool lost = false;
-            while (ld_acquire_gpu(flag) - (a.lfac_epoch + g + 1) < 0) {
+            while ((int)((unsigned)ld_acquire_gpu(flag) - ((unsigned)a.lfac_epoch + (unsigned)(g + 1))) < 0) {  // wrap-safe
                 __nanosleep(64);
                 unsigned long long t_now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));

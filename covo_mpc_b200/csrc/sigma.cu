@@ -1238,11 +1238,11 @@ __global__ void __launch_bounds__(TC, 1) cholesky_kernel(const SigmaArgs a) {
         // one release by one thread publishes the block: the CTA barrier orders every thread's stores before it and a
         // release is cumulative (PTX memory model).  The publisher is the last trailing-update thread, idle in late panels.
         if (a.progress && tid == TC - kPanelThreads - 32)
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.progress + env), "r"(a.epoch + it + 1) : "memory");
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.progress + env), "r"((int)((unsigned)a.epoch + (unsigned)(it + 1))) : "memory");
     }
     __syncthreads();
     if (a.progress && tid == 0)  // the last block (its iteration left the loop before the barrier)
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.progress + env), "r"(a.epoch + ((n + 7) >> 3)) : "memory");
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.progress + env), "r"((int)((unsigned)a.epoch + (unsigned)((n + 7) >> 3))) : "memory");
     COVO_STAMP(a, 25);
     // outputs: row-major L (upper part zeroed) and the packed k-major factor
     if (a.L) {
