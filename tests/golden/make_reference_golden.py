@@ -528,6 +528,31 @@ def main():
                             pos_traj=np.asarray(st.pos_traj, F), vel_traj=np.asarray(st.vel_traj, F), a_mean=a_prev, rng_act=key,
                             a_cov_in=np.asarray(cp.a_cov, F), a_cov=np.asarray(cp2.a_cov, F), a_mean_new=np.asarray(cp2.a_mean, F),
                             action=np.asarray(u, F), lam=ctl.lam, N=ctl.N, H=ctl.H)
+
+    # ---- 11. the whole evaluation protocol: eval_env executed from the reference (envs/quadrotor.py:506-591) -------------------
+    # Controller = the reference's RandomController (0.3 * normal(rng_act, (4,))): CPU-only, and wild enough to fly out of the
+    # |pos| <= 3 box, so BaseEnvironment.step's auto-reset (base.py:27-38) is exercised.  Pins the key schedule of the
+    # protocol end to end: PRNGKey(1), reset keys, per-step split(rng, 4), env.step, the extra split after every step.
+    import tempfile
+
+    import quadjax as _q
+    from quadjax.controllers import RandomController
+    from quadjax.envs import quadrotor as ref_quadrotor
+
+    tmp = tempfile.mkdtemp()
+    os.makedirs(os.path.join(tmp, "pkg"))
+    _q.get_package_path = lambda: os.path.join(tmp, "pkg")  # results/ lands under tmp instead of the read-only reference tree
+    ev = {}
+    for disturb in ("none", "gaussian"):
+        e = Quad3D(task="tracking_zigzag", obs_type="quad", lower_controller="base", enable_randomizer=False, disturb_type=disturb,
+                   disable_rollover_terminate=True, generate_noisy_state=True)
+        e.get_obs = lambda *a, **k: None
+        ref_quadrotor.eval_env(e, RandomController(e, None), total_steps=300 * 4, filename=f"random_{disturb}")
+        import pickle
+
+        with open(os.path.join(tmp, "results", f"eval_err_pos_random_{disturb}.pkl"), "rb") as f:
+            ev[disturb] = np.asarray(pickle.load(f), np.float64)
+    np.savez_compressed(os.path.join(out_dir, "reference_eval_env_random.npz"), **ev)
     print("reference goldens written to", out_dir)
 
 

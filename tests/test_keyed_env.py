@@ -55,3 +55,18 @@ def test_zigzag_key_quirks():
     seg = [np.linalg.norm(vel[40 * i]) * 41 * 0.02 for i in range(8)]  # |next - prev| per segment
     assert abs(seg[0] - seg[1]) < 1e-5 and 1.0 <= min(seg) and max(seg) <= 1.5
     assert len({round(float(x), 5) for x in seg[1:]}) == 7
+
+
+@pytest.mark.parametrize("disturb", ["none", "gaussian"])
+def test_eval_env_protocol_matches_the_reference_source(disturb):
+    """harness.eval_env(keyed=True) vs the reference's eval_env executed from its own source (generator section 11) with the
+    reference's RandomController: PRNGKey(1), four reset keys, per-step split(rng, 4), env.step with auto-reset (the random
+    policy leaves the |pos| <= 3 box), the extra split after each step -- per-episode mean err_pos must coincide."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_eval_env_random.npz"))[disturb]
+    env = cm.Quad3D("tracking_zigzag", disturb_type=disturb)
+    ctl, _ = cm.get_controller(env, "random")
+    mean, std, per_ep = cm.eval_env(env, ctl, total_steps=300 * 4, num_trajs=4, seed=1, keyed=True)
+    assert per_ep.shape == g.shape == (4,)
+    assert per_ep.mean() > 0.5  # the episodes do crash and get reset: the auto-reset path is part of what is compared
+    assert np.abs(per_ep - g).max() < 1e-5, (per_ep, g)  # observed 1e-7
+    assert abs(mean - g.mean()) < 1e-5 and abs(std - g.std()) < 1e-5
