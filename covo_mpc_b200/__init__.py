@@ -9,10 +9,10 @@ from .env import Quad3D, EnvParams3D, EnvState3D
 from .controllers import (BaseController, MPPIController, CoVOController, PIDController, RandomController, MPPIParams, CoVOParams,
                           PIDParams, get_controller)
 from . import jaxrng
-from .harness import run_episode, run_episode_device, run_episode_keyed, eval_env, save_eval_results, save_state_seq
+from .harness import run_episode, run_episode_device, run_episode_keyed, render_env, eval_env, save_eval_results, save_state_seq
 
 _lib.load()
 
 __all__ = ["Handle", "CovoConfig", "default_config", "MODE_MPPI", "MODE_COVO_ONLINE", "MODE_COVO_OFFLINE",
            "Quad3D", "EnvParams3D", "EnvState3D", "BaseController", "MPPIController", "CoVOController",
-           "PIDController", "RandomController", "MPPIParams", "CoVOParams", "PIDParams", "get_controller", "jaxrng", "run_episode", "run_episode_device", "run_episode_keyed", "eval_env", "save_eval_results", "save_state_seq"]
+           "PIDController", "RandomController", "MPPIParams", "CoVOParams", "PIDParams", "get_controller", "jaxrng", "run_episode", "run_episode_device", "run_episode_keyed", "render_env", "eval_env", "save_eval_results", "save_state_seq"]

@@ -84,6 +84,43 @@ def run_episode_keyed(env, controller, rng_reset, rng, n_steps: Optional[int] = 
     return rng, np.asarray(errs), np.asarray(rews)
 
 
+def render_env(env, controller, control_params=None, repeat_times: int = 1, filename: str = "", results_dir: Optional[str] = "results",
+               seed: int = 1):
+    """The eager loop of the reference's ``render_env`` (quadjax/envs/quadrotor.py:594-667) with its key schedule:
+    ``PRNGKey(1)``; one split each for the parameter draw, the reset and the controller reset; per step
+    ``rng, rng_act, rng_step = split(rng, 3)``; after a ``done`` two more splits (parameters, controller reset) and the
+    controller is reset with its CURRENT params (:636-641).  Runs until ``repeat_times`` episodes have ended and writes
+    ``results/state_seq_{filename}.pkl`` (list of per-step state dicts, :655-666); plotting (``utils.plot_states``) is out of
+    scope.  Returns (state_seq, reward_seq)."""
+    rng = jr.PRNGKey(seed)
+    rng, rng_params = jr.split(rng)
+    env_params = env.sample_params(rng_params)
+    state_seq, reward_seq = [], []
+    rng, rng_reset = jr.split(rng)
+    obs, info, env_state = env.reset(rng_reset, env_params)
+    rng, rng_control = jr.split(rng)
+    control_params = controller.reset(env_state, env_params, controller.init_control_params, rng_control)
+    n_dones = 0
+    while n_dones < repeat_times:
+        state_seq.append(dict(env_state.__dict__))
+        rng, rng_act, rng_step = jr.split(rng, 3)
+        action, control_params, _ = controller(obs, env_state, env_params, rng_act, control_params, info)
+        if hasattr(control_params, "quat_desired"):  # :626-627
+            state_seq[-1]["quat_desired"] = control_params.quat_desired
+        next_obs, next_env_state, reward, done, info = env.step(rng_step, env_state, action, env_params)
+        if done:
+            rng, rng_params = jr.split(rng)
+            env_params = env.sample_params(rng_params)
+            rng, rng_control = jr.split(rng)
+            control_params = controller.reset(env_state, env_params, control_params, rng_control)
+            n_dones += 1
+        reward_seq.append(reward)
+        obs, env_state = next_obs, next_env_state
+    if results_dir is not None:
+        save_state_seq(state_seq, filename, results_dir)
+    return state_seq, reward_seq
+
+
 def eval_env(env, controller, total_steps: int = 300 * 4 * 10, num_trajs: int = 4, seed: int = 1, keyed: bool = False):
     """quadjax/envs/quadrotor.py:506-591 (PRNGKey(1); num_trajs reference trajectories, each re-used for
     num_eps // num_trajs episodes).  Returns (mean, std, per-episode array).

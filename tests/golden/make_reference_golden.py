@@ -553,6 +553,24 @@ def main():
         with open(os.path.join(tmp, "results", f"eval_err_pos_random_{disturb}.pkl"), "rb") as f:
             ev[disturb] = np.asarray(pickle.load(f), np.float64)
     np.savez_compressed(os.path.join(out_dir, "reference_eval_env_random.npz"), **ev)
+
+    # ---- 12. render_env executed from the reference (envs/quadrotor.py:594-667), RandomController, one episode -----------------
+    # utils.plot_states (matplotlib figures) is out of scope and stubbed; everything else, including the state_seq pickle, is the
+    # reference's own code.
+    from quadjax.dynamics import utils as ref_utils
+
+    ref_utils.plot_states = lambda *a, **k: None
+    e = Quad3D(task="tracking_zigzag", obs_type="quad", lower_controller="base", enable_randomizer=False, disturb_type="gaussian",
+               disable_rollover_terminate=True, generate_noisy_state=True)
+    e.get_obs = lambda *a, **k: None
+    rc = RandomController(e, None)
+    ref_quadrotor.render_env(e, rc, None, repeat_times=1, filename="random")
+    with open(os.path.join(tmp, "results", "state_seq_random.pkl"), "rb") as f:
+        seq = pickle.load(f)
+    np.savez_compressed(os.path.join(out_dir, "reference_render_env_random.npz"),
+                        keys=np.array(sorted(seq[0].keys())), n_steps=len(seq),
+                        **{k: np.stack([np.asarray(d[k], np.float32) for d in seq]) for k in ("pos", "vel", "quat", "omega", "f_disturb", "pos_tar", "vel_tar")},
+                        time=np.array([int(d["time"]) for d in seq]))
     print("reference goldens written to", out_dir)
 
 

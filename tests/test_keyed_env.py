@@ -70,3 +70,25 @@ def test_eval_env_protocol_matches_the_reference_source(disturb):
     assert per_ep.mean() > 0.5  # the episodes do crash and get reset: the auto-reset path is part of what is compared
     assert np.abs(per_ep - g).max() < 1e-5, (per_ep, g)  # observed 1e-7
     assert abs(mean - g.mean()) < 1e-5 and abs(std - g.std()) < 1e-5
+
+
+def test_render_env_matches_the_reference_source(tmp_path):
+    """harness.render_env vs the reference's render_env executed from its own source (generator section 12): same key
+    schedule, same states step for step, same pickle layout (list of per-step state dicts, envs/quadrotor.py:655-666)."""
+    import pickle
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_render_env_random.npz"))
+    env = cm.Quad3D("tracking_zigzag", disturb_type="gaussian")
+    ctl, cp = cm.get_controller(env, "random")
+    seq, rewards = cm.render_env(env, ctl, cp, repeat_times=1, filename="random", results_dir=str(tmp_path))
+    assert len(seq) == int(g["n_steps"]) == len(rewards)
+    for k in ("pos", "vel", "quat", "omega", "f_disturb", "pos_tar", "vel_tar"):
+        mine = np.stack([np.asarray(d[k], np.float32) for d in seq])
+        assert np.abs(mine - g[k]).max() < 1e-4 * max(1.0, np.abs(g[k]).max()), k
+    assert [int(d["time"]) for d in seq] == g["time"].tolist()
+    with open(os.path.join(str(tmp_path), "state_seq_random.pkl"), "rb") as f:
+        stored = pickle.load(f)
+    assert isinstance(stored, list) and len(stored) == len(seq) and isinstance(stored[0], dict)
+    # every field of the reference's dict that scripts/vis.py (:70-95) reads is there under the same name
+    assert {"pos", "quat", "pos_tar", "f_disturb", "pos_traj", "vel", "omega", "time"} <= set(stored[0].keys())
+    assert {"pos", "quat", "pos_tar", "f_disturb", "pos_traj", "vel", "omega", "time"} <= set(g["keys"].tolist())
