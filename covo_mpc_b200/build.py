@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcovo_b200.so")
-SOURCES = ["capi.cu", "rollout.cu", "hessian.cu", "sigma.cu", "offline.cu", "envstep.cu"]
+SOURCES = ["capi.cu", "rollout.cu", "hessian.cu", "sigma.cu", "offline.cu", "envstep.cu", "sigma_dense.cu"]
 HEADERS = ["common.cuh", "quad_model.cuh", "rng.cuh", "hessian.cuh", "hessian_local.cuh", "sigma.cuh", "offline.cuh", "pid.cuh", "envstep.cuh",
            os.path.join("..", "..", "include", "covo_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

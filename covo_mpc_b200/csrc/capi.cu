@@ -104,7 +104,10 @@ struct covo_handle {
     unsigned int chol_epoch = 64;  // wraps; compared as a signed difference on the device
     int num_sms = 0;
     bool pipeline_enabled = true;
-    bool pipeline_forced = false;  // COVO_PIPELINE=2 (development): keep the pipeline on while per-kernel timings are taken
+    bool pipeline_forced = false;
+    bool sigma_dense = false;  // COVO_SIGMA=dense: experimental tridiagonalisation-free optimize_sigma (sigma_dense.cu)
+    DevBuf<double> dense_scal;
+    DevBuf<float> dense_X;  // COVO_PIPELINE=2 (development): keep the pipeline on while per-kernel timings are taken
     unsigned int rng_stream = 0;
     bool jax_key_pending = false;  // covo_set_jax_key: the next sampling launch uses the JAX-compatible stream
     unsigned int jax_key[2] = {0, 0};
@@ -172,6 +175,8 @@ void release_all(covo_handle* h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     h->chol_progress.release();
+    h->dense_scal.release();
+    h->dense_X.release();
 }
 
 HessianArgs hess_args(covo_handle* h, const float* st, const int* tm, const float* a_mean, int shift, float* R, float* ws,
@@ -295,19 +300,28 @@ bool pipeline_ok(covo_handle* h) {
 int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = false, bool pipelined = false) {
     SigmaArgs sa = sigma_args(h);
     if (!want_L) sa.L = nullptr;  // the sampler only needs the packed factor
-    CK(launch_tridiag(sa, h->E, st));
-    if (pf) pf->mark(2);
-    // Q^T from the reflectors does not depend on the tridiagonal matrix function: it runs on a side stream, in
-    // the shadow of E2, and joins before the sandwich kernel
-    CK(cudaEventRecord(h->ev_fork, st));
-    CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
-    CK(launch_qacc(sa, h->E, h->aux_stream));
-    CK(cudaEventRecord(h->ev_join, h->aux_stream));
-    CK(launch_trifunc(sa, h->E, st));
-    if (pf) pf->mark(3);
-    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
-    CK(launch_sandwich(sa, h->E, st));
-    if (pf) pf->mark(4);
+    if (h->sigma_dense) {  // experimental: Lanczos + 17 shifted factorisations + combine instead of E1-E3
+        CK(launch_sigma_dense(sa, h->dense_scal.p, h->dense_X.p, h->E, st));
+        if (pf) {
+            pf->mark(2);
+            pf->mark(3);
+            pf->mark(4);
+        }
+    } else {
+        CK(launch_tridiag(sa, h->E, st));
+        if (pf) pf->mark(2);
+        // Q^T from the reflectors does not depend on the tridiagonal matrix function: it runs on a side stream, in
+        // the shadow of E2, and joins before the sandwich kernel
+        CK(cudaEventRecord(h->ev_fork, st));
+        CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+        CK(launch_qacc(sa, h->E, h->aux_stream));
+        CK(cudaEventRecord(h->ev_join, h->aux_stream));
+        CK(launch_trifunc(sa, h->E, st));
+        if (pf) pf->mark(3);
+        CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+        CK(launch_sandwich(sa, h->E, st));
+        if (pf) pf->mark(4);
+    }
     sa.cov_symmetric = 1;
     if (pipelined) {  // the rollout kernel follows in the same stream as a programmatic dependent launch (step_common)
         sa.progress = h->chol_progress.p;
@@ -455,6 +469,12 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
         const char* pe = getenv("COVO_PIPELINE");
         h->pipeline_enabled = !(pe && pe[0] == '0');
         h->pipeline_forced = pe && pe[0] == '2';
+        const char* se = getenv("COVO_SIGMA");
+        h->sigma_dense = se && strcmp(se, "dense") == 0 && cfg->mode != COVO_MODE_MPPI;
+        if (h->sigma_dense) {
+            A(h->dense_scal.alloc(E * 4));
+            A(h->dense_X.alloc(E * sigma_dense_scratch_floats(h->n)));
+        }
     }
     for (auto& ev : h->ev) A(cudaEventCreate(&ev));
     A(h->state24.alloc(E * kStateFloats));

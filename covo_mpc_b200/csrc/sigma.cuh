@@ -45,4 +45,9 @@ cudaError_t launch_sandwich(const SigmaArgs& a, int n_env, cudaStream_t st);  //
 cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st);     // E1 + E2 + E3: R -> cov
 cudaError_t launch_cholesky(const SigmaArgs& a, int n_env, cudaStream_t st);  // cov -> L, Lt (and symmetrise cov)
 
+// EXPERIMENTAL dense path (sigma_dense.cu; COVO_SIGMA=dense): optimize_sigma without tridiagonalisation.  Writes a.cov (symmetric).
+// scal: [n_env][4] doubles, Xbuf: [n_env][sigma_dense_scratch_floats(n)] floats.
+size_t sigma_dense_scratch_floats(int n);
+cudaError_t launch_sigma_dense(const SigmaArgs& a, double* scal, float* Xbuf, int n_env, cudaStream_t st);
+
 }  // namespace covo
