@@ -240,18 +240,47 @@ class Handle:
             raise ValueError("a JAX key is two uint32 words")
         check(self.lib.covo_set_jax_key(self._h, k.ctypes.data_as(C.POINTER(C.c_uint))))
 
+    def _step_buffers(self):
+        """Staging arrays of the per-step call and their ctypes pointers, made once: building numpy arrays and pointer objects
+        per call cost more than the H2D copy they feed (17 us -> 5 us per call, measured with a no-op library)."""
+        sb = getattr(self, "_step_bufs", None)
+        if sb is None:
+            s = np.empty(self.E * 24, dtype=np.float32)
+            t = np.empty(self.E, dtype=np.int32)
+            out = np.empty((self.E, 4), dtype=np.float32)
+            sb = self._step_bufs = (s, t, out, fptr(s), iptr(t), fptr(out))
+        return sb
+
     def step(self, state24, time, eps=None) -> np.ndarray:
+        if eps is None:  # production path: no per-call allocations besides the returned action
+            s, t, out, sp, tp, op = self._step_buffers()
+            a = np.asarray(state24)
+            if a.size != s.size or np.size(time) != t.size:
+                raise ValueError("state24 / time have the wrong size")
+            s[:] = a.reshape(-1)
+            t[:] = time
+            check(self.lib.covo_step(self._h, sp, tp, None, op))
+            return out.copy()
         s, t = f32(state24), i32(time)
         if s.size != self.E * 24 or t.size != self.E:
             raise ValueError("state24 / time have the wrong size")
-        e = None
-        if eps is not None:
-            e = f32(eps)
-            if e.size != self.E * self.n_local * self.n:
-                raise ValueError("eps must be [E][N_local][4H]")
+        e = f32(eps)
+        if e.size != self.E * self.n_local * self.n:
+            raise ValueError("eps must be [E][N_local][4H]")
         out = np.empty((self.E, 4), dtype=np.float32)
         check(self.lib.covo_step(self._h, fptr(s), iptr(t), fptr(e), fptr(out)))
         return out
+
+    def step_state(self, env_state) -> np.ndarray:
+        """covo_step for ONE environment straight from an EnvState3D-like object (``pack_into``, ``time``): the plugin call's
+        path, without the intermediate 24-float array."""
+        if self.E != 1:
+            raise ValueError("step_state is the single-environment path")
+        s, t, out, sp, tp, op = self._step_buffers()
+        env_state.pack_into(s)
+        t[0] = env_state.time
+        check(self.lib.covo_step(self._h, sp, tp, None, op))
+        return out[0].copy()
 
     def step_device(self, state24_ptr: int, time_ptr: int, eps_ptr: int, action_ptr: int, stream: int = 0):
         check(self.lib.covo_step_device(self._h, state24_ptr, time_ptr, eps_ptr or None, action_ptr, stream or None))

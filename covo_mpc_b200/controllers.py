@@ -203,8 +203,10 @@ class _SamplingController(BaseController):
     def _finish(self, control_params, action):
         self._generation += 1
         gen = self._generation
-        new = control_params.replace(a_mean=_DeviceArray(self, gen, "a_mean"), a_cov=_DeviceArray(self, gen, "a_cov"))
-        new._gen = gen
+        # control_params.replace(a_mean=..., a_cov=...) without re-running the dataclass constructor (per-step path)
+        new = object.__new__(type(control_params))
+        new.__dict__.update(control_params.__dict__)
+        new.a_mean, new.a_cov, new._gen = _DeviceArray(self, gen, "a_mean"), _DeviceArray(self, gen, "a_cov"), gen
         info = None
         if self.want_info:
             m, s = self._handle.pos_stats()
@@ -232,7 +234,7 @@ class MPPIController(_SamplingController):
         if self.want_info:
             h.enable_pos_stats(True)
         eps = self._eps(rng_act, (1, h.n_local, self.H * 4))
-        action = h.step(state.to_state24(), [state.time], eps)[0]
+        action = h.step_state(state) if eps is None else h.step(state.to_state24(), [state.time], eps)[0]
         return self._finish(control_params, action)
 
 
@@ -287,7 +289,7 @@ class CoVOController(_SamplingController):
         if self.want_info:
             h.enable_pos_stats(True)
         eps = self._eps(rng_act, (1, h.n_local, self.H * 4))
-        action = h.step(state.to_state24(), [state.time], eps)[0]
+        action = h.step_state(state) if eps is None else h.step(state.to_state24(), [state.time], eps)[0]
         return self._finish(control_params, action)
 
 

@@ -69,6 +69,17 @@ class EnvState3D:
     def replace(self, **kw):
         return replace(self, **kw)
 
+    def pack_into(self, o: np.ndarray) -> None:
+        """Write the C-ABI record into the first 24 floats of ``o`` (no allocation: the per-step call path)."""
+        o[0:3] = self.pos
+        o[3:7] = self.quat
+        o[7:10] = self.vel
+        o[10:13] = self.omega
+        o[13:16] = self.f_disturb
+        o[16:19] = self.pos_tar
+        o[19:22] = self.vel_tar
+        o[22:24] = 0.0
+
     def to_state24(self) -> np.ndarray:
         """Pack into the C-ABI record (include/covo_b200.h)."""
         o = np.zeros(24, F)

@@ -3,6 +3,7 @@ with g++ (tests/host_check), against the oracle: float path, hyper-dual first/se
 import ctypes
 
 import numpy as np
+import pytest
 
 from oracle import oracle_np as o
 from oracle.oracle_np import Jet
@@ -103,3 +104,79 @@ def test_result_artefacts_match_the_reference_formats(tmp_path):
     assert os.path.basename(p2) == "state_seq_.pkl"  # scripts/vis.py:71 loads exactly this name by default
     back = pickle.load(open(p2, "rb"))
     assert isinstance(back, list) and set(["pos", "quat", "pos_tar", "f_disturb", "pos_traj"]) <= set(back[0])
+
+
+def test_plugin_call_marshalling_fast_path():
+    """The per-step plugin call reuses staging buffers and cached pointers (no per-call allocations): with a recording stand-in
+    for the library, what covo_step receives through Handle.step_state / Handle.step(eps=None) must equal what the generic
+    path (fresh arrays per call) hands over, for float32 and float64 / list inputs alike, and the action must come back as a
+    fresh array every time."""
+    import ctypes as C
+
+    import covo_mpc_b200 as cm
+    from covo_mpc_b200 import _lib
+
+    calls = []
+
+    class RecordingLib:
+        def covo_step(self, h, sp, tp, ep, op):
+            s = np.ctypeslib.as_array(sp, shape=(24,)).copy()
+            t = int(tp[0])
+            calls.append((s, t, ep is None))
+            for k in range(4):
+                op[k] = 0.25 * (k + 1) + t
+            return 0
+
+        def __getattr__(self, name):
+            return lambda *a: 0
+
+    h = object.__new__(_lib.Handle)
+    h.lib, h._h, h.E, h.H, h.n, h.n_local = RecordingLib(), C.c_void_p(1), 1, 8, 32, 64
+    env = cm.Quad3D("tracking_zigzag")
+    _, info, st = env.reset(np.random.default_rng(3))
+    ns = info["noisy_state"].replace(time=17)
+    a1 = h.step_state(ns)
+    a2 = h.step(ns.to_state24(), [ns.time])[0]
+    a3 = h.step(ns.to_state24().astype(np.float64).tolist(), np.array([ns.time], np.int64))[0]
+    a4 = h.step(ns.to_state24(), [ns.time], eps=np.zeros((1, 64, 32), np.float32))[0]
+    ref = ns.to_state24()
+    assert len(calls) == 4
+    for s, t, no_eps in calls:
+        assert np.array_equal(s, ref) and t == 17
+    assert [c[2] for c in calls] == [True, True, True, False]
+    for a in (a1, a2, a3, a4):
+        assert a.dtype == np.float32 and np.allclose(a, [17.25, 17.5, 17.75, 18.0])
+    assert a1 is not a2 and not np.shares_memory(a1, a2)  # callers may keep actions: never a view of the staging buffer
+    with pytest.raises(ValueError):
+        h.step(np.zeros(23, np.float32), [0])
+    with pytest.raises(ValueError):
+        h.step(np.zeros(24, np.float32), [0, 1])
+    # the controller's functional params update without the dataclass constructor keeps every field
+    ctl, cp = cm.get_controller(env, "covo-online", "N64_H8_lam0.01")
+    ctl._handle, ctl._cfg.traj_len = h, ns.pos_traj.shape[0]
+    h.cfg = _lib.CovoConfig()
+    h.cfg.traj_len = ns.pos_traj.shape[0]
+    action, cp2, info2 = ctl(None, st, env.default_params, None, cp, {"noisy_state": ns})
+    assert np.allclose(action, [17.25, 17.5, 17.75, 18.0]) and info2 is None
+    assert type(cp2) is type(cp) and cp2 is not cp
+    assert (cp2.gamma_mean, cp2.gamma_sigma, cp2.discount, cp2.sample_sigma) == (cp.gamma_mean, cp.gamma_sigma, cp.discount, cp.sample_sigma)
+    assert cp2._gen == ctl._generation and np.array_equal(np.asarray(cp.a_mean), np.tile(np.array([cp.a_mean[0][0], 0, 0, 0], np.float32), (8, 1)))
+    cp3 = cp2.replace(a_mean=np.zeros((8, 4), np.float32))  # the reference-style replace still works on the returned object
+    assert cp3.a_mean.shape == (8, 4) and cp3.sample_sigma == cp.sample_sigma
+
+
+def test_fast_path_pointers_are_accepted_by_the_real_library():
+    """The cached ctypes pointers go through the real library's argtypes: with a NULL handle covo_step must come back with
+    its own 'null argument' status (no GPU involved), not a ctypes conversion error."""
+    import covo_mpc_b200 as cm
+    from covo_mpc_b200 import _lib
+
+    h = object.__new__(_lib.Handle)
+    h.lib, h._h, h.E, h.H, h.n, h.n_local = _lib.load(), None, 1, 8, 32, 64
+    env = cm.Quad3D("hovering")
+    _, info, st = env.reset(np.random.default_rng(0))
+    with pytest.raises(ValueError, match="null argument"):
+        h.step_state(info["noisy_state"])
+    with pytest.raises(ValueError, match="null argument"):
+        h.step(st.to_state24(), [0])
+    h._h = None  # keep __del__ from touching the library
