@@ -24,6 +24,16 @@ __host__ __device__ inline int lt_col_offset(int k, int n_pad) {
 }
 __host__ __device__ inline int lt_size(int n, int n_pad) { return lt_col_offset(n, n_pad); }
 
+// Dynamic shared memory, named barriers: spelled through macros so that tests/emu (a CPU stand-in for the CUDA execution model,
+// test infrastructure) can run kernel logic without a GPU.
+#if defined(COVO_CPU_EMU)
+#define COVO_DYN_SMEM(name) unsigned char* name = emu_dyn_smem()
+#define COVO_NAMED_BARRIER(id, count) emu_named_barrier(id, count)
+#else
+#define COVO_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define COVO_NAMED_BARRIER(id, count) asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(count) : "memory")
+#endif
+
 #define COVO_STAMP(args, slot)                                              \
     do {                                                                     \
         if ((args).prof && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) (args).prof[slot] = clock64(); \

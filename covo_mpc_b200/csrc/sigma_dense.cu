@@ -35,7 +35,11 @@ constexpr int TD = 1024;  // shifted_inverse_kernel threads
 
 __device__ __forceinline__ float rsqrt_newton_d(float x) {
     float r;
+#if defined(COVO_CPU_EMU)
+    r = 1.0f / sqrtf(x);
+#else
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+#endif
     return r * fmaf(-0.5f * x * r, r, 1.5f);
 }
 
@@ -106,7 +110,7 @@ struct DenseArgs {
 // D1
 // ---------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TL, 1) lanczos_kernel(const DenseArgs a) {
-    extern __shared__ __align__(16) unsigned char smraw[];
+    COVO_DYN_SMEM(smraw);
     const int n = a.n, tid = threadIdx.x, env = blockIdx.x, ld = n + 1;
     double* v = reinterpret_cast<double*>(smraw);  // [n]
     double* vp = v + n;                            // [n]
@@ -292,7 +296,7 @@ __device__ __forceinline__ void chol_factor_smem(float* As, float* Lp, int n, in
                 *reinterpret_cast<float4*>(As + i * n + r0) = make_float4(x[0], x[1], x[2], x[3]);
                 if (nbn == 8) *reinterpret_cast<float4*>(As + i * n + r0 + 4) = make_float4(x[4], x[5], x[6], x[7]);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            COVO_NAMED_BARRIER(1, 256);
             factor_panel(r0, nbn, LpNext);
         } else {
             const int c0 = r0 + nbn;
@@ -335,7 +339,7 @@ __device__ __forceinline__ void chol_factor_smem(float* As, float* Lp, int n, in
 }
 
 __global__ void __launch_bounds__(TD, 1) shifted_inverse_kernel(const DenseArgs a) {
-    extern __shared__ __align__(16) unsigned char smraw[];
+    COVO_DYN_SMEM(smraw);
     const int n = a.n, n_pad = a.n_pad, tid = threadIdx.x, pole = blockIdx.x, env = blockIdx.y, lane = tid & 31, warp = tid >> 5;
     float* As = reinterpret_cast<float*>(smraw);  // [n][n]
     float* Lp = As + n * n;                       // Cholesky panel buffers
@@ -447,6 +451,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const DenseArgs a) {
 // ---------------------------------------------------------------------------------------------------------------------------
 size_t sigma_dense_scratch_floats(int n) { return (size_t)kZoloPoles * n * n; }
 
+#if !defined(COVO_CPU_EMU)
 cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, int n_env, cudaStream_t st) {
     if (s.n > kSigmaMaxN || (s.n & 3)) return cudaErrorInvalidValue;
     DenseArgs a;
@@ -476,5 +481,7 @@ cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, in
     combine_kernel<<<dim3((npairs + 255) / 256, n_env), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
+
+#endif
 
 }  // namespace covo

@@ -1,0 +1,61 @@
+"""csrc/sigma_dense.cu (experimental, COVO_SIGMA=dense) executed on the CPU stand-in for the CUDA execution model
+(tests/emu/cuda_runtime.h: every CUDA thread a cooperative fiber; barriers, named barriers, shuffles and ballots block until
+the peers arrive; shared memory poisoned; a barrier that can never complete aborts) against the float64 eigen-decomposition
+of the oracle.  Checks the kernels' LOGIC -- indexing, hand-overs through shared memory, barrier placement -- with the launch
+geometry and shared-memory layout of launch_sigma_dense; it says nothing about timing or the GPU memory model."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as o
+from tests.util import scenario
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+
+
+def _emu_lib():
+    so = os.path.join(EMU, "libemu_sigma_dense.so")
+    srcs = [os.path.join(EMU, "run_sigma_dense.cpp"), os.path.join(EMU, "cuda_runtime.h"),
+            os.path.join(ROOT, "covo_mpc_b200", "csrc", "sigma_dense.cu"), os.path.join(ROOT, "covo_mpc_b200", "csrc", "common.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-DCOVO_CPU_EMU", "-I" + EMU, "-I" + os.path.join(ROOT, "include"), "-shared", "-fPIC",
+                               "-o", so, srcs[0]])
+    return C.CDLL(so)
+
+
+def _zolo_table():
+    from covo_mpc_b200 import _lib
+
+    lib = _lib.load()  # the ladder of sigma.cu, through the C-ABI's host-side helper (no GPU involved)
+    lib.covo_zolotarev_nodes.argtypes = [C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    m = 1e-2 * (1 - 1e-7)
+    tab = np.zeros((10, 2, 16))
+    for i in range(10):
+        sh, w = np.zeros(16), np.zeros(16)
+        assert lib.covo_zolotarev_nodes(m, m * 4.0 ** (4 + i), 16, sh.ctypes.data_as(C.POINTER(C.c_double)), w.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        tab[i, 0], tab[i, 1] = sh, w
+    return tab
+
+
+@pytest.mark.parametrize("H", [8, 9])  # n = 32 and n = 36 (last Cholesky panel 4 wide, n_pad = 40)
+def test_dense_sigma_kernels_on_the_cpu_execution_model(H):
+    emu = _emu_lib()
+    p, ns, a_mean, rng = scenario("tracking_zigzag", seed=3, H=H, warm_steps=6)
+    R = o.get_hessian(ns, o.shift_mean(a_mean), p, dtype=np.float64).astype(np.float32)
+    n = 4 * H
+    S_ref = o.optimize_sigma(R.astype(np.float64), 0.5, np.float64)
+    lam = np.linalg.eigvalsh(0.5 * (R + R.T).astype(np.float64))
+    cov = np.full((n, n), np.nan, np.float32)
+    scal, status, tab = np.zeros(4), np.zeros(1, np.int32), _zolo_table()
+    rc = emu.emu_sigma_dense(n, C.c_float(0.5), R.ctypes.data_as(C.POINTER(C.c_float)), tab.ctypes.data_as(C.POINTER(C.c_double)),
+                             cov.ctypes.data_as(C.POINTER(C.c_float)), scal.ctypes.data_as(C.POINTER(C.c_double)),
+                             status.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == 0 and status[0] == 0
+    assert abs(scal[0] - lam[0]) < 1e-12 and abs(scal[1] - lam[-1]) < 1e-12  # Lanczos + multisection, fp64
+    assert abs(scal[2] - np.log(lam - lam[0] + 1e-2).sum()) < 1e-4          # log det from the fp32 factorisation
+    assert np.isfinite(cov).all() and np.array_equal(cov, cov.T)
+    assert np.linalg.norm(cov - S_ref) / np.linalg.norm(S_ref) < 2e-6
