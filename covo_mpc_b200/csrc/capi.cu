@@ -105,7 +105,7 @@ struct covo_handle {
     int num_sms = 0;
     bool pipeline_enabled = true;
     bool pipeline_forced = false;
-    bool sigma_dense = false;  // COVO_SIGMA=dense: experimental tridiagonalisation-free optimize_sigma (sigma_dense.cu)
+    int sigma_dense = 0;  // COVO_SIGMA=dense (1) / dense-gj (2): experimental tridiagonalisation-free optimize_sigma (sigma_dense.cu)
     DevBuf<double> dense_scal;
     DevBuf<float> dense_X;  // COVO_PIPELINE=2 (development): keep the pipeline on while per-kernel timings are taken
     unsigned int rng_stream = 0;
@@ -301,7 +301,7 @@ int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = fals
     SigmaArgs sa = sigma_args(h);
     if (!want_L) sa.L = nullptr;  // the sampler only needs the packed factor
     if (h->sigma_dense) {  // experimental: Lanczos + 17 shifted factorisations + combine instead of E1-E3
-        CK(launch_sigma_dense(sa, h->dense_scal.p, h->dense_X.p, h->E, st));
+        CK(launch_sigma_dense(sa, h->dense_scal.p, h->dense_X.p, h->E, st, h->sigma_dense));
         if (pf) {
             pf->mark(2);
             pf->mark(3);
@@ -470,7 +470,7 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
         h->pipeline_enabled = !(pe && pe[0] == '0');
         h->pipeline_forced = pe && pe[0] == '2';
         const char* se = getenv("COVO_SIGMA");
-        h->sigma_dense = se && strcmp(se, "dense") == 0 && cfg->mode != COVO_MODE_MPPI;
+        h->sigma_dense = (se && cfg->mode != COVO_MODE_MPPI) ? (strcmp(se, "dense") == 0 ? 1 : strcmp(se, "dense-gj") == 0 ? 2 : 0) : 0;
         if (h->sigma_dense) {
             A(h->dense_scal.alloc(E * 4));
             A(h->dense_X.alloc(E * sigma_dense_scratch_floats(h->n)));

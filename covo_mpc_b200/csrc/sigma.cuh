@@ -48,6 +48,7 @@ cudaError_t launch_cholesky(const SigmaArgs& a, int n_env, cudaStream_t st);  //
 // EXPERIMENTAL dense path (sigma_dense.cu; COVO_SIGMA=dense): optimize_sigma without tridiagonalisation.  Writes a.cov (symmetric).
 // scal: [n_env][4] doubles, Xbuf: [n_env][sigma_dense_scratch_floats(n)] floats.
 size_t sigma_dense_scratch_floats(int n);
-cudaError_t launch_sigma_dense(const SigmaArgs& a, double* scal, float* Xbuf, int n_env, cudaStream_t st);
+// variant 1: Cholesky + triangular inverse + X^T X per pole (shared memory); variant 2: register-resident Gauss-Jordan per pole
+cudaError_t launch_sigma_dense(const SigmaArgs& a, double* scal, float* Xbuf, int n_env, cudaStream_t st, int variant);
 
 }  // namespace covo

@@ -423,6 +423,147 @@ __global__ void __launch_bounds__(TD, 1) shifted_inverse_kernel(const DenseArgs 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// D2' (alternative to D2, COVO_SIGMA=dense-gj): w_j (A + t_j I)^-1 by in-place Gauss-Jordan elimination without pivoting (A + t_j I
+// is SPD: every pivot is a positive Schur complement), the matrix RESIDENT IN REGISTERS.  512 threads as a 16 x 32 grid; thread
+// (ty, tx) owns the elements (ty + 16 a, tx + 32 b), a < RI, b < 7, rows packed in pairs for FFMA2.  Step k:
+//     p = a_kk;  a_ij -= a_ik a_kj / p  (i, j != k);  row k <- r / p;  column k <- -c / p;  a_kk <- 1 / p.
+// With this sign convention the matrix stays symmetric on the not yet eliminated index set and ANTI-symmetric between eliminated
+// and remaining indices (a_im = -a_mi for m < k <= i), so column k is row k with the sign of (i < k): only the ROW is published
+// (by the one warp that owns it; double-buffered, one barrier per step), never the column.  The loop over k is unrolled over the
+// 16-row blocks, so every register-tile index is a compile-time constant and the row / column fix-ups touch 7 and 14 registers
+// instead of the whole tile.  log det A = sum log p_k comes for free (the CTA without a pole).  n^3 FMA per matrix instead of the
+// three n^3 / 3 sweeps of D2, but no serial panel chain.  Numerics (CPU study, fp32): Sigma to 1e-6 on the tracking / zigzag path.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int TG = 512;
+
+template <int RI>
+__global__ void __launch_bounds__(TG, 1) gj_inverse_kernel(const DenseArgs a) {
+    COVO_DYN_SMEM(smraw);
+    constexpr int CJ = 7, RP = (RI + 1) / 2;
+    const int n = a.n, tid = threadIdx.x, pole = blockIdx.x, env = blockIdx.y, tx = tid & 31, ty = tid >> 5;
+    float* rbuf = reinterpret_cast<float*>(smraw);  // [2][512]: row k and the column multipliers, double-buffered
+    const double lam_min = a.scal[(long long)env * 4 + 0], lam_max = a.scal[(long long)env * 4 + 1];
+    int lad = 0;
+    {
+        const double Mb = 1.02 * (lam_max - lam_min) + kOffset;
+        double Mi = kOffset * (1.0 - 1e-7) * 256.0;
+        while (lad < kZoloLadder - 1 && Mi < Mb) {
+            Mi *= 4.0;
+            ++lad;
+        }
+        if (Mi < Mb && tid == 0) a.status[env] = 1;
+    }
+    const double* zt = a.zolo + (size_t)lad * 2 * kZoloPoles;
+    const bool want_logdet = pole == kZoloPoles;
+    const double shift = (kOffset - lam_min) + (want_logdet ? 0.0 : zt[pole]);
+    const float wj = want_logdet ? 0.f : (float)zt[kZoloPoles + pole];
+    const float* Rg = a.R + (long long)env * n * n;
+    // tile load: (R + R^T)/2 + shift I; elements outside the matrix form an identity block (never a pivot, no coupling)
+    float2 acc[RP][CJ];  // [row pair][col]: .x = tile row 2q, .y = tile row 2q + 1
+#pragma unroll
+    for (int q = 0; q < RP; ++q)
+#pragma unroll
+        for (int b = 0; b < CJ; ++b) {
+            float v2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = ty + 16 * (2 * q + h), j = tx + 32 * b;
+                float v = (i == j) ? 1.f : 0.f;
+                if (i < n && j < n) {
+                    v = 0.5f * (Rg[(long long)i * n + j] + Rg[(long long)j * n + i]);
+                    if (i == j) v = (float)((double)v + shift);
+                }
+                v2[h] = v;
+            }
+            acc[q][b] = make_float2(v2[0], v2[1]);
+        }
+    float my_pivot = 1.f;  // thread k keeps pivot k: the logarithms are taken once, after the elimination
+    bool bad = false;
+#pragma unroll
+    for (int ak = 0; ak < 2 * RP; ++ak) {  // 16-row block of the pivot: tile row ak, tile column ak / 2 -- compile-time
+        const int qk = ak >> 1, bk = ak >> 1;  // pivot row lives in acc[qk][.].(ak & 1 ? y : x); pivot column is tile column bk
+        if (16 * ak < n) {
+            for (int kk = 0; kk < 16; ++kk) {
+                const int k = 16 * ak + kk;
+                if (k >= n) break;
+                float* rb = rbuf + (k & 1) * 512;  // [256] row k, then [256] the column multipliers -a_ik / p
+                float* cb = rb + 256;
+                float piv = 0.f;
+                if (ty == kk) {
+                    // The warp that owns row k publishes it, and with it the multipliers of the column: by (anti)symmetry
+                    // a_ik = (i < k ? -1 : 1) a_ki, so -a_ik / p is the row again, signed and scaled -- the other 15 warps
+                    // never see the column, only these two vectors.
+                    const float own = (ak & 1) ? acc[qk][bk].y : acc[qk][bk].x;  // lane k mod 32 holds the pivot
+                    const float p = __shfl_sync(0xffffffffu, own, k & 31);
+                    if (!(p > 0.f)) bad = true;
+                    piv = 1.0f / p;
+#pragma unroll
+                    for (int b = 0; b < CJ; ++b) {
+                        const int j = tx + 32 * b;
+                        const float r = (ak & 1) ? acc[qk][b].y : acc[qk][b].x;
+                        rb[j] = r;
+                        cb[j] = (j < k ? r : -r) * piv;
+                    }
+                }
+                __syncthreads();
+                if (tid == k) my_pivot = rb[k];
+                float rk[CJ];
+#pragma unroll
+                for (int b = 0; b < CJ; ++b) rk[b] = rb[tx + 32 * b];
+                float2 cn[RP];
+#pragma unroll
+                for (int q = 0; q < RP; ++q) cn[q] = make_float2(cb[ty + 32 * q], cb[ty + 32 * q + 16]);
+#pragma unroll
+                for (int q = 0; q < RP; ++q)
+#pragma unroll
+                    for (int b = 0; b < CJ; ++b) acc[q][b] = __ffma2_rn(cn[q], make_float2(rk[b], rk[b]), acc[q][b]);
+                if (tx == (k & 31)) {  // column k (tile column bk): -a_ik / p
+#pragma unroll
+                    for (int q = 0; q < RP; ++q) acc[q][bk] = cn[q];
+                }
+                if (ty == kk) {  // row k: a_kj / p, pivot 1 / p
+#pragma unroll
+                    for (int b = 0; b < CJ; ++b) {
+                        const float v = (tx + 32 * b == k) ? piv : rk[b] * piv;
+                        if (ak & 1) acc[qk][b].y = v;
+                        else acc[qk][b].x = v;
+                    }
+                }
+                // no second barrier: step k + 1 publishes into the other buffer, and step k + 2 writes this one only after the
+                // barrier of step k + 1, which every thread reaches after it has finished reading here
+            }
+        }
+    }
+    if (bad && tid == 0) a.status[env] = 2;
+    if (want_logdet) {  // log det A = sum_k log p_k  (n <= TG: one pivot per thread)
+        double lp = (tid < n) ? log((double)my_pivot) : 0.0;
+        lp = warp_sum_d(lp);
+        double* red = reinterpret_cast<double*>(rbuf);
+        __syncthreads();  // the row buffers are no longer read
+        if (tx == 0) red[ty] = lp;
+        __syncthreads();
+        if (tid == 0) {
+            double sum = 0.0;
+            for (int w = 0; w < TG / 32; ++w) sum += red[w];
+            a.scal[(long long)env * 4 + 2] = sum;
+        }
+        return;
+    }
+    float* Xg = a.Xbuf + ((long long)env * kZoloPoles + pole) * n * n;
+#pragma unroll
+    for (int q = 0; q < RP; ++q)
+#pragma unroll
+        for (int b = 0; b < CJ; ++b) {
+            const int j = tx + 32 * b;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = ty + 16 * (2 * q + h);
+                if (i < n && j <= i) Xg[i * n + j] = wj * (h ? acc[q][b].y : acc[q][b].x);  // lower triangle, as D2
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // D3
 // ---------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) combine_kernel(const DenseArgs a) {
@@ -452,7 +593,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const DenseArgs a) {
 size_t sigma_dense_scratch_floats(int n) { return (size_t)kZoloPoles * n * n; }
 
 #if !defined(COVO_CPU_EMU)
-cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, int n_env, cudaStream_t st) {
+cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, int n_env, cudaStream_t st, int variant) {
     if (s.n > kSigmaMaxN || (s.n & 3)) return cudaErrorInvalidValue;
     DenseArgs a;
     a.n = s.n;
@@ -471,12 +612,18 @@ cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, in
     lanczos_kernel<<<n_env, TL, smem1, st>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const size_t smem2 = ((size_t)a.n * a.n + 2 * 8 * a.n_pad + 64 + a.n_pad) * sizeof(float) + 16;
-    e = ensure_smem_attr(shifted_inverse_kernel, smem2, conf2);
-    if (e != cudaSuccess) return e;
-    shifted_inverse_kernel<<<dim3(kZoloPoles + 1, n_env), TD, smem2, st>>>(a);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    if (variant == 2) {  // register-resident Gauss-Jordan
+        gj_inverse_kernel<14><<<dim3(kZoloPoles + 1, n_env), TG, 1024 * sizeof(float), st>>>(a);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    } else {
+        const size_t smem2 = ((size_t)a.n * a.n + 2 * 8 * a.n_pad + 64 + a.n_pad) * sizeof(float) + 16;
+        e = ensure_smem_attr(shifted_inverse_kernel, smem2, conf2);
+        if (e != cudaSuccess) return e;
+        shifted_inverse_kernel<<<dim3(kZoloPoles + 1, n_env), TD, smem2, st>>>(a);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     const int npairs = a.n * (a.n + 1) / 2;
     combine_kernel<<<dim3((npairs + 255) / 256, n_env), 256, 0, st>>>(a);
     return cudaGetLastError();

@@ -198,6 +198,22 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
     return out;
 }
 
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "emu shuffle: 4- or 8-byte types");
+    emu::Block* b = emu::cur();
+    const int t = emu::tid_linear();
+    unsigned long long raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    b->slot[t] = raw;
+    __syncwarp();
+    raw = b->slot[(t & ~31) | (src_lane & 31)];
+    __syncwarp();
+    T out;
+    memcpy(&out, &raw, sizeof(T));
+    return out;
+}
+
 inline unsigned __ballot_sync(unsigned, bool p) {
     emu::Block* b = emu::cur();
     const int t = emu::tid_linear();

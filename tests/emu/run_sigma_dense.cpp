@@ -2,7 +2,7 @@
 // (g++ -DCOVO_CPU_EMU -Itests/emu) -- one environment, the same launch geometry and shared-memory sizes as launch_sigma_dense.
 #include "../../covo_mpc_b200/csrc/sigma_dense.cu"
 
-extern "C" int emu_sigma_dense(int n, float sample_sigma, const float* R, const double* zolo, float* cov, double* scal4, int* status) {
+extern "C" int emu_sigma_dense(int n, float sample_sigma, const float* R, const double* zolo, float* cov, double* scal4, int* status, int variant) {
     using namespace covo;
     if (n > kSigmaMaxN || (n & 3)) return 1;
     std::vector<float> xbuf((size_t)kZoloPoles * n * n, std::nanf(""));  // NaN: an entry read before it was written poisons the result
@@ -18,8 +18,12 @@ extern "C" int emu_sigma_dense(int n, float sample_sigma, const float* R, const 
     a.status = status;
     const size_t smem1 = (size_t)(2 * n + 8 + 2 * kLanczosMax) * sizeof(double) + (size_t)n * (n + 1) * sizeof(float);
     emu_launch(lanczos_kernel, dim3(1), TL, smem1, a);
-    const size_t smem2 = ((size_t)n * n + 2 * 8 * a.n_pad + 64 + a.n_pad) * sizeof(float) + 16;
-    emu_launch(shifted_inverse_kernel, dim3(kZoloPoles + 1, 1), TD, smem2, a);
+    if (variant == 2) {
+        emu_launch(gj_inverse_kernel<14>, dim3(kZoloPoles + 1, 1), TG, 1024 * sizeof(float), a);
+    } else {
+        const size_t smem2 = ((size_t)n * n + 2 * 8 * a.n_pad + 64 + a.n_pad) * sizeof(float) + 16;
+        emu_launch(shifted_inverse_kernel, dim3(kZoloPoles + 1, 1), TD, smem2, a);
+    }
     const int npairs = n * (n + 1) / 2;
     emu_launch(combine_kernel, dim3((npairs + 255) / 256, 1), 256, 0, a);
     return 0;

@@ -159,12 +159,13 @@ def test_maximum_horizon_full_step():
 @pytest.mark.skipif(__import__("os").environ.get("COVO_TEST_DENSE") != "1",
                     reason="experimental dense optimize_sigma (csrc/sigma_dense.cu): written after the round-1 GPU budget was spent, "
                            "not yet run on hardware; enable with COVO_TEST_DENSE=1")
+@pytest.mark.parametrize("variant", ["dense", "dense-gj"])
 @pytest.mark.parametrize("H", [8, 20, 50])
-def test_dense_sigma_path_matches_oracle(monkeypatch, H):
+def test_dense_sigma_path_matches_oracle(monkeypatch, H, variant):
     """COVO_SIGMA=dense: Lanczos + shifted factorisations + combine vs the float64 eigen-decomposition."""
     from covo_mpc_b200 import _lib
 
-    monkeypatch.setenv("COVO_SIGMA", "dense")
+    monkeypatch.setenv("COVO_SIGMA", variant)
     p, ns, a_mean, rng = scenario("tracking_zigzag", seed=3, H=H, warm_steps=6)
     R = o.get_hessian(ns, o.shift_mean(a_mean), p, dtype=np.float64).astype(np.float32)
     S_ref = o.optimize_sigma(R.astype(np.float64), 0.5, np.float64)

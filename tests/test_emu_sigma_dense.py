@@ -27,6 +27,21 @@ def _emu_lib():
     return C.CDLL(so)
 
 
+def test_gauss_jordan_variant_at_the_headline_size():
+    """n = 200 (H = 50): every register tile of gj_inverse_kernel is in use, 13 of its 14 row blocks are pivoted."""
+    emu = _emu_lib()
+    p, ns, a_mean, rng = scenario("tracking_zigzag", seed=3, H=50, warm_steps=6)
+    R = o.get_hessian(ns, o.shift_mean(a_mean), p, dtype=np.float64).astype(np.float32)
+    S_ref = o.optimize_sigma(R.astype(np.float64), 0.5, np.float64)
+    cov = np.full((200, 200), np.nan, np.float32)
+    scal, status, tab = np.zeros(4), np.zeros(1, np.int32), _zolo_table()
+    rc = emu.emu_sigma_dense(200, C.c_float(0.5), R.ctypes.data_as(C.POINTER(C.c_float)), tab.ctypes.data_as(C.POINTER(C.c_double)),
+                             cov.ctypes.data_as(C.POINTER(C.c_float)), scal.ctypes.data_as(C.POINTER(C.c_double)),
+                             status.ctypes.data_as(C.POINTER(C.c_int)), 2)
+    assert rc == 0 and status[0] == 0 and np.isfinite(cov).all()
+    assert np.linalg.norm(cov - S_ref) / np.linalg.norm(S_ref) < 5e-6
+
+
 def _zolo_table():
     from covo_mpc_b200 import _lib
 
@@ -41,8 +56,9 @@ def _zolo_table():
     return tab
 
 
+@pytest.mark.parametrize("variant", [1, 2], ids=["cholesky-inverse", "gauss-jordan"])
 @pytest.mark.parametrize("H", [8, 9])  # n = 32 and n = 36 (last Cholesky panel 4 wide, n_pad = 40)
-def test_dense_sigma_kernels_on_the_cpu_execution_model(H):
+def test_dense_sigma_kernels_on_the_cpu_execution_model(H, variant):
     emu = _emu_lib()
     p, ns, a_mean, rng = scenario("tracking_zigzag", seed=3, H=H, warm_steps=6)
     R = o.get_hessian(ns, o.shift_mean(a_mean), p, dtype=np.float64).astype(np.float32)
@@ -53,7 +69,7 @@ def test_dense_sigma_kernels_on_the_cpu_execution_model(H):
     scal, status, tab = np.zeros(4), np.zeros(1, np.int32), _zolo_table()
     rc = emu.emu_sigma_dense(n, C.c_float(0.5), R.ctypes.data_as(C.POINTER(C.c_float)), tab.ctypes.data_as(C.POINTER(C.c_double)),
                              cov.ctypes.data_as(C.POINTER(C.c_float)), scal.ctypes.data_as(C.POINTER(C.c_double)),
-                             status.ctypes.data_as(C.POINTER(C.c_int)))
+                             status.ctypes.data_as(C.POINTER(C.c_int)), variant)
     assert rc == 0 and status[0] == 0
     assert abs(scal[0] - lam[0]) < 1e-12 and abs(scal[1] - lam[-1]) < 1e-12  # Lanczos + multisection, fp64
     assert abs(scal[2] - np.log(lam - lam[0] + 1e-2).sum()) < 1e-4          # log det from the fp32 factorisation
