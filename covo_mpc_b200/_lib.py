@@ -59,6 +59,7 @@ _SIGNATURES = {
     "covo_get_cov_offline": [_H, _F, C.c_int],
     "covo_reset_offline": [_H, _F, _I, C.c_int],
     "covo_step": [_H, _F, _I, _F, _F],
+    "covo_set_env_params": [_H, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _F, C.c_int],
     "covo_step_device": [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "covo_step_partial_device": [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "covo_partial_buffer": [_H, C.POINTER(C.c_void_p), _I],
@@ -281,6 +282,10 @@ class Handle:
         t[0] = env_state.time
         check(self.lib.covo_step(self._h, sp, tp, None, op))
         return out[0].copy()
+
+    def set_env_params(self, m, g, max_thrust, dt, alpha_bodyrate, action_scale, max_omega, max_steps_in_episode):
+        mo = f32(max_omega)
+        check(self.lib.covo_set_env_params(self._h, m, g, max_thrust, dt, alpha_bodyrate, action_scale, fptr(mo), int(max_steps_in_episode)))
 
     def step_device(self, state24_ptr: int, time_ptr: int, eps_ptr: int, action_ptr: int, stream: int = 0):
         check(self.lib.covo_step_device(self._h, state24_ptr, time_ptr, eps_ptr or None, action_ptr, stream or None))

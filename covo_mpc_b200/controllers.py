@@ -143,18 +143,47 @@ class _SamplingController(BaseController):
         self._handle: Optional[_lib.Handle] = None
         self._traj_id = None
         self._generation = 0
+        self._env_params_seen = None
         self.want_info = False  # pos_mean / pos_std (covo.py:281) are computed only on request
 
     # -- plumbing ---------------------------------------------------------------------------------------
     def _ensure_handle(self, traj_len: int) -> _lib.Handle:
         if self._handle is None or self._cfg.traj_len != traj_len:
+            carried = None
             if self._handle is not None:
+                # a reference trajectory of another length: the resident controller state moves to the new handle, so that
+                # the params object returned by the last call stays valid (its _gen still matches)
+                carried = (self._handle.get_mean(), self._handle.get_cov() if self._mode == _lib.MODE_MPPI else None)
                 self._handle.close()
             self._cfg.traj_len = traj_len
             self._handle = _lib.Handle(self._cfg)
             self._traj_id = None
+            self._env_params_seen = None
+            if carried is not None:
+                self._handle.set_mean(carried[0])
+                if carried[1] is not None:
+                    self._handle.set_cov(carried[1])
             self._on_new_handle()
         return self._handle
+
+    _MODEL_FIELDS = ("m", "g", "max_thrust", "dt", "alpha_bodyrate", "action_scale", "max_omega", "max_steps_in_episode")
+
+    def _sync_env_params(self, env_params):
+        """The reference plans with the env_params of the CALL (controllers/covo.py:187-283, mppi.py:28-134), e.g. a mass drawn by
+        sample_params: forward the model constants to the handle whenever the caller passes a different params object."""
+        if env_params is None or env_params is self._env_params_seen:
+            return
+        self._env_params_seen = env_params
+        vals = tuple(getattr(env_params, f, getattr(self.env.default_params, f)) for f in self._MODEL_FIELDS)
+        key = tuple(tuple(float(x) for x in v) if isinstance(v, (tuple, list, np.ndarray)) else float(v) for v in vals)
+        if key != getattr(self, "_model_key", None):
+            m, g, mt, dt, al, sc, mo, ms = vals
+            self._handle.set_env_params(float(m), float(g), float(mt), float(dt), float(al), float(sc), mo, int(ms))
+            self._cfg.m, self._cfg.g, self._cfg.max_thrust, self._cfg.dt = float(m), float(g), float(mt), float(dt)
+            self._cfg.alpha_bodyrate, self._cfg.action_scale, self._cfg.max_steps_in_episode = float(al), float(sc), int(ms)
+            for k in range(3):
+                self._cfg.max_omega[k] = float(mo[k])
+            self._model_key = key
 
     def _on_new_handle(self):
         pass
@@ -230,6 +259,7 @@ class MPPIController(_SamplingController):
     def __call__(self, obs, env_state, env_params, rng_act, control_params, info=None):
         state: EnvState3D = info["noisy_state"]  # mppi.py:40
         h = self._sync_reference(state)
+        self._sync_env_params(env_params)
         self._upload_params(control_params)
         if self.want_info:
             h.enable_pos_stats(True)
@@ -263,12 +293,16 @@ class CoVOController(_SamplingController):
         if getattr(self.env, "disturb_type", "none") != "none":
             raise NotImplementedError("covo-offline schedule: only disturb_type='none' is implemented")
         h = self._sync_reference(env_state)
+        self._sync_env_params(env_params)
         T = int(self.env.default_params.max_steps_in_episode)
         h.reset_offline(env_state.to_state24(), [env_state.time], T)
         self._table = None
-        self._generation += 1
+        # The reference keeps a_mean / a_cov across this reset (covo.py:101-104 replaces a_cov_offline only) and render_env calls it
+        # with the CURRENT params after `done` (envs/quadrotor.py:637-639): the resident mean is untouched by the schedule build, so
+        # the returned object stays in the generation of the one passed in.
         cp = control_params if control_params is not None else self.init_control_params
         new = cp.replace(a_cov_offline=_OfflineTable(self, T))
+        new._gen = getattr(cp, "_gen", -1)
         return new
 
     def _upload_cov(self, control_params):
@@ -285,6 +319,7 @@ class CoVOController(_SamplingController):
     def __call__(self, obs, env_state, env_params, rng_act, control_params, info=None):
         state: EnvState3D = info["noisy_state"]  # covo.py:198
         h = self._sync_reference(state)
+        self._sync_env_params(env_params)
         self._upload_params(control_params)
         if self.want_info:
             h.enable_pos_stats(True)
@@ -412,7 +447,7 @@ def get_controller(env, controller_name: str, controller_params: Optional[str] =
         N, H, lam, sigma = parse_sample_params(controller_params)
         if debug:
             N, H = 4, 2
-        mode = "offline" if "offline" in controller_name else "online"
+        mode = "online" if "online" in controller_name else ("offline" if "offline" in controller_name else "online")  # :731-737
         control_params = CoVOParams(gamma_mean=1.0, gamma_sigma=0.0, discount=1.0, sample_sigma=sigma,
                                     a_mean=get_sample_mean(H), a_cov=np.diag(np.full(H * 4, sigma ** 2, np.float32)),
                                     a_cov_offline=np.zeros((H, 4, 4), np.float32))

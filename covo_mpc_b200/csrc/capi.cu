@@ -134,13 +134,14 @@ struct covo_handle {
     DevBuf<long long> prof;
     bool phase_clocks = false;
     // device-resident environment (caller side of the hot path)
-    DevBuf<float> env_state24, env_noisy24, env_noise, env_log_f, env_action;
+    DevBuf<float> env_state24, env_noisy24, env_noise, env_log_f, env_action, pid_integral;
     DevBuf<int> env_time, env_noisy_time, env_done;
     bool env_ready = false;
     // pinned staging
     float* h_state = nullptr;
     int* h_time = nullptr;
     float* h_action = nullptr;
+    int* h_status = nullptr;
 };
 
 
@@ -168,6 +169,7 @@ void release_all(covo_handle* h) {
     if (h->h_state) cudaFreeHost(h->h_state);
     if (h->h_time) cudaFreeHost(h->h_time);
     if (h->h_action) cudaFreeHost(h->h_action);
+    if (h->h_status) cudaFreeHost(h->h_status);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -177,6 +179,7 @@ void release_all(covo_handle* h) {
     h->chol_progress.release();
     h->dense_scal.release();
     h->dense_X.release();
+    h->pid_integral.release();
 }
 
 HessianArgs hess_args(covo_handle* h, const float* st, const int* tm, const float* a_mean, int shift, float* R, float* ws,
@@ -194,6 +197,7 @@ HessianArgs hess_args(covo_handle* h, const float* st, const int* tm, const floa
     a.a_mean = a_mean;
     a.workspace = ws;
     a.R = R;
+    a.status = (R == h->R.p) ? h->status.p : nullptr;  // the offline schedule keeps its own status array
     a.prof = h->phase_clocks ? h->prof.p : nullptr;
     return a;
 }
@@ -514,6 +518,7 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
     A(cudaMallocHost(&h->h_state, E * kStateFloats * sizeof(float)));
     A(cudaMallocHost(&h->h_time, E * sizeof(int)));
     A(cudaMallocHost(&h->h_action, E * 4 * sizeof(float)));
+    A(cudaMallocHost(&h->h_status, E * sizeof(int)));
     if (e != cudaSuccess) {
         release_all(h);
         delete h;
@@ -539,6 +544,12 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
             h2d(h, h->cov.p, C.data(), C.size() * sizeof(float));
             h->have_factor = true;
         }
+        ce = cudaStreamSynchronize(h->own_stream);  // initial uploads complete before any caller-stream launch
+        if (ce != cudaSuccess) {
+            release_all(h);
+            delete h;
+            return fail(COVO_ERR_CUDA, "initial upload failed: %s", cudaGetErrorString(ce));
+        }
     }
     *out = h;
     return COVO_OK;
@@ -561,6 +572,8 @@ int covo_set_reference(covo_handle* h, const float* pos, const float* vel, const
     CK(h2d(h, h->vel_traj.p, vel, bytes));
     if (acc) CK(h2d(h, h->acc_traj.p, acc, bytes));
     else CK(dzero(h, h->acc_traj.p, bytes));
+    // the step entry points may run on a caller stream: uploads on the handle's own stream are complete on return
+    CK(cudaStreamSynchronize(h->own_stream));
     return COVO_OK;
 }
 
@@ -569,6 +582,7 @@ int covo_set_mean(covo_handle* h, const float* a_mean) {
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->own_stream));
     CK(h2d(h, h->a_mean.p, a_mean, (size_t)h->E * h->n * sizeof(float)));
+    CK(cudaStreamSynchronize(h->own_stream));
     return COVO_OK;
 }
 int covo_get_mean(covo_handle* h, float* a_mean) {
@@ -604,6 +618,7 @@ int covo_set_cov(covo_handle* h, const float* a_cov) {
         }
         CK(h2d(h, h->Lblk.p, L.data(), cnt * sizeof(float)));
         CK(h2d(h, h->cov.p, a_cov, cnt * sizeof(float)));
+        CK(cudaStreamSynchronize(h->own_stream));
     } else {
         CK(h2d(h, h->cov.p, a_cov, (size_t)h->E * h->n * h->n * sizeof(float)));
         CK(dzero(h, h->status.p, h->E * sizeof(int)));
@@ -703,10 +718,12 @@ int covo_pid_action(covo_handle* h, const float* state24, const int* time, float
     cudaStream_t st = h->own_stream;
     CK(cudaMemcpyAsync(h->state24.p, state24, (size_t)h->E * kStateFloats * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->time.p, time, (size_t)h->E * sizeof(int), cudaMemcpyHostToDevice, st));
-    DevBuf<float> integ;
     if (integral) {
-        CK(integ.alloc((size_t)h->E * 3));
-        CK(cudaMemcpyAsync(integ.p, integral, (size_t)h->E * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (h->pid_integral.n < (size_t)h->E * 3) {
+            h->pid_integral.release();
+            CK(h->pid_integral.alloc((size_t)h->E * 3));
+        }
+        CK(cudaMemcpyAsync(h->pid_integral.p, integral, (size_t)h->E * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
     }
     PidArgs pa;
     pa.n_env = h->E;
@@ -720,12 +737,11 @@ int covo_pid_action(covo_handle* h, const float* state24, const int* time, float
     pa.state24 = h->state24.p;
     pa.time = h->time.p;
     pa.acc_traj = h->acc_traj.p;
-    pa.integral = integral ? integ.p : nullptr;
+    pa.integral = integral ? h->pid_integral.p : nullptr;
     pa.action = h->action.p;
     cudaError_t e = launch_pid(pa, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(action, h->action.p, (size_t)h->E * 4 * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    integ.release();
     if (e != cudaSuccess) return fail(COVO_ERR_CUDA, "pid_action: %s", cudaGetErrorString(e));
     return COVO_OK;
 }
@@ -825,6 +841,7 @@ int covo_env_reset(covo_handle* h, const float* state24, const int* time) {
     if (int rc = env_alloc(h)) return rc;
     CK(h2d(h, h->env_state24.p, state24, (size_t)h->E * kStateFloats * sizeof(float)));
     CK(h2d(h, h->env_time.p, time, (size_t)h->E * sizeof(int)));
+    CK(cudaStreamSynchronize(h->own_stream));
     h->env_ready = true;
     return COVO_OK;
 }
@@ -950,8 +967,32 @@ int covo_step(covo_handle* h, const float* state24, const int* time, const float
     int rc = step_common(h, h->state24.p, h->time.p, eps_d, h->action.p, st, 1);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->h_action, h->action.p, (size_t)h->E * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    const bool online = h->cfg.mode == COVO_MODE_COVO_ONLINE;
+    if (online) CK(cudaMemcpyAsync(h->h_status, h->status.p, (size_t)h->E * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     memcpy(action, h->h_action, (size_t)h->E * 4 * sizeof(float));
+    if (online)  // the covariance step of THIS call (the Hessian kernel clears the status): the action was sampled from a bad factor
+        for (int e = 0; e < h->E; ++e)
+            if (h->h_status[e])
+                return fail(COVO_ERR_NUMERIC, "covo_step: numeric status %d in environment %d (%s)", h->h_status[e], e,
+                            h->h_status[e] == 1 ? "spectral range of the Hessian exceeds the rational-approximation ladder"
+                                                : "covariance not positive definite in float32");
+    return COVO_OK;
+}
+
+int covo_set_env_params(covo_handle* h, float m, float g, float max_thrust, float dt, float alpha_bodyrate, float action_scale,
+                        const float* max_omega3, int max_steps_in_episode) {
+    if (!h || !max_omega3) return fail(COVO_ERR_INVALID, "null argument");
+    if (!(m > 0.f) || !(dt > 0.f) || !(max_thrust > 0.f)) return fail(COVO_ERR_INVALID, "m, dt and max_thrust must be positive");
+    // the model constants travel by value in every kernel's argument block: the next launch uses the new ones
+    h->cfg.m = h->env.m = m;
+    h->cfg.g = h->env.g = g;
+    h->cfg.max_thrust = h->env.max_thrust = max_thrust;
+    h->cfg.dt = h->env.dt = dt;
+    h->cfg.alpha_bodyrate = h->env.alpha_bodyrate = alpha_bodyrate;
+    h->cfg.action_scale = h->env.action_scale = action_scale;
+    for (int k = 0; k < 3; ++k) h->cfg.max_omega[k] = h->env.max_omega[k] = max_omega3[k];
+    h->cfg.max_steps_in_episode = h->env.max_steps = max_steps_in_episode;
     return COVO_OK;
 }
 

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(160) hess_local_kernel(const HessianArgs a) {
     const int H = a.H;
     __shared__ float sx[16], su[4], sfd[4], spt[4], svt[4];
     if (tid == 0) {
+        if (t == 0 && a.status) a.status[env] = 0;  // first kernel of the covariance step: the status is per step, not sticky
         const float* st_g = a.state24 + (long long)env * kStateFloats;
         QState<float> s;
         float fd[3], pt[3], vt[3];

@@ -16,6 +16,7 @@ struct HessianArgs {
     const float* a_mean;    // [E][H][4]   nominal controls (shift applied on load if `shift`)
     float* workspace;       // [E][H][14*153 + 14*17]
     float* R;               // [E][n][n]
+    int* status = nullptr;  // [E] numeric status of the covariance step: cleared here, set by the sigma / Cholesky kernels
 };
 
 size_t hessian_workspace_floats(int H);

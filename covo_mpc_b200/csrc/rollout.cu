@@ -582,7 +582,13 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
     // last CTA of this environment: merge all tile partials in tile order (bit-reproducible)
     __threadfence();
     const float* base = a.partials + (long long)env * n_cta * rec;
-    float* scale = sm.tile;  // the U tile is dead now; reuse it as scratch [n_cta]
+    // Scratch: everything in front of sm.prog (factor + E/U tiles) is dead now.  [n_cta] scale table (when it fits: huge N with a
+    // tiny horizon does not, then the factors are recomputed from the record headers) + [ngrp][n_pad] partial sums, ngrp capped
+    // by what is left (MPPI with H = 2 has 576 floats here, not the ~1000 the uncapped layout needs).
+    const int scratch_floats = (int)(reinterpret_cast<float*>(sm.prog) - sm.lfac);
+    const int n_cta_pad = (n_cta + 3) & ~3;
+    const bool have_table = n_cta_pad + n_pad <= scratch_floats;
+    float* scale = sm.lfac;
     float lm = CUDART_INF_F;
     for (int b = tid; b < n_cta; b += blockDim.x) lm = fminf(lm, __ldcg(base + (long long)b * rec));
     lm = warp_min(lm);
@@ -590,10 +596,16 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
     __syncthreads();
     float M = CUDART_INF_F;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) M = fminf(M, sm.red[16 + w]);
-    for (int b = tid; b < n_cta; b += blockDim.x) {
-        float mb = __ldcg(base + (long long)b * rec);
-        scale[b] = (mb < CUDART_INF_F) ? expf(-(mb - M) * inv_lam) : 0.f;
-    }
+    auto scale_of = [&](int b) -> float {
+        if (have_table) return scale[b];
+        const float mb = __ldcg(base + (long long)b * rec);
+        return (mb < CUDART_INF_F) ? expf(-(mb - M) * inv_lam) : 0.f;
+    };
+    if (have_table)
+        for (int b = tid; b < n_cta; b += blockDim.x) {
+            float mb = __ldcg(base + (long long)b * rec);
+            scale[b] = (mb < CUDART_INF_F) ? expf(-(mb - M) * inv_lam) : 0.f;
+        }
     __syncthreads();
     // Deterministic sums over the tile partials.  Loads are issued 16 at a time so the L2 latency of the records
     // overlaps (the partials were written by other SMs).  V[r]: thread r, tiles in order.  S: the last warp,
@@ -601,7 +613,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
     __shared__ float s_S;
     if (warp_id_of(tid) == (int)(blockDim.x >> 5) - 1) {
         float sp = 0.f;
-        for (int b = tid & 31; b < n_cta; b += 32) sp = fmaf(__ldcg(base + (long long)b * rec + 1), scale[b], sp);
+        for (int b = tid & 31; b < n_cta; b += 32) sp = fmaf(__ldcg(base + (long long)b * rec + 1), scale_of(b), sp);
         sp = warp_sum(sp);
         if ((tid & 31) == 0) s_S = sp;
     }
@@ -611,9 +623,10 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
     float Vr[2] = {0.f, 0.f};
     {
         const int ncol4 = n_pad >> 2;                       // <= 64
-        const int ngrp = max(1, (int)blockDim.x / ncol4);   // tile groups (4 at n_pad = 208)
+        const int vfloats = scratch_floats - (have_table ? n_cta_pad : 0);
+        const int ngrp = max(1, min((int)blockDim.x / ncol4, vfloats / n_pad));  // tile groups (4 at n_pad = 208)
         const int per = (n_cta + ngrp - 1) / ngrp;
-        float* vpart = sm.tile + ((n_cta + 3) & ~3);        // [ngrp][n_pad] behind the scale table
+        float* vpart = sm.lfac + (have_table ? n_cta_pad : 0);  // [ngrp][n_pad] behind the scale table
         const int cg = tid % ncol4, tg = tid / ncol4;
         if (tg < ngrp) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -627,7 +640,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     if (b0 + j < b_hi) {
-                        const float sc = scale[b0 + j];
+                        const float sc = scale_of(b0 + j);
                         acc.x = fmaf(v[j].x, sc, acc.x);
                         acc.y = fmaf(v[j].y, sc, acc.y);
                         acc.z = fmaf(v[j].z, sc, acc.z);

@@ -110,6 +110,16 @@ int covo_reset_offline(covo_handle* h, const float* state24, const int* time, in
 /* One MPC step for all E environments.  Host buffers; H2D of (state24, time[, eps]) and D2H of the
  * action happen inside the call, which returns after the stream is idle.  eps may be NULL. */
 int covo_step(covo_handle* h, const float* state24, const int* time, const float* eps, float* action);
+/* Numeric status: the covariance step of every CoVO-online call starts by clearing the per-environment status (it is per step,
+ * not sticky).  covo_step reads it back with the action and returns COVO_ERR_NUMERIC (action still written) when the spectral
+ * range left the rational-approximation ladder (1) or a Cholesky pivot was not positive (2) -- where the reference would surface
+ * NaNs (controllers/covo.py:116-132, :216).  The asynchronous entry points (covo_step_device, covo_step_partial_device,
+ * covo_closed_loop) cannot: their callers poll covo_get_status(). */
+/* The physical model a handle plans with (dynamics/dataclass.py:43-49, 71, 76, 81), replaceable after creation: the reference rolls
+ * out and differentiates with the env_params of the CALL (controllers/covo.py:187-283 `env_params`), e.g. a mass sampled by
+ * Quad3D.sample_params.  Takes effect with the next launch (the constants travel in the kernel argument blocks). */
+int covo_set_env_params(covo_handle* h, float m, float g, float max_thrust, float dt, float alpha_bodyrate, float action_scale,
+                        const float* max_omega3, int max_steps_in_episode);
 /* Same, device pointers, asynchronous on `stream` (a cudaStream_t passed as void*). */
 int covo_step_device(covo_handle* h, const float* state24_dev, const int* time_dev, const float* eps_dev,
                      float* action_dev, void* stream);

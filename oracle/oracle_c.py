@@ -28,6 +28,8 @@ def _load():
         lib = C.CDLL(path)
         lib.oracle_rollout_costs.argtypes = [FP, FP, C.c_int, FP, FP, C.c_int, FP, C.c_int, C.c_int, C.c_float, FP]
         lib.oracle_hessian_fof.argtypes = [FP, FP, C.c_int, FP, FP, C.c_int, FP, C.c_int, FP]
+        DP = C.POINTER(C.c_double)
+        lib.oracle_hessian_fof_f64.argtypes = [FP, FP, C.c_int, FP, FP, C.c_int, FP, C.c_int, DP]
         lib.oracle_num_threads.restype = C.c_int
         _LIB = lib
     return _LIB
@@ -75,6 +77,21 @@ def hessian(ns: o.QuadState, a_mean: np.ndarray, p: o.EnvParams) -> np.ndarray:
     R = np.zeros((4 * H, 4 * H), dtype=np.float32)
     envp = _envp(p)
     _load().oracle_hessian_fof(_p(envp), _p(st), int(ns.time), _p(pt), _p(vt), pt.shape[0], _p(am), H, _p(R))
+    return R
+
+
+def hessian_f64(ns: o.QuadState, a_mean: np.ndarray, p: o.EnvParams) -> np.ndarray:
+    """The same forward-over-forward Hessian in float64 arithmetic on the same float32 inputs: what the float32 results
+    (the reference's, the device's) are rounding-error perturbations of."""
+    am = np.ascontiguousarray(a_mean, dtype=np.float32)
+    H = am.shape[0]
+    st = o.state_to_vec24(ns)
+    pt = np.ascontiguousarray(ns.pos_traj, dtype=np.float32)
+    vt = np.ascontiguousarray(ns.vel_traj, dtype=np.float32)
+    R = np.zeros((4 * H, 4 * H), dtype=np.float64)
+    envp = _envp(p)
+    _load().oracle_hessian_fof_f64(_p(envp), _p(st), int(ns.time), _p(pt), _p(vt), pt.shape[0], _p(am), H,
+                                   R.ctypes.data_as(C.POINTER(C.c_double)))
     return R
 
 

@@ -180,3 +180,92 @@ def test_fast_path_pointers_are_accepted_by_the_real_library():
     with pytest.raises(ValueError, match="null argument"):
         h.step(st.to_state24(), [0])
     h._h = None  # keep __del__ from touching the library
+
+
+def _standin_handle(cm, _lib, calls, H=8, N=64):
+    """A Handle whose library is a recording stand-in (no GPU): enough surface for the controllers' host logic."""
+    import ctypes as C
+
+    class Lib:
+        def covo_step(self, h, sp, tp, ep, op):
+            calls.append(("step",))
+            for k in range(4):
+                op[k] = 0.5
+            return 0
+
+        def covo_set_mean(self, h, p):
+            calls.append(("set_mean", np.ctypeslib.as_array(p, shape=(4 * H,)).copy()))
+            return 0
+
+        def covo_get_mean(self, h, p):
+            calls.append(("get_mean",))
+            np.ctypeslib.as_array(p, shape=(4 * H,))[:] = 7.0
+            return 0
+
+        def covo_set_env_params(self, h, m, g, mt, dt, al, sc, mo, ms):
+            calls.append(("set_env_params", float(m), float(mt), int(ms), [float(mo[k]) for k in range(3)]))
+            return 0
+
+        def __getattr__(self, name):
+            def f(*a):
+                calls.append((name.replace("covo_", ""),))
+                return 0
+            return f
+
+    h = object.__new__(_lib.Handle)
+    h.lib, h._h, h.E, h.H, h.n, h.n_local = Lib(), C.c_void_p(1), 1, H, 4 * H, N
+    h.cfg = _lib.CovoConfig()
+    return h
+
+
+def test_offline_reset_with_current_params_keeps_the_resident_mean():
+    """render_env's pattern (envs/quadrotor.py:637-639): after `done`, controller.reset is called with the CURRENT control_params.
+    The reference keeps a_mean across that reset (covo.py:101-104); here the returned object must stay usable -- no 'stale
+    control_params' -- and must not trigger a re-upload of the mean."""
+    import covo_mpc_b200 as cm
+    from covo_mpc_b200 import _lib
+
+    calls = []
+    env = cm.Quad3D("tracking_zigzag")
+    _, info, st = env.reset(np.random.default_rng(5))
+    ns = info["noisy_state"]
+    ctl, cp = cm.get_controller(env, "covo-offline", "N64_H8_lam0.01")
+    h = _standin_handle(cm, _lib, calls)
+    ctl._handle, ctl._cfg.traj_len = h, ns.pos_traj.shape[0]
+    h.cfg.traj_len = ns.pos_traj.shape[0]
+    cp = ctl.reset(st, env.default_params, cp, None)
+    _, cp, _ = ctl(None, st, env.default_params, None, cp, {"noisy_state": ns})
+    assert [c[0] for c in calls].count("set_mean") == 1  # the initial (host) mean, uploaded once
+    _, cp, _ = ctl(None, st, env.default_params, None, cp, {"noisy_state": ns})
+    cp_r = ctl.reset(st, env.default_params, cp, None)  # reset with the params of the previous step
+    assert cp_r._gen == cp._gen == ctl._generation
+    n_set = [c[0] for c in calls].count("set_mean")
+    action, cp2, _ = ctl(None, st, env.default_params, None, cp_r, {"noisy_state": ns})  # raised RuntimeError before the fix
+    assert [c[0] for c in calls].count("set_mean") == n_set and np.allclose(action, 0.5)
+    assert np.allclose(np.asarray(cp2.a_mean), 7.0)  # materialises from the (stand-in) device
+    # a reset with the INITIAL params re-uploads the hover mean, as the reference's eval_env does (quadrotor.py:548-550)
+    cp_i = ctl.reset(st, env.default_params, ctl.init_control_params, None)
+    ctl(None, st, env.default_params, None, cp_i, {"noisy_state": ns})
+    assert [c[0] for c in calls].count("set_mean") == n_set + 1
+
+
+def test_call_time_env_params_reach_the_handle():
+    """The reference plans with the env_params of the call (covo.py:187-283): a modified mass must be forwarded, once per object."""
+    import covo_mpc_b200 as cm
+    from covo_mpc_b200 import _lib
+
+    calls = []
+    env = cm.Quad3D("tracking_zigzag")
+    _, info, st = env.reset(np.random.default_rng(6))
+    ns = info["noisy_state"]
+    ctl, cp = cm.get_controller(env, "mppi", "N64_H8_lam0.01")
+    h = _standin_handle(cm, _lib, calls)
+    ctl._handle, ctl._cfg.traj_len = h, ns.pos_traj.shape[0]
+    h.cfg.traj_len = ns.pos_traj.shape[0]
+    _, cp, _ = ctl(None, st, env.default_params, None, cp, {"noisy_state": ns})
+    heavy = env.default_params.replace(m=0.04)
+    _, cp, _ = ctl(None, st, heavy, None, cp, {"noisy_state": ns})
+    _, cp, _ = ctl(None, st, heavy, None, cp, {"noisy_state": ns})
+    sets = [c for c in calls if c[0] == "set_env_params"]
+    assert len(sets) == 2 and abs(sets[0][1] - 0.027) < 1e-9 and abs(sets[1][1] - 0.04) < 1e-9 and sets[1][3] == 300
+    assert cm.get_controller(env, "covo_offline_online")[0].mode == "online"  # "online" is tested first (quadrotor.py:731-737)

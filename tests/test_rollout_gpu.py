@@ -254,3 +254,38 @@ def test_jax_compatible_stream_in_kernel(mode_name):
         hr.set_jax_key(act_key)
         _, _, cr, sr = hr.rollout(st, [ns.time], a_mean[None], want_costs=True, want_samples=True)
         assert np.array_equal(sr[0], s1[0][r * N // 2:(r + 1) * N // 2])
+
+
+@pytest.mark.parametrize("mode_name", ["mppi", "covo"])
+@pytest.mark.parametrize("N,H", [(4, 2), (4, 3), (8192, 2), (8192, 3), (65536, 2)])
+def test_tiny_horizons_merge_scratch(mode_name, N, H):
+    """get_controller(..., debug=True) forces N = 4, H = 2 (envs/quadrotor.py:705-707, 726-728).  The grid-wide merge keeps its
+    scale table and partial sums in the dead part of the dynamic shared memory, which at H = 2 is far smaller than the layout
+    tuned for n = 200 (out-of-bounds shared-memory write).  gamma_mean != 1 reads the staged mean AFTER the merge
+    scratch was written.  N = 65536 at H = 2: the scale table no longer fits and is recomputed from the record headers."""
+    from covo_mpc_b200 import _lib
+
+    p, ns, a_mean, rng = scenario("tracking_zigzag", seed=17, H=H, warm_steps=5)
+    n = 4 * H
+    mode = _lib.MODE_MPPI if mode_name == "mppi" else _lib.MODE_COVO_ONLINE
+    h = _handle(mode, N, H, ns.pos_traj.shape[0], gamma_mean=0.7)
+    h.set_reference(ns.pos_traj[None], ns.vel_traj[None])
+    if mode_name == "mppi":
+        eps = rng.standard_normal((N, H, 4)).astype(np.float32)
+        Lblk = np.tile(0.5 * np.eye(4, dtype=np.float32), (H, 1, 1))
+        a_s = o.sample_actions_blockdiag(o.shift_mean(a_mean), Lblk, eps)
+    else:
+        A = rng.standard_normal((n, n)) / np.sqrt(n)
+        cov = (0.2 * A @ A.T + 0.1 * np.eye(n)).astype(np.float32)
+        h.set_cov(cov[None])
+        L = np.linalg.cholesky(h.get_cov()[0].astype(np.float64)).astype(np.float32)
+        eps = rng.standard_normal((N, n)).astype(np.float32)
+        a_s = o.sample_actions(o.shift_mean(a_mean), L, eps)
+    a_out, act, costs, samples = h.rollout(o.state_to_vec24(ns), [ns.time], a_mean[None], shift=True, eps=eps.reshape(1, N, n),
+                                           want_costs=True, want_samples=True)
+    assert np.abs(samples[0] - a_s).max() < 5e-6
+    cost_o = o.rollout_costs(ns, samples[0], p)
+    assert np.abs(costs[0] - cost_o).max() <= 1e-5 * max(1.0, np.abs(cost_o).max())
+    new_o, _ = o.softmax_update(o.shift_mean(a_mean), samples[0], cost_o, 0.01, 0.7)
+    assert np.abs(a_out[0] - new_o).max() < 2e-5
+    h.close()
