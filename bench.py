@@ -14,9 +14,15 @@ envs/quadrotor.py:323-351).
            L2 flushed (256 MiB memset) between steps and excluded from the timing.
   e2e    : the same steps through the reference-facing plugin call controller(obs, state, params, rng,
            control_params, info) with HOST numpy state: H2D (pinned) + kernels + D2H inside the timed region.
-  N > 1  : one process per GPU (torch.distributed / NCCL for barrier + max-over-ranks); default is one
-           independent environment per rank (no data-path collective, weak scaling).  --shard nsample splits
-           the N samples of ONE environment across ranks with one all-gather of 808 B per rank per step.
+  N > 1  : one process per GPU (torch.distributed / NCCL for barrier + max-over-ranks), one independent environment per rank
+           (no data-path collective, weak scaling).
+  The same JSON line carries the BASELINE configurations the replica number does not show:
+    nsample_shard : config 4 -- CoVO-offline, the N samples of ONE environment split over the ranks with one exchange of the
+                    (min cost, sum w, sum w u) records per step; device-timed and wall, with the strong-scaling efficiency against
+                    the same handle at world = 1 run in the same process, at N = 8192 and N = 65536;
+    env_batch     : config 5 -- 512 environments per GPU x N = 1024, device-resident closed loop, per-kernel times;
+    tracking_cost : 40 x 300-step episodes, device vs the oracle fixture (mean +- s.e., z-scores);
+    cpu_baseline  : the oracle port on the host cores, bounded sample.
 """
 from __future__ import annotations
 
@@ -38,21 +44,27 @@ METRIC, UNIT = "mpc_control_steps_per_sec", "steps/s"
 
 
 # ---------------------------------------------------------------------------------------------------
-def record_states(n_states: int, seed: int, controller_name="covo-online", N=1024, device=0):
-    """Closed-loop episode (untimed, smaller N) to obtain a realistic sequence of noisy states."""
-    import covo_mpc_b200 as cm
+def synthetic_states(n_states: int, seed: int):
+    """The inputs BOTH arms time: noisy states along closed-loop episodes of the reference's own PID policy (gains of
+    envs/quadrotor.py:692-699) on zigzag reference trajectories, observation noise as envs/quadrotor.py:323-351, disturb none.
+    Generated on the host without any kernel under test (oracle/ restatement of the environment, untimed) so that `--impl b200`
+    and `--impl reference` see bit-identical states (same inputs / seeds).  Returns (states [n][24], times [n],
+    (pos_traj, vel_traj) of each state's episode, episode index per state)."""
+    from oracle import oracle_np as o
 
-    env = cm.Quad3D(TASK)
-    ctl, _ = cm.get_controller(env, controller_name, f"N{N}_H{HORIZON}_lam{LAM}", seed=seed, device=device)
-    rec = []
+    p = o.EnvParams()
     rng = np.random.default_rng(seed)
-    while len(rec) < n_states:
-        cm.run_episode(env, ctl, rng, n_steps=min(290, n_states - len(rec)), record=rec, reset_rng=np.random.default_rng(seed))
-    traj = ctl._ref_keepalive
-    ctl.close()
-    states = np.stack([r[0] for r in rec[:n_states]]).astype(np.float32)
-    times = np.array([r[1] for r in rec[:n_states]], dtype=np.int32)
-    return env, states, times, traj
+    states, times, trajs, ep_of = [], [], [], []
+    while len(states) < n_states:
+        s = o.reset_env(TASK, p, rng, dtype=np.float32, zero_disturb=True)
+        trajs.append((np.ascontiguousarray(s.pos_traj, np.float32), np.ascontiguousarray(s.vel_traj, np.float32)))
+        for _ in range(min(290, n_states - len(states))):
+            ns = o.noisy_state(s, p, rng)
+            states.append(o.state_to_vec24(ns))
+            times.append(ns.time)
+            ep_of.append(len(trajs) - 1)
+            s, _, _, _ = o.env_step(s, o.pid_action(s, p, Kp=10.0, Kd=5.0, Ki=0.0, Kp_att=10.0), p, rng, "none")
+    return np.stack(states).astype(np.float32), np.array(times, dtype=np.int32), trajs, ep_of
 
 
 class ClockSampler:
@@ -122,6 +134,144 @@ def algorithmic_bytes(n, H, N, parity=False):
 
 
 # ---------------------------------------------------------------------------------------------------
+def record_states(n_states: int, seed: int, controller_name="covo-online", N=1024, device=0):
+    """Compatibility shim for the tools: (env, states, times, (pos_traj, vel_traj)) of ONE synthetic episode."""
+    import covo_mpc_b200 as cm
+
+    st, tm, trajs, _ = synthetic_states(min(n_states, 290), seed)
+    idx = np.arange(n_states) % len(st)
+    return cm.Quad3D(TASK), st[idx], tm[idx], trajs[0]
+
+
+def _hover(E=1):
+    return np.tile(np.array([(0.027 * 9.81 / 0.8) * 2 - 1, 0, 0, 0], np.float32), (E, HORIZON, 1))
+
+
+def _events(n):
+    import torch
+
+    return [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+
+
+def bench_nsample_shard(dist, world, rank, dev, states, times, traj, K, W, flush, n_samples):
+    """BASELINE config 4: CoVO-offline, the N samples of ONE environment split over the ranks, one exchange of the (min cost,
+    sum w, sum w u) records per MPC step (controllers/covo.py:266-275 merged across ranks).  Device-timed (CUDA events, max over
+    ranks) and wall-clock, next to the same handle type at world = 1 run in the same process: strong-scaling efficiency =
+    t(world 1) / (world x t(world))."""
+    import torch
+
+    from covo_mpc_b200 import _lib
+
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def make(r, w):
+        cfg = _lib.default_config()
+        cfg.mode, cfg.n_samples, cfg.horizon, cfg.traj_len, cfg.device = _lib.MODE_COVO_OFFLINE, n_samples, HORIZON, int(traj[0].shape[0]), dev.index
+        cfg.lam, cfg.seed, cfg.rank, cfg.world = LAM, 100, r, w
+        h = _lib.Handle(cfg)
+        h.set_reference(traj[0][None], traj[1][None])
+        h.reset_offline(states[0].cpu().numpy(), [0], 300)
+        return h
+
+    actions = torch.zeros((W + K, 4), dtype=torch.float32, device=dev)
+
+    def timed(step_fn):
+        for i in range(W):
+            step_fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev = _events(K)
+        t0 = time.perf_counter()
+        for i in range(K):
+            flush.zero_()
+            ev[i][0].record()
+            step_fn(W + i)
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+        t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) / K, float(t[1]) / K
+
+    h1 = make(0, 1)
+    one = lambda i: h1.step_device(states.data_ptr() + 96 * i, times.data_ptr() + 4 * i, 0, actions.data_ptr() + 16 * i, stream)
+    d1, w1 = timed(one)
+    a1 = actions[W:W + K].clone()
+    out = {"n_samples": n_samples, "world1_device_ms_per_step": d1, "world1_wall_ms_per_step_incl_flush": w1}
+    if world > 1:
+        hs = make(rank, world)
+        pbuf, pn = hs.partial_buffer()
+
+        class _W:
+            __cuda_array_interface__ = {"shape": (pn,), "typestr": "<f4", "data": (pbuf, False), "version": 2}
+
+        part = torch.as_tensor(_W(), device=dev)
+        gathered = torch.zeros((world, pn), dtype=torch.float32, device=dev)
+
+        def sharded(i):
+            hs.step_partial_device(states.data_ptr() + 96 * i, times.data_ptr() + 4 * i, 0, stream)
+            dist.all_gather_into_tensor(gathered.view(-1), part)
+            hs.step_merge_device(gathered.data_ptr(), actions.data_ptr() + 16 * i, stream)
+
+        dw, ww = timed(sharded)
+        out.update({"device_ms_per_step": dw, "wall_ms_per_step_incl_flush": ww, "steps_per_sec": 1e3 / dw,
+                    "strong_scaling_efficiency": d1 / (world * dw), "speedup_vs_world1": d1 / dw,
+                    "exchange": "ncclAllGather of %d B per rank per step + merge kernel" % (4 * pn),
+                    "exchange_bytes_per_step_per_rank": 4 * pn * (world - 1),
+                    "max_action_diff_vs_world1": float((actions[W:W + K] - a1).abs().max()),
+                    "limiter": "the rollout grid is ceil(N/64) CTAs: at N=8192 it is ONE wave (128 CTAs on 148 SMs) on one GPU already, so sharding "
+                               "cannot shorten the per-CTA chain (GEMM || 50-step rollout ~25 us) and only adds the exchange; it pays when N/64 >> 148"})
+        hs.close()
+    h1.close()
+    return out
+
+
+def bench_env_batch(dist, world, rank, dev, K, E=512, N=1024):
+    """BASELINE config 5: E environments per GPU behind one handle (CoVO-online, N = 1024, H = 50), the whole closed loop
+    (noisy state -> controller -> Quad3D.step_env) on the device; ranks are independent (no collective)."""
+    import torch
+
+    from covo_mpc_b200 import _lib
+
+    _, _, trajs, _ = synthetic_states(16 * 290, 1000 + rank)
+    pos = np.stack([trajs[e % len(trajs)][0] for e in range(E)])
+    vel = np.stack([trajs[e % len(trajs)][1] for e in range(E)])
+    cfg = _lib.default_config()
+    cfg.mode, cfg.n_samples, cfg.horizon, cfg.traj_len, cfg.n_env, cfg.seed, cfg.device = _lib.MODE_COVO_ONLINE, N, HORIZON, pos.shape[1], E, 3 + rank, dev.index
+    cfg.lam = LAM
+    h = _lib.Handle(cfg)
+    h.set_reference(pos, vel)
+    h.set_mean(_hover(E))
+    s0 = np.zeros((E, 24), np.float32)
+    s0[:, 6] = 1.0
+    s0[:, 16:19] = pos[:, 0]
+    s0[:, 19:22] = vel[:, 0]
+    h.env_reset(s0, np.zeros(E, np.int32))
+    h.closed_loop(3, noise_seed=1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    _, _, err = h.closed_loop(K, noise_seed=2)
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    h.set_profiling(True)
+    h.closed_loop(1, noise_seed=3)
+    km = h.kernel_ms()
+    ok = bool((h.status() == 0).all())
+    h.close()
+    return {"metric": "env_mpc_steps_per_sec", "value": E * world * K / float(tt.item()), "unit": "env-steps/s", "envs_per_gpu": E, "n_samples": N,
+            "horizon": HORIZON, "steps": K, "ms_per_batched_step": 1e3 * float(tt.item()) / K, "scaling": "weak",
+            "timing": "wall clock around covo_closed_loop (K batched steps, one D2H of the logs at the end), max over ranks",
+            "kernel_ms_one_step": {k: float(v) for k, v in zip(["hessian", "sigma_stage1", "sigma_stage2", "sigma_stage3", "cholesky", "rollout"], km)},
+            "mean_err_pos": float(err.mean()), "status_ok": ok}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -140,18 +290,18 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
-    shard = args.shard if world > 1 else "env"
-    n_states = W + K
-    seed = 100 + (rank if shard == "env" else 0)
-    mode_name = "covo-offline" if shard == "nsample" else args.controller
-    env, states_h, times_h, traj = record_states(n_states, seed, "covo-online" if mode_name != "mppi" else "mppi", device=local_rank)
+    n_states = min(W + K, 290)
+    seed = 100 + rank  # one independent environment per rank
+    mode_name = args.controller
+    states_h, times_h, trajs, _ = synthetic_states(n_states, seed)
+    traj = trajs[0]
+    env = cm.Quad3D(TASK)
+    sidx = lambda i: i % n_states
 
     cfg = _lib.default_config()
     cfg.mode = {"covo-online": _lib.MODE_COVO_ONLINE, "covo-offline": _lib.MODE_COVO_OFFLINE, "mppi": _lib.MODE_MPPI}[mode_name]
     cfg.n_samples, cfg.horizon, cfg.traj_len, cfg.device = N_SAMPLES, HORIZON, int(traj[0].shape[0]), local_rank
     cfg.lam, cfg.seed = LAM, seed
-    if shard == "nsample":
-        cfg.rank, cfg.world = rank, world
     h = _lib.Handle(cfg)
     h.set_reference(traj[0][None], traj[1][None])
     if cfg.mode == _lib.MODE_COVO_OFFLINE:
@@ -161,37 +311,17 @@ def run_gpu(args):
     actions = torch.zeros((n_states, 4), dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
-    gathered = None
-    if shard == "nsample":
-        pbuf, pn = h.partial_buffer()
-        gathered = torch.zeros((world, pn), dtype=torch.float32, device=dev)
-        part_view = None
 
     def one_step(i):
-        sp, tp, ap = states.data_ptr() + 96 * i, times.data_ptr() + 4 * i, actions.data_ptr() + 16 * i
-        if shard == "nsample":
-            h.step_partial_device(sp, tp, 0, stream)
-            # 808 B per rank: all-gather of (min cost, sum w, sum w*u) records, then the merge kernel
-            src = _as_tensor(pbuf, pn, dev)
-            dist.all_gather_into_tensor(gathered.view(-1), src)
-            h.step_merge_device(gathered.data_ptr(), ap, stream)
-        else:
-            h.step_device(sp, tp, 0, ap, stream)
-
-    def _as_tensor(ptr, n, dev):
-        nonlocal part_view
-        if part_view is None:
-            class _W:  # __cuda_array_interface__ view of the library-owned partial buffer
-                __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-            part_view = torch.as_tensor(_W(), device=dev)
-        return part_view
+        i = sidx(i)
+        h.step_device(states.data_ptr() + 96 * i, times.data_ptr() + 4 * i, 0, actions.data_ptr() + 16 * i, stream)
 
     for i in range(W):
         one_step(i)
     torch.cuda.synchronize()
     # per-kernel device time (instrumented pass, not the timed one)
     kernel_ms = None
-    if shard == "env" and cfg.mode != _lib.MODE_MPPI:
+    if cfg.mode != _lib.MODE_MPPI:
         h.set_profiling(True)
         acc = np.zeros(6)
         reps = min(10, K)
@@ -202,7 +332,7 @@ def run_gpu(args):
         kernel_ms = acc / reps
         h.set_profiling(False)
         # restart the controller state so the timed pass sees the same sequence again
-        h.set_mean(np.tile(np.array([(0.027 * 9.81 / 0.8) * 2 - 1, 0, 0, 0], np.float32), (1, HORIZON, 1)))
+        h.set_mean(_hover())
         for i in range(W):
             one_step(i)
     torch.cuda.synchronize()
@@ -210,7 +340,7 @@ def run_gpu(args):
         dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    ev = _events(K)
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     for i in range(K):
@@ -229,79 +359,71 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms_max = float(tmax.item())
-    units = K * (world if shard == "env" else 1)
-    value = units / (total_ms_max / 1e3)
-    acts = actions[W:W + K].cpu().numpy()
-    assert np.isfinite(acts).all(), "non-finite actions"
+    value = K * world / (total_ms_max / 1e3)
+    assert torch.isfinite(actions).all(), "non-finite actions"
+    status_ok = bool((h.status() == 0).all()) if cfg.mode == _lib.MODE_COVO_ONLINE else True
 
     # ---- e2e through the plugin surface with host buffers -------------------------------------------
-    e2e = None
-    if shard == "env":
-        ctl, cp = cm.get_controller(env, mode_name, f"N{N_SAMPLES}_H{HORIZON}_lam{LAM}", device=local_rank, seed=seed)
-        f32 = np.float32
-        st0 = cm.EnvState3D(pos=np.zeros(3, f32), vel=np.zeros(3, f32), quat=np.array([0, 0, 0, 1], f32), omega=np.zeros(3, f32),
-                            pos_traj=traj[0], vel_traj=traj[1], acc_traj=np.zeros_like(traj[0]), pos_tar=np.zeros(3, f32),
-                            vel_tar=np.zeros(3, f32), acc_tar=np.zeros(3, f32), time=0, f_disturb=np.zeros(3, f32))
+    ctl, cp = cm.get_controller(env, mode_name, f"N{N_SAMPLES}_H{HORIZON}_lam{LAM}", device=local_rank, seed=seed)
+    f32 = np.float32
+    st0 = cm.EnvState3D(pos=np.zeros(3, f32), vel=np.zeros(3, f32), quat=np.array([0, 0, 0, 1], f32), omega=np.zeros(3, f32),
+                        pos_traj=traj[0], vel_traj=traj[1], acc_traj=np.zeros_like(traj[0]), pos_tar=np.zeros(3, f32),
+                        vel_tar=np.zeros(3, f32), acc_tar=np.zeros(3, f32), time=0, f_disturb=np.zeros(3, f32))
 
-        def mk(i):
-            s = states_h[i]
-            return st0.replace(pos=s[0:3], quat=s[3:7], vel=s[7:10], omega=s[10:13], f_disturb=s[13:16], pos_tar=s[16:19],
-                               vel_tar=s[19:22], time=int(times_h[i]))
+    def mk(i):
+        s = states_h[i]
+        return st0.replace(pos=s[0:3], quat=s[3:7], vel=s[7:10], omega=s[10:13], f_disturb=s[13:16], pos_tar=s[16:19],
+                           vel_tar=s[19:22], time=int(times_h[i]))
 
-        host_states = [mk(i) for i in range(n_states)]
-        if mode_name == "covo-offline":
-            cp = ctl.reset(host_states[0], env.default_params, cp, None)
-        for i in range(W):
-            _, cp, _ = ctl(None, host_states[i], env.default_params, None, cp, {"noisy_state": host_states[i]})
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for i in range(K):
-            act, cp, _ = ctl(None, host_states[W + i], env.default_params, None, cp, {"noisy_state": host_states[W + i]})
-        torch.cuda.synchronize()
-        te = time.perf_counter() - t0
-        tt = torch.tensor([te], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": K * world / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": 24 * 4 + 4, "d2h_bytes_per_step": 16,
-               "ms_per_step": 1e3 * float(tt.item()) / K}
-        ctl.close()
+    host_states = [mk(i) for i in range(n_states)]
+    if mode_name == "covo-offline":
+        cp = ctl.reset(host_states[0], env.default_params, cp, None)
+    for i in range(W):
+        _, cp, _ = ctl(None, host_states[i], env.default_params, None, cp, {"noisy_state": host_states[i]})
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        hs_i = host_states[sidx(W + i)]
+        act, cp, _ = ctl(None, hs_i, env.default_params, None, cp, {"noisy_state": hs_i})
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    tt = torch.tensor([te], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e = {"value": K * world / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": 24 * 4 + 4, "d2h_bytes_per_step": 16 + 4,
+           "ms_per_step": 1e3 * float(tt.item()) / K,
+           "path": "get_controller(...)(obs, state, env_params, rng, control_params, info) with numpy state -> covo_step (pinned staging) -> action"}
+    ctl.close()
 
     # ---- device-resident closed loop: controller + environment step, no host round trip -----
-    closed = None
-    if shard == "env":
-        h.set_mean(np.tile(np.array([(0.027 * 9.81 / 0.8) * 2 - 1, 0, 0, 0], np.float32), (1, HORIZON, 1)))
-        h.env_reset(states_h[0][None], times_h[:1])
-        h.closed_loop(W, noise_seed=seed)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        _, _, err_cl = h.closed_loop(K, noise_seed=seed + 1)
-        tc = time.perf_counter() - t0
-        closed = {"value": K * world / tc, "unit": UNIT, "ms_per_step": 1e3 * tc / K, "mean_err_pos": float(err_cl.mean()),
-                  "note": "covo_closed_loop: K x [noisy state -> controller -> Quad3D.step_env] on the device, one D2H of the logs at the end (wall clock)"}
-    launches_per_step = {"covo-online": 9, "covo-offline": 1, "mppi": 2}[mode_name] + (1 if shard == "nsample" else 0)
+    h.set_mean(_hover())
+    h.env_reset(states_h[0][None], times_h[:1])
+    h.closed_loop(W, noise_seed=seed)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, _, err_cl = h.closed_loop(K, noise_seed=seed + 1)
+    tc = time.perf_counter() - t0
+    closed = {"value": K * world / tc, "unit": UNIT, "ms_per_step": 1e3 * tc / K, "mean_err_pos": float(err_cl.mean()),
+              "note": "covo_closed_loop: K x [noisy state -> controller -> Quad3D.step_env] on the device, one D2H of the logs at the end (wall clock)"}
+    launches_per_step = h.launches_per_step() if hasattr(h, "launches_per_step") else {"covo-online": 9, "covo-offline": 1, "mppi": 2}[mode_name]
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak" if shard == "env" else "strong",
+        "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{mode_name} {TASK} N={N_SAMPLES} H={HORIZON} u_dim=4 lam={LAM} sigma=0.5, 1 env per GPU"
-                   if shard == "env" else f"covo-offline tracking_zigzag N={N_SAMPLES} H={HORIZON} N-sharded over {world} GPUs",
+        "config": {"workload": f"{mode_name} {TASK} N={N_SAMPLES} H={HORIZON} u_dim=4 lam={LAM} sigma=0.5, 1 env per GPU",
                    "controller": mode_name, "n_samples": N_SAMPLES, "horizon": HORIZON, "envs_per_gpu": 1,
-                   "parallelism": ("env-replicas x%d (no collective)" % world) if shard == "env" else "nsample-shard x%d (allgather 808B/rank/step)" % world,
+                   "parallelism": "env-replicas x%d (no collective)" % world,
+                   "inputs": "noisy states of a PID closed loop on a zigzag reference (host-generated, shared with --impl reference)",
                    "rng": "in-kernel Philox (production mode)", "l2": "256 MiB memset between steps, excluded from the event timing",
                    "timing": "CUDA events per step on the launch stream, sum over K steps, max over ranks",
-                   "pipeline": ("cholesky -> rollout as a programmatic dependent launch: the rollout kernel runs next to the factorisation "
-                                "and consumes the factor 8 columns at a time; roofline_kernels are per-kernel times with the pipeline "
-                                "switched off (profiling mode), so their sum exceeds ms_per_step") if mode_name == "covo-online" else "n/a"},
+                   "sigma_path": os.environ.get("COVO_SIGMA", "default")},
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
         "step_ms_p50": float(np.median(step_ms)), "step_ms_p99": float(np.percentile(step_ms, 99)),
-        "gpu_launches": launches_per_step * K, "clocks": clocks,
+        "gpu_launches": launches_per_step * K, "clocks": clocks, "numeric_status_ok": status_ok,
+        "e2e": e2e, "closed_loop": closed,
     }
-    if e2e:
-        out["e2e"] = e2e
-    if closed:
-        out["closed_loop"] = closed
     # ---- roofline ---------------------------------------------------------------------------------------
     peak, peak_src = measured_peaks()
     n = 4 * HORIZON
@@ -310,32 +432,43 @@ def run_gpu(args):
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp))
-    if kernel_ms is not None:
-        per = {"hessian": kernel_ms[0], "tridiag": kernel_ms[1], "trifunc": kernel_ms[2], "sandwich": kernel_ms[3],
-               "cholesky": kernel_ms[4], "rollout": kernel_ms[5]}
+    if kernel_ms is not None and cfg.mode == _lib.MODE_COVO_ONLINE:
+        names = h.kernel_slot_names() if hasattr(h, "kernel_slot_names") else ["hessian", "tridiag", "trifunc", "sandwich", "cholesky", "rollout"]
+        per = {k: float(v) for k, v in zip(names, kernel_ms) if v > 1e-4}
         dom = max(per, key=per.get)
         rl = {}
         for k, ms in per.items():
-            ach = ab[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            b = ab.get(k, ab.get("sigma"))
+            ach = b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             rl[k] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(k),
-                     "ms": float(ms), "algorithmic_bytes": ab[k], "share_of_step": float(ms / sum(per.values()))}
+                     "ms": float(ms), "algorithmic_bytes": b, "share_of_step": float(ms / sum(per.values()))}
         out["roofline"] = dict(rl[dom], kernel=dom, peak_source=peak_src,
-                               note="latency-bound serial factorisation by construction (SURVEY 8d): 198 dependent Householder steps, "
-                                    "one DSMEM exchange each; HBM traffic is ~0.3 MB per launch")
+                               note="latency-bound by construction (SURVEY 8d): the whole step moves ~1.7 MB through HBM; the dominant "
+                                    "kernel is a chain of dependent small-matrix steps, see DESIGN.md section 4")
         out["roofline_kernels"] = rl
         flops = N_SAMPLES * n * (n + 1) + N_SAMPLES * HORIZON * 200 + 2 * N_SAMPLES * n
         out["rollout_fp32"] = {"algorithmic_gflop": flops / 1e9, "achieved_tflops": flops / (per["rollout"] * 1e-3) / 1e12,
                                "nominal_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12}
-    elif cfg.mode != _lib.MODE_COVO_ONLINE or shard != "env":
+    else:
         ms = total_ms_max / K
         ach = ab["rollout"] / (ms * 1e-3) / 1e9
         out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                            "traffic": traffic.get("rollout"), "kernel": "rollout", "peak_source": peak_src}
+    # ---- the BASELINE configurations the replica line does not show --------------------------------------------
+    if not args.no_subrecords:
+        h.close()
+        Ks = min(K, 100)
+        out["nsample_shard"] = {
+            "workload": f"covo-offline {TASK} H={HORIZON}, the N samples of ONE environment split over {world} rank(s) (BASELINE config 4)",
+            "N8192": bench_nsample_shard(dist, world, rank, dev, states, times, traj, Ks, W, flush, 8192),
+            "N65536": bench_nsample_shard(dist, world, rank, dev, states, times, traj, Ks, W, flush, 65536)}
+        out["env_batch"] = bench_env_batch(dist, world, rank, dev, min(K, 20))
+        out["env_batch"]["workload"] = f"{512 * world} envs x covo-online N=1024 H={HORIZON}, env-batch sharded over {world} GPU(s), no collective (BASELINE config 5)"
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(states_h, times_h, traj, budget_s=args.cpu_budget, mode_name=mode_name)
         if mode_name == "covo-online":
-            out["tracking_cost"] = tracking_cost(h, traj, seed, n_steps=min(100, max(K, 20)))
+            out["tracking_cost"] = tracking_cost(local_rank)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -388,53 +521,27 @@ def cpu_baseline(states_h, times_h, traj, budget_s=20.0, mode_name="covo-online"
             "steps": done, "seconds": t_used}
 
 
-def tracking_cost(h, traj, seed, n_steps=100):
-    """BASELINE metric, second half ("tracking cost delta vs ref"): the same closed-loop protocol -- zigzag reference,
-    zero initial state, observation noise, disturb_type none -- through the device loop (covo_closed_loop) and through
-    the oracle port on the host.  Sample and noise streams are independent (the reference's Threefry streams are not
-    reproducible here), so this is a statistical comparison of mean ||pos_tar - pos|| over the episode."""
-    from oracle import oracle_np as o
+def tracking_cost(device=0, controller="covo-online"):
+    """BASELINE metric, second half ("tracking cost delta vs ref"), POWERED: the reference's protocol (envs/quadrotor.py:564-579:
+    4 trajectories x 10 episodes x 300 steps, mean over episodes of the per-episode mean ||pos_tar - pos||) on both sides with the
+    SAME trajectories, initial states and observation-noise streams per episode (tools/tracking_protocol.py).  Oracle arm: the
+    fixture tests/golden/oracle_tracking_*.npz written by tools/oracle_tracking_stats.py (CPU, ~35 min; committed with the script).
+    Device arm: all 40 episodes as one batched device-resident closed loop with the production Philox sample field.  The sample
+    streams differ (numpy vs Philox), so this is a statistical comparison: means +- s.e., z-scores unpaired and paired by episode."""
+    from tools import device_tracking_stats as dts
 
-    try:
-        from oracle import oracle_c
-
-        step = lambda ns, mean, eps, p: oracle_c.covo_step(ns, mean, eps, p, LAM)
-    except Exception:
-        def step(ns, mean, eps, p):
-            u, m, _, _ = o.covo_call(ns, mean, eps, p, lam=LAM, hessian_dtype=np.float32)
-            return u, m
-    p = o.EnvParams()
-    s0 = o.make_state(np.zeros(3), np.array([0, 0, 0, 1.0]), np.zeros(3), np.zeros(3), np.zeros(3), 0, traj[0], traj[1], traj[0][0], traj[1][0],
-                      dtype=np.float32)
-    hover = o.hover_mean(HORIZON, p)
-    # device: 8 episodes (independent noise streams; the sample stream advances from episode to episode)
-    dev = []
-    for k in range(8):
-        h.set_mean(hover[None])
-        h.env_reset(o.state_to_vec24(s0)[None], [0])
-        _, _, err_d = h.closed_loop(n_steps, noise_seed=seed + 11 + k)
-        dev.append(float(err_d[:, 0].mean()))
-    # oracle port on the host: as many episodes as fit into ~40 s, at most 3
-    ora, t0 = [], time.perf_counter()
-    for k in range(3):
-        rng = np.random.default_rng(seed + 7 + k)
-        s, mean, errs = s0.copy(), hover, []
-        for i in range(n_steps):
-            ns = o.noisy_state(s, p, rng)
-            eps = rng.standard_normal((N_SAMPLES, 4 * HORIZON)).astype(np.float32)
-            u, mean = step(ns, mean, eps, p)
-            s, _, _, e = o.env_step(s, u, p, rng, "none")
-            errs.append(e)
-        ora.append(float(np.mean(errs)))
-        if time.perf_counter() - t0 > 25.0:
-            break
-    dm, om = float(np.mean(dev)), float(np.mean(ora))
-    return {"metric": "mean ||pos_tar - pos|| over the first %d closed-loop steps (m), mean over episodes" % n_steps,
-            "device": dm, "device_std": float(np.std(dev)), "device_episodes": len(dev),
-            "oracle_port": om, "oracle_std": float(np.std(ora)), "oracle_episodes": len(ora),
-            "rel_delta": (dm - om) / om if om > 0 else None,
-            "note": "same protocol and reference trajectory, independent sample/noise streams: statistical agreement only "
-                    "(episode-to-episode std ~12%); seed-identical parity is tests/test_step_gpu.py"}
+    fx_path = dts.fixture_path(controller, N_SAMPLES, HORIZON)
+    if not os.path.exists(fx_path):
+        return {"unavailable": f"{os.path.relpath(fx_path, ROOT)} missing: run tools/oracle_tracking_stats.py"}
+    fx = np.load(fx_path)
+    ora = fx["err_pos"]
+    dev_err, status = dts.production_arm(controller, N_SAMPLES, HORIZON, float(fx["lam"]), ora.shape[0], ora.shape[1], device=device)
+    out = dts.summarise(dev_err, ora)
+    out.update({"metric": "mean ||pos_tar - pos|| over 300-step episodes (m), mean over episodes", "protocol": "tools/tracking_protocol.py",
+                "oracle_fixture": os.path.relpath(fx_path, ROOT), "device_numeric_status_nonzero": int(np.count_nonzero(status)),
+                "note": "same trajectories / initial states / observation noise per episode, independent sample streams; identical-eps "
+                        "parity is tests/test_tracking_gpu.py"})
+    return out
 
 
 def run_reference(args):
@@ -442,6 +549,7 @@ def run_reference(args):
     if rank != 0:
         return
     K, W = args.steps, args.warmup
+    world = max(1, args.gpus)
     # all host threads this process may use: torchrun exports OMP_NUM_THREADS=1, which would silently serialise the
     # OpenMP loops of the port (libgomp reads it when the library is first loaded, i.e. below) and LAPACK/BLAS
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -452,26 +560,34 @@ def run_reference(args):
         threadpool_limits(limits=ncores)
     except Exception:
         pass
-    # states: a fixed synthetic sequence (no GPU needed): hover-ish noisy states along a zigzag reference
-    from oracle import oracle_np as o
-
-    p = o.EnvParams()
-    rng = np.random.default_rng(100)
-    s = o.reset_env(TASK, p, rng, dtype=np.float32, zero_disturb=True)
-    states, times = [], []
-    hover = o.hover_mean(1, p)[0]
-    for _ in range(32):
-        ns = o.noisy_state(s, p, rng)
-        states.append(o.state_to_vec24(ns))
-        times.append(ns.time)
-        s, _, _, _ = o.env_step(s, hover + rng.normal(0, 0.1, 4), p, rng, "none")
-    cb = cpu_baseline(np.stack(states), np.array(times), (s.pos_traj, s.vel_traj), mode_name=args.controller, max_steps=K, warmup=W)
-    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": cb["steps"],
-           "warmup": W, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    # The GPU arm at --gpus G steps G independent environments (one per GPU); the host steps the SAME G environments one after the
+    # other (same generator, seeds 100 .. 100 + G - 1), so value = environment-steps / s is a ratio of equal work at every G.
+    per_env = []
+    for r in range(world):
+        st, tm, trajs, _ = synthetic_states(min(W + K, 290), 100 + r)
+        per_env.append((st, tm, trajs[0]))
+    steps_each = max(1, K // world)
+    t_used, done, cb = 0.0, 0, None
+    for r in range(world):
+        st, tm, traj = per_env[r]
+        cb = cpu_baseline(st, tm, traj, mode_name=args.controller, max_steps=steps_each, warmup=W if r == 0 else 0)
+        t_used += cb["seconds"]
+        done += cb["steps"]
+    value = done / t_used
+    cb.update({"value": value, "steps": done, "seconds": t_used,
+               "sample": f"{done} full MPC steps ({args.controller}, N={N_SAMPLES}, H={HORIZON}) over {world} environment(s) stepped one after "
+                         f"the other on the host, {cb['sample'].split(') of ', 1)[-1]}"})
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+           "warmup": W, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{args.controller} {TASK} N={N_SAMPLES} H={HORIZON} u_dim=4 lam={LAM} sigma=0.5, 1 env per GPU",
-                      "note": "CPU restatement of the reference algorithm (JAX cannot be installed offline); timed steps capped at ~170 s"},
-           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                      "controller": args.controller, "n_samples": N_SAMPLES, "horizon": HORIZON, "envs_per_gpu": 1,
+                      "parallelism": "env-replicas x%d (no collective)" % world,
+                      "inputs": "noisy states of a PID closed loop on a zigzag reference (host-generated, shared with --impl reference)",
+                      "equal_work": f"the {world} environment(s) of the GPU arm, stepped sequentially on all host cores: steps/s here is "
+                                    "environment-steps per second, the same unit as the GPU arm's whole-job value",
+                      "note": "CPU restatement of the reference algorithm (JAX cannot be installed offline)"},
+           "cpu_baseline": cb, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
 
@@ -482,7 +598,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--controller", default="covo-online", choices=["covo-online", "covo-offline", "mppi"])
-    ap.add_argument("--shard", default="env", choices=["env", "nsample"])
+    ap.add_argument("--no-subrecords", action="store_true", help="skip the nsample_shard / env_batch records (configs 4 and 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

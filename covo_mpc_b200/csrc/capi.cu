@@ -474,7 +474,7 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
         h->pipeline_enabled = !(pe && pe[0] == '0');
         h->pipeline_forced = pe && pe[0] == '2';
         const char* se = getenv("COVO_SIGMA");
-        h->sigma_dense = (se && cfg->mode != COVO_MODE_MPPI) ? (strcmp(se, "dense") == 0 ? 1 : strcmp(se, "dense-gj") == 0 ? 2 : 0) : 0;
+        h->sigma_dense = (se && cfg->mode != COVO_MODE_MPPI) ? (strcmp(se, "dense") == 0 ? 1 : strcmp(se, "dense-gj") == 0 ? 2 : strcmp(se, "dense-gjb") == 0 ? 3 : 0) : 0;
         if (h->sigma_dense) {
             A(h->dense_scal.alloc(E * 4));
             A(h->dense_X.alloc(E * sigma_dense_scratch_floats(h->n)));

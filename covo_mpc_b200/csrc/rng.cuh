@@ -36,9 +36,11 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k
 }
 
 // four standard normals for (global sample i, column block b): columns 4b .. 4b+3
+// `env`: environment index of a batched handle (counter word 3), so that the environments of a batch draw independent fields;
+// environment 0 is the stream of a single-environment handle
 __device__ __forceinline__ void philox_normal4(unsigned long long seed, uint32_t stream, uint32_t i, uint32_t b,
-                                               float z[4]) {
-    uint32_t c[4] = {i, b, stream, 0u};
+                                               float z[4], uint32_t env = 0u) {
+    uint32_t c[4] = {i, b, stream, env};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     const float s = 2.3283064365386963e-10f;  // 2^-32
     float u0 = (__uint2float_rn(c[0]) + 0.5f) * s, u1 = (__uint2float_rn(c[1]) + 0.5f) * s;

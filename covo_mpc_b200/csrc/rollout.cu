@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
             int s = i % TS, b = i / TS;
             float z[4] = {0.f, 0.f, 0.f, 0.f};
             if (s < n_valid && b * 4 < n)
-                philox_normal4(a.seed, a.stream, (uint32_t)(a.sample_offset + tile0 + s), (uint32_t)b, z);
+                philox_normal4(a.seed, a.stream, (uint32_t)(a.sample_offset + tile0 + s), (uint32_t)b, z, (uint32_t)env);
 #pragma unroll
             for (int j = 0; j < 4; ++j) sm.tile[(b * 4 + j) * TSP + s] = z[j];
         }

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sigma.cuh"
@@ -104,6 +105,8 @@ struct DenseArgs {
     float* cov;          // [E][n][n]
     const double* zolo;  // the ladder of sigma.cu: [kZoloLadder][2][kZoloPoles]
     int* status;         // [E]
+    float* Asym = nullptr;       // optional [E][n][n]: (R + R^T)/2 written by the Lanczos kernel for the factorisation kernels
+    long long* prof = nullptr;   // optional clock64() stamps (slots 48..)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -178,6 +181,341 @@ __global__ void __launch_bounds__(TL, 1) lanczos_kernel(const DenseArgs a) {
         const double ev = warp_multisect(al, be, k, gl - pad, gu + pad, low ? 1 : k);
         if ((tid & 31) == 0) a.scal[(long long)env * 4 + (low ? 0 : 1)] = ev;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// D1' lanczos2_kernel -- the same recurrence on 1024 threads with the matrix held ONCE, as float64, in shared memory
+// (packed lower triangle, 161 KB at n = 200): no float -> double conversion inside the loop (F2F.F64.F32 runs at a quarter of the
+// DFMA rate and made D1 a 150 us kernel), and every element is read once per product and used twice (y_i += a_ij v_j and
+// y_j += a_ij v_i).  One warp owns ~7 rows (paired short + long); lane l owns the columns l, l + 32, ...: the row sums are
+// reduced across the warp with an 8-value butterfly (9 shuffles instead of 40), the column sums stay lane-private and are added
+// across warps through a [32][n] buffer in a fixed order (bit-reproducible).
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int TL2 = 1024;
+
+// Eight values per lane -> their warp totals: value q = 4 b4 + 2 b3 + b2 (bits of the lane index) ends up in every lane of that group
+__device__ __forceinline__ double multi_reduce8(double (&x)[8], int lane) {
+    bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const double send = hi ? x[q] : x[q + 4], keep = hi ? x[q + 4] : x[q];
+        x[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    hi = (lane & 8) != 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const double send = hi ? x[q] : x[q + 2], keep = hi ? x[q + 2] : x[q];
+        x[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    hi = (lane & 4) != 0;
+    {
+        const double send = hi ? x[0] : x[1], keep = hi ? x[1] : x[0];
+        x[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    x[0] += __shfl_xor_sync(0xffffffffu, x[0], 2);
+    x[0] += __shfl_xor_sync(0xffffffffu, x[0], 1);
+    return x[0];
+}
+
+struct Lanczos2Smem {
+    int nrow_doubles, nslot;
+    size_t bytes;
+    bool fits;
+};
+// Row i (group g = i / 32) holds its STRICTLY lower elements zero-padded to 32 (g + 1) doubles, so that the product loop has
+// compile-time trip counts and no predicates; the diagonal lives apart.
+__host__ __device__ inline int lz_row_offset(int i) {
+    const int g = i >> 5;
+    return 512 * g * (g + 1) + 32 * (i & 31) * (g + 1);
+}
+// column-sum slots: as many of the 32 warps as fit next to the matrix (16 at n = 200: two hand-over passes)
+__host__ __device__ inline Lanczos2Smem lanczos2_layout(int n) {
+    Lanczos2Smem L;
+    L.nrow_doubles = lz_row_offset(n);
+    const size_t fixed = ((size_t)L.nrow_doubles + 3 * 224 + 4 * 32 + 2 * kLanczosMax) * sizeof(double) + 64;
+    L.nslot = 32;
+    while (L.nslot > 1 && fixed + (size_t)L.nslot * n * sizeof(double) > (size_t)227 * 1024) L.nslot >>= 1;
+    L.bytes = fixed + (size_t)L.nslot * n * sizeof(double);
+    L.fits = L.bytes <= (size_t)227 * 1024 && L.nslot >= 8;
+    return L;
+}
+
+__device__ __forceinline__ int lz_row_of(int warp, int k) { return (k & 1) ? 32 * k + 31 - warp : 32 * k + warp; }
+
+// number of eigenvalues of the k x k Lanczos matrix below x: sign changes of the leading principal minors p_i(x), the
+// division-free form of the Sturm sequence (al, be pre-scaled so that nothing over- or underflows in k <= 32 steps)
+__device__ __forceinline__ int sturm_count_poly(const double* al, const double* b2, int k, double x) {
+    double pm = 1.0, p = al[0] - x;
+    int sg_prev = 1, cnt = 0;
+    {
+        const int sg = (p > 0.0) ? 1 : ((p < 0.0) ? -1 : -sg_prev);
+        cnt += (sg != sg_prev);
+        sg_prev = sg;
+    }
+    for (int i = 1; i < k; ++i) {
+        const double pn = fma(al[i] - x, p, -b2[i - 1] * pm);
+        pm = p;
+        p = pn;
+        const int sg = (p > 0.0) ? 1 : ((p < 0.0) ? -1 : -sg_prev);
+        cnt += (sg != sg_prev);
+        sg_prev = sg;
+    }
+    return cnt;
+}
+
+#define DENSE_STAMP(slot)                                                        \
+    do {                                                                         \
+        if (a.prof && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.prof[slot] = clock64(); \
+    } while (0)
+
+// one row of the product: KK + 1 chunks of 32 columns (compile-time), no predicates: the padding is zero
+template <int KK>
+__device__ __forceinline__ double lz_row_product(const double* __restrict__ Ai, const double (&vr)[7], double vi, double (&cacc)[7], int lane) {
+    double r = 0.0;
+#pragma unroll
+    for (int c = 0; c <= KK; ++c) {
+        const double aij = Ai[lane + 32 * c];
+        r = fma(aij, vr[c], r);
+        cacc[c] = fma(aij, vi, cacc[c]);
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(TL2, 1) lanczos2_kernel(const DenseArgs a) {
+    COVO_DYN_SMEM(smraw);
+    const int n = a.n, tid = threadIdx.x, env = blockIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Lanczos2Smem L = lanczos2_layout(n);
+    double* Ad = reinterpret_cast<double*>(smraw);  // padded strictly-lower rows, row i at lz_row_offset(i)
+    double* dg = Ad + L.nrow_doubles;               // [224] diagonal
+    double* v = dg + 224;                           // [224] current vector, zero beyond n
+    double* rowy = v + 224;                         // [224] row-part of the product
+    double* red = rowy + 224;                       // [2][32] alpha partials (by iteration parity), [2][32] beta partials
+    double* al = red + 4 * 32;                      // [kLanczosMax]
+    double* be = al + kLanczosMax;                  // [kLanczosMax]
+    double* cpart = be + kLanczosMax;               // [nslot][n]
+    const float* Rg = a.R + (long long)env * n * n;
+    float* Asym = a.Asym ? a.Asym + (long long)env * n * n : nullptr;
+    DENSE_STAMP(48);
+    // (R + R^T)/2 in float32 as controllers/covo.py:117 forms it, then widened.  Both passes read global memory along rows
+    // (7 independent loads in flight per thread): pass 1 the lower triangle with the diagonal (row i, columns j <= i), pass 2 the
+    // upper one (row j, columns i > j) into the same slots.
+    for (int i = warp; i < n; i += 32) {
+        double* Ai = Ad + lz_row_offset(i);
+        const int len = 32 * ((i >> 5) + 1);
+        float x[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            const int j = lane + 32 * c;
+            x[c] = (j <= i) ? Rg[(long long)i * n + j] : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            const int j = lane + 32 * c;
+            if (j < len) Ai[j] = (j < i) ? (double)x[c] : 0.0;
+            if (j == i) {
+                dg[i] = (double)x[c];
+                if (Asym) Asym[(long long)i * n + i] = x[c];
+            }
+        }
+    }
+    if (tid >= n && tid < 224) dg[tid] = 0.0;
+    __syncthreads();
+    for (int j = warp; j < n; j += 32) {
+        float x[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            const int i = j + 1 + lane + 32 * c;
+            x[c] = (i < n) ? Rg[(long long)j * n + i] : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            const int i = j + 1 + lane + 32 * c;
+            if (i < n) {
+                double* p = Ad + lz_row_offset(i) + j;
+                const float sym = 0.5f * ((float)*p + x[c]);
+                *p = (double)sym;
+                if (Asym) {  // the symmetrised matrix for the factorisation kernels (they then read rows only)
+                    Asym[(long long)j * n + i] = sym;
+                    Asym[(long long)i * n + j] = sym;
+                }
+            }
+        }
+    }
+    double vj = 0.0, vprev = 0.0, dj = 0.0;  // thread j < n keeps its components in registers
+    if (tid < 224) {
+        double x0 = 0.0;
+        if (tid < n) x0 = cos(0.37 * (double)tid + 0.1) + 0.01 * (double)tid / (double)n;
+        vj = x0;
+    }
+    {  // normalise the start vector
+        const double p2 = warp_sum_d(vj * vj);
+        if (lane == 0) red[warp] = p2;
+        __syncthreads();  // (also orders the matrix stores before the first product)
+        double s2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) s2 += red[q];
+        vj /= sqrt(s2);
+    }
+    if (tid < 224) {
+        v[tid] = vj;
+        dj = dg[tid];
+    }
+    // the rows of this warp (paired short + long) and where they start
+    int roff[7];
+#pragma unroll
+    for (int kk = 0; kk < 7; ++kk) {
+        const int i = lz_row_of(warp, kk);
+        roff[kk] = (i < n) ? lz_row_offset(i) : -1;
+    }
+    const int passes = 32 / L.nslot, my_pass = warp / L.nslot;
+    double* cp = cpart + (warp % L.nslot) * n;
+    __syncthreads();
+    DENSE_STAMP(49);
+    const int k_max = min(kLanczosMax, n);
+    int k = 0;
+    double beta = 0.0;
+    for (int it = 0; it < k_max; ++it) {
+        // ---- y = A v: strictly lower part, used twice (row sums and column sums) ----------------------------------------------
+        double vr[7], cacc[7], rs[8];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            vr[c] = v[lane + 32 * c];
+            cacc[c] = 0.0;
+        }
+        rs[0] = (roff[0] >= 0) ? lz_row_product<0>(Ad + roff[0], vr, v[lz_row_of(warp, 0)], cacc, lane) : 0.0;
+        rs[1] = (roff[1] >= 0) ? lz_row_product<1>(Ad + roff[1], vr, v[lz_row_of(warp, 1)], cacc, lane) : 0.0;
+        rs[2] = (roff[2] >= 0) ? lz_row_product<2>(Ad + roff[2], vr, v[lz_row_of(warp, 2)], cacc, lane) : 0.0;
+        rs[3] = (roff[3] >= 0) ? lz_row_product<3>(Ad + roff[3], vr, v[lz_row_of(warp, 3)], cacc, lane) : 0.0;
+        rs[4] = (roff[4] >= 0) ? lz_row_product<4>(Ad + roff[4], vr, v[lz_row_of(warp, 4)], cacc, lane) : 0.0;
+        rs[5] = (roff[5] >= 0) ? lz_row_product<5>(Ad + roff[5], vr, v[lz_row_of(warp, 5)], cacc, lane) : 0.0;
+        rs[6] = (roff[6] >= 0) ? lz_row_product<6>(Ad + roff[6], vr, v[lz_row_of(warp, 6)], cacc, lane) : 0.0;
+        rs[7] = 0.0;
+        const double tot = multi_reduce8(rs, lane);
+        {
+            const int q = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            const int i = lz_row_of(warp, q);
+            if ((lane & 3) == 0 && q < 7 && i < n) rowy[i] = tot;
+        }
+        for (int ps = 0; ps < passes; ++ps) {
+            if (my_pass == ps) {
+#pragma unroll
+                for (int c = 0; c < 7; ++c) {
+                    const int j = lane + 32 * c;
+                    if (j < n) cp[j] = (ps == 0) ? cacc[c] : cp[j] + cacc[c];
+                }
+            }
+            __syncthreads();
+        }
+        // ---- three-term recurrence, thread j --------------------------------------------------------------------------
+        double w = 0.0;
+        if (tid < n) {
+            double s0 = rowy[tid], s1 = dj * vj, s2 = 0.0, s3 = 0.0;
+            for (int q = 0; q < L.nslot; q += 4) {
+                s0 += cpart[q * n + tid];
+                s1 += cpart[(q + 1) * n + tid];
+                s2 += cpart[(q + 2) * n + tid];
+                s3 += cpart[(q + 3) * n + tid];
+            }
+            w = ((s0 + s1) + (s2 + s3)) - beta * vprev;
+        }
+        double* ra = red + (it & 1) * 32;
+        double* rb = red + 64 + (it & 1) * 32;
+        if (warp < 7) {
+            const double pa = warp_sum_d(w * vj);
+            if (lane == 0) ra[warp] = pa;
+        }
+        __syncthreads();
+        double alpha = 0.0;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) alpha += ra[q];
+        w -= alpha * vj;
+        if (warp < 7) {
+            const double pb = warp_sum_d(w * w);
+            if (lane == 0) rb[warp] = pb;
+        }
+        __syncthreads();
+        double b2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) b2 += rb[q];
+        beta = sqrt(b2);
+        if (tid == 0) {
+            al[it] = alpha;
+            be[it] = beta;
+        }
+        k = it + 1;
+        if (!(beta > 1e-200)) break;  // invariant subspace found (uniform across the CTA)
+        if (tid < n) {
+            vprev = vj;
+            vj = w / beta;
+            v[tid] = vj;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    DENSE_STAMP(50);
+    // Extreme eigenvalues of the k x k Lanczos matrix by multisection of the (division-free) Sturm count.  Threads 0..127 look for
+    // the smallest with FOUR trial shifts each (513-way, 5 rounds: 513^5 = 3.5e13 of the Gershgorin interval; the four independent
+    // recurrences hide the DFMA latency); threads 128..255 bracket the largest to 129^-2 (it only selects the approximation interval).
+    if (tid < 256) {
+        double gl = 1e300, gu = -1e300;
+        for (int i = 0; i < k; ++i) {
+            const double r = ((i > 0) ? fabs(be[i - 1]) : 0.0) + ((i < k - 1) ? fabs(be[i]) : 0.0);
+            gl = fmin(gl, al[i] - r);
+            gu = fmax(gu, al[i] + r);
+        }
+        const double pad = 1e-12 * fmax(fabs(gl), fabs(gu)) + 1e-300;
+        gl -= pad;
+        gu += pad;
+        // scaled copy: (T - gl) / (gu - gl) has its spectrum in [0, 1]
+        double* sal = cpart;             // [32]  (the column buffers are dead)
+        double* sb2 = cpart + 32;        // [32]
+        int* first = reinterpret_cast<int*>(cpart + 64);  // [2][8]
+        const double isc = 1.0 / (gu - gl);
+        if (tid < k) {
+            sal[tid] = (al[tid] - gl) * isc;
+            const double b = be[tid] * isc;
+            sb2[tid] = b * b;
+        }
+        COVO_NAMED_BARRIER(2, 256);
+        const bool low = tid < 128;
+        const int t = tid & 127, target = low ? 1 : k;
+        double lo = 0.0, hi = 1.0;
+        for (int round = 0; round < 5; ++round) {
+            int f_mine = 1 << 20;  // first trial index (of this thread's) whose count reaches the target
+            double step;
+            if (low) {
+                step = (hi - lo) / 513.0;
+#pragma unroll
+                for (int u = 3; u >= 0; --u) {
+                    const int idx = 4 * t + u;  // trial shifts in increasing order across (t, u)
+                    if (sturm_count_poly(sal, sb2, k, lo + step * (double)(idx + 1)) >= target) f_mine = idx;
+                }
+            } else {
+                step = (hi - lo) / 129.0;
+                if (round < 2 && sturm_count_poly(sal, sb2, k, lo + step * (double)(t + 1)) >= target) f_mine = t;
+            }
+            // first index over the 4 warps of this search (monotone predicate: the minimum over threads)
+            int fm = f_mine;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) fm = min(fm, __shfl_xor_sync(0xffffffffu, fm, o));
+            int* fr = first + (round & 1) * 8;
+            if (lane == 0) fr[warp] = fm;
+            COVO_NAMED_BARRIER(2, 256);
+            const int w0 = low ? 0 : 4;
+            const int f = min(min(fr[w0], fr[w0 + 1]), min(fr[w0 + 2], fr[w0 + 3]));
+            const int nsub = low ? 512 : 128;
+            if (low || round < 2) {
+                if (f >= nsub) {
+                    lo = lo + step * (double)nsub;  // the crossing is in the last sub-interval
+                } else {
+                    hi = lo + step * (double)(f + 1);
+                    lo = lo + step * (double)f;
+                }
+            }
+        }
+        if (t == 0) a.scal[(long long)env * 4 + (low ? 0 : 1)] = gl + (low ? 0.5 * (lo + hi) : hi) * (gu - gl);
+    }
+    DENSE_STAMP(51);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -564,6 +902,352 @@ __global__ void __launch_bounds__(TG, 1) gj_inverse_kernel(const DenseArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// D2'' gjb_inverse_kernel (COVO_SIGMA=dense-gjb): the same in-place Gauss-Jordan sweep, BLOCKED (8 pivots per step) and spread over
+// a 2-CTA cluster per pole, the matrix resident in registers.  Sweeping the index block K with P = A_KK:
+//     A_IJ -= A_IK P^-1 A_KJ,   A_KJ <- P^-1 A_KJ =: G,   A_IK <- -A_IK P^-1,   A_KK <- P^-1.
+// With the sign convention of D2' the matrix is symmetric on the unswept index set and ANTI-symmetric between swept and unswept
+// indices, so the column panel is the row panel again: A_iK = sigma(i) (A_Ki)^T, sigma = -1 for swept i.  Everything a step needs
+// therefore follows from the 8 raw pivot rows (8 x n) alone:
+//     A_ij -= sigma(i) sum_s raw[s][i] G[s][j],    row K_s <- G[s][:],   column K_s <- -sigma(i) G[s][i],   block KK <- P^-1.
+// Roles (640 threads per CTA):
+//   * 16 UPDATE warps hold the matrix: thread (ty = warp, tx = lane) owns rows ty + 16 (rank + 2 a'), a' < 8 (row pairs packed for
+//     FFMA2) and columns tx + 32 b, b < 7.  Per step: 224 FFMA2 per thread against 28 + 16 vector loads.
+//   * 4 SOLVER warps run one block ahead: they wait for the raw rows of block m + 1 (published through distributed shared memory with
+//     st.async, completion counted by an mbarrier -- no fences, no cluster barrier), invert the 8 x 8 pivot block on one warp
+//     (lane = two entries, 8 shuffle-driven pivots), build G = P^-1 raw and the signed multiplier table, while the update warps
+//     are still applying block m.
+//   * look-ahead: after the barrier that opens step m, the warps that own the rows of block m + 1 (one row per warp) apply step m to
+//     that row first (56 FMAs, same operation order as the full update, so the values are bit-identical) and publish it.
+// Flow control: the raw panels live in a ring of 4 slots.  Blocks are owned in pairs (tile = 16 rows = 2 blocks, tiles alternate
+// between the CTAs), so a CTA can run at most 3 blocks ahead of its peer before it needs a panel from it: 4 slots never collide.
+// Cost model at n = 200: 25 steps x max(update 1800 cycles, solver chain ~1600) instead of 200 steps x 1100.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int GB_CL = 2;     // CTAs per matrix
+constexpr int GB_UT = 512;   // update threads
+constexpr int GB_ST = 128;   // solver threads
+constexpr int GB_T = GB_UT + GB_ST;
+constexpr int GB_NP = 224;   // padded order: 14 row tiles of 16, 7 column slots of 32
+constexpr int GB_RS = 256;   // row stride of a raw panel (the unused 8th row slot addresses rows up to 255)
+constexpr int GB_SLOTS = 4;
+
+struct GjbSmem {
+    float raw[GB_SLOTS][8][GB_RS];  // pivot-row panels [s][j]
+    float G[2][4][GB_NP][2];        // [parity][s / 2][j][s & 1]
+    float2 Mneg[2][16][4][8];       // [parity][ty][row pair q][s]: (-sigma(i0) raw[s][i0], -sigma(i1) raw[s][i1]); 0 for pivot rows
+    float Pinv[2][64];
+    float piv[GB_NP];
+    unsigned long long rawbar[GB_SLOTS];
+    int bad;
+};
+
+#if defined(COVO_CPU_EMU)
+__device__ __forceinline__ unsigned gjb_rank() { return emu_cluster_rank(); }
+__device__ __forceinline__ void gjb_cluster_sync() { emu_cluster_barrier(); }
+__device__ __forceinline__ void gjb_mbar_init(unsigned long long* b, int count) { emu_mbar_init(b, count); }
+__device__ __forceinline__ void gjb_mbar_expect(unsigned long long* b, int bytes) { emu_mbar_expect_tx(b, bytes); }
+__device__ __forceinline__ void gjb_mbar_wait(unsigned long long* b, unsigned parity) { emu_mbar_wait(b, parity); }
+__device__ __forceinline__ void gjb_send(float* dst_local, unsigned rank, float v, unsigned long long* bar_local) {
+    emu_dsmem_st_signal(dst_local, rank, v, bar_local);
+}
+__device__ __forceinline__ float gjb_rcp(float x) { return 1.0f / x; }
+#else
+__device__ __forceinline__ unsigned gjb_s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned gjb_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void gjb_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void gjb_mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gjb_s32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gjb_mbar_expect(unsigned long long* b, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(gjb_s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gjb_mbar_wait(unsigned long long* b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GJB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GJB_DONE_%=;\n"
+        "bra GJB_WAIT_%=;\n"
+        "GJB_DONE_%=:\n"
+        "}\n" ::"r"(gjb_s32(b)),
+        "r"(parity)
+        : "memory");
+}
+// one float into the shared memory of CTA `rank` of the cluster (same offset as here), 4 bytes completed on that CTA's mbarrier
+__device__ __forceinline__ void gjb_send(float* dst_local, unsigned rank, float v, unsigned long long* bar_local) {
+    unsigned d, b;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(gjb_s32(dst_local)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(b) : "r"(gjb_s32(bar_local)), "r"(rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(d), "f"(v), "r"(b) : "memory");
+}
+__device__ __forceinline__ float gjb_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * fmaf(-x, r, 2.0f);
+}
+#endif
+
+__global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a) {
+    COVO_DYN_SMEM(smraw);
+    GjbSmem& sm = *reinterpret_cast<GjbSmem*>(smraw);
+    const int n = a.n, tid = threadIdx.x, env = blockIdx.y, pole = blockIdx.x / GB_CL;
+    const int rank = (int)gjb_rank();
+    const int nblk = (n + 7) >> 3;
+    const double lam_min = a.scal[(long long)env * 4 + 0], lam_max = a.scal[(long long)env * 4 + 1];
+    int lad = 0;
+    {
+        const double Mb = 1.02 * (lam_max - lam_min) + kOffset;
+        double Mi = kOffset * (1.0 - 1e-7) * 256.0;
+        while (lad < kZoloLadder - 1 && Mi < Mb) {
+            Mi *= 4.0;
+            ++lad;
+        }
+        if (Mi < Mb && tid == 0 && rank == 0) a.status[env] = 1;
+    }
+    const double* zt = a.zolo + (size_t)lad * 2 * kZoloPoles;
+    const bool want_logdet = pole == kZoloPoles;
+    const double shift = (kOffset - lam_min) + (want_logdet ? 0.0 : zt[pole]);
+    const float wj = want_logdet ? 0.f : (float)zt[kZoloPoles + pole];
+    if (tid == 0) {
+        sm.bad = 0;
+        for (int q = 0; q < GB_SLOTS; ++q) gjb_mbar_init(&sm.rawbar[q], 1);
+#if !defined(COVO_CPU_EMU)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+    }
+    for (int i = tid; i < GB_SLOTS * 8 * GB_RS; i += GB_T) (&sm.raw[0][0][0])[i] = 0.f;
+    gjb_cluster_sync();  // barriers initialised and panels zeroed everywhere before anybody publishes
+
+    if (tid >= GB_UT) {
+        // ================================================ solver warps ================================================
+        const int sidx = tid - GB_UT, lane = sidx & 31, swarp = sidx >> 5;
+        for (int m = 0; m < nblk; ++m) {
+            const int slot = m & (GB_SLOTS - 1), par = m & 1, K0 = 8 * m;
+            if (sidx == 0) gjb_mbar_expect(&sm.rawbar[slot], 8 * GB_NP * 4);
+            gjb_mbar_wait(&sm.rawbar[slot], (unsigned)((m / GB_SLOTS) & 1));
+            const float(*rw)[GB_RS] = sm.raw[slot];
+            if (swarp == 0) {
+                // P^-1 by an in-place Gauss-Jordan sweep of the 8 x 8 block: lane = (row r, columns c0, c0 + 1)
+                const int r = lane >> 2, c0 = (lane & 3) * 2;
+                float x0 = rw[r][K0 + c0], x1 = rw[r][K0 + c0 + 1];
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp) {
+                    const float mine = (sp & 1) ? x1 : x0;
+                    const float p = __shfl_sync(0xffffffffu, mine, (sp << 2) | (sp >> 1));
+                    const float prs = __shfl_sync(0xffffffffu, mine, (r << 2) | (sp >> 1));   // P[r][sp]
+                    const float ps0 = __shfl_sync(0xffffffffu, x0, (sp << 2) | (lane & 3));   // P[sp][c0]
+                    const float ps1 = __shfl_sync(0xffffffffu, x1, (sp << 2) | (lane & 3));   // P[sp][c0 + 1]
+                    if (lane == 0) {
+                        sm.piv[K0 + sp] = p;
+                        if (!(p > 0.f)) sm.bad = 1;
+                    }
+                    const float rinv = gjb_rcp(p);
+                    if (r == sp) {
+                        x0 = (c0 == sp) ? rinv : ps0 * rinv;
+                        x1 = (c0 + 1 == sp) ? rinv : ps1 * rinv;
+                    } else {
+                        const float f = prs * rinv;
+                        x0 = (c0 == sp) ? -f : fmaf(-f, ps0, x0);
+                        x1 = (c0 + 1 == sp) ? -f : fmaf(-f, ps1, x1);
+                    }
+                }
+                sm.Pinv[par][r * 8 + c0] = x0;
+                sm.Pinv[par][r * 8 + c0 + 1] = x1;
+            } else {
+                // signed, negated, pair-packed multipliers of this CTA's rows
+                for (int e = sidx - 32; e < 16 * 4 * 8; e += GB_ST - 32) {
+                    const int ty = e >> 5, q = (e >> 3) & 3, sp = e & 7;
+                    float2 val;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int tile = rank + GB_CL * (2 * q + h), i = ty + 16 * tile;
+                        float x = 0.f;
+                        if (tile < GB_NP / 16 && !(i >= K0 && i < K0 + 8)) x = (i < K0) ? rw[sp][i] : -rw[sp][i];
+                        if (h) val.y = x;
+                        else val.x = x;
+                    }
+                    sm.Mneg[par][ty][q][sp] = val;
+                }
+            }
+            COVO_NAMED_BARRIER(1, GB_ST);
+            for (int j = sidx; j < GB_NP; j += GB_ST) {
+                float col[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) col[t] = rw[t][j];
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp) {
+                    float g = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) g = fmaf(sm.Pinv[par][sp * 8 + t], col[t], g);
+                    sm.G[par][sp >> 1][j][sp & 1] = g;
+                }
+            }
+            __syncthreads();  // opens step m for the update warps
+        }
+    } else {
+        // ================================================ update warps ================================================
+        const int tx = tid & 31, ty = tid >> 5;
+        const float* Ag = a.Asym ? a.Asym + (long long)env * n * n : nullptr;
+        const float* Rg = a.R + (long long)env * n * n;
+        float2 acc[4][7];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int b = 0; b < 7; ++b) {
+                float v2[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int tile = rank + GB_CL * (2 * q + h), i = ty + 16 * tile, j = tx + 32 * b;
+                    float v = (i == j && tile < GB_NP / 16) ? 1.f : 0.f;  // identity padding: never coupled, pivots 1
+                    if (i < n && j < n) {
+                        v = Ag ? Ag[(long long)i * n + j] : 0.5f * (Rg[(long long)i * n + j] + Rg[(long long)j * n + i]);
+                        if (i == j) v = (float)((double)v + shift);
+                    }
+                    v2[h] = v;
+                }
+                acc[q][b] = make_float2(v2[0], v2[1]);
+            }
+        // block 0 lives in tile 0 = CTA 0, row slot 0 (.x of pair 0): warps 0..7 publish their row
+        if (rank == 0 && ty < 8) {
+#pragma unroll
+            for (int b = 0; b < 7; ++b)
+#pragma unroll
+                for (int r = 0; r < GB_CL; ++r) gjb_send(&sm.raw[0][ty][tx + 32 * b], (unsigned)r, acc[0][b].x, &sm.rawbar[0]);
+        }
+        for (int m = 0; m < nblk; ++m) {
+            __syncthreads();  // G, multipliers and P^-1 of block m are in place; everybody is done with step m - 1
+            const int par = m & 1, K0 = 8 * m;
+            const float2* mrow = &sm.Mneg[par][ty][0][0];
+            // ---- look-ahead: the rows of block m + 1 after step m, published before the bulk of the update ----------------
+            if (m + 1 < nblk) {
+                const int tile1 = (m + 1) >> 1;
+                if (rank == tile1 % GB_CL && (ty >> 3) == ((m + 1) & 1)) {
+                    const int a1 = tile1 / GB_CL, q1 = a1 >> 1, h1 = a1 & 1, i = ty + 16 * tile1;
+                    float tmp[7];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q == q1) {
+#pragma unroll
+                            for (int b = 0; b < 7; ++b) tmp[b] = h1 ? acc[q][b].y : acc[q][b].x;
+                        }
+#pragma unroll
+                    for (int sp = 0; sp < 8; ++sp) {
+                        const float2 m2 = mrow[q1 * 8 + sp];
+                        const float mm = h1 ? m2.y : m2.x;
+#pragma unroll
+                        for (int b = 0; b < 7; ++b) tmp[b] = fmaf(mm, sm.G[par][sp >> 1][tx + 32 * b][sp & 1], tmp[b]);
+                    }
+                    if ((tx & ~7) == (K0 & 31)) {  // its entries in the pivot columns of step m: -G[s][i]  (i is unswept)
+                        const int sc = tx - (K0 & 31), b0 = K0 >> 5;
+                        const float v = -sm.G[par][sc >> 1][i][sc & 1];
+#pragma unroll
+                        for (int b = 0; b < 7; ++b)
+                            if (b == b0) tmp[b] = v;
+                    }
+                    const int slot1 = (m + 1) & (GB_SLOTS - 1);
+#pragma unroll
+                    for (int b = 0; b < 7; ++b)
+#pragma unroll
+                        for (int r = 0; r < GB_CL; ++r)
+                            gjb_send(&sm.raw[slot1][ty & 7][tx + 32 * b], (unsigned)r, tmp[b], &sm.rawbar[slot1]);
+                }
+            }
+            // ---- the rank-8 update of everything this thread owns --------------------------------------------------------
+#pragma unroll
+            for (int qt = 0; qt < 4; ++qt) {  // two of the eight s at a time
+                float2 g2[7];
+#pragma unroll
+                for (int b = 0; b < 7; ++b) g2[b] = *reinterpret_cast<const float2*>(&sm.G[par][qt][tx + 32 * b][0]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 m4 = *reinterpret_cast<const float4*>(&mrow[q * 8 + 2 * qt]);
+                    const float2 ma = make_float2(m4.x, m4.y), mb = make_float2(m4.z, m4.w);
+#pragma unroll
+                    for (int b = 0; b < 7; ++b) {
+                        acc[q][b] = __ffma2_rn(ma, make_float2(g2[b].x, g2[b].x), acc[q][b]);
+                        acc[q][b] = __ffma2_rn(mb, make_float2(g2[b].y, g2[b].y), acc[q][b]);
+                    }
+                }
+            }
+            // ---- fix-ups: pivot rows <- G (P^-1 inside the block), pivot columns <- -sigma(i) G[s][i] ---------------------
+            const int tile0 = m >> 1;
+            const bool pivot_warp = (rank == tile0 % GB_CL) && ((ty >> 3) == (m & 1));
+            const int q0 = (tile0 / GB_CL) >> 1, h0 = (tile0 / GB_CL) & 1;
+            if (pivot_warp) {
+                const int sr = ty & 7;
+#pragma unroll
+                for (int b = 0; b < 7; ++b) {
+                    const int j = tx + 32 * b;
+                    const float v = (j >= K0 && j < K0 + 8) ? sm.Pinv[par][sr * 8 + (j - K0)] : sm.G[par][sr >> 1][j][sr & 1];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q == q0) {
+                            if (h0) acc[q][b].y = v;
+                            else acc[q][b].x = v;
+                        }
+                }
+            }
+            if ((tx & ~7) == (K0 & 31)) {
+                const int sc = tx - (K0 & 31), b0 = K0 >> 5;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int tile = rank + GB_CL * (2 * q + h), i = ty + 16 * tile;
+                        if (tile < GB_NP / 16 && !(i >= K0 && i < K0 + 8)) {
+                            const float g = sm.G[par][sc >> 1][i][sc & 1];
+                            const float v = (i < K0) ? g : -g;
+#pragma unroll
+                            for (int b = 0; b < 7; ++b)
+                                if (b == b0) {
+                                    if (h) acc[q][b].y = v;
+                                    else acc[q][b].x = v;
+                                }
+                        }
+                    }
+            }
+        }
+        // ---- results ---------------------------------------------------------------------------------------------------------
+        if (!want_logdet) {
+            float* Xg = a.Xbuf + ((long long)env * kZoloPoles + pole) * n * n;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int b = 0; b < 7; ++b) {
+                    const int j = tx + 32 * b;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int tile = rank + GB_CL * (2 * q + h), i = ty + 16 * tile;
+                        if (tile < GB_NP / 16 && i < n && j <= i) Xg[(long long)i * n + j] = wj * (h ? acc[q][b].y : acc[q][b].x);
+                    }
+                }
+        } else if (rank == 0 && ty < 7) {  // log det A = sum of the logarithms of the scalar pivots (both CTAs hold all of them)
+            double lp = 0.0;
+            const int i = tx + 32 * ty;
+            if (i < n) lp = log((double)sm.piv[i]);
+            lp = warp_sum_d(lp);
+            double* red = reinterpret_cast<double*>(&sm.G[0][0][0][0]);  // dead: every step is over for these warps' inputs
+            COVO_NAMED_BARRIER(3, 224);
+            if (tx == 0) red[ty] = lp;
+            COVO_NAMED_BARRIER(3, 224);
+            if (tid == 0) {
+                double sum = 0.0;
+                for (int w = 0; w < 7; ++w) sum += red[w];
+                a.scal[(long long)env * 4 + 2] = sum;
+            }
+        }
+        if (tid == 0 && sm.bad) a.status[env] = 2;
+    }
+    gjb_cluster_sync();  // nobody leaves while a peer could still be sending to it
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // D3
 // ---------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) combine_kernel(const DenseArgs a) {
@@ -605,14 +1289,43 @@ cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, in
     a.cov = s.cov;
     a.zolo = s.zolo;
     a.status = s.status;
-    static size_t conf1[32] = {}, conf2[32] = {};
-    const size_t smem1 = (size_t)(2 * a.n + 8 + 2 * kLanczosMax) * sizeof(double) + (size_t)a.n * (a.n + 1) * sizeof(float);
-    cudaError_t e = ensure_smem_attr(lanczos_kernel, smem1, conf1);
-    if (e != cudaSuccess) return e;
-    lanczos_kernel<<<n_env, TL, smem1, st>>>(a);
+    a.prof = s.prof;
+    static size_t conf1[32] = {}, conf2[32] = {}, conf3[32] = {};
+    cudaError_t e;
+    const bool lz_v1 = getenv("COVO_LANCZOS_V1") || !lanczos2_layout(a.n).fits;
+    a.Asym = lz_v1 ? nullptr : s.F;  // the symmetrised matrix, written by the Lanczos kernel (F is unused on this path)
+    if (lz_v1) {  // n > 200: the padded float64 rows no longer fit next to the column buffers
+        const size_t smem1 = (size_t)(2 * a.n + 8 + 2 * kLanczosMax) * sizeof(double) + (size_t)a.n * (a.n + 1) * sizeof(float);
+        e = ensure_smem_attr(lanczos_kernel, smem1, conf1);
+        if (e != cudaSuccess) return e;
+        lanczos_kernel<<<n_env, TL, smem1, st>>>(a);
+    } else {
+        const size_t smem3 = lanczos2_layout(a.n).bytes;
+        e = ensure_smem_attr(lanczos2_kernel, smem3, conf3);
+        if (e != cudaSuccess) return e;
+        lanczos2_kernel<<<n_env, TL2, smem3, st>>>(a);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (variant == 2) {  // register-resident Gauss-Jordan
+    if (variant == 3) {  // blocked Gauss-Jordan on a 2-CTA cluster per pole
+        static size_t conf4[32] = {};
+        e = ensure_smem_attr(gjb_inverse_kernel, sizeof(GjbSmem), conf4);
+        if (e != cudaSuccess) return e;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(GB_CL * (kZoloPoles + 1), n_env);
+        cfg.blockDim = dim3(GB_T);
+        cfg.dynamicSmemBytes = sizeof(GjbSmem);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = GB_CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, gjb_inverse_kernel, a);
+        if (e != cudaSuccess) return e;
+    } else if (variant == 2) {  // register-resident Gauss-Jordan
         gj_inverse_kernel<14><<<dim3(kZoloPoles + 1, n_env), TG, 1024 * sizeof(float), st>>>(a);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

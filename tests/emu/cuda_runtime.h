@@ -73,6 +73,15 @@ inline Block*& cur() {
     static Block* b = nullptr;
     return b;
 }
+inline ucontext_t*& sched_ptr() {  // the scheduler context fibers yield to (one CTA, or all CTAs of a cluster)
+    static ucontext_t* p = nullptr;
+    return p;
+}
+struct Cluster;
+inline Cluster*& cur_cluster() {
+    static Cluster* c = nullptr;
+    return c;
+}
 inline long long& progress() {  // barrier arrivals + thread exits: a scheduler pass without any is a deadlock
     static long long p = 0;
     return p;
@@ -80,7 +89,7 @@ inline long long& progress() {  // barrier arrivals + thread exits: a scheduler 
 
 inline void yield() {
     Block* b = cur();
-    swapcontext(&b->ctx[b->cur], &b->sched);
+    swapcontext(&b->ctx[b->cur], sched_ptr());
 }
 
 inline void wait(Barrier& bar, int expected) {
@@ -106,12 +115,11 @@ inline void trampoline() {
     Block* b = cur();
     b->body();
     b->done[b->cur] = 1;
-    swapcontext(&b->ctx[b->cur], &b->sched);
+    swapcontext(&b->ctx[b->cur], sched_ptr());
 }
 
 // run ONE CTA: body() is executed once per thread (fiber)
-inline void run_block(Block& b, size_t stack_bytes = 256 * 1024) {
-    cur() = &b;
+inline void prepare_block(Block& b, ucontext_t* sched, size_t stack_bytes) {
     const int n = b.n_threads;
     b.ctx.resize(n);
     b.stacks.clear();
@@ -123,9 +131,16 @@ inline void run_block(Block& b, size_t stack_bytes = 256 * 1024) {
         getcontext(&b.ctx[t]);
         b.ctx[t].uc_stack.ss_sp = b.stacks[t].get();
         b.ctx[t].uc_stack.ss_size = stack_bytes;
-        b.ctx[t].uc_link = &b.sched;
+        b.ctx[t].uc_link = sched;
         makecontext(&b.ctx[t], (void (*)())trampoline, 0);
     }
+}
+
+inline void run_block(Block& b, size_t stack_bytes = 256 * 1024) {
+    cur() = &b;
+    sched_ptr() = &b.sched;
+    const int n = b.n_threads;
+    prepare_block(b, &b.sched, stack_bytes);
     int live = n;
     while (live > 0) {
         const long long before = progress();
@@ -144,6 +159,44 @@ inline void run_block(Block& b, size_t stack_bytes = 256 * 1024) {
         }
     }
     cur() = nullptr;
+}
+
+// A thread-block cluster: the CTAs run interleaved (all fibers of all CTAs under one scheduler), each with its own shared memory;
+// distributed-shared-memory stores and the cluster barrier go through this object.
+struct Cluster {
+    std::vector<Block*> blocks;
+    Barrier all;
+    ucontext_t sched;
+};
+
+inline void run_cluster(Cluster& c, size_t stack_bytes = 256 * 1024) {
+    cur_cluster() = &c;
+    sched_ptr() = &c.sched;
+    int live = 0;
+    for (Block* b : c.blocks) {
+        prepare_block(*b, &c.sched, stack_bytes);
+        live += b->n_threads;
+    }
+    while (live > 0) {
+        const long long before = progress();
+        for (Block* b : c.blocks)
+            for (int t = 0; t < b->n_threads; ++t) {
+                if (b->done[t]) continue;
+                cur() = b;
+                b->cur = t;
+                swapcontext(&c.sched, &b->ctx[t]);
+                if (b->done[t]) {
+                    --live;
+                    ++progress();
+                }
+            }
+        if (live > 0 && progress() == before) {
+            fprintf(stderr, "emu: cluster deadlock -- %d threads wait at barriers that can never complete\n", live);
+            abort();
+        }
+    }
+    cur() = nullptr;
+    cur_cluster() = nullptr;
 }
 
 struct Idx {
@@ -241,5 +294,77 @@ inline void emu_launch(Kernel kernel, dim3 grid, int threads, size_t smem_bytes,
             b.smem.assign(smem_bytes + 64, 0xCD);  // poison: reads of never-written shared memory show up as garbage
             b.body = [&]() { kernel(args); };
             emu::run_block(b);
+        }
+}
+
+// ---- thread-block clusters: distributed shared memory, mbarriers with transaction counts, cluster barrier --------------------
+struct EmuMbar {  // lives in the 8 bytes of the kernel's mbarrier object
+    int tx;                 // outstanding transaction bytes (may go negative: data can arrive before the expectation is posted)
+    signed char pending;    // outstanding arrivals of the current phase
+    signed char count;      // arrivals per phase
+    unsigned short phase;
+};
+static_assert(sizeof(EmuMbar) == 8, "EmuMbar must fit an mbarrier object");
+inline void emu_mbar_check(EmuMbar* m) {
+    if (m->pending == 0 && m->tx == 0) {
+        ++m->phase;
+        m->pending = m->count;
+        ++emu::progress();
+    }
+}
+inline void emu_mbar_init(void* bar, int count) {
+    EmuMbar* m = reinterpret_cast<EmuMbar*>(bar);
+    m->tx = 0;
+    m->pending = m->count = (signed char)count;
+    m->phase = 0;
+}
+inline void emu_mbar_expect_tx(void* bar, int bytes) {  // mbarrier.arrive.expect_tx
+    EmuMbar* m = reinterpret_cast<EmuMbar*>(bar);
+    m->tx += bytes;
+    --m->pending;
+    emu_mbar_check(m);
+}
+inline void emu_mbar_wait(void* bar, unsigned parity) {  // mbarrier.try_wait.parity loop
+    EmuMbar* m = reinterpret_cast<EmuMbar*>(bar);
+    while ((m->phase & 1u) == (parity & 1u)) emu::yield();
+}
+inline unsigned emu_cluster_rank() { return emu::cur()->block_idx.x % (unsigned)emu::cur_cluster()->blocks.size(); }
+// st.async to CTA `rank` of the cluster: the value lands at the same shared-memory offset there and completes 4 bytes on that CTA's mbarrier
+inline void emu_dsmem_st_signal(float* local_addr, unsigned rank, float v, void* local_bar) {
+    emu::Block* me = emu::cur();
+    emu::Block* peer = emu::cur_cluster()->blocks[rank];
+    const size_t off = reinterpret_cast<unsigned char*>(local_addr) - me->smem.data();
+    const size_t boff = reinterpret_cast<unsigned char*>(local_bar) - me->smem.data();
+    memcpy(peer->smem.data() + off, &v, 4);
+    EmuMbar* m = reinterpret_cast<EmuMbar*>(peer->smem.data() + boff);
+    m->tx -= 4;
+    emu_mbar_check(m);
+}
+inline void emu_cluster_barrier() {
+    emu::Cluster* c = emu::cur_cluster();
+    int total = 0;
+    for (emu::Block* b : c->blocks) total += b->n_threads;
+    emu::wait(c->all, total);
+}
+
+// launch helper for clustered grids: clusters of `cluster_x` consecutive CTAs along x, one cluster at a time
+template <class Kernel, class Args>
+inline void emu_launch_cluster(Kernel kernel, dim3 grid, int cluster_x, int threads, size_t smem_bytes, const Args& args) {
+    for (unsigned by = 0; by < grid.y; ++by)
+        for (unsigned bx0 = 0; bx0 < grid.x; bx0 += cluster_x) {
+            std::vector<std::unique_ptr<emu::Block>> owned;
+            emu::Cluster c;
+            for (int r = 0; r < cluster_x; ++r) {
+                owned.emplace_back(new emu::Block());
+                emu::Block& b = *owned.back();
+                b.grid = grid;
+                b.block_dim = dim3(threads);
+                b.block_idx = dim3(bx0 + r, by);
+                b.n_threads = threads;
+                b.smem.assign(smem_bytes + 64, 0xCD);
+                b.body = [&]() { kernel(args); };
+                c.blocks.push_back(&b);
+            }
+            emu::run_cluster(c);
         }
 }

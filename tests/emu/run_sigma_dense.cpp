@@ -16,9 +16,15 @@ extern "C" int emu_sigma_dense(int n, float sample_sigma, const float* R, const 
     a.cov = cov;
     a.zolo = zolo;
     a.status = status;
+    a.prof = nullptr;
+    a.Asym = nullptr;
     const size_t smem1 = (size_t)(2 * n + 8 + 2 * kLanczosMax) * sizeof(double) + (size_t)n * (n + 1) * sizeof(float);
-    emu_launch(lanczos_kernel, dim3(1), TL, smem1, a);
-    if (variant == 2) {
+    if ((variant & 16) || !lanczos2_layout(n).fits) emu_launch(lanczos_kernel, dim3(1), TL, smem1, a);  // the first Lanczos kernel
+    else emu_launch(lanczos2_kernel, dim3(1), TL2, lanczos2_layout(n).bytes, a);
+    variant &= 15;
+    if (variant == 3) {
+        emu_launch_cluster(gjb_inverse_kernel, dim3(GB_CL * (kZoloPoles + 1), 1), GB_CL, GB_T, sizeof(GjbSmem), a);
+    } else if (variant == 2) {
         emu_launch(gj_inverse_kernel<14>, dim3(kZoloPoles + 1, 1), TG, 1024 * sizeof(float), a);
     } else {
         const size_t smem2 = ((size_t)n * n + 2 * 8 * a.n_pad + 64 + a.n_pad) * sizeof(float) + 16;

@@ -159,7 +159,7 @@ def test_maximum_horizon_full_step():
 @pytest.mark.skipif(__import__("os").environ.get("COVO_TEST_DENSE") != "1",
                     reason="experimental dense optimize_sigma (csrc/sigma_dense.cu): written after the round-1 GPU budget was spent, "
                            "not yet run on hardware; enable with COVO_TEST_DENSE=1")
-@pytest.mark.parametrize("variant", ["dense", "dense-gj"])
+@pytest.mark.parametrize("variant", ["dense", "dense-gj", "dense-gjb"])
 @pytest.mark.parametrize("H", [8, 20, 50])
 def test_dense_sigma_path_matches_oracle(monkeypatch, H, variant):
     """COVO_SIGMA=dense: Lanczos + shifted factorisations + combine vs the float64 eigen-decomposition."""

@@ -1,0 +1,44 @@
+"""In-kernel phase breakdown (clock64 stamps of CTA 0) of the tridiagonalisation-free optimize_sigma kernels (csrc/sigma_dense.cu), next
+to the per-kernel CUDA-event times.  Development tool: `COVO_SIGMA=dense-gj python tools/dense_profile.py` on a GPU box."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("COVO_SIGMA", "dense-gj")
+
+import bench  # noqa: E402
+from covo_mpc_b200 import _lib  # noqa: E402
+
+
+def main():
+    import torch
+
+    env, states, times, traj = bench.record_states(12, 100, "covo-online", device=0)
+    cfg = _lib.default_config()
+    cfg.mode, cfg.n_samples, cfg.horizon, cfg.traj_len, cfg.device = _lib.MODE_COVO_ONLINE, 8192, 50, int(traj[0].shape[0]), 0
+    h = _lib.Handle(cfg)
+    h.set_reference(traj[0][None], traj[1][None])
+    for i in range(4):
+        h.step(states[i], times[i:i + 1])
+    h.set_profiling(True)
+    acc = np.zeros(6)
+    for i in range(4, 10):
+        h.step(states[i], times[i:i + 1])
+        acc += h.kernel_ms()
+    h.set_profiling(False)
+    print(os.environ["COVO_SIGMA"], "kernel us:", [round(float(v) / 6 * 1e3, 1) for v in acc])
+    h.phase_clocks(True)
+    h.step(states[10], times[10:11])
+    torch.cuda.synchronize()
+    c = h.phase_clocks(True, read=True)
+    mhz = 1965.0
+    d = lambda a, b: round((c[b] - c[a]) / mhz, 2)
+    print("lanczos: load", d(48, 49), "iterations", d(49, 50), "multisection", d(50, 51), "us")
+    print("raw stamps 48..59:", [int(x) for x in c[48:60]])
+
+
+if __name__ == "__main__":
+    main()

@@ -37,7 +37,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for v in ("", "dense", "dense-gj"):
+        for v in ("", "dense-gj", "dense-gjb"):
             env = dict(os.environ)
             if v:
                 env["COVO_SIGMA"] = v
