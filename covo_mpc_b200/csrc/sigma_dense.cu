@@ -21,6 +21,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "sigma.cuh"
@@ -31,6 +32,7 @@ namespace {
 
 constexpr double kOffset = 1e-2;  // controllers/covo.py:121
 constexpr int kLanczosMax = 32;
+constexpr int kLanczosSteps = 24;  // steps of the cluster kernel (see lanczos_cluster_kernel)
 constexpr int TL = 256;   // lanczos_kernel threads
 constexpr int TD = 1024;  // shifted_inverse_kernel threads
 
@@ -902,44 +904,9 @@ __global__ void __launch_bounds__(TG, 1) gj_inverse_kernel(const DenseArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// D2'' gjb_inverse_kernel (COVO_SIGMA=dense-gjb): the same in-place Gauss-Jordan sweep, BLOCKED (8 pivots per step) and spread over
-// a 2-CTA cluster per pole, the matrix resident in registers.  Sweeping the index block K with P = A_KK:
-//     A_IJ -= A_IK P^-1 A_KJ,   A_KJ <- P^-1 A_KJ =: G,   A_IK <- -A_IK P^-1,   A_KK <- P^-1.
-// With the sign convention of D2' the matrix is symmetric on the unswept index set and ANTI-symmetric between swept and unswept
-// indices, so the column panel is the row panel again: A_iK = sigma(i) (A_Ki)^T, sigma = -1 for swept i.  Everything a step needs
-// therefore follows from the 8 raw pivot rows (8 x n) alone:
-//     A_ij -= sigma(i) sum_s raw[s][i] G[s][j],    row K_s <- G[s][:],   column K_s <- -sigma(i) G[s][i],   block KK <- P^-1.
-// Roles (640 threads per CTA):
-//   * 16 UPDATE warps hold the matrix: thread (ty = warp, tx = lane) owns rows ty + 16 (rank + 2 a'), a' < 8 (row pairs packed for
-//     FFMA2) and columns tx + 32 b, b < 7.  Per step: 224 FFMA2 per thread against 28 + 16 vector loads.
-//   * 4 SOLVER warps run one block ahead: they wait for the raw rows of block m + 1 (published through distributed shared memory with
-//     st.async, completion counted by an mbarrier -- no fences, no cluster barrier), invert the 8 x 8 pivot block on one warp
-//     (lane = two entries, 8 shuffle-driven pivots), build G = P^-1 raw and the signed multiplier table, while the update warps
-//     are still applying block m.
-//   * look-ahead: after the barrier that opens step m, the warps that own the rows of block m + 1 (one row per warp) apply step m to
-//     that row first (56 FMAs, same operation order as the full update, so the values are bit-identical) and publish it.
-// Flow control: the raw panels live in a ring of 4 slots.  Blocks are owned in pairs (tile = 16 rows = 2 blocks, tiles alternate
-// between the CTAs), so a CTA can run at most 3 blocks ahead of its peer before it needs a panel from it: 4 slots never collide.
-// Cost model at n = 200: 25 steps x max(update 1800 cycles, solver chain ~1600) instead of 200 steps x 1100.
+// Thread-block-cluster primitives shared by D1'' and D2'': distributed shared memory stores that carry their own completion
+// signal (st.async ... mbarrier::complete_tx), mbarrier waits, the cluster barrier.  tests/emu provides CPU stand-ins.
 // ---------------------------------------------------------------------------------------------------------------------------
-constexpr int GB_CL = 2;     // CTAs per matrix
-constexpr int GB_UT = 512;   // update threads
-constexpr int GB_ST = 128;   // solver threads
-constexpr int GB_T = GB_UT + GB_ST;
-constexpr int GB_NP = 224;   // padded order: 14 row tiles of 16, 7 column slots of 32
-constexpr int GB_RS = 256;   // row stride of a raw panel (the unused 8th row slot addresses rows up to 255)
-constexpr int GB_SLOTS = 4;
-
-struct GjbSmem {
-    float raw[GB_SLOTS][8][GB_RS];  // pivot-row panels [s][j]
-    float G[2][4][GB_NP][2];        // [parity][s / 2][j][s & 1]
-    float2 Mneg[2][16][4][8];       // [parity][ty][row pair q][s]: (-sigma(i0) raw[s][i0], -sigma(i1) raw[s][i1]); 0 for pivot rows
-    float Pinv[2][64];
-    float piv[GB_NP];
-    unsigned long long rawbar[GB_SLOTS];
-    int bad;
-};
-
 #if defined(COVO_CPU_EMU)
 __device__ __forceinline__ unsigned gjb_rank() { return emu_cluster_rank(); }
 __device__ __forceinline__ void gjb_cluster_sync() { emu_cluster_barrier(); }
@@ -949,6 +916,13 @@ __device__ __forceinline__ void gjb_mbar_wait(unsigned long long* b, unsigned pa
 __device__ __forceinline__ void gjb_send(float* dst_local, unsigned rank, float v, unsigned long long* bar_local) {
     emu_dsmem_st_signal(dst_local, rank, v, bar_local);
 }
+__device__ __forceinline__ void gjb_send64(double* dst_local, unsigned rank, double v, unsigned long long* bar_local) {
+    emu_dsmem_st_signal64(dst_local, rank, v, bar_local);
+}
+__device__ __forceinline__ void gjb_bulk_send(void* dst_local, const void* src_local, unsigned bytes, unsigned rank, unsigned long long* bar_local) {
+    emu_dsmem_bulk_copy(dst_local, src_local, bytes, rank, bar_local);
+}
+__device__ __forceinline__ void gjb_fence_async_proxy() {}
 __device__ __forceinline__ float gjb_rcp(float x) { return 1.0f / x; }
 #else
 __device__ __forceinline__ unsigned gjb_s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -986,12 +960,409 @@ __device__ __forceinline__ void gjb_send(float* dst_local, unsigned rank, float 
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(b) : "r"(gjb_s32(bar_local)), "r"(rank));
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(d), "f"(v), "r"(b) : "memory");
 }
+__device__ __forceinline__ void gjb_send64(double* dst_local, unsigned rank, double v, unsigned long long* bar_local) {
+    unsigned d, b;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(gjb_s32(dst_local)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(b) : "r"(gjb_s32(bar_local)), "r"(rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(d), "l"(__double_as_longlong(v)), "r"(b)
+                 : "memory");
+}
+// One bulk copy (multiple of 16 bytes, 16-byte aligned) from this CTA's shared memory into CTA `rank` (same offset as dst_local),
+// counted into that CTA's mbarrier.  Measured: publishing a 224-float row as 224 st.async messages made the DSMEM message rate
+// (~2 cycles per message per SM) the bottleneck of D2'' (3584 messages = 7000 cycles per block step); one copy per row and
+// destination is 16 messages per step.
+__device__ __forceinline__ void gjb_bulk_send(void* dst_local, const void* src_local, unsigned bytes, unsigned rank, unsigned long long* bar_local) {
+    unsigned d, b;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(gjb_s32(dst_local)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(b) : "r"(gjb_s32(bar_local)), "r"(rank));
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "r"(gjb_s32(src_local)),
+                 "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void gjb_fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ float gjb_rcp(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r * fmaf(-x, r, 2.0f);
 }
 #endif
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// D1'' lanczos_cluster_kernel -- the Lanczos recurrence on an 8-CTA cluster.  Measured on B200: scalar float64 instructions issue at
+// ~16 lanes / clock / SM, so a 200 x 200 product is >= 2500 cycles on one SM whatever the layout (D1 and D1' both sit at ~3.5 us per
+// iteration); the only way down is more SMs.  CTA c keeps rows [c R, (c + 1) R) of (R + R^T)/2 in REGISTERS as float64, four
+// threads per row (columns 4 k + p), and per iteration
+//     y = A w / beta  (w: last iteration's unnormalised vector, complete in every CTA's shared memory),
+//     w' = y - beta v_prev,  warp partials of w'.v and w'.w',
+// then ONE exchange: every row leader sends its w' and every warp its two partials to all 8 CTAs with st.async (the stores count
+// themselves into the receiver's mbarrier: no fence, no cluster barrier), everybody waits for its own mbarrier and finishes
+// alpha, beta^2 = w'.w' - alpha^2 and w = w' - alpha v redundantly.  The all-to-all makes every iteration an implicit barrier,
+// so two buffers (iteration parity) are enough.  CTA 0 then finds the smallest Ritz value: five rounds of 128-way multisection
+// (division-free Sturm counts: the bracket is 2.8e-11 of the Gershgorin interval wide) and a short Newton polish from its left end
+// (monotone for a real-rooted polynomial).  Required accuracy: |error| << 1e-2 * 2e-5 = 2e-7 ABSOLUTE (the offset 1e-2 of
+// controllers/covo.py:121 sets the scale), not relative to |R|.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int LC_CL = 8;      // CTAs
+constexpr int LC_T = 128;     // threads per CTA: 32 rows x 4 column phases
+constexpr int LC_KMAX = 56;   // columns per thread (n <= 224)
+
+struct LcSmem {
+    double v[2][224];                 // normalised Lanczos vector v_k (by iteration parity), all n entries, zero beyond n
+    double u[2][224];                 // u = A v_k - beta_{k-1} v_{k-1}, gathered from all CTAs (by iteration parity)
+    double part[2][LC_CL * 4][2];     // (u.v_k, u.u) partial of every warp of the cluster
+    double al[kLanczosMax], be[kLanczosMax];
+    double sal[kLanczosMax], sb2[kLanczosMax];
+    unsigned long long bar[2];
+    int first[2][4];
+    float salf[kLanczosMax], sb2f[kLanczosMax];
+};
+
+// float32 twin of sturm_count_poly for the first, coarse multisection rounds (the bracket is widened afterwards by far more than
+// its rounding error can move a crossing)
+__device__ __forceinline__ int sturm_count_poly_f32(const float* al, const float* b2, int k, float x) {
+    float pm = 1.0f, p = al[0] - x;
+    int sg_prev = 1, cnt = 0;
+    {
+        const int sg = (p > 0.f) ? 1 : ((p < 0.f) ? -1 : -sg_prev);
+        cnt += (sg != sg_prev);
+        sg_prev = sg;
+    }
+    for (int i = 1; i < k; ++i) {
+        const float pn = fmaf(al[i] - x, p, -b2[i - 1] * pm);
+        pm = p;
+        p = pn;
+        const int sg = (p > 0.f) ? 1 : ((p < 0.f) ? -1 : -sg_prev);
+        cnt += (sg != sg_prev);
+        sg_prev = sg;
+    }
+    return cnt;
+}
+
+// Remote addresses of one thread's three exchange targets in CTA `rank`: its row entry of u, its warp's partial pair, the barrier
+// (all for parity 0; parity 1 is a fixed byte offset away) -- mapa once, outside the loop.
+#if defined(COVO_CPU_EMU)
+struct LcRemote {
+    double* u;
+    double* part;
+    unsigned long long* bar;
+    unsigned rank;
+};
+__device__ __forceinline__ LcRemote lc_remote(double* u, double* part, unsigned long long* bar, unsigned rank) { return LcRemote{u, part, bar, rank}; }
+__device__ __forceinline__ void lc_send(const LcRemote& r, int what, int parity, double v) {
+    double* dst = (what == 0) ? r.u + parity * 224 : r.part + parity * (LC_CL * 4 * 2) + (what - 1);
+    emu_dsmem_st_signal64(dst, r.rank, v, r.bar + parity);
+}
+#else
+struct LcRemote {
+    unsigned u, part, bar;
+};
+__device__ __forceinline__ LcRemote lc_remote(double* u, double* part, unsigned long long* bar, unsigned rank) {
+    LcRemote r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r.u) : "r"(gjb_s32(u)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r.part) : "r"(gjb_s32(part)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r.bar) : "r"(gjb_s32(bar)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void lc_send(const LcRemote& r, int what, int parity, double v) {
+    const unsigned dst = (what == 0) ? r.u + parity * 224 * 8 : r.part + parity * (LC_CL * 4 * 2 * 8) + (what - 1) * 8;
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst), "l"(__double_as_longlong(v)),
+                 "r"(r.bar + parity * 8)
+                 : "memory");
+}
+#endif
+
+// characteristic polynomial of the scaled k x k Lanczos matrix and its derivative at x (three-term recurrences)
+__device__ __forceinline__ void lc_poly_newton(const double* al, const double* b2, int k, double x, double& p_out, double& dp_out) {
+    double pm = 1.0, p = al[0] - x, dm = 0.0, d = -1.0;
+    for (int i = 1; i < k; ++i) {
+        const double t = al[i] - x;
+        const double pn = fma(t, p, -b2[i - 1] * pm);
+        const double dn = fma(t, d, -b2[i - 1] * dm) - p;
+        pm = p;
+        p = pn;
+        dm = d;
+        d = dn;
+    }
+    p_out = p;
+    dp_out = d;
+}
+
+__global__ void __launch_bounds__(LC_T, 1) lanczos_cluster_kernel(const DenseArgs a) {
+    COVO_DYN_SMEM(smraw);
+    LcSmem& sm = *reinterpret_cast<LcSmem*>(smraw);
+    const int n = a.n, tid = threadIdx.x, env = blockIdx.y, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)gjb_rank();
+    const int R = (n + LC_CL - 1) / LC_CL;      // rows per CTA (25 at n = 200)
+    const int rl = tid >> 2, ph = tid & 3;      // local row, column phase
+    const int row = rank * R + rl;
+    const bool has_row = rl < R && row < n;
+    const bool leader = has_row && ph == 0;
+    const int kc = (n + 3) >> 2;                // columns per thread
+    const float* Rg = a.R + (long long)env * n * n;
+    float* Asym = a.Asym ? a.Asym + (long long)env * n * n : nullptr;
+    DENSE_STAMP(48);
+    if (tid == 0) {
+        gjb_mbar_init(&sm.bar[0], 1);
+        gjb_mbar_init(&sm.bar[1], 1);
+#if !defined(COVO_CPU_EMU)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+    }
+    // rows of (R + R^T)/2 (float32, controllers/covo.py:117) widened into registers
+    double ar[LC_KMAX];
+    {
+        float xa[LC_KMAX], xb[LC_KMAX];  // all loads in flight before the first store (the compiler must assume Asym aliases R)
+#pragma unroll
+        for (int k = 0; k < LC_KMAX; ++k) {
+            const int j = 4 * k + ph;
+            const bool ok = has_row && j < n;
+            xa[k] = ok ? __ldg(Rg + (long long)row * n + j) : 0.f;
+            xb[k] = ok ? __ldg(Rg + (long long)j * n + row) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < LC_KMAX; ++k) {
+            const int j = 4 * k + ph;
+            const float x = 0.5f * (xa[k] + xb[k]);
+            if (Asym && has_row && j < n) Asym[(long long)row * n + j] = x;
+            ar[k] = (double)x;
+        }
+    }
+    // start vector: every CTA builds and normalises all of it (same arithmetic everywhere)
+    {
+        double x[7], s2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            const int j = lane + 32 * c;
+            // fixed start vector with a component along every eigenvector in practice: 1 + a 16-bit multiplicative hash of j (no
+            // float64 transcendental: cos() alone cost 4 us here)
+            x[c] = (j < n) ? 1.0 + (double)(float)((((unsigned)j + 1u) * 2654435761u >> 8) & 0xffffu) * (1.0 / 65536.0) : 0.0;
+            s2 = fma(x[c], x[c], s2);
+        }
+        const double inv = 1.0 / sqrt(warp_sum_d(s2));
+        if (warp == 0) {
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                sm.v[0][lane + 32 * c] = x[c] * inv;
+                sm.v[1][lane + 32 * c] = 0.0;
+            }
+        }
+    }
+    __syncthreads();
+    double vj = has_row ? sm.v[0][row] : 0.0, vprev = 0.0;  // row leaders keep v_k[row], v_{k-1}[row]
+    const int n_warps_total = LC_CL * 4;
+    const int tx_bytes = n * 8 + n_warps_total * 16;
+    gjb_cluster_sync();  // barriers initialised everywhere before the first send
+    DENSE_STAMP(49);
+    // 24 steps: over 72 scenarios (three tasks, six seeds, four flight phases, H = 50) the smallest Ritz value is within 2e-8 of
+    // lambda_min after 20 steps and 5e-12 after 24 (needed: << 2e-7 absolute); every step is a dependent ~1 us exchange
+    const int k_max = min(kLanczosSteps, n);
+    int kdone = 0;
+    double beta_prev = 0.0;
+    LcRemote rem[LC_CL];  // where this thread's row entry / this warp's partial slot / the barrier live in every CTA of the cluster
+#pragma unroll
+    for (int r = 0; r < LC_CL; ++r)
+        rem[r] = lc_remote(&sm.u[0][has_row ? row : 0], &sm.part[0][rank * 4 + warp][0], &sm.bar[0], (unsigned)r);
+    for (int it = 0; it < k_max; ++it) {
+        const int pc = it & 1;  // v_k is in v[pc]; this iteration's exchange uses u[pc], part[pc], bar[pc]
+        // y_row = (A v_k)_row: four threads per row, four independent chains each
+        // (dependent float64 operations are ~40 cycles apart on this pipe: eight chains of seven, not four of thirteen)
+        double ac[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        const double* vv = sm.v[pc];
+#pragma unroll
+        for (int k = 0; k < LC_KMAX; k += 8) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (k + e < kc) ac[e] = fma(ar[k + e], vv[4 * (k + e) + ph], ac[e]);
+        }
+        double y = ((ac[0] + ac[1]) + (ac[2] + ac[3])) + ((ac[4] + ac[5]) + (ac[6] + ac[7]));
+        y += __shfl_xor_sync(0xffffffffu, y, 1);
+        y += __shfl_xor_sync(0xffffffffu, y, 2);
+        // u = y - beta_{k-1} v_{k-1} (row leaders); partials of u.v_k and u.u over the 8 rows of the warp
+        const double u = leader ? y - beta_prev * vprev : 0.0;
+        double pa = u * vj, pu = u * u;
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            pa += __shfl_xor_sync(0xffffffffu, pa, o);
+            pu += __shfl_xor_sync(0xffffffffu, pu, o);
+        }
+        if (tid == 0) gjb_mbar_expect(&sm.bar[pc], tx_bytes);
+        long long tq0 = 0;
+        if (a.prof && tid == 0 && rank == 0 && blockIdx.y == 0) tq0 = clock64();
+        // the exchange: u of this row and the warp's partials to every CTA of the cluster (this one included)
+#pragma unroll
+        for (int r = 0; r < LC_CL; ++r) {
+            if (leader) lc_send(rem[r], 0, pc, u);
+            if (lane == 0) {
+                lc_send(rem[r], 1, pc, pa);
+                lc_send(rem[r], 2, pc, pu);
+            }
+        }
+        gjb_mbar_wait(&sm.bar[pc], (unsigned)((it >> 1) & 1));
+        if (a.prof && tid == 0 && rank == 0 && blockIdx.y == 0) a.prof[52] = (it == 0 ? 0 : a.prof[52]) + (clock64() - tq0);  // send + wait
+        // alpha = u.v_k, beta_k^2 = |u - alpha v_k|^2 = u.u - alpha^2: every warp sums the 32 partial pairs with the same butterfly
+        double qa = (lane < n_warps_total) ? sm.part[pc][lane][0] : 0.0;
+        double qu = (lane < n_warps_total) ? sm.part[pc][lane][1] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {  // the two sums interleaved: five levels of (shuffle + add) each
+            qa += __shfl_xor_sync(0xffffffffu, qa, o);
+            qu += __shfl_xor_sync(0xffffffffu, qu, o);
+        }
+        const double alpha = qa;
+        double b2 = qu - alpha * alpha;
+        if (b2 < 1e-3 * qu) {
+            // |u|^2 - alpha^2 cancels when beta << |alpha| (Krylov space nearly exhausted, small n): form |u - alpha v_k|^2 directly.
+            // Every CTA holds all of u and v_k, so this needs no exchange; the branch is uniform across the cluster.
+            double ps = 0.0;
+            for (int j = tid; j < n; j += LC_T) {
+                const double wj = sm.u[pc][j] - alpha * vv[j];
+                ps = fma(wj, wj, ps);
+            }
+            ps = warp_sum_d(ps);
+            double* red = &sm.sal[0];  // free until the Ritz stage
+            if (lane == 0) red[warp] = ps;
+            __syncthreads();
+            b2 = (red[0] + red[1]) + (red[2] + red[3]);
+            __syncthreads();
+        }
+        // 1 / beta and beta without float64 sqrt / division (each a chain of ~15 dependent float64 operations at ~40 cycles): float32
+        // rsqrt seed, two Newton steps (1e-7 -> 1e-14 -> rounding), six dependent operations
+        double beta_new = 0.0, ib = 0.0;
+        if (b2 > 1e-280) {
+            const double sc = (b2 < 1e-30) ? 1e60 : 1.0;  // keep the seed inside the float32 range
+            const double bs = b2 * sc;
+            double r = (double)rsqrtf((float)bs);
+            r = r * fma(-0.5 * bs, r * r, 1.5);
+            r = r * fma(-0.5 * bs, r * r, 1.5);
+            ib = r * ((b2 < 1e-30) ? 1e30 : 1.0);
+            beta_new = b2 * ib;
+        }
+        if (tid == 0) {
+            sm.al[it] = alpha;
+            sm.be[it] = beta_new;
+        }
+        kdone = it + 1;
+        if (!(beta_new > 1e-200)) break;  // invariant subspace (uniform across the cluster: every CTA sees the same data)
+        // v_{k+1} = (u - alpha v_k) / beta_k: every CTA forms all of it (two entries per thread)
+        for (int j = tid; j < n; j += LC_T) sm.v[pc ^ 1][j] = (sm.u[pc][j] - alpha * vv[j]) * ib;
+        if (leader) {
+            const double vn = (u - alpha * vj) * ib;
+            vprev = vj;
+            vj = vn;
+        }
+        beta_prev = beta_new;
+        __syncthreads();
+    }
+    __syncthreads();
+    DENSE_STAMP(50);
+    // ---- smallest Ritz value (CTA 0) ---------------------------------------------------------------------------------------
+    if (rank == 0) {
+        const int k = kdone;
+        double gl = 1e300, gu = -1e300;
+        for (int i = 0; i < k; ++i) {
+            const double r = ((i > 0) ? fabs(sm.be[i - 1]) : 0.0) + ((i < k - 1) ? fabs(sm.be[i]) : 0.0);
+            gl = fmin(gl, sm.al[i] - r);
+            gu = fmax(gu, sm.al[i] + r);
+        }
+        const double pad = 1e-12 * fmax(fabs(gl), fabs(gu)) + 1e-300;
+        gl -= pad;
+        gu += pad;
+        const double isc = 1.0 / (gu - gl);
+        if (tid < k) {
+            sm.sal[tid] = (sm.al[tid] - gl) * isc;
+            const double b = sm.be[tid] * isc;
+            sm.sb2[tid] = b * b;
+            sm.salf[tid] = (float)sm.sal[tid];
+            sm.sb2f[tid] = (float)sm.sb2[tid];
+        }
+        __syncthreads();
+        double lo = 0.0, hi = 1.0;
+        // rounds 0, 1 in float32 (the float64 pipe issues 16 lanes / clock: a float64 round costs ~0.65 us), then the bracket
+        // [lo, hi] (6e-5 wide) is widened by 2e-5 on both sides -- 10x what float32 rounding of the scaled recurrence can move a
+        // crossing -- and three float64 rounds bring it to 1e-4 / 129^3 = 4.7e-11 of the Gershgorin interval
+        for (int round = 0; round < 5; ++round) {
+            if (round == 2) {
+                lo = fmax(lo - 2e-5, 0.0);
+                hi = fmin(hi + 2e-5, 1.0);
+            }
+            const double step = (hi - lo) / 129.0;
+            const double xs = lo + step * (double)(tid + 1);
+            const bool ge = (round < 2 ? sturm_count_poly_f32(sm.salf, sm.sb2f, k, (float)xs) : sturm_count_poly(sm.sal, sm.sb2, k, xs)) >= 1;
+            const unsigned m = __ballot_sync(0xffffffffu, ge);
+            if (lane == 0) sm.first[round & 1][warp] = m ? 32 * warp + __ffs(m) - 1 : 128;
+            __syncthreads();
+            const int* fr = sm.first[round & 1];
+            const int f = min(min(fr[0], fr[1]), min(fr[2], fr[3]));
+            if (f >= 128) {
+                lo = lo + step * 128.0;
+            } else {
+                hi = lo + step * (double)(f + 1);
+                lo = lo + step * (double)f;
+            }
+        }
+        // Newton from the left end: lo is below every root, the iteration increases monotonically to the smallest one
+        if (tid == 0) {
+            double x = lo;
+            for (int itn = 0; itn < 4; ++itn) {  // polish: quadratic for a simple root, harmless (stays inside the bracket) otherwise
+                double p, dp;
+                lc_poly_newton(sm.sal, sm.sb2, k, x, p, dp);
+                if (!(dp != 0.0)) break;
+                const double xn = x - p / dp;
+                if (!(xn > x) || xn > hi) break;  // converged to rounding (or left the bracket: keep the last safe iterate)
+                x = xn;
+            }
+            a.scal[(long long)env * 4 + 0] = gl + x * (gu - gl);
+            a.scal[(long long)env * 4 + 1] = gu;  // upper bound of the spectrum of T (selects the approximation interval only)
+        }
+    }
+    DENSE_STAMP(51);
+    gjb_cluster_sync();  // nobody leaves while a peer could still be sending to it
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// D2'' gjb_inverse_kernel (COVO_SIGMA=dense-gjb): the same in-place Gauss-Jordan sweep, BLOCKED (8 pivots per step) and spread over
+// a 2-CTA cluster per pole, the matrix resident in registers.  Sweeping the index block K with P = A_KK:
+//     A_IJ -= A_IK P^-1 A_KJ,   A_KJ <- P^-1 A_KJ =: G,   A_IK <- -A_IK P^-1,   A_KK <- P^-1.
+// With the sign convention of D2' the matrix is symmetric on the unswept index set and ANTI-symmetric between swept and unswept
+// indices, so the column panel is the row panel again: A_iK = sigma(i) (A_Ki)^T, sigma = -1 for swept i.  Everything a step needs
+// therefore follows from the 8 raw pivot rows (8 x n) alone:
+//     A_ij -= sigma(i) sum_s raw[s][i] G[s][j],    row K_s <- G[s][:],   column K_s <- -sigma(i) G[s][i],   block KK <- P^-1.
+// Roles (640 threads per CTA):
+//   * 16 UPDATE warps hold the matrix: thread (ty = warp, tx = lane) owns rows ty + 16 (rank + 2 a'), a' < 8 (row pairs packed for
+//     FFMA2) and columns tx + 32 b, b < 7.  Per step: 224 FFMA2 per thread against 28 + 16 vector loads.
+//   * 4 SOLVER warps run one block ahead: they wait for the raw rows of block m + 1 (published through distributed shared memory with
+//     st.async, completion counted by an mbarrier -- no fences, no cluster barrier), invert the 8 x 8 pivot block on one warp
+//     (lane = two entries, 8 shuffle-driven pivots), build G = P^-1 raw and the signed multiplier table, while the update warps
+//     are still applying block m.
+//   * look-ahead: after the barrier that opens step m, the warps that own the rows of block m + 1 (one row per warp) apply step m to
+//     that row first (56 FMAs, same operation order as the full update, so the values are bit-identical) and publish it.
+// Flow control: the raw panels live in a ring of 4 slots.  Blocks are owned in pairs (tile = 16 rows = 2 blocks, tiles alternate
+// between the CTAs), so a CTA can run at most 3 blocks ahead of its peer before it needs a panel from it: 4 slots never collide.
+// Cost model at n = 200: 25 steps x max(update 1800 cycles, solver chain ~1600) instead of 200 steps x 1100.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int GB_CL = 2;     // CTAs per matrix
+constexpr int GB_UT = 512;   // update threads
+constexpr int GB_ST = 128;   // solver threads
+constexpr int GB_T = GB_UT + GB_ST;
+constexpr int GB_NP = 224;   // padded order: 14 row tiles of 16, 7 column slots of 32
+constexpr int GB_RS = 256;   // row stride of a raw panel (the unused 8th row slot addresses rows up to 255)
+constexpr int GB_SLOTS = 4;
+
+template <int V>
+struct IntC {
+    static constexpr int value = V;
+};
+
+struct GjbSmem {
+    float raw[GB_SLOTS][8][GB_RS];  // pivot-row panels [s][j]
+    float stage[2][8][GB_NP];       // a pivot row on its way out (by block parity): source of the bulk copies
+    float G[2][4][GB_NP][2];        // [parity][s / 2][j][s & 1]
+    float2 Mneg[2][16][4][8];       // [parity][ty][row pair q][s]: (-sigma(i0) raw[s][i0], -sigma(i1) raw[s][i1]); 0 for pivot rows
+    float Pinv[2][64];
+    float piv[GB_NP];
+    unsigned long long rawbar[GB_SLOTS];
+    int bad;
+};
+
 
 __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a) {
     COVO_DYN_SMEM(smraw);
@@ -1030,7 +1401,14 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         for (int m = 0; m < nblk; ++m) {
             const int slot = m & (GB_SLOTS - 1), par = m & 1, K0 = 8 * m;
             if (sidx == 0) gjb_mbar_expect(&sm.rawbar[slot], 8 * GB_NP * 4);
+            const bool pf = a.prof && sidx == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+            long long t0 = pf ? clock64() : 0;
             gjb_mbar_wait(&sm.rawbar[slot], (unsigned)((m / GB_SLOTS) & 1));
+            if (pf) {
+                const long long t1 = clock64();
+                a.prof[54] = (m == 0 ? 0 : a.prof[54]) + (t1 - t0);
+                t0 = t1;
+            }
             const float(*rw)[GB_RS] = sm.raw[slot];
             if (swarp == 0) {
                 // P^-1 by an in-place Gauss-Jordan sweep of the 8 x 8 block: lane = (row r, columns c0, c0 + 1)
@@ -1076,19 +1454,47 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 }
             }
             COVO_NAMED_BARRIER(1, GB_ST);
-            for (int j = sidx; j < GB_NP; j += GB_ST) {
-                float col[8];
+            if (pf) {
+                const long long t1 = clock64();
+                a.prof[55] = (m == 0 ? 0 : a.prof[55]) + (t1 - t0);
+                t0 = t1;
+            }
+            {
+                // G = P^-1 raw: thread = columns (sidx, sidx + 128) packed for FFMA2; P^-1 rows come as broadcast float4 loads
+                const int j0 = sidx, j1 = min(sidx + GB_ST, GB_RS - 1);  // (the second column of sidx >= 96 is padding: never stored)
+                float2 col[8];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) col[t] = rw[t][j];
+                for (int t = 0; t < 8; ++t) col[t] = make_float2(rw[t][j0], rw[t][j1]);
+                const float4* pv = reinterpret_cast<const float4*>(sm.Pinv[par]);
 #pragma unroll
-                for (int sp = 0; sp < 8; ++sp) {
-                    float g = 0.f;
+                for (int sp = 0; sp < 8; sp += 2) {
+                    float2 g[2];
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) g = fmaf(sm.Pinv[par][sp * 8 + t], col[t], g);
-                    sm.G[par][sp >> 1][j][sp & 1] = g;
+                    for (int u = 0; u < 2; ++u) {
+                        const float4 pa = pv[(sp + u) * 2], pb = pv[(sp + u) * 2 + 1];
+                        float2 acc2 = make_float2(0.f, 0.f);
+                        acc2 = __ffma2_rn(make_float2(pa.x, pa.x), col[0], acc2);
+                        acc2 = __ffma2_rn(make_float2(pa.y, pa.y), col[1], acc2);
+                        acc2 = __ffma2_rn(make_float2(pa.z, pa.z), col[2], acc2);
+                        acc2 = __ffma2_rn(make_float2(pa.w, pa.w), col[3], acc2);
+                        acc2 = __ffma2_rn(make_float2(pb.x, pb.x), col[4], acc2);
+                        acc2 = __ffma2_rn(make_float2(pb.y, pb.y), col[5], acc2);
+                        acc2 = __ffma2_rn(make_float2(pb.z, pb.z), col[6], acc2);
+                        acc2 = __ffma2_rn(make_float2(pb.w, pb.w), col[7], acc2);
+                        g[u] = acc2;
+                    }
+                    // [s / 2][j][s & 1]: the two s of this pair are adjacent
+                    *reinterpret_cast<float2*>(&sm.G[par][sp >> 1][j0][0]) = make_float2(g[0].x, g[1].x);
+                    if (sidx + GB_ST < GB_NP) *reinterpret_cast<float2*>(&sm.G[par][sp >> 1][sidx + GB_ST][0]) = make_float2(g[0].y, g[1].y);
                 }
             }
+            if (pf) {
+                const long long t1 = clock64();
+                a.prof[56] = (m == 0 ? 0 : a.prof[56]) + (t1 - t0);
+                t0 = t1;
+            }
             __syncthreads();  // opens step m for the update warps
+            if (pf) a.prof[57] = (m == 0 ? 0 : a.prof[57]) + (clock64() - t0);
         }
     } else {
         // ================================================ update warps ================================================
@@ -1114,21 +1520,62 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 acc[q][b] = make_float2(v2[0], v2[1]);
             }
         // block 0 lives in tile 0 = CTA 0, row slot 0 (.x of pair 0): warps 0..7 publish their row
+        // a row leaves as ONE bulk copy per destination CTA (this one included): staged in shared memory, fenced for the async proxy
+        auto publish_row = [&](int blk, int s_row, const float (&vals)[7]) {
+            float* st = sm.stage[blk & 1][s_row];
+#pragma unroll
+            for (int b = 0; b < 7; ++b) st[tx + 32 * b] = vals[b];
+            gjb_fence_async_proxy();
+            __syncwarp();
+            if (tx == 0) {
+                const int slot = blk & (GB_SLOTS - 1);
+#pragma unroll
+                for (int r = 0; r < GB_CL; ++r) gjb_bulk_send(&sm.raw[slot][s_row][0], st, GB_NP * 4, (unsigned)r, &sm.rawbar[slot]);
+            }
+        };
         if (rank == 0 && ty < 8) {
+            float vals[7];
 #pragma unroll
-            for (int b = 0; b < 7; ++b)
-#pragma unroll
-                for (int r = 0; r < GB_CL; ++r) gjb_send(&sm.raw[0][ty][tx + 32 * b], (unsigned)r, acc[0][b].x, &sm.rawbar[0]);
+            for (int b = 0; b < 7; ++b) vals[b] = acc[0][b].x;
+            publish_row(0, ty, vals);
         }
+        const bool pfu = a.prof && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+        long long tu0 = pfu ? clock64() : 0;
         for (int m = 0; m < nblk; ++m) {
             __syncthreads();  // G, multipliers and P^-1 of block m are in place; everybody is done with step m - 1
+            if (pfu) {
+                const long long t1 = clock64();
+                a.prof[58] = (m == 0 ? 0 : a.prof[58]) + (t1 - tu0);
+                tu0 = t1;
+            }
             const int par = m & 1, K0 = 8 * m;
             const float2* mrow = &sm.Mneg[par][ty][0][0];
-            // ---- look-ahead: the rows of block m + 1 after step m, published before the bulk of the update ----------------
+            // One row pair: all eight s of the rank-8 update (G is re-read per pair here; the bulk below re-uses it across pairs)
+            auto update_pair = [&](auto QC) {
+                constexpr int q = decltype(QC)::value;
+#pragma unroll
+                for (int qt = 0; qt < 4; ++qt) {
+                    const float4 m4 = *reinterpret_cast<const float4*>(&mrow[q * 8 + 2 * qt]);
+                    const float2 ma = make_float2(m4.x, m4.y), mb = make_float2(m4.z, m4.w);
+#pragma unroll
+                    for (int b = 0; b < 7; ++b) {
+                        const float2 g2 = *reinterpret_cast<const float2*>(&sm.G[par][qt][tx + 32 * b][0]);
+                        acc[q][b] = __ffma2_rn(ma, make_float2(g2.x, g2.x), acc[q][b]);
+                        acc[q][b] = __ffma2_rn(mb, make_float2(g2.y, g2.y), acc[q][b]);
+                    }
+                }
+            };
+            // ---- look-ahead: the warps that own the rows of block m + 1 update THAT pair first and publish their row -------------
+            int q_done = -1;
             if (m + 1 < nblk) {
                 const int tile1 = (m + 1) >> 1;
                 if (rank == tile1 % GB_CL && (ty >> 3) == ((m + 1) & 1)) {
                     const int a1 = tile1 / GB_CL, q1 = a1 >> 1, h1 = a1 & 1, i = ty + 16 * tile1;
+                    q_done = q1;
+                    if (q1 == 0) update_pair(IntC<0>());
+                    else if (q1 == 1) update_pair(IntC<1>());
+                    else if (q1 == 2) update_pair(IntC<2>());
+                    else update_pair(IntC<3>());
                     float tmp[7];
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
@@ -1136,13 +1583,6 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
 #pragma unroll
                             for (int b = 0; b < 7; ++b) tmp[b] = h1 ? acc[q][b].y : acc[q][b].x;
                         }
-#pragma unroll
-                    for (int sp = 0; sp < 8; ++sp) {
-                        const float2 m2 = mrow[q1 * 8 + sp];
-                        const float mm = h1 ? m2.y : m2.x;
-#pragma unroll
-                        for (int b = 0; b < 7; ++b) tmp[b] = fmaf(mm, sm.G[par][sp >> 1][tx + 32 * b][sp & 1], tmp[b]);
-                    }
                     if ((tx & ~7) == (K0 & 31)) {  // its entries in the pivot columns of step m: -G[s][i]  (i is unswept)
                         const int sc = tx - (K0 & 31), b0 = K0 >> 5;
                         const float v = -sm.G[par][sc >> 1][i][sc & 1];
@@ -1150,15 +1590,10 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                         for (int b = 0; b < 7; ++b)
                             if (b == b0) tmp[b] = v;
                     }
-                    const int slot1 = (m + 1) & (GB_SLOTS - 1);
-#pragma unroll
-                    for (int b = 0; b < 7; ++b)
-#pragma unroll
-                        for (int r = 0; r < GB_CL; ++r)
-                            gjb_send(&sm.raw[slot1][ty & 7][tx + 32 * b], (unsigned)r, tmp[b], &sm.rawbar[slot1]);
+                    publish_row(m + 1, ty & 7, tmp);
                 }
             }
-            // ---- the rank-8 update of everything this thread owns --------------------------------------------------------
+            // ---- the rank-8 update of everything else this thread owns ---------------------------------------------------
 #pragma unroll
             for (int qt = 0; qt < 4; ++qt) {  // two of the eight s at a time
                 float2 g2[7];
@@ -1166,6 +1601,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 for (int b = 0; b < 7; ++b) g2[b] = *reinterpret_cast<const float2*>(&sm.G[par][qt][tx + 32 * b][0]);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
+                    if (q == q_done) continue;  // warp-uniform
                     const float4 m4 = *reinterpret_cast<const float4*>(&mrow[q * 8 + 2 * qt]);
                     const float2 ma = make_float2(m4.x, m4.y), mb = make_float2(m4.z, m4.w);
 #pragma unroll
@@ -1211,6 +1647,11 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                                 }
                         }
                     }
+            }
+            if (pfu) {
+                const long long t1 = clock64();
+                a.prof[59] = (m == 0 ? 0 : a.prof[59]) + (t1 - tu0);
+                tu0 = t1;
             }
         }
         // ---- results ---------------------------------------------------------------------------------------------------------
@@ -1292,18 +1733,35 @@ cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, in
     a.prof = s.prof;
     static size_t conf1[32] = {}, conf2[32] = {}, conf3[32] = {};
     cudaError_t e;
-    const bool lz_v1 = getenv("COVO_LANCZOS_V1") || !lanczos2_layout(a.n).fits;
-    a.Asym = lz_v1 ? nullptr : s.F;  // the symmetrised matrix, written by the Lanczos kernel (F is unused on this path)
-    if (lz_v1) {  // n > 200: the padded float64 rows no longer fit next to the column buffers
+    // Lanczos kernel: the 8-CTA cluster version by default; COVO_LANCZOS=v1 | v2 select the single-CTA kernels (development)
+    const char* lz = getenv("COVO_LANCZOS");
+    const int lz_kind = (lz && !strcmp(lz, "v1")) ? 1 : (lz && !strcmp(lz, "v2") && lanczos2_layout(a.n).fits) ? 2 : 3;
+    a.Asym = (lz_kind == 1) ? nullptr : s.F;  // the symmetrised matrix, written by the Lanczos kernel (F is unused on this path)
+    if (lz_kind == 1) {
         const size_t smem1 = (size_t)(2 * a.n + 8 + 2 * kLanczosMax) * sizeof(double) + (size_t)a.n * (a.n + 1) * sizeof(float);
         e = ensure_smem_attr(lanczos_kernel, smem1, conf1);
         if (e != cudaSuccess) return e;
         lanczos_kernel<<<n_env, TL, smem1, st>>>(a);
-    } else {
+    } else if (lz_kind == 2) {
         const size_t smem3 = lanczos2_layout(a.n).bytes;
         e = ensure_smem_attr(lanczos2_kernel, smem3, conf3);
         if (e != cudaSuccess) return e;
         lanczos2_kernel<<<n_env, TL2, smem3, st>>>(a);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(LC_CL, n_env);
+        cfg.blockDim = dim3(LC_T);
+        cfg.dynamicSmemBytes = sizeof(LcSmem);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = LC_CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, lanczos_cluster_kernel, a);
+        if (e != cudaSuccess) return e;
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -40,12 +40,15 @@ struct dim3 {
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 struct float2 { float x, y; };
+struct alignas(16) double2 { double x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline long long clock64() { return 0; }
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 
 namespace emu {
 
@@ -338,6 +341,27 @@ inline void emu_dsmem_st_signal(float* local_addr, unsigned rank, float v, void*
     memcpy(peer->smem.data() + off, &v, 4);
     EmuMbar* m = reinterpret_cast<EmuMbar*>(peer->smem.data() + boff);
     m->tx -= 4;
+    emu_mbar_check(m);
+}
+inline void emu_dsmem_st_signal64(double* local_addr, unsigned rank, double v, void* local_bar) {
+    emu::Block* me = emu::cur();
+    emu::Block* peer = emu::cur_cluster()->blocks[rank];
+    const size_t off = reinterpret_cast<unsigned char*>(local_addr) - me->smem.data();
+    const size_t boff = reinterpret_cast<unsigned char*>(local_bar) - me->smem.data();
+    memcpy(peer->smem.data() + off, &v, 8);
+    EmuMbar* m = reinterpret_cast<EmuMbar*>(peer->smem.data() + boff);
+    m->tx -= 8;
+    emu_mbar_check(m);
+}
+// cp.async.bulk shared::cta -> shared::cluster: `bytes` from this CTA's src to the same-offset-as-dst_local location in CTA `rank`
+inline void emu_dsmem_bulk_copy(void* dst_local, const void* src_local, unsigned bytes, unsigned rank, void* local_bar) {
+    emu::Block* me = emu::cur();
+    emu::Block* peer = emu::cur_cluster()->blocks[rank];
+    const size_t off = reinterpret_cast<unsigned char*>(dst_local) - me->smem.data();
+    const size_t boff = reinterpret_cast<unsigned char*>(local_bar) - me->smem.data();
+    memcpy(peer->smem.data() + off, src_local, bytes);
+    EmuMbar* m = reinterpret_cast<EmuMbar*>(peer->smem.data() + boff);
+    m->tx -= (int)bytes;
     emu_mbar_check(m);
 }
 inline void emu_cluster_barrier() {

@@ -19,7 +19,8 @@ extern "C" int emu_sigma_dense(int n, float sample_sigma, const float* R, const 
     a.prof = nullptr;
     a.Asym = nullptr;
     const size_t smem1 = (size_t)(2 * n + 8 + 2 * kLanczosMax) * sizeof(double) + (size_t)n * (n + 1) * sizeof(float);
-    if ((variant & 16) || !lanczos2_layout(n).fits) emu_launch(lanczos_kernel, dim3(1), TL, smem1, a);  // the first Lanczos kernel
+    if (variant & 32) emu_launch_cluster(lanczos_cluster_kernel, dim3(LC_CL, 1), LC_CL, LC_T, sizeof(LcSmem), a);  // 8-CTA cluster
+    else if ((variant & 16) || !lanczos2_layout(n).fits) emu_launch(lanczos_kernel, dim3(1), TL, smem1, a);  // the first Lanczos kernel
     else emu_launch(lanczos2_kernel, dim3(1), TL2, lanczos2_layout(n).bytes, a);
     variant &= 15;
     if (variant == 3) {

@@ -37,6 +37,9 @@ def main():
     mhz = 1965.0
     d = lambda a, b: round((c[b] - c[a]) / mhz, 2)
     print("lanczos: load", d(48, 49), "iterations", d(49, 50), "multisection", d(50, 51), "us")
+    print("lanczos exchange (send + mbarrier wait, all iterations, CTA 0 thread 0):", round(c[52] / mhz, 2), "us")
+    print("gjb (CTA 0): solver wait-for-rows", round(c[54] / mhz, 2), "inversion", round(c[55] / mhz, 2), "G", round(c[56] / mhz, 2),
+          "solver at step barrier", round(c[57] / mhz, 2), "| update warp 0: at step barrier", round(c[58] / mhz, 2), "update", round(c[59] / mhz, 2), "us (sums over the steps)")
     print("raw stamps 48..59:", [int(x) for x in c[48:60]])
 
 
