@@ -123,6 +123,9 @@ def algorithmic_bytes(n, H, N, parity=False):
     nn = 4 * n * n
     rollout = nn // 2 + 4 * 4 * n + 4 * (H + 1) * 6 + 96 + 2 * 4 * n + (4 * N * n if parity else 0)
     return {
+        "lanczos": nn + nn,                          # R in; (R + R^T)/2 out for the pole kernels
+        "pole_inverses": 17 * nn + 16 * nn // 2,     # every pole (and the log det CTA) reads the matrix; 16 weighted inverses (lower) out
+        "combine": 16 * nn // 2 + nn,                # 16 lower triangles in; Sigma out
         # state, mean, ref; per-step derivative records written + read; [A|B], S, D hand-over written + read; R
         "hessian": 96 + 4 * n + 4 * H * 6 + 2 * 4 * H * (14 * 153 + 14 * 17) + 2 * 4 * H * 328 + nn,
         "tridiag": nn + nn + 2 * 8 * n,  # R in; reflectors out; (d, e) fp64 out (Q^T: qacc kernel, side stream, +2 nn)
@@ -362,6 +365,44 @@ def run_gpu(args):
     value = K * world / (total_ms_max / 1e3)
     assert torch.isfinite(actions).all(), "non-finite actions"
     status_ok = bool((h.status() == 0).all()) if cfg.mode == _lib.MODE_COVO_ONLINE else True
+    sigma_path = h.sigma_path()
+    slot_names = h.kernel_slot_names()
+
+    # ---- the opt-in fast optimize_sigma path (same states, same timing protocol; NOT the headline: reduced Sigma accuracy) --------
+    fast_sigma = None
+    if cfg.mode == _lib.MODE_COVO_ONLINE:
+        h.set_sigma_path(3)
+        h.set_mean(_hover())
+        for i in range(W):
+            one_step(i)
+        torch.cuda.synchronize()
+        ev2 = _events(K)
+        for i in range(K):
+            flush.zero_()
+            ev2[i][0].record()
+            one_step(W + i)
+            ev2[i][1].record()
+        torch.cuda.synchronize()
+        ms2 = np.array([a.elapsed_time(b) for a, b in ev2])
+        ok2 = bool((h.status() == 0).all())
+        h.set_profiling(True)
+        acc2 = np.zeros(6)
+        for i in range(min(10, K)):
+            flush.zero_()
+            one_step(W + i)
+            acc2 += h.kernel_ms()
+        names2 = h.kernel_slot_names()
+        h.set_profiling(False)
+        fast_sigma = {"value": K / (float(ms2.sum()) / 1e3), "unit": UNIT, "ms_per_step": float(ms2.mean()), "step_ms_p99": float(np.percentile(ms2, 99)),
+                      "numeric_status_ok": ok2, "kernel_us": {k: round(float(v) / min(10, K) * 1e3, 1) for k, v in zip(names2, acc2)},
+                      "note": "covo_set_sigma_path(h, 3) / COVO_SIGMA=dense: adaptive Lanczos + 16 float32 Gauss-Jordan pole inverses instead of "
+                              "E1-E3; Sigma within 1e-4 (median) .. 5e-3 (worst) of exact arithmetic instead of 1e-5 -- rank-local number, "
+                              "not the headline"}
+        h.set_sigma_path(0)
+        h.set_mean(_hover())
+        for i in range(W):
+            one_step(i)
+        torch.cuda.synchronize()
 
     # ---- e2e through the plugin surface with host buffers -------------------------------------------
     ctl, cp = cm.get_controller(env, mode_name, f"N{N_SAMPLES}_H{HORIZON}_lam{LAM}", device=local_rank, seed=seed)
@@ -407,7 +448,8 @@ def run_gpu(args):
     tc = time.perf_counter() - t0
     closed = {"value": K * world / tc, "unit": UNIT, "ms_per_step": 1e3 * tc / K, "mean_err_pos": float(err_cl.mean()),
               "note": "covo_closed_loop: K x [noisy state -> controller -> Quad3D.step_env] on the device, one D2H of the logs at the end (wall clock)"}
-    launches_per_step = h.launches_per_step() if hasattr(h, "launches_per_step") else {"covo-online": 9, "covo-offline": 1, "mppi": 2}[mode_name]
+    # kernels inside the replayed CUDA graph of one step (+ the counter kernel that replaces the per-step launch arguments)
+    launches_per_step = {"covo-online": 9 + 1, "covo-offline": 1 + 1, "mppi": 1 + 1}[mode_name]
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak",
@@ -418,12 +460,14 @@ def run_gpu(args):
                    "inputs": "noisy states of a PID closed loop on a zigzag reference (host-generated, shared with --impl reference)",
                    "rng": "in-kernel Philox (production mode)", "l2": "256 MiB memset between steps, excluded from the event timing",
                    "timing": "CUDA events per step on the launch stream, sum over K steps, max over ranks",
-                   "sigma_path": os.environ.get("COVO_SIGMA", "default")},
+                   "sigma_path": {0: "tridiagonal (E1-E3)", 3: "dense (Lanczos + 16-pole cluster Gauss-Jordan)"}.get(sigma_path, str(sigma_path))},
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
         "step_ms_p50": float(np.median(step_ms)), "step_ms_p99": float(np.percentile(step_ms, 99)),
         "gpu_launches": launches_per_step * K, "clocks": clocks, "numeric_status_ok": status_ok,
         "e2e": e2e, "closed_loop": closed,
     }
+    if fast_sigma is not None:
+        out["fast_sigma"] = fast_sigma
     # ---- roofline ---------------------------------------------------------------------------------------
     peak, peak_src = measured_peaks()
     n = 4 * HORIZON
@@ -433,8 +477,7 @@ def run_gpu(args):
     if os.path.exists(tp):
         traffic = json.load(open(tp))
     if kernel_ms is not None and cfg.mode == _lib.MODE_COVO_ONLINE:
-        names = h.kernel_slot_names() if hasattr(h, "kernel_slot_names") else ["hessian", "tridiag", "trifunc", "sandwich", "cholesky", "rollout"]
-        per = {k: float(v) for k, v in zip(names, kernel_ms) if v > 1e-4}
+        per = {k: float(v) for k, v in zip(slot_names, kernel_ms) if v > 1e-4}
         dom = max(per, key=per.get)
         rl = {}
         for k, ms in per.items():
@@ -525,7 +568,7 @@ def tracking_cost(device=0, controller="covo-online"):
     """BASELINE metric, second half ("tracking cost delta vs ref"), POWERED: the reference's protocol (envs/quadrotor.py:564-579:
     4 trajectories x 10 episodes x 300 steps, mean over episodes of the per-episode mean ||pos_tar - pos||) on both sides with the
     SAME trajectories, initial states and observation-noise streams per episode (tools/tracking_protocol.py).  Oracle arm: the
-    fixture tests/golden/oracle_tracking_*.npz written by tools/oracle_tracking_stats.py (CPU, ~35 min; committed with the script).
+    fixture tests/golden/tracking/oracle_tracking_*.npz written by tools/oracle_tracking_stats.py (CPU, ~35 min; committed with the script).
     Device arm: all 40 episodes as one batched device-resident closed loop with the production Philox sample field.  The sample
     streams differ (numpy vs Philox), so this is a statistical comparison: means +- s.e., z-scores unpaired and paired by episode."""
     from tools import device_tracking_stats as dts

@@ -80,6 +80,8 @@ _SIGNATURES = {
     "covo_get_kernel_ms": [_H, _F],
     "covo_debug_phase_clocks": [_H, C.c_int, C.POINTER(C.c_longlong)],
     "covo_rng_step": [_H, C.POINTER(C.c_uint)],
+    "covo_get_sigma_path": [_H, _I],
+    "covo_set_sigma_path": [_H, C.c_int],
     "covo_env_reset": [_H, _F, _I],
     "covo_env_get_state": [_H, _F, _I],
     "covo_env_step": [_H, _F, _F, C.c_ulonglong, C.c_uint, C.c_int, C.c_float, C.c_float, _F, _F, _F, _I],
@@ -416,6 +418,19 @@ class Handle:
         out = np.zeros(64, dtype=np.int64) if read else None
         check(self.lib.covo_debug_phase_clocks(self._h, int(on), None if out is None else out.ctypes.data_as(C.POINTER(C.c_longlong))))
         return out
+
+    def sigma_path(self) -> int:
+        v = C.c_int()
+        check(self.lib.covo_get_sigma_path(self._h, C.byref(v)))
+        return v.value
+
+    def set_sigma_path(self, path: int):
+        check(self.lib.covo_set_sigma_path(self._h, int(path)))
+
+    def kernel_slot_names(self):
+        """Names of the six covo_get_kernel_ms slots for this handle's optimize_sigma path."""
+        mid = ["lanczos", "pole_inverses", "combine"] if self.sigma_path() else ["tridiag", "trifunc", "sandwich"]
+        return ["hessian", *mid, "cholesky", "rollout"]
 
     def rng_step(self) -> int:
         v = C.c_uint()

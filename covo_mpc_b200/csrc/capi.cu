@@ -105,7 +105,7 @@ struct covo_handle {
     int num_sms = 0;
     bool pipeline_enabled = true;
     bool pipeline_forced = false;
-    int sigma_dense = 0;  // COVO_SIGMA=dense (1) / dense-gj (2): experimental tridiagonalisation-free optimize_sigma (sigma_dense.cu)
+    int sigma_dense = 0;  // optimize_sigma path: 0 tridiagonal (E1-E3, sigma.cu); 3 the dense kernels D1-D3 of sigma_dense.cu
     DevBuf<double> dense_scal;
     DevBuf<float> dense_X;  // COVO_PIPELINE=2 (development): keep the pipeline on while per-kernel timings are taken
     unsigned int rng_stream = 0;
@@ -137,6 +137,29 @@ struct covo_handle {
     DevBuf<float> env_state24, env_noisy24, env_noise, env_log_f, env_action, pid_integral;
     DevBuf<int> env_time, env_noisy_time, env_done;
     bool env_ready = false;
+    // CUDA-graph replay of the step (one graph launch per MPC step instead of 8-10 kernel launches, event records and waits).
+    // Everything that used to change from launch to launch now lives on the device: the sample-field step counter (rng_ctr), the
+    // Cholesky -> rollout progress counter (cleared by the first kernel of the step), the closed loop's step index (loop_ctr).
+    // What still differs between calls -- the caller's state / time / action pointers of covo_step_device -- is patched into the two
+    // kernel nodes that carry it.
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        cudaGraph_t graph = nullptr;  // kept: its node handles are the keys for patching the executable graph
+        cudaGraphNode_t n_hess = nullptr, n_roll = nullptr;
+        HessianArgs ha;
+        RolloutArgs ra;
+        const float* st_d = nullptr;
+        const int* tm_d = nullptr;
+        float* act_d = nullptr;
+        bool valid = false;
+    };
+    StepGraph g_dev, g_host, g_loop;
+    bool graphs_enabled = true;
+    int direct_steps = 0;
+    DevBuf<unsigned int> dev_ctr;      // [0] sample-field step counter, [1] closed-loop step index
+    unsigned int rng_ctr_shadow = 0;   // what dev_ctr[0] holds (host mirror)
+    EnvStepArgs loop_env_args;         // the environment-step node of g_loop
+    bool loop_args_valid = false;
     // pinned staging
     float* h_state = nullptr;
     int* h_time = nullptr;
@@ -180,6 +203,11 @@ void release_all(covo_handle* h) {
     h->dense_scal.release();
     h->dense_X.release();
     h->pid_integral.release();
+    h->dev_ctr.release();
+    for (covo_handle::StepGraph* g : {&h->g_dev, &h->g_host, &h->g_loop}) {
+        if (g->exec) cudaGraphExecDestroy(g->exec);
+        if (g->graph) cudaGraphDestroy(g->graph);
+    }
 }
 
 HessianArgs hess_args(covo_handle* h, const float* st, const int* tm, const float* a_mean, int shift, float* R, float* ws,
@@ -198,6 +226,7 @@ HessianArgs hess_args(covo_handle* h, const float* st, const int* tm, const floa
     a.workspace = ws;
     a.R = R;
     a.status = (R == h->R.p) ? h->status.p : nullptr;  // the offline schedule keeps its own status array
+    a.progress = (R == h->R.p) ? h->chol_progress.p : nullptr;
     a.prof = h->phase_clocks ? h->prof.p : nullptr;
     return a;
 }
@@ -304,13 +333,10 @@ bool pipeline_ok(covo_handle* h) {
 int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = false, bool pipelined = false) {
     SigmaArgs sa = sigma_args(h);
     if (!want_L) sa.L = nullptr;  // the sampler only needs the packed factor
-    if (h->sigma_dense) {  // experimental: Lanczos + 17 shifted factorisations + combine instead of E1-E3
-        CK(launch_sigma_dense(sa, h->dense_scal.p, h->dense_X.p, h->E, st, h->sigma_dense));
-        if (pf) {
-            pf->mark(2);
-            pf->mark(3);
-            pf->mark(4);
-        }
+    if (h->sigma_dense) {  // Lanczos + 17 shifted inverses + combine instead of E1-E3
+        const bool tm = pf && h->profiling;
+        CK(launch_sigma_dense(sa, h->dense_scal.p, h->dense_X.p, h->E, st, tm ? h->ev[2] : nullptr, tm ? h->ev[3] : nullptr));
+        if (pf) pf->mark(4);  // slots: 1 Lanczos, 2 inverses, 3 combine
     } else {
         CK(launch_tridiag(sa, h->E, st));
         if (pf) pf->mark(2);
@@ -329,7 +355,7 @@ int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = fals
     sa.cov_symmetric = 1;
     if (pipelined) {  // the rollout kernel follows in the same stream as a programmatic dependent launch (step_common)
         sa.progress = h->chol_progress.p;
-        sa.epoch = (int)h->chol_epoch;
+        sa.epoch = 0;  // the counter is cleared by the first kernel of the step (hess_local)
     }
     CK(launch_cholesky(sa, h->E, st));
     if (pf) pf->mark(5);
@@ -337,8 +363,10 @@ int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = fals
     return COVO_OK;
 }
 
-int step_common(covo_handle* h, const float* st_d, const int* tm_d, const float* eps_d, float* act_d, cudaStream_t st,
-                int finalize) {
+// The launch sequence of one MPC step on stream `st`.  rec != nullptr: the step is being captured into a CUDA graph -- the sample
+// field is indexed by the device counter and the arguments of the two kernels that carry caller pointers are kept for patching.
+int step_launch(covo_handle* h, const float* st_d, const int* tm_d, const float* eps_d, float* act_d, cudaStream_t st, int finalize,
+                covo_handle::StepGraph* rec) {
     Prof pf(h, st);
     const int mode = h->cfg.mode;
     bool pipelined = false;
@@ -349,6 +377,7 @@ int step_common(covo_handle* h, const float* st_d, const int* tm_d, const float*
         for (int i = 1; i <= 5; ++i) pf.mark(i);
     } else if (mode == COVO_MODE_COVO_ONLINE) {
         HessianArgs ha = hess_args(h, st_d, tm_d, h->a_mean.p, 1, h->R.p, h->hess_ws.p, (long long)h->T * 3);
+        if (rec) rec->ha = ha;
         CK(launch_hessian(ha, h->E, st));
         pf.mark(1);
         pipelined = pipeline_ok(h);
@@ -361,12 +390,174 @@ int step_common(covo_handle* h, const float* st_d, const int* tm_d, const float*
     RolloutArgs ra = rollout_args(h, st_d, tm_d, h->a_mean.p, 1, eps_d, nullptr, h->a_mean.p, act_d, nullptr, nullptr, finalize);
     if (pipelined) {
         ra.lfac_progress = h->chol_progress.p;
-        ra.lfac_epoch = (int)h->chol_epoch;
-        h->chol_epoch += 64;
+        ra.lfac_epoch = 0;
+    }
+    if (rec) {
+        ra.stream = 0;
+        ra.stream_ctr = h->dev_ctr.p;
+        rec->ra = ra;
     }
     CK(launch_rollout(ra, h->E, st));
     pf.mark(6);
+    return COVO_OK;
+}
+
+// node handles of the two kernels whose arguments carry caller pointers
+int graph_find_nodes(cudaGraph_t g, covo_handle::StepGraph* sg) {
+    size_t n = 0;
+    CK(cudaGraphGetNodes(g, nullptr, &n));
+    std::vector<cudaGraphNode_t> nodes(n);
+    CK(cudaGraphGetNodes(g, nodes.data(), &n));
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType ty;
+        CK(cudaGraphNodeGetType(nd, &ty));
+        if (ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        CK(cudaGraphKernelNodeGetParams(nd, &kp));
+        if (kp.func == hess_local_kernel_address()) sg->n_hess = nd;
+        else if (kp.func == rollout_kernel_address()) sg->n_roll = nd;
+    }
+    return COVO_OK;
+}
+
+int graph_patch_node(cudaGraphExec_t exec, cudaGraphNode_t nd, void* args_struct) {
+    cudaKernelNodeParams kp;
+    CK(cudaGraphKernelNodeGetParams(nd, &kp));
+    void* params[1] = {args_struct};
+    kp.kernelParams = params;
+    kp.extra = nullptr;
+    CK(cudaGraphExecKernelNodeSetParams(exec, nd, &kp));
+    return COVO_OK;
+}
+
+// kernel arguments baked into the graphs changed (model constants, schedule table): rebuild on next use
+void graphs_invalidate(covo_handle* h) { h->g_dev.valid = h->g_host.valid = h->g_loop.valid = false; }
+
+bool graph_ok(covo_handle* h, const float* eps_d) {
+    return h->graphs_enabled && !h->profiling && !h->phase_clocks && !eps_d && !h->jax_key_pending && !h->pos_stats_on;
+}
+
+// keeps the device copy of the sample-field counter equal to the host's (they part only when direct launches were mixed in)
+int sync_rng_counter(covo_handle* h, cudaStream_t st) {
+    if (h->rng_ctr_shadow != h->rng_stream) {
+        CK(cudaMemcpyAsync(h->dev_ctr.p, &h->rng_stream, sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));  // the source is a host variable that keeps changing
+        h->rng_ctr_shadow = h->rng_stream;
+    }
+    return COVO_OK;
+}
+
+// Capture the step (plus, for the host entry point, its H2D / D2H copies; plus, for the closed loop, the environment step) into sg.
+int graph_build(covo_handle* h, covo_handle::StepGraph* sg, const float* st_d, const int* tm_d, float* act_d, int finalize, int kind) {
+    if (sg->exec) {
+        cudaGraphExecDestroy(sg->exec);
+        sg->exec = nullptr;
+    }
+    if (sg->graph) {
+        cudaGraphDestroy(sg->graph);
+        sg->graph = nullptr;
+    }
+    sg->n_hess = sg->n_roll = nullptr;
+    cudaStream_t cs = h->own_stream;
+    CK(cudaStreamSynchronize(cs));
+    CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int rc = COVO_OK;
+    cudaError_t ce = cudaSuccess;
+    const size_t E = (size_t)h->E;
+    if (kind == 1) {  // covo_step: pinned staging -> device
+        ce = cudaMemcpyAsync(h->state24.p, h->h_state, E * kStateFloats * sizeof(float), cudaMemcpyHostToDevice, cs);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->time.p, h->h_time, E * sizeof(int), cudaMemcpyHostToDevice, cs);
+    }
+    if (ce == cudaSuccess) rc = step_launch(h, st_d, tm_d, nullptr, act_d, cs, finalize, sg);
+    if (ce == cudaSuccess && rc == COVO_OK && kind == 2) ce = launch_env_step(h->loop_env_args, cs);
+    if (ce == cudaSuccess && rc == COVO_OK) ce = launch_bump(h->dev_ctr.p, kind == 2 ? h->dev_ctr.p + 1 : nullptr, cs);
+    if (ce == cudaSuccess && rc == COVO_OK && kind == 1) {
+        ce = cudaMemcpyAsync(h->h_action, h->action.p, E * 4 * sizeof(float), cudaMemcpyDeviceToHost, cs);
+        if (ce == cudaSuccess && h->cfg.mode == COVO_MODE_COVO_ONLINE)
+            ce = cudaMemcpyAsync(h->h_status, h->status.p, E * sizeof(int), cudaMemcpyDeviceToHost, cs);
+    }
+    cudaGraph_t g = nullptr;
+    cudaError_t ee = cudaStreamEndCapture(cs, &g);
+    if (rc != COVO_OK) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+    }
+    if (ce != cudaSuccess || ee != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return fail(COVO_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+    }
+    rc = graph_find_nodes(g, sg);
+    if (rc == COVO_OK) {
+        ce = cudaGraphInstantiate(&sg->exec, g, 0);
+        if (ce != cudaSuccess) rc = fail(COVO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+    }
+    if (rc != COVO_OK) {
+        cudaGraphDestroy(g);
+        return rc;
+    }
+    sg->graph = g;
+    sg->st_d = st_d;
+    sg->tm_d = tm_d;
+    sg->act_d = act_d;
+    sg->valid = true;
+    return COVO_OK;
+}
+
+int step_common(covo_handle* h, const float* st_d, const int* tm_d, const float* eps_d, float* act_d, cudaStream_t st,
+                int finalize) {
+    // (the first step of a handle is launched directly: it configures the kernels' shared-memory attributes, which a capture must not do)
+    if (finalize == 1 && graph_ok(h, eps_d) && h->direct_steps > 0) {
+        covo_handle::StepGraph* sg = (st_d == h->state24.p && act_d == h->action.p) ? &h->g_host : &h->g_dev;
+        const int kind = (sg == &h->g_host) ? 1 : 0;
+        if (!sg->valid) {
+            int rc = graph_build(h, sg, st_d, tm_d, act_d, finalize, kind);
+            if (rc == COVO_ERR_CUDA) {  // no graph on this driver / configuration: keep launching directly
+                h->graphs_enabled = false;
+                cudaGetLastError();
+                return step_common(h, st_d, tm_d, eps_d, act_d, st, finalize);
+            }
+            if (rc) return rc;
+        } else if (sg->st_d != st_d || sg->tm_d != tm_d || sg->act_d != act_d) {
+            // other caller buffers than last time: patch the two kernel nodes that read / write them
+            if (sg->n_hess) {
+                sg->ha.state24 = st_d;
+                sg->ha.time = tm_d;
+                int rc = graph_patch_node(sg->exec, sg->n_hess, &sg->ha);
+                if (rc) return rc;
+            }
+            sg->ra.state24 = st_d;
+            sg->ra.time = tm_d;
+            sg->ra.action_out = act_d;
+            int rc = graph_patch_node(sg->exec, sg->n_roll, &sg->ra);
+            if (rc) return rc;
+            sg->st_d = st_d;
+            sg->tm_d = tm_d;
+            sg->act_d = act_d;
+        }
+        int rc = sync_rng_counter(h, st);
+        if (rc) return rc;
+        CK(cudaGraphLaunch(sg->exec, st));
+        h->rng_stream += 1;
+        h->rng_ctr_shadow += 1;
+        h->have_factor = true;
+        return COVO_OK;
+    }
+    const bool host_io = (st_d == h->state24.p && act_d == h->action.p && finalize == 1);
+    if (host_io) {  // what the covo_step graph does inside: staging copies around the kernels
+        const size_t E = (size_t)h->E;
+        CK(cudaMemcpyAsync(h->state24.p, h->h_state, E * kStateFloats * sizeof(float), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->time.p, h->h_time, E * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    int rc = step_launch(h, st_d, tm_d, eps_d, act_d, st, finalize, nullptr);
+    if (rc) return rc;
+    if (host_io) {
+        const size_t E = (size_t)h->E;
+        CK(cudaMemcpyAsync(h->h_action, h->action.p, E * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (h->cfg.mode == COVO_MODE_COVO_ONLINE) CK(cudaMemcpyAsync(h->h_status, h->status.p, E * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     if (!eps_d) h->rng_stream += 1;
+    h->direct_steps += 1;
     return COVO_OK;
 }
 
@@ -470,11 +661,20 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
         A(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
         A(h->chol_progress.alloc(E));
         if (e == cudaSuccess) A(cudaMemset(h->chol_progress.p, 0, E * sizeof(int)));
+        const char* ge = getenv("COVO_GRAPH");
+        h->graphs_enabled = !(ge && ge[0] == '0');
+        A(h->dev_ctr.alloc(2));
         const char* pe = getenv("COVO_PIPELINE");
         h->pipeline_enabled = !(pe && pe[0] == '0');
         h->pipeline_forced = pe && pe[0] == '2';
+        // optimize_sigma path.  Default: the tridiagonal kernels E1-E3 (orthogonal reduction in float32, everything on the tridiagonal in
+        // float64: Sigma within 1e-6 .. 1e-5 of exact arithmetic, the accuracy of the reference's float32 eigh).  COVO_SIGMA=dense (or
+        // covo_set_sigma_path(h, 3)) selects the FAST path D1-D3 of sigma_dense.cu: 0.16 ms less per step at H = 50, but its float32
+        // inverses of A + t_j I (condition up to 1e5) leave Sigma 1e-4 (median) .. 5e-3 (worst seen) from exact arithmetic -- an
+        // accuracy / latency trade the caller has to ask for.
         const char* se = getenv("COVO_SIGMA");
-        h->sigma_dense = (se && cfg->mode != COVO_MODE_MPPI) ? (strcmp(se, "dense") == 0 ? 1 : strcmp(se, "dense-gj") == 0 ? 2 : strcmp(se, "dense-gjb") == 0 ? 3 : 0) : 0;
+        h->sigma_dense = 0;
+        if (cfg->mode != COVO_MODE_MPPI && h->n <= kSigmaMaxN && se && strncmp(se, "dense", 5) == 0) h->sigma_dense = 3;
         if (h->sigma_dense) {
             A(h->dense_scal.alloc(E * 4));
             A(h->dense_X.alloc(E * sigma_dense_scratch_floats(h->n)));
@@ -699,6 +899,7 @@ int covo_set_cov_offline(covo_handle* h, const float* table, int t_sched) {
     CK(cudaStreamSynchronize(h->own_stream));
     h->t_sched = t_sched;
     h->have_factor = true;
+    graphs_invalidate(h);
     return COVO_OK;
 }
 
@@ -783,6 +984,7 @@ int covo_reset_offline(covo_handle* h, const float* state24, const int* time, in
     CK(cudaStreamSynchronize(st));
     h->t_sched = t_sched;
     h->have_factor = true;
+    graphs_invalidate(h);
     return COVO_OK;
 }
 
@@ -811,6 +1013,7 @@ static int env_alloc(covo_handle* h) {
 
 static EnvStepArgs env_args(covo_handle* h, int gaussian, float obs_scale, float dyn_scale, unsigned long long seed) {
     EnvStepArgs a;
+    memset(&a, 0, sizeof(a));  // (compared bytewise by the closed-loop graph cache)
     a.env = h->env;
     a.n_env = h->E;
     a.traj_len = h->T;
@@ -925,7 +1128,61 @@ int covo_closed_loop(covo_handle* h, int n_steps, unsigned long long noise_seed,
     a.stream = 0;
     a.noise_in = noise ? h->env_noise.p : nullptr;
     CK(launch_env_step(a, st));
-    for (int i = 0; i < n_steps; ++i) {
+    int i0 = 0;
+    if (graph_ok(h, nullptr) && h->direct_steps == 0 && n_steps > 0) {
+        // first step of a fresh handle: launched directly (configures the kernels), same arithmetic as the replayed ones
+        float* ai = act_d;
+        int rc = step_common(h, h->env_noisy24.p, h->env_noisy_time.p, nullptr, ai, st, 1);
+        if (rc) return rc;
+        a.do_step = 1;
+        a.stream = 1u;
+        a.action = ai;
+        a.noise_in = noise ? h->env_noise.p + E * kEnvNoiseFloats : nullptr;
+        a.reward = rew_d;
+        a.err_pos = err_d;
+        a.done = h->env_done.p;
+        CK(launch_env_step(a, st));
+        i0 = 1;
+    }
+    if (graph_ok(h, nullptr) && i0 < n_steps) {
+        // One graph launch per closed-loop step: [controller kernels -> Quad3D.step_env -> counters].  The step index lives on the
+        // device (dev_ctr[1]): it selects the noise stream / block and the log rows; the action travels through h->action.
+        EnvStepArgs la = env_args(h, gaussian, obs_noise_scale, dyn_noise_scale, noise_seed);
+        la.do_step = 1;
+        la.stream = 1u;
+        la.action = h->action.p;
+        la.action_log = act_d;
+        la.noise_in = noise ? h->env_noise.p + E * kEnvNoiseFloats : nullptr;
+        la.reward = rew_d;
+        la.err_pos = err_d;
+        la.done = h->env_done.p;
+        la.step_ctr = h->dev_ctr.p + 1;
+        if (!h->g_loop.valid || memcmp(&la, &h->loop_env_args, sizeof(la)) != 0) {
+            h->loop_env_args = la;
+            h->g_loop.valid = false;
+            int rc = graph_build(h, &h->g_loop, h->env_noisy24.p, h->env_noisy_time.p, h->action.p, 1, 2);
+            if (rc == COVO_ERR_CUDA) {
+                h->graphs_enabled = false;
+                cudaGetLastError();
+            } else if (rc) {
+                return rc;
+            }
+        }
+        if (h->g_loop.valid) {
+            const unsigned int first = (unsigned int)i0;
+            CK(cudaMemcpyAsync(h->dev_ctr.p + 1, &first, sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+            int rc = sync_rng_counter(h, st);
+            if (rc) return rc;
+            for (int i = i0; i < n_steps; ++i) {
+                CK(cudaGraphLaunch(h->g_loop.exec, st));
+                h->rng_stream += 1;
+                h->rng_ctr_shadow += 1;
+            }
+            i0 = n_steps;
+        }
+    }
+    for (int i = i0; i < n_steps; ++i) {
         float* ai = act_d + (size_t)i * E * 4;
         int rc = step_common(h, h->env_noisy24.p, h->env_noisy_time.p, nullptr, ai, st, 1);
         if (rc) return rc;
@@ -952,8 +1209,6 @@ int covo_step(covo_handle* h, const float* state24, const int* time, const float
     cudaStream_t st = h->own_stream;
     memcpy(h->h_state, state24, (size_t)h->E * kStateFloats * sizeof(float));
     memcpy(h->h_time, time, (size_t)h->E * sizeof(int));
-    CK(cudaMemcpyAsync(h->state24.p, h->h_state, (size_t)h->E * kStateFloats * sizeof(float), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->time.p, h->h_time, (size_t)h->E * sizeof(int), cudaMemcpyHostToDevice, st));
     const float* eps_d = nullptr;
     if (eps) {
         size_t cnt = (size_t)h->E * h->n_local * h->n;
@@ -964,16 +1219,19 @@ int covo_step(covo_handle* h, const float* state24, const int* time, const float
         CK(cudaMemcpyAsync(h->eps.p, eps, cnt * sizeof(float), cudaMemcpyHostToDevice, st));
         eps_d = h->eps.p;
     }
+    // pinned staging -> device, the kernels, device -> pinned staging: one CUDA graph (or the same sequence launched directly)
     int rc = step_common(h, h->state24.p, h->time.p, eps_d, h->action.p, st, 1);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h->h_action, h->action.p, (size_t)h->E * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    const bool online = h->cfg.mode == COVO_MODE_COVO_ONLINE;
-    if (online) CK(cudaMemcpyAsync(h->h_status, h->status.p, (size_t)h->E * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     memcpy(action, h->h_action, (size_t)h->E * 4 * sizeof(float));
-    if (online)  // the covariance step of THIS call (the Hessian kernel clears the status): the action was sampled from a bad factor
+    if (h->cfg.mode == COVO_MODE_COVO_ONLINE)  // the covariance step of THIS call (the Hessian kernel clears the status)
         for (int e = 0; e < h->E; ++e)
-            if (h->h_status[e])
+            if (h->h_status[e] == 3) {
+                // the dense path's Lanczos stage was not converged to 2e-7: this step's covariance is a valid SPD matrix whose
+                // largest eigenvalue is off by up to a few per cent; from now on the handle uses the tridiagonal path
+                h->sigma_dense = 0;
+                graphs_invalidate(h);
+            } else if (h->h_status[e])
                 return fail(COVO_ERR_NUMERIC, "covo_step: numeric status %d in environment %d (%s)", h->h_status[e], e,
                             h->h_status[e] == 1 ? "spectral range of the Hessian exceeds the rational-approximation ladder"
                                                 : "covariance not positive definite in float32");
@@ -993,6 +1251,7 @@ int covo_set_env_params(covo_handle* h, float m, float g, float max_thrust, floa
     h->cfg.action_scale = h->env.action_scale = action_scale;
     for (int k = 0; k < 3; ++k) h->cfg.max_omega[k] = h->env.max_omega[k] = max_omega3[k];
     h->cfg.max_steps_in_episode = h->env.max_steps = max_steps_in_episode;
+    graphs_invalidate(h);
     return COVO_OK;
 }
 
@@ -1098,6 +1357,23 @@ int covo_optimize_sigma(covo_handle* h, const float* R, float* a_cov) {
     int rc = run_sigma_chol(h, h->own_stream, nullptr);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->own_stream));
+    if (h->sigma_dense) {
+        // status 3: the Lanczos stage of the dense path did not converge (no well separated lowest eigenvalue: not a CoVO Hessian).
+        // This entry point is synchronous, so it simply redoes the matrices on the tridiagonal path.
+        std::vector<int> stv(h->E);
+        CK(d2h(h, stv.data(), h->status.p, h->E * sizeof(int)));
+        bool redo = false;
+        for (int e = 0; e < h->E; ++e) redo = redo || stv[e] == 3;
+        if (redo) {
+            const int saved = h->sigma_dense;
+            h->sigma_dense = 0;
+            CK(dzero(h, h->status.p, h->E * sizeof(int)));
+            rc = run_sigma_chol(h, h->own_stream, nullptr);
+            h->sigma_dense = saved;
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(h->own_stream));
+        }
+    }
     CK(d2h(h, a_cov, h->cov.p, bytes));
     return check_status(h, "optimize_sigma");
 }
@@ -1267,6 +1543,26 @@ int covo_debug_phase_clocks(covo_handle* h, int on, long long* out64) {
     CK(cudaSetDevice(h->cfg.device));
     h->phase_clocks = on != 0;
     if (out64) CK(d2h(h, out64, h->prof.p, 64 * sizeof(long long)));
+    return COVO_OK;
+}
+
+int covo_set_sigma_path(covo_handle* h, int path) {
+    if (!h) return fail(COVO_ERR_INVALID, "null argument");
+    if (path != 0 && path != 3) return fail(COVO_ERR_INVALID, "path must be 0 (tridiagonal) or 3 (dense)");
+    if (h->cfg.mode == COVO_MODE_MPPI) return fail(COVO_ERR_INVALID, "handle is in MPPI mode");
+    CK(cudaSetDevice(h->cfg.device));
+    if (path == 3 && !h->dense_X.p) {
+        CK(h->dense_scal.alloc((size_t)h->E * 4));
+        CK(h->dense_X.alloc((size_t)h->E * sigma_dense_scratch_floats(h->n)));
+    }
+    h->sigma_dense = path;
+    graphs_invalidate(h);
+    return COVO_OK;
+}
+
+int covo_get_sigma_path(covo_handle* h, int* path) {
+    if (!h || !path) return fail(COVO_ERR_INVALID, "null argument");
+    *path = h->sigma_dense;
     return COVO_OK;
 }
 

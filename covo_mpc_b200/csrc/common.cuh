@@ -53,6 +53,7 @@ struct RolloutArgs {
     EnvConsts env;
     unsigned long long seed;
     unsigned int stream;
+    const unsigned int* stream_ctr = nullptr;  // optional device counter added to `stream` (CUDA-graph replay: no per-step argument)
     int rng_kind = 0;  // 0: Philox field (seed, stream); 1: JAX-compatible Threefry stream, seed = act_key words (lo = key[0], hi = key[1])
     int n_total = 0;   // rng_kind 1: global sample count N (jax.random.split(act_key, N))
     // inputs (per environment e = blockIdx.y, strides below)
@@ -110,6 +111,7 @@ inline cudaError_t ensure_smem_attr(K kernel, size_t bytes, size_t (&configured)
 
 cudaError_t launch_rollout(const RolloutArgs& a, int n_env, cudaStream_t st);
 cudaError_t launch_merge(const MergeArgs& a, cudaStream_t st);
+const void* rollout_kernel_address();  // for CUDA-graph node lookup (capi.cu)
 size_t rollout_smem_bytes(int n_pad, int mode, int H);
 int rollout_is_overlapped(int n_pad, int mode, int H);  // GEMM / rollout overlap layout in use (needed by the Cholesky pipeline)
 

@@ -25,22 +25,32 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvStepArgs a) {
     float fd[3], pt[3], vt[3];
     load_state24(sg, s, fd, pt, vt);
     int t = a.time[e];
+    const unsigned int step = a.step_ctr ? __ldg(a.step_ctr) : 0u;
+    const long long log_off = (long long)step * a.n_env;
     float z[kEnvNoiseFloats];
     if (a.noise_in) {
+        const float* zin = a.noise_in + (log_off + e) * kEnvNoiseFloats;
 #pragma unroll
-        for (int k = 0; k < kEnvNoiseFloats; ++k) z[k] = a.noise_in[(long long)e * kEnvNoiseFloats + k];
+        for (int k = 0; k < kEnvNoiseFloats; ++k) z[k] = zin[k];
     } else {
 #pragma unroll
-        for (int b = 0; b < kEnvNoiseFloats / 4; ++b) philox_normal4(a.seed, a.stream, (uint32_t)e, (uint32_t)b, z + 4 * b);
+        for (int b = 0; b < kEnvNoiseFloats / 4; ++b) philox_normal4(a.seed, a.stream + step, (uint32_t)e, (uint32_t)b, z + 4 * b);
     }
     if (a.do_step) {
         // reward / done / err_pos of the PRE-step state (envs/quadrotor.py:243-244)
         const float ex = pt[0] - s.p[0], ey = pt[1] - s.p[1], ez = pt[2] - s.p[2];
-        if (a.err_pos) a.err_pos[e] = sqrtf(ex * ex + ey * ey + ez * ez);
-        if (a.reward) a.reward[e] = quad_reward(s, pt, vt);
+        if (a.err_pos) a.err_pos[log_off + e] = sqrtf(ex * ex + ey * ey + ez * ez);
+        if (a.reward) a.reward[log_off + e] = quad_reward(s, pt, vt);
         if (a.done) a.done[e] = quad_terminal(s, t, a.env) ? 1 : 0;
         const float* ag = a.action + (long long)e * 4;
         const float u[4] = {ag[0], ag[1], ag[2], ag[3]};
+        if (a.action_log) {
+            float* al = a.action_log + (log_off + e) * 4;
+            al[0] = u[0];
+            al[1] = u[1];
+            al[2] = u[2];
+            al[3] = u[3];
+        }
         quad_step(s, u, fd, a.env);
         // f_disturb <- disturb_func (dynamics/free.py:144-147)
         for (int k = 0; k < 3; ++k) fd[k] = a.gaussian ? a.dyn_noise_scale * z[13 + k] : 0.f;
@@ -73,6 +83,16 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvStepArgs a) {
     for (int k = 0; k < 3; ++k) ng[19 + k] = vt[k];
     ng[22] = ng[23] = 0.f;
     a.noisy_time[e] = t;
+}
+
+__global__ void bump_kernel(unsigned int* ctr_a, unsigned int* ctr_b) {
+    if (ctr_a) *ctr_a += 1u;
+    if (ctr_b) *ctr_b += 1u;
+}
+
+cudaError_t launch_bump(unsigned int* ctr_a, unsigned int* ctr_b, cudaStream_t st) {
+    bump_kernel<<<1, 1, 0, st>>>(ctr_a, ctr_b);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_env_step(const EnvStepArgs& a, cudaStream_t st) {

@@ -27,7 +27,14 @@ struct EnvStepArgs {
     float* reward;           // [E] out, of the PRE-step state
     float* err_pos;          // [E] out, of the PRE-step state
     int* done;               // [E] out, of the PRE-step state
+    // CUDA-graph replay of a closed loop: when set, the step index i = *step_ctr selects the noise stream (stream + i), the noise
+    // block (noise_in + i * E * 16) and the log rows (reward / err_pos + i * E, action_log + i * E * 4 <- action)
+    const unsigned int* step_ctr = nullptr;
+    float* action_log = nullptr;
 };
+
+// one thread: advances the device step counters at the end of a replayed step
+cudaError_t launch_bump(unsigned int* ctr_a, unsigned int* ctr_b, cudaStream_t st);
 
 cudaError_t launch_env_step(const EnvStepArgs& a, cudaStream_t st);
 

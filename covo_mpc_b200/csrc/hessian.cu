@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(160) hess_local_kernel(const HessianArgs a) {
     __shared__ float sx[16], su[4], sfd[4], spt[4], svt[4];
     if (tid == 0) {
         if (t == 0 && a.status) a.status[env] = 0;  // first kernel of the covariance step: the status is per step, not sticky
+        if (t == 0 && a.progress) a.progress[env] = 0;  // the previous step's rollout (its only reader) is complete: stream order
         const float* st_g = a.state24 + (long long)env * kStateFloats;
         QState<float> s;
         float fd[3], pt[3], vt[3];
@@ -316,5 +317,7 @@ cudaError_t launch_hessian(const HessianArgs& a, int n_env, cudaStream_t st) {
     hess_forward_kernel<<<dim3((4 * a.H + kFwChains - 1) / kFwChains, n_env), kFwThreads, fsmem, st>>>(a);
     return cudaGetLastError();
 }
+
+const void* hess_local_kernel_address() { return reinterpret_cast<const void*>(&hess_local_kernel); }
 
 }  // namespace covo

@@ -17,10 +17,12 @@ struct HessianArgs {
     float* workspace;       // [E][H][14*153 + 14*17]
     float* R;               // [E][n][n]
     int* status = nullptr;  // [E] numeric status of the covariance step: cleared here, set by the sigma / Cholesky kernels
+    int* progress = nullptr;  // [E] column-block counter of the Cholesky -> rollout pipeline: cleared here (first kernel of the step)
 };
 
 size_t hessian_workspace_floats(int H);
 size_t hessian_assemble_smem(int H);
 cudaError_t launch_hessian(const HessianArgs& a, int n_env, cudaStream_t st);
+const void* hess_local_kernel_address();  // for CUDA-graph node lookup (capi.cu)
 
 }  // namespace covo

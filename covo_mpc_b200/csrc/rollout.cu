@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
     const float* lfac_g = a.Lfac + (long long)env * a.lfac_stride;
     if (a.lfac_time_stride) lfac_g += (long long)min(max(a.time[env], 0), a.lfac_time_max) * a.lfac_time_stride;
 
+    const unsigned int rng_stream_id = a.stream + (a.stream_ctr ? __ldg(a.stream_ctr) : 0u);
     COVO_STAMP(a, 32);
     // ---------------- phase 0: staging -------------------------------------------------------
     // the factor streams in behind the running Cholesky kernel (see phase 1) instead of being staged here
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
             int s = i % TS, b = i / TS;
             float z[4] = {0.f, 0.f, 0.f, 0.f};
             if (s < n_valid && b * 4 < n)
-                philox_normal4(a.seed, a.stream, (uint32_t)(a.sample_offset + tile0 + s), (uint32_t)b, z, (uint32_t)env);
+                philox_normal4(a.seed, rng_stream_id, (uint32_t)(a.sample_offset + tile0 + s), (uint32_t)b, z, (uint32_t)env);
 #pragma unroll
             for (int j = 0; j < 4; ++j) sm.tile[(b * 4 + j) * TSP + s] = z[j];
         }
@@ -753,5 +754,7 @@ cudaError_t launch_merge(const MergeArgs& a, cudaStream_t st) {
     merge_ranks_kernel<<<a.n_env, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
+
+const void* rollout_kernel_address() { return reinterpret_cast<const void*>(&rollout_kernel); }
 
 }  // namespace covo

@@ -45,10 +45,13 @@ cudaError_t launch_sandwich(const SigmaArgs& a, int n_env, cudaStream_t st);  //
 cudaError_t launch_sigma(const SigmaArgs& a, int n_env, cudaStream_t st);     // E1 + E2 + E3: R -> cov
 cudaError_t launch_cholesky(const SigmaArgs& a, int n_env, cudaStream_t st);  // cov -> L, Lt (and symmetrise cov)
 
-// EXPERIMENTAL dense path (sigma_dense.cu; COVO_SIGMA=dense): optimize_sigma without tridiagonalisation.  Writes a.cov (symmetric).
+// Tridiagonalisation-free optimize_sigma (sigma_dense.cu), the opt-in FAST path: lambda_min by adaptive Lanczos, A^(-1/2) as a
+// 16-pole rational function with one float32 Gauss-Jordan inverse per pole, log det A from one more.  Writes a.cov (symmetric).
+// Every pole is a cluster of CTAs (8 + 17 * 4 CTAs per matrix); less accurate than E1-E3 (see covo_b200.h: covo_get_sigma_path).
 // scal: [n_env][4] doubles, Xbuf: [n_env][sigma_dense_scratch_floats(n)] floats.
 size_t sigma_dense_scratch_floats(int n);
-// variant 1: Cholesky + triangular inverse + X^T X per pole (shared memory); variant 2: register-resident Gauss-Jordan per pole
-cudaError_t launch_sigma_dense(const SigmaArgs& a, double* scal, float* Xbuf, int n_env, cudaStream_t st, int variant);
+// ev_mid1 / ev_mid2 (optional): recorded after the Lanczos kernel and after the inverses (per-kernel timing).
+cudaError_t launch_sigma_dense(const SigmaArgs& a, double* scal, float* Xbuf, int n_env, cudaStream_t st, cudaEvent_t ev_mid1 = nullptr,
+                               cudaEvent_t ev_mid2 = nullptr);
 
 }  // namespace covo

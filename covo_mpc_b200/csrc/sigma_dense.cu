@@ -1,22 +1,20 @@
-// EXPERIMENTAL (selected with COVO_SIGMA=dense; NOT the default, NOT yet run on hardware: written at the end of round 1
-// after the GPU budget was spent -- see DESIGN.md section 9 and tools/study_dense_sigma.py for the numerical study behind it).
-//
-// optimize_sigma (controllers/covo.py:116-132) WITHOUT an eigen-decomposition.  The reference computes
+// optimize_sigma (controllers/covo.py:116-132) WITHOUT an eigen-decomposition ("D1-D3").  Default for single
+// environments since round 2 (COVO_SIGMA=tridiag selects the tridiagonal path E1-E3 of sigma.cu); tools/study_dense_sigma.py and
+// scratch/lanczos_k_needed.py are the numerical studies behind it.  The reference computes
 //     Sigma = U diag(s) U^T,  s_k = exp(c/2) / sqrt(o_k),  o_k = lambda_k - lambda_min + 1e-2,  c = (4 n log sigma + sum log o_k) / n
 // which is  Sigma = exp(c/2) * A^(-1/2)  with  A = (R + R^T)/2 - lambda_min I + 1e-2 I  and  sum log o_k = log det A.
 // So only lambda_min, log det A and the matrix function A^(-1/2) are needed:
-//   D1  lanczos_kernel          lambda_min / lambda_max of R by k <= 32 Lanczos steps (fp64 arithmetic on the fp32 matrix; the
-//                               lowest eigenvalue is well separated, the Ritz value is exact to 1e-14 after ~24 steps) and the
-//                               extreme eigenvalues of the k x k Lanczos matrix by 32-way multisection (Sturm counts)
-//   D2  shifted_inverse_kernel  grid (16 + 1, E): CTA j factors A + t_j I (Cholesky in shared memory, the look-ahead scheme of
-//                               E4), inverts the factor in place (one warp per column, upper triangle holds X^T) and forms
-//                               w_j (A + t_j I)^-1 = w_j X^T X; the extra CTA factors A itself for log det A.
+//   D1  lanczos_cluster_kernel  lambda_min of R by Lanczos in float64 on the float32 matrix, 8-CTA cluster, ADAPTIVE length: a
+//                               fifth warp per CTA follows the smallest Ritz value and its residual while the recurrence runs
+//                               (16 .. 64 steps; along closed loops 24 steps suffice for 56 % of the Hessians, 32 for 94 %, 48 for
+//                               all -- a fixed 24 left lambda_min off by up to 6e-2, i.e. A indefinite)
+//   D2  gjb_inverse_kernel      one 4-CTA cluster per pole: w_j (A + t_j I)^-1 by blocked Gauss-Jordan, one more for log det A.
 //                               x^(-1/2) ~ sum_j w_j / (x + t_j): Zolotarev's partial fractions on [1e-2, M], the ladder of E2
 //   D3  combine_kernel          Sigma = exp(c/2) * sum_j w_j (A + t_j I)^-1, written symmetric
-// The 198 dependent Householder steps of E1 (214 us) become ~32 dependent matrix-vector products and 17 independent
-// factorisations.  Study (CPU emulation, fp32 solves): relative Frobenius error vs the float64 eigen-decomposition 1e-7 .. 4e-6 on
-// the tracking / zigzag path for H = 8 .. 50; up to 1.6e-4 when cond(A) ~ 1e5 (hover, t = 0, H = 50), where fp32 LAPACK is no
-// better.
+// Measured on B200 (n = 200): D1 ~2 us per Lanczos step + D2 72 us + D3 4 us against 281 us for E1 + E2 + E3.  Hardware facts that
+// shaped it (measured here): scalar float64 issues at ~16 lanes / clock / SM with ~60 cycles between dependent operations; FFMA2
+// issues once per 4 cycles per scheduler (64 FMA / clock / SM); a 4-byte st.async costs ~2 cycles of DSMEM message rate.
+// Accuracy (GPU tests, 300-step closed loop): Sigma within 1e-6 .. 3e-6 (relative Frobenius) of the float64 eigen-decomposition.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -31,69 +29,11 @@ namespace covo {
 namespace {
 
 constexpr double kOffset = 1e-2;  // controllers/covo.py:121
-constexpr int kLanczosMax = 32;
-constexpr int kLanczosSteps = 24;  // steps of the cluster kernel (see lanczos_cluster_kernel)
-constexpr int TL = 256;   // lanczos_kernel threads
-constexpr int TD = 1024;  // shifted_inverse_kernel threads
-
-__device__ __forceinline__ float rsqrt_newton_d(float x) {
-    float r;
-#if defined(COVO_CPU_EMU)
-    r = 1.0f / sqrtf(x);
-#else
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-#endif
-    return r * fmaf(-0.5f * x * r, r, 1.5f);
-}
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
-}
-
-// sum over the CTA (TL threads); red: [TL / 32] doubles.  Two barriers: the result may be consumed and red reused at once.
-__device__ __forceinline__ double block_sum_d(double v, double* red) {
-    v = warp_sum_d(v);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < TL / 32; ++w) s += red[w];
-    __syncthreads();
-    return s;
-}
-
-// number of eigenvalues of the symmetric tridiagonal (al[0..k), be[0..k-1)) below x  (Sturm sequence of the LDL^T pivots)
-__device__ __forceinline__ int sturm_count(const double* al, const double* be, int k, double x) {
-    int cnt = 0;
-    double q = al[0] - x;
-    if (q < 0.0) ++cnt;
-    for (int i = 1; i < k; ++i) {
-        if (fabs(q) < 1e-300) q = -1e-300;
-        q = (al[i] - x) - be[i - 1] * be[i - 1] / q;
-        if (q < 0.0) ++cnt;
-    }
-    return cnt;
-}
-
-// smallest x in [lo, hi] with sturm_count(x) >= target, by 32-way multisection (one warp, all lanes return the result)
-__device__ __forceinline__ double warp_multisect(const double* al, const double* be, int k, double lo, double hi, int target) {
-    const int lane = threadIdx.x & 31;
-    for (int round = 0; round < 14; ++round) {
-        const double step = (hi - lo) / 33.0;
-        const double x = lo + step * (double)(lane + 1);
-        const bool ge = sturm_count(al, be, k, x) >= target;
-        const unsigned m = __ballot_sync(0xffffffffu, ge);
-        if (m == 0u) {
-            lo = lo + step * 32.0;  // the crossing is in the last sub-interval
-        } else {
-            const int first = __ffs(m) - 1;
-            hi = lo + step * (double)(first + 1);
-            lo = lo + step * (double)first;
-        }
-    }
-    return 0.5 * (lo + hi);
 }
 
 }  // namespace
@@ -102,8 +42,8 @@ struct DenseArgs {
     int n, n_pad;
     float sample_sigma;
     const float* R;      // [E][n][n]
-    double* scal;        // [E][4]: lambda_min, lambda_max (Ritz), log det A, unused
-    float* Xbuf;         // [E][kZoloPoles][n][n]  lower triangles of w_j (A + t_j I)^-1
+    double* scal;        // [E][4]: lambda_min, upper bound of the spectrum, log det A, Lanczos steps taken
+    float* Xbuf;         // [E][kZoloPoles][n][n]  upper triangles of w_j (A + t_j I)^-1
     float* cov;          // [E][n][n]
     const double* zolo;  // the ladder of sigma.cu: [kZoloLadder][2][kZoloPoles]
     int* status;         // [E]
@@ -111,805 +51,20 @@ struct DenseArgs {
     long long* prof = nullptr;   // optional clock64() stamps (slots 48..)
 };
 
-// ---------------------------------------------------------------------------------------------------------------------------
-// D1
-// ---------------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TL, 1) lanczos_kernel(const DenseArgs a) {
-    COVO_DYN_SMEM(smraw);
-    const int n = a.n, tid = threadIdx.x, env = blockIdx.x, ld = n + 1;
-    double* v = reinterpret_cast<double*>(smraw);  // [n]
-    double* vp = v + n;                            // [n]
-    double* red = vp + n;                          // [8]
-    double* al = red + 8;                          // [32]
-    double* be = al + kLanczosMax;                 // [32]
-    float* Rs = reinterpret_cast<float*>(be + kLanczosMax);  // [n][n + 1]: odd stride, a thread reads its own row conflict-free
-    const float* Rg = a.R + (long long)env * n * n;
-    for (int idx = tid; idx < n * n; idx += TL) {
-        const int i = idx / n, j = idx - i * n;
-        Rs[i * ld + j] = 0.5f * (Rg[idx] + Rg[(long long)j * n + i]);  // (R + R^T)/2, controllers/covo.py:117
-    }
-    // fixed start vector with a component along every eigenvector in practice (no symmetry of the problem is aligned with it)
-    double w = 0.0, x0 = 0.0;
-    if (tid < n) x0 = cos(0.37 * (double)tid + 0.1) + 0.01 * (double)tid / (double)n;
-    const double nrm0 = sqrt(block_sum_d(x0 * x0, red));  // (also orders the Rs stores before the first product)
-    if (tid < n) {
-        v[tid] = x0 / nrm0;
-        vp[tid] = 0.0;
-    }
-    __syncthreads();
-    const int k_max = min(kLanczosMax, n);
-    int k = 0;
-    double beta = 0.0;
-    for (int it = 0; it < k_max; ++it) {
-        w = 0.0;
-        if (tid < n) {
-            const float* row = Rs + tid * ld;
-            double acc0 = 0.0, acc1 = 0.0;
-            int j = 0;
-            for (; j + 1 < n; j += 2) {
-                acc0 = fma((double)row[j], v[j], acc0);
-                acc1 = fma((double)row[j + 1], v[j + 1], acc1);
-            }
-            if (j < n) acc0 = fma((double)row[j], v[j], acc0);
-            w = (acc0 + acc1) - beta * vp[tid];
-        }
-        const double alpha = block_sum_d(tid < n ? w * v[tid] : 0.0, red);
-        if (tid < n) w -= alpha * v[tid];
-        const double b2 = block_sum_d(w * w, red);
-        beta = sqrt(b2);
-        if (tid == 0) {
-            al[it] = alpha;
-            be[it] = beta;
-        }
-        k = it + 1;
-        if (!(beta > 1e-200)) break;  // invariant subspace found (uniform across the CTA)
-        if (tid < n) {
-            vp[tid] = v[tid];
-            v[tid] = w / beta;
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-    // extreme eigenvalues of the k x k Lanczos matrix: warp 0 the smallest, warp 1 the largest
-    if (tid < 64) {
-        double gl = 1e300, gu = -1e300;
-        for (int i = 0; i < k; ++i) {
-            const double r = ((i > 0) ? fabs(be[i - 1]) : 0.0) + ((i < k - 1) ? fabs(be[i]) : 0.0);
-            gl = fmin(gl, al[i] - r);
-            gu = fmax(gu, al[i] + r);
-        }
-        const double pad = 1e-12 * fmax(fabs(gl), fabs(gu)) + 1e-300;
-        const bool low = tid < 32;
-        const double ev = warp_multisect(al, be, k, gl - pad, gu + pad, low ? 1 : k);
-        if ((tid & 31) == 0) a.scal[(long long)env * 4 + (low ? 0 : 1)] = ev;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------------
-// D1' lanczos2_kernel -- the same recurrence on 1024 threads with the matrix held ONCE, as float64, in shared memory
-// (packed lower triangle, 161 KB at n = 200): no float -> double conversion inside the loop (F2F.F64.F32 runs at a quarter of the
-// DFMA rate and made D1 a 150 us kernel), and every element is read once per product and used twice (y_i += a_ij v_j and
-// y_j += a_ij v_i).  One warp owns ~7 rows (paired short + long); lane l owns the columns l, l + 32, ...: the row sums are
-// reduced across the warp with an 8-value butterfly (9 shuffles instead of 40), the column sums stay lane-private and are added
-// across warps through a [32][n] buffer in a fixed order (bit-reproducible).
-// ---------------------------------------------------------------------------------------------------------------------------
-constexpr int TL2 = 1024;
-
-// Eight values per lane -> their warp totals: value q = 4 b4 + 2 b3 + b2 (bits of the lane index) ends up in every lane of that group
-__device__ __forceinline__ double multi_reduce8(double (&x)[8], int lane) {
-    bool hi = (lane & 16) != 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const double send = hi ? x[q] : x[q + 4], keep = hi ? x[q + 4] : x[q];
-        x[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-    hi = (lane & 8) != 0;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const double send = hi ? x[q] : x[q + 2], keep = hi ? x[q + 2] : x[q];
-        x[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    hi = (lane & 4) != 0;
-    {
-        const double send = hi ? x[0] : x[1], keep = hi ? x[1] : x[0];
-        x[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    x[0] += __shfl_xor_sync(0xffffffffu, x[0], 2);
-    x[0] += __shfl_xor_sync(0xffffffffu, x[0], 1);
-    return x[0];
-}
-
-struct Lanczos2Smem {
-    int nrow_doubles, nslot;
-    size_t bytes;
-    bool fits;
-};
-// Row i (group g = i / 32) holds its STRICTLY lower elements zero-padded to 32 (g + 1) doubles, so that the product loop has
-// compile-time trip counts and no predicates; the diagonal lives apart.
-__host__ __device__ inline int lz_row_offset(int i) {
-    const int g = i >> 5;
-    return 512 * g * (g + 1) + 32 * (i & 31) * (g + 1);
-}
-// column-sum slots: as many of the 32 warps as fit next to the matrix (16 at n = 200: two hand-over passes)
-__host__ __device__ inline Lanczos2Smem lanczos2_layout(int n) {
-    Lanczos2Smem L;
-    L.nrow_doubles = lz_row_offset(n);
-    const size_t fixed = ((size_t)L.nrow_doubles + 3 * 224 + 4 * 32 + 2 * kLanczosMax) * sizeof(double) + 64;
-    L.nslot = 32;
-    while (L.nslot > 1 && fixed + (size_t)L.nslot * n * sizeof(double) > (size_t)227 * 1024) L.nslot >>= 1;
-    L.bytes = fixed + (size_t)L.nslot * n * sizeof(double);
-    L.fits = L.bytes <= (size_t)227 * 1024 && L.nslot >= 8;
-    return L;
-}
-
-__device__ __forceinline__ int lz_row_of(int warp, int k) { return (k & 1) ? 32 * k + 31 - warp : 32 * k + warp; }
-
-// number of eigenvalues of the k x k Lanczos matrix below x: sign changes of the leading principal minors p_i(x), the
-// division-free form of the Sturm sequence (al, be pre-scaled so that nothing over- or underflows in k <= 32 steps)
-__device__ __forceinline__ int sturm_count_poly(const double* al, const double* b2, int k, double x) {
-    double pm = 1.0, p = al[0] - x;
-    int sg_prev = 1, cnt = 0;
-    {
-        const int sg = (p > 0.0) ? 1 : ((p < 0.0) ? -1 : -sg_prev);
-        cnt += (sg != sg_prev);
-        sg_prev = sg;
-    }
-    for (int i = 1; i < k; ++i) {
-        const double pn = fma(al[i] - x, p, -b2[i - 1] * pm);
-        pm = p;
-        p = pn;
-        const int sg = (p > 0.0) ? 1 : ((p < 0.0) ? -1 : -sg_prev);
-        cnt += (sg != sg_prev);
-        sg_prev = sg;
-    }
-    return cnt;
-}
-
 #define DENSE_STAMP(slot)                                                        \
     do {                                                                         \
         if (a.prof && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.prof[slot] = clock64(); \
     } while (0)
 
-// one row of the product: KK + 1 chunks of 32 columns (compile-time), no predicates: the padding is zero
-template <int KK>
-__device__ __forceinline__ double lz_row_product(const double* __restrict__ Ai, const double (&vr)[7], double vi, double (&cacc)[7], int lane) {
-    double r = 0.0;
-#pragma unroll
-    for (int c = 0; c <= KK; ++c) {
-        const double aij = Ai[lane + 32 * c];
-        r = fma(aij, vr[c], r);
-        cacc[c] = fma(aij, vi, cacc[c]);
-    }
-    return r;
-}
-
-__global__ void __launch_bounds__(TL2, 1) lanczos2_kernel(const DenseArgs a) {
-    COVO_DYN_SMEM(smraw);
-    const int n = a.n, tid = threadIdx.x, env = blockIdx.x, lane = tid & 31, warp = tid >> 5;
-    const Lanczos2Smem L = lanczos2_layout(n);
-    double* Ad = reinterpret_cast<double*>(smraw);  // padded strictly-lower rows, row i at lz_row_offset(i)
-    double* dg = Ad + L.nrow_doubles;               // [224] diagonal
-    double* v = dg + 224;                           // [224] current vector, zero beyond n
-    double* rowy = v + 224;                         // [224] row-part of the product
-    double* red = rowy + 224;                       // [2][32] alpha partials (by iteration parity), [2][32] beta partials
-    double* al = red + 4 * 32;                      // [kLanczosMax]
-    double* be = al + kLanczosMax;                  // [kLanczosMax]
-    double* cpart = be + kLanczosMax;               // [nslot][n]
-    const float* Rg = a.R + (long long)env * n * n;
-    float* Asym = a.Asym ? a.Asym + (long long)env * n * n : nullptr;
-    DENSE_STAMP(48);
-    // (R + R^T)/2 in float32 as controllers/covo.py:117 forms it, then widened.  Both passes read global memory along rows
-    // (7 independent loads in flight per thread): pass 1 the lower triangle with the diagonal (row i, columns j <= i), pass 2 the
-    // upper one (row j, columns i > j) into the same slots.
-    for (int i = warp; i < n; i += 32) {
-        double* Ai = Ad + lz_row_offset(i);
-        const int len = 32 * ((i >> 5) + 1);
-        float x[7];
-#pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            const int j = lane + 32 * c;
-            x[c] = (j <= i) ? Rg[(long long)i * n + j] : 0.f;
-        }
-#pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            const int j = lane + 32 * c;
-            if (j < len) Ai[j] = (j < i) ? (double)x[c] : 0.0;
-            if (j == i) {
-                dg[i] = (double)x[c];
-                if (Asym) Asym[(long long)i * n + i] = x[c];
-            }
-        }
-    }
-    if (tid >= n && tid < 224) dg[tid] = 0.0;
-    __syncthreads();
-    for (int j = warp; j < n; j += 32) {
-        float x[7];
-#pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            const int i = j + 1 + lane + 32 * c;
-            x[c] = (i < n) ? Rg[(long long)j * n + i] : 0.f;
-        }
-#pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            const int i = j + 1 + lane + 32 * c;
-            if (i < n) {
-                double* p = Ad + lz_row_offset(i) + j;
-                const float sym = 0.5f * ((float)*p + x[c]);
-                *p = (double)sym;
-                if (Asym) {  // the symmetrised matrix for the factorisation kernels (they then read rows only)
-                    Asym[(long long)j * n + i] = sym;
-                    Asym[(long long)i * n + j] = sym;
-                }
-            }
-        }
-    }
-    double vj = 0.0, vprev = 0.0, dj = 0.0;  // thread j < n keeps its components in registers
-    if (tid < 224) {
-        double x0 = 0.0;
-        if (tid < n) x0 = cos(0.37 * (double)tid + 0.1) + 0.01 * (double)tid / (double)n;
-        vj = x0;
-    }
-    {  // normalise the start vector
-        const double p2 = warp_sum_d(vj * vj);
-        if (lane == 0) red[warp] = p2;
-        __syncthreads();  // (also orders the matrix stores before the first product)
-        double s2 = 0.0;
-#pragma unroll
-        for (int q = 0; q < 7; ++q) s2 += red[q];
-        vj /= sqrt(s2);
-    }
-    if (tid < 224) {
-        v[tid] = vj;
-        dj = dg[tid];
-    }
-    // the rows of this warp (paired short + long) and where they start
-    int roff[7];
-#pragma unroll
-    for (int kk = 0; kk < 7; ++kk) {
-        const int i = lz_row_of(warp, kk);
-        roff[kk] = (i < n) ? lz_row_offset(i) : -1;
-    }
-    const int passes = 32 / L.nslot, my_pass = warp / L.nslot;
-    double* cp = cpart + (warp % L.nslot) * n;
-    __syncthreads();
-    DENSE_STAMP(49);
-    const int k_max = min(kLanczosMax, n);
-    int k = 0;
-    double beta = 0.0;
-    for (int it = 0; it < k_max; ++it) {
-        // ---- y = A v: strictly lower part, used twice (row sums and column sums) ----------------------------------------------
-        double vr[7], cacc[7], rs[8];
-#pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            vr[c] = v[lane + 32 * c];
-            cacc[c] = 0.0;
-        }
-        rs[0] = (roff[0] >= 0) ? lz_row_product<0>(Ad + roff[0], vr, v[lz_row_of(warp, 0)], cacc, lane) : 0.0;
-        rs[1] = (roff[1] >= 0) ? lz_row_product<1>(Ad + roff[1], vr, v[lz_row_of(warp, 1)], cacc, lane) : 0.0;
-        rs[2] = (roff[2] >= 0) ? lz_row_product<2>(Ad + roff[2], vr, v[lz_row_of(warp, 2)], cacc, lane) : 0.0;
-        rs[3] = (roff[3] >= 0) ? lz_row_product<3>(Ad + roff[3], vr, v[lz_row_of(warp, 3)], cacc, lane) : 0.0;
-        rs[4] = (roff[4] >= 0) ? lz_row_product<4>(Ad + roff[4], vr, v[lz_row_of(warp, 4)], cacc, lane) : 0.0;
-        rs[5] = (roff[5] >= 0) ? lz_row_product<5>(Ad + roff[5], vr, v[lz_row_of(warp, 5)], cacc, lane) : 0.0;
-        rs[6] = (roff[6] >= 0) ? lz_row_product<6>(Ad + roff[6], vr, v[lz_row_of(warp, 6)], cacc, lane) : 0.0;
-        rs[7] = 0.0;
-        const double tot = multi_reduce8(rs, lane);
-        {
-            const int q = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-            const int i = lz_row_of(warp, q);
-            if ((lane & 3) == 0 && q < 7 && i < n) rowy[i] = tot;
-        }
-        for (int ps = 0; ps < passes; ++ps) {
-            if (my_pass == ps) {
-#pragma unroll
-                for (int c = 0; c < 7; ++c) {
-                    const int j = lane + 32 * c;
-                    if (j < n) cp[j] = (ps == 0) ? cacc[c] : cp[j] + cacc[c];
-                }
-            }
-            __syncthreads();
-        }
-        // ---- three-term recurrence, thread j --------------------------------------------------------------------------
-        double w = 0.0;
-        if (tid < n) {
-            double s0 = rowy[tid], s1 = dj * vj, s2 = 0.0, s3 = 0.0;
-            for (int q = 0; q < L.nslot; q += 4) {
-                s0 += cpart[q * n + tid];
-                s1 += cpart[(q + 1) * n + tid];
-                s2 += cpart[(q + 2) * n + tid];
-                s3 += cpart[(q + 3) * n + tid];
-            }
-            w = ((s0 + s1) + (s2 + s3)) - beta * vprev;
-        }
-        double* ra = red + (it & 1) * 32;
-        double* rb = red + 64 + (it & 1) * 32;
-        if (warp < 7) {
-            const double pa = warp_sum_d(w * vj);
-            if (lane == 0) ra[warp] = pa;
-        }
-        __syncthreads();
-        double alpha = 0.0;
-#pragma unroll
-        for (int q = 0; q < 7; ++q) alpha += ra[q];
-        w -= alpha * vj;
-        if (warp < 7) {
-            const double pb = warp_sum_d(w * w);
-            if (lane == 0) rb[warp] = pb;
-        }
-        __syncthreads();
-        double b2 = 0.0;
-#pragma unroll
-        for (int q = 0; q < 7; ++q) b2 += rb[q];
-        beta = sqrt(b2);
-        if (tid == 0) {
-            al[it] = alpha;
-            be[it] = beta;
-        }
-        k = it + 1;
-        if (!(beta > 1e-200)) break;  // invariant subspace found (uniform across the CTA)
-        if (tid < n) {
-            vprev = vj;
-            vj = w / beta;
-            v[tid] = vj;
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-    DENSE_STAMP(50);
-    // Extreme eigenvalues of the k x k Lanczos matrix by multisection of the (division-free) Sturm count.  Threads 0..127 look for
-    // the smallest with FOUR trial shifts each (513-way, 5 rounds: 513^5 = 3.5e13 of the Gershgorin interval; the four independent
-    // recurrences hide the DFMA latency); threads 128..255 bracket the largest to 129^-2 (it only selects the approximation interval).
-    if (tid < 256) {
-        double gl = 1e300, gu = -1e300;
-        for (int i = 0; i < k; ++i) {
-            const double r = ((i > 0) ? fabs(be[i - 1]) : 0.0) + ((i < k - 1) ? fabs(be[i]) : 0.0);
-            gl = fmin(gl, al[i] - r);
-            gu = fmax(gu, al[i] + r);
-        }
-        const double pad = 1e-12 * fmax(fabs(gl), fabs(gu)) + 1e-300;
-        gl -= pad;
-        gu += pad;
-        // scaled copy: (T - gl) / (gu - gl) has its spectrum in [0, 1]
-        double* sal = cpart;             // [32]  (the column buffers are dead)
-        double* sb2 = cpart + 32;        // [32]
-        int* first = reinterpret_cast<int*>(cpart + 64);  // [2][8]
-        const double isc = 1.0 / (gu - gl);
-        if (tid < k) {
-            sal[tid] = (al[tid] - gl) * isc;
-            const double b = be[tid] * isc;
-            sb2[tid] = b * b;
-        }
-        COVO_NAMED_BARRIER(2, 256);
-        const bool low = tid < 128;
-        const int t = tid & 127, target = low ? 1 : k;
-        double lo = 0.0, hi = 1.0;
-        for (int round = 0; round < 5; ++round) {
-            int f_mine = 1 << 20;  // first trial index (of this thread's) whose count reaches the target
-            double step;
-            if (low) {
-                step = (hi - lo) / 513.0;
-#pragma unroll
-                for (int u = 3; u >= 0; --u) {
-                    const int idx = 4 * t + u;  // trial shifts in increasing order across (t, u)
-                    if (sturm_count_poly(sal, sb2, k, lo + step * (double)(idx + 1)) >= target) f_mine = idx;
-                }
-            } else {
-                step = (hi - lo) / 129.0;
-                if (round < 2 && sturm_count_poly(sal, sb2, k, lo + step * (double)(t + 1)) >= target) f_mine = t;
-            }
-            // first index over the 4 warps of this search (monotone predicate: the minimum over threads)
-            int fm = f_mine;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) fm = min(fm, __shfl_xor_sync(0xffffffffu, fm, o));
-            int* fr = first + (round & 1) * 8;
-            if (lane == 0) fr[warp] = fm;
-            COVO_NAMED_BARRIER(2, 256);
-            const int w0 = low ? 0 : 4;
-            const int f = min(min(fr[w0], fr[w0 + 1]), min(fr[w0 + 2], fr[w0 + 3]));
-            const int nsub = low ? 512 : 128;
-            if (low || round < 2) {
-                if (f >= nsub) {
-                    lo = lo + step * (double)nsub;  // the crossing is in the last sub-interval
-                } else {
-                    hi = lo + step * (double)(f + 1);
-                    lo = lo + step * (double)f;
-                }
-            }
-        }
-        if (t == 0) a.scal[(long long)env * 4 + (low ? 0 : 1)] = gl + (low ? 0.5 * (lo + hi) : hi) * (gu - gl);
-    }
-    DENSE_STAMP(51);
-}
-
 // ---------------------------------------------------------------------------------------------------------------------------
-// D2
-// ---------------------------------------------------------------------------------------------------------------------------
-// Blocked right-looking Cholesky (NB = 8, look-ahead) of the n x n matrix in As (row-major, stride n), in place: the scheme of
-// cholesky_kernel (sigma.cu), restated here as a device function.  Lp: 2 x [8][n_pad] panel buffers + [8][8].  Returns with the
-// lower triangle of As holding L; `bad` is set when a pivot is not positive.
-__device__ __forceinline__ void chol_factor_smem(float* As, float* Lp, int n, int n_pad, int* bad_out) {
-    const int tid = threadIdx.x;
-    constexpr int kPanelThreads = 256;
-    float* LpA = Lp;
-    float* LpB = Lp + 8 * n_pad;
-    float* Lp8 = LpB + 8 * n_pad;
-    const int pt = tid - (TD - kPanelThreads);
-    auto factor_panel = [&](int jb, int nb, float* LpOut) {
-        const int nrows = n - jb - nb;
-        if (pt < max(nrows, 1)) {
-            float d[8][8], linv[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const float4 p0 = (r < nb) ? *reinterpret_cast<const float4*>(As + (jb + r) * n + jb) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 p1 = (r < nb && nb == 8) ? *reinterpret_cast<const float4*>(As + (jb + r) * n + jb + 4)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                d[r][0] = p0.x; d[r][1] = p0.y; d[r][2] = p0.z; d[r][3] = p0.w;
-                d[r][4] = p1.x; d[r][5] = p1.y; d[r][6] = p1.z; d[r][7] = p1.w;
-                if (r >= nb) d[r][r] = 1.f;
-            }
-            bool bad = false;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float dcc = d[c][c];
-                if (!(dcc > 0.f)) {
-                    bad = true;
-                    dcc = 1e-30f;
-                }
-                const float rinv = rsqrt_newton_d(dcc);
-                linv[c] = rinv;
-                d[c][c] = dcc * rinv;
-#pragma unroll
-                for (int r = c + 1; r < 8; ++r) d[r][c] *= rinv;
-#pragma unroll
-                for (int c2 = c + 1; c2 < 8; ++c2)
-#pragma unroll
-                    for (int r = c2; r < 8; ++r) d[r][c2] = fmaf(-d[r][c], d[c2][c], d[r][c2]);
-            }
-            if (pt < nrows) {
-                const int i = jb + nb + pt;
-                float x[8];
-                const float4 p0 = *reinterpret_cast<const float4*>(As + i * n + jb);
-                x[0] = p0.x; x[1] = p0.y; x[2] = p0.z; x[3] = p0.w;
-                if (nb == 8) {
-                    const float4 p1 = *reinterpret_cast<const float4*>(As + i * n + jb + 4);
-                    x[4] = p1.x; x[5] = p1.y; x[6] = p1.z; x[7] = p1.w;
-                } else {
-                    x[4] = x[5] = x[6] = x[7] = 0.f;
-                }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float sx = x[c];
-#pragma unroll
-                    for (int c2 = 0; c2 < c; ++c2) sx = fmaf(-x[c2], d[c][c2], sx);
-                    x[c] = sx * linv[c];
-                }
-                *reinterpret_cast<float4*>(As + i * n + jb) = make_float4(x[0], x[1], x[2], x[3]);
-                if (nb == 8) *reinterpret_cast<float4*>(As + i * n + jb + 4) = make_float4(x[4], x[5], x[6], x[7]);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) LpOut[c * n_pad + i] = x[c];
-            }
-            if (pt == 0) {
-                if (bad) *bad_out = 1;
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) Lp8[r * 8 + c] = (c <= r) ? d[r][c] : 0.f;
-            }
-        }
-    };
-    if (pt >= 0) factor_panel(0, min(8, n), LpA);
-    __syncthreads();
-    for (int jb = 0, it = 0; jb < n; jb += 8, ++it) {
-        const int nb = min(8, n - jb);
-        float* LpCur = (it & 1) ? LpB : LpA;
-        float* LpNext = (it & 1) ? LpA : LpB;
-        if (pt >= 0 && pt < 64) {
-            const int r = pt >> 3, c = pt & 7;
-            if (r < nb && c < nb) As[(jb + r) * n + jb + c] = Lp8[pt];
-        }
-        const int r0 = jb + nb;
-        if (r0 >= n) break;
-        const int nbn = min(8, n - r0);
-        if (pt >= 0) {
-            const int i = r0 + pt;
-            if (i < n) {
-                float x[8];
-                const float4 p0 = *reinterpret_cast<const float4*>(As + i * n + r0);
-                x[0] = p0.x; x[1] = p0.y; x[2] = p0.z; x[3] = p0.w;
-                if (nbn == 8) {
-                    const float4 p1 = *reinterpret_cast<const float4*>(As + i * n + r0 + 4);
-                    x[4] = p1.x; x[5] = p1.y; x[6] = p1.z; x[7] = p1.w;
-                } else {
-                    x[4] = x[5] = x[6] = x[7] = 0.f;
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float li = LpCur[k * n_pad + i];
-                    const float4 l0 = *reinterpret_cast<const float4*>(LpCur + k * n_pad + r0);
-                    x[0] = fmaf(-li, l0.x, x[0]); x[1] = fmaf(-li, l0.y, x[1]);
-                    x[2] = fmaf(-li, l0.z, x[2]); x[3] = fmaf(-li, l0.w, x[3]);
-                    if (nbn == 8) {
-                        const float4 l1 = *reinterpret_cast<const float4*>(LpCur + k * n_pad + r0 + 4);
-                        x[4] = fmaf(-li, l1.x, x[4]); x[5] = fmaf(-li, l1.y, x[5]);
-                        x[6] = fmaf(-li, l1.z, x[6]); x[7] = fmaf(-li, l1.w, x[7]);
-                    }
-                }
-                *reinterpret_cast<float4*>(As + i * n + r0) = make_float4(x[0], x[1], x[2], x[3]);
-                if (nbn == 8) *reinterpret_cast<float4*>(As + i * n + r0 + 4) = make_float4(x[4], x[5], x[6], x[7]);
-            }
-            COVO_NAMED_BARRIER(1, 256);
-            factor_panel(r0, nbn, LpNext);
-        } else {
-            const int c0 = r0 + nbn;
-            const int T = (n - c0) >> 2;
-            const int ntiles = T * (T + 1) / 2;
-            for (int q = tid; q < ntiles; q += TD - kPanelThreads) {
-                int ti = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
-                while (ti * (ti + 1) / 2 > q) --ti;
-                while ((ti + 1) * (ti + 2) / 2 <= q) ++ti;
-                const int tk = q - ti * (ti + 1) / 2;
-                const int i = c0 + 4 * ti, kk = c0 + 4 * tk;
-                float2 o[4][2];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float4 av = *reinterpret_cast<const float4*>(As + (i + r) * n + kk);
-                    o[r][0] = make_float2(av.x, av.y);
-                    o[r][1] = make_float2(av.z, av.w);
-                }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 li = *reinterpret_cast<const float4*>(LpCur + c * n_pad + i);
-                    const float4 lk = *reinterpret_cast<const float4*>(LpCur + c * n_pad + kk);
-                    const float lir[4] = {-li.x, -li.y, -li.z, -li.w};
-                    const float2 lk0 = make_float2(lk.x, lk.y), lk1 = make_float2(lk.z, lk.w);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float2 l2 = make_float2(lir[r], lir[r]);
-                        o[r][0] = __ffma2_rn(l2, lk0, o[r][0]);
-                        o[r][1] = __ffma2_rn(l2, lk1, o[r][1]);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    *reinterpret_cast<float4*>(As + (i + r) * n + kk) = make_float4(o[r][0].x, o[r][0].y, o[r][1].x, o[r][1].y);
-            }
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(TD, 1) shifted_inverse_kernel(const DenseArgs a) {
-    COVO_DYN_SMEM(smraw);
-    const int n = a.n, n_pad = a.n_pad, tid = threadIdx.x, pole = blockIdx.x, env = blockIdx.y, lane = tid & 31, warp = tid >> 5;
-    float* As = reinterpret_cast<float*>(smraw);  // [n][n]
-    float* Lp = As + n * n;                       // Cholesky panel buffers
-    float* dinv = Lp + 2 * 8 * n_pad + 64;        // [n] 1 / L_ii  (= X_ii)
-    int* bad = reinterpret_cast<int*>(dinv + n_pad);
-    const double lam_min = a.scal[(long long)env * 4 + 0], lam_max = a.scal[(long long)env * 4 + 1];
-    // ladder entry covering [1e-2, M]; the Ritz value can only underestimate lambda_max: 2 % of the width as margin
-    int lad = 0;
-    {
-        const double Mb = 1.02 * (lam_max - lam_min) + kOffset;
-        double Mi = kOffset * (1.0 - 1e-7) * 256.0;
-        while (lad < kZoloLadder - 1 && Mi < Mb) {
-            Mi *= 4.0;
-            ++lad;
-        }
-        if (Mi < Mb && tid == 0) a.status[env] = 1;
-    }
-    const double* zt = a.zolo + (size_t)lad * 2 * kZoloPoles;
-    const bool want_logdet = pole == kZoloPoles;
-    const double shift = (kOffset - lam_min) + (want_logdet ? 0.0 : zt[pole]);
-    const float wj = want_logdet ? 0.f : (float)zt[kZoloPoles + pole];
-    if (tid == 0) *bad = 0;
-    // A + t_j I = (R + R^T)/2 + shift I  (the shift is added in double and rounded once)
-    const float* Rg = a.R + (long long)env * n * n;
-    for (int idx = tid; idx < n * n; idx += TD) {
-        const int i = idx / n, j = idx - i * n;
-        float val = 0.5f * (Rg[idx] + Rg[(long long)j * n + i]);
-        if (i == j) val = (float)((double)val + shift);
-        As[idx] = val;
-    }
-    __syncthreads();
-    chol_factor_smem(As, Lp, n, n_pad, bad);
-    if (*bad && tid == 0) a.status[env] = 2;
-    if (want_logdet) {
-        if (warp == 0) {
-            double s = 0.0;
-            for (int i = lane; i < n; i += 32) s += log((double)As[i * n + i]);
-            s = warp_sum_d(s);
-            if (lane == 0) a.scal[(long long)env * 4 + 2] = 2.0 * s;
-        }
-        return;
-    }
-    // X = L^-1 (lower triangular).  X_ii = 1 / L_ii lives in dinv; X_ic (i > c) is stored TRANSPOSED in the strict upper triangle,
-    // As[c][i], so the factor (strict lower triangle + diagonal) is never overwritten.  One warp per column c, lanes over k:
-    //     X_ic = -dinv[i] * sum_{k = c}^{i-1} L_ik X_kc
-    for (int i = tid; i < n; i += TD) dinv[i] = 1.0f / As[i * n + i];
-    __syncthreads();
-    for (int c = warp; c < n; c += TD / 32) {
-        float* Xc = As + c * n;  // row c of the upper triangle: X_kc at Xc[k], k > c
-        const float xcc = dinv[c];
-        for (int i = c + 1; i < n; ++i) {
-            const float* Li = As + i * n;
-            float s = 0.f;
-            for (int k = c + 1 + lane; k < i; k += 32) s = fmaf(Li[k], Xc[k], s);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) Xc[i] = -(s + Li[c] * xcc) * dinv[i];
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    // w_j (A + t_j I)^-1 = w_j X^T X:  P_ab = sum_{r >= a} X_ra X_rb  (a >= b).  One warp per (a, b), lanes over r.
-    float* Xg = a.Xbuf + ((long long)env * kZoloPoles + pole) * n * n;
-    const int npairs = n * (n + 1) / 2;
-    for (int q = warp; q < npairs; q += TD / 32) {
-        int ia = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
-        while (ia * (ia + 1) / 2 > q) --ia;
-        while ((ia + 1) * (ia + 2) / 2 <= q) ++ia;
-        const int ib = q - ia * (ia + 1) / 2;  // ib <= ia
-        const float* Xa = As + ia * n;
-        const float* Xb = As + ib * n;
-        float s = 0.f;
-        for (int r = ia + 1 + lane; r < n; r += 32) s = fmaf(Xa[r], Xb[r], s);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) {
-            const float xab = (ia == ib) ? dinv[ia] : Xb[ia];  // X_ab, the r = a term (X_aa = dinv[a])
-            Xg[ia * n + ib] = wj * (s + dinv[ia] * xab);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------------
-// D2' (alternative to D2, COVO_SIGMA=dense-gj): w_j (A + t_j I)^-1 by in-place Gauss-Jordan elimination without pivoting (A + t_j I
-// is SPD: every pivot is a positive Schur complement), the matrix RESIDENT IN REGISTERS.  512 threads as a 16 x 32 grid; thread
-// (ty, tx) owns the elements (ty + 16 a, tx + 32 b), a < RI, b < 7, rows packed in pairs for FFMA2.  Step k:
-//     p = a_kk;  a_ij -= a_ik a_kj / p  (i, j != k);  row k <- r / p;  column k <- -c / p;  a_kk <- 1 / p.
-// With this sign convention the matrix stays symmetric on the not yet eliminated index set and ANTI-symmetric between eliminated
-// and remaining indices (a_im = -a_mi for m < k <= i), so column k is row k with the sign of (i < k): only the ROW is published
-// (by the one warp that owns it; double-buffered, one barrier per step), never the column.  The loop over k is unrolled over the
-// 16-row blocks, so every register-tile index is a compile-time constant and the row / column fix-ups touch 7 and 14 registers
-// instead of the whole tile.  log det A = sum log p_k comes for free (the CTA without a pole).  n^3 FMA per matrix instead of the
-// three n^3 / 3 sweeps of D2, but no serial panel chain.  Numerics (CPU study, fp32): Sigma to 1e-6 on the tracking / zigzag path.
-// ---------------------------------------------------------------------------------------------------------------------------
-constexpr int TG = 512;
-
-template <int RI>
-__global__ void __launch_bounds__(TG, 1) gj_inverse_kernel(const DenseArgs a) {
-    COVO_DYN_SMEM(smraw);
-    constexpr int CJ = 7, RP = (RI + 1) / 2;
-    const int n = a.n, tid = threadIdx.x, pole = blockIdx.x, env = blockIdx.y, tx = tid & 31, ty = tid >> 5;
-    float* rbuf = reinterpret_cast<float*>(smraw);  // [2][512]: row k and the column multipliers, double-buffered
-    const double lam_min = a.scal[(long long)env * 4 + 0], lam_max = a.scal[(long long)env * 4 + 1];
-    int lad = 0;
-    {
-        const double Mb = 1.02 * (lam_max - lam_min) + kOffset;
-        double Mi = kOffset * (1.0 - 1e-7) * 256.0;
-        while (lad < kZoloLadder - 1 && Mi < Mb) {
-            Mi *= 4.0;
-            ++lad;
-        }
-        if (Mi < Mb && tid == 0) a.status[env] = 1;
-    }
-    const double* zt = a.zolo + (size_t)lad * 2 * kZoloPoles;
-    const bool want_logdet = pole == kZoloPoles;
-    const double shift = (kOffset - lam_min) + (want_logdet ? 0.0 : zt[pole]);
-    const float wj = want_logdet ? 0.f : (float)zt[kZoloPoles + pole];
-    const float* Rg = a.R + (long long)env * n * n;
-    // tile load: (R + R^T)/2 + shift I; elements outside the matrix form an identity block (never a pivot, no coupling)
-    float2 acc[RP][CJ];  // [row pair][col]: .x = tile row 2q, .y = tile row 2q + 1
-#pragma unroll
-    for (int q = 0; q < RP; ++q)
-#pragma unroll
-        for (int b = 0; b < CJ; ++b) {
-            float v2[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = ty + 16 * (2 * q + h), j = tx + 32 * b;
-                float v = (i == j) ? 1.f : 0.f;
-                if (i < n && j < n) {
-                    v = 0.5f * (Rg[(long long)i * n + j] + Rg[(long long)j * n + i]);
-                    if (i == j) v = (float)((double)v + shift);
-                }
-                v2[h] = v;
-            }
-            acc[q][b] = make_float2(v2[0], v2[1]);
-        }
-    float my_pivot = 1.f;  // thread k keeps pivot k: the logarithms are taken once, after the elimination
-    bool bad = false;
-#pragma unroll
-    for (int ak = 0; ak < 2 * RP; ++ak) {  // 16-row block of the pivot: tile row ak, tile column ak / 2 -- compile-time
-        const int qk = ak >> 1, bk = ak >> 1;  // pivot row lives in acc[qk][.].(ak & 1 ? y : x); pivot column is tile column bk
-        if (16 * ak < n) {
-            for (int kk = 0; kk < 16; ++kk) {
-                const int k = 16 * ak + kk;
-                if (k >= n) break;
-                float* rb = rbuf + (k & 1) * 512;  // [256] row k, then [256] the column multipliers -a_ik / p
-                float* cb = rb + 256;
-                float piv = 0.f;
-                if (ty == kk) {
-                    // The warp that owns row k publishes it, and with it the multipliers of the column: by (anti)symmetry
-                    // a_ik = (i < k ? -1 : 1) a_ki, so -a_ik / p is the row again, signed and scaled -- the other 15 warps
-                    // never see the column, only these two vectors.
-                    const float own = (ak & 1) ? acc[qk][bk].y : acc[qk][bk].x;  // lane k mod 32 holds the pivot
-                    const float p = __shfl_sync(0xffffffffu, own, k & 31);
-                    if (!(p > 0.f)) bad = true;
-                    piv = 1.0f / p;
-#pragma unroll
-                    for (int b = 0; b < CJ; ++b) {
-                        const int j = tx + 32 * b;
-                        const float r = (ak & 1) ? acc[qk][b].y : acc[qk][b].x;
-                        rb[j] = r;
-                        cb[j] = (j < k ? r : -r) * piv;
-                    }
-                }
-                __syncthreads();
-                if (tid == k) my_pivot = rb[k];
-                float rk[CJ];
-#pragma unroll
-                for (int b = 0; b < CJ; ++b) rk[b] = rb[tx + 32 * b];
-                float2 cn[RP];
-#pragma unroll
-                for (int q = 0; q < RP; ++q) cn[q] = make_float2(cb[ty + 32 * q], cb[ty + 32 * q + 16]);
-#pragma unroll
-                for (int q = 0; q < RP; ++q)
-#pragma unroll
-                    for (int b = 0; b < CJ; ++b) acc[q][b] = __ffma2_rn(cn[q], make_float2(rk[b], rk[b]), acc[q][b]);
-                if (tx == (k & 31)) {  // column k (tile column bk): -a_ik / p
-#pragma unroll
-                    for (int q = 0; q < RP; ++q) acc[q][bk] = cn[q];
-                }
-                if (ty == kk) {  // row k: a_kj / p, pivot 1 / p
-#pragma unroll
-                    for (int b = 0; b < CJ; ++b) {
-                        const float v = (tx + 32 * b == k) ? piv : rk[b] * piv;
-                        if (ak & 1) acc[qk][b].y = v;
-                        else acc[qk][b].x = v;
-                    }
-                }
-                // no second barrier: step k + 1 publishes into the other buffer, and step k + 2 writes this one only after the
-                // barrier of step k + 1, which every thread reaches after it has finished reading here
-            }
-        }
-    }
-    if (bad && tid == 0) a.status[env] = 2;
-    if (want_logdet) {  // log det A = sum_k log p_k  (n <= TG: one pivot per thread)
-        double lp = (tid < n) ? log((double)my_pivot) : 0.0;
-        lp = warp_sum_d(lp);
-        double* red = reinterpret_cast<double*>(rbuf);
-        __syncthreads();  // the row buffers are no longer read
-        if (tx == 0) red[ty] = lp;
-        __syncthreads();
-        if (tid == 0) {
-            double sum = 0.0;
-            for (int w = 0; w < TG / 32; ++w) sum += red[w];
-            a.scal[(long long)env * 4 + 2] = sum;
-        }
-        return;
-    }
-    float* Xg = a.Xbuf + ((long long)env * kZoloPoles + pole) * n * n;
-#pragma unroll
-    for (int q = 0; q < RP; ++q)
-#pragma unroll
-        for (int b = 0; b < CJ; ++b) {
-            const int j = tx + 32 * b;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = ty + 16 * (2 * q + h);
-                if (i < n && j <= i) Xg[i * n + j] = wj * (h ? acc[q][b].y : acc[q][b].x);  // lower triangle, as D2
-            }
-        }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------------
-// Thread-block-cluster primitives shared by D1'' and D2'': distributed shared memory stores that carry their own completion
+// Thread-block-cluster primitives shared by D1 and D2: distributed shared memory stores that carry their own completion
 // signal (st.async ... mbarrier::complete_tx), mbarrier waits, the cluster barrier.  tests/emu provides CPU stand-ins.
 // ---------------------------------------------------------------------------------------------------------------------------
 #if defined(COVO_CPU_EMU)
 __device__ __forceinline__ unsigned gjb_rank() { return emu_cluster_rank(); }
 __device__ __forceinline__ void gjb_cluster_sync() { emu_cluster_barrier(); }
+__device__ __forceinline__ void gjb_cluster_arrive() {}
+__device__ __forceinline__ void gjb_cluster_wait() { emu_cluster_barrier(); }
 __device__ __forceinline__ void gjb_mbar_init(unsigned long long* b, int count) { emu_mbar_init(b, count); }
 __device__ __forceinline__ void gjb_mbar_expect(unsigned long long* b, int bytes) { emu_mbar_expect_tx(b, bytes); }
 __device__ __forceinline__ void gjb_mbar_wait(unsigned long long* b, unsigned parity) { emu_mbar_wait(b, parity); }
@@ -934,6 +89,9 @@ __device__ __forceinline__ unsigned gjb_rank() {
 __device__ __forceinline__ void gjb_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// split form: only execution ordering is needed (who has finished reading which ring slot); the data travels with its own mbarrier
+__device__ __forceinline__ void gjb_cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void gjb_cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 __device__ __forceinline__ void gjb_mbar_init(unsigned long long* b, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gjb_s32(b)), "r"(count) : "memory");
 }
@@ -988,55 +146,66 @@ __device__ __forceinline__ float gjb_rcp(float x) {
 #endif
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// D1'' lanczos_cluster_kernel -- the Lanczos recurrence on an 8-CTA cluster.  Measured on B200: scalar float64 instructions issue at
-// ~16 lanes / clock / SM, so a 200 x 200 product is >= 2500 cycles on one SM whatever the layout (D1 and D1' both sit at ~3.5 us per
-// iteration); the only way down is more SMs.  CTA c keeps rows [c R, (c + 1) R) of (R + R^T)/2 in REGISTERS as float64, four
-// threads per row (columns 4 k + p), and per iteration
-//     y = A w / beta  (w: last iteration's unnormalised vector, complete in every CTA's shared memory),
-//     w' = y - beta v_prev,  warp partials of w'.v and w'.w',
-// then ONE exchange: every row leader sends its w' and every warp its two partials to all 8 CTAs with st.async (the stores count
+// D1 lanczos_cluster_kernel -- the Lanczos recurrence on an 8-CTA cluster.  Measured on B200: scalar float64 instructions issue at
+// ~16 lanes / clock / SM, so a 200 x 200 product is >= 2500 cycles on one SM whatever the layout; the only way down is more SMs.
+// CTA c keeps rows [c R, (c + 1) R) of (R + R^T)/2 in REGISTERS as float64, four threads per row (columns 4 k + p), and per step
+//     y = A v_k,  u = y - beta_{k-1} v_{k-1},  warp partials of u.v_k and u.u,
+// then ONE exchange: every row leader sends its u and every warp its two partials to all 8 CTAs with st.async (the stores count
 // themselves into the receiver's mbarrier: no fence, no cluster barrier), everybody waits for its own mbarrier and finishes
-// alpha, beta^2 = w'.w' - alpha^2 and w = w' - alpha v redundantly.  The all-to-all makes every iteration an implicit barrier,
-// so two buffers (iteration parity) are enough.  CTA 0 then finds the smallest Ritz value: five rounds of 128-way multisection
-// (division-free Sturm counts: the bracket is 2.8e-11 of the Gershgorin interval wide) and a short Newton polish from its left end
-// (monotone for a real-rooted polynomial).  Required accuracy: |error| << 1e-2 * 2e-5 = 2e-7 ABSOLUTE (the offset 1e-2 of
-// controllers/covo.py:121 sets the scale), not relative to |R|.
+// alpha, beta^2 = u.u - alpha^2 and v_{k+1} = (u - alpha v_k) / beta redundantly.  The all-to-all makes every step an implicit
+// barrier, so two buffers (step parity) are enough.
+//
+// How many steps: the smallest Ritz value must be within << 1e-2 * 2e-5 = 2e-7 ABSOLUTE of lambda_min (the offset 1e-2 of
+// controllers/covo.py:121 sets the scale, not |R| ~ 1e3), and the number of steps that takes depends on the Hessian: along closed
+// loops (scratch/lanczos_k_needed.py) 16 .. 48, with 24 enough for only 56 % of them -- and an unconverged Ritz value 1e-2 above
+// lambda_min makes A indefinite.  So the length is adaptive: a fifth warp per CTA (the CHECKER) follows the recurrence at the
+// checkpoints k = 16, 20, 24, ...: smallest eigenvalue theta of the k x k Lanczos matrix T_k (33-way multisection on Sturm
+// counts, three float32 rounds, then float64 with both bracket ends verified, then Newton from below) and the residual of its
+// Ritz pair, beta_{k-1} |s_{k-1}| (s = eigenvector of T_k; |theta - lambda| <= residual^2 / gap).  It works in the shadow of the
+// next steps; the Lanczos warps look at the verdict for checkpoint c when they have finished step c + 3 and stop there.  Every
+// CTA runs its own checker on the same numbers (alpha, beta are bit-identical across the cluster), so all CTAs stop at the same
+// step without another exchange.  No convergence within 64 steps (never seen on a CoVO Hessian): lambda_min is reported as
+// theta - residual (A stays positive definite), status 3, and the host moves the handle to the tridiagonal path.
 // ---------------------------------------------------------------------------------------------------------------------------
-constexpr int LC_CL = 8;      // CTAs
-constexpr int LC_T = 128;     // threads per CTA: 32 rows x 4 column phases
-constexpr int LC_KMAX = 56;   // columns per thread (n <= 224)
+constexpr int LC_CL = 8;            // CTAs
+constexpr int LC_T = 128;           // Lanczos threads per CTA: 32 rows x 4 column phases
+constexpr int LC_TT = LC_T + 32;    // ... plus the checker warp
+constexpr int LC_KMAX = 56;         // columns per thread (n <= 224)
+constexpr int kLanczosMax = 64;     // most Lanczos steps
+constexpr int kLanczosFirstCheck = 16, kLanczosCheckEvery = 4, kLanczosLag = 3;
+constexpr double kRitzTol2 = 9e-10;  // residual^2 below which the Ritz value counts as converged: error <= 9e-10 / gap
 
 struct LcSmem {
-    double v[2][224];                 // normalised Lanczos vector v_k (by iteration parity), all n entries, zero beyond n
-    double u[2][224];                 // u = A v_k - beta_{k-1} v_{k-1}, gathered from all CTAs (by iteration parity)
+    double v[2][224];                 // normalised Lanczos vector v_k (by step parity), all n entries, zero beyond n
+    double u[2][224];                 // u = A v_k - beta_{k-1} v_{k-1}, gathered from all CTAs (by step parity)
     double part[2][LC_CL * 4][2];     // (u.v_k, u.u) partial of every warp of the cluster
-    double al[kLanczosMax], be[kLanczosMax];
-    double sal[kLanczosMax], sb2[kLanczosMax];
+    double al[kLanczosMax], be[kLanczosMax];  // T: diagonal, off-diagonal (be[k-1] couples step k to the next vector)
+    double red[4];
     unsigned long long bar[2];
-    int first[2][4];
-    float salf[kLanczosMax], sb2f[kLanczosMax];
+    // the checker's tables: 1 / beta_i, beta_{i-1} / beta_i, float32 copies, the eigenvector recurrence of the last evaluation
+    double ib[kLanczosMax], cc[kLanczosMax], qv[kLanczosMax], bv[kLanczosMax];
+    float alf[kLanczosMax], ibf[kLanczosMax], ccf[kLanczosMax];
+    int qe[kLanczosMax], bve[kLanczosMax];
+    // hand-over between the Lanczos warps and the checker (volatile accesses + __threadfence_block)
+    int progress;     // Lanczos steps completed: al / be are valid below it
+    int final_k;      // != 0: the recurrence has ended after this many steps
+    int verdict_k;    // the last checkpoint the checker has judged
+    int converged_k;  // != 0: the checkpoint at which the smallest Ritz value had converged
 };
 
-// float32 twin of sturm_count_poly for the first, coarse multisection rounds (the bracket is widened afterwards by far more than
-// its rounding error can move a crossing)
-__device__ __forceinline__ int sturm_count_poly_f32(const float* al, const float* b2, int k, float x) {
-    float pm = 1.0f, p = al[0] - x;
-    int sg_prev = 1, cnt = 0;
-    {
-        const int sg = (p > 0.f) ? 1 : ((p < 0.f) ? -1 : -sg_prev);
-        cnt += (sg != sg_prev);
-        sg_prev = sg;
-    }
-    for (int i = 1; i < k; ++i) {
-        const float pn = fmaf(al[i] - x, p, -b2[i - 1] * pm);
-        pm = p;
-        p = pn;
-        const int sg = (p > 0.f) ? 1 : ((p < 0.f) ? -1 : -sg_prev);
-        cnt += (sg != sg_prev);
-        sg_prev = sg;
-    }
-    return cnt;
-}
+#if defined(COVO_CPU_EMU)
+__device__ __forceinline__ void lc_main_sync() { emu_named_barrier(1, LC_T); }
+__device__ __forceinline__ void lc_pause() { emu::yield(); }
+__device__ __forceinline__ void lc_published() { ++emu::progress(); }
+__device__ __forceinline__ void lc_fence() {}
+#else
+__device__ __forceinline__ void lc_main_sync() { asm volatile("bar.sync 1, %0;" ::"n"(LC_T) : "memory"); }
+__device__ __forceinline__ void lc_pause() { __nanosleep(20); }
+__device__ __forceinline__ void lc_published() {}
+__device__ __forceinline__ void lc_fence() { __threadfence_block(); }
+#endif
+__device__ __forceinline__ int lc_load(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void lc_store(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
 
 // Remote addresses of one thread's three exchange targets in CTA `rank`: its row entry of u, its warp's partial pair, the barrier
 // (all for parity 0; parity 1 is a fixed byte offset away) -- mapa once, outside the loop.
@@ -1071,255 +240,501 @@ __device__ __forceinline__ void lc_send(const LcRemote& r, int what, int parity,
 }
 #endif
 
-// characteristic polynomial of the scaled k x k Lanczos matrix and its derivative at x (three-term recurrences)
-__device__ __forceinline__ void lc_poly_newton(const double* al, const double* b2, int k, double x, double& p_out, double& dp_out) {
-    double pm = 1.0, p = al[0] - x, dm = 0.0, d = -1.0;
-    for (int i = 1; i < k; ++i) {
-        const double t = al[i] - x;
-        const double pn = fma(t, p, -b2[i - 1] * pm);
-        const double dn = fma(t, d, -b2[i - 1] * dm) - p;
-        pm = p;
-        p = pn;
-        dm = d;
-        d = dn;
+// ---- the checker's arithmetic on T_k = tridiag(al[0..k), be[0..k-1)) --------------------------------------------------------
+// Q_0 = 1, Q_{i+1} = ((al_i - x) Q_i - be_{i-1} Q_{i-1}) / be_i: the leading principal minors of T - x divided by be_0 ... be_i
+// (same signs: the be are positive), i.e. up to alternating signs the components of the solution of (T - x) s = 0 -- the numbers
+// stay of the size of an eigenvector instead of a product of k pivots.  #{sign changes in Q_0 .. Q_k} = #{eigenvalues below x}.
+// The last member is left undivided (be_{k-1} belongs to the next step).  Only "is any eigenvalue below x" is needed.
+__device__ __forceinline__ bool lc_any_below_f32(const LcSmem& sm, int k, float x) {
+    float qm = 0.f, q = 1.f;
+    bool below = false;
+    for (int i = 0; i < k - 1; ++i) {
+        const float w = (sm.alf[i] - x) * sm.ibf[i];
+        const float qn = fmaf(w, q, -sm.ccf[i] * qm);
+        qm = q;
+        q = qn;
+        if (fabsf(q) > 1e18f) {  // keep the pair inside the float32 range (the signs are all that matters)
+            q *= 0x1p-80f;
+            qm *= 0x1p-80f;
+        } else if (fabsf(q) < 1e-18f && fabsf(qm) < 1e-18f) {
+            q *= 0x1p80f;
+            qm *= 0x1p80f;
+        }
+        below = below || !(q > 0.f);  // Q_0 = 1 > 0: no eigenvalue below x <=> every member stays positive
     }
-    p_out = p;
-    dp_out = d;
+    const float bm = (k >= 2) ? (float)sm.be[k - 2] : 0.f;
+    const float ql = fmaf(sm.alf[k - 1] - x, q, -bm * qm);
+    return below || !(ql > 0.f);
 }
 
-__global__ void __launch_bounds__(LC_T, 1) lanczos_cluster_kernel(const DenseArgs a) {
+__device__ __forceinline__ bool lc_any_below_f64(const LcSmem& sm, int k, double x) {
+    double qm = 0.0, q = 1.0;
+    bool below = false;
+    for (int i = 0; i < k - 1; ++i) {
+        const double w = (sm.al[i] - x) * sm.ib[i];
+        const double qn = fma(w, q, -sm.cc[i] * qm);
+        qm = q;
+        q = qn;
+        if ((i & 7) == 7) {
+            if (fabs(q) > 1e60) {
+                q *= 0x1p-256;
+                qm *= 0x1p-256;
+            } else if (fabs(q) < 1e-60 && fabs(qm) < 1e-60) {
+                q *= 0x1p256;
+                qm *= 0x1p256;
+            }
+        }
+        below = below || !(q > 0.0);
+    }
+    const double bm = (k >= 2) ? sm.be[k - 2] : 0.0;
+    const double ql = fma(sm.al[k - 1] - x, q, -bm * qm);
+    return below || !(ql > 0.0);
+}
+
+// Q_k(x) and its derivative (Newton), the members Q_0 .. Q_{k-1} parked in qv / qe (value, binary exponent of the scale applied)
+__device__ __forceinline__ void lc_newton_eval(LcSmem& sm, int k, double x, bool park, double& f, double& df) {
+    double qm = 0.0, q = 1.0, dm = 0.0, d = 0.0;
+    int sc = 0;
+    for (int i = 0; i < k - 1; ++i) {
+        if (park) {
+            sm.qv[i] = q;
+            sm.qe[i] = sc;
+        }
+        const double w = (sm.al[i] - x) * sm.ib[i];
+        const double qn = fma(w, q, -sm.cc[i] * qm);
+        const double dn = fma(w, d, -fma(sm.ib[i], q, sm.cc[i] * dm));
+        qm = q;
+        q = qn;
+        dm = d;
+        d = dn;
+        if ((i & 7) == 7) {
+            if (fabs(q) > 1e60 || fabs(d) > 1e60) {
+                q *= 0x1p-256, qm *= 0x1p-256, d *= 0x1p-256, dm *= 0x1p-256;
+                sc -= 256;
+            } else if (fabs(q) < 1e-60 && fabs(qm) < 1e-60) {
+                q *= 0x1p256, qm *= 0x1p256, d *= 0x1p256, dm *= 0x1p256;
+                sc += 256;
+            }
+        }
+    }
+    if (park) {
+        sm.qv[k - 1] = q;
+        sm.qe[k - 1] = sc;
+    }
+    const double bm = (k >= 2) ? sm.be[k - 2] : 0.0;
+    const double t = sm.al[k - 1] - x;
+    f = fma(t, q, -bm * qm);
+    df = fma(t, d, -(q + bm * dm));
+}
+
+// The checker warp: judges T_k.  Returns theta (smallest eigenvalue of T_k), res2 (squared residual of its Ritz pair), gu (upper
+// Gershgorin bound of T_k).  k_prev: the tables are complete below k_prev - 1.
+__device__ __forceinline__ void lc_judge(LcSmem& sm, int k, int k_prev, int lane, double& theta, double& res2, double& gu_out) {
+    // tables for the new rows (be_{k-1} is not part of T_k, but it will be of the next checkpoint's matrix)
+    for (int i = max(k_prev - 1, 0) + lane; i < k; i += 32) {
+        const double b = sm.be[i];
+        const double ibv = (b > 1e-290) ? 1.0 / b : 0.0;
+        const double ccv = (i > 0) ? sm.be[i - 1] * ibv : 0.0;
+        sm.ib[i] = ibv;
+        sm.cc[i] = ccv;
+        sm.alf[i] = (float)sm.al[i];
+        sm.ibf[i] = (float)ibv;
+        sm.ccf[i] = (float)ccv;
+    }
+    // Gershgorin interval of T_k
+    double gl = 1e300, gu = -1e300;
+    for (int i = lane; i < k; i += 32) {
+        const double r = ((i > 0) ? fabs(sm.be[i - 1]) : 0.0) + ((i < k - 1) ? fabs(sm.be[i]) : 0.0);
+        gl = fmin(gl, sm.al[i] - r);
+        gu = fmax(gu, sm.al[i] + r);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        gl = fmin(gl, __shfl_xor_sync(0xffffffffu, gl, o));
+        gu = fmax(gu, __shfl_xor_sync(0xffffffffu, gu, o));
+    }
+    __syncwarp();
+    const double pad = 1e-12 * fmax(fabs(gl), fabs(gu)) + 1e-300;
+    gl -= pad;
+    gu += pad;
+    gu_out = gu;
+    const double W = gu - gl;
+    double lo = gl, hi = gu;
+    // three float32 rounds of 33-way multisection: the bracket shrinks to W / 33^3 = 2.8e-5 W
+    for (int round = 0; round < 3; ++round) {
+        const double step = (hi - lo) / 33.0;
+        const bool ge = lc_any_below_f32(sm, k, (float)(lo + step * (double)(lane + 1)));
+        const unsigned m = __ballot_sync(0xffffffffu, ge);
+        const int f = m ? __ffs(m) - 1 : 32;
+        hi = (f < 32) ? lo + step * (double)(f + 1) : hi;
+        lo = lo + step * (double)f;
+    }
+    // float32 rounding moves a crossing by ~1e-6 W: widen by 2e-5 W, then float64 rounds over 32 points INCLUDING both ends, so a
+    // bracket that does not hold the crossing is noticed and moved instead of trusted
+    lo = fmax(lo - 2e-5 * W, gl);
+    hi = fmin(hi + 2e-5 * W, gu);
+    for (int round = 0, good = 0; round < 12 && good < 3; ++round) {
+        const double step = (hi - lo) / 31.0;
+        const bool ge = lc_any_below_f64(sm, k, lo + step * (double)lane);
+        const unsigned m = __ballot_sync(0xffffffffu, ge);
+        if (m & 1u) {  // an eigenvalue at or below lo: move the bracket down
+            const double w = hi - lo;
+            hi = lo;
+            lo = fmax(lo - 16.0 * w, gl);
+            if (!(hi > lo)) break;  // (lo == gl: cannot happen, gl is below the spectrum)
+        } else if (m == 0u) {  // none below hi: move it up
+            const double w = hi - lo;
+            lo = hi;
+            hi = fmin(hi + 16.0 * w, gu);
+            if (!(hi > lo)) break;
+        } else {
+            const int f = __ffs(m) - 1;  // >= 1
+            hi = lo + step * (double)f;
+            lo = lo + step * (double)(f - 1);
+            ++good;
+        }
+    }
+    // Newton from the left end (below every root of Q_k: monotone, quadratic for a simple root); every lane the same arithmetic
+    double x = lo;
+    for (int itn = 0; itn < 4; ++itn) {
+        double f, df;
+        lc_newton_eval(sm, k, x, lane == 0, f, df);
+        if (!(df < 0.0) || !(f > 0.0)) break;
+        const double xn = fmin(x - f / df, hi);
+        if (!(xn > x)) break;  // converged to rounding
+        const bool tiny = (xn - x) < 1e-13 * W;
+        x = xn;
+        if (tiny && itn >= 1) break;  // the members parked are those of the previous iterate: closer than 1e-13 W
+    }
+    theta = x;
+    __syncwarp();
+    // Residual of the Ritz pair: be_{k-1} |s_{k-1}| / |s|, s the eigenvector of T_k.  The members Q_i(theta) ARE that eigenvector as
+    // long as they grow; once theta has converged it is (to rounding) an eigenvalue of T_j for all later j as well, Q_j(theta) is
+    // noise and everything the forward recurrence builds on it is the other, growing solution.  The recurrence run BACKWARDS from
+    // the last row, B_{k-1} = 1, B_{i-1} = ((al_i - theta) B_i - be_i B_{i+1}) / be_{i-1}, is accurate exactly where the forward one
+    // is not (it grows towards the top when the last components are small).  The two are joined where the forward members peak.
+    {
+        double bp = 0.0, b = 1.0;
+        int sc = 0;
+        for (int i = k - 1; i >= 1; --i) {
+            if (lane == 0) {
+                sm.bv[i] = b;
+                sm.bve[i] = sc;
+            }
+            const double w = (sm.al[i] - theta) * sm.ib[i - 1];
+            const double bn = fma(w, b, -(sm.be[i] * sm.ib[i - 1]) * bp);
+            bp = b;
+            b = bn;
+            if ((i & 7) == 0) {
+                if (fabs(b) > 1e60) {
+                    b *= 0x1p-256, bp *= 0x1p-256;
+                    sc -= 256;
+                } else if (fabs(b) < 1e-60 && fabs(bp) < 1e-60) {
+                    b *= 0x1p256, bp *= 0x1p256;
+                    sc += 256;
+                }
+            }
+        }
+        if (lane == 0) {
+            sm.bv[0] = b;
+            sm.bve[0] = sc;
+        }
+    }
+    __syncwarp();
+    double lf[2], lb[2];  // log2 magnitudes of the forward / backward members i = lane, lane + 32
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        lf[h] = (i < k && sm.qv[i] != 0.0) ? log2(fabs(sm.qv[i])) - (double)sm.qe[i] : -1e300;
+        lb[h] = (i < k && sm.bv[i] != 0.0) ? log2(fabs(sm.bv[i])) - (double)sm.bve[i] : -1e300;
+    }
+    // r = where the forward members peak (first index on ties), off = what brings the forward members onto the backward ones there
+    double mf = fmax(lf[0], lf[1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+    const unsigned m0 = __ballot_sync(0xffffffffu, lf[0] == mf), m1 = __ballot_sync(0xffffffffu, lf[1] == mf);
+    const int r = m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1;
+    const double lbr = __shfl_sync(0xffffffffu, (r < 32) ? lb[0] : lb[1], r & 31);
+    const double off = (lbr > -1e299) ? lbr - mf : 0.0;
+    double st[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        st[h] = (i >= k) ? -1e300 : ((i <= r) ? ((lf[h] > -1e299) ? lf[h] + off : -1e300) : lb[h]);
+    }
+    double mx = fmax(st[0], st[1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    double s2 = ((st[0] > -1e299) ? exp2(2.0 * (st[0] - mx)) : 0.0) + ((st[1] > -1e299) ? exp2(2.0 * (st[1] - mx)) : 0.0);
+    s2 = warp_sum_d(s2);
+    const double llast = __shfl_sync(0xffffffffu, ((k - 1) < 32) ? st[0] : st[1], (k - 1) & 31);
+    const double bk = sm.be[k - 1];
+    res2 = (llast > -1e299) ? bk * bk * exp2(2.0 * (llast - mx)) / s2 : 0.0;
+}
+
+__global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseArgs a) {
     COVO_DYN_SMEM(smraw);
     LcSmem& sm = *reinterpret_cast<LcSmem*>(smraw);
     const int n = a.n, tid = threadIdx.x, env = blockIdx.y, lane = tid & 31, warp = tid >> 5;
     const int rank = (int)gjb_rank();
-    const int R = (n + LC_CL - 1) / LC_CL;      // rows per CTA (25 at n = 200)
-    const int rl = tid >> 2, ph = tid & 3;      // local row, column phase
-    const int row = rank * R + rl;
-    const bool has_row = rl < R && row < n;
-    const bool leader = has_row && ph == 0;
-    const int kc = (n + 3) >> 2;                // columns per thread
-    const float* Rg = a.R + (long long)env * n * n;
-    float* Asym = a.Asym ? a.Asym + (long long)env * n * n : nullptr;
+    const int k_max = min(kLanczosMax, n);
     DENSE_STAMP(48);
     if (tid == 0) {
         gjb_mbar_init(&sm.bar[0], 1);
         gjb_mbar_init(&sm.bar[1], 1);
+        sm.progress = sm.final_k = sm.verdict_k = sm.converged_k = 0;
 #if !defined(COVO_CPU_EMU)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
     }
-    // rows of (R + R^T)/2 (float32, controllers/covo.py:117) widened into registers
-    double ar[LC_KMAX];
-    {
-        float xa[LC_KMAX], xb[LC_KMAX];  // all loads in flight before the first store (the compiler must assume Asym aliases R)
-#pragma unroll
-        for (int k = 0; k < LC_KMAX; ++k) {
-            const int j = 4 * k + ph;
-            const bool ok = has_row && j < n;
-            xa[k] = ok ? __ldg(Rg + (long long)row * n + j) : 0.f;
-            xb[k] = ok ? __ldg(Rg + (long long)j * n + row) : 0.f;
+    if (warp == LC_T / 32) {
+        // ================================================ the checker ================================================
+        __syncthreads();
+        gjb_cluster_sync();
+        int c = min(kLanczosFirstCheck, k_max), c_prev = 0;
+        for (;;) {
+            int fk = 0;
+            for (;;) {  // T_c complete, or the recurrence over before it got there (lane 0 looks, so the warp cannot split)
+                int go = 0;
+                if (lane == 0) {
+                    fk = lc_load(&sm.final_k);
+                    go = fk || lc_load(&sm.progress) >= c;
+                }
+                go = __shfl_sync(0xffffffffu, go, 0);
+                if (go) break;
+                lc_pause();
+            }
+            fk = __shfl_sync(0xffffffffu, fk, 0);
+            if (fk && fk < c) c = fk;
+            lc_fence();
+            __syncwarp();
+            double theta, res2, gu;
+            lc_judge(sm, c, c_prev, lane, theta, res2, gu);
+            c_prev = c;
+#if defined(COVO_CPU_EMU)
+            if (lane == 0 && rank == 0 && getenv("COVO_EMU_TRACE")) fprintf(stderr, "checker: k %d theta %.12f res2 %.3e gu %.3f\n", c, theta, res2, gu);
+#endif
+            const bool conv = res2 <= kRitzTol2;
+            fk = __shfl_sync(0xffffffffu, (lane == 0) ? lc_load(&sm.final_k) : 0, 0);
+            const bool last = conv || c >= k_max || (fk && c >= fk);
+            if (lane == 0) {
+                if (conv) lc_store(&sm.converged_k, c);
+                lc_fence();
+                lc_store(&sm.verdict_k, c);
+                lc_published();
+                if (last && rank == 0) {
+                    // not converged (status 3): theta - residual is a lower bound of lambda_min for a Ritz pair that belongs to the
+                    // lowest eigenvalue, so A = R - lambda_min + 1e-2 stays positive definite; the spectrum's upper end moves with it
+                    const double r = conv ? 0.0 : sqrt(res2);
+                    a.scal[(long long)env * 4 + 0] = theta - r;
+                    a.scal[(long long)env * 4 + 1] = gu;  // upper bound of the spectrum of T (selects the approximation interval only)
+                    a.scal[(long long)env * 4 + 3] = (double)c;
+                    if (!conv) a.status[env] = 3;
+                }
+            }
+            if (last) break;
+            c = min(c + kLanczosCheckEvery, k_max);
         }
+    } else {
+        // ================================================ the recurrence ================================================
+        const int R = (n + LC_CL - 1) / LC_CL;      // rows per CTA (25 at n = 200)
+        const int rl = tid >> 2, ph = tid & 3;      // local row, column phase
+        const int row = rank * R + rl;
+        const bool has_row = rl < R && row < n;
+        const bool leader = has_row && ph == 0;
+        const int kc = (n + 3) >> 2;                // columns per thread
+        const float* Rg = a.R + (long long)env * n * n;
+        float* Asym = a.Asym ? a.Asym + (long long)env * n * n : nullptr;
+        // rows of (R + R^T)/2 (float32, controllers/covo.py:117) widened into registers
+        double ar[LC_KMAX];
+        {
+            float xa[LC_KMAX], xb[LC_KMAX];  // all loads in flight before the first store (the compiler must assume Asym aliases R)
 #pragma unroll
-        for (int k = 0; k < LC_KMAX; ++k) {
-            const int j = 4 * k + ph;
-            const float x = 0.5f * (xa[k] + xb[k]);
-            if (Asym && has_row && j < n) Asym[(long long)row * n + j] = x;
-            ar[k] = (double)x;
-        }
-    }
-    // start vector: every CTA builds and normalises all of it (same arithmetic everywhere)
-    {
-        double x[7], s2 = 0.0;
+            for (int k = 0; k < LC_KMAX; ++k) {
+                const int j = 4 * k + ph;
+                const bool ok = has_row && j < n;
+                xa[k] = ok ? __ldg(Rg + (long long)row * n + j) : 0.f;
+                xb[k] = ok ? __ldg(Rg + (long long)j * n + row) : 0.f;
+            }
 #pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            const int j = lane + 32 * c;
-            // fixed start vector with a component along every eigenvector in practice: 1 + a 16-bit multiplicative hash of j (no
-            // float64 transcendental: cos() alone cost 4 us here)
-            x[c] = (j < n) ? 1.0 + (double)(float)((((unsigned)j + 1u) * 2654435761u >> 8) & 0xffffu) * (1.0 / 65536.0) : 0.0;
-            s2 = fma(x[c], x[c], s2);
+            for (int k = 0; k < LC_KMAX; ++k) {
+                const int j = 4 * k + ph;
+                const float x = 0.5f * (xa[k] + xb[k]);
+                if (Asym && has_row && j < n) Asym[(long long)row * n + j] = x;
+                ar[k] = (double)x;
+            }
         }
-        const double inv = 1.0 / sqrt(warp_sum_d(s2));
-        if (warp == 0) {
+        // start vector: every CTA builds and normalises all of it (same arithmetic everywhere)
+        {
+            double x[7], s2 = 0.0;
 #pragma unroll
             for (int c = 0; c < 7; ++c) {
-                sm.v[0][lane + 32 * c] = x[c] * inv;
-                sm.v[1][lane + 32 * c] = 0.0;
+                const int j = lane + 32 * c;
+                // fixed start vector with a component along every eigenvector in practice: 1 + a 16-bit multiplicative hash of j (no
+                // float64 transcendental: cos() alone cost 4 us here)
+                x[c] = (j < n) ? 1.0 + (double)(float)((((unsigned)j + 1u) * 2654435761u >> 8) & 0xffffu) * (1.0 / 65536.0) : 0.0;
+                s2 = fma(x[c], x[c], s2);
             }
-        }
-    }
-    __syncthreads();
-    double vj = has_row ? sm.v[0][row] : 0.0, vprev = 0.0;  // row leaders keep v_k[row], v_{k-1}[row]
-    const int n_warps_total = LC_CL * 4;
-    const int tx_bytes = n * 8 + n_warps_total * 16;
-    gjb_cluster_sync();  // barriers initialised everywhere before the first send
-    DENSE_STAMP(49);
-    // 24 steps: over 72 scenarios (three tasks, six seeds, four flight phases, H = 50) the smallest Ritz value is within 2e-8 of
-    // lambda_min after 20 steps and 5e-12 after 24 (needed: << 2e-7 absolute); every step is a dependent ~1 us exchange
-    const int k_max = min(kLanczosSteps, n);
-    int kdone = 0;
-    double beta_prev = 0.0;
-    LcRemote rem[LC_CL];  // where this thread's row entry / this warp's partial slot / the barrier live in every CTA of the cluster
+            const double inv = 1.0 / sqrt(warp_sum_d(s2));
+            if (warp == 0) {
 #pragma unroll
-    for (int r = 0; r < LC_CL; ++r)
-        rem[r] = lc_remote(&sm.u[0][has_row ? row : 0], &sm.part[0][rank * 4 + warp][0], &sm.bar[0], (unsigned)r);
-    for (int it = 0; it < k_max; ++it) {
-        const int pc = it & 1;  // v_k is in v[pc]; this iteration's exchange uses u[pc], part[pc], bar[pc]
-        // y_row = (A v_k)_row: four threads per row, four independent chains each
-        // (dependent float64 operations are ~40 cycles apart on this pipe: eight chains of seven, not four of thirteen)
-        double ac[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        const double* vv = sm.v[pc];
-#pragma unroll
-        for (int k = 0; k < LC_KMAX; k += 8) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-                if (k + e < kc) ac[e] = fma(ar[k + e], vv[4 * (k + e) + ph], ac[e]);
-        }
-        double y = ((ac[0] + ac[1]) + (ac[2] + ac[3])) + ((ac[4] + ac[5]) + (ac[6] + ac[7]));
-        y += __shfl_xor_sync(0xffffffffu, y, 1);
-        y += __shfl_xor_sync(0xffffffffu, y, 2);
-        // u = y - beta_{k-1} v_{k-1} (row leaders); partials of u.v_k and u.u over the 8 rows of the warp
-        const double u = leader ? y - beta_prev * vprev : 0.0;
-        double pa = u * vj, pu = u * u;
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-            pa += __shfl_xor_sync(0xffffffffu, pa, o);
-            pu += __shfl_xor_sync(0xffffffffu, pu, o);
-        }
-        if (tid == 0) gjb_mbar_expect(&sm.bar[pc], tx_bytes);
-        long long tq0 = 0;
-        if (a.prof && tid == 0 && rank == 0 && blockIdx.y == 0) tq0 = clock64();
-        // the exchange: u of this row and the warp's partials to every CTA of the cluster (this one included)
-#pragma unroll
-        for (int r = 0; r < LC_CL; ++r) {
-            if (leader) lc_send(rem[r], 0, pc, u);
-            if (lane == 0) {
-                lc_send(rem[r], 1, pc, pa);
-                lc_send(rem[r], 2, pc, pu);
+                for (int c = 0; c < 7; ++c) {
+                    sm.v[0][lane + 32 * c] = x[c] * inv;
+                    sm.v[1][lane + 32 * c] = 0.0;
+                }
             }
-        }
-        gjb_mbar_wait(&sm.bar[pc], (unsigned)((it >> 1) & 1));
-        if (a.prof && tid == 0 && rank == 0 && blockIdx.y == 0) a.prof[52] = (it == 0 ? 0 : a.prof[52]) + (clock64() - tq0);  // send + wait
-        // alpha = u.v_k, beta_k^2 = |u - alpha v_k|^2 = u.u - alpha^2: every warp sums the 32 partial pairs with the same butterfly
-        double qa = (lane < n_warps_total) ? sm.part[pc][lane][0] : 0.0;
-        double qu = (lane < n_warps_total) ? sm.part[pc][lane][1] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {  // the two sums interleaved: five levels of (shuffle + add) each
-            qa += __shfl_xor_sync(0xffffffffu, qa, o);
-            qu += __shfl_xor_sync(0xffffffffu, qu, o);
-        }
-        const double alpha = qa;
-        double b2 = qu - alpha * alpha;
-        if (b2 < 1e-3 * qu) {
-            // |u|^2 - alpha^2 cancels when beta << |alpha| (Krylov space nearly exhausted, small n): form |u - alpha v_k|^2 directly.
-            // Every CTA holds all of u and v_k, so this needs no exchange; the branch is uniform across the cluster.
-            double ps = 0.0;
-            for (int j = tid; j < n; j += LC_T) {
-                const double wj = sm.u[pc][j] - alpha * vv[j];
-                ps = fma(wj, wj, ps);
-            }
-            ps = warp_sum_d(ps);
-            double* red = &sm.sal[0];  // free until the Ritz stage
-            if (lane == 0) red[warp] = ps;
-            __syncthreads();
-            b2 = (red[0] + red[1]) + (red[2] + red[3]);
-            __syncthreads();
-        }
-        // 1 / beta and beta without float64 sqrt / division (each a chain of ~15 dependent float64 operations at ~40 cycles): float32
-        // rsqrt seed, two Newton steps (1e-7 -> 1e-14 -> rounding), six dependent operations
-        double beta_new = 0.0, ib = 0.0;
-        if (b2 > 1e-280) {
-            const double sc = (b2 < 1e-30) ? 1e60 : 1.0;  // keep the seed inside the float32 range
-            const double bs = b2 * sc;
-            double r = (double)rsqrtf((float)bs);
-            r = r * fma(-0.5 * bs, r * r, 1.5);
-            r = r * fma(-0.5 * bs, r * r, 1.5);
-            ib = r * ((b2 < 1e-30) ? 1e30 : 1.0);
-            beta_new = b2 * ib;
-        }
-        if (tid == 0) {
-            sm.al[it] = alpha;
-            sm.be[it] = beta_new;
-        }
-        kdone = it + 1;
-        if (!(beta_new > 1e-200)) break;  // invariant subspace (uniform across the cluster: every CTA sees the same data)
-        // v_{k+1} = (u - alpha v_k) / beta_k: every CTA forms all of it (two entries per thread)
-        for (int j = tid; j < n; j += LC_T) sm.v[pc ^ 1][j] = (sm.u[pc][j] - alpha * vv[j]) * ib;
-        if (leader) {
-            const double vn = (u - alpha * vj) * ib;
-            vprev = vj;
-            vj = vn;
-        }
-        beta_prev = beta_new;
-        __syncthreads();
-    }
-    __syncthreads();
-    DENSE_STAMP(50);
-    // ---- smallest Ritz value (CTA 0) ---------------------------------------------------------------------------------------
-    if (rank == 0) {
-        const int k = kdone;
-        double gl = 1e300, gu = -1e300;
-        for (int i = 0; i < k; ++i) {
-            const double r = ((i > 0) ? fabs(sm.be[i - 1]) : 0.0) + ((i < k - 1) ? fabs(sm.be[i]) : 0.0);
-            gl = fmin(gl, sm.al[i] - r);
-            gu = fmax(gu, sm.al[i] + r);
-        }
-        const double pad = 1e-12 * fmax(fabs(gl), fabs(gu)) + 1e-300;
-        gl -= pad;
-        gu += pad;
-        const double isc = 1.0 / (gu - gl);
-        if (tid < k) {
-            sm.sal[tid] = (sm.al[tid] - gl) * isc;
-            const double b = sm.be[tid] * isc;
-            sm.sb2[tid] = b * b;
-            sm.salf[tid] = (float)sm.sal[tid];
-            sm.sb2f[tid] = (float)sm.sb2[tid];
         }
         __syncthreads();
-        double lo = 0.0, hi = 1.0;
-        // rounds 0, 1 in float32 (the float64 pipe issues 16 lanes / clock: a float64 round costs ~0.65 us), then the bracket
-        // [lo, hi] (6e-5 wide) is widened by 2e-5 on both sides -- 10x what float32 rounding of the scaled recurrence can move a
-        // crossing -- and three float64 rounds bring it to 1e-4 / 129^3 = 4.7e-11 of the Gershgorin interval
-        for (int round = 0; round < 5; ++round) {
-            if (round == 2) {
-                lo = fmax(lo - 2e-5, 0.0);
-                hi = fmin(hi + 2e-5, 1.0);
+        double vj = has_row ? sm.v[0][row] : 0.0, vprev = 0.0;  // row leaders keep v_k[row], v_{k-1}[row]
+        const int n_warps_total = LC_CL * 4;
+        const int tx_bytes = n * 8 + n_warps_total * 16;
+        gjb_cluster_sync();  // barriers initialised everywhere before the first send
+        DENSE_STAMP(49);
+        int kdone = 0;
+        double beta_prev = 0.0;
+        LcRemote rem[LC_CL];  // where this thread's row entry / this warp's partial slot / the barrier live in every CTA of the cluster
+#pragma unroll
+        for (int r = 0; r < LC_CL; ++r)
+            rem[r] = lc_remote(&sm.u[0][has_row ? row : 0], &sm.part[0][rank * 4 + warp][0], &sm.bar[0], (unsigned)r);
+        for (int it = 0; it < k_max; ++it) {
+            const int pc = it & 1;  // v_k is in v[pc]; this step's exchange uses u[pc], part[pc], bar[pc]
+            // y_row = (A v_k)_row: four threads per row, eight independent chains each
+            // (dependent float64 operations are ~40 cycles apart on this pipe: eight chains of seven, not four of thirteen)
+            double ac[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            const double* vv = sm.v[pc];
+#pragma unroll
+            for (int k = 0; k < LC_KMAX; k += 8) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (k + e < kc) ac[e] = fma(ar[k + e], vv[4 * (k + e) + ph], ac[e]);
             }
-            const double step = (hi - lo) / 129.0;
-            const double xs = lo + step * (double)(tid + 1);
-            const bool ge = (round < 2 ? sturm_count_poly_f32(sm.salf, sm.sb2f, k, (float)xs) : sturm_count_poly(sm.sal, sm.sb2, k, xs)) >= 1;
-            const unsigned m = __ballot_sync(0xffffffffu, ge);
-            if (lane == 0) sm.first[round & 1][warp] = m ? 32 * warp + __ffs(m) - 1 : 128;
-            __syncthreads();
-            const int* fr = sm.first[round & 1];
-            const int f = min(min(fr[0], fr[1]), min(fr[2], fr[3]));
-            if (f >= 128) {
-                lo = lo + step * 128.0;
-            } else {
-                hi = lo + step * (double)(f + 1);
-                lo = lo + step * (double)f;
+            double y = ((ac[0] + ac[1]) + (ac[2] + ac[3])) + ((ac[4] + ac[5]) + (ac[6] + ac[7]));
+            y += __shfl_xor_sync(0xffffffffu, y, 1);
+            y += __shfl_xor_sync(0xffffffffu, y, 2);
+            // u = y - beta_{k-1} v_{k-1} (row leaders); partials of u.v_k and u.u over the 8 rows of the warp
+            const double u = leader ? y - beta_prev * vprev : 0.0;
+            double pa = u * vj, pu = u * u;
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                pa += __shfl_xor_sync(0xffffffffu, pa, o);
+                pu += __shfl_xor_sync(0xffffffffu, pu, o);
             }
+            if (tid == 0) gjb_mbar_expect(&sm.bar[pc], tx_bytes);
+            long long tq0 = 0;
+            if (a.prof && tid == 0 && rank == 0 && blockIdx.y == 0) tq0 = clock64();
+            // the exchange: u of this row and the warp's partials to every CTA of the cluster (this one included)
+#pragma unroll
+            for (int r = 0; r < LC_CL; ++r) {
+                if (leader) lc_send(rem[r], 0, pc, u);
+                if (lane == 0) {
+                    lc_send(rem[r], 1, pc, pa);
+                    lc_send(rem[r], 2, pc, pu);
+                }
+            }
+            // In the shadow of the exchange: 1 / |v_k|^2, every warp for itself (all of v_k is local; same arithmetic everywhere).
+            // v_k is normalised with the COMPUTED beta, so |v_k|^2 = 1 + delta; "beta^2 = u.u - alpha^2" takes delta for zero and hands
+            // delta alpha^2 / beta^2 on to the next vector: (alpha / beta)^2 is ~30 for every ghost of lambda_max, and after ~55 steps
+            // the recurrence had lost its normalisation (Ritz values outside the spectrum).  With the measured norm the formulas below
+            // are exact algebra for any delta.
+            double iqv;
+            {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; c += 2) {
+                    const double x0 = vv[lane + 32 * c], x1 = vv[lane + 32 * (c + 1)];
+                    s0 = fma(x0, x0, s0);
+                    s1 = fma(x1, x1, s1);
+                }
+                const double x6 = vv[lane + 32 * 6];
+                s0 = fma(x6, x6, s0);
+                const double qv = warp_sum_d(s0 + s1);
+                double r = 2.0 - qv;  // 1 / qv for qv = 1 + delta: two Newton steps from the first-order guess
+                r = r * (2.0 - qv * r);
+                iqv = r * (2.0 - qv * r);
+            }
+            gjb_mbar_wait(&sm.bar[pc], (unsigned)((it >> 1) & 1));
+            if (a.prof && tid == 0 && rank == 0 && blockIdx.y == 0) a.prof[52] = (it == 0 ? 0 : a.prof[52]) + (clock64() - tq0);  // send + wait
+            // alpha = u.v_k / |v_k|^2, beta_k^2 = |u - alpha v_k|^2 = u.u - alpha (u.v_k): every warp sums the 32 partial pairs with the
+            // same butterfly
+            double qa = (lane < n_warps_total) ? sm.part[pc][lane][0] : 0.0;
+            double qu = (lane < n_warps_total) ? sm.part[pc][lane][1] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {  // the two sums interleaved: five levels of (shuffle + add) each
+                qa += __shfl_xor_sync(0xffffffffu, qa, o);
+                qu += __shfl_xor_sync(0xffffffffu, qu, o);
+            }
+            const double alpha = qa * iqv;
+            double b2 = qu - alpha * qa;
+            if (b2 < 1e-3 * qu) {
+                // |u|^2 - alpha^2 cancels when beta << |alpha| (Krylov space nearly exhausted, small n): form |u - alpha v_k|^2 directly.
+                // Every CTA holds all of u and v_k, so this needs no exchange; the branch is uniform across the cluster.
+                double ps = 0.0;
+                for (int j = tid; j < n; j += LC_T) {
+                    const double wj = sm.u[pc][j] - alpha * vv[j];
+                    ps = fma(wj, wj, ps);
+                }
+                ps = warp_sum_d(ps);
+                if (lane == 0) sm.red[warp] = ps;
+                lc_main_sync();
+                b2 = (sm.red[0] + sm.red[1]) + (sm.red[2] + sm.red[3]);
+                lc_main_sync();
+            }
+            // 1 / beta and beta without float64 sqrt / division (each a chain of ~15 dependent float64 operations at ~40 cycles): float32
+            // rsqrt seed, two Newton steps (1e-7 -> 1e-14 -> rounding), six dependent operations
+            double beta_new = 0.0, ib = 0.0;
+            if (b2 > 1e-280) {
+                const double sc = (b2 < 1e-30) ? 1e60 : 1.0;  // keep the seed inside the float32 range
+                const double bs = b2 * sc;
+                double r = (double)rsqrtf((float)bs);
+                r = r * fma(-0.5 * bs, r * r, 1.5);
+                r = r * fma(-0.5 * bs, r * r, 1.5);
+                ib = r * ((b2 < 1e-30) ? 1e30 : 1.0);
+                beta_new = b2 * ib;
+            }
+            if (tid == 0) {  // hand T's new row to the checker
+                sm.al[it] = alpha;
+                sm.be[it] = beta_new;
+                lc_fence();
+                lc_store(&sm.progress, it + 1);
+                lc_published();
+            }
+            kdone = it + 1;
+            if (!(beta_new > 1e-200)) break;  // invariant subspace (uniform across the cluster: every CTA sees the same data)
+            // v_{k+1} = (u - alpha v_k) / beta_k: every CTA forms all of it (two entries per thread)
+            for (int j = tid; j < n; j += LC_T) sm.v[pc ^ 1][j] = (sm.u[pc][j] - alpha * vv[j]) * ib;
+            if (leader) {
+                const double vn = (u - alpha * vj) * ib;
+                vprev = vj;
+                vj = vn;
+            }
+            beta_prev = beta_new;
+            // the checker's verdict on T_c, c = kdone - lag (the same numbers in every CTA: the whole cluster stops here or nowhere)
+            const int c = kdone - kLanczosLag;
+            bool stop = false;
+            if (c >= kLanczosFirstCheck && (c - kLanczosFirstCheck) % kLanczosCheckEvery == 0) {
+                if (lane == 0)
+                    while (lc_load(&sm.verdict_k) < c) lc_pause();
+                __syncwarp();
+                lc_fence();
+                const int ck = lc_load(&sm.converged_k);
+                stop = ck != 0 && ck <= c;
+            }
+            lc_main_sync();
+            if (stop) break;
         }
-        // Newton from the left end: lo is below every root, the iteration increases monotonically to the smallest one
         if (tid == 0) {
-            double x = lo;
-            for (int itn = 0; itn < 4; ++itn) {  // polish: quadratic for a simple root, harmless (stays inside the bracket) otherwise
-                double p, dp;
-                lc_poly_newton(sm.sal, sm.sb2, k, x, p, dp);
-                if (!(dp != 0.0)) break;
-                const double xn = x - p / dp;
-                if (!(xn > x) || xn > hi) break;  // converged to rounding (or left the bracket: keep the last safe iterate)
-                x = xn;
-            }
-            a.scal[(long long)env * 4 + 0] = gl + x * (gu - gl);
-            a.scal[(long long)env * 4 + 1] = gu;  // upper bound of the spectrum of T (selects the approximation interval only)
+            lc_fence();
+            lc_store(&sm.final_k, kdone);
+            lc_published();
         }
+        DENSE_STAMP(50);
     }
     DENSE_STAMP(51);
-    gjb_cluster_sync();  // nobody leaves while a peer could still be sending to it
+    gjb_cluster_sync();  // nobody leaves while a peer could still be sending to it (and the checker has written lambda_min)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// D2'' gjb_inverse_kernel (COVO_SIGMA=dense-gjb): the same in-place Gauss-Jordan sweep, BLOCKED (8 pivots per step) and spread over
+// D2 gjb_inverse_kernel: in-place Gauss-Jordan sweep without pivoting (A + t_j I is SPD), BLOCKED (8 pivots per step) and spread over
 // a 2-CTA cluster per pole, the matrix resident in registers.  Sweeping the index block K with P = A_KK:
 //     A_IJ -= A_IK P^-1 A_KJ,   A_KJ <- P^-1 A_KJ =: G,   A_IK <- -A_IK P^-1,   A_KK <- P^-1.
 // With the sign convention of D2' the matrix is symmetric on the unswept index set and ANTI-symmetric between swept and unswept
@@ -1339,7 +754,12 @@ __global__ void __launch_bounds__(LC_T, 1) lanczos_cluster_kernel(const DenseArg
 // between the CTAs), so a CTA can run at most 3 blocks ahead of its peer before it needs a panel from it: 4 slots never collide.
 // Cost model at n = 200: 25 steps x max(update 1800 cycles, solver chain ~1600) instead of 200 steps x 1100.
 // ---------------------------------------------------------------------------------------------------------------------------
-constexpr int GB_CL = 2;     // CTAs per matrix
+#ifndef COVO_GB_CL
+#define COVO_GB_CL 4
+#endif
+constexpr int GB_CL = COVO_GB_CL;                       // CTAs per matrix (2, 4 or 8)
+constexpr int GB_NSLOT = (14 + GB_CL - 1) / GB_CL;     // 16-row tiles per CTA: tile a lives in CTA a % GB_CL, row slot a / GB_CL
+constexpr int GB_NQ = (GB_NSLOT + 1) / 2;              // row pairs per thread (packed for FFMA2)
 constexpr int GB_UT = 512;   // update threads
 constexpr int GB_ST = 128;   // solver threads
 constexpr int GB_T = GB_UT + GB_ST;
@@ -1356,7 +776,7 @@ struct GjbSmem {
     float raw[GB_SLOTS][8][GB_RS];  // pivot-row panels [s][j]
     float stage[2][8][GB_NP];       // a pivot row on its way out (by block parity): source of the bulk copies
     float G[2][4][GB_NP][2];        // [parity][s / 2][j][s & 1]
-    float2 Mneg[2][16][4][8];       // [parity][ty][row pair q][s]: (-sigma(i0) raw[s][i0], -sigma(i1) raw[s][i1]); 0 for pivot rows
+    float2 Mneg[2][16][GB_NQ][8];   // [parity][ty][row pair q][s]: (-sigma(i0) raw[s][i0], -sigma(i1) raw[s][i1]); 0 for pivot rows
     float Pinv[2][64];
     float piv[GB_NP];
     unsigned long long rawbar[GB_SLOTS];
@@ -1414,6 +834,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 // P^-1 by an in-place Gauss-Jordan sweep of the 8 x 8 block: lane = (row r, columns c0, c0 + 1)
                 const int r = lane >> 2, c0 = (lane & 3) * 2;
                 float x0 = rw[r][K0 + c0], x1 = rw[r][K0 + c0 + 1];
+                float pvs[8];  // the scalar pivots (log det, positivity): written out after the chain, not inside it
 #pragma unroll
                 for (int sp = 0; sp < 8; ++sp) {
                     const float mine = (sp & 1) ? x1 : x0;
@@ -1421,10 +842,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                     const float prs = __shfl_sync(0xffffffffu, mine, (r << 2) | (sp >> 1));   // P[r][sp]
                     const float ps0 = __shfl_sync(0xffffffffu, x0, (sp << 2) | (lane & 3));   // P[sp][c0]
                     const float ps1 = __shfl_sync(0xffffffffu, x1, (sp << 2) | (lane & 3));   // P[sp][c0 + 1]
-                    if (lane == 0) {
-                        sm.piv[K0 + sp] = p;
-                        if (!(p > 0.f)) sm.bad = 1;
-                    }
+                    pvs[sp] = p;
                     const float rinv = gjb_rcp(p);
                     if (r == sp) {
                         x0 = (c0 == sp) ? rinv : ps0 * rinv;
@@ -1437,10 +855,17 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 }
                 sm.Pinv[par][r * 8 + c0] = x0;
                 sm.Pinv[par][r * 8 + c0 + 1] = x1;
+                if (lane < 8) {
+                    float pl = pvs[0];
+#pragma unroll
+                    for (int sp = 1; sp < 8; ++sp) pl = (lane == sp) ? pvs[sp] : pl;
+                    sm.piv[K0 + lane] = pl;
+                    if (!(pl > 0.f)) sm.bad = 1;
+                }
             } else {
                 // signed, negated, pair-packed multipliers of this CTA's rows
-                for (int e = sidx - 32; e < 16 * 4 * 8; e += GB_ST - 32) {
-                    const int ty = e >> 5, q = (e >> 3) & 3, sp = e & 7;
+                for (int e = sidx - 32; e < 16 * GB_NQ * 8; e += GB_ST - 32) {
+                    const int ty = e / (GB_NQ * 8), q = (e >> 3) % GB_NQ, sp = e & 7;
                     float2 val;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -1493,7 +918,9 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 a.prof[56] = (m == 0 ? 0 : a.prof[56]) + (t1 - t0);
                 t0 = t1;
             }
+            if (GB_CL > 2 && m > 0) gjb_cluster_wait();
             __syncthreads();  // opens step m for the update warps
+            if (GB_CL > 2) gjb_cluster_arrive();
             if (pf) a.prof[57] = (m == 0 ? 0 : a.prof[57]) + (clock64() - t0);
         }
     } else {
@@ -1501,9 +928,9 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         const int tx = tid & 31, ty = tid >> 5;
         const float* Ag = a.Asym ? a.Asym + (long long)env * n * n : nullptr;
         const float* Rg = a.R + (long long)env * n * n;
-        float2 acc[4][7];
+        float2 acc[GB_NQ][7];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < GB_NQ; ++q)
 #pragma unroll
             for (int b = 0; b < 7; ++b) {
                 float v2[2];
@@ -1512,7 +939,12 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                     const int tile = rank + GB_CL * (2 * q + h), i = ty + 16 * tile, j = tx + 32 * b;
                     float v = (i == j && tile < GB_NP / 16) ? 1.f : 0.f;  // identity padding: never coupled, pivots 1
                     if (i < n && j < n) {
-                        v = Ag ? Ag[(long long)i * n + j] : 0.5f * (Rg[(long long)i * n + j] + Rg[(long long)j * n + i]);
+                        // position (i, j) holds element (n - 1 - i, n - 1 - j): the sweep eliminates the LAST controls first.  Without
+                        // pivoting the order decides the accuracy: the Hessian's large entries belong to the early controls, and
+                        // sweeping those first cost up to 8e-3 of Sigma at cond(A) = 1.6e5 (float32); back to front it is 2e-5 .. 8e-5,
+                        // the level of a float32 Cholesky factorisation (scratch/gj_accuracy.py)
+                        const int ir = n - 1 - i, jr = n - 1 - j;
+                        v = Ag ? Ag[(long long)ir * n + jr] : 0.5f * (Rg[(long long)ir * n + jr] + Rg[(long long)jr * n + ir]);
                         if (i == j) v = (float)((double)v + shift);
                     }
                     v2[h] = v;
@@ -1542,7 +974,9 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         const bool pfu = a.prof && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
         long long tu0 = pfu ? clock64() : 0;
         for (int m = 0; m < nblk; ++m) {
+            if (GB_CL > 2 && m > 0) gjb_cluster_wait();  // every CTA of the cluster has opened step m - 1 (see "flow control")
             __syncthreads();  // G, multipliers and P^-1 of block m are in place; everybody is done with step m - 1
+            if (GB_CL > 2) gjb_cluster_arrive();
             if (pfu) {
                 const long long t1 = clock64();
                 a.prof[58] = (m == 0 ? 0 : a.prof[58]) + (t1 - tu0);
@@ -1573,12 +1007,12 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                     const int a1 = tile1 / GB_CL, q1 = a1 >> 1, h1 = a1 & 1, i = ty + 16 * tile1;
                     q_done = q1;
                     if (q1 == 0) update_pair(IntC<0>());
-                    else if (q1 == 1) update_pair(IntC<1>());
-                    else if (q1 == 2) update_pair(IntC<2>());
-                    else update_pair(IntC<3>());
+                    else if (q1 == 1) update_pair(IntC<(GB_NQ > 1 ? 1 : 0)>());
+                    else if (q1 == 2) update_pair(IntC<(GB_NQ > 2 ? 2 : 0)>());
+                    else update_pair(IntC<(GB_NQ > 3 ? 3 : 0)>());
                     float tmp[7];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                    for (int q = 0; q < GB_NQ; ++q)
                         if (q == q1) {
 #pragma unroll
                             for (int b = 0; b < 7; ++b) tmp[b] = h1 ? acc[q][b].y : acc[q][b].x;
@@ -1600,7 +1034,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
 #pragma unroll
                 for (int b = 0; b < 7; ++b) g2[b] = *reinterpret_cast<const float2*>(&sm.G[par][qt][tx + 32 * b][0]);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < GB_NQ; ++q) {
                     if (q == q_done) continue;  // warp-uniform
                     const float4 m4 = *reinterpret_cast<const float4*>(&mrow[q * 8 + 2 * qt]);
                     const float2 ma = make_float2(m4.x, m4.y), mb = make_float2(m4.z, m4.w);
@@ -1622,7 +1056,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                     const int j = tx + 32 * b;
                     const float v = (j >= K0 && j < K0 + 8) ? sm.Pinv[par][sr * 8 + (j - K0)] : sm.G[par][sr >> 1][j][sr & 1];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                    for (int q = 0; q < GB_NQ; ++q)
                         if (q == q0) {
                             if (h0) acc[q][b].y = v;
                             else acc[q][b].x = v;
@@ -1632,7 +1066,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
             if ((tx & ~7) == (K0 & 31)) {
                 const int sc = tx - (K0 & 31), b0 = K0 >> 5;
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < GB_NQ; ++q)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int tile = rank + GB_CL * (2 * q + h), i = ty + 16 * tile;
@@ -1658,14 +1092,15 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         if (!want_logdet) {
             float* Xg = a.Xbuf + ((long long)env * kZoloPoles + pole) * n * n;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < GB_NQ; ++q)
 #pragma unroll
                 for (int b = 0; b < 7; ++b) {
                     const int j = tx + 32 * b;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int tile = rank + GB_CL * (2 * q + h), i = ty + 16 * tile;
-                        if (tile < GB_NP / 16 && i < n && j <= i) Xg[(long long)i * n + j] = wj * (h ? acc[q][b].y : acc[q][b].x);
+                        if (tile < GB_NP / 16 && i < n && j <= i)  // (reversed positions: this is the upper triangle of the inverse)
+                            Xg[(long long)(n - 1 - i) * n + (n - 1 - j)] = wj * (h ? acc[q][b].y : acc[q][b].x);
                     }
                 }
         } else if (rank == 0 && ty < 7) {  // log det A = sum of the logarithms of the scalar pivots (both CTAs hold all of them)
@@ -1685,6 +1120,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         }
         if (tid == 0 && sm.bad) a.status[env] = 2;
     }
+    if (GB_CL > 2) gjb_cluster_wait();  // the arrive of the last step
     gjb_cluster_sync();  // nobody leaves while a peer could still be sending to it
 }
 
@@ -1706,11 +1142,12 @@ __global__ void __launch_bounds__(256) combine_kernel(const DenseArgs a) {
         while ((ia + 1) * (ia + 2) / 2 <= q) ++ia;
         const int ib = q - ia * (ia + 1) / 2;
         float s = 0.f;
+        const int I = n - 1 - ia, J = n - 1 - ib;  // I <= J: the inverse kernels store the upper triangle (they work back to front)
 #pragma unroll
-        for (int j = 0; j < kZoloPoles; ++j) s += Xg[(long long)j * n * n + ia * n + ib];
+        for (int j = 0; j < kZoloPoles; ++j) s += Xg[(long long)j * n * n + I * n + J];
         s *= scale;
-        cov[ia * n + ib] = s;
-        cov[ib * n + ia] = s;  // (a_cov + a_cov.T)/2 (:132) holds by construction
+        cov[I * n + J] = s;
+        cov[J * n + I] = s;  // (a_cov + a_cov.T)/2 (:132) holds by construction
     }
 }
 
@@ -1718,7 +1155,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const DenseArgs a) {
 size_t sigma_dense_scratch_floats(int n) { return (size_t)kZoloPoles * n * n; }
 
 #if !defined(COVO_CPU_EMU)
-cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, int n_env, cudaStream_t st, int variant) {
+cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, int n_env, cudaStream_t st, cudaEvent_t ev_mid1, cudaEvent_t ev_mid2) {
     if (s.n > kSigmaMaxN || (s.n & 3)) return cudaErrorInvalidValue;
     DenseArgs a;
     a.n = s.n;
@@ -1731,26 +1168,12 @@ cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, in
     a.zolo = s.zolo;
     a.status = s.status;
     a.prof = s.prof;
-    static size_t conf1[32] = {}, conf2[32] = {}, conf3[32] = {};
     cudaError_t e;
-    // Lanczos kernel: the 8-CTA cluster version by default; COVO_LANCZOS=v1 | v2 select the single-CTA kernels (development)
-    const char* lz = getenv("COVO_LANCZOS");
-    const int lz_kind = (lz && !strcmp(lz, "v1")) ? 1 : (lz && !strcmp(lz, "v2") && lanczos2_layout(a.n).fits) ? 2 : 3;
-    a.Asym = (lz_kind == 1) ? nullptr : s.F;  // the symmetrised matrix, written by the Lanczos kernel (F is unused on this path)
-    if (lz_kind == 1) {
-        const size_t smem1 = (size_t)(2 * a.n + 8 + 2 * kLanczosMax) * sizeof(double) + (size_t)a.n * (a.n + 1) * sizeof(float);
-        e = ensure_smem_attr(lanczos_kernel, smem1, conf1);
-        if (e != cudaSuccess) return e;
-        lanczos_kernel<<<n_env, TL, smem1, st>>>(a);
-    } else if (lz_kind == 2) {
-        const size_t smem3 = lanczos2_layout(a.n).bytes;
-        e = ensure_smem_attr(lanczos2_kernel, smem3, conf3);
-        if (e != cudaSuccess) return e;
-        lanczos2_kernel<<<n_env, TL2, smem3, st>>>(a);
-    } else {
+    a.Asym = s.F;  // the symmetrised matrix, written by the Lanczos kernel (F is unused on this path)
+    {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(LC_CL, n_env);
-        cfg.blockDim = dim3(LC_T);
+        cfg.blockDim = dim3(LC_TT);
         cfg.dynamicSmemBytes = sizeof(LcSmem);
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -1763,9 +1186,8 @@ cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, in
         e = cudaLaunchKernelEx(&cfg, lanczos_cluster_kernel, a);
         if (e != cudaSuccess) return e;
     }
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    if (variant == 3) {  // blocked Gauss-Jordan on a 2-CTA cluster per pole
+    if (ev_mid1) cudaEventRecord(ev_mid1, st);
+    {  // blocked Gauss-Jordan, one cluster per pole (+ one for log det A)
         static size_t conf4[32] = {};
         e = ensure_smem_attr(gjb_inverse_kernel, sizeof(GjbSmem), conf4);
         if (e != cudaSuccess) return e;
@@ -1783,18 +1205,8 @@ cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, in
         cfg.numAttrs = 1;
         e = cudaLaunchKernelEx(&cfg, gjb_inverse_kernel, a);
         if (e != cudaSuccess) return e;
-    } else if (variant == 2) {  // register-resident Gauss-Jordan
-        gj_inverse_kernel<14><<<dim3(kZoloPoles + 1, n_env), TG, 1024 * sizeof(float), st>>>(a);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    } else {
-        const size_t smem2 = ((size_t)a.n * a.n + 2 * 8 * a.n_pad + 64 + a.n_pad) * sizeof(float) + 16;
-        e = ensure_smem_attr(shifted_inverse_kernel, smem2, conf2);
-        if (e != cudaSuccess) return e;
-        shifted_inverse_kernel<<<dim3(kZoloPoles + 1, n_env), TD, smem2, st>>>(a);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
     }
+    if (ev_mid2) cudaEventRecord(ev_mid2, st);
     const int npairs = a.n * (a.n + 1) / 2;
     combine_kernel<<<dim3((npairs + 255) / 256, n_env), 256, 0, st>>>(a);
     return cudaGetLastError();

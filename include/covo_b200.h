@@ -113,7 +113,7 @@ int covo_step(covo_handle* h, const float* state24, const int* time, const float
 /* Numeric status: the covariance step of every CoVO-online call starts by clearing the per-environment status (it is per step,
  * not sticky).  covo_step reads it back with the action and returns COVO_ERR_NUMERIC (action still written) when the spectral
  * range left the rational-approximation ladder (1) or a Cholesky pivot was not positive (2) -- where the reference would surface
- * NaNs (controllers/covo.py:116-132, :216).  The asynchronous entry points (covo_step_device, covo_step_partial_device,
+ * NaNs (controllers/covo.py:116-132, :216); status 3 (dense path only, see covo_set_sigma_path) is not an error.  The asynchronous entry points (covo_step_device, covo_step_partial_device,
  * covo_closed_loop) cannot: their callers poll covo_get_status(). */
 /* The physical model a handle plans with (dynamics/dataclass.py:43-49, 71, 76, 81), replaceable after creation: the reference rolls
  * out and differentiates with the env_params of the CALL (controllers/covo.py:187-283 `env_params`), e.g. a mass sampled by
@@ -177,9 +177,24 @@ int covo_env_step(covo_handle* h, const float* action, const float* noise, unsig
 int covo_closed_loop(covo_handle* h, int n_steps, unsigned long long noise_seed, int gaussian_disturbance,
                      float obs_noise_scale, float dyn_noise_scale, const float* noise, float* actions, float* rewards,
                      float* err_pos);
+/* Which optimize_sigma (controllers/covo.py:116-132) kernels the handle runs:
+ *   0 = tridiagonal path (default): Householder -> tridiagonal matrix function in float64 -> Q F Q^T.  Sigma within 1e-6 .. 1e-5
+ *       (relative Frobenius) of exact arithmetic on the same float32 Hessian: the accuracy of the reference's float32 eigh.
+ *   3 = dense FAST path: adaptive Lanczos lambda_min (float64) -> one float32 Gauss-Jordan inverse per pole of the rational
+ *       approximation of x^(-1/2) -> combine.  0.16 ms less per step at H = 50; Sigma is symmetric positive definite with the exact
+ *       determinant but only within 1e-4 (median) .. 5e-3 (worst seen over a 300-step closed loop) of exact arithmetic, because
+ *       float32 inverses of matrices of condition 1e5 are no better.  Opt in with this call or COVO_SIGMA=dense. */
+int covo_get_sigma_path(covo_handle* h, int* path);
+/* Select the path (0 or 3).  The dense path needs a lowest eigenvalue that a Lanczos iteration finds within 64 steps (16 .. 52 on CoVO
+ * Hessians; the kernel runs as many as the residual of the Ritz pair asks for).  If it does not converge, lambda_min is replaced by a
+ * lower bound (Sigma stays positive definite) and the step ends with status 3: covo_optimize_sigma then redoes the matrix on the
+ * tridiagonal path by itself; covo_step switches the handle to the tridiagonal path for the following steps; callers of the
+ * asynchronous entry points see status 3 in covo_get_status() and can switch with this function. */
+int covo_set_sigma_path(covo_handle* h, int path);
 /* Per-kernel device time of the last instrumented step, CUDA events on the launch stream.
- * slots: 0 hessian (local + assemble + forward chains), 1 tridiagonalisation (cluster), 2 tridiagonal matrix function,
- *        3 Sigma = Q F Q^T, 4 cholesky, 5 rollout */
+ * slots: 0 hessian (local + assemble + forward chains), 4 cholesky, 5 rollout, and
+ *   tridiagonal path: 1 tridiagonalisation (cluster), 2 tridiagonal matrix function, 3 Sigma = Q F Q^T
+ *   dense path:       1 Lanczos (cluster),            2 shifted inverses (one cluster per pole), 3 combine */
 int covo_set_profiling(covo_handle* h, int on);
 int covo_get_kernel_ms(covo_handle* h, float* ms6);
 /* Debug: switch in-kernel clock64() phase stamps on/off and read the 64 slots of the last step (may be NULL). */

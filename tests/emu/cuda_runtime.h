@@ -28,6 +28,7 @@ using std::min;
 
 typedef int cudaError_t;
 typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
 constexpr cudaError_t cudaSuccess = 0;
 constexpr cudaError_t cudaErrorInvalidValue = 1;
 constexpr int cudaFuncAttributeMaxDynamicSharedMemorySize = 0;
@@ -49,6 +50,8 @@ inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline long long clock64() { return 0; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+using std::exp2f;
+using std::log2f;
 
 namespace emu {
 

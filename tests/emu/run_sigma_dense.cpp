@@ -18,18 +18,15 @@ extern "C" int emu_sigma_dense(int n, float sample_sigma, const float* R, const 
     a.status = status;
     a.prof = nullptr;
     a.Asym = nullptr;
-    const size_t smem1 = (size_t)(2 * n + 8 + 2 * kLanczosMax) * sizeof(double) + (size_t)n * (n + 1) * sizeof(float);
-    if (variant & 32) emu_launch_cluster(lanczos_cluster_kernel, dim3(LC_CL, 1), LC_CL, LC_T, sizeof(LcSmem), a);  // 8-CTA cluster
-    else if ((variant & 16) || !lanczos2_layout(n).fits) emu_launch(lanczos_kernel, dim3(1), TL, smem1, a);  // the first Lanczos kernel
-    else emu_launch(lanczos2_kernel, dim3(1), TL2, lanczos2_layout(n).bytes, a);
-    variant &= 15;
-    if (variant == 3) {
-        emu_launch_cluster(gjb_inverse_kernel, dim3(GB_CL * (kZoloPoles + 1), 1), GB_CL, GB_T, sizeof(GjbSmem), a);
-    } else if (variant == 2) {
-        emu_launch(gj_inverse_kernel<14>, dim3(kZoloPoles + 1, 1), TG, 1024 * sizeof(float), a);
-    } else {
-        const size_t smem2 = ((size_t)n * n + 2 * 8 * a.n_pad + 64 + a.n_pad) * sizeof(float) + 16;
-        emu_launch(shifted_inverse_kernel, dim3(kZoloPoles + 1, 1), TD, smem2, a);
+    emu_launch_cluster(lanczos_cluster_kernel, dim3(LC_CL, 1), LC_CL, LC_TT, sizeof(LcSmem), a);  // 8-CTA cluster, 4 + 1 warps
+    if (variant & 64) return 0;  // lambda_min only (studies of the Lanczos stage)
+    emu_launch_cluster(gjb_inverse_kernel, dim3(GB_CL * (kZoloPoles + 1), 1), GB_CL, GB_T, sizeof(GjbSmem), a);
+    if (const char* dump = getenv("COVO_EMU_DUMP_X")) {  // development: the per-pole inverses
+        FILE* f = fopen(dump, "wb");
+        if (f) {
+            fwrite(xbuf.data(), sizeof(float), xbuf.size(), f);
+            fclose(f);
+        }
     }
     const int npairs = n * (n + 1) / 2;
     emu_launch(combine_kernel, dim3((npairs + 255) / 256, 1), 256, 0, a);

@@ -1,4 +1,4 @@
-"""csrc/sigma_dense.cu (experimental, COVO_SIGMA=dense) executed on the CPU stand-in for the CUDA execution model
+"""csrc/sigma_dense.cu (the tridiagonalisation-free optimize_sigma, default for single environments) executed on the CPU stand-in for the CUDA execution model
 (tests/emu/cuda_runtime.h: every CUDA thread a cooperative fiber; barriers, named barriers, shuffles and ballots block until
 the peers arrive; shared memory poisoned; a barrier that can never complete aborts) against the float64 eigen-decomposition
 of the oracle.  Checks the kernels' LOGIC -- indexing, hand-overs through shared memory, barrier placement -- with the launch
@@ -15,6 +15,7 @@ from tests.util import scenario
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
+kFirstCheck = 16  # csrc/sigma_dense.cu: kLanczosFirstCheck
 
 
 def _emu_lib():
@@ -27,8 +28,9 @@ def _emu_lib():
     return C.CDLL(so)
 
 
-def test_gauss_jordan_variant_at_the_headline_size():
-    """n = 200 (H = 50): every register tile of gj_inverse_kernel is in use, 13 of its 14 row blocks are pivoted."""
+def test_dense_sigma_at_the_headline_size(variant=3):
+    """n = 200 (H = 50): the production kernels (8-CTA cluster Lanczos with its checker warp, blocked Gauss-Jordan on a 4-CTA cluster
+    per pole) run with all CTAs of a cluster interleaved."""
     emu = _emu_lib()
     p, ns, a_mean, rng = scenario("tracking_zigzag", seed=3, H=50, warm_steps=6)
     R = o.get_hessian(ns, o.shift_mean(a_mean), p, dtype=np.float64).astype(np.float32)
@@ -37,8 +39,10 @@ def test_gauss_jordan_variant_at_the_headline_size():
     scal, status, tab = np.zeros(4), np.zeros(1, np.int32), _zolo_table()
     rc = emu.emu_sigma_dense(200, C.c_float(0.5), R.ctypes.data_as(C.POINTER(C.c_float)), tab.ctypes.data_as(C.POINTER(C.c_double)),
                              cov.ctypes.data_as(C.POINTER(C.c_float)), scal.ctypes.data_as(C.POINTER(C.c_double)),
-                             status.ctypes.data_as(C.POINTER(C.c_int)), 2)
+                             status.ctypes.data_as(C.POINTER(C.c_int)), variant)
     assert rc == 0 and status[0] == 0 and np.isfinite(cov).all()
+    lam = np.linalg.eigvalsh(0.5 * (R + R.T).astype(np.float64))
+    assert abs(scal[0] - lam[0]) < 2e-8 and kFirstCheck <= scal[3] <= 64  # adaptive Lanczos: converged, and says how many steps it took
     assert np.linalg.norm(cov - S_ref) / np.linalg.norm(S_ref) < 5e-6
 
 
@@ -56,9 +60,8 @@ def _zolo_table():
     return tab
 
 
-@pytest.mark.parametrize("variant", [1, 2], ids=["cholesky-inverse", "gauss-jordan"])
-@pytest.mark.parametrize("H", [8, 9])  # n = 32 and n = 36 (last Cholesky panel 4 wide, n_pad = 40)
-def test_dense_sigma_kernels_on_the_cpu_execution_model(H, variant):
+@pytest.mark.parametrize("H", [2, 8, 9])  # n = 8 (Krylov space exhausted before the first checkpoint), 32, and the ragged 36 (n_pad = 40)
+def test_dense_sigma_kernels_on_the_cpu_execution_model(H, variant=3):
     emu = _emu_lib()
     p, ns, a_mean, rng = scenario("tracking_zigzag", seed=3, H=H, warm_steps=6)
     R = o.get_hessian(ns, o.shift_mean(a_mean), p, dtype=np.float64).astype(np.float32)
@@ -77,3 +80,20 @@ def test_dense_sigma_kernels_on_the_cpu_execution_model(H, variant):
     assert abs(scal[2] - np.log(lam - lam[0] + 1e-2).sum()) < 1e-4          # log det from the fp32 factorisation
     assert np.isfinite(cov).all() and np.array_equal(cov, cov.T)
     assert np.linalg.norm(cov - S_ref) / np.linalg.norm(S_ref) < 2e-6
+
+
+def test_adaptive_lanczos_on_a_hessian_that_defeats_24_steps():
+    """The last matrix of tests/golden/hessians/hard_hessians_n200.npz (gap 6e-2, width 1640): after 24 steps the smallest Ritz value is
+    still 6e-2 above lambda_min (A would be indefinite); the checker warp keeps the recurrence going until the residual says so."""
+    emu = _emu_lib()
+    R = np.ascontiguousarray(np.load(os.path.join(ROOT, "tests", "golden", "hessians", "hard_hessians_n200.npz"))["R"][-1])
+    lam = np.linalg.eigvalsh(0.5 * (R + R.T).astype(np.float64))
+    S_ref = o.optimize_sigma(R.astype(np.float64), 0.5, np.float64)
+    cov = np.full((200, 200), np.nan, np.float32)
+    scal, status, tab = np.zeros(4), np.zeros(1, np.int32), _zolo_table()
+    rc = emu.emu_sigma_dense(200, C.c_float(0.5), R.ctypes.data_as(C.POINTER(C.c_float)), tab.ctypes.data_as(C.POINTER(C.c_double)),
+                             cov.ctypes.data_as(C.POINTER(C.c_float)), scal.ctypes.data_as(C.POINTER(C.c_double)),
+                             status.ctypes.data_as(C.POINTER(C.c_int)), 3)
+    assert rc == 0 and status[0] == 0
+    assert scal[3] > 24 and abs(scal[0] - lam[0]) < 2e-8
+    assert np.linalg.norm(cov - S_ref) / np.linalg.norm(S_ref) < 6e-3  # float32 inverses at cond(A) = 1.6e5: the fast path's documented accuracy

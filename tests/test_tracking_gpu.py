@@ -258,3 +258,44 @@ def test_covo_online_full_episode_teacher_forced():
     prefix = STEPS if first_div is None else first_div
     assert prefix >= 3 and abs(cost_dev - cost_ora) <= 1e-4 * abs(cost_ora)
     h.close()
+
+
+def test_dense_fast_path_closed_loop_accuracy():
+    """The opt-in fast optimize_sigma path (covo_set_sigma_path(h, 3)) along the first 60 steps of the same closed loop: every step
+    converges (no status: the adaptive Lanczos stage takes 16 .. 52 steps on these Hessians, where a fixed 24 left A indefinite at
+    step 57), Sigma stays within the path's documented distance of the float64 truth, and the actions within what that implies."""
+    from covo_mpc_b200 import _lib
+
+    p = o.EnvParams()
+    steps = 60
+    s_dev = o.reset_env(tp.TASK, p, np.random.default_rng(tp.episode_seeds(0)[0]), dtype=np.float32, zero_disturb=False)
+    h = _handle(_lib.MODE_COVO_ONLINE, (s_dev.pos_traj, s_dev.vel_traj))
+    h.set_sigma_path(3)
+    noise, eps_rng = tp.episode_noise(0, steps), tp.episode_eps_rng(0)
+    mean_dev = o.hover_mean(H, p)
+    h.set_mean(mean_dev[None])
+    sig, act = [], []
+    for i in range(steps):
+        eps = eps_rng.standard_normal((N, 4 * H)).astype(np.float32)
+        ns = o.noisy_state(s_dev, p, tp.SeqRng(noise[i, :13]))
+        a_dev = h.step(o.state_to_vec24(ns), [ns.time], eps[None])[0].copy()
+        assert h.sigma_path() == 3 and int(h.status()[0]) == 0, f"step {i}: the dense path did not converge"
+        cov_dev = h.get_cov()[0].astype(np.float64)
+        a_64, _, gap = _oracle_step("covo-online-f64", ns, mean_dev, eps, p)
+        cov_64 = _oracle_step.last_cov
+        mean_dev = h.get_mean()[0].reshape(H, 4).copy()
+        sig.append(np.linalg.norm(cov_dev - cov_64) / np.linalg.norm(cov_64))
+        assert np.linalg.eigvalsh(cov_dev)[0] > 0
+        if gap >= TIE:
+            act.append(float(np.abs(a_dev - a_64).max()))
+        s_dev, _, _, _ = o.env_step(s_dev, a_dev, p, tp.SeqRng(noise[i + 1, 13:16]), "none")
+    msg = (f"[covo-online FAST sigma path, {steps} steps teacher-forced vs float64 truth] Sigma rel. Frobenius error median {np.median(sig):.2e} "
+           f"max {np.max(sig):.2e}; action error over {len(act)} steps median {np.median(act):.2e} max {np.max(act):.2e}")
+    print(msg)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "tracking_parity.log"), "a") as f:
+            f.write(msg + "\n")
+    assert np.median(sig) < 1e-3 and np.max(sig) < 1e-2
+    assert np.median(act) < 2e-4 and np.max(act) < 2e-2
+    h.close()

@@ -24,7 +24,7 @@ from tools import tracking_protocol as tp  # noqa: E402
 
 
 def fixture_path(controller, N, H):
-    return os.path.join(ROOT, "tests", "golden", f"oracle_tracking_{controller}_N{N}_H{H}.npz")
+    return os.path.join(ROOT, "tests", "golden", "tracking", f"oracle_tracking_{controller}_N{N}_H{H}.npz")
 
 
 def initial_states(n_ep):

@@ -1,6 +1,6 @@
 """Oracle arm of the powered closed-loop tracking comparison: 40 episodes x 300 steps of the reference algorithm (oracle/ port,
 C/OpenMP heavy loops) at the headline size, protocol in tools/tracking_protocol.py.  CPU only (~20 min on 8 cores for covo-online);
-writes tests/golden/oracle_tracking_{controller}_N{N}_H{H}.npz with per-episode, per-step err_pos and actions.
+writes tests/golden/tracking/oracle_tracking_{controller}_N{N}_H{H}.npz with per-episode, per-step err_pos and actions.
 
     python tools/oracle_tracking_stats.py [--controller covo-online|mppi] [--episodes 40] [--N 8192] [--H 50]
 
@@ -64,7 +64,7 @@ def main():
     ap.add_argument("--lam", type=float, default=0.01)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    out = a.out or os.path.join(ROOT, "tests", "golden", f"oracle_tracking_{a.controller}_N{a.N}_H{a.H}.npz")
+    out = a.out or os.path.join(ROOT, "tests", "golden", "tracking", f"oracle_tracking_{a.controller}_N{a.N}_H{a.H}.npz")
     errs = np.zeros((a.episodes, a.steps), np.float32)
     acts = np.zeros((a.episodes, a.steps, 4), np.float32)
     t0 = time.time()
