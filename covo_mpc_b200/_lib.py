@@ -58,6 +58,7 @@ _SIGNATURES = {
     "covo_set_cov_offline": [_H, _F, C.c_int],
     "covo_get_cov_offline": [_H, _F, C.c_int],
     "covo_reset_offline": [_H, _F, _I, C.c_int],
+    "covo_reset_offline_disturbed": [_H, _F, _I, C.c_int, _F],
     "covo_step": [_H, _F, _I, _F, _F],
     "covo_set_env_params": [_H, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _F, C.c_int],
     "covo_step_device": [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
@@ -231,9 +232,16 @@ class Handle:
         check(self.lib.covo_pid_action(self._h, fptr(s), iptr(t), Kp, Kd, Ki, Kp_att, fptr(g), fptr(out)))
         return out
 
-    def reset_offline(self, state24, time, t_sched: int):
+    def reset_offline(self, state24, time, t_sched: int, f_disturb=None):
+        """f_disturb [t_sched][3]: the gaussian disturbance force after every path step (covo_reset_offline_disturbed); None: none."""
         s, t = f32(state24), i32(time)
-        check(self.lib.covo_reset_offline(self._h, fptr(s), iptr(t), t_sched))
+        if f_disturb is None:
+            check(self.lib.covo_reset_offline(self._h, fptr(s), iptr(t), t_sched))
+            return
+        d = f32(f_disturb)
+        if d.shape != (t_sched, 3):
+            raise ValueError("f_disturb must be [t_sched][3]")
+        check(self.lib.covo_reset_offline_disturbed(self._h, fptr(s), iptr(t), t_sched, fptr(d)))
 
     # -- the MPC step -----------------------------------------------------------------------------
     def set_jax_key(self, act_key):

@@ -268,6 +268,20 @@ class MPPIController(_SamplingController):
         return self._finish(control_params, action)
 
 
+def offline_disturbance_normals(key, T: int) -> np.ndarray:
+    """The [T][3] standard normals reset_a_cov_offline (controllers/covo.py:77-99) draws for the disturbance of its T state advances,
+    from the reference's key schedule: per schedule step `rng_step, key = split(key)` (expansion controller, unused by the PID policy),
+    `rng_step, key = split(key)` (step_env); inside step_env the disturbance key is split(split(split(rng_step)[1])[0])[0]
+    (envs/quadrotor.py:262, dynamics/free.py:136-144) -- the chain env.Quad3D.step_env follows for the same key."""
+    k = np.asarray(key, dtype=np.uint32)
+    z = np.empty((T, 3), np.float32)
+    for t in range(T):
+        k = jaxrng.split(k)[1]
+        rs, k = jaxrng.split(k)
+        z[t] = jaxrng.normal(jaxrng.split(jaxrng.split(jaxrng.split(rs)[1])[0])[0], (3,))
+    return z
+
+
 class CoVOController(_SamplingController):
     """quadjax/controllers/covo.py:25-283"""
 
@@ -290,12 +304,26 @@ class CoVOController(_SamplingController):
         if self._mode != _lib.MODE_COVO_OFFLINE:
             return self.init_control_params
         # reset_a_cov_offline, covo.py:101-104: rebuild the covariance schedule from this state (on device)
-        if getattr(self.env, "disturb_type", "none") != "none":
-            raise NotImplementedError("covo-offline schedule: only disturb_type='none' is implemented")
+        disturb_type = getattr(self.env, "disturb_type", "none")
+        if disturb_type not in ("none", "gaussian"):
+            raise NotImplementedError(f"covo-offline schedule under disturb_type {disturb_type!r}")
         h = self._sync_reference(env_state)
         self._sync_env_params(env_params)
         T = int(self.env.default_params.max_steps_in_episode)
-        h.reset_offline(env_state.to_state24(), [env_state.time], T)
+        f_disturb = None
+        if disturb_type == "gaussian":
+            # The state advance between schedule entries is stochastic (covo.py:80-89).  Key schedule of get_single_a_cov_offline:
+            # `rng_step, key = split(key)` for the expansion controller, `rng_step, key = split(key)` for step_env (:81-88); inside
+            # step_env the disturbance key is split(split(split(rng_step)[1])[0])[0] (quadrotor.py:262, dynamics/free.py:136-144).
+            scale = float((env_params or self.env.default_params).dyn_noise_scale)
+            z = np.empty((T, 3), np.float32)
+            if jaxrng.is_key(key):
+                z[:] = offline_disturbance_normals(key, T)
+            else:
+                gen = key if isinstance(key, np.random.Generator) else np.random.default_rng(int(self._cfg.seed))
+                z[:] = gen.standard_normal((T, 3))
+            f_disturb = scale * z
+        h.reset_offline(env_state.to_state24(), [env_state.time], T, f_disturb)
         self._table = None
         # The reference keeps a_mean / a_cov across this reset (covo.py:101-104 replaces a_cov_offline only) and render_env calls it
         # with the CURRENT params after `done` (envs/quadrotor.py:637-639): the resident mean is untouched by the schedule build, so

@@ -125,7 +125,7 @@ struct covo_handle {
     DevBuf<double> diag, zolo;
     DevBuf<int> status;
     // offline schedule (batched over schedule steps)
-    DevBuf<float> cov_table, Lt_table, sched_states, sched_anom, sched_R, sched_Vh, sched_tau, sched_Qt, sched_F, sched_ws;
+    DevBuf<float> cov_table, Lt_table, sched_states, sched_anom, sched_R, sched_Vh, sched_tau, sched_Qt, sched_F, sched_ws, sched_disturb;
     DevBuf<double> sched_diag;
     DevBuf<int> sched_times, sched_status;
     // rollout
@@ -182,7 +182,7 @@ void release_all(covo_handle* h) {
     h->R.release(); h->Vh.release(); h->tau.release(); h->Qt.release(); h->F.release(); h->cov.release();
     h->Lfull.release(); h->Lt.release(); h->Lblk.release(); h->hess_ws.release(); h->diag.release();
     h->zolo.release(); h->status.release();
-    h->cov_table.release(); h->Lt_table.release(); h->sched_states.release(); h->sched_anom.release();
+    h->cov_table.release(); h->Lt_table.release(); h->sched_states.release(); h->sched_anom.release(); h->sched_disturb.release();
     h->sched_R.release(); h->sched_Vh.release(); h->sched_tau.release(); h->sched_Qt.release(); h->sched_F.release();
     h->sched_ws.release(); h->sched_diag.release(); h->sched_times.release(); h->sched_status.release();
     h->partials.release(); h->rank_partial.release(); h->action.release(); h->costs.release();
@@ -948,11 +948,22 @@ int covo_pid_action(covo_handle* h, const float* state24, const int* time, float
 }
 
 int covo_reset_offline(covo_handle* h, const float* state24, const int* time, int t_sched) {
+    return covo_reset_offline_disturbed(h, state24, time, t_sched, nullptr);
+}
+
+int covo_reset_offline_disturbed(covo_handle* h, const float* state24, const int* time, int t_sched, const float* f_disturb) {
     if (!h || !state24 || !time) return fail(COVO_ERR_INVALID, "null argument");
     CK(cudaSetDevice(h->cfg.device));
     int rc = alloc_schedule(h, t_sched, true);
     if (rc) return rc;
     cudaStream_t st = h->own_stream;
+    if (f_disturb) {
+        if (h->sched_disturb.n < (size_t)t_sched * 3) {
+            h->sched_disturb.release();
+            CK(h->sched_disturb.alloc((size_t)t_sched * 3));
+        }
+        CK(cudaMemcpyAsync(h->sched_disturb.p, f_disturb, (size_t)t_sched * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
     CK(cudaMemcpyAsync(h->state24.p, state24, kStateFloats * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->time.p, time, sizeof(int), cudaMemcpyHostToDevice, st));
     OfflineArgs oa;
@@ -969,6 +980,7 @@ int covo_reset_offline(covo_handle* h, const float* state24, const int* time, in
     oa.pos_traj = h->pos_traj.p;
     oa.vel_traj = h->vel_traj.p;
     oa.acc_traj = h->acc_traj.p;
+    oa.f_disturb = f_disturb ? h->sched_disturb.p : nullptr;
     oa.states24 = h->sched_states.p;
     oa.times = h->sched_times.p;
     oa.a_nom = h->sched_anom.p;

@@ -6,7 +6,8 @@
 // deterministic PID rollout that becomes the nominal control sequence (:58-76).  The Hessian / sigma /
 // Cholesky of all schedule steps then run as ONE batched launch each (capi.cu: covo_reset_offline),
 // schedule step t playing the role of "environment t".
-// disturb_type == "none" only (the state advance is then deterministic).
+// disturb_type "none" (deterministic state advance) or "gaussian" (the caller supplies the force the state carries after each
+// path step; the H-step nominal rollouts are deterministic=True in the reference, controllers/covo.py:67-69, i.e. force 0).
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -45,7 +46,9 @@ __global__ void pid_path_kernel(const OfflineArgs a) {
         float act[4];
         pid_action(s, pt, vt, at, a.env, a.max_thrust, a.Kp, a.Kd, a.Kp_att, act);
         quad_step(s, act, fd, a.env);
-        fd[0] = fd[1] = fd[2] = 0.f;  // disturb_type none
+        // the stochastic state advance of get_single_a_cov_offline (controllers/covo.py:86-89): disturb_type none -> 0,
+        // gaussian -> dyn_noise_scale * N(0, I) drawn by the caller for every path step (dynamics/free.py:66-70)
+        for (int k = 0; k < 3; ++k) fd[k] = a.f_disturb ? a.f_disturb[(long long)t * 3 + k] : 0.f;
         ++time;
         int row = min(time, a.traj_len - 1);
         gather3(a.pos_traj, row, pt);
@@ -68,7 +71,7 @@ __global__ void pid_nominal_kernel(const OfflineArgs a) {
         pid_action(s, pt, vt, at, a.env, a.max_thrust, a.Kp, a.Kd, a.Kp_att, act);
         for (int k = 0; k < 4; ++k) a.a_nom[((long long)t * a.H + h) * 4 + k] = act[k];
         quad_step(s, act, fd, a.env);
-        fd[0] = fd[1] = fd[2] = 0.f;
+        fd[0] = fd[1] = fd[2] = 0.f;  // deterministic=True (controllers/covo.py:67-69)
         ++time;
         int row = min(time, a.traj_len - 1);
         gather3(a.pos_traj, row, pt);

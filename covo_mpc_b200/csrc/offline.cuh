@@ -13,6 +13,7 @@ struct OfflineArgs {
     const float* pos_traj;  // [T][3]
     const float* vel_traj;  // [T][3]
     const float* acc_traj;  // [T][3] or nullptr
+    const float* f_disturb = nullptr;  // [t_sched][3] or nullptr: the disturbance force the state carries AFTER path step t (gaussian)
     float* states24;        // [t_sched][24]
     int* times;             // [t_sched]
     float* a_nom;           // [t_sched][H][4]

@@ -8,7 +8,7 @@
  *                                      constants chosen by get_controller, envs/quadrotor.py:670-752
  *   covo_step / covo_step_device   <-> CoVOController.__call__  controllers/covo.py:187-283
  *                                      MPPIController.__call__  controllers/mppi.py:28-134
- *   covo_reset_offline             <-> reset_a_cov_offline      controllers/covo.py:58-104
+ *   covo_reset_offline[_disturbed] <-> reset_a_cov_offline      controllers/covo.py:58-104
  *   covo_hessian                   <-> CoVOController.get_hessian      controllers/covo.py:134-185
  *   covo_optimize_sigma            <-> CoVOController.optimize_sigma   controllers/covo.py:116-132
  *   covo_cholesky                  <-> the factorisation inside jax.random.multivariate_normal
@@ -106,6 +106,12 @@ int covo_get_cov_offline(covo_handle* h, float* table, int t_sched);
 /* Build the table on device: PID expansion policy closed loop + nominal rollouts + Hessian + sigma,
  * as controllers/covo.py:58-104 with disturb_type == "none".  state24/time: the reset state. */
 int covo_reset_offline(covo_handle* h, const float* state24, const int* time, int t_sched);
+/* The same under disturb_type == "gaussian" (the reference's default, envs/quadrotor.py:765): the state advance between schedule
+ * entries (controllers/covo.py:86-89) is stochastic.  f_disturb [t_sched][3] (host): the force dyn_noise_scale * N(0, I)
+ * (dynamics/free.py:66-70) the state carries after path step t -- drawn by the caller, with the reference's key schedule when it
+ * holds a JAX key (covo_mpc_b200/controllers.py does).  The H-step nominal rollouts stay deterministic (covo.py:67-69).
+ * f_disturb == NULL: covo_reset_offline. */
+int covo_reset_offline_disturbed(covo_handle* h, const float* state24, const int* time, int t_sched, const float* f_disturb);
 
 /* One MPC step for all E environments.  Host buffers; H2D of (state24, time[, eps]) and D2H of the
  * action happen inside the call, which returns after the stream is idle.  eps may be NULL. */

@@ -92,3 +92,24 @@ def test_render_env_matches_the_reference_source(tmp_path):
     # every field of the reference's dict that scripts/vis.py (:70-95) reads is there under the same name
     assert {"pos", "quat", "pos_tar", "f_disturb", "pos_traj", "vel", "omega", "time"} <= set(stored[0].keys())
     assert {"pos", "quat", "pos_tar", "f_disturb", "pos_traj", "vel", "omega", "time"} <= set(g["keys"].tolist())
+
+
+def test_offline_schedule_disturbance_follows_the_reference_key_schedule():
+    """reset_a_cov_offline under disturb_type gaussian (controllers/covo.py:77-99): per schedule step two splits of the carried key,
+    the second one's first half goes to step_env.  The controller hands the device the normals that chain produces; here the same chain
+    is walked with the key-driven host environment (pinned to the reference's own step_env above)."""
+    from covo_mpc_b200.controllers import offline_disturbance_normals
+
+    env = cm.Quad3D("tracking_zigzag", disturb_type="gaussian")
+    key = jr.PRNGKey(5)
+    _, _, st = env.reset(jr.PRNGKey(1))
+    T = 6
+    z = offline_disturbance_normals(key, T)
+    k = key
+    act = np.array([0.1, 0.0, 0.0, 0.0], np.float32)
+    for t in range(T):
+        _, k = jr.split(k)       # rng_step for the expansion controller (covo.py:81)
+        rs, k = jr.split(k)      # rng_step for step_env (covo.py:87)
+        _, st, _, _, _ = env.step_env(rs, st, act, env.default_params)
+        assert np.abs(st.f_disturb - np.float32(env.default_params.dyn_noise_scale) * z[t]).max() < 1e-7
+    assert np.abs(z).max() > 0.1 and np.abs(z.mean()) < 1.0

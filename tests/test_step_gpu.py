@@ -99,22 +99,26 @@ def test_episode_tracking_quality():
     assert np.isfinite(errs2).all() and errs2.mean() < 0.3
 
 
-def test_offline_schedule_matches_oracle():
-    """covo-offline reset (controllers/covo.py:58-104) on device vs the oracle, then a lookup step."""
+@pytest.mark.parametrize("disturb", ["none", "gaussian"])
+def test_offline_schedule_matches_oracle(disturb):
+    """covo-offline reset (controllers/covo.py:58-104) on device vs the oracle, then a lookup step.  gaussian (the reference's default
+    disturb_type): the state advance between schedule entries carries dyn_noise_scale * N(0, I); both sides get the same normals."""
     import covo_mpc_b200 as cm
+    from tools.tracking_protocol import SeqRng
 
     N, H, T = 256, 8, 6
     p = o.EnvParams()
     rng = np.random.default_rng(3)
     s = o.reset_env("tracking", p, rng, dtype=np.float32, zero_disturb=False)
-    env = cm.Quad3D("tracking")
+    z = np.random.default_rng(17).standard_normal((T, 3)).astype(np.float32)
+    env = cm.Quad3D("tracking", disturb_type=disturb)
     ctl, cp = cm.get_controller(env, "covo-offline", f"N{N}_H{H}_lam0.01")
     st = _to_env_state(cm, s)
     pos, vel, acc = o.generate_lissa_traj(300, 0.02, np.random.default_rng(3))  # same generator draw as reset_env
     st.acc_traj = acc.astype(np.float32)
     st.acc_tar = acc[0].astype(np.float32)
     h = ctl._sync_reference(st)
-    h.reset_offline(st.to_state24(), [0], T)
+    h.reset_offline(st.to_state24(), [0], T, None if disturb == "none" else np.float32(p.dyn_noise_scale) * z)
     tab = h.get_cov_offline(T)
     # oracle (needs acc_tar for the PID): restate with the oracle's PID + env
     so = s.copy()
@@ -129,7 +133,7 @@ def test_offline_schedule_matches_oracle():
         R = o.get_hessian(so, np.asarray(nom), p)
         tab_o.append(o.optimize_sigma(R, 0.5, np.float64))
         a = o.pid_action(so, p, acc_tar=acc[min(so.time, 349)])
-        so, _, _, _ = o.env_step(so, a, p, rng, "none")
+        so, _, _, _ = o.env_step(so, a, p, SeqRng(z[t]), disturb)
     tab_o = np.stack(tab_o)
     for t in range(T):
         assert np.linalg.norm(tab[t] - tab_o[t]) / np.linalg.norm(tab_o[t]) < 1e-4, t
