@@ -16,7 +16,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 GROUP = {"hess_local": "hessian", "hess_assemble": "hessian", "hess_forward": "hessian", "tridiag_reg": "tridiag", "qacc": "qacc", "sigma_trifunc": "trifunc",
-         "sandwich": "sandwich", "cholesky": "cholesky", "rollout": "rollout"}
+         "sandwich": "sandwich", "cholesky": "cholesky", "rollout": "rollout",
+         "lanczos_cluster": "lanczos", "gjb_inverse": "pole_inverses", "combine": "combine"}
 
 
 def to_bytes(v, unit):
@@ -26,6 +27,7 @@ def to_bytes(v, unit):
 
 def main():
     rep, tag = sys.argv[1], sys.argv[2]
+    merge = len(sys.argv) > 3 and sys.argv[3] == "--merge-traffic"  # add this capture's kernels to profiles/ncu_traffic.json (fast-path capture)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -36,7 +38,11 @@ def main():
             if len(r) == len(hdr):
                 w.writerow([r[i] for i in keep])
     ci = {h: i for i, h in enumerate(hdr)}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     traffic = {}
+    if merge and os.path.exists(tpath):
+        traffic = {k: v for k, v in json.load(open(tpath)).items() if k not in ("lanczos", "pole_inverses", "combine")}
+    seen = set()
     lines = ["| kernel | " + " | ".join(k.split(".")[0].replace("smsp__average_warps_issue_stalled_", "stall_").replace("_per_issue_active", "") for k in KEYS) + " |",
              "|" + "---|" * (len(KEYS) + 1)]
     for r in rows[2:]:
@@ -53,12 +59,16 @@ def main():
         for pat, g in GROUP.items():
             if pat in name:
                 b = to_bytes(r[ci["dram__bytes_read.sum"]], units[ci["dram__bytes_read.sum"]]) + to_bytes(r[ci["dram__bytes_write.sum"]], units[ci["dram__bytes_write.sum"]])
-                traffic[g] = traffic.get(g, 0) + int(b)
-    traffic["_source"] = (f"profiles/{tag}_ncu_full_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch (hessian = local + assemble + "
-                          "forward); ncu --set full --clock-control none, one CoVO-online step at N=8192, H=50")
-    json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"))
+                if merge and g not in ("lanczos", "pole_inverses", "combine"):
+                    continue
+                traffic[g] = (traffic.get(g, 0) if g in seen else 0) + int(b)
+                seen.add(g)
+    if not merge:
+        traffic["_source"] = (f"profiles/{tag}_ncu_full_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch (hessian = local + assemble + "
+                              "forward); ncu --set full --clock-control none, one CoVO-online step at N=8192, H=50")
+    json.dump(traffic, open(tpath, "w"))
     head = (f"# ncu --set full, one MPC step (CoVO-online, N=8192, H=50), {tag}\n\nCaptured with `ncu --set full --clock-control none "
-            "--import-source on` around `bench.py --steps 2 --warmup 1` (third step). Units as printed by ncu.\n\n")
+            "--import-source on` around `tools/one_step.py` (fourth step, direct launches: COVO_GRAPH=0). Units as printed by ncu.\n\n")
     open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.md"), "w").write(head + "\n".join(lines) + "\n")
     print("\n".join(lines))
     print(traffic)
