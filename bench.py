@@ -205,6 +205,7 @@ def bench_nsample_shard(dist, world, rank, dev, states, times, traj, K, W, flush
     a1 = actions[W:W + K].clone()
     out = {"n_samples": n_samples, "world1_device_ms_per_step": d1, "world1_wall_ms_per_step_incl_flush": w1}
     if world > 1:
+        # (a) the exchange as a collective call between two kernels: kernel -> ncclAllGather -> kernel
         hs = make(rank, world)
         pbuf, pn = hs.partial_buffer()
 
@@ -220,14 +221,40 @@ def bench_nsample_shard(dist, world, rank, dev, states, times, traj, K, W, flush
             hs.step_merge_device(gathered.data_ptr(), actions.data_ptr() + 16 * i, stream)
 
         dw, ww = timed(sharded)
-        out.update({"device_ms_per_step": dw, "wall_ms_per_step_incl_flush": ww, "steps_per_sec": 1e3 / dw,
-                    "strong_scaling_efficiency": d1 / (world * dw), "speedup_vs_world1": d1 / dw,
-                    "exchange": "ncclAllGather of %d B per rank per step + merge kernel" % (4 * pn),
-                    "exchange_bytes_per_step_per_rank": 4 * pn * (world - 1),
-                    "max_action_diff_vs_world1": float((actions[W:W + K] - a1).abs().max()),
-                    "limiter": "the rollout grid is ceil(N/64) CTAs: at N=8192 it is ONE wave (128 CTAs on 148 SMs) on one GPU already, so sharding "
-                               "cannot shorten the per-CTA chain (GEMM || 50-step rollout ~25 us) and only adds the exchange; it pays when N/64 >> 148"})
+        a_nccl = actions[W:W + K].clone()
         hs.close()
+        # (b) the fused exchange: the rollout kernel's finalising CTA stores the record into every rank's buffer (peer memory mapped
+        # through CUDA IPC) and raises a flag; the merge kernel behind it waits for the flags.  No collective, no host involvement.
+        hf = make(rank, world)
+        handle, _ = hf.exchange_info()
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        for r in range(world):
+            if r != rank:
+                hf.exchange_attach(r, ipc_handle=handles[r])
+        dist.barrier()
+
+        def fused(i):
+            hf.step_sharded_device(states.data_ptr() + 96 * i, times.data_ptr() + 4 * i, 0, actions.data_ptr() + 16 * i, stream)
+
+        df, wf = timed(fused)
+        a_fused = actions[W:W + K].clone()
+        ok = bool((hf.status() == 0).all())
+        dist.barrier()
+        hf.close()
+        out.update({"device_ms_per_step": df, "wall_ms_per_step_incl_flush": wf, "steps_per_sec": 1e3 / df,
+                    "strong_scaling_efficiency": d1 / (world * df), "speedup_vs_world1": d1 / df,
+                    "exchange": "fused: %d B record stored into each of the %d ranks' buffers over NVLink (CUDA IPC peer memory) by the rollout "
+                                "kernel + one flag per rank; merge kernel waits on the flags (covo_step_sharded_device)" % (4 * pn, world),
+                    "nvlink_bytes_per_step_per_rank": (4 * pn + 4) * (world - 1),
+                    "launches_per_step": 2, "exchange_status_ok": ok,
+                    "max_action_diff_vs_world1": float((a_fused - a1).abs().max()),
+                    "fused_equals_allgather_bitwise": bool(torch.equal(a_fused, a_nccl)),
+                    "nccl_allgather_variant": {"device_ms_per_step": dw, "wall_ms_per_step_incl_flush": ww,
+                                               "exchange": "kernel -> ncclAllGather of %d B per rank -> merge kernel (3 launches + a D2D copy)" % (4 * pn)},
+                    "limiter": "the rollout grid is ceil(N/world/64) CTAs: at N=8192 it is ONE wave (128 CTAs on 148 SMs) on one GPU already, so "
+                               "sharding cannot shorten the per-CTA chain (GEMM || 50-step rollout ~25 us) and only adds the exchange; it pays "
+                               "when N/64 >> 148 (N=65536: 1024 CTAs = 7 waves on one GPU)"})
     h1.close()
     return out
 

@@ -65,6 +65,9 @@ _SIGNATURES = {
     "covo_step_partial_device": [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "covo_partial_buffer": [_H, C.POINTER(C.c_void_p), _I],
     "covo_step_merge_device": [_H, C.c_void_p, C.c_void_p, C.c_void_p],
+    "covo_exchange_info": [_H, C.c_void_p, C.POINTER(C.c_void_p)],
+    "covo_exchange_attach": [_H, C.c_int, C.c_void_p, C.c_void_p],
+    "covo_step_sharded_device": [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "covo_hessian": [_H, _F, _I, _F, C.c_int, _F],
     "covo_optimize_sigma": [_H, _F, _F],
     "covo_cholesky": [_H, _F, _F],
@@ -310,6 +313,22 @@ class Handle:
 
     def step_merge_device(self, gathered_ptr: int, action_ptr: int, stream: int = 0):
         check(self.lib.covo_step_merge_device(self._h, gathered_ptr, action_ptr, stream or None))
+
+    # -- fused exchange of the N-sharded step (no collective call: records go peer to peer from inside the rollout kernel) ------
+    def exchange_info(self):
+        """(64-byte CUDA IPC handle, raw device pointer) of this rank's exchange buffer."""
+        hd = C.create_string_buffer(64)
+        p = C.c_void_p()
+        check(self.lib.covo_exchange_info(self._h, hd, C.byref(p)))
+        return hd.raw, p.value
+
+    def exchange_attach(self, peer_rank: int, ipc_handle: Optional[bytes] = None, dev_ptr: Optional[int] = None):
+        """Make rank `peer_rank`'s exchange buffer known: by IPC handle (another process) or by pointer (a handle of this process)."""
+        buf = C.create_string_buffer(ipc_handle, 64) if ipc_handle is not None else None
+        check(self.lib.covo_exchange_attach(self._h, int(peer_rank), buf, dev_ptr))
+
+    def step_sharded_device(self, state_ptr: int, time_ptr: int, eps_ptr: int, action_ptr: int, stream: int = 0):
+        check(self.lib.covo_step_sharded_device(self._h, state_ptr, time_ptr, eps_ptr or None, action_ptr, stream or None))
 
     # -- operators -------------------------------------------------------------------------------
     def hessian(self, state24, time, a_mean, shift: bool = False) -> np.ndarray:

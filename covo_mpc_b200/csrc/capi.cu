@@ -130,6 +130,12 @@ struct covo_handle {
     DevBuf<int> sched_times, sched_status;
     // rollout
     DevBuf<float> partials, rank_partial, action, costs, samples, pos_stats, gathered_scratch;
+    // fused exchange of the N-sharded step (world > 1): [2][world][E][rec] floats followed by [2][world][E] flags, one allocation
+    // (one CUDA IPC handle); xpeer[w] = rank w's buffer as this process sees it (IPC mapping, or a pointer of the same process)
+    DevBuf<float> xchg;
+    float* xpeer[kMaxPeers] = {};
+    bool xpeer_ipc[kMaxPeers] = {};
+    unsigned int xchg_step = 0;  // steps taken through covo_step_sharded_device
     DevBuf<unsigned int> counters;
     DevBuf<long long> prof;
     bool phase_clocks = false;
@@ -185,6 +191,9 @@ void release_all(covo_handle* h) {
     h->cov_table.release(); h->Lt_table.release(); h->sched_states.release(); h->sched_anom.release(); h->sched_disturb.release();
     h->sched_R.release(); h->sched_Vh.release(); h->sched_tau.release(); h->sched_Qt.release(); h->sched_F.release();
     h->sched_ws.release(); h->sched_diag.release(); h->sched_times.release(); h->sched_status.release();
+    for (int w = 0; w < kMaxPeers; ++w)
+        if (h->xpeer[w] && h->xpeer_ipc[w]) cudaIpcCloseMemHandle(h->xpeer[w]);
+    h->xchg.release();
     h->partials.release(); h->rank_partial.release(); h->action.release(); h->costs.release();
     h->env_state24.release(); h->env_noisy24.release(); h->env_noise.release(); h->env_log_f.release(); h->env_action.release();
     h->env_time.release(); h->env_noisy_time.release(); h->env_done.release();
@@ -689,6 +698,10 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
     A(h->a_mean.alloc(E * n));
     A(h->partials.alloc(E * h->n_cta * h->rec));
     A(h->rank_partial.alloc(E * h->rec));
+    if (cfg->world > 1 && cfg->world <= kMaxPeers) {
+        A(h->xchg.alloc((size_t)2 * cfg->world * E * (h->rec + 1)));
+        h->xpeer[cfg->rank] = h->xchg.p;
+    }
     A(h->counters.alloc(E));
     A(h->action.alloc(E * 4));
     A(h->pos_stats.alloc(E * h->H * 6));
@@ -1321,6 +1334,93 @@ int covo_step_merge_device(covo_handle* h, const float* gathered_dev, float* act
     m.a_mean_out = h->a_mean.p;
     m.action_out = action_dev;
     CK(launch_merge(m, (cudaStream_t)stream));
+    return COVO_OK;
+}
+
+// ---- fused exchange of the N-sharded step -----------------------------------------------------------------------------------
+int covo_exchange_info(covo_handle* h, void* ipc_handle64, void** dev_ptr) {
+    if (!h) return fail(COVO_ERR_INVALID, "null argument");
+    if (!h->xchg.p) return fail(COVO_ERR_INVALID, "no exchange buffer: the handle was created with world == 1 (or world > %d)", kMaxPeers);
+    CK(cudaSetDevice(h->cfg.device));
+    if (ipc_handle64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        cudaIpcMemHandle_t hd;
+        CK(cudaIpcGetMemHandle(&hd, h->xchg.p));
+        memcpy(ipc_handle64, &hd, 64);
+    }
+    if (dev_ptr) *dev_ptr = h->xchg.p;
+    return COVO_OK;
+}
+
+int covo_exchange_attach(covo_handle* h, int peer_rank, const void* ipc_handle64, void* dev_ptr) {
+    if (!h) return fail(COVO_ERR_INVALID, "null argument");
+    if (!h->xchg.p) return fail(COVO_ERR_INVALID, "no exchange buffer: the handle was created with world == 1");
+    if (peer_rank < 0 || peer_rank >= h->cfg.world || peer_rank == h->cfg.rank) return fail(COVO_ERR_INVALID, "peer_rank %d out of range", peer_rank);
+    if ((ipc_handle64 != nullptr) == (dev_ptr != nullptr)) return fail(COVO_ERR_INVALID, "pass either an IPC handle or a device pointer");
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->xpeer[peer_rank] && h->xpeer_ipc[peer_rank]) CK(cudaIpcCloseMemHandle(h->xpeer[peer_rank]));
+    if (ipc_handle64) {
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, ipc_handle64, 64);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        h->xpeer[peer_rank] = (float*)p;
+        h->xpeer_ipc[peer_rank] = true;
+    } else {
+        h->xpeer[peer_rank] = (float*)dev_ptr;
+        h->xpeer_ipc[peer_rank] = false;
+    }
+    return COVO_OK;
+}
+
+int covo_step_sharded_device(covo_handle* h, const float* st_d, const int* tm_d, const float* eps_d, float* act_d, void* stream) {
+    if (!h || !st_d || !tm_d || !act_d) return fail(COVO_ERR_INVALID, "null argument");
+    if (!h->xchg.p) return fail(COVO_ERR_INVALID, "no exchange buffer: the handle was created with world == 1");
+    const int world = h->cfg.world;
+    for (int w = 0; w < world; ++w)
+        if (!h->xpeer[w]) return fail(COVO_ERR_INVALID, "rank %d is not attached (covo_exchange_attach)", w);
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mode = h->cfg.mode;
+    if (mode == COVO_MODE_MPPI) {
+        shift_blocks_kernel<<<h->E, 128, 2 * h->H * 16 * sizeof(float), st>>>(h->Lblk.p, h->cov.p, h->H);
+        CK(cudaGetLastError());
+    } else if (mode == COVO_MODE_COVO_ONLINE) {  // every rank repeats the covariance step (it depends on the merged mean only)
+        HessianArgs ha = hess_args(h, st_d, tm_d, h->a_mean.p, 1, h->R.p, h->hess_ws.p, (long long)h->T * 3);
+        CK(launch_hessian(ha, h->E, st));
+        int rc = run_sigma_chol(h, st, nullptr);
+        if (rc) return rc;
+    } else if (h->t_sched <= 0) {
+        return fail(COVO_ERR_INVALID, "covo-offline: no schedule");
+    }
+    const size_t flag_off = (size_t)2 * world * h->E * h->rec;  // floats in front of the flags
+    RolloutArgs ra = rollout_args(h, st_d, tm_d, h->a_mean.p, 1, eps_d, nullptr, h->a_mean.p, h->action.p, nullptr, nullptr, 0);
+    ra.px.world = world;
+    ra.px.rank = h->cfg.rank;
+    for (int w = 0; w < world; ++w) {
+        ra.px.rec[w] = h->xpeer[w];
+        ra.px.flag[w] = reinterpret_cast<unsigned int*>(h->xpeer[w] + flag_off);
+    }
+    ra.px.epoch = h->xchg_step + 1u;  // the exchange is keyed by the step number, which every rank advances alike
+    CK(launch_rollout(ra, h->E, st));
+    MergeArgs m;
+    m.world = world;
+    m.n = h->n;
+    m.n_pad = h->n_pad;
+    m.n_env = h->E;
+    m.lam = h->cfg.lam;
+    m.gamma_mean = h->cfg.gamma_mean;
+    m.shift = 1;
+    m.gathered = h->xchg.p;
+    m.flags = reinterpret_cast<const unsigned int*>(h->xchg.p + flag_off);
+    m.stream = h->xchg_step;
+    m.status = h->status.p;
+    m.a_mean_in = h->a_mean.p;  // in place: the kernel reads before it writes
+    m.a_mean_out = h->a_mean.p;
+    m.action_out = act_d;
+    CK(launch_merge(m, st));
+    h->xchg_step += 1;
+    if (!eps_d) h->rng_stream += 1;
     return COVO_OK;
 }
 

@@ -39,6 +39,18 @@ __host__ __device__ inline int lt_size(int n, int n_pad) { return lt_col_offset(
         if ((args).prof && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) (args).prof[slot] = clock64(); \
     } while (0)
 
+// N-sharded step (BASELINE config 4): every rank writes its (min cost, sum w, sum w u) record straight into the exchange buffer of
+// every rank -- peer device memory over NVLink (CUDA IPC mappings), or plain device pointers when the "ranks" are handles of one
+// process -- and raises a flag there; the merge waits for the flags of all ranks.  Two slots by step parity: a rank can be at most
+// one step ahead of a peer (it needs the peer's record of step t before it can finish step t).
+constexpr int kMaxPeers = 8;
+struct PeerExchange {
+    int world = 0, rank = 0;          // world == 0: off
+    unsigned int epoch = 0;           // step number + 1 (what the flags are raised to)
+    float* rec[kMaxPeers] = {};       // rank w's buffer: [2][world][E][kPartialHdr + n_pad] floats ...
+    unsigned int* flag[kMaxPeers] = {};  // ... and [2][world][E] flags (the step number the slot holds, + 1)
+};
+
 struct RolloutArgs {
     long long* prof = nullptr;  // optional: clock64() stamps at phase boundaries (debug)
     int n_samples;      // samples of THIS launch (this rank's shard)
@@ -82,12 +94,19 @@ struct RolloutArgs {
     const int* lfac_progress = nullptr;
     int lfac_epoch = 0;
     int overlap = 0;  // set by launch_rollout: sampling GEMM and rollouts run concurrently (separate U tile fits in smem)
+    PeerExchange px;  // !finalize: also publish the rank record to every peer (fused exchange)
 };
 
 struct MergeArgs {
     int world, n, n_pad, n_env;
     float lam, gamma_mean;
     int shift;
+    // fused exchange: gathered = this rank's exchange buffer [2][world][E][rec], flags [2][world][E]; the kernel waits until every
+    // rank's flag of the slot says step (stream + *stream_ctr)
+    const unsigned int* flags = nullptr;
+    unsigned int stream = 0;
+    const unsigned int* stream_ctr = nullptr;
+    int* status = nullptr;   // [E]: 4 = a peer's record did not arrive within the watchdog time
     const float* gathered;   // [world][E][kPartialHdr + n_pad]
     const float* a_mean_in;  // [E][n]
     float* a_mean_out;       // [E][n]

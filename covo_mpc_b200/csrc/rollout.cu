@@ -688,13 +688,62 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) rollout_kernel(const Rollo
         a.counters[env] = 0u;  // re-arm for the next launch
         if (a.prof) a.prof[39] = clock64();
     }
+    if (!a.finalize && a.px.world > 0) {
+        // fused exchange: the record goes straight into slot [step parity][this rank][env] of EVERY rank's buffer (remote stores over
+        // NVLink for the peers), then -- behind a system-scope fence and the CTA barrier -- the flag of that slot is raised everywhere
+        const unsigned int epoch = a.px.epoch;
+        const int n_env = (int)gridDim.y;
+        const long long slot = ((long long)(epoch & 1u) * a.px.world + a.px.rank) * n_env + env;
+        for (int w = 0; w < a.px.world; ++w) {
+            float* dst = a.px.rec[w] + slot * rec;
+            int sl = 0;
+            for (int r = tid; r < n_pad; r += blockDim.x, ++sl) dst[kPartialHdr + r] = Vr[sl < 2 ? sl : 1];
+            if (tid == 0) {
+                dst[0] = M;
+                dst[1] = S;
+                dst[2] = 0.f;
+                dst[3] = 0.f;
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < a.px.world) {
+            unsigned int* f = a.px.flag[tid] + slot;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+        }
+    }
 }
 
 // C1 epilogue: merge the per-rank (m, s, v) records gathered over NCCL, in rank order.
-__global__ void merge_ranks_kernel(const MergeArgs a) {
+__global__ void merge_ranks_kernel(const MergeArgs a_in) {
+    MergeArgs a = a_in;
     const int env = blockIdx.x;
     const int rec = kPartialHdr + a.n_pad;
     const float inv_lam = 1.0f / a.lam;
+    if (a.flags) {
+        // fused exchange: wait until every rank's record of this step has landed in this rank's buffer (written by the peers' rollout
+        // kernels, see rollout_kernel), then merge in rank order exactly as after an all-gather
+        const unsigned int epoch = a.stream + (a.stream_ctr ? __ldg(a.stream_ctr) : 0u) + 1u;
+        const long long slot0 = (long long)(epoch & 1u) * a.world * a.n_env;
+        if ((int)threadIdx.x < a.world) {
+            const unsigned int* f = a.flags + slot0 + (long long)threadIdx.x * a.n_env + env;
+            unsigned long long t0 = 0, t1 = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            for (;;) {
+                unsigned int v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if ((int)(v - epoch) >= 0) break;
+                __nanosleep(100);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 4000000000ull) {  // 4 s: a peer is gone; report instead of hanging the device
+                    if (a.status) a.status[env] = 4;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        a.gathered += slot0 * rec;
+    }
     float M = CUDART_INF_F;
     for (int w = 0; w < a.world; ++w) M = fminf(M, a.gathered[((long long)w * a.n_env + env) * rec]);
     float S = 0.f;
@@ -704,17 +753,31 @@ __global__ void merge_ranks_kernel(const MergeArgs a) {
         S = fmaf(g[1], sc, S);
     }
     const int H = a.n >> 2;
-    for (int r = threadIdx.x; r < a.n; r += blockDim.x) {
+    // a_mean_in may be a_mean_out (in place): every thread reads the shifted entries it blends with before anybody writes
+    constexpr int kPer = 4;  // entries per thread: n <= 4 * blockDim.x
+    float mu[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        const int r = threadIdx.x + j * blockDim.x;
+        mu[j] = 0.f;
+        if (r < a.n) {
+            const int h = r >> 2, c = r & 3;
+            const int hs = a.shift ? min(h + 1, H - 1) : h;
+            mu[j] = a.a_mean_in[(long long)env * a.n + hs * 4 + c];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        const int r = threadIdx.x + j * blockDim.x;
+        if (r >= a.n) continue;
         float V = 0.f;
         for (int w = 0; w < a.world; ++w) {
             const float* g = a.gathered + ((long long)w * a.n_env + env) * rec;
             float sc = (g[0] < CUDART_INF_F) ? expf(-(g[0] - M) * inv_lam) : 0.f;
             V = fmaf(g[kPartialHdr + r], sc, V);
         }
-        int h = r >> 2, c = r & 3;
-        int hs = a.shift ? min(h + 1, H - 1) : h;
-        float mu = a.a_mean_in[(long long)env * a.n + hs * 4 + c];
-        float nm = (S > 0.f) ? (V / S) * a.gamma_mean + mu * (1.0f - a.gamma_mean) : mu;
+        float nm = (S > 0.f) ? (V / S) * a.gamma_mean + mu[j] * (1.0f - a.gamma_mean) : mu[j];
         a.a_mean_out[(long long)env * a.n + r] = nm;
         if (r < 4) a.action_out[(long long)env * 4 + r] = nm;
     }

@@ -137,6 +137,18 @@ int covo_step_partial_device(covo_handle* h, const float* state24_dev, const int
                              void* stream);
 int covo_partial_buffer(covo_handle* h, float** dev_ptr, int* n_floats);
 int covo_step_merge_device(covo_handle* h, const float* gathered_dev, float* action_dev, void* stream);
+/* Fused exchange for the same step (world <= 8 ranks on one NVLink domain): instead of kernel -> all-gather -> kernel, the rollout
+ * kernel's finalising CTA writes the rank record (832 B at H = 50) straight into the exchange buffer of EVERY rank -- peer device
+ * memory mapped through CUDA IPC -- and raises a flag there; the merge kernel, launched right behind it, waits for the flags of all
+ * ranks and merges in rank order (bit-identical to the all-gather path).  No collective call, no host synchronisation.
+ *   covo_exchange_info   : this rank's buffer as a 64-byte cudaIpcMemHandle_t (ship it to the other processes, e.g. with
+ *                          torch.distributed.all_gather_object) and/or as a raw device pointer (handles of one process);
+ *   covo_exchange_attach : make rank `peer_rank`'s buffer known, by IPC handle or by pointer (exactly one non-NULL);
+ *   covo_step_sharded_device : one MPC step; every rank must call it the same number of times (slots are keyed by the call count).
+ * A peer that never delivers is reported as status 4 after a 4 s watchdog instead of hanging the device. */
+int covo_exchange_info(covo_handle* h, void* ipc_handle64, void** dev_ptr);
+int covo_exchange_attach(covo_handle* h, int peer_rank, const void* ipc_handle64, void* dev_ptr);
+int covo_step_sharded_device(covo_handle* h, const float* state24_dev, const int* time_dev, const float* eps_dev, float* action_dev, void* stream);
 
 /* Operators, exposed on their own for parity tests (host pointers, synchronous). */
 int covo_hessian(covo_handle* h, const float* state24, const int* time, const float* a_mean, int shift, float* R);

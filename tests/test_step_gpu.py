@@ -289,6 +289,80 @@ def test_sample_sharded_step_equals_single_device():
     assert np.abs(outs[0][0] - act1.cpu().numpy()).max() < 2e-6
 
 
+def test_fused_peer_exchange_equals_allgather_path():
+    """The fused exchange (covo_step_sharded_device): two handles of one process play rank 0 / rank 1 on two streams, attached to
+    each other by device pointer (across processes the same buffers are mapped through CUDA IPC).  Each rollout kernel writes its
+    record into both exchange buffers and raises the flags; each merge kernel waits for both flags.  Several steps in a row (slot
+    parity, in-place mean update); the result must be bit-identical to the all-gather + merge path and agree with world 1."""
+    import torch
+
+    from covo_mpc_b200 import _lib
+
+    N, H, T, STEPS_ = 1024, 12, 8, 5
+    p, ns, a_mean, rng = scenario("tracking_zigzag", seed=31, H=H, warm_steps=6)
+    n = 4 * H
+    A = rng.standard_normal((T, n, n)) / np.sqrt(n)
+    table = (0.2 * A @ A.transpose(0, 2, 1) + 0.1 * np.eye(n)).astype(np.float32)
+    st = torch.from_numpy(o.state_to_vec24(ns)).cuda()
+    tms = [torch.tensor([k], dtype=torch.int32).cuda() for k in range(STEPS_)]
+
+    def mk(rank, world):
+        cfg = _lib.default_config()
+        cfg.mode, cfg.n_samples, cfg.horizon, cfg.traj_len = _lib.MODE_COVO_OFFLINE, N, H, ns.pos_traj.shape[0]
+        cfg.rank, cfg.world, cfg.seed = rank, world, 77
+        h = _lib.Handle(cfg)
+        h.set_reference(ns.pos_traj[None], ns.vel_traj[None])
+        h.set_cov_offline(table)
+        h.set_mean(a_mean[None])
+        return h
+
+    # reference 1: world 1
+    h1 = mk(0, 1)
+    act1 = torch.zeros((STEPS_, 4), device="cuda")
+    for k in range(STEPS_):
+        h1.step_device(st.data_ptr(), tms[k].data_ptr(), 0, act1[k].data_ptr(), 0)
+    torch.cuda.synchronize()
+    # reference 2: partial -> "all-gather" -> merge
+    shards = [mk(r, 2) for r in range(2)]
+    act_ag = torch.zeros((2, STEPS_, 4), device="cuda")
+    for k in range(STEPS_):
+        recs = []
+        for h in shards:
+            h.step_partial_device(st.data_ptr(), tms[k].data_ptr(), 0, 0)
+            torch.cuda.synchronize()
+            ptr, cnt = h.partial_buffer()
+
+            class _W:
+                __cuda_array_interface__ = {"shape": (cnt,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+            recs.append(torch.as_tensor(_W(), device="cuda").clone())
+        gathered = torch.stack(recs).contiguous()
+        for r, h in enumerate(shards):
+            h.step_merge_device(gathered.data_ptr(), act_ag[r, k].data_ptr(), 0)
+        torch.cuda.synchronize()
+    mean_ag = shards[0].get_mean()[0]
+    # the fused path: both ranks launched back to back on their own streams, no host synchronisation between the steps
+    fused = [mk(r, 2) for r in range(2)]
+    infos = [h.exchange_info() for h in fused]
+    fused[0].exchange_attach(1, dev_ptr=infos[1][1])
+    fused[1].exchange_attach(0, dev_ptr=infos[0][1])
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    act_f = torch.zeros((2, STEPS_, 4), device="cuda")
+    torch.cuda.synchronize()
+    for k in range(STEPS_):
+        for r, h in enumerate(fused):
+            h.step_sharded_device(st.data_ptr(), tms[k].data_ptr(), 0, act_f[r, k].data_ptr(), streams[r].cuda_stream)
+    torch.cuda.synchronize()
+    assert (fused[0].status() == 0).all() and (fused[1].status() == 0).all()  # 4 = the watchdog gave up on a peer
+    assert torch.equal(act_f[0], act_f[1])
+    assert torch.equal(act_f[0], act_ag[0]), "fused exchange differs from the all-gather path"
+    assert np.array_equal(fused[0].get_mean()[0], mean_ag) and np.array_equal(fused[1].get_mean()[0], mean_ag)
+    # same samples (global RNG index); the merge order differs from the tile order, and the difference is carried through the steps
+    assert (act_f[0, 0] - act1[0]).abs().max().item() < 2e-6 and (act_f[0] - act1).abs().max().item() < 1e-4
+    for h in [h1, *shards, *fused]:
+        h.close()
+
+
 def test_keyed_episode_follows_the_reference_key_schedule():
     """run_episode_keyed: reset / noise / sampling all driven by JAX PRNG keys split as eval_env splits them
     (envs/quadrotor.py:520-563).  Deterministic; and the controller's in-kernel Threefry draws equal the host twin's."""
