@@ -89,6 +89,7 @@ _SIGNATURES = {
     "covo_env_reset": [_H, _F, _I],
     "covo_env_get_state": [_H, _F, _I],
     "covo_env_step": [_H, _F, _F, C.c_ulonglong, C.c_uint, C.c_int, C.c_float, C.c_float, _F, _F, _F, _I],
+    "covo_env_set_reset_pool": [_H, C.c_int, _F, _I, _F, _F, _F],
     "covo_closed_loop": [_H, C.c_int, C.c_ulonglong, C.c_int, C.c_float, C.c_float, _F, _F, _F, _F],
     "covo_local_samples": [_H, _I, _I],
 }
@@ -369,6 +370,22 @@ class Handle:
         if s.size != self.E * 24 or t.size != self.E:
             raise ValueError("state24 / time have the wrong size")
         check(self.lib.covo_env_reset(self._h, fptr(s), iptr(t)))
+
+    def env_set_reset_pool(self, state24, time, pos_traj, vel_traj, a_mean_init=None):
+        """Auto-reset on the device (envs/base.py:27-38): state24 [P][E][24], time [P][E], pos_traj / vel_traj [P][E][T][3] are the
+        reset_env draws each environment continues from when its pre-step state is terminal; a_mean_init [H][4]: also reset the
+        controller's mean.  state24 None switches it off."""
+        if state24 is None:
+            check(self.lib.covo_env_set_reset_pool(self._h, 0, None, None, None, None, None))
+            return
+        s, t, pt, vt = f32(state24), i32(time), f32(pos_traj), f32(vel_traj)
+        P = s.size // (self.E * 24)
+        if s.size != P * self.E * 24 or t.size != P * self.E or pt.size != vt.size or pt.size % (P * self.E * 3):
+            raise ValueError("reset pool arrays have inconsistent sizes")
+        m = None if a_mean_init is None else f32(a_mean_init)
+        if m is not None and m.size != self.n:
+            raise ValueError("a_mean_init must be [H][4]")
+        check(self.lib.covo_env_set_reset_pool(self._h, P, fptr(s), iptr(t), fptr(pt), fptr(vt), fptr(m)))
 
     def env_state(self):
         s = np.empty((self.E, 24), dtype=np.float32)

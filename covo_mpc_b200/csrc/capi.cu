@@ -1,5 +1,6 @@
 // C-ABI (include/covo_b200.h): handle, device workspace and the per-mode step schedules.
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -77,6 +78,95 @@ __global__ void shift_blocks_kernel(float* Lblk, float* cov, int H) {
     }
 }
 
+// MPPI covariance update (controllers/mppi.py:119-125, gamma_sigma != 0):
+//     a_cov[h] <- gamma_sigma * sum_i w_i (a_i[h] - a_mean[h]) (a_i[h] - a_mean[h])^T + (1 - gamma_sigma) * a_cov[h]
+// with w the normalised softmax weights of this step, a_i the CLIPPED samples (:66), a_mean the UPDATED (blended) mean and a_cov the
+// shifted covariance the samples were drawn from; then the 4 x 4 Cholesky factor the next step's sampler uses (:59).  One CTA per
+// (horizon step, environment) over the per-sample costs and samples the rollout kernel leaves behind in this mode.  A pivot that is
+// not positive (the weighted covariance has rank ~ESS: with lambda = 0.01 the reference's own Cholesky returns NaN there) sets status 2.
+__global__ void __launch_bounds__(256) mppi_cov_update_kernel(const float* __restrict__ costs, const float* __restrict__ samples,
+                                                              const float* __restrict__ a_mean, float* cov, float* Lblk, int* status, int N, int H,
+                                                              float inv_lam, float gamma_sigma) {
+    const int h = blockIdx.x, env = blockIdx.y, tid = threadIdx.x, n = 4 * H;
+    const float* c_e = costs + (long long)env * N;
+    const float* s_e = samples + (long long)env * N * n + 4 * h;
+    __shared__ float red[8][12];
+    float m = CUDART_INF_F;
+    for (int i = tid; i < N; i += 256) m = fminf(m, c_e[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) red[tid >> 5][0] = m;
+    __syncthreads();
+    m = red[0][0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fminf(m, red[w][0]);
+    __syncthreads();
+    const float4 mu = *reinterpret_cast<const float4*>(a_mean + (long long)env * n + 4 * h);
+    float acc[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) acc[k] = 0.f;
+    for (int i = tid; i < N; i += 256) {
+        const float c = c_e[i];
+        const float w = (c < CUDART_INF_F) ? expf(-(c - m) * inv_lam) : 0.f;
+        const float4 a = *reinterpret_cast<const float4*>(s_e + (long long)i * n);
+        const float d[4] = {a.x - mu.x, a.y - mu.y, a.z - mu.z, a.w - mu.w};
+        acc[0] += w;
+        int k = 1;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q <= r; ++q) acc[k++] = fmaf(w * d[r], d[q], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) red[tid >> 5][k] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float tot[11];
+        for (int k = 0; k < 11; ++k) {
+            float v = 0.f;
+            for (int w = 0; w < 8; ++w) v += red[w][k];
+            tot[k] = v;
+        }
+        float* C = cov + ((long long)env * H + h) * 16;
+        float* L = Lblk + ((long long)env * H + h) * 16;
+        const float inv_s = tot[0] > 0.f ? 1.f / tot[0] : 0.f;
+        float Cn[4][4];
+        int k = 1;
+        for (int r = 0; r < 4; ++r)
+            for (int q = 0; q <= r; ++q) {
+                const float v = gamma_sigma * tot[k++] * inv_s + (1.f - gamma_sigma) * C[r * 4 + q];
+                Cn[r][q] = Cn[q][r] = v;
+            }
+        float Lf[4][4] = {};
+        bool bad = false;
+        for (int r = 0; r < 4; ++r)
+            for (int q = 0; q <= r; ++q) {
+                float v = Cn[r][q];
+                for (int t = 0; t < q; ++t) v -= Lf[r][t] * Lf[q][t];
+                if (r == q) {
+                    if (!(v > 0.f)) {
+                        bad = true;
+                        v = 1e-30f;
+                    }
+                    Lf[r][r] = sqrtf(v);
+                } else {
+                    Lf[r][q] = v / Lf[q][q];
+                }
+            }
+        for (int r = 0; r < 4; ++r)
+            for (int q = 0; q < 4; ++q) {
+                C[r * 4 + q] = Cn[r][q];
+                L[r * 4 + q] = Lf[r][q];
+            }
+        if (bad && status) status[env] = 2;
+    }
+}
+
 __global__ void debug_eps_kernel(float* out, int n_local, int offset, int n, unsigned long long seed, unsigned int stream) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int blocks4 = n >> 2;
@@ -141,6 +231,10 @@ struct covo_handle {
     bool phase_clocks = false;
     // device-resident environment (caller side of the hot path)
     DevBuf<float> env_state24, env_noisy24, env_noise, env_log_f, env_action, pid_integral;
+    DevBuf<float> pool_state24, pool_pos, pool_vel, mean_init;  // auto-reset pool (covo_env_set_reset_pool)
+    DevBuf<int> pool_time, pool_count;
+    int pool_n = 0;
+    bool pool_reset_mean = false;
     DevBuf<int> env_time, env_noisy_time, env_done;
     bool env_ready = false;
     // CUDA-graph replay of the step (one graph launch per MPC step instead of 8-10 kernel launches, event records and waits).
@@ -212,6 +306,7 @@ void release_all(covo_handle* h) {
     h->dense_scal.release();
     h->dense_X.release();
     h->pid_integral.release();
+    h->pool_state24.release(); h->pool_pos.release(); h->pool_vel.release(); h->mean_init.release(); h->pool_time.release(); h->pool_count.release();
     h->dev_ctr.release();
     for (covo_handle::StepGraph* g : {&h->g_dev, &h->g_host, &h->g_loop}) {
         if (g->exec) cudaGraphExecDestroy(g->exec);
@@ -372,6 +467,11 @@ int run_sigma_chol(covo_handle* h, cudaStream_t st, Prof* pf, bool want_L = fals
     return COVO_OK;
 }
 
+// steps whose covariance work can end with a numeric status: CoVO-online (optimize_sigma, Cholesky), MPPI with gamma_sigma != 0
+static bool step_has_status(const covo_handle* h) {
+    return h->cfg.mode == COVO_MODE_COVO_ONLINE || (h->cfg.mode == COVO_MODE_MPPI && h->cfg.gamma_sigma != 0.f);
+}
+
 // The launch sequence of one MPC step on stream `st`.  rec != nullptr: the step is being captured into a CUDA graph -- the sample
 // field is indexed by the device counter and the arguments of the two kernels that carry caller pointers are kept for patching.
 int step_launch(covo_handle* h, const float* st_d, const int* tm_d, const float* eps_d, float* act_d, cudaStream_t st, int finalize,
@@ -396,7 +496,9 @@ int step_launch(covo_handle* h, const float* st_d, const int* tm_d, const float*
         if (h->t_sched <= 0) return fail(COVO_ERR_INVALID, "covo-offline: no schedule; call covo_reset_offline or covo_set_cov_offline first");
         for (int i = 1; i <= 5; ++i) pf.mark(i);
     }
-    RolloutArgs ra = rollout_args(h, st_d, tm_d, h->a_mean.p, 1, eps_d, nullptr, h->a_mean.p, act_d, nullptr, nullptr, finalize);
+    const bool cov_update = mode == COVO_MODE_MPPI && h->cfg.gamma_sigma != 0.f;  // mppi.py:119-125 needs the samples and their costs
+    RolloutArgs ra = rollout_args(h, st_d, tm_d, h->a_mean.p, 1, eps_d, nullptr, h->a_mean.p, act_d, cov_update ? h->costs.p : nullptr,
+                                  cov_update ? h->samples.p : nullptr, finalize);
     if (pipelined) {
         ra.lfac_progress = h->chol_progress.p;
         ra.lfac_epoch = 0;
@@ -407,6 +509,12 @@ int step_launch(covo_handle* h, const float* st_d, const int* tm_d, const float*
         rec->ra = ra;
     }
     CK(launch_rollout(ra, h->E, st));
+    if (cov_update) {
+        CK(cudaMemsetAsync(h->status.p, 0, (size_t)h->E * sizeof(int), st));
+        mppi_cov_update_kernel<<<dim3(h->H, h->E), 256, 0, st>>>(h->costs.p, h->samples.p, h->a_mean.p, h->cov.p, h->Lblk.p, h->status.p,
+                                                                  h->n_local, h->H, 1.0f / h->cfg.lam, h->cfg.gamma_sigma);
+        CK(cudaGetLastError());
+    }
     pf.mark(6);
     return COVO_OK;
 }
@@ -482,7 +590,7 @@ int graph_build(covo_handle* h, covo_handle::StepGraph* sg, const float* st_d, c
     if (ce == cudaSuccess && rc == COVO_OK) ce = launch_bump(h->dev_ctr.p, kind == 2 ? h->dev_ctr.p + 1 : nullptr, cs);
     if (ce == cudaSuccess && rc == COVO_OK && kind == 1) {
         ce = cudaMemcpyAsync(h->h_action, h->action.p, E * 4 * sizeof(float), cudaMemcpyDeviceToHost, cs);
-        if (ce == cudaSuccess && h->cfg.mode == COVO_MODE_COVO_ONLINE)
+        if (ce == cudaSuccess && step_has_status(h))
             ce = cudaMemcpyAsync(h->h_status, h->status.p, E * sizeof(int), cudaMemcpyDeviceToHost, cs);
     }
     cudaGraph_t g = nullptr;
@@ -563,7 +671,7 @@ int step_common(covo_handle* h, const float* st_d, const int* tm_d, const float*
     if (host_io) {
         const size_t E = (size_t)h->E;
         CK(cudaMemcpyAsync(h->h_action, h->action.p, E * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (h->cfg.mode == COVO_MODE_COVO_ONLINE) CK(cudaMemcpyAsync(h->h_status, h->status.p, E * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (step_has_status(h)) CK(cudaMemcpyAsync(h->h_status, h->status.p, E * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     if (!eps_d) h->rng_stream += 1;
     h->direct_steps += 1;
@@ -629,7 +737,9 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
     if (cfg->n_samples < 1 || cfg->n_env < 1 || cfg->traj_len < 1) return fail(COVO_ERR_INVALID, "sizes must be positive");
     if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(COVO_ERR_INVALID, "bad rank/world");
     if (cfg->n_samples % cfg->world) return fail(COVO_ERR_INVALID, "n_samples must divide evenly across world");
-    if (cfg->gamma_sigma != 0.f) return fail(COVO_ERR_NOT_IMPLEMENTED, "gamma_sigma != 0 (MPPI covariance update) is not implemented");
+    if (cfg->gamma_sigma != 0.f && cfg->mode == COVO_MODE_MPPI && cfg->world != 1)
+        return fail(COVO_ERR_NOT_IMPLEMENTED, "gamma_sigma != 0 (MPPI covariance update) with the sample axis sharded (world > 1) is not implemented");
+    if (cfg->gamma_sigma < 0.f || cfg->gamma_sigma > 1.f) return fail(COVO_ERR_INVALID, "gamma_sigma must be in [0, 1]");
     if (cfg->mode == COVO_MODE_COVO_OFFLINE && cfg->n_env != 1)
         return fail(COVO_ERR_NOT_IMPLEMENTED, "covo-offline supports n_env == 1");
     if (!(cfg->lam > 0.f)) return fail(COVO_ERR_INVALID, "lam must be positive");
@@ -710,6 +820,10 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
     if (cfg->mode == COVO_MODE_MPPI) {
         A(h->Lblk.alloc(E * h->H * 16));
         A(h->cov.alloc(E * h->H * 16));
+        if (cfg->gamma_sigma != 0.f) {  // the covariance update reads the samples and their costs back (mppi.py:119-125)
+            A(h->costs.alloc(E * (size_t)h->n_local));
+            A(h->samples.alloc(E * (size_t)h->n_local * h->n));
+        }
     } else {
         A(h->R.alloc(E * nn));
         A(h->Vh.alloc(E * nn));
@@ -1060,7 +1174,59 @@ static EnvStepArgs env_args(covo_handle* h, int gaussian, float obs_scale, float
     a.reward = nullptr;
     a.err_pos = nullptr;
     a.done = nullptr;
+    if (h->pool_n > 0) {
+        a.reset_pool = h->pool_n;
+        a.reset_state24 = h->pool_state24.p;
+        a.reset_time = h->pool_time.p;
+        a.reset_pos_traj = h->pool_pos.p;
+        a.reset_vel_traj = h->pool_vel.p;
+        a.reset_count = h->pool_count.p;
+        a.traj_pos_rw = h->pos_traj.p;
+        a.traj_vel_rw = h->vel_traj.p;
+        if (h->pool_reset_mean) {
+            a.a_mean = h->a_mean.p;
+            a.a_mean_init = h->mean_init.p;
+            a.n_mean = h->n;
+        }
+    }
     return a;
+}
+
+int covo_env_set_reset_pool(covo_handle* h, int n_pool, const float* state24, const int* time, const float* pos_traj, const float* vel_traj,
+                            const float* a_mean_init) {
+    if (!h) return fail(COVO_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    graphs_invalidate(h);  // the closed-loop graph carries the pool pointers
+    h->loop_args_valid = false;
+    if (n_pool <= 0) {
+        h->pool_n = 0;
+        return COVO_OK;
+    }
+    if (!state24 || !time || !pos_traj || !vel_traj) return fail(COVO_ERR_INVALID, "null argument");
+    if (h->cfg.mode == COVO_MODE_COVO_OFFLINE)
+        return fail(COVO_ERR_NOT_IMPLEMENTED, "auto-reset on the device for covo-offline (the covariance schedule is rebuilt per episode: covo_reset_offline)");
+    const size_t E = (size_t)h->E, P = (size_t)n_pool, tl = (size_t)h->T * 3;
+    h->pool_state24.release(); h->pool_time.release(); h->pool_pos.release(); h->pool_vel.release(); h->pool_count.release();
+    CK(h->pool_state24.alloc(P * E * kStateFloats));
+    CK(h->pool_time.alloc(P * E));
+    CK(h->pool_pos.alloc(P * E * tl));
+    CK(h->pool_vel.alloc(P * E * tl));
+    CK(h->pool_count.alloc(E));
+    CK(h2d(h, h->pool_state24.p, state24, P * E * kStateFloats * sizeof(float)));
+    CK(h2d(h, h->pool_time.p, time, P * E * sizeof(int)));
+    CK(h2d(h, h->pool_pos.p, pos_traj, P * E * tl * sizeof(float)));
+    CK(h2d(h, h->pool_vel.p, vel_traj, P * E * tl * sizeof(float)));
+    h->pool_reset_mean = a_mean_init != nullptr;
+    if (a_mean_init) {
+        if (h->mean_init.n < (size_t)h->n) {
+            h->mean_init.release();
+            CK(h->mean_init.alloc(h->n));
+        }
+        CK(h2d(h, h->mean_init.p, a_mean_init, (size_t)h->n * sizeof(float)));
+    }
+    CK(cudaStreamSynchronize(h->own_stream));
+    h->pool_n = n_pool;
+    return COVO_OK;
 }
 
 int covo_env_reset(covo_handle* h, const float* state24, const int* time) {
@@ -1249,7 +1415,7 @@ int covo_step(covo_handle* h, const float* state24, const int* time, const float
     if (rc) return rc;
     CK(cudaStreamSynchronize(st));
     memcpy(action, h->h_action, (size_t)h->E * 4 * sizeof(float));
-    if (h->cfg.mode == COVO_MODE_COVO_ONLINE)  // the covariance step of THIS call (the Hessian kernel clears the status)
+    if (step_has_status(h))  // the covariance step of THIS call (its first kernel clears the status)
         for (int e = 0; e < h->E; ++e)
             if (h->h_status[e] == 3) {
                 // the dense path's Lanczos stage was not converged to 2e-7: this step's covariance is a valid SPD matrix whose

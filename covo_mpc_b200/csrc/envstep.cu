@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvStepArgs a) {
         const float ex = pt[0] - s.p[0], ey = pt[1] - s.p[1], ez = pt[2] - s.p[2];
         if (a.err_pos) a.err_pos[log_off + e] = sqrtf(ex * ex + ey * ey + ez * ez);
         if (a.reward) a.reward[log_off + e] = quad_reward(s, pt, vt);
-        if (a.done) a.done[e] = quad_terminal(s, t, a.env) ? 1 : 0;
+        const bool quad_terminal_prestep = quad_terminal(s, t, a.env);
+        if (a.done) a.done[e] = quad_terminal_prestep ? 1 : 0;
         const float* ag = a.action + (long long)e * 4;
         const float u[4] = {ag[0], ag[1], ag[2], ag[3]};
         if (a.action_log) {
@@ -61,6 +62,25 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvStepArgs a) {
         for (int k = 0; k < 3; ++k) {
             pt[k] = pr[k];
             vt[k] = vr[k];
+        }
+        if (a.reset_pool > 0 && quad_terminal_prestep) {
+            // envs/base.py:27-38: done (of the pre-step state) -> the next reset_env draw replaces the stepped state
+            const int k = a.reset_count[e] % a.reset_pool;
+            a.reset_count[e] += 1;
+            const float* rs = a.reset_state24 + ((long long)k * a.n_env + e) * kStateFloats;
+            load_state24(rs, s, fd, pt, vt);
+            t = a.reset_time[(long long)k * a.n_env + e];
+            const long long tl = (long long)a.traj_len * 3;
+            const float* rp = a.reset_pos_traj + ((long long)k * a.n_env + e) * tl;
+            const float* rv = a.reset_vel_traj + ((long long)k * a.n_env + e) * tl;
+            float* wp = a.traj_pos_rw + (long long)e * a.traj_stride;
+            float* wv = a.traj_vel_rw + (long long)e * a.traj_stride;
+            for (long long i = 0; i < tl; ++i) {
+                wp[i] = rp[i];
+                wv[i] = rv[i];
+            }
+            if (a.a_mean)
+                for (int i = 0; i < a.n_mean; ++i) a.a_mean[(long long)e * a.n_mean + i] = a.a_mean_init[i];
         }
         for (int k = 0; k < 3; ++k) sg[k] = s.p[k];
         for (int k = 0; k < 4; ++k) sg[3 + k] = s.q[k];

@@ -31,6 +31,22 @@ struct EnvStepArgs {
     // block (noise_in + i * E * 16) and the log rows (reward / err_pos + i * E, action_log + i * E * 4 <- action)
     const unsigned int* step_ctr = nullptr;
     float* action_log = nullptr;
+    // Auto-reset of BaseEnvironment.step (envs/base.py:27-38): when the PRE-step state is terminal, the stepped state is discarded
+    // and environment e continues from the next entry of its reset pool (reset_env draws prepared by the host: state, time, reference
+    // trajectory), the trajectory tables are overwritten in place (the controller kernels read the same buffers), and -- what the
+    // reference's harness does next (envs/quadrotor.py:637-639: controller.reset returns the initial parameters) -- the
+    // controller's resident mean goes back to its initial value.  reset_pool == 0: no auto-reset (episodes bounded by the caller).
+    int reset_pool = 0;
+    const float* reset_state24 = nullptr;  // [P][E][24]
+    const int* reset_time = nullptr;       // [P][E]
+    const float* reset_pos_traj = nullptr; // [P][E][T][3]
+    const float* reset_vel_traj = nullptr; // [P][E][T][3]
+    int* reset_count = nullptr;            // [E]: resets taken so far (entry = count % P)
+    float* traj_pos_rw = nullptr;          // = pos_traj / vel_traj, writable
+    float* traj_vel_rw = nullptr;
+    float* a_mean = nullptr;               // optional [E][n_mean]: the controller's mean, reset with the environment
+    const float* a_mean_init = nullptr;    // [n_mean]
+    int n_mean = 0;
 };
 
 // one thread: advances the device step counters at the end of a replayed step

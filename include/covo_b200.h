@@ -66,7 +66,7 @@ typedef struct covo_config {
     float lam;           /* temperature (reference default 0.01) */
     float sample_sigma;  /* sigma (0.5) */
     float gamma_mean;    /* 1.0 */
-    float gamma_sigma;   /* 0.0 (MPPI covariance update; only 0 is implemented) */
+    float gamma_sigma;   /* 0.0 (reference default); MPPI: != 0 enables the covariance update of mppi.py:119-125 (world == 1); ignored by CoVO */
     float discount;      /* 1.0 */
     /* EnvParams3D, quadjax/dynamics/dataclass.py:40-100 */
     float m, g, max_thrust, dt, alpha_bodyrate, action_scale, pos_limit;
@@ -195,6 +195,14 @@ int covo_env_step(covo_handle* h, const float* action, const float* noise, unsig
 int covo_closed_loop(covo_handle* h, int n_steps, unsigned long long noise_seed, int gaussian_disturbance,
                      float obs_noise_scale, float dyn_noise_scale, const float* noise, float* actions, float* rewards,
                      float* err_pos);
+/* Auto-reset of BaseEnvironment.step (envs/base.py:27-38) on the device.  The host prepares n_pool reset_env draws per environment
+ * (state24 [n_pool][E][24], time [n_pool][E], pos_traj / vel_traj [n_pool][E][T][3]: envs/quadrotor.py:265-312 with its own key
+ * schedule); from then on covo_env_step / covo_closed_loop replace the state of an environment whose PRE-step state was terminal by
+ * its next pool entry (round robin), overwrite its reference trajectory in place, and -- when a_mean_init [4H] is given -- put the
+ * controller's resident mean back to it, which is what the reference's harness does after `done` (envs/quadrotor.py:637-639:
+ * controller.reset returns the initial parameters).  n_pool == 0 switches it off.  Not for covo-offline (schedule per episode). */
+int covo_env_set_reset_pool(covo_handle* h, int n_pool, const float* state24, const int* time, const float* pos_traj, const float* vel_traj,
+                            const float* a_mean_init);
 /* Which optimize_sigma (controllers/covo.py:116-132) kernels the handle runs:
  *   0 = tridiagonal path (default): Householder -> tridiagonal matrix function in float64 -> Q F Q^T.  Sigma within 1e-6 .. 1e-5
  *       (relative Frobenius) of exact arithmetic on the same float32 Hessian: the accuracy of the reference's float32 eigh.

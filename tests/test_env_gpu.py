@@ -208,3 +208,66 @@ def test_pid_controller_matches_the_reference_source():
     ctl_r, cp_r = cm.get_controller(env, "random")
     a_r, _, _ = ctl_r(None, st, env.default_params, cm.jaxrng.PRNGKey(0), cp_r, None)
     assert a_r.shape == (4,) and np.allclose(a_r, 0.3 * cm.jaxrng.normal(cm.jaxrng.PRNGKey(0), (4,)))
+
+
+def test_auto_reset_on_device():
+    """BaseEnvironment.step's auto-reset (envs/base.py:27-38) on the device: when the PRE-step state is terminal (here: time >= a
+    shortened max_steps_in_episode, and one environment flown out of the |pos| <= 3 box), the stepped state is discarded, the
+    environment continues from its next reset-pool entry with that entry's reference trajectory, and the controller's mean goes back
+    to its initial value (what render_env's controller.reset does after `done`, envs/quadrotor.py:637-639)."""
+    import dataclasses
+
+    from covo_mpc_b200 import _lib
+
+    E, H, P, steps = 2, 6, 2, 17
+    scen = [scenario("tracking_zigzag", seed=60 + e, H=H, warm_steps=2) for e in range(E)]
+    p = dataclasses.replace(scen[0][0], max_steps_in_episode=4)
+    T = scen[0][1].pos_traj.shape[0]
+    cfg = _lib.default_config()
+    cfg.mode, cfg.n_samples, cfg.horizon, cfg.traj_len, cfg.n_env, cfg.max_steps_in_episode = _lib.MODE_MPPI, 64, H, T, E, 4
+    h = _lib.Handle(cfg)
+    h.set_reference(np.stack([s[1].pos_traj for s in scen]), np.stack([s[1].vel_traj for s in scen]))
+    states = [s[1].copy() for s in scen]
+    for s in states:
+        s.time = 1
+    states[1].pos = [np.float32(2.9), np.float32(0.0), np.float32(0.0)]
+    states[1].vel = [np.float32(8.0), np.float32(0.0), np.float32(0.0)]  # leaves the box after one step
+    pool = [[scenario("tracking_zigzag", seed=80 + 7 * k + e, H=H, warm_steps=0)[1] for e in range(E)] for k in range(P)]
+    for k in range(P):
+        for e in range(E):
+            pool[k][e].time = 0
+    mean_init = o.hover_mean(H, p)
+    h.set_mean(np.stack([mean_init + 0.1 * (e + 1) for e in range(E)]))
+    h.env_set_reset_pool(np.stack([[o.state_to_vec24(pool[k][e]) for e in range(E)] for k in range(P)]),
+                         np.zeros((P, E), np.int32),
+                         np.stack([[pool[k][e].pos_traj for e in range(E)] for k in range(P)]),
+                         np.stack([[pool[k][e].vel_traj for e in range(E)] for k in range(P)]), mean_init)
+    h.env_reset(np.stack([o.state_to_vec24(s) for s in states]), [s.time for s in states])
+    rng = np.random.default_rng(5)
+    count = [0] * E
+    n_resets = 0
+    for step in range(steps):
+        act = rng.uniform(-0.5, 0.5, size=(E, 4)).astype(np.float32)
+        z = rng.standard_normal((E, 16)).astype(np.float32)
+        noisy, rew, err, done = h.env_step(act, noise=z)
+        s24, tm = h.env_state()
+        for e in range(E):
+            srng = SeqRng([float(x) for x in z[e, :13]])
+            nxt, r_o, d_o, e_o = o.env_step(states[e], act[e], p, srng, "none")
+            assert bool(done[e]) == d_o and abs(rew[e] - r_o) < 2e-6 * max(1.0, abs(r_o))
+            if d_o:
+                nxt = pool[count[e] % P][e].copy()
+                count[e] += 1
+                n_resets += 1
+                assert np.array_equal(h.get_mean()[e].reshape(H, 4), mean_init)
+            ns_o = o.noisy_state(nxt, p, srng)
+            assert np.abs(s24[e] - o.state_to_vec24(nxt)).max() < 3e-6 and tm[e] == nxt.time, (step, e)
+            assert np.abs(noisy[e] - o.state_to_vec24(ns_o)).max() < 3e-6
+            states[e] = nxt
+    assert n_resets >= 6 and count[1] >= 3  # both environments went through the pool more than once (round robin)
+    # switched off again: a terminal pre-step state is reported but nothing is replaced
+    h.env_set_reset_pool(None, None, None, None)
+    for step in range(5):
+        noisy, rew, err, done = h.env_step(np.zeros((E, 4), np.float32), noise=np.zeros((E, 16), np.float32))
+    assert done.all() and (h.env_state()[1] >= 4).all()
+    h.close()

@@ -289,3 +289,36 @@ def test_tiny_horizons_merge_scratch(mode_name, N, H):
     new_o, _ = o.softmax_update(o.shift_mean(a_mean), samples[0], cost_o, 0.01, 0.7)
     assert np.abs(a_out[0] - new_o).max() < 2e-5
     h.close()
+
+
+@pytest.mark.parametrize("gamma_sigma,lam", [(0.3, 0.5), (0.1, 0.01)])
+def test_mppi_covariance_update(gamma_sigma, lam):
+    """MPPI with gamma_sigma != 0 (controllers/mppi.py:119-125): the per-step 4 x 4 covariances follow the weighted second moments of
+    the clipped samples about the UPDATED mean, blended with the shifted covariance the samples were drawn from; the next step samples
+    from their Cholesky factors.  Three consecutive steps against the oracle on identical eps (lam = 0.5: many samples carry weight;
+    lam = 0.01 with a small gamma: the arg-min regime, the blend keeps the covariance positive definite)."""
+    from covo_mpc_b200 import _lib
+
+    N, H = 512, 12
+    p, ns, a_mean, rng = scenario("tracking_zigzag", seed=9, H=H, warm_steps=10)
+    cfg = _lib.default_config()
+    cfg.mode, cfg.n_samples, cfg.horizon, cfg.traj_len, cfg.lam = _lib.MODE_MPPI, N, H, ns.pos_traj.shape[0], lam
+    cfg.gamma_sigma = gamma_sigma
+    h = _lib.Handle(cfg)
+    h.set_reference(ns.pos_traj[None], ns.vel_traj[None])
+    h.set_mean(a_mean[None])
+    cov = np.tile(0.25 * np.eye(4, dtype=np.float32), (H, 1, 1))
+    mean = a_mean.copy()
+    for step in range(3):
+        eps = rng.standard_normal((N, H, 4)).astype(np.float32)
+        act = h.step(o.state_to_vec24(ns), [ns.time], eps.reshape(1, N, 4 * H))[0]
+        u_o, mean, cov, _ = o.mppi_call(ns, mean, cov, eps, p, lam=lam, gamma_sigma=gamma_sigma)
+        cov_d = h.get_cov()[0].reshape(H, 4, 4)
+        tol = 2e-5 if lam > 0.1 else 1e-4  # lam = 0.01: d w / d cost = w (1 - w) / lam amplifies the float32 cost rounding (carried over the steps)
+        assert np.abs(act - u_o).max() < tol, step
+        assert np.abs(h.get_mean()[0].reshape(H, 4) - mean).max() < tol, step
+        assert np.abs(cov_d - cov).max() < tol * max(1.0, np.abs(cov).max()), step
+        assert np.array_equal(cov_d, cov_d.transpose(0, 2, 1))
+        assert (h.status() == 0).all()
+    assert np.abs(cov - 0.25 * np.eye(4)).max() > 1e-3  # the update did something
+    h.close()
