@@ -252,6 +252,7 @@ struct covo_handle {
         const int* tm_d = nullptr;
         float* act_d = nullptr;
         bool valid = false;
+        bool zero_copy = false;
     };
     StepGraph g_dev, g_host, g_loop;
     bool graphs_enabled = true;
@@ -265,6 +266,19 @@ struct covo_handle {
     int* h_time = nullptr;
     float* h_action = nullptr;
     int* h_status = nullptr;
+    // The staging buffers are MAPPED pinned memory.  In the replayed graph of covo_step the kernels read the state / time straight
+    // through these device aliases (zero-copy over PCIe: 100 bytes), the last node stores the action and the status words there and
+    // raises h_flag to the step number, and the host spins on h_flag instead of synchronising the stream: no copy nodes, no wake-up
+    // through the driver.
+    float* dh_state = nullptr;
+    int* dh_time = nullptr;
+    float* dh_action = nullptr;
+    int* dh_status = nullptr;
+    unsigned int* h_flag = nullptr;
+    unsigned int* dh_flag = nullptr;
+    unsigned int host_epoch = 0;  // value the flag will hold when the step in flight is complete
+    bool zero_copy = true;
+    bool flag_pending = false;  // the step in flight signals its completion through h_flag
 };
 
 
@@ -296,6 +310,7 @@ void release_all(covo_handle* h) {
     if (h->h_time) cudaFreeHost(h->h_time);
     if (h->h_action) cudaFreeHost(h->h_action);
     if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->h_flag) cudaFreeHost(h->h_flag);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -581,14 +596,21 @@ int graph_build(covo_handle* h, covo_handle::StepGraph* sg, const float* st_d, c
     int rc = COVO_OK;
     cudaError_t ce = cudaSuccess;
     const size_t E = (size_t)h->E;
-    if (kind == 1) {  // covo_step: pinned staging -> device
+    const bool zc = kind == 1 && h->zero_copy;
+    if (kind == 1 && !zc) {  // covo_step: pinned staging -> device
         ce = cudaMemcpyAsync(h->state24.p, h->h_state, E * kStateFloats * sizeof(float), cudaMemcpyHostToDevice, cs);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->time.p, h->h_time, E * sizeof(int), cudaMemcpyHostToDevice, cs);
     }
+    if (zc) {  // the kernels read the staged state / time through the device aliases of the pinned buffers; the last node hands the result back
+        st_d = h->dh_state;
+        tm_d = h->dh_time;
+    }
     if (ce == cudaSuccess) rc = step_launch(h, st_d, tm_d, nullptr, act_d, cs, finalize, sg);
     if (ce == cudaSuccess && rc == COVO_OK && kind == 2) ce = launch_env_step(h->loop_env_args, cs);
-    if (ce == cudaSuccess && rc == COVO_OK) ce = launch_bump(h->dev_ctr.p, kind == 2 ? h->dev_ctr.p + 1 : nullptr, cs);
-    if (ce == cudaSuccess && rc == COVO_OK && kind == 1) {
+    if (ce == cudaSuccess && rc == COVO_OK)
+        ce = launch_bump(h->dev_ctr.p, kind == 2 ? h->dev_ctr.p + 1 : nullptr, cs, zc && step_has_status(h) ? h->status.p : nullptr, zc ? h->dh_status : nullptr,
+                         (int)E, zc ? h->dh_flag : nullptr, zc ? h->action.p : nullptr, zc ? h->dh_action : nullptr);
+    if (ce == cudaSuccess && rc == COVO_OK && kind == 1 && !zc) {
         ce = cudaMemcpyAsync(h->h_action, h->action.p, E * 4 * sizeof(float), cudaMemcpyDeviceToHost, cs);
         if (ce == cudaSuccess && step_has_status(h))
             ce = cudaMemcpyAsync(h->h_status, h->status.p, E * sizeof(int), cudaMemcpyDeviceToHost, cs);
@@ -614,9 +636,10 @@ int graph_build(covo_handle* h, covo_handle::StepGraph* sg, const float* st_d, c
         return rc;
     }
     sg->graph = g;
-    sg->st_d = st_d;
-    sg->tm_d = tm_d;
-    sg->act_d = act_d;
+    sg->st_d = zc ? h->state24.p : st_d;  // (the host entry point is recognised by these markers, see step_common)
+    sg->tm_d = zc ? h->time.p : tm_d;
+    sg->act_d = zc ? h->action.p : act_d;
+    sg->zero_copy = zc;
     sg->valid = true;
     return COVO_OK;
 }
@@ -658,6 +681,8 @@ int step_common(covo_handle* h, const float* st_d, const int* tm_d, const float*
         h->rng_stream += 1;
         h->rng_ctr_shadow += 1;
         h->have_factor = true;
+        h->flag_pending = sg->zero_copy;
+        if (sg->zero_copy) h->host_epoch = h->rng_stream;  // the counter kernel raises the flag to the new step number
         return COVO_OK;
     }
     const bool host_io = (st_d == h->state24.p && act_d == h->action.p && finalize == 1);
@@ -842,10 +867,22 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
             A(h2d(h, h->zolo.p, tab.data(), tab.size() * sizeof(double)));
         }
     }
-    A(cudaMallocHost(&h->h_state, E * kStateFloats * sizeof(float)));
-    A(cudaMallocHost(&h->h_time, E * sizeof(int)));
-    A(cudaMallocHost(&h->h_action, E * 4 * sizeof(float)));
-    A(cudaMallocHost(&h->h_status, E * sizeof(int)));
+    A(cudaHostAlloc(&h->h_state, E * kStateFloats * sizeof(float), cudaHostAllocMapped));
+    A(cudaHostAlloc(&h->h_time, E * sizeof(int), cudaHostAllocMapped));
+    A(cudaHostAlloc(&h->h_action, E * 4 * sizeof(float), cudaHostAllocMapped));
+    A(cudaHostAlloc(&h->h_status, E * sizeof(int), cudaHostAllocMapped));
+    A(cudaHostAlloc(&h->h_flag, sizeof(unsigned int), cudaHostAllocMapped));
+    if (e == cudaSuccess) {
+        *h->h_flag = 0u;
+        memset(h->h_status, 0, E * sizeof(int));
+        A(cudaHostGetDevicePointer((void**)&h->dh_state, h->h_state, 0));
+        A(cudaHostGetDevicePointer((void**)&h->dh_time, h->h_time, 0));
+        A(cudaHostGetDevicePointer((void**)&h->dh_action, h->h_action, 0));
+        A(cudaHostGetDevicePointer((void**)&h->dh_status, h->h_status, 0));
+        A(cudaHostGetDevicePointer((void**)&h->dh_flag, h->h_flag, 0));
+        const char* zc = getenv("COVO_ZEROCOPY");
+        h->zero_copy = !(zc && zc[0] == '0');
+    }
     if (e != cudaSuccess) {
         release_all(h);
         delete h;
@@ -1411,9 +1448,29 @@ int covo_step(covo_handle* h, const float* state24, const int* time, const float
         eps_d = h->eps.p;
     }
     // pinned staging -> device, the kernels, device -> pinned staging: one CUDA graph (or the same sequence launched directly)
+    h->flag_pending = false;
     int rc = step_common(h, h->state24.p, h->time.p, eps_d, h->action.p, st, 1);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(st));
+    if (h->flag_pending) {
+        // zero-copy graph: spin on the flag the last node raises (mapped pinned memory); look at the stream now and then so that a
+        // failed kernel surfaces as an error instead of an endless wait
+        volatile unsigned int* flag = h->h_flag;
+        unsigned int spins = 0;
+        while (*flag != h->host_epoch) {
+            if ((++spins & 0x3fffu) == 0u) {
+                cudaError_t q = cudaStreamQuery(st);
+                if (q != cudaErrorNotReady) {
+                    CK(q);
+                    if (*flag == h->host_epoch) break;
+                    return fail(COVO_ERR_CUDA, "covo_step: the step completed without raising its completion flag");
+                }
+            }
+        }
+        __sync_synchronize();
+        h->flag_pending = false;
+    } else {
+        CK(cudaStreamSynchronize(st));
+    }
     memcpy(action, h->h_action, (size_t)h->E * 4 * sizeof(float));
     if (step_has_status(h))  // the covariance step of THIS call (its first kernel clears the status)
         for (int e = 0; e < h->E; ++e)

@@ -105,13 +105,31 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvStepArgs a) {
     a.noisy_time[e] = t;
 }
 
-__global__ void bump_kernel(unsigned int* ctr_a, unsigned int* ctr_b) {
-    if (ctr_a) *ctr_a += 1u;
+// Last node of a replayed step: advances the device step counters and -- for the host entry point -- hands the result over without
+// a copy node or a stream synchronisation: the actions and the status words go to mapped pinned memory and, behind a system-scope
+// fence in the same thread, the flag the host spins on is raised to the new step number.
+__global__ void bump_kernel(unsigned int* ctr_a, unsigned int* ctr_b, const int* status_src, int* status_dst, int n_status, unsigned int* flag,
+                            const float* action_src, float* action_dst) {
+    unsigned int v = 0u;
+    if (ctr_a) {
+        v = *ctr_a + 1u;
+        *ctr_a = v;
+    }
     if (ctr_b) *ctr_b += 1u;
+    if (flag) {
+        for (int e = 0; e < n_status; ++e) {
+            if (status_dst) status_dst[e] = status_src ? status_src[e] : 0;
+            if (action_dst)
+                for (int k = 0; k < 4; ++k) action_dst[4 * e + k] = action_src[4 * e + k];
+        }
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int*>(flag) = v;
+    }
 }
 
-cudaError_t launch_bump(unsigned int* ctr_a, unsigned int* ctr_b, cudaStream_t st) {
-    bump_kernel<<<1, 1, 0, st>>>(ctr_a, ctr_b);
+cudaError_t launch_bump(unsigned int* ctr_a, unsigned int* ctr_b, cudaStream_t st, const int* status_src, int* status_dst, int n_status,
+                        unsigned int* flag, const float* action_src, float* action_dst) {
+    bump_kernel<<<1, 1, 0, st>>>(ctr_a, ctr_b, status_src, status_dst, n_status, flag, action_src, action_dst);
     return cudaGetLastError();
 }
 

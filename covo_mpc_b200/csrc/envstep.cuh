@@ -50,7 +50,8 @@ struct EnvStepArgs {
 };
 
 // one thread: advances the device step counters at the end of a replayed step
-cudaError_t launch_bump(unsigned int* ctr_a, unsigned int* ctr_b, cudaStream_t st);
+cudaError_t launch_bump(unsigned int* ctr_a, unsigned int* ctr_b, cudaStream_t st, const int* status_src = nullptr, int* status_dst = nullptr,
+                        int n_status = 0, unsigned int* flag = nullptr, const float* action_src = nullptr, float* action_dst = nullptr);
 
 cudaError_t launch_env_step(const EnvStepArgs& a, cudaStream_t st);
 
