@@ -530,6 +530,9 @@ def run_gpu(args):
     if not args.no_subrecords:
         h.close()
         Ks = min(K, 100)
+        if world > 1:  # config 4 is ONE environment: every rank holds rank 0's states and reference (the replica run above has one per rank)
+            s0_h, t0_h, trajs0, _ = synthetic_states(n_states, 100)
+            states, times, traj = torch.from_numpy(s0_h).to(dev), torch.from_numpy(t0_h).to(dev), trajs0[0]
         out["nsample_shard"] = {
             "workload": f"covo-offline {TASK} H={HORIZON}, the N samples of ONE environment split over {world} rank(s) (BASELINE config 4)",
             "N8192": bench_nsample_shard(dist, world, rank, dev, states, times, traj, Ks, W, flush, 8192),
