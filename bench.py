@@ -90,6 +90,9 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def n_samples(self) -> int:
+        return len(self.lines) if self.proc is not None else 1 << 30
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -382,6 +385,15 @@ def run_gpu(args):
         ev[i][1].record()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
+    # nvidia-smi needs a few hundred ms to deliver its first line (longer on an 8-GPU box) and K steps can be over before that: keep the
+    # same load running, untimed, until two clock samples have been taken under it
+    t_lim, j = time.perf_counter() + 4.0, 0
+    while sampler.n_samples() < 2 and time.perf_counter() < t_lim:
+        for _ in range(50):
+            flush.zero_()
+            one_step(W + (j % K))
+            j += 1
+        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
