@@ -60,6 +60,7 @@ _SIGNATURES = {
     "covo_reset_offline": [_H, _F, _I, C.c_int],
     "covo_reset_offline_disturbed": [_H, _F, _I, C.c_int, _F],
     "covo_step": [_H, _F, _I, _F, _F],
+    "covo_set_rollout_disturbance": [_H, _F],
     "covo_set_env_params": [_H, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _F, C.c_int],
     "covo_step_device": [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "covo_step_partial_device": [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
@@ -235,6 +236,16 @@ class Handle:
         out = np.empty((self.E, 4), dtype=np.float32)
         check(self.lib.covo_pid_action(self._h, fptr(s), iptr(t), Kp, Kd, Ki, Kp_att, fptr(g), fptr(out)))
         return out
+
+    def set_rollout_disturbance(self, fdist_seq):
+        """MPPI, disturb_type gaussian (mppi.py:74): fdist_seq [E][H][3] = the force the rollouts see after step h; None: off."""
+        if fdist_seq is None:
+            check(self.lib.covo_set_rollout_disturbance(self._h, None))
+            return
+        f = f32(fdist_seq)
+        if f.size != self.E * self.H * 3:
+            raise ValueError("fdist_seq must be [E][H][3]")
+        check(self.lib.covo_set_rollout_disturbance(self._h, fptr(f)))
 
     def reset_offline(self, state24, time, t_sched: int, f_disturb=None):
         """f_disturb [t_sched][3]: the gaussian disturbance force after every path step (covo_reset_offline_disturbed); None: none."""

@@ -145,10 +145,22 @@ class _SamplingController(BaseController):
         self._generation = 0
         self._env_params_seen = None
         self.want_info = False  # pos_mean / pos_std (covo.py:281) are computed only on request
+        self._noise_rng = None
+        self._fdist_set = False
 
     # -- plumbing ---------------------------------------------------------------------------------------
+    def _sync_control_consts(self, control_params):
+        """gamma_mean / gamma_sigma / discount / sample_sigma are fields of control_params in the reference and read at CALL time
+        (covo.py:270-278, mppi.py:100-125): a caller that passes cp.replace(gamma_sigma=0.3) gets a handle configured that way."""
+        vals = tuple(float(getattr(control_params, f)) for f in ("gamma_mean", "gamma_sigma", "discount", "sample_sigma"))
+        cur = (float(self._cfg.gamma_mean), float(self._cfg.gamma_sigma), float(self._cfg.discount), float(self._cfg.sample_sigma))
+        if any(abs(a - b) > 1e-7 * max(1.0, abs(b)) for a, b in zip(vals, cur)):
+            self._cfg.gamma_mean, self._cfg.gamma_sigma, self._cfg.discount, self._cfg.sample_sigma = vals
+            self._cfg_dirty = True
+
     def _ensure_handle(self, traj_len: int) -> _lib.Handle:
-        if self._handle is None or self._cfg.traj_len != traj_len:
+        if self._handle is None or self._cfg.traj_len != traj_len or getattr(self, "_cfg_dirty", False):
+            self._cfg_dirty = False
             carried = None
             if self._handle is not None:
                 # a reference trajectory of another length: the resident controller state moves to the new handle, so that
@@ -258,11 +270,30 @@ class MPPIController(_SamplingController):
 
     def __call__(self, obs, env_state, env_params, rng_act, control_params, info=None):
         state: EnvState3D = info["noisy_state"]  # mppi.py:40
+        self._sync_control_consts(control_params)
         h = self._sync_reference(state)
         self._sync_env_params(env_params)
         self._upload_params(control_params)
         if self.want_info:
             h.enable_pos_stats(True)
+        if getattr(self.env, "disturb_type", "none") == "gaussian":
+            # mppi.py:74 rolls out with a STOCHASTIC step_env, and every sample and horizon step gets the same step_key: one force
+            # dyn_noise_scale * N(0, I)^3 for the whole call.  With a JAX key: rng_act, act_key = split(rng_act) (:53);
+            # rng_act, step_key = split(rng_act) (:69); inside step_env the disturbance key is three splits down (quadrotor.py:262,
+            # dynamics/free.py:136-144).  Without one: the controller's own generator.
+            scale = np.float32((env_params or self.env.default_params).dyn_noise_scale)
+            if jaxrng.is_key(rng_act):
+                step_key = jaxrng.split(jaxrng.split(np.asarray(rng_act, dtype=np.uint32))[0])[1]
+                z = jaxrng.normal(jaxrng.split(jaxrng.split(jaxrng.split(step_key)[1])[0])[0], (3,))
+            else:
+                if self._noise_rng is None:
+                    self._noise_rng = np.random.default_rng(int(self._cfg.seed) + 7919)
+                z = self._noise_rng.standard_normal(3)
+            h.set_rollout_disturbance(np.tile((scale * np.asarray(z, np.float32))[None, None, :], (1, self.H, 1)))
+            self._fdist_set = True
+        elif self._fdist_set:
+            h.set_rollout_disturbance(None)
+            self._fdist_set = False
         eps = self._eps(rng_act, (1, h.n_local, self.H * 4))
         action = h.step_state(state) if eps is None else h.step(state.to_state24(), [state.time], eps)[0]
         return self._finish(control_params, action)
@@ -346,6 +377,7 @@ class CoVOController(_SamplingController):
 
     def __call__(self, obs, env_state, env_params, rng_act, control_params, info=None):
         state: EnvState3D = info["noisy_state"]  # covo.py:198
+        self._sync_control_consts(control_params)
         h = self._sync_reference(state)
         self._sync_env_params(env_params)
         self._upload_params(control_params)

@@ -209,6 +209,7 @@ struct covo_handle {
     float kernel_ms[6] = {0, 0, 0, 0, 0, 0};
     // inputs
     DevBuf<float> state24, pos_traj, vel_traj, acc_traj, a_mean, eps, fdist;
+    bool fdist_on = false;  // MPPI under disturb_type gaussian: the rollouts of the step see the force set by covo_set_rollout_disturbance
     DevBuf<int> time;
     // covariance pipeline
     DevBuf<float> R, Vh, tau, Qt, F, cov, Lfull, Lt, Lblk, hess_ws;
@@ -512,7 +513,8 @@ int step_launch(covo_handle* h, const float* st_d, const int* tm_d, const float*
         for (int i = 1; i <= 5; ++i) pf.mark(i);
     }
     const bool cov_update = mode == COVO_MODE_MPPI && h->cfg.gamma_sigma != 0.f;  // mppi.py:119-125 needs the samples and their costs
-    RolloutArgs ra = rollout_args(h, st_d, tm_d, h->a_mean.p, 1, eps_d, nullptr, h->a_mean.p, act_d, cov_update ? h->costs.p : nullptr,
+    const float* fdist = (mode == COVO_MODE_MPPI && h->fdist_on) ? h->fdist.p : nullptr;  // mppi.py:74: stochastic step_env in the rollouts
+    RolloutArgs ra = rollout_args(h, st_d, tm_d, h->a_mean.p, 1, eps_d, fdist, h->a_mean.p, act_d, cov_update ? h->costs.p : nullptr,
                                   cov_update ? h->samples.p : nullptr, finalize);
     if (pipelined) {
         ra.lfac_progress = h->chol_progress.p;
@@ -1483,6 +1485,26 @@ int covo_step(covo_handle* h, const float* state24, const int* time, const float
                 return fail(COVO_ERR_NUMERIC, "covo_step: numeric status %d in environment %d (%s)", h->h_status[e], e,
                             h->h_status[e] == 1 ? "spectral range of the Hessian exceeds the rational-approximation ladder"
                                                 : "covariance not positive definite in float32");
+    return COVO_OK;
+}
+
+int covo_set_rollout_disturbance(covo_handle* h, const float* fdist_seq) {
+    if (!h) return fail(COVO_ERR_INVALID, "null argument");
+    if (h->cfg.mode != COVO_MODE_MPPI) return fail(COVO_ERR_INVALID, "only MPPI rolls out with a stochastic step_env (mppi.py:74); CoVO's rollouts are deterministic (covo.py:229)");
+    CK(cudaSetDevice(h->cfg.device));
+    const bool on = fdist_seq != nullptr;
+    if (on) {
+        const size_t cnt = (size_t)h->E * h->H * 3;
+        if (h->fdist.n < cnt) {
+            h->fdist.release();
+            CK(h->fdist.alloc(cnt));
+            graphs_invalidate(h);
+        }
+        CK(cudaMemcpyAsync(h->fdist.p, fdist_seq, cnt * sizeof(float), cudaMemcpyHostToDevice, h->own_stream));
+        CK(cudaStreamSynchronize(h->own_stream));
+    }
+    if (on != h->fdist_on) graphs_invalidate(h);  // the rollout node carries the pointer (or its absence)
+    h->fdist_on = on;
     return COVO_OK;
 }
 

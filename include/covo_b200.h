@@ -121,6 +121,12 @@ int covo_step(covo_handle* h, const float* state24, const int* time, const float
  * range left the rational-approximation ladder (1) or a Cholesky pivot was not positive (2) -- where the reference would surface
  * NaNs (controllers/covo.py:116-132, :216); status 3 (dense path only, see covo_set_sigma_path) is not an error.  The asynchronous entry points (covo_step_device, covo_step_partial_device,
  * covo_closed_loop) cannot: their callers poll covo_get_status(). */
+/* MPPI under disturb_type "gaussian" (the reference's default): its rollouts call step_env WITHOUT deterministic=True
+ * (controllers/mppi.py:74), every sample and every horizon step with the same step_key, i.e. all of them see the same force
+ * dyn_noise_scale * N(0, I)^3 from the second step on (dynamics/free.py:66-70, 144-147).  fdist_seq [E][H][3] (host): the force produced
+ * by rollout step h (it acts during step h + 1); used by every following covo_step* of the handle until replaced; NULL switches it off
+ * (disturb_type "none").  CoVO's rollouts are deterministic (controllers/covo.py:229) and do not take one. */
+int covo_set_rollout_disturbance(covo_handle* h, const float* fdist_seq);
 /* The physical model a handle plans with (dynamics/dataclass.py:43-49, 71, 76, 81), replaceable after creation: the reference rolls
  * out and differentiates with the env_params of the CALL (controllers/covo.py:187-283 `env_params`), e.g. a mass sampled by
  * Quad3D.sample_params.  Takes effect with the next launch (the constants travel in the kernel argument blocks). */

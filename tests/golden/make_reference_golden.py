@@ -529,6 +529,27 @@ def main():
                             a_cov_in=np.asarray(cp.a_cov, F), a_cov=np.asarray(cp2.a_cov, F), a_mean_new=np.asarray(cp2.a_mean, F),
                             action=np.asarray(u, F), lam=ctl.lam, N=ctl.N, H=ctl.H)
 
+    # ---- 10b. MPPI behaviours beyond the defaults, executed from the reference with a PRNGKey ------------------------------------
+    #  * disturb_type "gaussian" (the reference's default): the rollouts call step_env WITHOUT deterministic=True (mppi.py:74), every
+    #    sample and horizon step with the same step_key -> one shared random force for the whole call;
+    #  * gamma_sigma != 0: the per-step covariance update of mppi.py:119-125.
+    env_g = Quad3D(task="tracking_zigzag", obs_type="quad", lower_controller="base", enable_randomizer=False, disturb_type="gaussian",
+                   disable_rollover_terminate=True, generate_noisy_state=True)
+    env_g.get_obs = lambda *a, **k: None
+    for tag, e_, gs, seed in (("gaussian", env_g, 0.0, 23), ("gamma_sigma", env, 0.3, 24)):
+        ctl, cp = get_controller(e_, "mppi", "N128_H8_lam0.5" if gs else "N128_H8_lam0.01")
+        pp, ns_, a_prev, _ = scenario("tracking_zigzag", seed=seed, H=ctl.H, warm_steps=5, zero_disturb=False)
+        a_prev = np.clip(np.asarray(a_prev, F), -0.9, 0.9)
+        st = to_ref_state(ns_)
+        key = jr.PRNGKey(1000 + seed)
+        cp_in = cp.replace(a_mean=a_prev, gamma_sigma=gs)
+        u, cp2, info = ctl(None, st, params, key, cp_in, {"noisy_state": st})
+        np.savez_compressed(os.path.join(out_dir, f"reference_call_mppi_keyed_{tag}.npz"), state24=vec24(st), time=int(st.time),
+                            pos_traj=np.asarray(st.pos_traj, F), vel_traj=np.asarray(st.vel_traj, F), a_mean=a_prev, rng_act=key,
+                            a_cov_in=np.asarray(cp.a_cov, F), a_cov=np.asarray(cp2.a_cov, F), a_mean_new=np.asarray(cp2.a_mean, F),
+                            action=np.asarray(u, F), lam=ctl.lam, N=ctl.N, H=ctl.H, gamma_sigma=gs,
+                            dyn_noise_scale=float(params.dyn_noise_scale))
+
     # ---- 11. the whole evaluation protocol: eval_env executed from the reference (envs/quadrotor.py:506-591) -------------------
     # Controller = the reference's RandomController (0.3 * normal(rng_act, (4,))): CPU-only, and wild enough to fly out of the
     # |pos| <= 3 box, so BaseEnvironment.step's auto-reset (base.py:27-38) is exercised.  Pins the key schedule of the

@@ -132,3 +132,31 @@ def test_same_key_in_same_action_out(name):
     assert np.abs(np.asarray(cp2.a_mean) - g["a_mean_new"]).max() < 2e-4
     if name != "mppi":
         assert np.linalg.norm(np.asarray(cp2.a_cov) - g["a_cov"]) / np.linalg.norm(g["a_cov"]) < 5e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["gaussian", "gamma_sigma"])
+def test_mppi_beyond_the_defaults_same_key_in_same_action_out(tag):
+    """MPPIController.__call__ executed from the reference's source with a PRNGKey (tests/golden/make_reference_golden.py, section 10b)
+    vs the product handed the same key:
+      * gaussian (the reference's default disturb_type): the rollouts run a STOCHASTIC step_env with one step_key for every sample and
+        horizon step (mppi.py:74) -- the controller derives that force from the key and hands it to the rollout kernel;
+      * gamma_sigma = 0.3 passed at CALL time: the covariance update of mppi.py:119-125."""
+    import covo_mpc_b200 as cm
+
+    g = np.load(os.path.join(HERE, "golden", f"reference_call_mppi_keyed_{tag}.npz"))
+    N, H = int(g["N"]), int(g["H"])
+    env = cm.Quad3D("tracking_zigzag", disturb_type="gaussian" if tag == "gaussian" else "none")
+    ctl, cp = cm.get_controller(env, "mppi", f"N{N}_H{H}_lam{float(g['lam'])}")
+    s = g["state24"]
+    z3 = np.zeros(3, np.float32)
+    st = cm.EnvState3D(pos=s[0:3], quat=s[3:7], vel=s[7:10], omega=s[10:13], f_disturb=s[13:16], pos_tar=s[16:19], vel_tar=s[19:22],
+                       acc_tar=z3, pos_traj=g["pos_traj"], vel_traj=g["vel_traj"], acc_traj=np.zeros_like(g["pos_traj"]), time=int(g["time"]))
+    cp_in = cp.replace(a_mean=g["a_mean"], gamma_sigma=float(g["gamma_sigma"]))
+    action, cp2, _ = ctl(None, st, env.default_params, g["rng_act"], cp_in, {"noisy_state": st})
+    assert np.abs(np.asarray(action) - g["action"]).max() < 2e-4
+    assert np.abs(np.asarray(cp2.a_mean) - g["a_mean_new"]).max() < 2e-4
+    assert np.abs(np.asarray(cp2.a_cov).reshape(H, 4, 4) - g["a_cov"]).max() < 2e-4
+    if tag == "gamma_sigma":
+        assert np.abs(g["a_cov"] - g["a_cov_in"]).max() > 1e-3  # the reference did update the covariance
+    ctl.close()

@@ -143,3 +143,24 @@ def test_keyed_call_matches_the_reference_source(name):
         u, new_mean, a_cov, _ = o.covo_call(_call_state(g), g["a_mean"], jr.covo_normals(act_key, N, 4 * H), o.EnvParams(), lam=float(g["lam"]))
         assert np.linalg.norm(a_cov - g["a_cov"]) / np.linalg.norm(g["a_cov"]) < 2e-5
     assert np.abs(new_mean - g["a_mean_new"]).max() < 2e-5 and np.abs(u - g["action"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("tag", ["gaussian", "gamma_sigma"])
+def test_mppi_beyond_the_defaults_matches_the_reference_source(tag):
+    """Generator section 10b: MPPI under disturb_type gaussian (stochastic rollouts, one step_key for every sample and horizon step:
+    mppi.py:69-74) and with gamma_sigma = 0.3 (covariance update, mppi.py:119-125), both executed from the reference with a PRNGKey.
+    The oracle, fed the normals and the force that key produces, lands on the same update."""
+    from covo_mpc_b200 import jaxrng as jr
+
+    g = np.load(os.path.join(G, f"reference_call_mppi_keyed_{tag}.npz"))
+    N, H = int(g["N"]), int(g["H"])
+    rng_act, act_key = jr.split(g["rng_act"])        # mppi.py:53
+    step_key = jr.split(rng_act)[1]                   # mppi.py:69
+    fd = None
+    if tag == "gaussian":  # step_env -> raw_step -> step_fn: the disturbance key is three splits down (quadrotor.py:262, free.py:136-144)
+        z = jr.normal(jr.split(jr.split(jr.split(step_key)[1])[0])[0], (3,))
+        fd = np.tile((np.float32(g["dyn_noise_scale"]) * z)[None], (H, 1)).astype(np.float32)
+    u, new_mean, new_cov, _ = o.mppi_call(_call_state(g), g["a_mean"], g["a_cov_in"], jr.mppi_normals(act_key, N, H), o.EnvParams(),
+                                          lam=float(g["lam"]), gamma_sigma=float(g["gamma_sigma"]), f_disturb_seq=fd)
+    assert np.abs(new_mean - g["a_mean_new"]).max() < 2e-5 and np.abs(u - g["action"]).max() < 2e-5
+    assert np.abs(new_cov - g["a_cov"]).max() < 2e-5

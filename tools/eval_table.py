@@ -41,7 +41,7 @@ def main():
     ap.add_argument("--ablation", action="store_true", help="also the N ablation of scripts/covo_quadrotor_N.sh (subset)")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
-    names = ("mppi", "covo-online", "covo-offline") if a.disturb == "none" else ("mppi", "covo-online")  # the offline schedule is built for 'none' only
+    names = ("mppi", "covo-online", "covo-offline")
     recs = [run(a.task, c, a.N, a.H, a.lam, a.episodes, a.disturb) for c in names]
     base = recs[0]["err_pos_mean_cm"]
     summary = {"summary": "improvement over mppi = 1 - err/err_mppi",
