@@ -1213,6 +1213,10 @@ static EnvStepArgs env_args(covo_handle* h, int gaussian, float obs_scale, float
     a.reward = nullptr;
     a.err_pos = nullptr;
     a.done = nullptr;
+    if (gaussian && h->cfg.mode == COVO_MODE_MPPI && h->fdist.p && h->fdist_on) {
+        a.mppi_fdist = h->fdist.p;
+        a.mppi_H = h->H;
+    }
     if (h->pool_n > 0) {
         a.reset_pool = h->pool_n;
         a.reset_state24 = h->pool_state24.p;
@@ -1351,6 +1355,17 @@ int covo_closed_loop(covo_handle* h, int n_steps, unsigned long long noise_seed,
             CK(h->env_noise.alloc(cnt));
         }
         CK(h2d(h, h->env_noise.p, noise, cnt * sizeof(float)));
+    }
+    if (h->cfg.mode == COVO_MODE_MPPI) {
+        // mppi.py:74 under gaussian: the rollouts of every call see one random force; the environment kernel draws it for the next call
+        const bool want = gaussian != 0;
+        if (want && h->fdist.n < E * h->H * 3) {
+            h->fdist.release();
+            CK(h->fdist.alloc(E * h->H * 3));
+            graphs_invalidate(h);
+        }
+        if (want != h->fdist_on) graphs_invalidate(h);
+        h->fdist_on = want;
     }
     EnvStepArgs a = env_args(h, gaussian, obs_noise_scale, dyn_noise_scale, noise_seed);
     // the noisy copy of the initial state (quadrotor.py:366-370: reset_env ends with get_info)

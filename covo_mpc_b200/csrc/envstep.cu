@@ -91,6 +91,13 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvStepArgs a) {
         for (int k = 0; k < 3; ++k) sg[19 + k] = vt[k];
         a.time[e] = t;
     }
+    if (a.mppi_fdist) {  // planning force of the next MPPI call: its own block of the noise field (never the caller-supplied normals)
+        float zp[4];
+        philox_normal4(a.seed, a.stream + step, (uint32_t)e, 4u, zp);
+        float* fo = a.mppi_fdist + (long long)e * a.mppi_H * 3;
+        for (int hh = 0; hh < a.mppi_H; ++hh)
+            for (int k = 0; k < 3; ++k) fo[hh * 3 + k] = a.dyn_noise_scale * zp[k];
+    }
     // info["noisy_state"] (envs/quadrotor.py:323-351)
     float* ng = a.noisy24 + (long long)e * kStateFloats;
     const float sc = a.obs_noise_scale;

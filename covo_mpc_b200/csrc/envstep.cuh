@@ -36,6 +36,10 @@ struct EnvStepArgs {
     // trajectory), the trajectory tables are overwritten in place (the controller kernels read the same buffers), and -- what the
     // reference's harness does next (envs/quadrotor.py:637-639: controller.reset returns the initial parameters) -- the
     // controller's resident mean goes back to its initial value.  reset_pool == 0: no auto-reset (episodes bounded by the caller).
+    // MPPI under disturb_type gaussian (mppi.py:74): the force the NEXT controller call's rollouts see (one draw per call, shared by all
+    // samples and horizon steps), written here so that the device-resident loop needs no host draw: [E][mppi_H][3]
+    float* mppi_fdist = nullptr;
+    int mppi_H = 0;
     int reset_pool = 0;
     const float* reset_state24 = nullptr;  // [P][E][24]
     const int* reset_time = nullptr;       // [P][E]

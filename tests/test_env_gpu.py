@@ -58,13 +58,16 @@ def test_env_step_matches_oracle(disturb):
             states[e] = nxt
 
 
-@pytest.mark.parametrize("mode_name", ["mppi", "covo-online"])
+@pytest.mark.parametrize("mode_name", ["mppi", "covo-online", "mppi-gaussian"])
 def test_closed_loop_on_device_equals_step_by_step(mode_name):
     """covo_closed_loop (no host round trip) == the same handle type driven one call at a time through
-    covo_env_step + covo_step with the same seeds: identical kernels, so the actions agree bit for bit."""
+    covo_env_step + covo_step with the same seeds: identical kernels, so the actions agree bit for bit.
+    mppi-gaussian: disturb_type gaussian -- the environment's force comes from the supplied normals, and the force MPPI's rollouts plan
+    against (mppi.py:74, one draw per call) is written by the environment kernel for the next controller call in both loops."""
     from covo_mpc_b200 import _lib
 
-    mode = _lib.MODE_MPPI if mode_name == "mppi" else _lib.MODE_COVO_ONLINE
+    gauss = mode_name.endswith("gaussian")
+    mode = _lib.MODE_MPPI if mode_name.startswith("mppi") else _lib.MODE_COVO_ONLINE
     N, H, steps = 256, 10, 6
     p, ns, a_mean, rng = scenario("tracking_zigzag", seed=9, H=H, warm_steps=4)
     T = ns.pos_traj.shape[0]
@@ -78,20 +81,26 @@ def test_closed_loop_on_device_equals_step_by_step(mode_name):
         return h
 
     ha = mk()
-    act_a, rew_a, err_a = ha.closed_loop(steps, noise=noise)
+    act_a, rew_a, err_a = ha.closed_loop(steps, noise=noise, gaussian=gauss)
     hb = mk()
-    noisy, _, _, _ = hb.env_step(None, noise=noise[0])
+    if gauss:
+        hb.set_rollout_disturbance(np.zeros((1, H, 3), np.float32))  # switches the planning force on; the kernel overwrites it
+    noisy, _, _, _ = hb.env_step(None, noise=noise[0], noise_step=0, gaussian=gauss)
     _, tm = hb.env_state()
     for i in range(steps):
         a = hb.step(noisy, tm)
         assert np.array_equal(a, act_a[i])
-        noisy, rew, err, _ = hb.env_step(a, noise=noise[i + 1])
+        noisy, rew, err, _ = hb.env_step(a, noise=noise[i + 1], noise_step=i + 1, gaussian=gauss)
         _, tm = hb.env_state()
         assert rew[0] == rew_a[i, 0] and err[0] == err_a[i, 0]
     sa, ta = ha.env_state()
     sb, tb = hb.env_state()
     assert np.array_equal(sa, sb) and np.array_equal(ta, tb)
     assert np.isfinite(act_a).all() and np.abs(act_a).max() <= 1.0 + 1e-6
+    if gauss:  # the planning force does something: the same loop without it takes other actions
+        hc = mk()
+        act_c, _, _ = hc.closed_loop(steps, noise=noise, gaussian=False)
+        assert not np.array_equal(act_c, act_a)
 
 
 def test_run_episode_device_tracks_like_the_host_loop():
