@@ -1,6 +1,6 @@
 // optimize_sigma (controllers/covo.py:116-132) WITHOUT an eigen-decomposition ("D1-D3").  Default for single
 // environments since round 2 (COVO_SIGMA=tridiag selects the tridiagonal path E1-E3 of sigma.cu); tools/study_dense_sigma.py and
-// scratch/lanczos_k_needed.py are the numerical studies behind it.  The reference computes
+// tools/studies/lanczos_k_needed.py are the numerical studies behind it.  The reference computes
 //     Sigma = U diag(s) U^T,  s_k = exp(c/2) / sqrt(o_k),  o_k = lambda_k - lambda_min + 1e-2,  c = (4 n log sigma + sum log o_k) / n
 // which is  Sigma = exp(c/2) * A^(-1/2)  with  A = (R + R^T)/2 - lambda_min I + 1e-2 I  and  sum log o_k = log det A.
 // So only lambda_min, log det A and the matrix function A^(-1/2) are needed:
@@ -157,7 +157,7 @@ __device__ __forceinline__ float gjb_rcp(float x) {
 //
 // How many steps: the smallest Ritz value must be within << 1e-2 * 2e-5 = 2e-7 ABSOLUTE of lambda_min (the offset 1e-2 of
 // controllers/covo.py:121 sets the scale, not |R| ~ 1e3), and the number of steps that takes depends on the Hessian: along closed
-// loops (scratch/lanczos_k_needed.py) 16 .. 48, with 24 enough for only 56 % of them -- and an unconverged Ritz value 1e-2 above
+// loops (tools/studies/lanczos_k_needed.py) 16 .. 48, with 24 enough for only 56 % of them -- and an unconverged Ritz value 1e-2 above
 // lambda_min makes A indefinite.  So the length is adaptive: a fifth warp per CTA (the CHECKER) follows the recurrence at the
 // checkpoints k = 16, 20, 24, ...: smallest eigenvalue theta of the k x k Lanczos matrix T_k (33-way multisection on Sturm
 // counts, three float32 rounds, then float64 with both bracket ends verified, then Newton from below) and the residual of its
@@ -735,14 +735,14 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // D2 gjb_inverse_kernel: in-place Gauss-Jordan sweep without pivoting (A + t_j I is SPD), BLOCKED (8 pivots per step) and spread over
-// a 2-CTA cluster per pole, the matrix resident in registers.  Sweeping the index block K with P = A_KK:
+// a cluster of GB_CL (4) CTAs per pole, the matrix resident in registers.  Sweeping the index block K with P = A_KK:
 //     A_IJ -= A_IK P^-1 A_KJ,   A_KJ <- P^-1 A_KJ =: G,   A_IK <- -A_IK P^-1,   A_KK <- P^-1.
-// With the sign convention of D2' the matrix is symmetric on the unswept index set and ANTI-symmetric between swept and unswept
+// With this sign convention the matrix is symmetric on the unswept index set and ANTI-symmetric between swept and unswept
 // indices, so the column panel is the row panel again: A_iK = sigma(i) (A_Ki)^T, sigma = -1 for swept i.  Everything a step needs
 // therefore follows from the 8 raw pivot rows (8 x n) alone:
 //     A_ij -= sigma(i) sum_s raw[s][i] G[s][j],    row K_s <- G[s][:],   column K_s <- -sigma(i) G[s][i],   block KK <- P^-1.
 // Roles (640 threads per CTA):
-//   * 16 UPDATE warps hold the matrix: thread (ty = warp, tx = lane) owns rows ty + 16 (rank + 2 a'), a' < 8 (row pairs packed for
+//   * 16 UPDATE warps hold the matrix: thread (ty = warp, tx = lane) owns rows ty + 16 (rank + GB_CL a'), a' < GB_NSLOT (row pairs packed for
 //     FFMA2) and columns tx + 32 b, b < 7.  Per step: 224 FFMA2 per thread against 28 + 16 vector loads.
 //   * 4 SOLVER warps run one block ahead: they wait for the raw rows of block m + 1 (published through distributed shared memory with
 //     st.async, completion counted by an mbarrier -- no fences, no cluster barrier), invert the 8 x 8 pivot block on one warp
@@ -750,8 +750,10 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
 //     are still applying block m.
 //   * look-ahead: after the barrier that opens step m, the warps that own the rows of block m + 1 (one row per warp) apply step m to
 //     that row first (56 FMAs, same operation order as the full update, so the values are bit-identical) and publish it.
-// Flow control: the raw panels live in a ring of 4 slots.  Blocks are owned in pairs (tile = 16 rows = 2 blocks, tiles alternate
-// between the CTAs), so a CTA can run at most 3 blocks ahead of its peer before it needs a panel from it: 4 slots never collide.
+// Flow control: the raw panels live in a ring of 4 slots.  Blocks are owned in pairs (tile = 16 rows = 2 blocks, tiles rotate over
+// the CTAs).  With two CTAs a CTA can run at most 3 blocks ahead of its peer before it needs a panel from it, so 4 slots never
+// collide; with four, a split cluster barrier (arrive after a step is opened, wait before the next one) keeps everybody within one
+// step of everybody else.
 // Cost model at n = 200: 25 steps x max(update 1800 cycles, solver chain ~1600) instead of 200 steps x 1100.
 // ---------------------------------------------------------------------------------------------------------------------------
 #ifndef COVO_GB_CL
@@ -942,7 +944,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                         // position (i, j) holds element (n - 1 - i, n - 1 - j): the sweep eliminates the LAST controls first.  Without
                         // pivoting the order decides the accuracy: the Hessian's large entries belong to the early controls, and
                         // sweeping those first cost up to 8e-3 of Sigma at cond(A) = 1.6e5 (float32); back to front it is 2e-5 .. 8e-5,
-                        // the level of a float32 Cholesky factorisation (scratch/gj_accuracy.py)
+                        // the level of a float32 Cholesky factorisation (tools/studies/gj_accuracy.py)
                         const int ir = n - 1 - i, jr = n - 1 - j;
                         v = Ag ? Ag[(long long)ir * n + jr] : 0.5f * (Rg[(long long)ir * n + jr] + Rg[(long long)jr * n + ir]);
                         if (i == j) v = (float)((double)v + shift);

@@ -1,5 +1,5 @@
 """In-kernel phase breakdown (clock64 stamps of CTA 0) of the tridiagonalisation-free optimize_sigma kernels (csrc/sigma_dense.cu), next
-to the per-kernel CUDA-event times.  Development tool: `COVO_SIGMA=dense-gj python tools/dense_profile.py` on a GPU box."""
+to the per-kernel CUDA-event times.  Development tool: `COVO_SIGMA=dense python tools/dense_profile.py` on a GPU box."""
 import os
 import sys
 
@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("COVO_SIGMA", "dense-gj")
+os.environ.setdefault("COVO_SIGMA", "dense")
 
 import bench  # noqa: E402
 from covo_mpc_b200 import _lib  # noqa: E402

@@ -1,7 +1,7 @@
 """Round-2 feasibility study (CPU, NumPy/SciPy): optimize_sigma without an eigen-decomposition -- lambda_min by Lanczos (fp64
 arithmetic on the fp32 matrix), A^(-1/2) by Zolotarev partial fractions with dense fp32 Cholesky solves, log det A from one more
 factorisation -- against the float64 eigen-decomposition, across tasks / horizons / states.  The CUDA counterpart is
-csrc/sigma_dense.cu (experimental, COVO_SIGMA=dense).  Prints per scenario: |lambda_min error| and the relative Frobenius error of
+csrc/sigma_dense.cu (the opt-in fast path, COVO_SIGMA=dense).  Prints per scenario: |lambda_min error| and the relative Frobenius error of
 Sigma for (Lanczos steps, poles) = (16, 8), (24, 8), (32, 10).
 
     python tools/study_dense_sigma.py
