@@ -862,10 +862,11 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
         A(h->Lt.alloc(E * h->lt_floats));
         A(h->diag.alloc(E * 4 * n));
         A(h->hess_ws.alloc(E * hessian_workspace_floats(h->H)));
-        A(h->zolo.alloc((size_t)kZoloLadder * 2 * kZoloPoles));
+        A(h->zolo.alloc(kZoloTableDoubles));
         if (e == cudaSuccess) {
-            std::vector<double> tab((size_t)kZoloLadder * 2 * kZoloPoles);
+            std::vector<double> tab(kZoloTableDoubles);
             zolotarev_table(tab.data());
+            zolotarev_table_dense(tab.data() + (size_t)kZoloLadder * 2 * kZoloPoles);
             A(h2d(h, h->zolo.p, tab.data(), tab.size() * sizeof(double)));
         }
     }

@@ -87,6 +87,12 @@ void zolotarev_table(double* table) {
                         table + (size_t)i * 2 * kZoloPoles + kZoloPoles);
 }
 
+void zolotarev_table_dense(double* table) {
+    for (int i = 0; i < kZoloLadder; ++i)
+        zolotarev_nodes(zolo_m(), zolotarev_ladder_M(i), kDensePoles, table + (size_t)i * 2 * kDensePoles,
+                        table + (size_t)i * 2 * kDensePoles + kDensePoles);
+}
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 namespace covo {
 
 constexpr int kZoloPoles = 16;    // poles of the rational approximation of x^(-1/2)
+constexpr int kDensePoles = 13;   // poles of the dense path (float64 inverses: 13 poles approximate x^(-1/2) to 2e-7 on the ladder's intervals)
 constexpr int kZoloLadder = 10;   // spectral-ratio ladder: M/m = 4^(4+i), i = 0..9
 constexpr int kSigmaMaxN = 224;   // n = 4H limit of the shared-memory resident kernels (H <= 56)
 constexpr double kCovoOffset = 1e-2;  // "offset = -min_eign + 1e-2", controllers/covo.py:120-121
@@ -36,6 +37,8 @@ struct SigmaArgs {
 // host: Zolotarev/Hale-Higham-Trefethen nodes for x^(-1/2) on [m, M]
 void zolotarev_nodes(double m, double M, int N, double* t, double* w);
 void zolotarev_table(double* table /* [kZoloLadder][2][kZoloPoles] */);
+void zolotarev_table_dense(double* table /* [kZoloLadder][2][kDensePoles] */);
+constexpr size_t kZoloTableDoubles = (size_t)kZoloLadder * 2 * (kZoloPoles + kDensePoles);  // both ladders, E2's first
 double zolotarev_ladder_M(int i);
 
 cudaError_t launch_tridiag(const SigmaArgs& a, int n_env, cudaStream_t st);   // E1: R -> (d, e), reflectors

@@ -43,9 +43,9 @@ struct DenseArgs {
     float sample_sigma;
     const float* R;      // [E][n][n]
     double* scal;        // [E][4]: lambda_min, upper bound of the spectrum, log det A, Lanczos steps taken
-    float* Xbuf;         // [E][kZoloPoles][n][n]  upper triangles of w_j (A + t_j I)^-1
+    float* Xbuf;         // [E][kDensePoles][n][n]  upper triangles of w_j (A + t_j I)^-1
     float* cov;          // [E][n][n]
-    const double* zolo;  // the ladder of sigma.cu: [kZoloLadder][2][kZoloPoles]
+    const double* zolo;  // the dense path's ladder: [kZoloLadder][2][kDensePoles] (zolotarev_table_dense)
     int* status;         // [E]
     float* Asym = nullptr;       // optional [E][n][n]: (R + R^T)/2 written by the Lanczos kernel for the factorisation kernels
     long long* prof = nullptr;   // optional clock64() stamps (slots 48..)
@@ -734,57 +734,63 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// D2 gjb_inverse_kernel: in-place Gauss-Jordan sweep without pivoting (A + t_j I is SPD), BLOCKED (8 pivots per step) and spread over
-// a cluster of GB_CL (4) CTAs per pole, the matrix resident in registers.  Sweeping the index block K with P = A_KK:
+// D2 gjb_inverse_kernel: in-place Gauss-Jordan sweep without pivoting (A + t_j I is SPD), BLOCKED (8 pivots per step), in FLOAT64, spread
+// over a cluster of GB_CL (8) CTAs per pole, the matrix resident in registers.  Sweeping the index block K with P = A_KK:
 //     A_IJ -= A_IK P^-1 A_KJ,   A_KJ <- P^-1 A_KJ =: G,   A_IK <- -A_IK P^-1,   A_KK <- P^-1.
 // With this sign convention the matrix is symmetric on the unswept index set and ANTI-symmetric between swept and unswept
 // indices, so the column panel is the row panel again: A_iK = sigma(i) (A_Ki)^T, sigma = -1 for swept i.  Everything a step needs
 // therefore follows from the 8 raw pivot rows (8 x n) alone:
 //     A_ij -= sigma(i) sum_s raw[s][i] G[s][j],    row K_s <- G[s][:],   column K_s <- -sigma(i) G[s][i],   block KK <- P^-1.
+// Why float64 (round 2): A + t_j I has condition up to 1.6e5 for the smallest poles and ANY float32 factorisation has a backward error
+// of eps |A| ~ 3e-5, 0.3 % of the eigenvalue 1e-2 that carries the largest direction of Sigma: the float32 version of this kernel left
+// Sigma 1e-4 .. 5e-3 from exact arithmetic where the reference's float32 eigh pipeline is at 1e-5 (tools/studies/gj_accuracy*.py).
+// In float64 the inverses are exact to ~1e-11 and the accuracy of the path is that of the rational approximation: 13 poles, 2e-7
+// (tools/studies/pole_count.py); 13 + 1 clusters of 8 CTAs = 112 of the 148 SMs, all resident at once.
 // Roles (640 threads per CTA):
-//   * 16 UPDATE warps hold the matrix: thread (ty = warp, tx = lane) owns rows ty + 16 (rank + GB_CL a'), a' < GB_NSLOT (row pairs packed for
-//     FFMA2) and columns tx + 32 b, b < 7.  Per step: 224 FFMA2 per thread against 28 + 16 vector loads.
-//   * 4 SOLVER warps run one block ahead: they wait for the raw rows of block m + 1 (published through distributed shared memory with
-//     st.async, completion counted by an mbarrier -- no fences, no cluster barrier), invert the 8 x 8 pivot block on one warp
+//   * 16 UPDATE warps hold the matrix: thread (ty = warp, tx = lane) owns rows ty + 16 (rank + GB_CL a), a < GB_NSLOT and columns
+//     tx + 32 b, b < 7: 14 doubles.  Per step: 112 DFMA per thread against 56 + 16 shared-memory loads.
+//   * 4 SOLVER warps run one block ahead: they wait for the raw rows of block m + 1 (published through distributed shared memory as
+//     bulk copies, completion counted by an mbarrier -- no fences, no cluster barrier), invert the 8 x 8 pivot block on one warp
 //     (lane = two entries, 8 shuffle-driven pivots), build G = P^-1 raw and the signed multiplier table, while the update warps
 //     are still applying block m.
 //   * look-ahead: after the barrier that opens step m, the warps that own the rows of block m + 1 (one row per warp) apply step m to
 //     that row first (56 FMAs, same operation order as the full update, so the values are bit-identical) and publish it.
 // Flow control: the raw panels live in a ring of 4 slots.  Blocks are owned in pairs (tile = 16 rows = 2 blocks, tiles rotate over
-// the CTAs).  With two CTAs a CTA can run at most 3 blocks ahead of its peer before it needs a panel from it, so 4 slots never
-// collide; with four, a split cluster barrier (arrive after a step is opened, wait before the next one) keeps everybody within one
-// step of everybody else.
-// Cost model at n = 200: 25 steps x max(update 1800 cycles, solver chain ~1600) instead of 200 steps x 1100.
+// the CTAs); a split cluster barrier (arrive after a step is opened, wait before the next one) keeps everybody within one step of
+// everybody else, so 4 slots never collide.
 // ---------------------------------------------------------------------------------------------------------------------------
-#ifndef COVO_GB_CL
-#define COVO_GB_CL 4
-#endif
-constexpr int GB_CL = COVO_GB_CL;                       // CTAs per matrix (2, 4 or 8)
+constexpr int GB_CL = 8;                               // CTAs per matrix
 constexpr int GB_NSLOT = (14 + GB_CL - 1) / GB_CL;     // 16-row tiles per CTA: tile a lives in CTA a % GB_CL, row slot a / GB_CL
-constexpr int GB_NQ = (GB_NSLOT + 1) / 2;              // row pairs per thread (packed for FFMA2)
 constexpr int GB_UT = 512;   // update threads
 constexpr int GB_ST = 128;   // solver threads
 constexpr int GB_T = GB_UT + GB_ST;
 constexpr int GB_NP = 224;   // padded order: 14 row tiles of 16, 7 column slots of 32
-constexpr int GB_RS = 256;   // row stride of a raw panel (the unused 8th row slot addresses rows up to 255)
 constexpr int GB_SLOTS = 4;
-
-template <int V>
-struct IntC {
-    static constexpr int value = V;
-};
+static_assert(GB_NSLOT == 2, "the update warps are written for two row slots per thread");
 
 struct GjbSmem {
-    float raw[GB_SLOTS][8][GB_RS];  // pivot-row panels [s][j]
-    float stage[2][8][GB_NP];       // a pivot row on its way out (by block parity): source of the bulk copies
-    float G[2][4][GB_NP][2];        // [parity][s / 2][j][s & 1]
-    float2 Mneg[2][16][GB_NQ][8];   // [parity][ty][row pair q][s]: (-sigma(i0) raw[s][i0], -sigma(i1) raw[s][i1]); 0 for pivot rows
-    float Pinv[2][64];
-    float piv[GB_NP];
+    double raw[GB_SLOTS][8][GB_NP];   // pivot-row panels [s][j]
+    double stage[2][8][GB_NP];        // a pivot row on its way out (by block parity): source of the bulk copies
+    double G[2][8][GB_NP];            // [parity][s][j]
+    double Mneg[2][16][GB_NSLOT][8];  // [parity][ty][row slot a][s]: -sigma(i) raw[s][i]; 0 for pivot rows and padding
+    double Pinv[2][64];
+    double piv[GB_NP];
     unsigned long long rawbar[GB_SLOTS];
     int bad;
 };
 
+#if defined(COVO_CPU_EMU)
+__device__ __forceinline__ double gjb_rcp64(double x) { return 1.0 / x; }
+#else
+// 1 / x for a pivot (1e-3 .. 1e5): float32 seed, two Newton steps in float64 (4 dependent DFMA instead of the division's ~20)
+__device__ __forceinline__ double gjb_rcp64(double x) {
+    double r = (double)gjb_rcp((float)x);
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+#endif
 
 __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a) {
     COVO_DYN_SMEM(smraw);
@@ -803,10 +809,10 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         }
         if (Mi < Mb && tid == 0 && rank == 0) a.status[env] = 1;
     }
-    const double* zt = a.zolo + (size_t)lad * 2 * kZoloPoles;
-    const bool want_logdet = pole == kZoloPoles;
+    const double* zt = a.zolo + (size_t)lad * 2 * kDensePoles;
+    const bool want_logdet = pole == kDensePoles;
     const double shift = (kOffset - lam_min) + (want_logdet ? 0.0 : zt[pole]);
-    const float wj = want_logdet ? 0.f : (float)zt[kZoloPoles + pole];
+    const double wj = want_logdet ? 0.0 : zt[kDensePoles + pole];
     if (tid == 0) {
         sm.bad = 0;
         for (int q = 0; q < GB_SLOTS; ++q) gjb_mbar_init(&sm.rawbar[q], 1);
@@ -814,7 +820,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
     }
-    for (int i = tid; i < GB_SLOTS * 8 * GB_RS; i += GB_T) (&sm.raw[0][0][0])[i] = 0.f;
+    for (int i = tid; i < GB_SLOTS * 8 * GB_NP; i += GB_T) (&sm.raw[0][0][0])[i] = 0.0;
     gjb_cluster_sync();  // barriers initialised and panels zeroed everywhere before anybody publishes
 
     if (tid >= GB_UT) {
@@ -822,7 +828,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         const int sidx = tid - GB_UT, lane = sidx & 31, swarp = sidx >> 5;
         for (int m = 0; m < nblk; ++m) {
             const int slot = m & (GB_SLOTS - 1), par = m & 1, K0 = 8 * m;
-            if (sidx == 0) gjb_mbar_expect(&sm.rawbar[slot], 8 * GB_NP * 4);
+            if (sidx == 0) gjb_mbar_expect(&sm.rawbar[slot], 8 * GB_NP * 8);
             const bool pf = a.prof && sidx == 0 && blockIdx.x == 0 && blockIdx.y == 0;
             long long t0 = pf ? clock64() : 0;
             gjb_mbar_wait(&sm.rawbar[slot], (unsigned)((m / GB_SLOTS) & 1));
@@ -831,53 +837,47 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 a.prof[54] = (m == 0 ? 0 : a.prof[54]) + (t1 - t0);
                 t0 = t1;
             }
-            const float(*rw)[GB_RS] = sm.raw[slot];
+            const double(*rw)[GB_NP] = sm.raw[slot];
             if (swarp == 0) {
                 // P^-1 by an in-place Gauss-Jordan sweep of the 8 x 8 block: lane = (row r, columns c0, c0 + 1)
                 const int r = lane >> 2, c0 = (lane & 3) * 2;
-                float x0 = rw[r][K0 + c0], x1 = rw[r][K0 + c0 + 1];
-                float pvs[8];  // the scalar pivots (log det, positivity): written out after the chain, not inside it
+                double x0 = rw[r][K0 + c0], x1 = rw[r][K0 + c0 + 1];
+                double pvs[8];  // the scalar pivots (log det, positivity): written out after the chain, not inside it
 #pragma unroll
                 for (int sp = 0; sp < 8; ++sp) {
-                    const float mine = (sp & 1) ? x1 : x0;
-                    const float p = __shfl_sync(0xffffffffu, mine, (sp << 2) | (sp >> 1));
-                    const float prs = __shfl_sync(0xffffffffu, mine, (r << 2) | (sp >> 1));   // P[r][sp]
-                    const float ps0 = __shfl_sync(0xffffffffu, x0, (sp << 2) | (lane & 3));   // P[sp][c0]
-                    const float ps1 = __shfl_sync(0xffffffffu, x1, (sp << 2) | (lane & 3));   // P[sp][c0 + 1]
+                    const double mine = (sp & 1) ? x1 : x0;
+                    const double p = __shfl_sync(0xffffffffu, mine, (sp << 2) | (sp >> 1));
+                    const double prs = __shfl_sync(0xffffffffu, mine, (r << 2) | (sp >> 1));   // P[r][sp]
+                    const double ps0 = __shfl_sync(0xffffffffu, x0, (sp << 2) | (lane & 3));   // P[sp][c0]
+                    const double ps1 = __shfl_sync(0xffffffffu, x1, (sp << 2) | (lane & 3));   // P[sp][c0 + 1]
                     pvs[sp] = p;
-                    const float rinv = gjb_rcp(p);
+                    const double rinv = gjb_rcp64(p);
                     if (r == sp) {
                         x0 = (c0 == sp) ? rinv : ps0 * rinv;
                         x1 = (c0 + 1 == sp) ? rinv : ps1 * rinv;
                     } else {
-                        const float f = prs * rinv;
-                        x0 = (c0 == sp) ? -f : fmaf(-f, ps0, x0);
-                        x1 = (c0 + 1 == sp) ? -f : fmaf(-f, ps1, x1);
+                        const double f = prs * rinv;
+                        x0 = (c0 == sp) ? -f : fma(-f, ps0, x0);
+                        x1 = (c0 + 1 == sp) ? -f : fma(-f, ps1, x1);
                     }
                 }
                 sm.Pinv[par][r * 8 + c0] = x0;
                 sm.Pinv[par][r * 8 + c0 + 1] = x1;
                 if (lane < 8) {
-                    float pl = pvs[0];
+                    double pl = pvs[0];
 #pragma unroll
                     for (int sp = 1; sp < 8; ++sp) pl = (lane == sp) ? pvs[sp] : pl;
                     sm.piv[K0 + lane] = pl;
-                    if (!(pl > 0.f)) sm.bad = 1;
+                    if (!(pl > 0.0)) sm.bad = 1;
                 }
             } else {
-                // signed, negated, pair-packed multipliers of this CTA's rows
-                for (int e = sidx - 32; e < 16 * GB_NQ * 8; e += GB_ST - 32) {
-                    const int ty = e / (GB_NQ * 8), q = (e >> 3) % GB_NQ, sp = e & 7;
-                    float2 val;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int tile = rank + GB_CL * (2 * q + h), i = ty + 16 * tile;
-                        float x = 0.f;
-                        if (tile < GB_NP / 16 && !(i >= K0 && i < K0 + 8)) x = (i < K0) ? rw[sp][i] : -rw[sp][i];
-                        if (h) val.y = x;
-                        else val.x = x;
-                    }
-                    sm.Mneg[par][ty][q][sp] = val;
+                // signed, negated multipliers of this CTA's rows
+                for (int e = sidx - 32; e < 16 * GB_NSLOT * 8; e += GB_ST - 32) {
+                    const int ty = e / (GB_NSLOT * 8), sl = (e >> 3) % GB_NSLOT, sp = e & 7;
+                    const int tile = rank + GB_CL * sl, i = ty + 16 * tile;
+                    double x = 0.0;
+                    if (tile < GB_NP / 16 && !(i >= K0 && i < K0 + 8)) x = (i < K0) ? rw[sp][i] : -rw[sp][i];
+                    sm.Mneg[par][ty][sl][sp] = x;
                 }
             }
             COVO_NAMED_BARRIER(1, GB_ST);
@@ -887,32 +887,27 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 t0 = t1;
             }
             {
-                // G = P^-1 raw: thread = columns (sidx, sidx + 128) packed for FFMA2; P^-1 rows come as broadcast float4 loads
-                const int j0 = sidx, j1 = min(sidx + GB_ST, GB_RS - 1);  // (the second column of sidx >= 96 is padding: never stored)
-                float2 col[8];
+                // G = P^-1 raw: thread = columns sidx and sidx + 128; P^-1 rows come as broadcast loads
+                const int j0 = sidx, j1 = sidx + GB_ST;
+                const bool two = j1 < GB_NP;
+                double c0v[8], c1v[8];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) col[t] = make_float2(rw[t][j0], rw[t][j1]);
-                const float4* pv = reinterpret_cast<const float4*>(sm.Pinv[par]);
+                for (int t = 0; t < 8; ++t) {
+                    c0v[t] = rw[t][j0];
+                    c1v[t] = two ? rw[t][j1] : 0.0;
+                }
+                const double* pv = sm.Pinv[par];
 #pragma unroll
-                for (int sp = 0; sp < 8; sp += 2) {
-                    float2 g[2];
+                for (int sp = 0; sp < 8; ++sp) {
+                    double g0 = 0.0, g1 = 0.0;
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const float4 pa = pv[(sp + u) * 2], pb = pv[(sp + u) * 2 + 1];
-                        float2 acc2 = make_float2(0.f, 0.f);
-                        acc2 = __ffma2_rn(make_float2(pa.x, pa.x), col[0], acc2);
-                        acc2 = __ffma2_rn(make_float2(pa.y, pa.y), col[1], acc2);
-                        acc2 = __ffma2_rn(make_float2(pa.z, pa.z), col[2], acc2);
-                        acc2 = __ffma2_rn(make_float2(pa.w, pa.w), col[3], acc2);
-                        acc2 = __ffma2_rn(make_float2(pb.x, pb.x), col[4], acc2);
-                        acc2 = __ffma2_rn(make_float2(pb.y, pb.y), col[5], acc2);
-                        acc2 = __ffma2_rn(make_float2(pb.z, pb.z), col[6], acc2);
-                        acc2 = __ffma2_rn(make_float2(pb.w, pb.w), col[7], acc2);
-                        g[u] = acc2;
+                    for (int t = 0; t < 8; ++t) {
+                        const double pe = pv[sp * 8 + t];
+                        g0 = fma(pe, c0v[t], g0);
+                        g1 = fma(pe, c1v[t], g1);
                     }
-                    // [s / 2][j][s & 1]: the two s of this pair are adjacent
-                    *reinterpret_cast<float2*>(&sm.G[par][sp >> 1][j0][0]) = make_float2(g[0].x, g[1].x);
-                    if (sidx + GB_ST < GB_NP) *reinterpret_cast<float2*>(&sm.G[par][sp >> 1][sidx + GB_ST][0]) = make_float2(g[0].y, g[1].y);
+                    sm.G[par][sp][j0] = g0;
+                    if (two) sm.G[par][sp][j1] = g1;
                 }
             }
             if (pf) {
@@ -920,9 +915,9 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 a.prof[56] = (m == 0 ? 0 : a.prof[56]) + (t1 - t0);
                 t0 = t1;
             }
-            if (GB_CL > 2 && m > 0) gjb_cluster_wait();
+            if (m > 0) gjb_cluster_wait();
             __syncthreads();  // opens step m for the update warps
-            if (GB_CL > 2) gjb_cluster_arrive();
+            gjb_cluster_arrive();
             if (pf) a.prof[57] = (m == 0 ? 0 : a.prof[57]) + (clock64() - t0);
         }
     } else {
@@ -930,33 +925,27 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         const int tx = tid & 31, ty = tid >> 5;
         const float* Ag = a.Asym ? a.Asym + (long long)env * n * n : nullptr;
         const float* Rg = a.R + (long long)env * n * n;
-        float2 acc[GB_NQ][7];
+        double acc[GB_NSLOT][7];
 #pragma unroll
-        for (int q = 0; q < GB_NQ; ++q)
+        for (int sl = 0; sl < GB_NSLOT; ++sl)
 #pragma unroll
             for (int b = 0; b < 7; ++b) {
-                float v2[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int tile = rank + GB_CL * (2 * q + h), i = ty + 16 * tile, j = tx + 32 * b;
-                    float v = (i == j && tile < GB_NP / 16) ? 1.f : 0.f;  // identity padding: never coupled, pivots 1
-                    if (i < n && j < n) {
-                        // position (i, j) holds element (n - 1 - i, n - 1 - j): the sweep eliminates the LAST controls first.  Without
-                        // pivoting the order decides the accuracy: the Hessian's large entries belong to the early controls, and
-                        // sweeping those first cost up to 8e-3 of Sigma at cond(A) = 1.6e5 (float32); back to front it is 2e-5 .. 8e-5,
-                        // the level of a float32 Cholesky factorisation (tools/studies/gj_accuracy.py)
-                        const int ir = n - 1 - i, jr = n - 1 - j;
-                        v = Ag ? Ag[(long long)ir * n + jr] : 0.5f * (Rg[(long long)ir * n + jr] + Rg[(long long)jr * n + ir]);
-                        if (i == j) v = (float)((double)v + shift);
-                    }
-                    v2[h] = v;
+                const int tile = rank + GB_CL * sl, i = ty + 16 * tile, j = tx + 32 * b;
+                double v = (i == j && tile < GB_NP / 16) ? 1.0 : 0.0;  // identity padding: never coupled, pivots 1
+                if (i < n && j < n) {
+                    // position (i, j) holds element (n - 1 - i, n - 1 - j): the sweep eliminates the LAST controls first (the order
+                    // that was the most accurate one in float32, tools/studies/gj_accuracy.py; kept: the combine kernel and the
+                    // tests know the triangle it produces)
+                    const int ir = n - 1 - i, jr = n - 1 - j;
+                    const float vf = Ag ? Ag[(long long)ir * n + jr] : 0.5f * (Rg[(long long)ir * n + jr] + Rg[(long long)jr * n + ir]);
+                    v = (double)vf;
+                    if (i == j) v += shift;
                 }
-                acc[q][b] = make_float2(v2[0], v2[1]);
+                acc[sl][b] = v;
             }
-        // block 0 lives in tile 0 = CTA 0, row slot 0 (.x of pair 0): warps 0..7 publish their row
         // a row leaves as ONE bulk copy per destination CTA (this one included): staged in shared memory, fenced for the async proxy
-        auto publish_row = [&](int blk, int s_row, const float (&vals)[7]) {
-            float* st = sm.stage[blk & 1][s_row];
+        auto publish_row = [&](int blk, int s_row, const double (&vals)[7]) {
+            double* st = sm.stage[blk & 1][s_row];
 #pragma unroll
             for (int b = 0; b < 7; ++b) st[tx + 32 * b] = vals[b];
             gjb_fence_async_proxy();
@@ -964,64 +953,48 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
             if (tx == 0) {
                 const int slot = blk & (GB_SLOTS - 1);
 #pragma unroll
-                for (int r = 0; r < GB_CL; ++r) gjb_bulk_send(&sm.raw[slot][s_row][0], st, GB_NP * 4, (unsigned)r, &sm.rawbar[slot]);
+                for (int r = 0; r < GB_CL; ++r) gjb_bulk_send(&sm.raw[slot][s_row][0], st, GB_NP * 8, (unsigned)r, &sm.rawbar[slot]);
             }
         };
-        if (rank == 0 && ty < 8) {
-            float vals[7];
-#pragma unroll
-            for (int b = 0; b < 7; ++b) vals[b] = acc[0][b].x;
-            publish_row(0, ty, vals);
-        }
+        // block 0 lives in tile 0 = CTA 0, row slot 0: warps 0..7 publish their row
+        if (rank == 0 && ty < 8) publish_row(0, ty, acc[0]);
         const bool pfu = a.prof && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
         long long tu0 = pfu ? clock64() : 0;
         for (int m = 0; m < nblk; ++m) {
-            if (GB_CL > 2 && m > 0) gjb_cluster_wait();  // every CTA of the cluster has opened step m - 1 (see "flow control")
+            if (m > 0) gjb_cluster_wait();  // every CTA of the cluster has opened step m - 1 (see "flow control")
             __syncthreads();  // G, multipliers and P^-1 of block m are in place; everybody is done with step m - 1
-            if (GB_CL > 2) gjb_cluster_arrive();
+            gjb_cluster_arrive();
             if (pfu) {
                 const long long t1 = clock64();
                 a.prof[58] = (m == 0 ? 0 : a.prof[58]) + (t1 - tu0);
                 tu0 = t1;
             }
             const int par = m & 1, K0 = 8 * m;
-            const float2* mrow = &sm.Mneg[par][ty][0][0];
-            // One row pair: all eight s of the rank-8 update (G is re-read per pair here; the bulk below re-uses it across pairs)
-            auto update_pair = [&](auto QC) {
-                constexpr int q = decltype(QC)::value;
-#pragma unroll
-                for (int qt = 0; qt < 4; ++qt) {
-                    const float4 m4 = *reinterpret_cast<const float4*>(&mrow[q * 8 + 2 * qt]);
-                    const float2 ma = make_float2(m4.x, m4.y), mb = make_float2(m4.z, m4.w);
-#pragma unroll
-                    for (int b = 0; b < 7; ++b) {
-                        const float2 g2 = *reinterpret_cast<const float2*>(&sm.G[par][qt][tx + 32 * b][0]);
-                        acc[q][b] = __ffma2_rn(ma, make_float2(g2.x, g2.x), acc[q][b]);
-                        acc[q][b] = __ffma2_rn(mb, make_float2(g2.y, g2.y), acc[q][b]);
-                    }
-                }
-            };
-            // ---- look-ahead: the warps that own the rows of block m + 1 update THAT pair first and publish their row -------------
-            int q_done = -1;
+            const double* mrow = &sm.Mneg[par][ty][0][0];
+            const double(*Gp)[GB_NP] = sm.G[par];
+            // ---- look-ahead: the warps that own the rows of block m + 1 update THAT row first and publish it -----------------------
+            int sl_done = -1;
             if (m + 1 < nblk) {
                 const int tile1 = (m + 1) >> 1;
                 if (rank == tile1 % GB_CL && (ty >> 3) == ((m + 1) & 1)) {
-                    const int a1 = tile1 / GB_CL, q1 = a1 >> 1, h1 = a1 & 1, i = ty + 16 * tile1;
-                    q_done = q1;
-                    if (q1 == 0) update_pair(IntC<0>());
-                    else if (q1 == 1) update_pair(IntC<(GB_NQ > 1 ? 1 : 0)>());
-                    else if (q1 == 2) update_pair(IntC<(GB_NQ > 2 ? 2 : 0)>());
-                    else update_pair(IntC<(GB_NQ > 3 ? 3 : 0)>());
-                    float tmp[7];
+                    const int sl1 = tile1 / GB_CL, i = ty + 16 * tile1;
+                    sl_done = sl1;
+                    double tmp[7];
 #pragma unroll
-                    for (int q = 0; q < GB_NQ; ++q)
-                        if (q == q1) {
+                    for (int sl = 0; sl < GB_NSLOT; ++sl)
+                        if (sl == sl1) {
 #pragma unroll
-                            for (int b = 0; b < 7; ++b) tmp[b] = h1 ? acc[q][b].y : acc[q][b].x;
+                            for (int s = 0; s < 8; ++s) {
+                                const double mm = mrow[sl * 8 + s];
+#pragma unroll
+                                for (int b = 0; b < 7; ++b) acc[sl][b] = fma(mm, Gp[s][tx + 32 * b], acc[sl][b]);
+                            }
+#pragma unroll
+                            for (int b = 0; b < 7; ++b) tmp[b] = acc[sl][b];
                         }
                     if ((tx & ~7) == (K0 & 31)) {  // its entries in the pivot columns of step m: -G[s][i]  (i is unswept)
                         const int sc = tx - (K0 & 31), b0 = K0 >> 5;
-                        const float v = -sm.G[par][sc >> 1][i][sc & 1];
+                        const double v = -Gp[sc][i];
 #pragma unroll
                         for (int b = 0; b < 7; ++b)
                             if (b == b0) tmp[b] = v;
@@ -1031,58 +1004,46 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
             }
             // ---- the rank-8 update of everything else this thread owns ---------------------------------------------------
 #pragma unroll
-            for (int qt = 0; qt < 4; ++qt) {  // two of the eight s at a time
-                float2 g2[7];
+            for (int s = 0; s < 8; ++s) {
+                double g[7];
 #pragma unroll
-                for (int b = 0; b < 7; ++b) g2[b] = *reinterpret_cast<const float2*>(&sm.G[par][qt][tx + 32 * b][0]);
+                for (int b = 0; b < 7; ++b) g[b] = Gp[s][tx + 32 * b];
 #pragma unroll
-                for (int q = 0; q < GB_NQ; ++q) {
-                    if (q == q_done) continue;  // warp-uniform
-                    const float4 m4 = *reinterpret_cast<const float4*>(&mrow[q * 8 + 2 * qt]);
-                    const float2 ma = make_float2(m4.x, m4.y), mb = make_float2(m4.z, m4.w);
+                for (int sl = 0; sl < GB_NSLOT; ++sl) {
+                    if (sl == sl_done) continue;  // warp-uniform
+                    const double mm = mrow[sl * 8 + s];
 #pragma unroll
-                    for (int b = 0; b < 7; ++b) {
-                        acc[q][b] = __ffma2_rn(ma, make_float2(g2[b].x, g2[b].x), acc[q][b]);
-                        acc[q][b] = __ffma2_rn(mb, make_float2(g2[b].y, g2[b].y), acc[q][b]);
-                    }
+                    for (int b = 0; b < 7; ++b) acc[sl][b] = fma(mm, g[b], acc[sl][b]);
                 }
             }
             // ---- fix-ups: pivot rows <- G (P^-1 inside the block), pivot columns <- -sigma(i) G[s][i] ---------------------
             const int tile0 = m >> 1;
             const bool pivot_warp = (rank == tile0 % GB_CL) && ((ty >> 3) == (m & 1));
-            const int q0 = (tile0 / GB_CL) >> 1, h0 = (tile0 / GB_CL) & 1;
+            const int sl0 = tile0 / GB_CL;
             if (pivot_warp) {
                 const int sr = ty & 7;
 #pragma unroll
                 for (int b = 0; b < 7; ++b) {
                     const int j = tx + 32 * b;
-                    const float v = (j >= K0 && j < K0 + 8) ? sm.Pinv[par][sr * 8 + (j - K0)] : sm.G[par][sr >> 1][j][sr & 1];
+                    const double v = (j >= K0 && j < K0 + 8) ? sm.Pinv[par][sr * 8 + (j - K0)] : Gp[sr][j];
 #pragma unroll
-                    for (int q = 0; q < GB_NQ; ++q)
-                        if (q == q0) {
-                            if (h0) acc[q][b].y = v;
-                            else acc[q][b].x = v;
-                        }
+                    for (int sl = 0; sl < GB_NSLOT; ++sl)
+                        if (sl == sl0) acc[sl][b] = v;
                 }
             }
             if ((tx & ~7) == (K0 & 31)) {
                 const int sc = tx - (K0 & 31), b0 = K0 >> 5;
 #pragma unroll
-                for (int q = 0; q < GB_NQ; ++q)
+                for (int sl = 0; sl < GB_NSLOT; ++sl) {
+                    const int tile = rank + GB_CL * sl, i = ty + 16 * tile;
+                    if (tile < GB_NP / 16 && !(i >= K0 && i < K0 + 8)) {
+                        const double g = Gp[sc][i];
+                        const double v = (i < K0) ? g : -g;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int tile = rank + GB_CL * (2 * q + h), i = ty + 16 * tile;
-                        if (tile < GB_NP / 16 && !(i >= K0 && i < K0 + 8)) {
-                            const float g = sm.G[par][sc >> 1][i][sc & 1];
-                            const float v = (i < K0) ? g : -g;
-#pragma unroll
-                            for (int b = 0; b < 7; ++b)
-                                if (b == b0) {
-                                    if (h) acc[q][b].y = v;
-                                    else acc[q][b].x = v;
-                                }
-                        }
+                        for (int b = 0; b < 7; ++b)
+                            if (b == b0) acc[sl][b] = v;
                     }
+                }
             }
             if (pfu) {
                 const long long t1 = clock64();
@@ -1092,25 +1053,22 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         }
         // ---- results ---------------------------------------------------------------------------------------------------------
         if (!want_logdet) {
-            float* Xg = a.Xbuf + ((long long)env * kZoloPoles + pole) * n * n;
+            float* Xg = a.Xbuf + ((long long)env * kDensePoles + pole) * n * n;
 #pragma unroll
-            for (int q = 0; q < GB_NQ; ++q)
+            for (int sl = 0; sl < GB_NSLOT; ++sl)
 #pragma unroll
                 for (int b = 0; b < 7; ++b) {
                     const int j = tx + 32 * b;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int tile = rank + GB_CL * (2 * q + h), i = ty + 16 * tile;
-                        if (tile < GB_NP / 16 && i < n && j <= i)  // (reversed positions: this is the upper triangle of the inverse)
-                            Xg[(long long)(n - 1 - i) * n + (n - 1 - j)] = wj * (h ? acc[q][b].y : acc[q][b].x);
-                    }
+                    const int tile = rank + GB_CL * sl, i = ty + 16 * tile;
+                    if (tile < GB_NP / 16 && i < n && j <= i)  // (reversed positions: this is the upper triangle of the inverse)
+                        Xg[(long long)(n - 1 - i) * n + (n - 1 - j)] = (float)(wj * acc[sl][b]);
                 }
-        } else if (rank == 0 && ty < 7) {  // log det A = sum of the logarithms of the scalar pivots (both CTAs hold all of them)
+        } else if (rank == 0 && ty < 7) {  // log det A = sum of the logarithms of the scalar pivots (every CTA holds all of them)
             double lp = 0.0;
             const int i = tx + 32 * ty;
-            if (i < n) lp = log((double)sm.piv[i]);
+            if (i < n) lp = log(sm.piv[i]);
             lp = warp_sum_d(lp);
-            double* red = reinterpret_cast<double*>(&sm.G[0][0][0][0]);  // dead: every step is over for these warps' inputs
+            double* red = &sm.G[0][0][0];  // dead: every step is over for these warps' inputs
             COVO_NAMED_BARRIER(3, 224);
             if (tx == 0) red[ty] = lp;
             COVO_NAMED_BARRIER(3, 224);
@@ -1122,7 +1080,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         }
         if (tid == 0 && sm.bad) a.status[env] = 2;
     }
-    if (GB_CL > 2) gjb_cluster_wait();  // the arrive of the last step
+    gjb_cluster_wait();  // the arrive of the last step
     gjb_cluster_sync();  // nobody leaves while a peer could still be sending to it
 }
 
@@ -1135,7 +1093,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const DenseArgs a) {
     // controllers/covo.py:123-127: log_const = (2 * n * 2 log(sigma) + sum log o) / n;  Sigma = exp(log_const / 2) A^(-1/2)
     const double log_const = (4.0 * (double)n * log((double)a.sample_sigma) + logdet) / (double)n;
     const float scale = (float)exp(0.5 * log_const);
-    const float* Xg = a.Xbuf + (long long)env * kZoloPoles * n * n;
+    const float* Xg = a.Xbuf + (long long)env * kDensePoles * n * n;
     float* cov = a.cov + (long long)env * n * n;
     const int npairs = n * (n + 1) / 2;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < npairs; q += gridDim.x * blockDim.x) {
@@ -1146,7 +1104,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const DenseArgs a) {
         float s = 0.f;
         const int I = n - 1 - ia, J = n - 1 - ib;  // I <= J: the inverse kernels store the upper triangle (they work back to front)
 #pragma unroll
-        for (int j = 0; j < kZoloPoles; ++j) s += Xg[(long long)j * n * n + I * n + J];
+        for (int j = 0; j < kDensePoles; ++j) s += Xg[(long long)j * n * n + I * n + J];
         s *= scale;
         cov[I * n + J] = s;
         cov[J * n + I] = s;  // (a_cov + a_cov.T)/2 (:132) holds by construction
@@ -1154,7 +1112,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const DenseArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-size_t sigma_dense_scratch_floats(int n) { return (size_t)kZoloPoles * n * n; }
+size_t sigma_dense_scratch_floats(int n) { return (size_t)kDensePoles * n * n; }
 
 #if !defined(COVO_CPU_EMU)
 cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, int n_env, cudaStream_t st, cudaEvent_t ev_mid1, cudaEvent_t ev_mid2) {
@@ -1167,7 +1125,7 @@ cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, in
     a.scal = scal;
     a.Xbuf = Xbuf;
     a.cov = s.cov;
-    a.zolo = s.zolo;
+    a.zolo = s.zolo + (size_t)kZoloLadder * 2 * kZoloPoles;  // the 13-pole ladder sits behind E2's 16-pole one (zolotarev_table_all)
     a.status = s.status;
     a.prof = s.prof;
     cudaError_t e;
@@ -1194,7 +1152,7 @@ cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, in
         e = ensure_smem_attr(gjb_inverse_kernel, sizeof(GjbSmem), conf4);
         if (e != cudaSuccess) return e;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(GB_CL * (kZoloPoles + 1), n_env);
+        cfg.gridDim = dim3(GB_CL * (kDensePoles + 1), n_env);
         cfg.blockDim = dim3(GB_T);
         cfg.dynamicSmemBytes = sizeof(GjbSmem);
         cfg.stream = st;

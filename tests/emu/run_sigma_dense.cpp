@@ -5,7 +5,7 @@
 extern "C" int emu_sigma_dense(int n, float sample_sigma, const float* R, const double* zolo, float* cov, double* scal4, int* status, int variant) {
     using namespace covo;
     if (n > kSigmaMaxN || (n & 3)) return 1;
-    std::vector<float> xbuf((size_t)kZoloPoles * n * n, std::nanf(""));  // NaN: an entry read before it was written poisons the result
+    std::vector<float> xbuf((size_t)kDensePoles * n * n, std::nanf(""));  // NaN: an entry read before it was written poisons the result
     DenseArgs a;
     a.n = n;
     a.n_pad = round_up8(n);
@@ -20,7 +20,7 @@ extern "C" int emu_sigma_dense(int n, float sample_sigma, const float* R, const 
     a.Asym = nullptr;
     emu_launch_cluster(lanczos_cluster_kernel, dim3(LC_CL, 1), LC_CL, LC_TT, sizeof(LcSmem), a);  // 8-CTA cluster, 4 + 1 warps
     if (variant & 64) return 0;  // lambda_min only (studies of the Lanczos stage)
-    emu_launch_cluster(gjb_inverse_kernel, dim3(GB_CL * (kZoloPoles + 1), 1), GB_CL, GB_T, sizeof(GjbSmem), a);
+    emu_launch_cluster(gjb_inverse_kernel, dim3(GB_CL * (kDensePoles + 1), 1), GB_CL, GB_T, sizeof(GjbSmem), a);
     if (const char* dump = getenv("COVO_EMU_DUMP_X")) {  // development: the per-pole inverses
         FILE* f = fopen(dump, "wb");
         if (f) {

@@ -16,6 +16,7 @@ from tests.util import scenario
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 kFirstCheck = 16  # csrc/sigma_dense.cu: kLanczosFirstCheck
+kDensePoles = 13  # csrc/sigma.cuh
 
 
 def _emu_lib():
@@ -52,10 +53,10 @@ def _zolo_table():
     lib = _lib.load()  # the ladder of sigma.cu, through the C-ABI's host-side helper (no GPU involved)
     lib.covo_zolotarev_nodes.argtypes = [C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     m = 1e-2 * (1 - 1e-7)
-    tab = np.zeros((10, 2, 16))
+    tab = np.zeros((10, 2, kDensePoles))
     for i in range(10):
-        sh, w = np.zeros(16), np.zeros(16)
-        assert lib.covo_zolotarev_nodes(m, m * 4.0 ** (4 + i), 16, sh.ctypes.data_as(C.POINTER(C.c_double)), w.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        sh, w = np.zeros(kDensePoles), np.zeros(kDensePoles)
+        assert lib.covo_zolotarev_nodes(m, m * 4.0 ** (4 + i), kDensePoles, sh.ctypes.data_as(C.POINTER(C.c_double)), w.ctypes.data_as(C.POINTER(C.c_double))) == 0
         tab[i, 0], tab[i, 1] = sh, w
     return tab
 
