@@ -129,8 +129,8 @@ def algorithmic_bytes(n, H, N, parity=False):
     rollout = nn // 2 + 4 * 4 * n + 4 * (H + 1) * 6 + 96 + 2 * 4 * n + (4 * N * n if parity else 0)
     return {
         "lanczos": nn + nn,                          # R in; (R + R^T)/2 out for the pole kernels
-        "pole_inverses": 17 * nn + 16 * nn // 2,     # every pole (and the log det CTA) reads the matrix; 16 weighted inverses (lower) out
-        "combine": 16 * nn // 2 + nn,                # 16 lower triangles in; Sigma out
+        "pole_inverses": 14 * nn + 13 * nn // 2,     # every pole cluster (and the log det one) reads the matrix; 13 weighted inverses (triangles) out
+        "combine": 13 * nn // 2 + nn,                # 13 triangles in; Sigma out
         # state, mean, ref; per-step derivative records written + read; [A|B], S, D hand-over written + read; R
         "hessian": 96 + 4 * n + 4 * H * 6 + 2 * 4 * H * (14 * 153 + 14 * 17) + 2 * 4 * H * 328 + nn,
         "tridiag": nn + nn + 2 * 8 * n,  # R in; reflectors out; (d, e) fp64 out (Q^T: qacc kernel, side stream, +2 nn)
@@ -409,10 +409,13 @@ def run_gpu(args):
     sigma_path = h.sigma_path()
     slot_names = h.kernel_slot_names()
 
-    # ---- the opt-in fast optimize_sigma path (same states, same timing protocol; NOT the headline: reduced Sigma accuracy) --------
+    # ---- the other optimize_sigma path (same states, same timing protocol; rank-local, not the headline) --------
+    PATH_NAMES = {0: "tridiagonal (E1-E3: cluster Householder + float64 Sturm/Zolotarev on the tridiagonal + sandwich)",
+                  3: "dense (D1-D3: adaptive float64 cluster Lanczos + 13 float64 cluster Gauss-Jordan pole inverses + combine)"}
     fast_sigma = None
     if cfg.mode == _lib.MODE_COVO_ONLINE:
-        h.set_sigma_path(3)
+        alt_path = 0 if sigma_path == 3 else 3
+        h.set_sigma_path(alt_path)
         h.set_mean(_hover())
         for i in range(W):
             one_step(i)
@@ -436,10 +439,10 @@ def run_gpu(args):
         h.set_profiling(False)
         fast_sigma = {"value": K / (float(ms2.sum()) / 1e3), "unit": UNIT, "ms_per_step": float(ms2.mean()), "step_ms_p99": float(np.percentile(ms2, 99)),
                       "numeric_status_ok": ok2, "kernel_us": {k: round(float(v) / min(10, K) * 1e3, 1) for k, v in zip(names2, acc2)},
-                      "note": "covo_set_sigma_path(h, 3) / COVO_SIGMA=dense: adaptive Lanczos + 16 float32 Gauss-Jordan pole inverses instead of "
-                              "E1-E3; Sigma within 1e-4 (median) .. 5e-3 (worst) of exact arithmetic instead of 1e-5 -- rank-local number, "
-                              "not the headline"}
-        h.set_sigma_path(0)
+                      "sigma_path": PATH_NAMES[alt_path],
+                      "note": "the optimize_sigma path that is NOT the default of this handle (covo_set_sigma_path / COVO_SIGMA=tridiag|dense); "
+                              "rank-local number, not the headline"}
+        h.set_sigma_path(sigma_path)
         h.set_mean(_hover())
         for i in range(W):
             one_step(i)
@@ -490,7 +493,7 @@ def run_gpu(args):
     closed = {"value": K * world / tc, "unit": UNIT, "ms_per_step": 1e3 * tc / K, "mean_err_pos": float(err_cl.mean()),
               "note": "covo_closed_loop: K x [noisy state -> controller -> Quad3D.step_env] on the device, one D2H of the logs at the end (wall clock)"}
     # kernels inside the replayed CUDA graph of one step (+ the counter kernel that replaces the per-step launch arguments)
-    launches_per_step = {"covo-online": 9 + 1, "covo-offline": 1 + 1, "mppi": 1 + 1}[mode_name]
+    launches_per_step = {"covo-online": (8 if sigma_path == 3 else 9) + 1, "covo-offline": 1 + 1, "mppi": 1 + 1}[mode_name]
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak",
@@ -501,14 +504,14 @@ def run_gpu(args):
                    "inputs": "noisy states of a PID closed loop on a zigzag reference (host-generated, shared with --impl reference)",
                    "rng": "in-kernel Philox (production mode)", "l2": "256 MiB memset between steps, excluded from the event timing",
                    "timing": "CUDA events per step on the launch stream, sum over K steps, max over ranks",
-                   "sigma_path": {0: "tridiagonal (E1-E3)", 3: "dense (Lanczos + 16-pole cluster Gauss-Jordan)"}.get(sigma_path, str(sigma_path))},
+                   "sigma_path": PATH_NAMES.get(sigma_path, str(sigma_path)) if cfg.mode == _lib.MODE_COVO_ONLINE else None},
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
         "step_ms_p50": float(np.median(step_ms)), "step_ms_p99": float(np.percentile(step_ms, 99)),
         "gpu_launches": launches_per_step * K, "clocks": clocks, "numeric_status_ok": status_ok,
         "e2e": e2e, "closed_loop": closed,
     }
     if fast_sigma is not None:
-        out["fast_sigma"] = fast_sigma
+        out["alt_sigma"] = fast_sigma
     # ---- roofline ---------------------------------------------------------------------------------------
     peak, peak_src = measured_peaks()
     n = 4 * HORIZON

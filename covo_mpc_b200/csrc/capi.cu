@@ -813,14 +813,19 @@ int covo_create(const covo_config* cfg, covo_handle** out) {
         const char* pe = getenv("COVO_PIPELINE");
         h->pipeline_enabled = !(pe && pe[0] == '0');
         h->pipeline_forced = pe && pe[0] == '2';
-        // optimize_sigma path.  Default: the tridiagonal kernels E1-E3 (orthogonal reduction in float32, everything on the tridiagonal in
-        // float64: Sigma within 1e-6 .. 1e-5 of exact arithmetic, the accuracy of the reference's float32 eigh).  COVO_SIGMA=dense (or
-        // covo_set_sigma_path(h, 3)) selects the FAST path D1-D3 of sigma_dense.cu: 0.16 ms less per step at H = 50, but its float32
-        // inverses of A + t_j I (condition up to 1e5) leave Sigma 1e-4 (median) .. 5e-3 (worst seen) from exact arithmetic -- an
-        // accuracy / latency trade the caller has to ask for.
+        // optimize_sigma path.  Single environments default to the DENSE kernels D1-D3 of sigma_dense.cu (adaptive Lanczos in float64,
+        // A^(-1/2) as 13 float64 Gauss-Jordan pole inverses: Sigma within 1e-7 .. 2e-7 of the float64 eigen-decomposition, 0.1 ms less
+        // per step at H = 50); batches of environments use the tridiagonal kernels E1-E3 of sigma.cu (orthogonal reduction in float32,
+        // everything on the tridiagonal in float64; 1e-6 .. 1e-5), which need 8 CTAs per matrix instead of 112.  COVO_SIGMA=tridiag /
+        // COVO_SIGMA=dense or covo_set_sigma_path(h, 0 / 3) override.  A Lanczos stage that does not converge (status 3: no separated
+        // lowest eigenvalue, not a CoVO Hessian) moves the handle to E1-E3.
         const char* se = getenv("COVO_SIGMA");
         h->sigma_dense = 0;
-        if (cfg->mode != COVO_MODE_MPPI && h->n <= kSigmaMaxN && se && strncmp(se, "dense", 5) == 0) h->sigma_dense = 3;
+        if (cfg->mode != COVO_MODE_MPPI && h->n <= kSigmaMaxN) {
+            if (se && strncmp(se, "dense", 5) == 0) h->sigma_dense = 3;
+            else if (se && strncmp(se, "tridiag", 7) == 0) h->sigma_dense = 0;
+            else if (E == 1) h->sigma_dense = 3;
+        }
         if (h->sigma_dense) {
             A(h->dense_scal.alloc(E * 4));
             A(h->dense_X.alloc(E * sigma_dense_scratch_floats(h->n)));
@@ -1870,6 +1875,13 @@ int covo_debug_tridiag(covo_handle* h, double* d, double* e, double* scalars5) {
     if (h->cfg.mode == COVO_MODE_MPPI) return fail(COVO_ERR_INVALID, "handle is in MPPI mode");
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->own_stream));
+    if (h->sigma_dense && h->dense_scal.p) {  // dense path: no tridiagonal matrix; the scalars of its Lanczos / log det stages instead
+        memset(d, 0, h->n * sizeof(double));
+        memset(e, 0, h->n * sizeof(double));
+        scalars5[4] = 0.0;
+        CK(d2h(h, scalars5, h->dense_scal.p, 4 * sizeof(double)));  // lambda_min, upper bound of the spectrum, log det A, Lanczos steps
+        return COVO_OK;
+    }
     CK(d2h(h, d, h->diag.p, h->n * sizeof(double)));
     CK(d2h(h, e, h->diag.p + h->n, h->n * sizeof(double)));
     CK(d2h(h, scalars5, h->diag.p + 2 * h->n, 5 * sizeof(double)));
@@ -1916,6 +1928,7 @@ int covo_debug_phase_clocks(covo_handle* h, int on, long long* out64) {
     CK(cudaSetDevice(h->cfg.device));
     h->phase_clocks = on != 0;
     if (out64) CK(d2h(h, out64, h->prof.p, 64 * sizeof(long long)));
+    else CK(dzero(h, h->prof.p, 64 * sizeof(long long)));  // some slots are accumulators
     return COVO_OK;
 }
 

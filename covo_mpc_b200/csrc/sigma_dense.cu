@@ -739,50 +739,69 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
 //     A_IJ -= A_IK P^-1 A_KJ,   A_KJ <- P^-1 A_KJ =: G,   A_IK <- -A_IK P^-1,   A_KK <- P^-1.
 // With this sign convention the matrix is symmetric on the unswept index set and ANTI-symmetric between swept and unswept
 // indices, so the column panel is the row panel again: A_iK = sigma(i) (A_Ki)^T, sigma = -1 for swept i.  Everything a step needs
-// therefore follows from the 8 raw pivot rows (8 x n) alone:
-//     A_ij -= sigma(i) sum_s raw[s][i] G[s][j],    row K_s <- G[s][:],   column K_s <- -sigma(i) G[s][i],   block KK <- P^-1.
+// therefore follows from the 8 raw pivot rows (8 x n) alone; with the multipliers MP[i][u] = -sigma(i) G[u][i] (P^-1 is symmetric):
+//     A_ij += sum_u MP[i][u] raw[u][j],    row K_s <- G[s][:],   column K_s <- MP[i][s],   block KK <- P^-1,
+// so that G is only needed at the columns of the CTA's own rows (the multipliers) and, for the owner of the pivot rows, in those rows.
 // Why float64 (round 2): A + t_j I has condition up to 1.6e5 for the smallest poles and ANY float32 factorisation has a backward error
 // of eps |A| ~ 3e-5, 0.3 % of the eigenvalue 1e-2 that carries the largest direction of Sigma: the float32 version of this kernel left
 // Sigma 1e-4 .. 5e-3 from exact arithmetic where the reference's float32 eigh pipeline is at 1e-5 (tools/studies/gj_accuracy*.py).
 // In float64 the inverses are exact to ~1e-11 and the accuracy of the path is that of the rational approximation: 13 poles, 2e-7
-// (tools/studies/pole_count.py); 13 + 1 clusters of 8 CTAs = 112 of the 148 SMs, all resident at once.
-// Roles (640 threads per CTA):
-//   * 16 UPDATE warps hold the matrix: thread (ty = warp, tx = lane) owns rows ty + 16 (rank + GB_CL a), a < GB_NSLOT and columns
-//     tx + 32 b, b < 7: 14 doubles.  Per step: 112 DFMA per thread against 56 + 16 shared-memory loads.
-//   * 4 SOLVER warps run one block ahead: they wait for the raw rows of block m + 1 (published through distributed shared memory as
-//     bulk copies, completion counted by an mbarrier -- no fences, no cluster barrier), invert the 8 x 8 pivot block on one warp
-//     (lane = two entries, 8 shuffle-driven pivots), build G = P^-1 raw and the signed multiplier table, while the update warps
-//     are still applying block m.
-//   * look-ahead: after the barrier that opens step m, the warps that own the rows of block m + 1 (one row per warp) apply step m to
-//     that row first (56 FMAs, same operation order as the full update, so the values are bit-identical) and publish it.
-// Flow control: the raw panels live in a ring of 4 slots.  Blocks are owned in pairs (tile = 16 rows = 2 blocks, tiles rotate over
-// the CTAs); a split cluster barrier (arrive after a step is opened, wait before the next one) keeps everybody within one step of
-// everybody else, so 4 slots never collide.
+// (tools/studies/pole_count.py); 13 + 1 clusters of 8 CTAs = 112 of the 148 SMs, all resident at once.  Measured on B200
+// (tools/microbench/fp64_rates.cu): DFMA issues at 64 lanes / clock / SM with 9 cycles between dependent operations (DMMA m8n8k4: the
+// same 64 FMA / clock / SM), so the arithmetic is cheap; what a step costs is shared-memory traffic and the dependent chain
+// "look-ahead rows -> DSMEM -> 8 x 8 inverse -> multipliers -> step barrier".
+// Layout: ROW-CYCLIC over the cluster -- row i lives in CTA i mod 8 -- so every 8-row pivot block is ONE row per CTA: each CTA sends
+// one row (1.8 KB) to its seven peers per step.  (Tiles of 16 rows per CTA, the first float64 version, made one CTA send all eight rows:
+// 115 KB through one SM's DSMEM port, measured 2.2 us per step; tools/microbench/dsmem_latency.cu: a 1792-byte copy alone is 735 cycles.)
+// Roles (384 threads per CTA):
+//   * 8 UPDATE warps hold the matrix: thread (ty = warp, tx = lane) owns the local rows ty + 8 k, k < 4 (global row rank + 8 (ty + 8 k);
+//     28 rows per CTA, 25 of them real at n = 200) and columns tx + 32 b, b < 7: 28 doubles.  Per step and thread: up to 224 DFMA
+//     against 56 + 16 shared-memory loads.
+//   * 4 SOLVER warps run one block ahead: warp 0 inverts the 8 x 8 pivot block of block m + 1, whose rows' owners send their eight
+//     pivot-column entries AHEAD of the rows (64 bytes each, an mbarrier of their own), lane = two entries, 8 shuffle-driven pivots; when
+//     the rows themselves have arrived (bulk copies through distributed shared memory, completion counted by an mbarrier -- no fences,
+//     no cluster barrier) all four build the multiplier table of this CTA's rows.  All of it happens while the update warps are
+//     still applying block m.
+//   * look-ahead: after the barrier that opens step m, the warp that owns the CTA's row of block m + 1 applies step m to that row
+//     first -- the eight pivot columns before the rest -- and publishes it.
+// Flow control: the raw panels live in a ring of 4 slots; a split cluster barrier (arrive after a step is opened, wait before the
+// next one) keeps everybody within one step of everybody else, so 4 slots never collide.
 // ---------------------------------------------------------------------------------------------------------------------------
-constexpr int GB_CL = 8;                               // CTAs per matrix
-constexpr int GB_NSLOT = (14 + GB_CL - 1) / GB_CL;     // 16-row tiles per CTA: tile a lives in CTA a % GB_CL, row slot a / GB_CL
-constexpr int GB_UT = 512;   // update threads
+constexpr int GB_CL = 8;     // CTAs per matrix = rows per pivot block
+constexpr int GB_NR = 4;     // rows per update thread
+constexpr int GB_UT = 256;   // update threads
 constexpr int GB_ST = 128;   // solver threads
 constexpr int GB_T = GB_UT + GB_ST;
-constexpr int GB_NP = 224;   // padded order: 14 row tiles of 16, 7 column slots of 32
+constexpr int GB_NP = 224;   // padded order: 28 local rows in each of the 8 CTAs, 7 column slots of 32
+constexpr int GB_LR = GB_NP / GB_CL;  // local rows per CTA
 constexpr int GB_SLOTS = 4;
-static_assert(GB_NSLOT == 2, "the update warps are written for two row slots per thread");
 
 struct GjbSmem {
-    double raw[GB_SLOTS][8][GB_NP];   // pivot-row panels [s][j]
-    double stage[2][8][GB_NP];        // a pivot row on its way out (by block parity): source of the bulk copies
-    double G[2][8][GB_NP];            // [parity][s][j]
-    double Mneg[2][16][GB_NSLOT][8];  // [parity][ty][row slot a][s]: -sigma(i) raw[s][i]; 0 for pivot rows and padding
+    double raw[GB_SLOTS][8][GB_NP];   // pivot-row panels [s][j]: row s comes from CTA s
+    double stage[2][GB_NP];           // this CTA's pivot row on its way out (by block parity): source of the bulk copies
+    double MP[2][8][8][GB_NR];        // [parity][ty][u][k]: -sigma(i) G[u][i] for the local row ty + 8 k; 0 for the pivot row and padding
+    double Pblk[GB_SLOTS][8][8];      // the 8 x 8 pivot blocks, sent ahead of the rows
+    double Pst[2][8];                 // ... this CTA's row of them on its way out
     double Pinv[2][64];
     double piv[GB_NP];
     unsigned long long rawbar[GB_SLOTS];
+    unsigned long long pbar[GB_SLOTS];
+    long long pacc[16];  // phase-clock accumulators (slots 48 + i), dumped once at the end: a global read-modify-write per stamp distorts what it measures
     int bad;
 };
 
 #if defined(COVO_CPU_EMU)
 __device__ __forceinline__ double gjb_rcp64(double x) { return 1.0 / x; }
+__device__ __forceinline__ double gjb_sel(bool c, double x, double y) { return c ? x : y; }
 #else
-// 1 / x for a pivot (1e-3 .. 1e5): float32 seed, two Newton steps in float64 (4 dependent DFMA instead of the division's ~20)
+// c ? x : y as an opaque select: written as `(b == idx) ? arr[b] : v` over an unrolled loop, the compiler turns the register array into
+// a local-memory array with a dynamic index
+__device__ __forceinline__ double gjb_sel(bool c, double x, double y) {
+    double r;
+    asm("{\n.reg .pred p;\nsetp.ne.s32 p, %3, 0;\nselp.f64 %0, %1, %2, p;\n}" : "=d"(r) : "d"(x), "d"(y), "r"((int)c));
+    return r;
+}
+// 1 / x for a pivot (1e-3 .. 1e5): float32 seed, two Newton steps in float64 (4 dependent DFMA instead of a division)
 __device__ __forceinline__ double gjb_rcp64(double x) {
     double r = (double)gjb_rcp((float)x);
     double e = fma(-x, r, 1.0);
@@ -813,9 +832,13 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
     const bool want_logdet = pole == kDensePoles;
     const double shift = (kOffset - lam_min) + (want_logdet ? 0.0 : zt[pole]);
     const double wj = want_logdet ? 0.0 : zt[kDensePoles + pole];
+    if (tid < 16) sm.pacc[tid] = 0;
     if (tid == 0) {
         sm.bad = 0;
-        for (int q = 0; q < GB_SLOTS; ++q) gjb_mbar_init(&sm.rawbar[q], 1);
+        for (int q = 0; q < GB_SLOTS; ++q) {
+            gjb_mbar_init(&sm.rawbar[q], 1);
+            gjb_mbar_init(&sm.pbar[q], 1);
+        }
 #if !defined(COVO_CPU_EMU)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
@@ -827,21 +850,24 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         // ================================================ solver warps ================================================
         const int sidx = tid - GB_UT, lane = sidx & 31, swarp = sidx >> 5;
         for (int m = 0; m < nblk; ++m) {
-            const int slot = m & (GB_SLOTS - 1), par = m & 1, K0 = 8 * m;
-            if (sidx == 0) gjb_mbar_expect(&sm.rawbar[slot], 8 * GB_NP * 8);
+            const int slot = m & (GB_SLOTS - 1), par = m & 1;
+            const unsigned ring_par = (unsigned)((m / GB_SLOTS) & 1);
+            if (sidx == 0) {
+                gjb_mbar_expect(&sm.pbar[slot], 8 * 8 * 8);
+                gjb_mbar_expect(&sm.rawbar[slot], 8 * GB_NP * 8);
+            }
             const bool pf = a.prof && sidx == 0 && blockIdx.x == 0 && blockIdx.y == 0;
             long long t0 = pf ? clock64() : 0;
-            gjb_mbar_wait(&sm.rawbar[slot], (unsigned)((m / GB_SLOTS) & 1));
-            if (pf) {
-                const long long t1 = clock64();
-                a.prof[54] = (m == 0 ? 0 : a.prof[54]) + (t1 - t0);
-                t0 = t1;
-            }
-            const double(*rw)[GB_NP] = sm.raw[slot];
             if (swarp == 0) {
+                gjb_mbar_wait(&sm.pbar[slot], ring_par);
+                if (pf) {
+                    const long long t1 = clock64();
+                    sm.pacc[6] += (t1 - t0);
+                    t0 = t1;
+                }
                 // P^-1 by an in-place Gauss-Jordan sweep of the 8 x 8 block: lane = (row r, columns c0, c0 + 1)
                 const int r = lane >> 2, c0 = (lane & 3) * 2;
-                double x0 = rw[r][K0 + c0], x1 = rw[r][K0 + c0 + 1];
+                double x0 = sm.Pblk[slot][r][c0], x1 = sm.Pblk[slot][r][c0 + 1];
                 double pvs[8];  // the scalar pivots (log det, positivity): written out after the chain, not inside it
 #pragma unroll
                 for (int sp = 0; sp < 8; ++sp) {
@@ -867,72 +893,68 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                     double pl = pvs[0];
 #pragma unroll
                     for (int sp = 1; sp < 8; ++sp) pl = (lane == sp) ? pvs[sp] : pl;
-                    sm.piv[K0 + lane] = pl;
+                    sm.piv[8 * m + lane] = pl;
                     if (!(pl > 0.0)) sm.bad = 1;
                 }
-            } else {
-                // signed, negated multipliers of this CTA's rows
-                for (int e = sidx - 32; e < 16 * GB_NSLOT * 8; e += GB_ST - 32) {
-                    const int ty = e / (GB_NSLOT * 8), sl = (e >> 3) % GB_NSLOT, sp = e & 7;
-                    const int tile = rank + GB_CL * sl, i = ty + 16 * tile;
-                    double x = 0.0;
-                    if (tile < GB_NP / 16 && !(i >= K0 && i < K0 + 8)) x = (i < K0) ? rw[sp][i] : -rw[sp][i];
-                    sm.Mneg[par][ty][sl][sp] = x;
+                if (pf) {
+                    const long long t1 = clock64();
+                    sm.pacc[7] += (t1 - t0);
+                    t0 = t1;
                 }
             }
-            COVO_NAMED_BARRIER(1, GB_ST);
+            gjb_mbar_wait(&sm.rawbar[slot], ring_par);  // every solver thread: it reads the rows below
+            COVO_NAMED_BARRIER(1, GB_ST);               // P^-1 is in place
             if (pf) {
                 const long long t1 = clock64();
-                a.prof[55] = (m == 0 ? 0 : a.prof[55]) + (t1 - t0);
+                sm.pacc[12] += (t1 - t0);
                 t0 = t1;
             }
             {
-                // G = P^-1 raw: thread = columns sidx and sidx + 128; P^-1 rows come as broadcast loads
-                const int j0 = sidx, j1 = sidx + GB_ST;
-                const bool two = j1 < GB_NP;
-                double c0v[8], c1v[8];
+                // multipliers of this CTA's rows: MP[ty][u][k] = -sigma(i) sum_v P^-1[u][v] raw[v][i]; thread = (ty, k, two of the eight u)
+                const double(*rw)[GB_NP] = sm.raw[slot];
+                const int ty = sidx >> 4, k = (sidx >> 2) & 3, u0 = (sidx & 3) * 2;
+                const int l = ty + 8 * k, i = rank + GB_CL * l;
+                const bool live = l < GB_LR && l != m;
+                double col[8];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    c0v[t] = rw[t][j0];
-                    c1v[t] = two ? rw[t][j1] : 0.0;
+                for (int v = 0; v < 8; ++v) col[v] = live ? rw[v][i] : 0.0;
+                const double sgn = (l < m) ? 1.0 : -1.0;
+                const double* pv = &sm.Pinv[par][u0 * 8];
+                double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    g0 = fma(pv[v], col[v], g0);
+                    g1 = fma(pv[8 + v], col[v], g1);
                 }
-                const double* pv = sm.Pinv[par];
-#pragma unroll
-                for (int sp = 0; sp < 8; ++sp) {
-                    double g0 = 0.0, g1 = 0.0;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const double pe = pv[sp * 8 + t];
-                        g0 = fma(pe, c0v[t], g0);
-                        g1 = fma(pe, c1v[t], g1);
-                    }
-                    sm.G[par][sp][j0] = g0;
-                    if (two) sm.G[par][sp][j1] = g1;
-                }
+                sm.MP[par][ty][u0][k] = live ? sgn * g0 : 0.0;
+                sm.MP[par][ty][u0 + 1][k] = live ? sgn * g1 : 0.0;
             }
             if (pf) {
                 const long long t1 = clock64();
-                a.prof[56] = (m == 0 ? 0 : a.prof[56]) + (t1 - t0);
+                sm.pacc[8] += (t1 - t0);
                 t0 = t1;
             }
             if (m > 0) gjb_cluster_wait();
             __syncthreads();  // opens step m for the update warps
             gjb_cluster_arrive();
-            if (pf) a.prof[57] = (m == 0 ? 0 : a.prof[57]) + (clock64() - t0);
+            if (pf) sm.pacc[9] += (clock64() - t0);
         }
     } else {
         // ================================================ update warps ================================================
         const int tx = tid & 31, ty = tid >> 5;
         const float* Ag = a.Asym ? a.Asym + (long long)env * n * n : nullptr;
         const float* Rg = a.R + (long long)env * n * n;
-        double acc[GB_NSLOT][7];
+        double acc[GB_NR][7];
+        bool row_live[GB_NR];  // warp-uniform: the row exists (not padding beyond n)
 #pragma unroll
-        for (int sl = 0; sl < GB_NSLOT; ++sl)
+        for (int k = 0; k < GB_NR; ++k) {
+            const int l = ty + 8 * k, i = rank + GB_CL * l;
+            row_live[k] = l < GB_LR && i < n;
 #pragma unroll
             for (int b = 0; b < 7; ++b) {
-                const int tile = rank + GB_CL * sl, i = ty + 16 * tile, j = tx + 32 * b;
-                double v = (i == j && tile < GB_NP / 16) ? 1.0 : 0.0;  // identity padding: never coupled, pivots 1
-                if (i < n && j < n) {
+                const int j = tx + 32 * b;
+                double v = (i == j && l < GB_LR) ? 1.0 : 0.0;  // identity padding: never coupled, pivots 1
+                if (l < GB_LR && i < n && j < n) {
                     // position (i, j) holds element (n - 1 - i, n - 1 - j): the sweep eliminates the LAST controls first (the order
                     // that was the most accurate one in float32, tools/studies/gj_accuracy.py; kept: the combine kernel and the
                     // tests know the triangle it produces)
@@ -941,113 +963,168 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                     v = (double)vf;
                     if (i == j) v += shift;
                 }
-                acc[sl][b] = v;
+                acc[k][b] = v;
             }
-        // a row leaves as ONE bulk copy per destination CTA (this one included): staged in shared memory, fenced for the async proxy
-        auto publish_row = [&](int blk, int s_row, const double (&vals)[7]) {
-            double* st = sm.stage[blk & 1][s_row];
-#pragma unroll
-            for (int b = 0; b < 7; ++b) st[tx + 32 * b] = vals[b];
+        }
+        // This CTA's row of a block leaves as ONE bulk copy per destination CTA (this one included): staged in shared memory, fenced
+        // for the async proxy; its eight entries in the block's own pivot columns travel ahead as a 64-byte copy of their own
+        // (lanes 0..7: one destination each)
+        auto publish_pblock = [&](int blk, double v) {  // called by all lanes of one warp; the lanes holding the block's columns pass their entry
+            const int K1 = 8 * blk;
+            if ((tx & ~7) == (K1 & 31)) sm.Pst[blk & 1][tx & 7] = v;
             gjb_fence_async_proxy();
             __syncwarp();
-            if (tx == 0) {
+            if (tx < GB_CL) {
                 const int slot = blk & (GB_SLOTS - 1);
-#pragma unroll
-                for (int r = 0; r < GB_CL; ++r) gjb_bulk_send(&sm.raw[slot][s_row][0], st, GB_NP * 8, (unsigned)r, &sm.rawbar[slot]);
+                gjb_bulk_send(&sm.Pblk[slot][rank][0], &sm.Pst[blk & 1][0], 64, (unsigned)tx, &sm.pbar[slot]);
             }
         };
-        // block 0 lives in tile 0 = CTA 0, row slot 0: warps 0..7 publish their row
-        if (rank == 0 && ty < 8) publish_row(0, ty, acc[0]);
+        auto publish_row = [&](int blk, const double (&vals)[7], int Kfix, double vfix) {
+            double* st = sm.stage[blk & 1];
+#pragma unroll
+            for (int b = 0; b < 7; ++b) st[tx + 32 * b] = vals[b];
+            if (Kfix >= 0 && (tx & ~7) == (Kfix & 31)) st[(Kfix & ~31) + tx] = vfix;  // same thread, same address: program order
+            gjb_fence_async_proxy();
+            __syncwarp();
+            if (tx < GB_CL) {
+                const int slot = blk & (GB_SLOTS - 1);
+                gjb_bulk_send(&sm.raw[slot][rank][0], st, GB_NP * 8, (unsigned)tx, &sm.rawbar[slot]);
+            }
+        };
+        // block 0: local row 0 of every CTA (warp 0, k = 0)
+        if (ty == 0) {
+            publish_pblock(0, acc[0][0]);
+            publish_row(0, acc[0], -1, 0.0);
+        }
         const bool pfu = a.prof && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
         long long tu0 = pfu ? clock64() : 0;
         for (int m = 0; m < nblk; ++m) {
             if (m > 0) gjb_cluster_wait();  // every CTA of the cluster has opened step m - 1 (see "flow control")
-            __syncthreads();  // G, multipliers and P^-1 of block m are in place; everybody is done with step m - 1
+            __syncthreads();  // multipliers and P^-1 of block m are in place; everybody is done with step m - 1
             gjb_cluster_arrive();
             if (pfu) {
                 const long long t1 = clock64();
-                a.prof[58] = (m == 0 ? 0 : a.prof[58]) + (t1 - tu0);
+                sm.pacc[10] += (t1 - tu0);
                 tu0 = t1;
             }
-            const int par = m & 1, K0 = 8 * m;
-            const double* mrow = &sm.Mneg[par][ty][0][0];
-            const double(*Gp)[GB_NP] = sm.G[par];
-            // ---- look-ahead: the warps that own the rows of block m + 1 update THAT row first and publish it -----------------------
-            int sl_done = -1;
-            if (m + 1 < nblk) {
-                const int tile1 = (m + 1) >> 1;
-                if (rank == tile1 % GB_CL && (ty >> 3) == ((m + 1) & 1)) {
-                    const int sl1 = tile1 / GB_CL, i = ty + 16 * tile1;
-                    sl_done = sl1;
-                    double tmp[7];
+            const int par = m & 1, K0 = 8 * m, slot = m & (GB_SLOTS - 1);
+            gjb_mbar_wait(&sm.rawbar[slot], (unsigned)((m / GB_SLOTS) & 1));  // complete long ago; makes the async-proxy writes visible HERE
+            const double(*rw)[GB_NP] = sm.raw[slot];
+            const double(*mp)[GB_NR] = sm.MP[par][ty];  // [u][k]
+            // ---- look-ahead: the warp that owns this CTA's row of block m + 1 (local row m + 1) updates it first and publishes it ------
+            // (straight-line code on a copy of the row: with the row / column slot chosen by predicates inside the FMA loops ptxas
+            // serialised every shared-memory load with its FMA, 60 cycles per FMA)
+            int k_done = -1;
+            if (m + 1 < nblk && ty == ((m + 1) & 7)) {
+                const int k1 = (m + 1) >> 3, K1 = K0 + 8;
+                k_done = k1;
+                double row[7], mk[8];
 #pragma unroll
-                    for (int sl = 0; sl < GB_NSLOT; ++sl)
-                        if (sl == sl1) {
+                for (int b = 0; b < 7; ++b) {
+                    row[b] = acc[0][b];
 #pragma unroll
-                            for (int s = 0; s < 8; ++s) {
-                                const double mm = mrow[sl * 8 + s];
-#pragma unroll
-                                for (int b = 0; b < 7; ++b) acc[sl][b] = fma(mm, Gp[s][tx + 32 * b], acc[sl][b]);
-                            }
-#pragma unroll
-                            for (int b = 0; b < 7; ++b) tmp[b] = acc[sl][b];
-                        }
-                    if ((tx & ~7) == (K0 & 31)) {  // its entries in the pivot columns of step m: -G[s][i]  (i is unswept)
-                        const int sc = tx - (K0 & 31), b0 = K0 >> 5;
-                        const double v = -Gp[sc][i];
-#pragma unroll
-                        for (int b = 0; b < 7; ++b)
-                            if (b == b0) tmp[b] = v;
-                    }
-                    publish_row(m + 1, ty & 7, tmp);
+                    for (int k = 1; k < GB_NR; ++k) row[b] = (k == k1) ? acc[k][b] : row[b];
                 }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) mk[u] = mp[u][k1];
+                const bool pfo = a.prof && tx == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+                long long to0 = pfo ? clock64() : 0;
+                {
+                    // the block's own pivot columns first (lanes K1 & 31 .. + 7 of column slot K1 >> 5): they leave ahead of the row.  Same
+                    // operations in the same order as the row update below, so the two agree bit for bit.
+                    const int jp = (K1 & ~31) + tx;
+                    double pe = row[0];
+#pragma unroll
+                    for (int b = 1; b < 7; ++b) pe = gjb_sel(b == (K1 >> 5), row[b], pe);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) pe = fma(mk[u], rw[u][jp], pe);
+                    if (pfo) {
+                        const long long t1 = clock64();
+                        sm.pacc[14] += (t1 - to0);  // pivot columns of the row
+                        to0 = t1;
+                    }
+                    publish_pblock(m + 1, pe);
+                    if (pfo) {
+                        const long long t1 = clock64();
+                        sm.pacc[15] += (t1 - to0);  // pivot block handed to the copy unit
+                        to0 = t1;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                    for (int b = 0; b < 7; ++b) row[b] = fma(mk[u], rw[u][tx + 32 * b], row[b]);
+                }
+#pragma unroll
+                for (int b = 0; b < 7; ++b) {
+#pragma unroll
+                    for (int k = 0; k < GB_NR; ++k) acc[k][b] = (k == k1) ? row[b] : acc[k][b];
+                }
+                if (pfo) {
+                    const long long t1 = clock64();
+                    sm.pacc[13] += (t1 - to0);  // rest of the row
+                    to0 = t1;
+                }
+                // (its entries in the pivot columns of step m are -G[s][i] (i is unswept) = MP[i][s]: patched into the staged copy)
+                publish_row(m + 1, row, K0, mp[tx & 7][k1]);
+                if (pfo) sm.pacc[5] += (clock64() - to0);  // row handed to the copy unit
             }
             // ---- the rank-8 update of everything else this thread owns ---------------------------------------------------
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
+            // Straight-line: no branch per row.  Padding rows have zero multipliers in the table and the look-ahead row gets zeros
+            // here (x + 0 g = x exactly), so that all 18 shared-memory loads of two panel rows are in flight before the 56 FMAs (with
+            // a branch per row ptxas issued every multiplier load right in front of the FMAs that need it: 2.8 us per step).
+            const bool kd0 = k_done == 0, kd1 = k_done == 1, kd2 = k_done == 2, kd3 = k_done == 3;
+#pragma unroll 2  // (fully unrolled, ptxas hoists all 56 panel loads and spills)
+            for (int u = 0; u < 8; ++u) {
                 double g[7];
+                const double2 ma = *reinterpret_cast<const double2*>(&mp[u][0]), mb = *reinterpret_cast<const double2*>(&mp[u][2]);
 #pragma unroll
-                for (int b = 0; b < 7; ++b) g[b] = Gp[s][tx + 32 * b];
+                for (int b = 0; b < 7; ++b) g[b] = rw[u][tx + 32 * b];
+                const double m0 = gjb_sel(kd0, 0.0, ma.x), m1 = gjb_sel(kd1, 0.0, ma.y), m2 = gjb_sel(kd2, 0.0, mb.x), m3 = gjb_sel(kd3, 0.0, mb.y);
 #pragma unroll
-                for (int sl = 0; sl < GB_NSLOT; ++sl) {
-                    if (sl == sl_done) continue;  // warp-uniform
-                    const double mm = mrow[sl * 8 + s];
-#pragma unroll
-                    for (int b = 0; b < 7; ++b) acc[sl][b] = fma(mm, g[b], acc[sl][b]);
+                for (int b = 0; b < 7; ++b) {
+                    acc[0][b] = fma(m0, g[b], acc[0][b]);
+                    acc[1][b] = fma(m1, g[b], acc[1][b]);
+                    acc[2][b] = fma(m2, g[b], acc[2][b]);
+                    acc[3][b] = fma(m3, g[b], acc[3][b]);
                 }
             }
-            // ---- fix-ups: pivot rows <- G (P^-1 inside the block), pivot columns <- -sigma(i) G[s][i] ---------------------
-            const int tile0 = m >> 1;
-            const bool pivot_warp = (rank == tile0 % GB_CL) && ((ty >> 3) == (m & 1));
-            const int sl0 = tile0 / GB_CL;
-            if (pivot_warp) {
-                const int sr = ty & 7;
+            // ---- fix-ups: the pivot row <- G (P^-1 inside the block), pivot columns <- MP[i][s] ----------------------------
+            if (ty == (m & 7)) {  // this warp owns the CTA's pivot row: local row m, row `rank` of the block
+                const int k0 = m >> 3;
+                const double* pv = &sm.Pinv[par][rank * 8];
+                double v[7];
+#pragma unroll
+                for (int b = 0; b < 7; ++b) v[b] = 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double pu = pv[u];
+#pragma unroll
+                    for (int b = 0; b < 7; ++b) v[b] = fma(pu, rw[u][tx + 32 * b], v[b]);  // G[rank][j]
+                }
+                const double pin = pv[tx & 7];
 #pragma unroll
                 for (int b = 0; b < 7; ++b) {
                     const int j = tx + 32 * b;
-                    const double v = (j >= K0 && j < K0 + 8) ? sm.Pinv[par][sr * 8 + (j - K0)] : Gp[sr][j];
+                    const double vb = gjb_sel(j >= K0 && j < K0 + 8, pin, v[b]);
 #pragma unroll
-                    for (int sl = 0; sl < GB_NSLOT; ++sl)
-                        if (sl == sl0) acc[sl][b] = v;
+                    for (int k = 0; k < GB_NR; ++k) acc[k][b] = gjb_sel(k == k0, vb, acc[k][b]);
                 }
             }
             if ((tx & ~7) == (K0 & 31)) {
-                const int sc = tx - (K0 & 31), b0 = K0 >> 5;
+                const int sc = tx & 7, b0 = K0 >> 5;
 #pragma unroll
-                for (int sl = 0; sl < GB_NSLOT; ++sl) {
-                    const int tile = rank + GB_CL * sl, i = ty + 16 * tile;
-                    if (tile < GB_NP / 16 && !(i >= K0 && i < K0 + 8)) {
-                        const double g = Gp[sc][i];
-                        const double v = (i < K0) ? g : -g;
+                for (int k = 0; k < GB_NR; ++k) {
+                    const int l = ty + 8 * k;
+                    const bool fix = l < GB_LR && l != m;
+                    const double v = mp[sc][k];
 #pragma unroll
-                        for (int b = 0; b < 7; ++b)
-                            if (b == b0) acc[sl][b] = v;
-                    }
+                    for (int b = 0; b < 7; ++b) acc[k][b] = gjb_sel(fix && b == b0, v, acc[k][b]);
                 }
             }
             if (pfu) {
                 const long long t1 = clock64();
-                a.prof[59] = (m == 0 ? 0 : a.prof[59]) + (t1 - tu0);
+                sm.pacc[11] += (t1 - tu0);
                 tu0 = t1;
             }
         }
@@ -1055,20 +1132,20 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         if (!want_logdet) {
             float* Xg = a.Xbuf + ((long long)env * kDensePoles + pole) * n * n;
 #pragma unroll
-            for (int sl = 0; sl < GB_NSLOT; ++sl)
+            for (int k = 0; k < GB_NR; ++k)
 #pragma unroll
                 for (int b = 0; b < 7; ++b) {
                     const int j = tx + 32 * b;
-                    const int tile = rank + GB_CL * sl, i = ty + 16 * tile;
-                    if (tile < GB_NP / 16 && i < n && j <= i)  // (reversed positions: this is the upper triangle of the inverse)
-                        Xg[(long long)(n - 1 - i) * n + (n - 1 - j)] = (float)(wj * acc[sl][b]);
+                    const int l = ty + 8 * k, i = rank + GB_CL * l;
+                    if (l < GB_LR && i < n && j <= i)  // (reversed positions: this is the upper triangle of the inverse)
+                        Xg[(long long)(n - 1 - i) * n + (n - 1 - j)] = (float)(wj * acc[k][b]);
                 }
         } else if (rank == 0 && ty < 7) {  // log det A = sum of the logarithms of the scalar pivots (every CTA holds all of them)
             double lp = 0.0;
             const int i = tx + 32 * ty;
             if (i < n) lp = log(sm.piv[i]);
             lp = warp_sum_d(lp);
-            double* red = &sm.G[0][0][0];  // dead: every step is over for these warps' inputs
+            double* red = &sm.MP[0][0][0][0];  // dead: every step is over for these warps
             COVO_NAMED_BARRIER(3, 224);
             if (tx == 0) red[ty] = lp;
             COVO_NAMED_BARRIER(3, 224);
@@ -1081,6 +1158,8 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         if (tid == 0 && sm.bad) a.status[env] = 2;
     }
     gjb_cluster_wait();  // the arrive of the last step
+    __syncthreads();
+    if (a.prof && tid >= 5 && tid < 16 && blockIdx.x == 0 && blockIdx.y == 0) a.prof[48 + tid] = sm.pacc[tid];
     gjb_cluster_sync();  // nobody leaves while a peer could still be sending to it
 }
 

@@ -180,7 +180,7 @@ int covo_set_jax_key(covo_handle* h, const unsigned int* act_key);
 int covo_get_pos_stats(covo_handle* h, float* pos_mean, float* pos_std); /* info dict, controllers/covo.py:281; [E][H][3] each */
 int covo_enable_pos_stats(covo_handle* h, int on);
 int covo_debug_eps(covo_handle* h, unsigned int stream_id, float* eps);  /* the production-mode field, [N_local][4H] */
-int covo_debug_tridiag(covo_handle* h, double* d, double* e, double* scalars5); /* after covo_optimize_sigma, env 0 */
+int covo_debug_tridiag(covo_handle* h, double* d, double* e, double* scalars5); /* after covo_optimize_sigma / a step, env 0; dense path: d = e = 0, scalars5 = lambda_min, spectrum upper bound, log det A, Lanczos steps taken, 0 */
 int covo_zolotarev_nodes(double m, double M, int n_poles, double* shifts, double* weights); /* host only, no GPU */
 int covo_get_status(covo_handle* h, int* status); /* [E] numeric status of the last covariance step */
 /* ---- device-resident environment and closed loop -------------------------------------------
@@ -210,12 +210,12 @@ int covo_closed_loop(covo_handle* h, int n_steps, unsigned long long noise_seed,
 int covo_env_set_reset_pool(covo_handle* h, int n_pool, const float* state24, const int* time, const float* pos_traj, const float* vel_traj,
                             const float* a_mean_init);
 /* Which optimize_sigma (controllers/covo.py:116-132) kernels the handle runs:
- *   0 = tridiagonal path (default): Householder -> tridiagonal matrix function in float64 -> Q F Q^T.  Sigma within 1e-6 .. 1e-5
- *       (relative Frobenius) of exact arithmetic on the same float32 Hessian: the accuracy of the reference's float32 eigh.
- *   3 = dense FAST path: adaptive Lanczos lambda_min (float64) -> one float32 Gauss-Jordan inverse per pole of the rational
- *       approximation of x^(-1/2) -> combine.  0.16 ms less per step at H = 50; Sigma is symmetric positive definite with the exact
- *       determinant but only within 1e-4 (median) .. 5e-3 (worst seen over a 300-step closed loop) of exact arithmetic, because
- *       float32 inverses of matrices of condition 1e5 are no better.  Opt in with this call or COVO_SIGMA=dense. */
+ *   3 = dense path (default of a single-environment handle): adaptive Lanczos lambda_min (float64) -> one float64 Gauss-Jordan inverse
+ *       per pole of a 13-pole rational approximation of x^(-1/2), each on an 8-CTA cluster -> combine.  Sigma within 1e-7 .. 2e-7
+ *       (relative Frobenius) of exact arithmetic on the same float32 Hessian (the reference's float32 eigh: 4e-7 .. 1e-5).
+ *   0 = tridiagonal path (default of environment batches, 8 CTAs per matrix instead of 112): Householder -> tridiagonal matrix
+ *       function in float64 -> Q F Q^T.  Sigma within 1e-6 .. 1e-5 of exact arithmetic; 0.1 ms more per step at H = 50.
+ * COVO_SIGMA=dense / COVO_SIGMA=tridiag choose at handle creation. */
 int covo_get_sigma_path(covo_handle* h, int* path);
 /* Select the path (0 or 3).  The dense path needs a lowest eigenvalue that a Lanczos iteration finds within 64 steps (16 .. 52 on CoVO
  * Hessians; the kernel runs as many as the residual of the Ritz pair asks for).  If it does not converge, lambda_min is replaced by a

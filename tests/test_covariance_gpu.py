@@ -43,21 +43,22 @@ def test_hessian_vs_forward_over_forward_oracle(H, task, warm, time):
 DENSE_TOL = 1e-5  # the dense path (float64 pole inverses since round 2) is held to the tolerance of E1-E3
 
 
-@pytest.mark.parametrize("path", ["default", "dense"])
+@pytest.mark.parametrize("path", ["default", "tridiag", "dense"])
 @pytest.mark.parametrize("H", [50, 32, 8, 3])
 def test_optimize_sigma_and_cholesky(monkeypatch, H, path):
-    """optimize_sigma on both kernel paths: the default (tridiagonal, E1-E3: parity grade) and the opt-in fast one (COVO_SIGMA=dense:
-    adaptive Lanczos + one float32 Gauss-Jordan inverse per pole), which is held to its documented, looser accuracy."""
-    if path == "dense":
-        monkeypatch.setenv("COVO_SIGMA", "dense")
+    """optimize_sigma on both kernel paths, held to the same tolerance: the dense one (D1-D3: adaptive Lanczos + one float64 Gauss-Jordan
+    inverse per pole; the default of a single-environment handle) and the tridiagonal one (E1-E3; COVO_SIGMA=tridiag, batches)."""
+    monkeypatch.delenv("COVO_SIGMA", raising=False)
+    if path != "default":
+        monkeypatch.setenv("COVO_SIGMA", path)
     p, ns, a_mean, rng = scenario("tracking_zigzag", seed=7, H=H, warm_steps=15)
     n = 4 * H
     h = _handle(64, H, ns.pos_traj.shape[0])
-    assert h.sigma_path() == (3 if path == "dense" else 0)
+    assert h.sigma_path() == (0 if path == "tridiag" else 3)
     R = o.get_hessian(ns, a_mean, p, dtype=np.float64).astype(np.float32)
     S = h.optimize_sigma(R[None])[0]
     So = o.optimize_sigma(R.astype(np.float64), 0.5, np.float64)
-    tol = DENSE_TOL if path == "dense" else 1e-5
+    tol = DENSE_TOL if path != "tridiag" else 1e-5
     assert np.linalg.norm(S - So) / np.linalg.norm(So) < tol
     assert np.abs(S - So).max() < tol * np.abs(So).max()
     assert np.abs(S - S.T).max() == 0.0
@@ -74,13 +75,12 @@ def test_optimize_sigma_and_cholesky(monkeypatch, H, path):
     assert np.abs(np.triu(L, 1)).max() == 0.0
 
 
-@pytest.mark.parametrize("path", ["default", "dense"])
+@pytest.mark.parametrize("path", ["tridiag", "dense"])
 def test_sigma_random_symmetric_and_degenerate(monkeypatch, path):
     """Arbitrary symmetric input (not a CoVO Hessian: no separated lowest eigenvalue).  The tridiagonal path handles it directly; the
     dense path either converges (to its own accuracy) or detects that its Lanczos stage has not (status 3), in which case
     covo_optimize_sigma redoes the matrix on the tridiagonal path."""
-    if path == "dense":
-        monkeypatch.setenv("COVO_SIGMA", "dense")
+    monkeypatch.setenv("COVO_SIGMA", path)
     rng = np.random.default_rng(0)
     H = 16
     n = 4 * H
@@ -95,7 +95,7 @@ def test_sigma_random_symmetric_and_degenerate(monkeypatch, path):
             R = np.diag(rng.uniform(-1, 5, n)).astype(np.float32)  # already diagonal: every reflector is trivial
         S = h.optimize_sigma(R[None])[0]
         So = o.optimize_sigma(R.astype(np.float64), 0.5, np.float64)
-        assert np.linalg.norm(S - So) / np.linalg.norm(So) < (DENSE_TOL if path == "dense" else 2e-5), kind
+        assert np.linalg.norm(S - So) / np.linalg.norm(So) < 2e-5, kind
         assert h.status()[0] == 0
 
 

@@ -173,6 +173,7 @@ def test_batched_environments_match_single(E):
         cfg1 = _lib.default_config()
         cfg1.mode, cfg1.n_samples, cfg1.horizon, cfg1.traj_len = _lib.MODE_COVO_ONLINE, N, H, 320
         h1 = _lib.Handle(cfg1)
+        h1.set_sigma_path(hb.sigma_path())  # batches run the tridiagonal optimize_sigma kernels, a single environment the dense ones by default
         h1.set_reference(trajs[e][0][None], trajs[e][1][None])
         h1.set_mean(means[e][None])
         act1 = h1.step(states[e], [times[e]], eps_all[e][None])

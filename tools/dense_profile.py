@@ -38,9 +38,12 @@ def main():
     d = lambda a, b: round((c[b] - c[a]) / mhz, 2)
     print("lanczos: load", d(48, 49), "iterations", d(49, 50), "multisection", d(50, 51), "us")
     print("lanczos exchange (send + mbarrier wait, all iterations, CTA 0 thread 0):", round(c[52] / mhz, 2), "us")
-    print("gjb (CTA 0): solver wait-for-rows", round(c[54] / mhz, 2), "inversion", round(c[55] / mhz, 2), "G", round(c[56] / mhz, 2),
-          "solver at step barrier", round(c[57] / mhz, 2), "| update warp 0: at step barrier", round(c[58] / mhz, 2), "update", round(c[59] / mhz, 2), "us (sums over the steps)")
-    print("raw stamps 48..59:", [int(x) for x in c[48:60]])
+    us = lambda k: round(c[k] / mhz, 2)
+    print("gjb (CTA 0, sums over the 25 steps, us): solver warp 0: wait for the pivot block", us(54), "8x8 inversion", us(55), "wait for the rows + P^-1 barrier", us(60),
+          "multipliers", us(56), "step barrier", us(57), "| update warp 0: at step barrier", us(58), "open -> step done", us(59))
+    print("gjb look-ahead on the owning CTA (its own clock, sums over 24 blocks, us): pivot columns", us(62), "pivot block to the copy unit", us(63), "rest of the row", us(61),
+          "row to the copy unit", us(53))
+    print("raw stamps 48..63:", [int(x) for x in c[48:64]])
 
 
 if __name__ == "__main__":
