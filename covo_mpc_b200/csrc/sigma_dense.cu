@@ -781,7 +781,6 @@ struct GjbSmem {
     double stage[2][GB_NP];           // this CTA's pivot row on its way out (by block parity): source of the bulk copies
     double MP[2][8][8][GB_NR];        // [parity][ty][u][k]: -sigma(i) G[u][i] for the local row ty + 8 k; 0 for the pivot row and padding
     double Pblk[GB_SLOTS][8][8];      // the 8 x 8 pivot blocks, sent ahead of the rows
-    double Pst[2][8];                 // ... this CTA's row of them on its way out
     double Pinv[2][64];
     double piv[GB_NP];
     unsigned long long rawbar[GB_SLOTS];
@@ -865,19 +864,30 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                     sm.pacc[6] += (t1 - t0);
                     t0 = t1;
                 }
-                // P^-1 by an in-place Gauss-Jordan sweep of the 8 x 8 block: lane = (row r, columns c0, c0 + 1)
+                // P^-1 by an in-place Gauss-Jordan sweep of the 8 x 8 block: lane = (row r, columns c0, c0 + 1).  The reciprocal of
+                // the NEXT pivot is started as soon as this pivot's is known -- P'[s+1][s+1] = P[s+1][s+1] - (P[s+1][s] / p) P[s][s+1] is the
+                // very operation the sweep applies to that entry -- so the dependent chain per pivot is multiply, FMA, reciprocal
+                // instead of shuffle, reciprocal, multiply, FMA, shuffle.
                 const int r = lane >> 2, c0 = (lane & 3) * 2;
                 double x0 = sm.Pblk[slot][r][c0], x1 = sm.Pblk[slot][r][c0 + 1];
                 double pvs[8];  // the scalar pivots (log det, positivity): written out after the chain, not inside it
+                pvs[0] = __shfl_sync(0xffffffffu, x0, 0);
+                double rinv = gjb_rcp64(pvs[0]);
 #pragma unroll
                 for (int sp = 0; sp < 8; ++sp) {
                     const double mine = (sp & 1) ? x1 : x0;
-                    const double p = __shfl_sync(0xffffffffu, mine, (sp << 2) | (sp >> 1));
                     const double prs = __shfl_sync(0xffffffffu, mine, (r << 2) | (sp >> 1));   // P[r][sp]
                     const double ps0 = __shfl_sync(0xffffffffu, x0, (sp << 2) | (lane & 3));   // P[sp][c0]
                     const double ps1 = __shfl_sync(0xffffffffu, x1, (sp << 2) | (lane & 3));   // P[sp][c0 + 1]
-                    pvs[sp] = p;
-                    const double rinv = gjb_rcp64(p);
+                    double rinv_next = 0.0;
+                    if (sp < 7) {
+                        const double mine1 = ((sp + 1) & 1) ? x1 : x0;
+                        const double pa = __shfl_sync(0xffffffffu, mine, ((sp + 1) << 2) | (sp >> 1));          // P[sp + 1][sp]
+                        const double pb = __shfl_sync(0xffffffffu, mine1, (sp << 2) | ((sp + 1) >> 1));         // P[sp][sp + 1]
+                        const double pc = __shfl_sync(0xffffffffu, mine1, ((sp + 1) << 2) | ((sp + 1) >> 1));   // P[sp + 1][sp + 1]
+                        pvs[sp + 1] = fma(-(pa * rinv), pb, pc);
+                        rinv_next = gjb_rcp64(pvs[sp + 1]);
+                    }
                     if (r == sp) {
                         x0 = (c0 == sp) ? rinv : ps0 * rinv;
                         x1 = (c0 + 1 == sp) ? rinv : ps1 * rinv;
@@ -886,6 +896,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                         x0 = (c0 == sp) ? -f : fma(-f, ps0, x0);
                         x1 = (c0 + 1 == sp) ? -f : fma(-f, ps1, x1);
                     }
+                    rinv = rinv_next;
                 }
                 sm.Pinv[par][r * 8 + c0] = x0;
                 sm.Pinv[par][r * 8 + c0 + 1] = x1;
@@ -919,13 +930,17 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
 #pragma unroll
                 for (int v = 0; v < 8; ++v) col[v] = live ? rw[v][i] : 0.0;
                 const double sgn = (l < m) ? 1.0 : -1.0;
-                const double* pv = &sm.Pinv[par][u0 * 8];
-                double g0 = 0.0, g1 = 0.0;
+                const double2* pv = reinterpret_cast<const double2*>(&sm.Pinv[par][u0 * 8]);  // rows u0, u0 + 1 of P^-1
+                double g0a = 0.0, g0b = 0.0, g1a = 0.0, g1b = 0.0;
 #pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    g0 = fma(pv[v], col[v], g0);
-                    g1 = fma(pv[8 + v], col[v], g1);
+                for (int v = 0; v < 4; ++v) {
+                    const double2 pu = pv[v], pw = pv[4 + v];
+                    g0a = fma(pu.x, col[2 * v], g0a);
+                    g0b = fma(pu.y, col[2 * v + 1], g0b);
+                    g1a = fma(pw.x, col[2 * v], g1a);
+                    g1b = fma(pw.y, col[2 * v + 1], g1b);
                 }
+                const double g0 = g0a + g0b, g1 = g1a + g1b;
                 sm.MP[par][ty][u0][k] = live ? sgn * g0 : 0.0;
                 sm.MP[par][ty][u0 + 1][k] = live ? sgn * g1 : 0.0;
             }
@@ -945,11 +960,9 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         const float* Ag = a.Asym ? a.Asym + (long long)env * n * n : nullptr;
         const float* Rg = a.R + (long long)env * n * n;
         double acc[GB_NR][7];
-        bool row_live[GB_NR];  // warp-uniform: the row exists (not padding beyond n)
 #pragma unroll
         for (int k = 0; k < GB_NR; ++k) {
             const int l = ty + 8 * k, i = rank + GB_CL * l;
-            row_live[k] = l < GB_LR && i < n;
 #pragma unroll
             for (int b = 0; b < 7; ++b) {
                 const int j = tx + 32 * b;
@@ -967,16 +980,15 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
             }
         }
         // This CTA's row of a block leaves as ONE bulk copy per destination CTA (this one included): staged in shared memory, fenced
-        // for the async proxy; its eight entries in the block's own pivot columns travel ahead as a 64-byte copy of their own
-        // (lanes 0..7: one destination each)
-        auto publish_pblock = [&](int blk, double v) {  // called by all lanes of one warp; the lanes holding the block's columns pass their entry
+        // for the async proxy; its eight entries in the block's own pivot columns travel ahead as st.async stores
+        auto publish_pblock = [&](int blk, double v) {  // called by all lanes of one warp; the lanes holding the block's columns send their entry
             const int K1 = 8 * blk;
-            if ((tx & ~7) == (K1 & 31)) sm.Pst[blk & 1][tx & 7] = v;
-            gjb_fence_async_proxy();
-            __syncwarp();
-            if (tx < GB_CL) {
+            if ((tx & ~7) == (K1 & 31)) {
+                // straight from the register into every CTA's copy of the block: st.async needs no staging and no proxy fence (the
+                // staged 64-byte bulk copy took 0.38 us from here to the copy unit)
                 const int slot = blk & (GB_SLOTS - 1);
-                gjb_bulk_send(&sm.Pblk[slot][rank][0], &sm.Pst[blk & 1][0], 64, (unsigned)tx, &sm.pbar[slot]);
+#pragma unroll
+                for (int r = 0; r < GB_CL; ++r) gjb_send64(&sm.Pblk[slot][rank][tx & 7], (unsigned)r, v, &sm.pbar[slot]);
             }
         };
         auto publish_row = [&](int blk, const double (&vals)[7], int Kfix, double vfix) {

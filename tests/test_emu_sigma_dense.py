@@ -30,7 +30,7 @@ def _emu_lib():
 
 
 def test_dense_sigma_at_the_headline_size(variant=3):
-    """n = 200 (H = 50): the production kernels (8-CTA cluster Lanczos with its checker warp, blocked Gauss-Jordan on a 4-CTA cluster
+    """n = 200 (H = 50): the production kernels (8-CTA cluster Lanczos with its checker warp, float64 blocked Gauss-Jordan on an 8-CTA cluster
     per pole) run with all CTAs of a cluster interleaved."""
     emu = _emu_lib()
     p, ns, a_mean, rng = scenario("tracking_zigzag", seed=3, H=50, warm_steps=6)
@@ -44,7 +44,7 @@ def test_dense_sigma_at_the_headline_size(variant=3):
     assert rc == 0 and status[0] == 0 and np.isfinite(cov).all()
     lam = np.linalg.eigvalsh(0.5 * (R + R.T).astype(np.float64))
     assert abs(scal[0] - lam[0]) < 2e-8 and kFirstCheck <= scal[3] <= 64  # adaptive Lanczos: converged, and says how many steps it took
-    assert np.linalg.norm(cov - S_ref) / np.linalg.norm(S_ref) < 5e-6
+    assert np.linalg.norm(cov - S_ref) / np.linalg.norm(S_ref) < 1e-6
 
 
 def _zolo_table():
@@ -97,4 +97,4 @@ def test_adaptive_lanczos_on_a_hessian_that_defeats_24_steps():
                              status.ctypes.data_as(C.POINTER(C.c_int)), 3)
     assert rc == 0 and status[0] == 0
     assert scal[3] > 24 and abs(scal[0] - lam[0]) < 2e-8
-    assert np.linalg.norm(cov - S_ref) / np.linalg.norm(S_ref) < 6e-3  # float32 inverses at cond(A) = 1.6e5: the fast path's documented accuracy
+    assert np.linalg.norm(cov - S_ref) / np.linalg.norm(S_ref) < 1e-6  # float64 inverses: what is left is the 13-pole approximation (2e-7)

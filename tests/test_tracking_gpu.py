@@ -261,9 +261,10 @@ def test_covo_online_full_episode_teacher_forced():
 
 
 def test_dense_fast_path_closed_loop_accuracy():
-    """The opt-in fast optimize_sigma path (covo_set_sigma_path(h, 3)) along the first 60 steps of the same closed loop: every step
-    converges (no status: the adaptive Lanczos stage takes 16 .. 52 steps on these Hessians, where a fixed 24 left A indefinite at
-    step 57), Sigma stays within the path's documented distance of the float64 truth, and the actions within what that implies."""
+    """The dense optimize_sigma path (covo_set_sigma_path(h, 3); the default of a single-environment handle) along the first 60 steps of
+    the same closed loop: every step converges (no status: the adaptive Lanczos stage takes 16 .. 52 steps on these Hessians, where a
+    fixed 24 left A indefinite at step 57) and Sigma stays as close to the float64 truth as the tridiagonal path does (the float32
+    Hessian is what separates both from it: median 5e-6, max 5e-5 measured)."""
     from covo_mpc_b200 import _lib
 
     p = o.EnvParams()
@@ -289,13 +290,13 @@ def test_dense_fast_path_closed_loop_accuracy():
         if gap >= TIE:
             act.append(float(np.abs(a_dev - a_64).max()))
         s_dev, _, _, _ = o.env_step(s_dev, a_dev, p, tp.SeqRng(noise[i + 1, 13:16]), "none")
-    msg = (f"[covo-online FAST sigma path, {steps} steps teacher-forced vs float64 truth] Sigma rel. Frobenius error median {np.median(sig):.2e} "
+    msg = (f"[covo-online dense sigma path, {steps} steps teacher-forced vs float64 truth] Sigma rel. Frobenius error median {np.median(sig):.2e} "
            f"max {np.max(sig):.2e}; action error over {len(act)} steps median {np.median(act):.2e} max {np.max(act):.2e}")
     print(msg)
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):
         with open(os.path.join(out, "tracking_parity.log"), "a") as f:
             f.write(msg + "\n")
-    assert np.median(sig) < 1e-3 and np.max(sig) < 1e-2
-    assert np.median(act) < 2e-4 and np.max(act) < 2e-2
+    assert np.median(sig) < 2e-5 and np.max(sig) < 3e-4
+    assert np.median(act) < 1e-4 and np.max(act) < 5e-3
     h.close()
