@@ -776,6 +776,11 @@ constexpr int GB_NP = 224;   // padded order: 28 local rows in each of the 8 CTA
 constexpr int GB_LR = GB_NP / GB_CL;  // local rows per CTA
 constexpr int GB_SLOTS = 4;
 
+template <int V>
+struct IntC {
+    static constexpr int value = V;
+};
+
 struct GjbSmem {
     double raw[GB_SLOTS][8][GB_NP];   // pivot-row panels [s][j]: row s comes from CTA s
     double stage[2][GB_NP];           // this CTA's pivot row on its way out (by block parity): source of the bulk copies
@@ -979,6 +984,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 acc[k][b] = v;
             }
         }
+        const bool has_row3 = rank + GB_CL * (ty + 24) < n;  // warp-uniform: the fourth row of this warp is a row of the matrix (not padding)
         // This CTA's row of a block leaves as ONE bulk copy per destination CTA (this one included): staged in shared memory, fenced
         // for the async proxy; its eight entries in the block's own pivot columns travel ahead as st.async stores
         auto publish_pblock = [&](int blk, double v) {  // called by all lanes of one warp; the lanes holding the block's columns send their entry
@@ -1079,28 +1085,34 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 }
                 // (its entries in the pivot columns of step m are -G[s][i] (i is unswept) = MP[i][s]: patched into the staged copy)
                 publish_row(m + 1, row, K0, mp[tx & 7][k1]);
-                if (pfo) sm.pacc[5] += (clock64() - to0);  // row handed to the copy unit
             }
             // ---- the rank-8 update of everything else this thread owns ---------------------------------------------------
             // Straight-line: no branch per row.  Padding rows have zero multipliers in the table and the look-ahead row gets zeros
             // here (x + 0 g = x exactly), so that all 18 shared-memory loads of two panel rows are in flight before the 56 FMAs (with
             // a branch per row ptxas issued every multiplier load right in front of the FMAs that need it: 2.8 us per step).
             const bool kd0 = k_done == 0, kd1 = k_done == 1, kd2 = k_done == 2, kd3 = k_done == 3;
+            long long tb0 = pfu ? clock64() : 0;
+            auto bulk = [&](auto WITH3) {  // (two straight-line instances: only warp 0 of a CTA has a real fourth row at n = 200)
+                constexpr bool with3 = decltype(WITH3)::value != 0;
 #pragma unroll 2  // (fully unrolled, ptxas hoists all 56 panel loads and spills)
-            for (int u = 0; u < 8; ++u) {
-                double g[7];
-                const double2 ma = *reinterpret_cast<const double2*>(&mp[u][0]), mb = *reinterpret_cast<const double2*>(&mp[u][2]);
+                for (int u = 0; u < 8; ++u) {
+                    double g[7];
+                    const double2 ma = *reinterpret_cast<const double2*>(&mp[u][0]), mb = *reinterpret_cast<const double2*>(&mp[u][2]);
 #pragma unroll
-                for (int b = 0; b < 7; ++b) g[b] = rw[u][tx + 32 * b];
-                const double m0 = gjb_sel(kd0, 0.0, ma.x), m1 = gjb_sel(kd1, 0.0, ma.y), m2 = gjb_sel(kd2, 0.0, mb.x), m3 = gjb_sel(kd3, 0.0, mb.y);
+                    for (int b = 0; b < 7; ++b) g[b] = rw[u][tx + 32 * b];
+                    const double m0 = gjb_sel(kd0, 0.0, ma.x), m1 = gjb_sel(kd1, 0.0, ma.y), m2 = gjb_sel(kd2, 0.0, mb.x), m3 = gjb_sel(kd3, 0.0, mb.y);
 #pragma unroll
-                for (int b = 0; b < 7; ++b) {
-                    acc[0][b] = fma(m0, g[b], acc[0][b]);
-                    acc[1][b] = fma(m1, g[b], acc[1][b]);
-                    acc[2][b] = fma(m2, g[b], acc[2][b]);
-                    acc[3][b] = fma(m3, g[b], acc[3][b]);
+                    for (int b = 0; b < 7; ++b) {
+                        acc[0][b] = fma(m0, g[b], acc[0][b]);
+                        acc[1][b] = fma(m1, g[b], acc[1][b]);
+                        acc[2][b] = fma(m2, g[b], acc[2][b]);
+                        if (with3) acc[3][b] = fma(m3, g[b], acc[3][b]);
+                    }
                 }
-            }
+            };
+            if (has_row3) bulk(IntC<1>());
+            else bulk(IntC<0>());
+            if (pfu) sm.pacc[5] += clock64() - tb0;  // the bulk update alone
             // ---- fix-ups: the pivot row <- G (P^-1 inside the block), pivot columns <- MP[i][s] ----------------------------
             if (ty == (m & 7)) {  // this warp owns the CTA's pivot row: local row m, row `rank` of the block
                 const int k0 = m >> 3;

@@ -10,7 +10,8 @@ python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${TAG}_bench
 # launch list of the bench command (kernel nodes of the replayed step graph are listed like direct launches)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-subrecords > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
-# full capture of the 9 kernels of the fourth step of tools/one_step.py (direct launches: COVO_GRAPH=0, so -s counts kernels only)
-COVO_GRAPH=0 ncu --set full --clock-control none --import-source on -s 27 -c 9 -o gpurun_out/${TAG}_step_full python tools/one_step.py > gpurun_out/${TAG}_one_step_under_ncu.log 2>&1
-# the fast optimize_sigma path (D1-D3): hessian(3) + lanczos + inverses + combine + cholesky + rollout = 8 kernels per step
-COVO_GRAPH=0 COVO_SIGMA=dense ncu --set full --clock-control none --import-source on -s 24 -c 8 -o gpurun_out/${TAG}_step_full_dense python tools/one_step.py > gpurun_out/${TAG}_one_step_dense_under_ncu.log 2>&1
+# full capture of one whole step of tools/one_step.py (direct launches: COVO_GRAPH=0, so -s counts kernels only).
+# default optimize_sigma path of a single environment (dense, D1-D3): hessian(3) + lanczos + inverses + combine + cholesky + rollout = 8 kernels per step
+COVO_GRAPH=0 ncu --set full --clock-control none --import-source on -s 24 -c 8 -o gpurun_out/${TAG}_step_full python tools/one_step.py > gpurun_out/${TAG}_one_step_under_ncu.log 2>&1
+# the tridiagonal path (E1-E3, the default of environment batches): 9 kernels per step
+COVO_GRAPH=0 COVO_SIGMA=tridiag ncu --set full --clock-control none --import-source on -s 27 -c 9 -o gpurun_out/${TAG}_step_full_tridiag python tools/one_step.py > gpurun_out/${TAG}_one_step_tridiag_under_ncu.log 2>&1

@@ -41,8 +41,8 @@ def main():
     us = lambda k: round(c[k] / mhz, 2)
     print("gjb (CTA 0, sums over the 25 steps, us): solver warp 0: wait for the pivot block", us(54), "8x8 inversion", us(55), "wait for the rows + P^-1 barrier", us(60),
           "multipliers", us(56), "step barrier", us(57), "| update warp 0: at step barrier", us(58), "open -> step done", us(59))
-    print("gjb look-ahead on the owning CTA (its own clock, sums over 24 blocks, us): pivot columns", us(62), "pivot block to the copy unit", us(63), "rest of the row", us(61),
-          "row to the copy unit", us(53))
+    print("gjb look-ahead on the owning CTA (its own clock, sums over 24 blocks, us): pivot columns", us(62), "pivot block to the copy unit", us(63), "rest of the row", us(61))
+    print("gjb bulk rank-8 update alone (update warp 0, sum over 25 steps, us):", us(53))
     print("raw stamps 48..63:", [int(x) for x in c[48:64]])
 
 
