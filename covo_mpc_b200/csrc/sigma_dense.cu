@@ -478,6 +478,11 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
     const int n = a.n, tid = threadIdx.x, env = blockIdx.y, lane = tid & 31, warp = tid >> 5;
     const int rank = (int)gjb_rank();
     const int k_max = min(kLanczosMax, n);
+#if !defined(COVO_CPU_EMU)
+    // programmatic dependent launch: the pole-inverse kernel may become resident now and load its copy of the matrix while this
+    // recurrence runs; it waits (griddepcontrol.wait) for lambda_min before it shifts the diagonal
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     DENSE_STAMP(48);
     if (tid == 0) {
         gjb_mbar_init(&sm.bar[0], 1);
@@ -821,21 +826,6 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
     const int n = a.n, tid = threadIdx.x, env = blockIdx.y, pole = blockIdx.x / GB_CL;
     const int rank = (int)gjb_rank();
     const int nblk = (n + 7) >> 3;
-    const double lam_min = a.scal[(long long)env * 4 + 0], lam_max = a.scal[(long long)env * 4 + 1];
-    int lad = 0;
-    {
-        const double Mb = 1.02 * (lam_max - lam_min) + kOffset;
-        double Mi = kOffset * (1.0 - 1e-7) * 256.0;
-        while (lad < kZoloLadder - 1 && Mi < Mb) {
-            Mi *= 4.0;
-            ++lad;
-        }
-        if (Mi < Mb && tid == 0 && rank == 0) a.status[env] = 1;
-    }
-    const double* zt = a.zolo + (size_t)lad * 2 * kDensePoles;
-    const bool want_logdet = pole == kDensePoles;
-    const double shift = (kOffset - lam_min) + (want_logdet ? 0.0 : zt[pole]);
-    const double wj = want_logdet ? 0.0 : zt[kDensePoles + pole];
     if (tid < 16) sm.pacc[tid] = 0;
     if (tid == 0) {
         sm.bad = 0;
@@ -853,6 +843,9 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
     if (tid >= GB_UT) {
         // ================================================ solver warps ================================================
         const int sidx = tid - GB_UT, lane = sidx & 31, swarp = sidx >> 5;
+#if !defined(COVO_CPU_EMU)
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // (the update warps wait where they need lambda_min; nothing here reads it)
+#endif
         for (int m = 0; m < nblk; ++m) {
             const int slot = m & (GB_SLOTS - 1), par = m & 1;
             const unsigned ring_par = (unsigned)((m / GB_SLOTS) & 1);
@@ -962,7 +955,6 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
     } else {
         // ================================================ update warps ================================================
         const int tx = tid & 31, ty = tid >> 5;
-        const float* Ag = a.Asym ? a.Asym + (long long)env * n * n : nullptr;
         const float* Rg = a.R + (long long)env * n * n;
         double acc[GB_NR][7];
 #pragma unroll
@@ -977,12 +969,37 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                     // that was the most accurate one in float32, tools/studies/gj_accuracy.py; kept: the combine kernel and the
                     // tests know the triangle it produces)
                     const int ir = n - 1 - i, jr = n - 1 - j;
-                    const float vf = Ag ? Ag[(long long)ir * n + jr] : 0.5f * (Rg[(long long)ir * n + jr] + Rg[(long long)jr * n + ir]);
-                    v = (double)vf;
-                    if (i == j) v += shift;
+                    // (R + R^T)/2 in float32, controllers/covo.py:117 -- formed here, not read from the Lanczos kernel: it is still running
+                    v = (double)(0.5f * (__ldg(Rg + (long long)ir * n + jr) + __ldg(Rg + (long long)jr * n + ir)));
                 }
                 acc[k][b] = v;
             }
+        }
+#if !defined(COVO_CPU_EMU)
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // lambda_min (the Lanczos kernel has completed and flushed)
+#endif
+        const double lam_min = a.scal[(long long)env * 4 + 0], lam_max = a.scal[(long long)env * 4 + 1];
+        int lad = 0;
+        {
+            const double Mb = 1.02 * (lam_max - lam_min) + kOffset;
+            double Mi = kOffset * (1.0 - 1e-7) * 256.0;
+            while (lad < kZoloLadder - 1 && Mi < Mb) {
+                Mi *= 4.0;
+                ++lad;
+            }
+            if (Mi < Mb && tid == 0 && rank == 0) a.status[env] = 1;
+        }
+        const double* zt = a.zolo + (size_t)lad * 2 * kDensePoles;
+        const bool want_logdet = pole == kDensePoles;
+        const double shift = (kOffset - lam_min) + (want_logdet ? 0.0 : zt[pole]);
+        const double wj = want_logdet ? 0.0 : zt[kDensePoles + pole];
+        // the shift of this pole on the diagonal: position (i, i) sits in column slot i >> 5, lane i & 31
+#pragma unroll
+        for (int k = 0; k < GB_NR; ++k) {
+            const int l = ty + 8 * k, i = rank + GB_CL * l;
+#pragma unroll
+            for (int b = 0; b < 7; ++b)
+                if (l < GB_LR && i < n && i == tx + 32 * b) acc[k][b] += shift;
         }
         const bool has_row3 = rank + GB_CL * (ty + 24) < n;  // warp-uniform: the fourth row of this warp is a row of the matrix (not padding)
         // This CTA's row of a block leaves as ONE bulk copy per destination CTA (this one included): staged in shared memory, fenced
@@ -1152,6 +1169,9 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 tu0 = t1;
             }
         }
+#if !defined(COVO_CPU_EMU)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the combine kernel may become resident; it waits for this grid to complete
+#endif
         // ---- results ---------------------------------------------------------------------------------------------------------
         if (!want_logdet) {
             float* Xg = a.Xbuf + ((long long)env * kDensePoles + pole) * n * n;
@@ -1192,6 +1212,9 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
 // ---------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) combine_kernel(const DenseArgs a) {
     const int n = a.n, env = blockIdx.y;
+#if !defined(COVO_CPU_EMU)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
     const double logdet = a.scal[(long long)env * 4 + 2];
     // controllers/covo.py:123-127: log_const = (2 * n * 2 log(sigma) + sum log o) / n;  Sigma = exp(log_const / 2) A^(-1/2)
     const double log_const = (4.0 * (double)n * log((double)a.sample_sigma) + logdet) / (double)n;
@@ -1232,7 +1255,10 @@ cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, in
     a.status = s.status;
     a.prof = s.prof;
     cudaError_t e;
-    a.Asym = s.F;  // the symmetrised matrix, written by the Lanczos kernel (F is unused on this path)
+    a.Asym = nullptr;  // (the pole-inverse kernel symmetrises R itself: it loads the matrix while the Lanczos kernel is still running)
+    // COVO_DENSE_PDL=0: plain stream order between the three kernels; also when the batch does not fit the device next to the Lanczos clusters
+    static const bool pdl_env = !(getenv("COVO_DENSE_PDL") && getenv("COVO_DENSE_PDL")[0] == '0');
+    const bool pdl = pdl_env && n_env == 1;
     {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(LC_CL, n_env);
@@ -1259,20 +1285,35 @@ cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, in
         cfg.blockDim = dim3(GB_T);
         cfg.dynamicSmemBytes = sizeof(GjbSmem);
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        // programmatic dependent launch behind the Lanczos kernel: the clusters become resident next to it (8 + 112 CTAs of one per SM),
+        // set up their barriers and load the matrix while the recurrence runs; griddepcontrol.wait in the kernel before lambda_min is read
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = GB_CL;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = pdl ? 2 : 1;
         e = cudaLaunchKernelEx(&cfg, gjb_inverse_kernel, a);
         if (e != cudaSuccess) return e;
     }
     if (ev_mid2) cudaEventRecord(ev_mid2, st);
-    const int npairs = a.n * (a.n + 1) / 2;
-    combine_kernel<<<dim3((npairs + 255) / 256, n_env), 256, 0, st>>>(a);
-    return cudaGetLastError();
+    {
+        const int npairs = a.n * (a.n + 1) / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((npairs + 255) / 256, n_env);
+        cfg.blockDim = dim3(256);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        e = cudaLaunchKernelEx(&cfg, combine_kernel, a);
+    }
+    return e;
 }
 
 #endif
