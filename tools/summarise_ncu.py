@@ -27,7 +27,7 @@ def to_bytes(v, unit):
 
 def main():
     rep, tag = sys.argv[1], sys.argv[2]
-    merge = len(sys.argv) > 3 and sys.argv[3] == "--merge-traffic"  # add this capture's kernels to profiles/ncu_traffic.json (fast-path capture)
+    merge = len(sys.argv) > 3 and sys.argv[3] == "--merge-traffic"  # add the kernels only this capture has to profiles/ncu_traffic.json (other optimize_sigma path)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -41,7 +41,8 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     traffic = {}
     if merge and os.path.exists(tpath):
-        traffic = {k: v for k, v in json.load(open(tpath)).items() if k not in ("lanczos", "pole_inverses", "combine")}
+        traffic = json.load(open(tpath))
+    known = set(traffic)  # merge mode: this capture only contributes the kernels the first one did not contain
     seen = set()
     lines = ["| kernel | " + " | ".join(k.split(".")[0].replace("smsp__average_warps_issue_stalled_", "stall_").replace("_per_issue_active", "") for k in KEYS) + " |",
              "|" + "---|" * (len(KEYS) + 1)]
@@ -59,7 +60,7 @@ def main():
         for pat, g in GROUP.items():
             if pat in name:
                 b = to_bytes(r[ci["dram__bytes_read.sum"]], units[ci["dram__bytes_read.sum"]]) + to_bytes(r[ci["dram__bytes_write.sum"]], units[ci["dram__bytes_write.sum"]])
-                if merge and g not in ("lanczos", "pole_inverses", "combine"):
+                if merge and g in known:
                     continue
                 traffic[g] = (traffic.get(g, 0) if g in seen else 0) + int(b)
                 seen.add(g)
