@@ -138,6 +138,11 @@ __device__ __forceinline__ void gjb_bulk_send(void* dst_local, const void* src_l
                  : "memory");
 }
 __device__ __forceinline__ void gjb_fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// tx-count of an mbarrier of THIS CTA, for data its own threads stored with ordinary stores (release fence first; the waiters acquire)
+__device__ __forceinline__ void gjb_mbar_complete_tx_local(unsigned long long* b, unsigned bytes) {
+    __threadfence_block();
+    asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(gjb_s32(b)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ float gjb_rcp(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -494,7 +499,8 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
     }
     if (warp == LC_T / 32) {
         // ================================================ the checker ================================================
-        __syncthreads();
+        // (one cluster barrier per role, none of the CTA-wide kind: a __syncthreads() in each branch of the role split is what the
+        // hardware executes happily and what synccheck reports as a barrier in divergent code)
         gjb_cluster_sync();
         int c = min(kLanczosFirstCheck, k_max), c_prev = 0;
         for (;;) {
@@ -589,11 +595,10 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
                 }
             }
         }
-        __syncthreads();
+        gjb_cluster_sync();  // the start vector is in place here, the mbarriers are initialised everywhere: before the first read / send
         double vj = has_row ? sm.v[0][row] : 0.0, vprev = 0.0;  // row leaders keep v_k[row], v_{k-1}[row]
         const int n_warps_total = LC_CL * 4;
         const int tx_bytes = n * 8 + n_warps_total * 16;
-        gjb_cluster_sync();  // barriers initialised everywhere before the first send
         DENSE_STAMP(49);
         int kdone = 0;
         double beta_prev = 0.0;
@@ -948,7 +953,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 t0 = t1;
             }
             if (m > 0) gjb_cluster_wait();
-            __syncthreads();  // opens step m for the update warps
+            COVO_NAMED_BARRIER(2, GB_T);  // opens step m for the update warps (named: the two roles arrive from different code)
             gjb_cluster_arrive();
             if (pf) sm.pacc[9] += (clock64() - t0);
         }
@@ -1015,16 +1020,28 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
             }
         };
         auto publish_row = [&](int blk, const double (&vals)[7], int Kfix, double vfix) {
+            const int slot = blk & (GB_SLOTS - 1);
             double* st = sm.stage[blk & 1];
 #pragma unroll
             for (int b = 0; b < 7; ++b) st[tx + 32 * b] = vals[b];
             if (Kfix >= 0 && (tx & ~7) == (Kfix & 31)) st[(Kfix & ~31) + tx] = vfix;  // same thread, same address: program order
+#if defined(COVO_CPU_EMU)
+            __syncwarp();
+            if (tx < GB_CL) gjb_bulk_send(&sm.raw[slot][rank][0], st, GB_NP * 8, (unsigned)tx, &sm.rawbar[slot]);
+#else
+            // this CTA's own copy of the row: ordinary stores + a local complete_tx (a bulk copy to the CTA's own shared::cluster address works
+            // on the hardware but compute-sanitizer's memcheck rejects it as "not located in remote CTA", tools/microbench/dsmem_latency.cu)
+            double* own = &sm.raw[slot][rank][0];
+#pragma unroll
+            for (int b = 0; b < 7; ++b) own[tx + 32 * b] = vals[b];
+            if (Kfix >= 0 && (tx & ~7) == (Kfix & 31)) own[(Kfix & ~31) + tx] = vfix;
             gjb_fence_async_proxy();
             __syncwarp();
             if (tx < GB_CL) {
-                const int slot = blk & (GB_SLOTS - 1);
-                gjb_bulk_send(&sm.raw[slot][rank][0], st, GB_NP * 8, (unsigned)tx, &sm.rawbar[slot]);
+                if (tx != rank) gjb_bulk_send(&sm.raw[slot][rank][0], st, GB_NP * 8, (unsigned)tx, &sm.rawbar[slot]);
+                else gjb_mbar_complete_tx_local(&sm.rawbar[slot], GB_NP * 8);
             }
+#endif
         };
         // block 0: local row 0 of every CTA (warp 0, k = 0)
         if (ty == 0) {
@@ -1035,7 +1052,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         long long tu0 = pfu ? clock64() : 0;
         for (int m = 0; m < nblk; ++m) {
             if (m > 0) gjb_cluster_wait();  // every CTA of the cluster has opened step m - 1 (see "flow control")
-            __syncthreads();  // multipliers and P^-1 of block m are in place; everybody is done with step m - 1
+            COVO_NAMED_BARRIER(2, GB_T);  // multipliers and P^-1 of block m are in place; everybody is done with step m - 1
             gjb_cluster_arrive();
             if (pfu) {
                 const long long t1 = clock64();

@@ -23,9 +23,16 @@ __device__ __forceinline__ void mbar_expect(unsigned long long* b, int bytes) {
 
 template <int MODE>
 __global__ void __cluster_dims__(8, 1, 1) pingpong(int iters, long long* out) {
+#if defined(DSMEM_DYNAMIC)  // the same buffers in DYNAMIC shared memory (what the production kernels use): for compute-sanitizer
+    extern __shared__ __align__(16) unsigned char dyn[];
+    double(*buf)[224] = reinterpret_cast<double(*)[224]>(dyn);
+    double* src = reinterpret_cast<double*>(dyn + 2 * 224 * 8);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(dyn + 3 * 224 * 8);
+#else
     __shared__ __align__(16) double buf[2][224];
     __shared__ __align__(16) double src[224];
     __shared__ unsigned long long bar[2];
+#endif
     unsigned rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     if (threadIdx.x == 0) {
@@ -85,20 +92,40 @@ __global__ void __cluster_dims__(8, 1, 1) pingpong(int iters, long long* out) {
         long long t1 = clock64();
         if (lane == 0 && rank == 0) out[MODE] = t1 - t0;
     }
+    // a copy to the CTA itself through its shared::cluster address (the production kernel publishes a row to all eight CTAs, itself included)
+    if (MODE == 2 && rank == 0 && threadIdx.x == 0) {
+        mbar_expect(&bar[0], 1792);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(mapa(s32(&buf[0][0]), 0)),
+                     "r"(s32(src)), "r"(1792), "r"(mapa(s32(&bar[0]), 0))
+                     : "memory");
+        mbar_wait(&bar[0], (unsigned)((iters >> 1) & 1));
+    }
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+#if defined(DSMEM_DYNAMIC)
+#define DYN_BYTES (100 * 1024)  // opt-in size (> 48 KB), like the production kernels
+#else
+#define DYN_BYTES 0
+#endif
+
 int main() {
+#if defined(DSMEM_DYNAMIC)
+    cudaFuncSetAttribute(pingpong<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES);
+    cudaFuncSetAttribute(pingpong<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES);
+    cudaFuncSetAttribute(pingpong<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES);
+#endif
     long long* out;
     cudaMallocManaged(&out, 64);
     const int iters = 2000;
-    pingpong<0><<<8, 64>>>(iters, out);
+    pingpong<0><<<8, 64, DYN_BYTES>>>(iters, out);
     cudaDeviceSynchronize();
     printf("st.async 8 B              : %.0f cycles one way\n", (double)out[0] / iters / 2);
-    pingpong<1><<<8, 64>>>(iters, out);
+    pingpong<1><<<8, 64, DYN_BYTES>>>(iters, out);
     cudaDeviceSynchronize();
     printf("stage + fence + bulk 64 B : %.0f cycles one way\n", (double)out[1] / iters / 2);
-    pingpong<2><<<8, 64>>>(iters, out);
+    pingpong<2><<<8, 64, DYN_BYTES>>>(iters, out);
     cudaDeviceSynchronize();
     printf("stage + fence + bulk 1792 B: %.0f cycles one way\n", (double)out[2] / iters / 2);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
