@@ -606,6 +606,8 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
 #pragma unroll
         for (int r = 0; r < LC_CL; ++r)
             rem[r] = lc_remote(&sm.u[0][has_row ? row : 0], &sm.part[0][rank * 4 + warp][0], &sm.bar[0], (unsigned)r);
+        const bool pfl = a.prof && tid == 0 && rank == 0 && blockIdx.y == 0;
+        long long pl[5] = {0, 0, 0, 0, 0}, tl0 = pfl ? clock64() : 0;  // phase clocks of the recurrence (registers; dumped once)
         for (int it = 0; it < k_max; ++it) {
             const int pc = it & 1;  // v_k is in v[pc]; this step's exchange uses u[pc], part[pc], bar[pc]
             // y_row = (A v_k)_row: four threads per row, eight independent chains each
@@ -632,6 +634,10 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
             if (tid == 0) gjb_mbar_expect(&sm.bar[pc], tx_bytes);
             long long tq0 = 0;
             if (a.prof && tid == 0 && rank == 0 && blockIdx.y == 0) tq0 = clock64();
+            if (pfl) {
+                pl[0] += tq0 - tl0;  // matrix-vector product, reductions
+                tl0 = tq0;
+            }
             // the exchange: u of this row and the warp's partials to every CTA of the cluster (this one included)
 #pragma unroll
             for (int r = 0; r < LC_CL; ++r) {
@@ -662,7 +668,17 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
                 r = r * (2.0 - qv * r);
                 iqv = r * (2.0 - qv * r);
             }
+            if (pfl) {
+                const long long t1 = clock64();
+                pl[1] += t1 - tl0;  // sends + |v|^2
+                tl0 = t1;
+            }
             gjb_mbar_wait(&sm.bar[pc], (unsigned)((it >> 1) & 1));
+            if (pfl) {
+                const long long t1 = clock64();
+                pl[2] += t1 - tl0;  // waiting for the exchange
+                tl0 = t1;
+            }
             if (a.prof && tid == 0 && rank == 0 && blockIdx.y == 0) a.prof[52] = (it == 0 ? 0 : a.prof[52]) + (clock64() - tq0);  // send + wait
             // alpha = u.v_k / |v_k|^2, beta_k^2 = |u - alpha v_k|^2 = u.u - alpha (u.v_k): every warp sums the 32 partial pairs with the
             // same butterfly
@@ -701,6 +717,11 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
                 ib = r * ((b2 < 1e-30) ? 1e30 : 1.0);
                 beta_new = b2 * ib;
             }
+            if (pfl) {
+                const long long t1 = clock64();
+                pl[3] += t1 - tl0;  // alpha, beta
+                tl0 = t1;
+            }
             if (tid == 0) {  // hand T's new row to the checker
                 sm.al[it] = alpha;
                 sm.be[it] = beta_new;
@@ -730,7 +751,17 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
                 stop = ck != 0 && ck <= c;
             }
             lc_main_sync();
+            if (pfl) {
+                const long long t1 = clock64();
+                pl[4] += t1 - tl0;  // next vector, verdict, barrier
+                tl0 = t1;
+            }
             if (stop) break;
+        }
+        if (pfl) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) a.prof[40 + q] = pl[q];
+            a.prof[45] = kdone;
         }
         if (tid == 0) {
             lc_fence();

@@ -39,6 +39,8 @@ def main():
     print("lanczos: load", d(48, 49), "iterations", d(49, 50), "multisection", d(50, 51), "us")
     print("lanczos exchange (send + mbarrier wait, all iterations, CTA 0 thread 0):", round(c[52] / mhz, 2), "us")
     us = lambda k: round(c[k] / mhz, 2)
+    print("lanczos recurrence (CTA 0 thread 0, sums over", int(c[45]), "steps, us): matvec + reductions", us(40), "sends + |v|^2", us(41), "exchange wait", us(42),
+          "alpha / beta", us(43), "next vector + verdict + barrier", us(44))
     print("gjb (CTA 0, sums over the 25 steps, us): solver warp 0: wait for the pivot block", us(54), "8x8 inversion", us(55), "wait for the rows + P^-1 barrier", us(60),
           "multipliers", us(56), "step barrier", us(57), "| update warp 0: at step barrier", us(58), "open -> step done", us(59))
     print("gjb look-ahead on the owning CTA (its own clock, sums over 24 blocks, us): pivot columns", us(62), "pivot block to the copy unit", us(63), "rest of the row", us(61))
