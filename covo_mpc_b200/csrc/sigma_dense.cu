@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
 // Flow control: the raw panels live in a ring of 4 slots; a split cluster barrier (arrive after a step is opened, wait before the
 // next one) keeps everybody within one step of everybody else, so 4 slots never collide.
 // ---------------------------------------------------------------------------------------------------------------------------
-constexpr int GB_CL = 8;     // CTAs per matrix = rows per pivot block
+constexpr int GB_CL = 8;     // CTAs per matrix
 constexpr int GB_NR = 4;     // rows per update thread
 constexpr int GB_UT = 256;   // update threads
 constexpr int GB_ST = 128;   // solver threads
@@ -822,12 +822,17 @@ struct IntC {
     static constexpr int value = V;
 };
 
-struct GjbSmem {
-    double raw[GB_SLOTS][8][GB_NP];   // pivot-row panels [s][j]: row s comes from CTA s
-    double stage[2][GB_NP];           // this CTA's pivot row on its way out (by block parity): source of the bulk copies
-    double MP[2][8][8][GB_NR];        // [parity][ty][u][k]: -sigma(i) G[u][i] for the local row ty + 8 k; 0 for the pivot row and padding
-    double Pblk[GB_SLOTS][8][8];      // the 8 x 8 pivot blocks, sent ahead of the rows
-    double Pinv[2][64];
+// NB = pivots per step (8, the default, or 16): a block is NB / 8 rows per CTA.  16 halves the number of steps and with it the per-step
+// fixed cost (DSMEM hop, barrier); the NB x NB inverse stays one warp's dependent chain of NB pivots -- and that is what makes 16 the
+// slower choice (launch_sigma_dense).
+template <int NB>
+struct GjbSmemT {
+    static constexpr int RB = NB / GB_CL;  // rows of a block per CTA
+    double raw[GB_SLOTS][NB][GB_NP];  // pivot-row panels [s][j]: row s comes from CTA s % 8
+    double stage[2][RB][GB_NP];       // this CTA's pivot rows on their way out (by block parity): source of the bulk copies
+    double MP[2][8][NB][GB_NR];       // [parity][ty][u][k]: -sigma(i) G[u][i] for the local row ty + 8 k; 0 for pivot rows and padding
+    double Pblk[GB_SLOTS][NB][NB];    // the NB x NB pivot blocks, sent ahead of the rows
+    double Pinv[2][NB * NB];
     double piv[GB_NP];
     unsigned long long rawbar[GB_SLOTS];
     unsigned long long pbar[GB_SLOTS];
@@ -856,12 +861,17 @@ __device__ __forceinline__ double gjb_rcp64(double x) {
 }
 #endif
 
-__global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a) {
+template <int NB>
+__global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel_t(const DenseArgs a) {
+    using Smem = GjbSmemT<NB>;
+    constexpr int RB = NB / GB_CL;      // rows of a block per CTA
+    constexpr int LPR = 32 / NB;        // lanes per row of the pivot block in the inverting warp (4 or 2)
+    constexpr int EPL = NB / LPR;       // entries per lane (2 or 8)
     COVO_DYN_SMEM(smraw);
-    GjbSmem& sm = *reinterpret_cast<GjbSmem*>(smraw);
+    Smem& sm = *reinterpret_cast<Smem*>(smraw);
     const int n = a.n, tid = threadIdx.x, env = blockIdx.y, pole = blockIdx.x / GB_CL;
     const int rank = (int)gjb_rank();
-    const int nblk = (n + 7) >> 3;
+    const int nblk = (n + NB - 1) / NB;
     if (tid < 16) sm.pacc[tid] = 0;
     if (tid == 0) {
         sm.bad = 0;
@@ -873,7 +883,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
     }
-    for (int i = tid; i < GB_SLOTS * 8 * GB_NP; i += GB_T) (&sm.raw[0][0][0])[i] = 0.0;
+    for (int i = tid; i < GB_SLOTS * NB * GB_NP; i += GB_T) (&sm.raw[0][0][0])[i] = 0.0;
     gjb_cluster_sync();  // barriers initialised and panels zeroed everywhere before anybody publishes
 
     if (tid >= GB_UT) {
@@ -886,8 +896,8 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
             const int slot = m & (GB_SLOTS - 1), par = m & 1;
             const unsigned ring_par = (unsigned)((m / GB_SLOTS) & 1);
             if (sidx == 0) {
-                gjb_mbar_expect(&sm.pbar[slot], 8 * 8 * 8);
-                gjb_mbar_expect(&sm.rawbar[slot], 8 * GB_NP * 8);
+                gjb_mbar_expect(&sm.pbar[slot], NB * NB * 8);
+                gjb_mbar_expect(&sm.rawbar[slot], NB * GB_NP * 8);
             }
             const bool pf = a.prof && sidx == 0 && blockIdx.x == 0 && blockIdx.y == 0;
             long long t0 = pf ? clock64() : 0;
@@ -898,47 +908,50 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                     sm.pacc[6] += (t1 - t0);
                     t0 = t1;
                 }
-                // P^-1 by an in-place Gauss-Jordan sweep of the 8 x 8 block: lane = (row r, columns c0, c0 + 1).  The reciprocal of
-                // the NEXT pivot is started as soon as this pivot's is known -- P'[s+1][s+1] = P[s+1][s+1] - (P[s+1][s] / p) P[s][s+1] is the
-                // very operation the sweep applies to that entry -- so the dependent chain per pivot is multiply, FMA, reciprocal
-                // instead of shuffle, reciprocal, multiply, FMA, shuffle.
-                const int r = lane >> 2, c0 = (lane & 3) * 2;
-                double x0 = sm.Pblk[slot][r][c0], x1 = sm.Pblk[slot][r][c0 + 1];
-                double pvs[8];  // the scalar pivots (log det, positivity): written out after the chain, not inside it
-                pvs[0] = __shfl_sync(0xffffffffu, x0, 0);
+                // P^-1 by an in-place Gauss-Jordan sweep of the NB x NB block: lane = (row r, columns EPL h .. EPL h + EPL - 1).  The
+                // reciprocal of the NEXT pivot is started as soon as this pivot's is known -- P'[s+1][s+1] = P[s+1][s+1] -
+                // (P[s+1][s] / p) P[s][s+1] is the very operation the sweep applies to that entry -- so the dependent chain per pivot is
+                // multiply, FMA, reciprocal instead of shuffle, reciprocal, multiply, FMA, shuffle.
+                const int r = lane / LPR, h = lane % LPR;
+                double x[EPL];
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) x[j] = sm.Pblk[slot][r][EPL * h + j];
+                double pvs[NB];  // the scalar pivots (log det, positivity): written out after the chain, not inside it
+                pvs[0] = __shfl_sync(0xffffffffu, x[0], 0);
                 double rinv = gjb_rcp64(pvs[0]);
 #pragma unroll
-                for (int sp = 0; sp < 8; ++sp) {
-                    const double mine = (sp & 1) ? x1 : x0;
-                    const double prs = __shfl_sync(0xffffffffu, mine, (r << 2) | (sp >> 1));   // P[r][sp]
-                    const double ps0 = __shfl_sync(0xffffffffu, x0, (sp << 2) | (lane & 3));   // P[sp][c0]
-                    const double ps1 = __shfl_sync(0xffffffffu, x1, (sp << 2) | (lane & 3));   // P[sp][c0 + 1]
+                for (int sp = 0; sp < NB; ++sp) {
+                    const int hs = sp / EPL, js = sp % EPL;  // compile-time after unrolling: column sp is entry js of the lanes with h = hs
+                    const double prs = __shfl_sync(0xffffffffu, x[js], r * LPR + hs);  // P[r][sp]
+                    double ps[EPL];
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) ps[j] = __shfl_sync(0xffffffffu, x[j], sp * LPR + h);  // P[sp][EPL h + j]
                     double rinv_next = 0.0;
-                    if (sp < 7) {
-                        const double mine1 = ((sp + 1) & 1) ? x1 : x0;
-                        const double pa = __shfl_sync(0xffffffffu, mine, ((sp + 1) << 2) | (sp >> 1));          // P[sp + 1][sp]
-                        const double pb = __shfl_sync(0xffffffffu, mine1, (sp << 2) | ((sp + 1) >> 1));         // P[sp][sp + 1]
-                        const double pc = __shfl_sync(0xffffffffu, mine1, ((sp + 1) << 2) | ((sp + 1) >> 1));   // P[sp + 1][sp + 1]
-                        pvs[sp + 1] = fma(-(pa * rinv), pb, pc);
-                        rinv_next = gjb_rcp64(pvs[sp + 1]);
+                    if (sp + 1 < NB) {
+                        const int hs1 = (sp + 1) / EPL, js1 = (sp + 1) % EPL;
+                        const double pa = __shfl_sync(0xffffffffu, x[js], (sp + 1) * LPR + hs);    // P[sp + 1][sp]
+                        const double pb = __shfl_sync(0xffffffffu, x[js1], sp * LPR + hs1);        // P[sp][sp + 1]
+                        const double pc = __shfl_sync(0xffffffffu, x[js1], (sp + 1) * LPR + hs1);  // P[sp + 1][sp + 1]
+                        pvs[(sp + 1 < NB) ? sp + 1 : 0] = fma(-(pa * rinv), pb, pc);
+                        rinv_next = gjb_rcp64(pvs[(sp + 1 < NB) ? sp + 1 : 0]);
                     }
                     if (r == sp) {
-                        x0 = (c0 == sp) ? rinv : ps0 * rinv;
-                        x1 = (c0 + 1 == sp) ? rinv : ps1 * rinv;
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j) x[j] = (EPL * h + j == sp) ? rinv : ps[j] * rinv;
                     } else {
                         const double f = prs * rinv;
-                        x0 = (c0 == sp) ? -f : fma(-f, ps0, x0);
-                        x1 = (c0 + 1 == sp) ? -f : fma(-f, ps1, x1);
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j) x[j] = (EPL * h + j == sp) ? -f : fma(-f, ps[j], x[j]);
                     }
                     rinv = rinv_next;
                 }
-                sm.Pinv[par][r * 8 + c0] = x0;
-                sm.Pinv[par][r * 8 + c0 + 1] = x1;
-                if (lane < 8) {
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) sm.Pinv[par][r * NB + EPL * h + j] = x[j];
+                if (lane < NB) {
                     double pl = pvs[0];
 #pragma unroll
-                    for (int sp = 1; sp < 8; ++sp) pl = (lane == sp) ? pvs[sp] : pl;
-                    sm.piv[8 * m + lane] = pl;
+                    for (int sp = 1; sp < NB; ++sp) pl = (lane == sp) ? pvs[sp] : pl;
+                    sm.piv[NB * m + lane] = pl;
                     if (!(pl > 0.0)) sm.bad = 1;
                 }
                 if (pf) {
@@ -955,28 +968,28 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 t0 = t1;
             }
             {
-                // multipliers of this CTA's rows: MP[ty][u][k] = -sigma(i) sum_v P^-1[u][v] raw[v][i]; thread = (ty, k, two of the eight u)
+                // multipliers of this CTA's rows: MP[ty][u][k] = -sigma(i) sum_v P^-1[u][v] raw[v][i]; thread = (ty, k, NB / 4 of the u)
+                constexpr int UPT = NB / 4;  // outputs per thread
                 const double(*rw)[GB_NP] = sm.raw[slot];
-                const int ty = sidx >> 4, k = (sidx >> 2) & 3, u0 = (sidx & 3) * 2;
+                const int ty = sidx >> 4, k = (sidx >> 2) & 3, u0 = (sidx & 3) * UPT;
                 const int l = ty + 8 * k, i = rank + GB_CL * l;
-                const bool live = l < GB_LR && l != m;
-                double col[8];
+                const bool live = l < GB_LR && !(l >= RB * m && l < RB * m + RB);
+                double col[NB];
 #pragma unroll
-                for (int v = 0; v < 8; ++v) col[v] = live ? rw[v][i] : 0.0;
-                const double sgn = (l < m) ? 1.0 : -1.0;
-                const double2* pv = reinterpret_cast<const double2*>(&sm.Pinv[par][u0 * 8]);  // rows u0, u0 + 1 of P^-1
-                double g0a = 0.0, g0b = 0.0, g1a = 0.0, g1b = 0.0;
+                for (int v = 0; v < NB; ++v) col[v] = live ? rw[v][i] : 0.0;
+                const double sgn = (l < RB * m) ? 1.0 : -1.0;
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const double2 pu = pv[v], pw = pv[4 + v];
-                    g0a = fma(pu.x, col[2 * v], g0a);
-                    g0b = fma(pu.y, col[2 * v + 1], g0b);
-                    g1a = fma(pw.x, col[2 * v], g1a);
-                    g1b = fma(pw.y, col[2 * v + 1], g1b);
+                for (int q = 0; q < UPT; ++q) {
+                    const double2* pv = reinterpret_cast<const double2*>(&sm.Pinv[par][(u0 + q) * NB]);  // row u0 + q of P^-1
+                    double ga = 0.0, gb = 0.0;
+#pragma unroll
+                    for (int v = 0; v < NB / 2; ++v) {
+                        const double2 pu = pv[v];
+                        ga = fma(pu.x, col[2 * v], ga);
+                        gb = fma(pu.y, col[2 * v + 1], gb);
+                    }
+                    sm.MP[par][ty][u0 + q][k] = live ? sgn * (ga + gb) : 0.0;
                 }
-                const double g0 = g0a + g0b, g1 = g1a + g1b;
-                sm.MP[par][ty][u0][k] = live ? sgn * g0 : 0.0;
-                sm.MP[par][ty][u0 + 1][k] = live ? sgn * g1 : 0.0;
             }
             if (pf) {
                 const long long t1 = clock64();
@@ -1038,46 +1051,46 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 if (l < GB_LR && i < n && i == tx + 32 * b) acc[k][b] += shift;
         }
         const bool has_row3 = rank + GB_CL * (ty + 24) < n;  // warp-uniform: the fourth row of this warp is a row of the matrix (not padding)
-        // This CTA's row of a block leaves as ONE bulk copy per destination CTA (this one included): staged in shared memory, fenced
-        // for the async proxy; its eight entries in the block's own pivot columns travel ahead as st.async stores
-        auto publish_pblock = [&](int blk, double v) {  // called by all lanes of one warp; the lanes holding the block's columns send their entry
-            const int K1 = 8 * blk;
-            if ((tx & ~7) == (K1 & 31)) {
+        // A row of a block leaves as ONE bulk copy per destination CTA: staged in shared memory, fenced for the async proxy; its NB
+        // entries in the block's own pivot columns travel ahead as st.async stores.  s_row = its row index inside the block.
+        auto publish_pblock = [&](int blk, int s_row, double v) {  // called by all lanes of one warp; the lanes holding the block's columns send their entry
+            const int K1 = NB * blk;
+            if ((tx & ~(NB - 1)) == (K1 & 31)) {
                 // straight from the register into every CTA's copy of the block: st.async needs no staging and no proxy fence (the
                 // staged 64-byte bulk copy took 0.38 us from here to the copy unit)
                 const int slot = blk & (GB_SLOTS - 1);
 #pragma unroll
-                for (int r = 0; r < GB_CL; ++r) gjb_send64(&sm.Pblk[slot][rank][tx & 7], (unsigned)r, v, &sm.pbar[slot]);
+                for (int r = 0; r < GB_CL; ++r) gjb_send64(&sm.Pblk[slot][s_row][tx & (NB - 1)], (unsigned)r, v, &sm.pbar[slot]);
             }
         };
-        auto publish_row = [&](int blk, const double (&vals)[7], int Kfix, double vfix) {
+        auto publish_row = [&](int blk, int s_row, const double (&vals)[7], int Kfix, double vfix) {
             const int slot = blk & (GB_SLOTS - 1);
-            double* st = sm.stage[blk & 1];
+            double* st = sm.stage[blk & 1][s_row / GB_CL];
 #pragma unroll
             for (int b = 0; b < 7; ++b) st[tx + 32 * b] = vals[b];
-            if (Kfix >= 0 && (tx & ~7) == (Kfix & 31)) st[(Kfix & ~31) + tx] = vfix;  // same thread, same address: program order
+            if (Kfix >= 0 && (tx & ~(NB - 1)) == (Kfix & 31)) st[(Kfix & ~31) + tx] = vfix;  // same thread, same address: program order
 #if defined(COVO_CPU_EMU)
             __syncwarp();
-            if (tx < GB_CL) gjb_bulk_send(&sm.raw[slot][rank][0], st, GB_NP * 8, (unsigned)tx, &sm.rawbar[slot]);
+            if (tx < GB_CL) gjb_bulk_send(&sm.raw[slot][s_row][0], st, GB_NP * 8, (unsigned)tx, &sm.rawbar[slot]);
 #else
             // this CTA's own copy of the row: ordinary stores + a local complete_tx (a bulk copy to the CTA's own shared::cluster address works
             // on the hardware but compute-sanitizer's memcheck rejects it as "not located in remote CTA", tools/microbench/dsmem_latency.cu)
-            double* own = &sm.raw[slot][rank][0];
+            double* own = &sm.raw[slot][s_row][0];
 #pragma unroll
             for (int b = 0; b < 7; ++b) own[tx + 32 * b] = vals[b];
-            if (Kfix >= 0 && (tx & ~7) == (Kfix & 31)) own[(Kfix & ~31) + tx] = vfix;
+            if (Kfix >= 0 && (tx & ~(NB - 1)) == (Kfix & 31)) own[(Kfix & ~31) + tx] = vfix;
             gjb_fence_async_proxy();
             __syncwarp();
             if (tx < GB_CL) {
-                if (tx != rank) gjb_bulk_send(&sm.raw[slot][rank][0], st, GB_NP * 8, (unsigned)tx, &sm.rawbar[slot]);
+                if (tx != rank) gjb_bulk_send(&sm.raw[slot][s_row][0], st, GB_NP * 8, (unsigned)tx, &sm.rawbar[slot]);
                 else gjb_mbar_complete_tx_local(&sm.rawbar[slot], GB_NP * 8);
             }
 #endif
         };
-        // block 0: local row 0 of every CTA (warp 0, k = 0)
-        if (ty == 0) {
-            publish_pblock(0, acc[0][0]);
-            publish_row(0, acc[0], -1, 0.0);
+        // block 0: local rows 0 .. RB - 1 of every CTA (warps 0 .. RB - 1, k = 0)
+        if (ty < RB) {
+            publish_pblock(0, rank + GB_CL * ty, acc[0][0]);
+            publish_row(0, rank + GB_CL * ty, acc[0], -1, 0.0);
         }
         const bool pfu = a.prof && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
         long long tu0 = pfu ? clock64() : 0;
@@ -1090,53 +1103,53 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 sm.pacc[10] += (t1 - tu0);
                 tu0 = t1;
             }
-            const int par = m & 1, K0 = 8 * m, slot = m & (GB_SLOTS - 1);
+            const int par = m & 1, K0 = NB * m, slot = m & (GB_SLOTS - 1);
             gjb_mbar_wait(&sm.rawbar[slot], (unsigned)((m / GB_SLOTS) & 1));  // complete long ago; makes the async-proxy writes visible HERE
             const double(*rw)[GB_NP] = sm.raw[slot];
             const double(*mp)[GB_NR] = sm.MP[par][ty];  // [u][k]
-            // ---- look-ahead: the warp that owns this CTA's row of block m + 1 (local row m + 1) updates it first and publishes it ------
-            // (straight-line code on a copy of the row: with the row / column slot chosen by predicates inside the FMA loops ptxas
-            // serialised every shared-memory load with its FMA, 60 cycles per FMA)
+            // ---- look-ahead: a warp that owns one of this CTA's rows of block m + 1 (local rows RB (m + 1) + q) updates it first and
+            // publishes it (straight-line code on a copy of the row: with the row / column slot chosen by predicates inside the FMA
+            // loops ptxas serialised every shared-memory load with its FMA, 60 cycles per FMA)
             int k_done = -1;
-            if (m + 1 < nblk && ty == ((m + 1) & 7)) {
-                const int k1 = (m + 1) >> 3, K1 = K0 + 8;
+            const int q1 = (ty - RB * (m + 1)) & 7;  // which of the block's rows in this CTA this warp would own
+            if (m + 1 < nblk && q1 < RB) {
+                const int l1 = RB * (m + 1) + q1, k1 = l1 >> 3, K1 = K0 + NB, s_row = rank + GB_CL * q1;
                 k_done = k1;
-                double row[7], mk[8];
+                double row[7];
 #pragma unroll
                 for (int b = 0; b < 7; ++b) {
                     row[b] = acc[0][b];
 #pragma unroll
                     for (int k = 1; k < GB_NR; ++k) row[b] = (k == k1) ? acc[k][b] : row[b];
                 }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) mk[u] = mp[u][k1];
                 const bool pfo = a.prof && tx == 0 && blockIdx.x == 0 && blockIdx.y == 0;
                 long long to0 = pfo ? clock64() : 0;
                 {
-                    // the block's own pivot columns first (lanes K1 & 31 .. + 7 of column slot K1 >> 5): they leave ahead of the row.  Same
-                    // operations in the same order as the row update below, so the two agree bit for bit.
+                    // the block's own pivot columns first (lanes K1 & 31 .. + NB - 1 of column slot K1 >> 5): they leave ahead of the row.
+                    // Same operations in the same order as the row update below, so the two agree bit for bit.
                     const int jp = (K1 & ~31) + tx;
                     double pe = row[0];
 #pragma unroll
                     for (int b = 1; b < 7; ++b) pe = gjb_sel(b == (K1 >> 5), row[b], pe);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) pe = fma(mk[u], rw[u][jp], pe);
+                    for (int u = 0; u < NB; ++u) pe = fma(mp[u][k1], rw[u][jp], pe);
                     if (pfo) {
                         const long long t1 = clock64();
                         sm.pacc[14] += (t1 - to0);  // pivot columns of the row
                         to0 = t1;
                     }
-                    publish_pblock(m + 1, pe);
+                    publish_pblock(m + 1, s_row, pe);
                     if (pfo) {
                         const long long t1 = clock64();
                         sm.pacc[15] += (t1 - to0);  // pivot block handed to the copy unit
                         to0 = t1;
                     }
                 }
+#pragma unroll 4
+                for (int u = 0; u < NB; ++u) {
+                    const double mm = mp[u][k1];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-#pragma unroll
-                    for (int b = 0; b < 7; ++b) row[b] = fma(mk[u], rw[u][tx + 32 * b], row[b]);
+                    for (int b = 0; b < 7; ++b) row[b] = fma(mm, rw[u][tx + 32 * b], row[b]);
                 }
 #pragma unroll
                 for (int b = 0; b < 7; ++b) {
@@ -1149,9 +1162,9 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                     to0 = t1;
                 }
                 // (its entries in the pivot columns of step m are -G[s][i] (i is unswept) = MP[i][s]: patched into the staged copy)
-                publish_row(m + 1, row, K0, mp[tx & 7][k1]);
+                publish_row(m + 1, s_row, row, K0, mp[tx & (NB - 1)][k1]);
             }
-            // ---- the rank-8 update of everything else this thread owns ---------------------------------------------------
+            // ---- the rank-NB update of everything else this thread owns --------------------------------------------------
             // Straight-line: no branch per row.  Padding rows have zero multipliers in the table and the look-ahead row gets zeros
             // here (x + 0 g = x exactly), so that all 18 shared-memory loads of two panel rows are in flight before the 56 FMAs (with
             // a branch per row ptxas issued every multiplier load right in front of the FMAs that need it: 2.8 us per step).
@@ -1160,7 +1173,7 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
             auto bulk = [&](auto WITH3) {  // (two straight-line instances: only warp 0 of a CTA has a real fourth row at n = 200)
                 constexpr bool with3 = decltype(WITH3)::value != 0;
 #pragma unroll 2  // (fully unrolled, ptxas hoists all 56 panel loads and spills)
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < NB; ++u) {
                     double g[7];
                     const double2 ma = *reinterpret_cast<const double2*>(&mp[u][0]), mb = *reinterpret_cast<const double2*>(&mp[u][2]);
 #pragma unroll
@@ -1178,34 +1191,35 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
             if (has_row3) bulk(IntC<1>());
             else bulk(IntC<0>());
             if (pfu) sm.pacc[5] += clock64() - tb0;  // the bulk update alone
-            // ---- fix-ups: the pivot row <- G (P^-1 inside the block), pivot columns <- MP[i][s] ----------------------------
-            if (ty == (m & 7)) {  // this warp owns the CTA's pivot row: local row m, row `rank` of the block
-                const int k0 = m >> 3;
-                const double* pv = &sm.Pinv[par][rank * 8];
+            // ---- fix-ups: pivot rows <- G (P^-1 inside the block), pivot columns <- MP[i][s] -------------------------------
+            const int q0 = (ty - RB * m) & 7;
+            if (q0 < RB) {  // this warp owns one of the CTA's pivot rows: local row RB m + q0, row rank + 8 q0 of the block
+                const int k0 = (RB * m + q0) >> 3, s0 = rank + GB_CL * q0;
+                const double* pv = &sm.Pinv[par][s0 * NB];
                 double v[7];
 #pragma unroll
                 for (int b = 0; b < 7; ++b) v[b] = 0.0;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
+#pragma unroll 4
+                for (int u = 0; u < NB; ++u) {
                     const double pu = pv[u];
 #pragma unroll
-                    for (int b = 0; b < 7; ++b) v[b] = fma(pu, rw[u][tx + 32 * b], v[b]);  // G[rank][j]
+                    for (int b = 0; b < 7; ++b) v[b] = fma(pu, rw[u][tx + 32 * b], v[b]);  // G[s0][j]
                 }
-                const double pin = pv[tx & 7];
+                const double pin = pv[tx & (NB - 1)];
 #pragma unroll
                 for (int b = 0; b < 7; ++b) {
                     const int j = tx + 32 * b;
-                    const double vb = gjb_sel(j >= K0 && j < K0 + 8, pin, v[b]);
+                    const double vb = gjb_sel(j >= K0 && j < K0 + NB, pin, v[b]);
 #pragma unroll
                     for (int k = 0; k < GB_NR; ++k) acc[k][b] = gjb_sel(k == k0, vb, acc[k][b]);
                 }
             }
-            if ((tx & ~7) == (K0 & 31)) {
-                const int sc = tx & 7, b0 = K0 >> 5;
+            if ((tx & ~(NB - 1)) == (K0 & 31)) {
+                const int sc = tx & (NB - 1), b0 = K0 >> 5;
 #pragma unroll
                 for (int k = 0; k < GB_NR; ++k) {
                     const int l = ty + 8 * k;
-                    const bool fix = l < GB_LR && l != m;
+                    const bool fix = l < GB_LR && !(l >= RB * m && l < RB * m + RB);
                     const double v = mp[sc][k];
 #pragma unroll
                     for (int b = 0; b < 7; ++b) acc[k][b] = gjb_sel(fix && b == b0, v, acc[k][b]);
@@ -1217,10 +1231,10 @@ __global__ void __launch_bounds__(GB_T, 1) gjb_inverse_kernel(const DenseArgs a)
                 tu0 = t1;
             }
         }
+        // ---- results ---------------------------------------------------------------------------------------------------------
 #if !defined(COVO_CPU_EMU)
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the combine kernel may become resident; it waits for this grid to complete
 #endif
-        // ---- results ---------------------------------------------------------------------------------------------------------
         if (!want_logdet) {
             float* Xg = a.Xbuf + ((long long)env * kDensePoles + pole) * n * n;
 #pragma unroll
@@ -1325,13 +1339,18 @@ cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, in
     }
     if (ev_mid1) cudaEventRecord(ev_mid1, st);
     {  // blocked Gauss-Jordan, one cluster per pole (+ one for log det A)
-        static size_t conf4[32] = {};
-        e = ensure_smem_attr(gjb_inverse_kernel, sizeof(GjbSmem), conf4);
+        // COVO_GJB_NB=16: sixteen pivots per elimination step instead of eight (see GjbSmemT).  Measured on B200: 92 us against 70 -- the
+        // 16 x 16 inverse on one warp is 440 cycles per pivot (eight entries per lane: the instruction count per thread, not the
+        // dependent chain, sets the pace of a lone warp), 3.7 us per block where two 8 x 8 inverses take 1.8
+        static const int nb = (getenv("COVO_GJB_NB") && atoi(getenv("COVO_GJB_NB")) == 16) ? 16 : 8;
+        static size_t conf8[32] = {}, conf16[32] = {};
+        const size_t smem = nb == 16 ? sizeof(GjbSmemT<16>) : sizeof(GjbSmemT<8>);
+        e = nb == 16 ? ensure_smem_attr(gjb_inverse_kernel_t<16>, smem, conf16) : ensure_smem_attr(gjb_inverse_kernel_t<8>, smem, conf8);
         if (e != cudaSuccess) return e;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(GB_CL * (kDensePoles + 1), n_env);
         cfg.blockDim = dim3(GB_T);
-        cfg.dynamicSmemBytes = sizeof(GjbSmem);
+        cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         // programmatic dependent launch behind the Lanczos kernel: the clusters become resident next to it (8 + 112 CTAs of one per SM),
         // set up their barriers and load the matrix while the recurrence runs; griddepcontrol.wait in the kernel before lambda_min is read
@@ -1344,7 +1363,7 @@ cudaError_t launch_sigma_dense(const SigmaArgs& s, double* scal, float* Xbuf, in
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl ? 2 : 1;
-        e = cudaLaunchKernelEx(&cfg, gjb_inverse_kernel, a);
+        e = nb == 16 ? cudaLaunchKernelEx(&cfg, gjb_inverse_kernel_t<16>, a) : cudaLaunchKernelEx(&cfg, gjb_inverse_kernel_t<8>, a);
         if (e != cudaSuccess) return e;
     }
     if (ev_mid2) cudaEventRecord(ev_mid2, st);

@@ -20,7 +20,8 @@ extern "C" int emu_sigma_dense(int n, float sample_sigma, const float* R, const 
     a.Asym = nullptr;
     emu_launch_cluster(lanczos_cluster_kernel, dim3(LC_CL, 1), LC_CL, LC_TT, sizeof(LcSmem), a);  // 8-CTA cluster, 4 + 1 warps
     if (variant & 64) return 0;  // lambda_min only (studies of the Lanczos stage)
-    emu_launch_cluster(gjb_inverse_kernel, dim3(GB_CL * (kDensePoles + 1), 1), GB_CL, GB_T, sizeof(GjbSmem), a);
+    if (variant & 16) emu_launch_cluster(gjb_inverse_kernel_t<16>, dim3(GB_CL * (kDensePoles + 1), 1), GB_CL, GB_T, sizeof(GjbSmemT<16>), a);  // 16 pivots per step
+    else emu_launch_cluster(gjb_inverse_kernel_t<8>, dim3(GB_CL * (kDensePoles + 1), 1), GB_CL, GB_T, sizeof(GjbSmemT<8>), a);
     if (const char* dump = getenv("COVO_EMU_DUMP_X")) {  // development: the per-pole inverses
         FILE* f = fopen(dump, "wb");
         if (f) {

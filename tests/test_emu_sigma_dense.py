@@ -29,7 +29,8 @@ def _emu_lib():
     return C.CDLL(so)
 
 
-def test_dense_sigma_at_the_headline_size(variant=3):
+@pytest.mark.parametrize("variant", [3, 3 | 16])  # 8 and 16 pivots per elimination step
+def test_dense_sigma_at_the_headline_size(variant):
     """n = 200 (H = 50): the production kernels (8-CTA cluster Lanczos with its checker warp, float64 blocked Gauss-Jordan on an 8-CTA cluster
     per pole) run with all CTAs of a cluster interleaved."""
     emu = _emu_lib()
@@ -61,8 +62,9 @@ def _zolo_table():
     return tab
 
 
+@pytest.mark.parametrize("variant", [3, 3 | 16])
 @pytest.mark.parametrize("H", [2, 8, 9])  # n = 8 (Krylov space exhausted before the first checkpoint), 32, and the ragged 36 (n_pad = 40)
-def test_dense_sigma_kernels_on_the_cpu_execution_model(H, variant=3):
+def test_dense_sigma_kernels_on_the_cpu_execution_model(H, variant):
     emu = _emu_lib()
     p, ns, a_mean, rng = scenario("tracking_zigzag", seed=3, H=H, warm_steps=6)
     R = o.get_hessian(ns, o.shift_mean(a_mean), p, dtype=np.float64).astype(np.float32)
