@@ -29,8 +29,7 @@ def _emu_lib():
     return C.CDLL(so)
 
 
-@pytest.mark.parametrize("variant", [3, 3 | 16])  # 8 and 16 pivots per elimination step
-def test_dense_sigma_at_the_headline_size(variant):
+def test_dense_sigma_at_the_headline_size(variant=3):
     """n = 200 (H = 50): the production kernels (8-CTA cluster Lanczos with its checker warp, float64 blocked Gauss-Jordan on an 8-CTA cluster
     per pole) run with all CTAs of a cluster interleaved."""
     emu = _emu_lib()
@@ -62,7 +61,7 @@ def _zolo_table():
     return tab
 
 
-@pytest.mark.parametrize("variant", [3, 3 | 16])
+@pytest.mark.parametrize("variant", [3, 3 | 16])  # 8 (default) and 16 pivots per elimination step (n = 200 with 16: run once by hand, 2 min)
 @pytest.mark.parametrize("H", [2, 8, 9])  # n = 8 (Krylov space exhausted before the first checkpoint), 32, and the ragged 36 (n_pad = 40)
 def test_dense_sigma_kernels_on_the_cpu_execution_model(H, variant):
     emu = _emu_lib()
