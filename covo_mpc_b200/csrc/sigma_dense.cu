@@ -177,7 +177,11 @@ constexpr int LC_T = 128;           // Lanczos threads per CTA: 32 rows x 4 colu
 constexpr int LC_TT = LC_T + 32;    // ... plus the checker warp
 constexpr int LC_KMAX = 56;         // columns per thread (n <= 224)
 constexpr int kLanczosMax = 64;     // most Lanczos steps
-constexpr int kLanczosFirstCheck = 16, kLanczosCheckEvery = 4, kLanczosLag = 3;
+constexpr int kLanczosFirstCheck = 16, kLanczosCheckEvery = 4;
+#ifndef COVO_LANCZOS_LAG
+#define COVO_LANCZOS_LAG 3
+#endif
+constexpr int kLanczosLag = COVO_LANCZOS_LAG;
 constexpr double kRitzTol2 = 9e-10;  // residual^2 below which the Ritz value counts as converged: error <= 9e-10 / gap
 
 struct LcSmem {
