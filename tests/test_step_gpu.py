@@ -45,6 +45,29 @@ def test_covo_online_call_matches_oracle(N, H):
     assert np.isfinite(np.asarray(cp4.a_mean)).all()
 
 
+@pytest.mark.parametrize("H", [2, 3])
+def test_covo_online_call_tiny_horizon(H):
+    """get_controller(..., debug=True) runs CoVO with N = 4, H = 2 (envs/quadrotor.py:726-728): n = 8 and 12 through the whole default
+    step -- the Krylov space of the dense optimize_sigma path is exhausted before its first convergence checkpoint and one
+    elimination block is mostly identity padding."""
+    import covo_mpc_b200 as cm
+
+    N = 64
+    p, ns, a_mean, rng = scenario("tracking_zigzag", seed=5, H=H, warm_steps=6)
+    env = cm.Quad3D("tracking_zigzag")
+    ctl, cp = cm.get_controller(env, "covo-online", f"N{N}_H{H}_lam0.01")
+    cp = cp.replace(a_mean=a_mean)
+    eps = rng.standard_normal((N, 4 * H)).astype(np.float32)
+    st = _to_env_state(cm, ns)
+    action, cp2, _ = ctl(None, st, env.default_params, eps, cp, {"noisy_state": st})
+    assert ctl._handle.sigma_path() == 3 and int(ctl._handle.status()[0]) == 0
+    u_o, mean_o, cov_o, _ = o.covo_call(ns, a_mean, eps, p, lam=0.01)
+    cov = np.asarray(cp2.a_cov)
+    assert np.linalg.norm(cov - cov_o) / np.linalg.norm(cov_o) < 2e-5
+    assert np.abs(np.asarray(cp2.a_mean) - mean_o).max() < 2e-4 and np.abs(action - u_o).max() < 2e-4
+    ctl.close()
+
+
 def test_mppi_call_matches_oracle():
     import covo_mpc_b200 as cm
 
