@@ -1368,6 +1368,198 @@ cudaError_t launch_trifunc(const SigmaArgs& a, int n_env, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// E3 for BATCHES on the tensor cores: Sigma[:, J] = P^T (F P[:, J]) for a 64-column tile J per CTA, both products as
+// mma.sync m16n8k8 TF32 with the operands split in two TF32 words each (x = hi + lo; hi*hi + hi*lo + lo*hi: the 3xTF32 scheme,
+// float32-grade products, float32 accumulation).  A CTA streams F (pass 1, 32-column chunks) and P (pass 2, 32-row chunks) through
+// shared memory once -- four CTAs per matrix instead of thirteen, 16 K MACs per streamed element instead of 16 -- and keeps P[:, J]
+// and Z = F P[:, J] resident.  Only the tiles on or below the diagonal are formed in pass 2; every entry is stored together with its
+// mirror image, so Sigma stays exactly symmetric as with the SIMT kernel.  512 matrices of order 200: 1.78 ms -> see DESIGN.md.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTcThreads = 256, kTcJW = 64, kTcNP = 224, kTcBS = 72 /* row pitch of Pj / Zs */, kTcAS1 = 36 /* F chunk pitch */, kTcAS2 = 216 /* P chunk pitch */;
+constexpr int kTcChunkFloats = kTcNP * kTcAS1;  // 8064 >= 32 * 216
+constexpr size_t kTcSmemBytes = (size_t)(2 * kTcNP * kTcBS + 2 * kTcChunkFloats) * sizeof(float);
+
+__device__ __forceinline__ void tf32_split(float x, unsigned& hi, unsigned& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) sandwich_tc_kernel(const float* __restrict__ Qt, const float* __restrict__ F,
+                                                                     float* __restrict__ cov, int n) {
+    extern __shared__ __align__(16) float ssm[];
+    float* Pj = ssm;                      // [224][72]  P[:, J], zero beyond n
+    float* Zs = Pj + kTcNP * kTcBS;       // [224][72]  Z = F P[:, J]
+    float* Ch = Zs + kTcNP * kTcBS;       // [2][8064]  chunk buffers
+    const int env = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int J0 = blockIdx.x * kTcJW;
+    Qt += (long long)env * n * n;
+    F += (long long)env * n * n;
+    cov += (long long)env * n * n;
+    const int MT = (n + 15) >> 4, nch = (n + 31) >> 5;
+    // P[:, J]: rows l < n, columns J0 .. J0 + 63 (n is a multiple of 4: 16-byte pieces are all-in or all-out); zero elsewhere
+    for (int idx = tid; idx < kTcNP * (kTcJW / 4); idx += kTcThreads) {
+        const int l = idx >> 4, q4 = idx & 15;
+        float* dst = Pj + l * kTcBS + 4 * q4;
+        if (l < n && J0 + 4 * q4 < n) cp_async16(dst, Qt + (long long)l * n + J0 + 4 * q4);
+        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // pass 1 chunk c: Ch[m][0..31] = F[m][32 c ..], m < 224 (zero outside the matrix); pass 2 chunk c: Ch[r][i] = P[32 c + r][i], i < 216
+    auto prefetch1 = [&](int c, int slot) {
+        float* dst = Ch + slot * kTcChunkFloats;
+        const int l0 = 32 * c;
+        for (int idx = tid; idx < kTcNP * 8; idx += kTcThreads) {
+            const int m = idx >> 3, q4 = idx & 7;
+            float* d = dst + m * kTcAS1 + 4 * q4;
+            if (m < n && l0 + 4 * q4 < n) cp_async16(d, F + (long long)m * n + l0 + 4 * q4);
+            else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        cp_async_commit();
+    };
+    auto prefetch2 = [&](int c, int slot) {
+        float* dst = Ch + slot * kTcChunkFloats;
+        const int k0 = 32 * c;
+        for (int idx = tid; idx < 32 * (kTcAS2 / 4); idx += kTcThreads) {
+            const int r = idx / (kTcAS2 / 4), q4 = idx - r * (kTcAS2 / 4);
+            float* d = dst + r * kTcAS2 + 4 * q4;
+            if (k0 + r < n && 4 * q4 < n) cp_async16(d, Qt + (long long)(k0 + r) * n + 4 * q4);
+            else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        cp_async_commit();
+    };
+    prefetch1(0, 0);
+    float acc[2][8][4];
+    // ---------------- pass 1: Z = F P[:, J]; warp w owns the m-tiles w and w + 8 ----------------
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[a][nt][e] = 0.f;
+    for (int c = 0; c < nch; ++c) {
+        if (c + 1 < nch) prefetch1(c + 1, (c + 1) & 1);
+        else prefetch2(0, (c + 1) & 1);
+        cp_async_wait<1>();
+        __syncthreads();
+        const float* A = Ch + (c & 1) * kTcChunkFloats;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            unsigned ah[2][4], al[2][4];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int m0 = 16 * (warp + 8 * a);  // (m-tiles beyond MT read zero rows or rows of the padding: their results are never stored)
+                const float* ap = A + (m0 + g) * kTcAS1 + 8 * ks + t;
+                tf32_split(m0 < 16 * MT ? ap[0] : 0.f, ah[a][0], al[a][0]);
+                tf32_split(m0 < 16 * MT ? ap[8 * kTcAS1] : 0.f, ah[a][1], al[a][1]);
+                tf32_split(m0 < 16 * MT ? ap[4] : 0.f, ah[a][2], al[a][2]);
+                tf32_split(m0 < 16 * MT ? ap[8 * kTcAS1 + 4] : 0.f, ah[a][3], al[a][3]);
+            }
+            const float* bp = Pj + (32 * c + 8 * ks + t) * kTcBS + g;
+            unsigned bh[8][2], bl[8][2];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                tf32_split(bp[8 * nt], bh[nt][0], bl[nt][0]);
+                tf32_split(bp[4 * kTcBS + 8 * nt], bh[nt][1], bl[nt][1]);
+            }
+            // the three terms of a tile go to the same accumulator: issued term by term over all sixteen tiles, so that consecutive
+            // mma instructions are independent (tile by tile, three dependent mma in a row, the kernel ran at a tenth of this rate)
+#pragma unroll
+            for (int term = 0; term < 3; ++term)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        if (16 * (warp + 8 * a) >= 16 * MT) continue;  // warp-uniform
+                        mma_tf32(acc[a][nt], term == 0 ? al[a] : ah[a], term == 1 ? bl[nt] : bh[nt]);
+                    }
+        }
+        __syncthreads();  // the slot is refilled two chunks later
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int m0 = 16 * (warp + 8 * a);
+        if (m0 >= kTcNP) continue;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const bool live = m0 < 16 * MT;
+            *reinterpret_cast<float2*>(Zs + (m0 + g) * kTcBS + 8 * nt + 2 * t) = live ? make_float2(acc[a][nt][0], acc[a][nt][1]) : make_float2(0.f, 0.f);
+            *reinterpret_cast<float2*>(Zs + (m0 + g + 8) * kTcBS + 8 * nt + 2 * t) = live ? make_float2(acc[a][nt][2], acc[a][nt][3]) : make_float2(0.f, 0.f);
+        }
+    }
+    // ---------------- pass 2: Sigma[i][J] = sum_k P[k][i] Z[k][J] for the m-tiles on or below the diagonal block ----------------
+    const int mt0 = J0 >> 4;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[a][nt][e] = 0.f;
+    for (int c = 0; c < nch; ++c) {
+        const int gidx = nch + c;
+        if (c + 1 < nch) {
+            prefetch2(c + 1, (gidx + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();  // (also orders the Zs stores of pass 1 before their first use)
+        const float* A = Ch + (gidx & 1) * kTcChunkFloats;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            unsigned ah[2][4], al[2][4];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int mt = mt0 + warp + 8 * a;
+                const bool live = mt < MT;
+                const float* ap = A + (8 * ks + t) * kTcAS2 + 16 * mt + g;  // A[m][kk] = P[k0 + kk][m]
+                tf32_split(live ? ap[0] : 0.f, ah[a][0], al[a][0]);
+                tf32_split(live ? ap[8] : 0.f, ah[a][1], al[a][1]);
+                tf32_split(live ? ap[4 * kTcAS2] : 0.f, ah[a][2], al[a][2]);
+                tf32_split(live ? ap[4 * kTcAS2 + 8] : 0.f, ah[a][3], al[a][3]);
+            }
+            const float* bp = Zs + (32 * c + 8 * ks + t) * kTcBS + g;
+            unsigned bh[8][2], bl[8][2];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                tf32_split(bp[8 * nt], bh[nt][0], bl[nt][0]);
+                tf32_split(bp[4 * kTcBS + 8 * nt], bh[nt][1], bl[nt][1]);
+            }
+#pragma unroll
+            for (int term = 0; term < 3; ++term)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        if (mt0 + warp + 8 * a >= MT) continue;  // warp-uniform
+                        mma_tf32(acc[a][nt], term == 0 ? al[a] : ah[a], term == 1 ? bl[nt] : bh[nt]);
+                    }
+        }
+        __syncthreads();
+    }
+    // lower triangle + mirror image
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int mt = mt0 + warp + 8 * a;
+        if (mt >= MT) continue;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = 16 * mt + g + ((e & 2) ? 8 : 0), j = J0 + 8 * nt + 2 * t + (e & 1);
+                if (i < n && j <= i) {
+                    cov[(long long)i * n + j] = acc[a][nt][e];
+                    if (j < i) cov[(long long)j * n + i] = acc[a][nt][e];
+                }
+            }
+    }
+}
+
 cudaError_t launch_sandwich(const SigmaArgs& a, int n_env, cudaStream_t st) {
     if (a.n > kSigmaMaxN || (a.n & 3)) return cudaErrorInvalidValue;
     cudaError_t e;
@@ -1377,6 +1569,12 @@ cudaError_t launch_sandwich(const SigmaArgs& a, int n_env, cudaStream_t st) {
         e = ensure_smem_attr(sandwich_kernel<8>, bytes, conf8);
         if (e != cudaSuccess) return e;
         sandwich_kernel<8><<<dim3((a.n + 7) / 8, n_env), kSwThreads, bytes, st>>>(a.Qt, a.F, a.cov, a.n);
+    } else if (!(getenv("COVO_SANDWICH") && strncmp(getenv("COVO_SANDWICH"), "simt", 4) == 0)) {
+        // batches: the two products on the tensor cores (3xTF32), four CTAs per matrix
+        static size_t conftc[32] = {};
+        e = ensure_smem_attr(sandwich_tc_kernel, kTcSmemBytes, conftc);
+        if (e != cudaSuccess) return e;
+        sandwich_tc_kernel<<<dim3((a.n + kTcJW - 1) / kTcJW, n_env), kTcThreads, kTcSmemBytes, st>>>(a.Qt, a.F, a.cov, a.n);
     } else {
         const size_t bytes = sandwich_smem_bytes(a.n, 16);
         e = ensure_smem_attr(sandwich_kernel<16>, bytes, conf16);

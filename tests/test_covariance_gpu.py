@@ -114,6 +114,35 @@ def test_sigma_batched_envs():
         assert np.linalg.norm(S[e] - So) / np.linalg.norm(So) < 2e-5
 
 
+@pytest.mark.parametrize("H,E", [(50, 20), (8, 40), (3, 24), (9, 19)])
+@pytest.mark.parametrize("sandwich", ["tensor", "simt"])
+def test_sigma_large_batches_tensor_core_sandwich(monkeypatch, H, E, sandwich):
+    """Batches of more than 18 matrices form Sigma = Q F Q^T on the tensor cores (mma.sync TF32, operands split 3 x TF32: float32-grade
+    products); COVO_SANDWICH=simt keeps the FFMA kernel.  Both against the float64 eigen-decomposition, exactly symmetric, n = 200, 32,
+    the tiny 12 and the ragged 36."""
+    if sandwich == "simt":
+        monkeypatch.setenv("COVO_SANDWICH", "simt")
+    else:
+        monkeypatch.delenv("COVO_SANDWICH", raising=False)
+    rng = np.random.default_rng(11)
+    n = 4 * H
+    h = _handle(64, H, 300, n_env=E)
+    if H == 50:
+        p, ns, a_mean, _ = scenario("tracking_zigzag", seed=3, H=50, warm_steps=20)
+        R0 = o.get_hessian(ns, a_mean, p, dtype=np.float64)
+        R = np.stack([(R0 * (1.0 + 0.05 * e) + 0.3 * e * np.eye(n)).astype(np.float32) for e in range(E)])  # CoVO Hessians, scaled / shifted per env
+    else:
+        A = rng.standard_normal((E, n, n)).astype(np.float32)
+        R = A + A.transpose(0, 2, 1)
+    S = h.optimize_sigma(R)
+    assert (h.status() == 0).all()
+    for e in range(0, E, 3):
+        So = o.optimize_sigma(R[e].astype(np.float64), 0.5, np.float64)
+        assert np.linalg.norm(S[e] - So) / np.linalg.norm(So) < 2e-5, e
+        assert np.abs(S[e] - S[e].T).max() == 0.0
+    h.close()
+
+
 @pytest.mark.parametrize("nc", [1, 2, 4, 8])
 def test_sigma_cluster_widths_agree(nc, monkeypatch):
     """The tridiagonalisation spreads one matrix over 1, 2, 4 or 8 CTAs of a cluster (batched environments use the
