@@ -216,9 +216,13 @@ __global__ void __launch_bounds__(kAsmThreads) hess_assemble_kernel(const Hessia
 // over the SMs.
 // ---------------------------------------------------------------------------------------------
 constexpr int kFwThreads = 128;
-constexpr int kFwChains = 2;  // per CTA
+constexpr int kFwChains = 2;  // per CTA (single environments: every chain at single-warp latency on an SM of its own)
+// Batches of environments: 40 chains (20 warps) per CTA share one staged copy of the records -- 5 CTAs per environment instead of 100,
+// a twentieth of the staging traffic (3.3 MB per environment with 2 chains per CTA) and 60 resident warps per SM instead of 3.
+constexpr int kFwChainsBatch = 40, kFwThreadsBatch = 640;
 
-__global__ void __launch_bounds__(kFwThreads) hess_forward_kernel(const HessianArgs a) {
+template <int kFwChains, int kFwThreads>
+__global__ void __launch_bounds__(kFwThreads) hess_forward_kernel_t(const HessianArgs a) {
     extern __shared__ __align__(16) float fsm[];  // [H][kFwRec]
     const int env = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int H = a.H, n = 4 * H;
@@ -237,8 +241,8 @@ __global__ void __launch_bounds__(kFwThreads) hess_forward_kernel(const HessianA
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    if (tid >= 32) return;
-    const int id = id0 + (lane >> 4), r = lane & 15;  // chain, row of Phi owned by this lane (13..15: idle rows)
+    if (tid >= 16 * kFwChains) return;
+    const int id = id0 + (tid >> 4), r = lane & 15;  // chain, row of Phi owned by this lane (13..15: idle rows)
     if (id >= n) return;  // whole half-warps drop out together (n is even)
     const int I = id >> 2, c = id & 3;
     const unsigned hmask = 0xFFFFu << (lane & 16);
@@ -311,10 +315,17 @@ cudaError_t launch_hessian(const HessianArgs& a, int n_env, cudaStream_t st) {
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const size_t fsmem = (size_t)a.H * kFwRec * sizeof(float);
-    static size_t configured_fw[32] = {};
-    e = ensure_smem_attr(hess_forward_kernel, fsmem, configured_fw);
-    if (e != cudaSuccess) return e;
-    hess_forward_kernel<<<dim3((4 * a.H + kFwChains - 1) / kFwChains, n_env), kFwThreads, fsmem, st>>>(a);
+    static size_t configured_fw[32] = {}, configured_fwb[32] = {};
+    if (n_env > 18) {
+        e = ensure_smem_attr(hess_forward_kernel_t<kFwChainsBatch, kFwThreadsBatch>, fsmem, configured_fwb);
+        if (e != cudaSuccess) return e;
+        hess_forward_kernel_t<kFwChainsBatch, kFwThreadsBatch>
+            <<<dim3((4 * a.H + kFwChainsBatch - 1) / kFwChainsBatch, n_env), kFwThreadsBatch, fsmem, st>>>(a);
+    } else {
+        e = ensure_smem_attr(hess_forward_kernel_t<kFwChains, kFwThreads>, fsmem, configured_fw);
+        if (e != cudaSuccess) return e;
+        hess_forward_kernel_t<kFwChains, kFwThreads><<<dim3((4 * a.H + kFwChains - 1) / kFwChains, n_env), kFwThreads, fsmem, st>>>(a);
+    }
     return cudaGetLastError();
 }
 

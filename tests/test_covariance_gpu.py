@@ -40,6 +40,27 @@ def test_hessian_vs_forward_over_forward_oracle(H, task, warm, time):
     assert np.abs(Rs - Rso).max() < 2e-5 * max(1.0, np.abs(Rso).max())
 
 
+@pytest.mark.parametrize("H", [50, 8])
+def test_hessian_large_batch_equals_single_environments(H):
+    """Batches of more than 18 environments run the forward chains 40 to a CTA (one staged copy of the records per 40 chains) instead of
+    2: the same per-chain arithmetic, so every environment's Hessian must equal bit for bit what a single-environment handle delivers."""
+    E = 20
+    hs = _handle(64, H, 320)
+    hb = _handle(64, H, 320, n_env=E)
+    states, times, means, pos, vel = [], [], [], [], []
+    for e in range(E):
+        p, ns, a_mean, rng = scenario("tracking_zigzag", seed=100 + e, H=H, warm_steps=5 + e, zero_disturb=False)
+        states.append(o.state_to_vec24(ns)); times.append(ns.time); means.append(a_mean); pos.append(ns.pos_traj); vel.append(ns.vel_traj)
+    hb.set_reference(np.stack(pos), np.stack(vel))
+    Rb = hb.hessian(np.stack(states), times, np.stack(means), shift=True)
+    for e in (0, 7, 19):
+        hs.set_reference(pos[e][None], vel[e][None])
+        R1 = hs.hessian(states[e], [times[e]], means[e][None], shift=True)[0]
+        assert np.array_equal(R1, Rb[e]), e
+    hs.close()
+    hb.close()
+
+
 DENSE_TOL = 1e-5  # the dense path (float64 pole inverses since round 2) is held to the tolerance of E1-E3
 
 
