@@ -15,3 +15,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 COVO_GRAPH=0 ncu --set full --clock-control none --import-source on -s 24 -c 8 -o gpurun_out/${TAG}_step_full python tools/one_step.py > gpurun_out/${TAG}_one_step_under_ncu.log 2>&1
 # the tridiagonal path (E1-E3, the default of environment batches): 9 kernels per step
 COVO_GRAPH=0 COVO_SIGMA=tridiag ncu --set full --clock-control none --import-source on -s 27 -c 9 -o gpurun_out/${TAG}_step_full_tridiag python tools/one_step.py > gpurun_out/${TAG}_one_step_tridiag_under_ncu.log 2>&1
+# launch list of one batched step of BASELINE config 5 (512 environments behind one handle)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/${TAG}_envbatch_launches.csv python tools/bench_env_batch.py 512 3 > gpurun_out/${TAG}_envbatch_under_ncu.log 2>&1
