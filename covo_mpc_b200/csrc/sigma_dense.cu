@@ -1,6 +1,6 @@
 // optimize_sigma (controllers/covo.py:116-132) WITHOUT an eigen-decomposition ("D1-D3").  Default for single
-// environments since round 2 (COVO_SIGMA=tridiag selects the tridiagonal path E1-E3 of sigma.cu); tools/study_dense_sigma.py and
-// tools/studies/lanczos_k_needed.py are the numerical studies behind it.  The reference computes
+// environments since the end of round 2 (COVO_SIGMA=tridiag selects the tridiagonal path E1-E3 of sigma.cu, which batches use);
+// tools/studies/ holds the numerical studies behind it.  The reference computes
 //     Sigma = U diag(s) U^T,  s_k = exp(c/2) / sqrt(o_k),  o_k = lambda_k - lambda_min + 1e-2,  c = (4 n log sigma + sum log o_k) / n
 // which is  Sigma = exp(c/2) * A^(-1/2)  with  A = (R + R^T)/2 - lambda_min I + 1e-2 I  and  sum log o_k = log det A.
 // So only lambda_min, log det A and the matrix function A^(-1/2) are needed:
@@ -8,13 +8,16 @@
 //                               fifth warp per CTA follows the smallest Ritz value and its residual while the recurrence runs
 //                               (16 .. 64 steps; along closed loops 24 steps suffice for 56 % of the Hessians, 32 for 94 %, 48 for
 //                               all -- a fixed 24 left lambda_min off by up to 6e-2, i.e. A indefinite)
-//   D2  gjb_inverse_kernel      one 4-CTA cluster per pole: w_j (A + t_j I)^-1 by blocked Gauss-Jordan, one more for log det A.
-//                               x^(-1/2) ~ sum_j w_j / (x + t_j): Zolotarev's partial fractions on [1e-2, M], the ladder of E2
+//   D2  gjb_inverse_kernel_t    one 8-CTA cluster per pole: w_j (A + t_j I)^-1 by blocked Gauss-Jordan IN FLOAT64, one more for log det A.
+//                               x^(-1/2) ~ sum_j w_j / (x + t_j): Zolotarev's partial fractions on [1e-2, M], 13 poles (exact inverses
+//                               need no more: 2e-7), the interval ladder of E2
 //   D3  combine_kernel          Sigma = exp(c/2) * sum_j w_j (A + t_j I)^-1, written symmetric
-// Measured on B200 (n = 200): D1 ~2 us per Lanczos step + D2 72 us + D3 4 us against 281 us for E1 + E2 + E3.  Hardware facts that
-// shaped it (measured here): scalar float64 issues at ~16 lanes / clock / SM with ~60 cycles between dependent operations; FFMA2
-// issues once per 4 cycles per scheduler (64 FMA / clock / SM); a 4-byte st.async costs ~2 cycles of DSMEM message rate.
-// Accuracy (GPU tests, 300-step closed loop): Sigma within 1e-6 .. 3e-6 (relative Frobenius) of the float64 eigen-decomposition.
+// Measured on B200 (n = 200): D1 ~2.4 us per Lanczos step (55 .. 70 us) + D2 68 us + D3 7 us against 283 us for E1 + E2 + E3.  Hardware
+// facts that shaped it (tools/microbench): float64 FMA issues at 64 lanes / clock / SM with 9 cycles between dependent operations
+// (mma.sync f64: the same rate), st.async to a cluster peer arrives after ~250 cycles, a 1.8 KB bulk DSMEM copy after ~700.
+// Accuracy (GPU tests): Sigma within 1e-7 .. 2e-7 (relative Frobenius) of the float64 eigen-decomposition of the same float32
+// Hessian; float32 LAPACK eigh, the reference's arithmetic: 4e-7 .. 1e-5.
+
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
