@@ -176,9 +176,14 @@ __device__ __forceinline__ float gjb_rcp(float x) {
 // theta - residual (A stays positive definite), status 3, and the host moves the handle to the tridiagonal path.
 // ---------------------------------------------------------------------------------------------------------------------------
 constexpr int LC_CL = 8;            // CTAs
-constexpr int LC_T = 128;           // Lanczos threads per CTA: 32 rows x 4 column phases
+#ifndef COVO_LC_TPR
+#define COVO_LC_TPR 4
+#endif
+constexpr int LC_TPR = COVO_LC_TPR;  // threads per matrix row (column phases): 4, or 8 (-DCOVO_LC_TPR=8: half the matrix-vector chain per thread, twice the warps)
+constexpr int LC_T = 32 * LC_TPR;   // Lanczos threads per CTA: 32 row slots x LC_TPR column phases
+constexpr int LC_WPC = LC_T / 32;   // Lanczos warps per CTA
 constexpr int LC_TT = LC_T + 32;    // ... plus the checker warp
-constexpr int LC_KMAX = 56;         // columns per thread (n <= 224)
+constexpr int LC_KMAX = 224 / LC_TPR;  // columns per thread (n <= 224)
 constexpr int kLanczosMax = 64;     // most Lanczos steps
 constexpr int kLanczosFirstCheck = 16, kLanczosCheckEvery = 4;
 #ifndef COVO_LANCZOS_LAG
@@ -190,9 +195,9 @@ constexpr double kRitzTol2 = 9e-10;  // residual^2 below which the Ritz value co
 struct LcSmem {
     double v[2][224];                 // normalised Lanczos vector v_k (by step parity), all n entries, zero beyond n
     double u[2][224];                 // u = A v_k - beta_{k-1} v_{k-1}, gathered from all CTAs (by step parity)
-    double part[2][LC_CL * 4][2];     // (u.v_k, u.u) partial of every warp of the cluster
+    double part[2][LC_CL * LC_WPC][2];  // (u.v_k, u.u) partial of every warp of the cluster
     double al[kLanczosMax], be[kLanczosMax];  // T: diagonal, off-diagonal (be[k-1] couples step k to the next vector)
-    double red[4];
+    double red[LC_WPC];
     unsigned long long bar[2];
     // the checker's tables: 1 / beta_i, beta_{i-1} / beta_i, float32 copies, the eigenvector recurrence of the last evaluation
     double ib[kLanczosMax], cc[kLanczosMax], qv[kLanczosMax], bv[kLanczosMax];
@@ -230,7 +235,7 @@ struct LcRemote {
 };
 __device__ __forceinline__ LcRemote lc_remote(double* u, double* part, unsigned long long* bar, unsigned rank) { return LcRemote{u, part, bar, rank}; }
 __device__ __forceinline__ void lc_send(const LcRemote& r, int what, int parity, double v) {
-    double* dst = (what == 0) ? r.u + parity * 224 : r.part + parity * (LC_CL * 4 * 2) + (what - 1);
+    double* dst = (what == 0) ? r.u + parity * 224 : r.part + parity * (LC_CL * LC_WPC * 2) + (what - 1);
     emu_dsmem_st_signal64(dst, r.rank, v, r.bar + parity);
 }
 #else
@@ -245,7 +250,7 @@ __device__ __forceinline__ LcRemote lc_remote(double* u, double* part, unsigned 
     return r;
 }
 __device__ __forceinline__ void lc_send(const LcRemote& r, int what, int parity, double v) {
-    const unsigned dst = (what == 0) ? r.u + parity * 224 * 8 : r.part + parity * (LC_CL * 4 * 2 * 8) + (what - 1) * 8;
+    const unsigned dst = (what == 0) ? r.u + parity * 224 * 8 : r.part + parity * (LC_CL * LC_WPC * 2 * 8) + (what - 1) * 8;
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst), "l"(__double_as_longlong(v)),
                  "r"(r.bar + parity * 8)
                  : "memory");
@@ -556,11 +561,11 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
     } else {
         // ================================================ the recurrence ================================================
         const int R = (n + LC_CL - 1) / LC_CL;      // rows per CTA (25 at n = 200)
-        const int rl = tid >> 2, ph = tid & 3;      // local row, column phase
+        const int rl = tid / LC_TPR, ph = tid % LC_TPR;  // local row, column phase
         const int row = rank * R + rl;
         const bool has_row = rl < R && row < n;
         const bool leader = has_row && ph == 0;
-        const int kc = (n + 3) >> 2;                // columns per thread
+        const int kc = (n + LC_TPR - 1) / LC_TPR;   // columns per thread
         const float* Rg = a.R + (long long)env * n * n;
         float* Asym = a.Asym ? a.Asym + (long long)env * n * n : nullptr;
         // rows of (R + R^T)/2 (float32, controllers/covo.py:117) widened into registers
@@ -569,14 +574,14 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
             float xa[LC_KMAX], xb[LC_KMAX];  // all loads in flight before the first store (the compiler must assume Asym aliases R)
 #pragma unroll
             for (int k = 0; k < LC_KMAX; ++k) {
-                const int j = 4 * k + ph;
+                const int j = LC_TPR * k + ph;
                 const bool ok = has_row && j < n;
                 xa[k] = ok ? __ldg(Rg + (long long)row * n + j) : 0.f;
                 xb[k] = ok ? __ldg(Rg + (long long)j * n + row) : 0.f;
             }
 #pragma unroll
             for (int k = 0; k < LC_KMAX; ++k) {
-                const int j = 4 * k + ph;
+                const int j = LC_TPR * k + ph;
                 const float x = 0.5f * (xa[k] + xb[k]);
                 if (Asym && has_row && j < n) Asym[(long long)row * n + j] = x;
                 ar[k] = (double)x;
@@ -604,7 +609,7 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
         }
         gjb_cluster_sync();  // the start vector is in place here, the mbarriers are initialised everywhere: before the first read / send
         double vj = has_row ? sm.v[0][row] : 0.0, vprev = 0.0;  // row leaders keep v_k[row], v_{k-1}[row]
-        const int n_warps_total = LC_CL * 4;
+        const int n_warps_total = LC_CL * LC_WPC;
         const int tx_bytes = n * 8 + n_warps_total * 16;
         DENSE_STAMP(49);
         int kdone = 0;
@@ -612,7 +617,7 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
         LcRemote rem[LC_CL];  // where this thread's row entry / this warp's partial slot / the barrier live in every CTA of the cluster
 #pragma unroll
         for (int r = 0; r < LC_CL; ++r)
-            rem[r] = lc_remote(&sm.u[0][has_row ? row : 0], &sm.part[0][rank * 4 + warp][0], &sm.bar[0], (unsigned)r);
+            rem[r] = lc_remote(&sm.u[0][has_row ? row : 0], &sm.part[0][rank * LC_WPC + warp][0], &sm.bar[0], (unsigned)r);
         const bool pfl = a.prof && tid == 0 && rank == 0 && blockIdx.y == 0;
         long long pl[5] = {0, 0, 0, 0, 0}, tl0 = pfl ? clock64() : 0;  // phase clocks of the recurrence (registers; dumped once)
         for (int it = 0; it < k_max; ++it) {
@@ -625,16 +630,16 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
             for (int k = 0; k < LC_KMAX; k += 8) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
-                    if (k + e < kc) ac[e] = fma(ar[k + e], vv[4 * (k + e) + ph], ac[e]);
+                    if (k + e < LC_KMAX && k + e < kc) ac[e] = fma(ar[(k + e < LC_KMAX) ? k + e : 0], vv[LC_TPR * (k + e) + ph], ac[e]);
             }
             double y = ((ac[0] + ac[1]) + (ac[2] + ac[3])) + ((ac[4] + ac[5]) + (ac[6] + ac[7]));
-            y += __shfl_xor_sync(0xffffffffu, y, 1);
-            y += __shfl_xor_sync(0xffffffffu, y, 2);
+#pragma unroll
+            for (int o = 1; o < LC_TPR; o <<= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
             // u = y - beta_{k-1} v_{k-1} (row leaders); partials of u.v_k and u.u over the 8 rows of the warp
             const double u = leader ? y - beta_prev * vprev : 0.0;
             double pa = u * vj, pu = u * u;
 #pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
+            for (int o = LC_TPR; o < 32; o <<= 1) {
                 pa += __shfl_xor_sync(0xffffffffu, pa, o);
                 pu += __shfl_xor_sync(0xffffffffu, pu, o);
             }
@@ -691,6 +696,10 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
             // same butterfly
             double qa = (lane < n_warps_total) ? sm.part[pc][lane][0] : 0.0;
             double qu = (lane < n_warps_total) ? sm.part[pc][lane][1] : 0.0;
+            if (LC_CL * LC_WPC > 32) {  // (eight threads per row: 64 warps in the cluster, two partial pairs per lane)
+                qa += sm.part[pc][(lane + 32) % (LC_CL * LC_WPC)][0];
+                qu += sm.part[pc][(lane + 32) % (LC_CL * LC_WPC)][1];
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {  // the two sums interleaved: five levels of (shuffle + add) each
                 qa += __shfl_xor_sync(0xffffffffu, qa, o);
@@ -709,7 +718,9 @@ __global__ void __launch_bounds__(LC_TT, 1) lanczos_cluster_kernel(const DenseAr
                 ps = warp_sum_d(ps);
                 if (lane == 0) sm.red[warp] = ps;
                 lc_main_sync();
-                b2 = (sm.red[0] + sm.red[1]) + (sm.red[2] + sm.red[3]);
+                b2 = 0.0;
+#pragma unroll
+                for (int w = 0; w < LC_WPC; ++w) b2 += sm.red[w];
                 lc_main_sync();
             }
             // 1 / beta and beta without float64 sqrt / division (each a chain of ~15 dependent float64 operations at ~40 cycles): float32
