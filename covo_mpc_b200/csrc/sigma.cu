@@ -812,8 +812,9 @@ __global__ void __launch_bounds__(TT, 1) sigma_trifunc_kernel(const SigmaArgs a)
 // communication between warps at all.  The kernel depends only on E1, so the host runs it on a side stream next
 // to E2 and joins before the sandwich kernel: an explicit Q for free.
 // ---------------------------------------------------------------------------------------------
-constexpr int kQaccWarps = 4, kQaccChunk = 32;
+constexpr int kQaccWarpsSingle = 4, kQaccWarpsBatch = 8, kQaccChunk = 32;  // batches: 16 columns per CTA share one streamed copy of the reflectors
 
+template <int kQaccWarps>
 __global__ void __launch_bounds__(kQaccWarps * 32) qacc_kernel(const SigmaArgs a) {
     extern __shared__ __align__(16) float qsmf[];  // [2][kQaccChunk][n] reflector chunks (cp.async), then tau[256]
     const int n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, env = blockIdx.y;
@@ -1342,10 +1343,17 @@ cudaError_t launch_tridiag(const SigmaArgs& a, int n_env, cudaStream_t st) {
 cudaError_t launch_qacc(const SigmaArgs& a, int n_env, cudaStream_t st) {
     if (a.n > kSigmaMaxN || (a.n & 3)) return cudaErrorInvalidValue;
     const size_t smem = ((size_t)2 * kQaccChunk * a.n + 256) * sizeof(float);
-    static size_t conf[32] = {};
-    cudaError_t e = ensure_smem_attr(qacc_kernel, smem, conf);
-    if (e != cudaSuccess) return e;
-    qacc_kernel<<<dim3((a.n / 2 + kQaccWarps - 1) / kQaccWarps, n_env), kQaccWarps * 32, smem, st>>>(a);
+    static size_t conf[32] = {}, confb[32] = {};
+    cudaError_t e;
+    if (n_env > 18) {
+        e = ensure_smem_attr(qacc_kernel<kQaccWarpsBatch>, smem, confb);
+        if (e != cudaSuccess) return e;
+        qacc_kernel<kQaccWarpsBatch><<<dim3((a.n / 2 + kQaccWarpsBatch - 1) / kQaccWarpsBatch, n_env), kQaccWarpsBatch * 32, smem, st>>>(a);
+    } else {
+        e = ensure_smem_attr(qacc_kernel<kQaccWarpsSingle>, smem, conf);
+        if (e != cudaSuccess) return e;
+        qacc_kernel<kQaccWarpsSingle><<<dim3((a.n / 2 + kQaccWarpsSingle - 1) / kQaccWarpsSingle, n_env), kQaccWarpsSingle * 32, smem, st>>>(a);
+    }
     return cudaGetLastError();
 }
 
